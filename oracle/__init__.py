@@ -1,0 +1,204 @@
+"""TEST INFRASTRUCTURE — ctypes access to the CPU oracle (oracle/_build/liboracle.so) and to the
+reference's own ORBextractor.cc built against the OpenCV stand-in (oracle/_ref/ref_orb).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+package.  Nothing here is on the product path."""
+import ctypes as C
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    so = os.path.join(_HERE, '_build', 'liboracle.so')
+    if force or not os.path.exists(so):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_orb_create.restype = C.c_void_p
+        _LIB.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _LIB.orc_orb_destroy.argtypes = [C.c_void_p]
+        _LIB.orc_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _LIB.orc_orb_tables.argtypes = [C.c_void_p] * 5
+        _LIB.orc_orb_level_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _LIB.orc_orb_level_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _LIB.orc_orb_level_cand.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _LIB.orc_orb_level_kps.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ref_orb_path():
+    p = os.path.join(_HERE, '_ref', 'ref_orb')
+    return p if os.path.exists(p) else None
+
+
+# ---- primitives -------------------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def blur7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_blur7(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def blur5(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_blur5(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def sobel3(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dx = np.empty(src.shape, np.int16)
+    dy = np.empty(src.shape, np.int16)
+    lib().orc_sobel3(_p(src), src.shape[1], src.shape[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def fast9(img, thr):
+    """FAST-9/16 + NMS on a (possibly strided) 2-D uint8 view; returns int32 [n,3] = x, y, score."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = max(16, w * h // 4)
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast9(C.c_void_p(img.ctypes.data), w, h, img.strides[0], thr, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib().orc_fast_atan2(_p(y), _p(x), _p(out), y.size)
+    return out
+
+
+# ---- ORB --------------------------------------------------------------------------------------------
+class OrbOracle:
+    """CPU restatement of ORB_SLAM2::ORBextractor (reference src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.params = (nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.nlevels = nlevels
+        self.cap = nfeatures + 4 * nlevels + 64
+        self._h = lib().orc_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, '_h', None):
+            lib().orc_orb_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        sf = np.empty(self.nlevels, np.float32)
+        isf = np.empty(self.nlevels, np.float32)
+        nf = np.empty(self.nlevels, np.int32)
+        um = np.empty(16, np.int32)
+        lib().orc_orb_tables(self._h, _p(sf), _p(isf), _p(nf), _p(um))
+        return sf, isf, nf, um
+
+    def extract(self, gray):
+        assert gray.dtype == np.uint8 and gray.ndim == 2 and gray.strides[1] == 1
+        kps = np.empty(self.cap, KP_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n = lib().orc_orb_extract(self._h, C.c_void_p(gray.ctypes.data), gray.shape[1], gray.shape[0],
+                                  gray.strides[0], _p(kps), _p(desc), self.cap)
+        assert n <= self.cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        """Intermediates of the last extract(): dict(img, blurred|None, cand [n,3], kps)."""
+        info = np.empty(4, np.int32)
+        lib().orc_orb_level_info(self._h, l, _p(info))
+        w, h, nc, nk = (int(v) for v in info)
+        img = np.empty((h, w), np.uint8)
+        lib().orc_orb_level_image(self._h, l, _p(img), 0)
+        blurred = None
+        if nk:
+            blurred = np.empty((h, w), np.uint8)
+            lib().orc_orb_level_image(self._h, l, _p(blurred), 1)
+        cand = np.empty((nc, 3), np.float32)
+        if nc:
+            lib().orc_orb_level_cand(self._h, l, _p(cand))
+        kps = np.empty(nk, KP_DTYPE)
+        if nk:
+            lib().orc_orb_level_kps(self._h, l, _p(kps))
+        return dict(img=img, blurred=blurred, cand=cand, kps=kps)
+
+
+def distribute(cand, minX, maxX, minY, maxY, N):
+    cand = np.ascontiguousarray(cand, np.float32).reshape(-1, 3)
+    out = np.empty((len(cand) + 8, 3), np.float32)
+    n = lib().orc_orb_distribute(_p(cand), len(cand), minX, maxX, minY, maxY, N, _p(out))
+    return out[:n].copy()
+
+
+def orb_extract_batch(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, nthreads=1,
+                      want_output=False):
+    """Frame-parallel oracle run (CPU baseline). frames: [n,h,w] uint8."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    counts = np.zeros(n, np.int32)
+    cap = nfeatures + 4 * nlevels + 64
+    kps = np.empty((n, cap), KP_DTYPE) if want_output else None
+    desc = np.empty((n, cap, 32), np.uint8) if want_output else None
+    lib().orc_orb_extract_batch(C.c_int(nfeatures), C.c_float(scale_factor), C.c_int(nlevels), C.c_int(ini_th),
+                                C.c_int(min_th), _p(frames), C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(nthreads),
+                                _p(counts), _p(kps) if want_output else None, _p(desc) if want_output else None,
+                                C.c_int(cap))
+    if want_output:
+        return counts, kps, desc
+    return counts
+
+
+def ref_orb_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """Run the reference's own ORBextractor.cc (oracle/_ref/ref_orb) on [n,h,w] uint8 frames.
+    Returns a list of (kps, desc) or None when the binary is not available."""
+    exe = ref_orb_path()
+    if exe is None:
+        return None
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('<8i', 0x4f524231, w, h, n, nfeatures, nlevels, ini_th, min_th))
+            f.write(struct.pack('<f', scale_factor))
+            f.write(frames.tobytes())
+        subprocess.check_call([exe, fi, fo])
+        raw = open(fo, 'rb').read()
+    out, off = [], 0
+    for _ in range(n):
+        (k,) = struct.unpack_from('<i', raw, off)
+        off += 4
+        kps = np.frombuffer(raw, KP_DTYPE, k, off).copy()
+        off += 28 * k
+        desc = np.frombuffer(raw, np.uint8, 32 * k, off).reshape(k, 32).copy()
+        off += 32 * k
+        out.append((kps, desc))
+    return out

@@ -1,0 +1,204 @@
+// TEST INFRASTRUCTURE — minimal stand-in for the slice of the OpenCV C++ API that the reference's
+// src/ORBextractor.cc uses, so that file can be compiled UNMODIFIED from /root/reference into
+// oracle/_ref/ (OpenCV's C++ headers/libs are absent from this image).  The image primitives forward to
+// oracle/cvprims.hpp, which is pinned bit-exactly against cv2 4.13.0.  Not a general OpenCV replacement.
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../cvprims.hpp"
+
+typedef unsigned char uchar;
+#define CV_PI 3.1415926535897932384626433832795
+#define CV_8U 0
+#define CV_8UC1 0
+
+static inline int cvRound(double v) { return cvp::cv_round(v); }
+static inline int cvRound(float v) { return cvp::cv_round(v); }
+static inline int cvRound(int v) { return v; }
+static inline int cvFloor(double v) { return cvp::cv_floor(v); }
+static inline int cvFloor(float v) { return cvp::cv_floor(v); }
+static inline int cvCeil(double v) { return cvp::cv_ceil(v); }
+static inline int cvCeil(float v) { return cvp::cv_ceil(v); }
+
+namespace cv {
+
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+enum { INTER_LINEAR = 1 };
+
+template <typename T>
+struct Point_ {
+    T x, y;
+    Point_() : x(0), y(0) {}
+    Point_(T _x, T _y) : x(_x), y(_y) {}
+};
+template <typename T>
+static inline Point_<T>& operator*=(Point_<T>& a, float b) {
+    a.x = (T)(a.x * b);
+    a.y = (T)(a.y * b);
+    return a;
+}
+typedef Point_<int> Point2i;
+typedef Point_<int> Point;
+typedef Point_<float> Point2f;
+
+struct Size {
+    int width, height;
+    Size() : width(0), height(0) {}
+    Size(int w, int h) : width(w), height(h) {}
+};
+struct Rect {
+    int x, y, width, height;
+    Rect(int _x, int _y, int w, int h) : x(_x), y(_y), width(w), height(h) {}
+};
+
+struct KeyPoint {
+    Point2f pt;
+    float size, angle, response;
+    int octave, class_id;
+    KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+    KeyPoint(float x, float y, float _size, float _angle = -1, float _response = 0, int _octave = 0,
+             int _class_id = -1)
+        : pt(x, y), size(_size), angle(_angle), response(_response), octave(_octave), class_id(_class_id) {}
+};
+static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
+
+struct MatStep {
+    size_t v;
+    MatStep() : v(0) {}
+    operator size_t() const { return v; }
+};
+
+struct MatZerosExpr { int rows, cols, type; };
+
+class Mat {
+public:
+    int rows, cols;
+    uchar* data;
+    MatStep step;
+    Mat() : rows(0), cols(0), data(nullptr) {}
+    Mat(Size s, int type) : rows(0), cols(0), data(nullptr) { create(s.height, s.width, type); }
+    Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr) { create(r, c, type); }
+    // external (non-owning) buffer
+    Mat(int r, int c, int type, void* ext, size_t st) : rows(r), cols(c), data((uchar*)ext) {
+        (void)type;
+        step.v = st;
+    }
+    void create(int r, int c, int type) {
+        assert(type == CV_8UC1);
+        (void)type;
+        if (data && r == rows && c == cols) return;
+        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * c);
+        rows = r;
+        cols = c;
+        data = buf_->data();
+        step.v = (size_t)c;
+    }
+    void release() { buf_.reset(); rows = cols = 0; data = nullptr; step.v = 0; }
+    Mat& operator=(const MatZerosExpr& z) {
+        create(z.rows, z.cols, z.type);  // no-op for a view of matching size: zeros are written in place
+        for (int y = 0; y < rows; ++y) std::memset(data + (size_t)y * step.v, 0, (size_t)cols);
+        return *this;
+    }
+    static MatZerosExpr zeros(int r, int c, int type) { return MatZerosExpr{r, c, type}; }
+    Mat operator()(const Rect& r) const {
+        Mat m(*this);
+        m.data = data + (size_t)r.y * step.v + r.x;
+        m.rows = r.height;
+        m.cols = r.width;
+        return m;
+    }
+    Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
+    Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
+    Mat clone() const {
+        Mat m(rows, cols, CV_8UC1);
+        for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step.v, data + (size_t)y * step.v, (size_t)cols);
+        return m;
+    }
+    int type() const { return CV_8UC1; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    size_t step1() const { return step.v; }
+    template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step.v + x * sizeof(T)); }
+    template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step.v + x * sizeof(T)); }
+    uchar* ptr(int y = 0) { return data + (size_t)y * step.v; }
+    const uchar* ptr(int y = 0) const { return data + (size_t)y * step.v; }
+
+private:
+    std::shared_ptr<std::vector<uchar>> buf_;
+};
+
+class _InputArray {
+public:
+    _InputArray(const Mat& m) : m_(&m) {}
+    bool empty() const { return m_->empty(); }
+    Mat getMat() const { return *m_; }
+private:
+    const Mat* m_;
+};
+class _OutputArray {
+public:
+    _OutputArray(Mat& m) : m_(&m) {}
+    void create(int r, int c, int type) const { m_->create(r, c, type); }
+    void release() const { m_->release(); }
+    Mat getMat() const { return *m_; }
+private:
+    Mat* m_;
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
+
+static inline float fastAtan2(float y, float x) { return cvp::fast_atan2_deg(y, x); }
+
+static inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool nms) {
+    assert(nms);
+    (void)nms;
+    std::vector<cvp::FastKp> r;
+    cvp::fast9_nms(img.data, img.cols, img.rows, img.step.v, threshold, r);
+    kps.clear();
+    for (const cvp::FastKp& k : r) kps.push_back(KeyPoint((float)k.x, (float)k.y, 7.f, -1, (float)k.score));
+}
+
+static inline void resize(const Mat& src, Mat& dst, Size sz, double, double, int interp) {
+    assert(interp == INTER_LINEAR);
+    (void)interp;
+    dst.create(sz.height, sz.width, CV_8UC1);
+    cvp::resize_linear_u8(src.data, src.cols, src.rows, src.step.v, dst.data, dst.cols, dst.rows, dst.step.v);
+}
+
+static inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int type) {
+    assert((type & ~BORDER_ISOLATED) == BORDER_REFLECT_101);
+    (void)type;
+    dst.create(src.rows + top + bottom, src.cols + left + right, CV_8UC1);
+    // works in place when src is the interior ROI of dst: interior pixels map to themselves
+    for (int y = 0; y < dst.rows; ++y) {
+        const uchar* s = src.data + (size_t)cvp::reflect101(y - top, src.rows) * src.step.v;
+        uchar* d = dst.data + (size_t)y * dst.step.v;
+        for (int x = 0; x < dst.cols; ++x) {
+            if (y >= top && y < top + src.rows && x >= left && x < left + src.cols && d + x == s + (x - left)) continue;
+            d[x] = s[cvp::reflect101(x - left, src.cols)];
+        }
+    }
+}
+
+static inline void GaussianBlur(const Mat& src, Mat& dst, Size k, double sx, double sy, int border) {
+    assert(k.width == 7 && k.height == 7 && sx == 2 && sy == 2 && border == BORDER_REFLECT_101);
+    (void)k; (void)sx; (void)sy; (void)border;
+    Mat tmp(src.rows, src.cols, CV_8UC1);
+    cvp::gaussian_blur7_s2(src.data, src.cols, src.rows, src.step.v, tmp.data, tmp.step.v);
+    dst.create(src.rows, src.cols, CV_8UC1);
+    for (int y = 0; y < tmp.rows; ++y) std::memcpy(dst.data + (size_t)y * dst.step.v, tmp.data + (size_t)y * tmp.step.v, (size_t)tmp.cols);
+}
+
+struct KeyPointsFilter {
+    static void retainBest(std::vector<KeyPoint>&, int) {
+        std::fprintf(stderr, "cvshim: KeyPointsFilter::retainBest is only reached from dead code\n");
+        std::abort();
+    }
+};
+
+}  // namespace cv

@@ -1,0 +1,99 @@
+// TEST INFRASTRUCTURE — C entry points of the CPU oracle for ctypes (tests/, bench.py cpu_baseline only).
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "cvprims.hpp"
+#include "orb_oracle.hpp"
+
+extern "C" {
+
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) {
+    cvp::resize_linear_u8(src, sw, sh, sw, dst, dw, dh, dw);
+}
+void orc_blur7(const uint8_t* src, int w, int h, uint8_t* dst) { cvp::gaussian_blur7_s2(src, w, h, w, dst, w); }
+void orc_blur5(const uint8_t* src, int w, int h, uint8_t* dst) { cvp::gaussian_blur5_s1(src, w, h, w, dst, w); }
+void orc_sobel3(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy) { cvp::sobel3_s16(src, w, h, w, dx, dy); }
+int orc_fast9(const uint8_t* src, int w, int h, int stride, int thr, int32_t* out_xys, int cap) {
+    std::vector<cvp::FastKp> r;
+    cvp::fast9_nms(src, w, h, stride, thr, r);
+    int n = (int)r.size();
+    for (int i = 0; i < n && i < cap; ++i) { out_xys[3 * i] = r[i].x; out_xys[3 * i + 1] = r[i].y; out_xys[3 * i + 2] = r[i].score; }
+    return n;
+}
+void orc_fast_atan2(const float* y, const float* x, float* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = cvp::fast_atan2_deg(y[i], x[i]);
+}
+
+// ---- ORB --------------------------------------------------------------------------------------------
+void* orc_orb_create(int nfeatures, float scale, int nlevels, int ini_th, int min_th) {
+    orbo::Params p;
+    p.nfeatures = nfeatures; p.scale_factor = scale; p.nlevels = nlevels; p.ini_th = ini_th; p.min_th = min_th;
+    return new orbo::Extractor(p);
+}
+void orc_orb_destroy(void* h) { delete (orbo::Extractor*)h; }
+int orc_orb_extract(void* h, const uint8_t* gray, int w, int hh, int stride, orbo::KeyPoint* kps, uint8_t* desc, int cap) {
+    std::vector<orbo::KeyPoint> k;
+    std::vector<uint8_t> d;
+    ((orbo::Extractor*)h)->extract(gray, w, hh, (size_t)stride, k, d);
+    int n = (int)k.size();
+    int m = n < cap ? n : cap;
+    if (m) { std::memcpy(kps, k.data(), (size_t)m * sizeof(orbo::KeyPoint)); std::memcpy(desc, d.data(), (size_t)m * 32); }
+    return n;
+}
+void orc_orb_tables(void* h, float* sf, float* isf, int* nfeat, int* umax) {
+    orbo::Extractor* e = (orbo::Extractor*)h;
+    for (size_t i = 0; i < e->scale_factors().size(); ++i) { sf[i] = e->scale_factors()[i]; isf[i] = e->inv_scale_factors()[i]; nfeat[i] = e->features_per_level()[i]; }
+    for (int i = 0; i < 16; ++i) umax[i] = e->umax()[i];
+}
+void orc_orb_level_info(void* h, int l, int* out4) {
+    const orbo::Level& L = ((orbo::Extractor*)h)->levels()[l];
+    out4[0] = L.w; out4[1] = L.h; out4[2] = (int)L.cand.size(); out4[3] = (int)L.kps.size();
+}
+void orc_orb_level_image(void* h, int l, uint8_t* out, int blurred) {
+    const orbo::Level& L = ((orbo::Extractor*)h)->levels()[l];
+    const std::vector<uint8_t>& v = blurred ? L.blurred : L.img;
+    if (!v.empty()) std::memcpy(out, v.data(), v.size());
+}
+void orc_orb_level_cand(void* h, int l, float* out3) {
+    const orbo::Level& L = ((orbo::Extractor*)h)->levels()[l];
+    for (size_t i = 0; i < L.cand.size(); ++i) { out3[3 * i] = L.cand[i].x; out3[3 * i + 1] = L.cand[i].y; out3[3 * i + 2] = L.cand[i].response; }
+}
+void orc_orb_level_kps(void* h, int l, orbo::KeyPoint* out) {
+    const orbo::Level& L = ((orbo::Extractor*)h)->levels()[l];
+    if (!L.kps.empty()) std::memcpy(out, L.kps.data(), L.kps.size() * sizeof(orbo::KeyPoint));
+}
+int orc_orb_distribute(const float* cand3, int n, int minX, int maxX, int minY, int maxY, int N, float* out3) {
+    std::vector<orbo::Candidate> in(n);
+    for (int i = 0; i < n; ++i) in[i] = {cand3[3 * i], cand3[3 * i + 1], cand3[3 * i + 2]};
+    std::vector<orbo::Candidate> r = orbo::Extractor::distribute(in, minX, maxX, minY, maxY, N);
+    for (size_t i = 0; i < r.size(); ++i) { out3[3 * i] = r[i].x; out3[3 * i + 1] = r[i].y; out3[3 * i + 2] = r[i].response; }
+    return (int)r.size();
+}
+// Frame-parallel batch (CPU baseline): frames are independent, one Extractor per thread.
+// counts[f] = number of keypoints of frame f; kps/desc (may be null) hold cap slots per frame.
+void orc_orb_extract_batch(int nfeatures, float scale, int nlevels, int ini_th, int min_th, const uint8_t* frames,
+                           int nframes, int w, int h, int nthreads, int32_t* counts, orbo::KeyPoint* kps,
+                           uint8_t* desc, int cap) {
+    orbo::Params p;
+    p.nfeatures = nfeatures; p.scale_factor = scale; p.nlevels = nlevels; p.ini_th = ini_th; p.min_th = min_th;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() {
+            orbo::Extractor ex(p);
+            std::vector<orbo::KeyPoint> k;
+            std::vector<uint8_t> d;
+            for (int f = t; f < nframes; f += nthreads) {
+                ex.extract(frames + (size_t)f * w * h, w, h, (size_t)w, k, d);
+                counts[f] = (int32_t)k.size();
+                int m = (int)k.size() < cap ? (int)k.size() : cap;
+                if (kps && m) std::memcpy(kps + (size_t)f * cap, k.data(), (size_t)m * sizeof(orbo::KeyPoint));
+                if (desc && m) std::memcpy(desc + (size_t)f * cap * 32, d.data(), (size_t)m * 32);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+}  // extern "C"
