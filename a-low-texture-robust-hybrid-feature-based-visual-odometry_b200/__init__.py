@@ -1,0 +1,263 @@
+"""hvo-front: B200-native (sm_100a) feature front-end of the hybrid point/line/plane VO.
+
+This package is a thin ctypes binding over the C ABI in include/hvo_capi.h (libhvofront.so, hand-written
+CUDA).  The classes mirror the reference's C++ interfaces (names, argument meaning, error behaviour) so the
+parity tests read like calls into the reference:
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   reference include/ORBextractor.h:51
+    ORBextractor.__call__(image, mask) -> (keypoints, descriptors)        reference include/ORBextractor.h:59
+
+There is no CPU fallback: importing works without a GPU (so the ABI can be inspected), but every compute call
+raises HvoError when the CUDA library or device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libhvofront.so')
+
+HVO_OK, HVO_ERR_ARG, HVO_ERR_CUDA, HVO_ERR_STATE, HVO_ERR_OVERFLOW = 0, 1, 2, 3, 4
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+
+
+class HvoError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f'hvo status {status}: {msg}')
+        self.status = status
+
+
+class _OrbParams(C.Structure):
+    _fields_ = [('nfeatures', C.c_int), ('scale_factor', C.c_float), ('nlevels', C.c_int),
+                ('ini_th_fast', C.c_int), ('min_th_fast', C.c_int)]
+
+
+class _RgbdParams(C.Structure):
+    _fields_ = [('depth_factor', C.c_float), ('bf', C.c_float)]
+
+
+_lib = None
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/hvo_capi.h declares
+ABI = {
+    'hvo_last_error': (C.c_char_p, []),
+    'hvo_version': (C.c_char_p, []),
+    'hvo_device_count': (C.c_int, [C.POINTER(C.c_int)]),
+    'hvo_orb_create': (C.c_int, [C.POINTER(_OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_orb_destroy': (None, [_vp]),
+    'hvo_orb_capacity': (C.c_int, [_vp]),
+    'hvo_orb_get_tables': (C.c_int, [_vp] * 6),
+    'hvo_orb_extract': (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_orb_extract_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(_RgbdParams), _vp, _vp]),
+    'hvo_orb_extract_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(_RgbdParams), _vp, _vp]),
+    'hvo_orb_sync': (C.c_int, [_vp]),
+    'hvo_orb_timer_start': (C.c_int, [_vp]),
+    'hvo_orb_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_orb_set_profiling': (C.c_int, [_vp, C.c_int]),
+    'hvo_orb_stage_times': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_orb_last_launches': (C.c_int, [_vp]),
+    'hvo_orb_level_size': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'hvo_orb_get_pyramid_level': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t]),
+    'hvo_orb_get_candidates': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
+}
+
+
+def lib():
+    """Load libhvofront.so.  Fails loudly when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HvoError(HVO_ERR_STATE, f'{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a)')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(st):
+    if st != HVO_OK:
+        raise HvoError(st, lib().hvo_last_error().decode())
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().hvo_device_count(C.byref(n)))
+    return n.value
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:46-110).
+
+    Extra constructor arguments (image size, max_batch, device) size the device buffers; when omitted the
+    handle is created lazily from the first image, as the C++ shim does.
+    """
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width=None, height=None, max_batch=1,
+                 device=0):
+        self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(scaleFactor), int(nlevels)
+        self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)
+        self.max_batch, self.device = int(max_batch), int(device)
+        self._h = None
+        self._size = None
+        if width is not None and height is not None:
+            self._create(int(width), int(height))
+
+    # -- lifecycle ------------------------------------------------------------------------------------
+    def _create(self, w, h):
+        self.close()
+        p = _OrbParams(self.nfeatures, self.scaleFactor, self.nlevels, self.iniThFAST, self.minThFAST)
+        out = _vp()
+        _check(lib().hvo_orb_create(C.byref(p), w, h, self.max_batch, self.device, C.byref(out)))
+        self._h = out
+        self._size = (w, h)
+        self.capacity = lib().hvo_orb_capacity(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_orb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ensure(self, w, h):
+        if self._h is None or self._size != (w, h):
+            self._create(w, h)
+
+    # -- getters (ORBextractor.h:63-83) -----------------------------------------------------------------
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def _tables(self):
+        if self._h is None:
+            raise HvoError(HVO_ERR_STATE, 'extractor has no device handle yet (no image size known)')
+        n = self.nlevels
+        t = [np.empty(n, np.float32) for _ in range(4)] + [np.empty(n, np.int32)]
+        _check(lib().hvo_orb_get_tables(self._h, *[_np_ptr(a) for a in t]))
+        return t
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def GetFeaturesPerLevel(self):
+        return self._tables()[4]
+
+    # -- operator() ---------------------------------------------------------------------------------
+    def __call__(self, image, mask=None):
+        """(keypoints[KP_DTYPE], descriptors[n,32] uint8).  The mask is ignored (ORBextractor.h:57)."""
+        if image is None or image.size == 0:
+            return np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)  # silent return, .cc:1044-1045
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise HvoError(HVO_ERR_ARG, 'image must be 8-bit single channel (assert at ORBextractor.cc:1048)')
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        self._ensure(w, h)
+        kps = np.empty(self.capacity, KP_DTYPE)
+        desc = np.empty((self.capacity, 32), np.uint8)
+        n = C.c_int(0)
+        _check(lib().hvo_orb_extract(self._h, _vp(image.ctypes.data), image.strides[0], _np_ptr(kps), _np_ptr(desc),
+                                     self.capacity, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # -- batched host path ----------------------------------------------------------------------------
+    def extract_batch(self, frames, depth16=None, depth_factor=None, bf=None, out=None):
+        """frames [n,h,w] uint8 (host; pinned memory makes the copies asynchronous).  Returns
+        dict(counts, kps [n,cap], desc [n,cap,32], depth, uright)."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+        n, h, w = frames.shape
+        self._ensure(w, h)
+        cap = self.capacity
+        if out is None:
+            out = dict(counts=np.empty(n, np.int32), kps=np.empty((n, cap), KP_DTYPE), desc=np.empty((n, cap, 32), np.uint8))
+            if depth16 is not None:
+                out['depth'] = np.empty((n, cap), np.float32)
+                out['uright'] = np.empty((n, cap), np.float32)
+        rg = None
+        if depth16 is not None:
+            assert depth16.dtype == np.uint16 and depth16.shape == frames.shape and depth16.flags.c_contiguous
+            rg = C.byref(_RgbdParams(float(depth_factor), float(bf)))
+        _check(lib().hvo_orb_extract_batch(self._h, _np_ptr(frames), n, _np_ptr(out['kps']), _np_ptr(out['desc']),
+                                           _np_ptr(out['counts']), _np_ptr(depth16) if depth16 is not None else None, rg,
+                                           _np_ptr(out['depth']) if depth16 is not None else None,
+                                           _np_ptr(out['uright']) if depth16 is not None else None))
+        return out
+
+    # -- device-resident path (raw device pointers, e.g. torch tensor .data_ptr()) ---------------------
+    def extract_batch_device(self, d_gray, nframes, d_kps, d_desc, d_counts, d_depth16=None, depth_factor=0.0, bf=0.0,
+                             d_kp_depth=None, d_kp_uright=None):
+        rg = C.byref(_RgbdParams(float(depth_factor), float(bf))) if d_depth16 else None
+        _check(lib().hvo_orb_extract_batch_device(self._h, _vp(d_gray), nframes, _vp(d_kps), _vp(d_desc), _vp(d_counts),
+                                                  _vp(d_depth16) if d_depth16 else None, rg,
+                                                  _vp(d_kp_depth) if d_kp_depth else None,
+                                                  _vp(d_kp_uright) if d_kp_uright else None))
+
+    def sync(self):
+        _check(lib().hvo_orb_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_orb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_orb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on):
+        _check(lib().hvo_orb_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        _check(lib().hvo_orb_stage_times(self._h, ms))
+        return dict(zip(('pyramid', 'fast', 'octree', 'describe'), [float(v) for v in ms]))
+
+    def last_launches(self):
+        return lib().hvo_orb_last_launches(self._h)
+
+    # -- inspection -----------------------------------------------------------------------------------
+    def level_size(self, level):
+        w, h = C.c_int(0), C.c_int(0)
+        _check(lib().hvo_orb_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def pyramid_level(self, frame, level):
+        """mvImagePyramid[level] of frame `frame` of the last call (ORBextractor.h:85)."""
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(lib().hvo_orb_get_pyramid_level(self._h, frame, level, _np_ptr(out), w))
+        return out
+
+    def candidates(self, frame, level):
+        """Pre-quadtree FAST keypoints of a level (unordered): int32 [n,3] = x, y (level coords), score."""
+        w, h = self.level_size(level)
+        cap = max(16, (w * h) // 4)
+        out = np.empty((cap, 3), np.int32)
+        n = C.c_int(0)
+        _check(lib().hvo_orb_get_candidates(self._h, frame, level, _np_ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()

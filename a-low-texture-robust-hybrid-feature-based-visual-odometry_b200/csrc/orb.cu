@@ -1,0 +1,832 @@
+// ORB extractor kernels for sm_100a (B200).  From-scratch design, batched over frames:
+//
+//   k_resize      x(nlevels-1)  fixed-point bilinear pyramid, bit-exact with cv::resize INTER_LINEAR 8U
+//                               (reference ORBextractor.cc:1105-1130)
+//   k_fast_cells  x1            one CTA per reference FAST cell: FAST-9/16 strength, cell-local NMS,
+//                               per-cell threshold fallback (ORBextractor.cc:763-826) - no score map in HBM
+//   k_octree      x1            one CTA per (frame, level): DistributeOctTree (ORBextractor.cc:537-761)
+//                               with parallel key partitioning and the std::list order emulated exactly
+//   k_describe    x1            one warp per keypoint: IC_Angle (.cc:75-102), on-the-fly 7x7 Q8 Gaussian
+//                               of the 37x37 patch (.cc:1083-1084), steered rBRIEF-256 (.cc:106-144),
+//                               KeyPoint assembly (.cc:835-846,1093-1099), RGB-D depth lookup
+//                               (Frame.cc:1940-1961) - no blurred pyramid in HBM
+//
+// Float semantics are pinned with explicit round-to-nearest intrinsics (no FMA contraction) so that
+// angles, sample coordinates and scaled keypoint positions are bit-identical to the CPU oracle.
+#include "orb.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace hvo {
+
+// ------------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------------
+__constant__ int8_t c_pattern[1024] = {
+#include "../../include/hvo_orb_pattern.inc"
+};
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+static const int h_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+static const int kEdge = 19;
+static const int kMaxCell = 64;  // wCell = ceil(width / floor(width/30)) <= 60
+
+__device__ __forceinline__ const uint8_t* level_ptr(const OrbGeom& g, const ImgSrc& s, int l, int f, int& pitch) {
+    if (l == 0) {
+        pitch = s.l0_pitch;
+        return s.l0 + (long long)f * s.l0_frame;
+    }
+    pitch = g.lv[l].pitch;
+    return s.pyr + (long long)f * g.pyr_frame_bytes + g.lv[l].img_off;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1: bilinear resize, 4 output pixels per thread
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int spitch, long long sframe, int sw,
+                                                uint8_t* __restrict__ dst, int dpitch, long long dframe, int dw, int dh,
+                                                const int2* __restrict__ xtab, const int4* __restrict__ ytab) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= dw || y >= dh) return;
+    const int f = blockIdx.z;
+    const int4 yt = __ldg(&ytab[y]);
+    const uint8_t* S0 = src + (long long)f * sframe + (long long)yt.x * spitch;
+    const uint8_t* S1 = src + (long long)f * sframe + (long long)yt.y * spitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        if (x < dw) {
+            const int2 xt = __ldg(&xtab[x]);
+            const int sx = xt.x;
+            const int s1 = min(sx + 1, sw - 1);
+            const int w0 = (int)(short)(xt.y & 0xffff), w1 = xt.y >> 16;
+            const int r0 = S0[sx] * w0 + S0[s1] * w1;
+            const int r1 = S1[sx] * w0 + S1[s1] * w1;
+            int v = (((yt.z * (r0 >> 4)) >> 16) + ((yt.w * (r1 >> 4)) >> 16) + 2) >> 2;
+            v = min(255, max(0, v));
+            packed |= (uint32_t)v << (8 * i);
+        }
+    }
+    uint8_t* D = dst + (long long)f * dframe + (long long)y * dpitch + x0;
+    if (x0 + 3 < dw) {
+        *reinterpret_cast<uint32_t*>(D) = packed;  // dpitch and x0 are multiples of 4
+    } else {
+        for (int i = 0; x0 + i < dw; ++i) D[i] = (uint8_t)(packed >> (8 * i));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: FAST per cell
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_run9(uint32_t m16) {
+    uint32_t m = m16 | (m16 << 16);
+    uint32_t a = m & (m >> 1);
+    a &= a >> 2;
+    a &= a >> 4;
+    a &= m >> 8;
+    return (a & 0xffffu) != 0;
+}
+
+// Threshold-independent FAST-9/16 strength S = max(A, B) - 1 (see oracle/cvprims.hpp fast_strength):
+//   A = max over the 16 arcs of min(v - ring), B = max over arcs of min(ring - v).
+__device__ __forceinline__ int fast_strength(const int (&d)[16]) {
+    int lo2[16], hi2[16], lo4[16], hi4[16], lo8[16], hi8[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo2[i] = min(d[i], d[(i + 1) & 15]);
+        hi2[i] = max(d[i], d[(i + 1) & 15]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo4[i] = min(lo2[i], lo2[(i + 2) & 15]);
+        hi4[i] = max(hi2[i], hi2[(i + 2) & 15]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo8[i] = min(lo4[i], lo4[(i + 4) & 15]);
+        hi8[i] = max(hi4[i], hi4[(i + 4) & 15]);
+    }
+    int A = -256, B = -256;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        A = max(A, min(lo8[i], d[(i + 8) & 15]));
+        B = max(B, -max(hi8[i], d[(i + 8) & 15]));
+    }
+    return max(A, B) - 1;
+}
+
+#define HVO_RING(p, st, k)                                                                                   \
+    ((k) == 0 ? (p)[3 * (st)] : (k) == 1 ? (p)[3 * (st) + 1] : (k) == 2 ? (p)[2 * (st) + 2] : (k) == 3 ? (p)[(st) + 3] \
+     : (k) == 4 ? (p)[3] : (k) == 5 ? (p)[-(st) + 3] : (k) == 6 ? (p)[-2 * (st) + 2] : (k) == 7 ? (p)[-3 * (st) + 1]   \
+     : (k) == 8 ? (p)[-3 * (st)] : (k) == 9 ? (p)[-3 * (st) - 1] : (k) == 10 ? (p)[-2 * (st) - 2]                      \
+     : (k) == 11 ? (p)[-(st) - 3] : (k) == 12 ? (p)[-3] : (k) == 13 ? (p)[(st) - 3] : (k) == 14 ? (p)[2 * (st) - 2]    \
+                                                                                                : (p)[3 * (st) - 1])
+
+static const int kTileStride = kMaxCell + 8;  // 72
+
+__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbGeom g, ImgSrc src,
+                                                    const CellDesc* __restrict__ cells, uint32_t* __restrict__ cand,
+                                                    int* __restrict__ ncand, int ini_th, int min_th) {
+    __shared__ uint8_t tile[(kMaxCell + 6) * kTileStride];
+    __shared__ uint8_t score[kMaxCell * kMaxCell];
+    __shared__ uint16_t clist[kMaxCell * kMaxCell];
+    __shared__ int s_ncorner, s_nini, s_nmin, s_base, s_slot;
+
+    const CellDesc c = cells[blockIdx.x];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom& L = g.lv[c.level];
+    int pitch;
+    const uint8_t* img = level_ptr(g, src, c.level, f, pitch);
+    const int zw = c.zw, zh = c.zh, tw = zw + 6, th = zh + 6;
+    const int low_th = min(ini_th, min_th);
+
+    const uint8_t* org = img + (long long)(c.y0 - 3) * pitch + (c.x0 - 3);
+    for (int i = tid; i < tw * th; i += 256) {
+        const int ty = i / tw, tx = i - ty * tw;
+        tile[ty * kTileStride + tx] = __ldg(org + (long long)ty * pitch + tx);
+    }
+    for (int i = tid; i < zh * kMaxCell; i += 256) score[i] = 0;
+    if (tid == 0) { s_ncorner = 0; s_nini = 0; s_nmin = 0; s_slot = 0; }
+    __syncthreads();
+
+    // pass 1: which zone pixels are FAST corners at the lower threshold (bit test for a run of 9)
+    const int npx = zw * zh;
+    for (int i = tid; i < npx; i += 256) {
+        const int zy = i / zw, zx = i - zy * zw;
+        const uint8_t* p = &tile[(zy + 3) * kTileStride + zx + 3];
+        const int v = *p;
+        uint32_t bright = 0, dark = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int d = v - (int)HVO_RING(p, kTileStride, k);
+            bright |= (d > low_th ? 1u : 0u) << k;
+            dark |= (d < -low_th ? 1u : 0u) << k;
+        }
+        if (has_run9(bright) || has_run9(dark)) clist[atomicAdd(&s_ncorner, 1)] = (uint16_t)(zy * kMaxCell + zx);
+    }
+    __syncthreads();
+
+    // pass 2: exact strength, only for corners, densely packed over threads
+    const int ncorner = s_ncorner;
+    for (int i = tid; i < ncorner; i += 256) {
+        const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
+        const uint8_t* p = &tile[(zy + 3) * kTileStride + zx + 3];
+        const int v = *p;
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, kTileStride, k);
+        score[pos] = (uint8_t)fast_strength(d);  // in [low_th, 254]
+    }
+    __syncthreads();
+
+    // pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the zone counts as 0)
+    uint32_t f_ini = 0, f_min = 0;
+    for (int i = tid, it = 0; i < ncorner; i += 256, ++it) {
+        const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
+        const int s = score[pos];
+        bool is_max = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dx == 0 && dy == 0) continue;
+                const int yy = zy + dy, xx = zx + dx;
+                if (yy >= 0 && yy < zh && xx >= 0 && xx < zw) is_max = is_max && (s > (int)score[yy * kMaxCell + xx]);
+            }
+        if (is_max) {
+            if (s >= ini_th) f_ini |= 1u << it;
+            if (s >= min_th) f_min |= 1u << it;
+        }
+    }
+    if (f_ini) atomicAdd(&s_nini, __popc(f_ini));
+    if (f_min) atomicAdd(&s_nmin, __popc(f_min));
+    __syncthreads();
+    const bool use_ini = s_nini > 0;
+    const int n = use_ini ? s_nini : s_nmin;
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(&ncand[f * g.nlevels + c.level], n);
+    __syncthreads();
+    uint32_t m = use_ini ? f_ini : f_min;
+    uint32_t* out = cand + (long long)f * g.cand_total + L.cand_off + s_base;
+    while (m) {
+        const int it = __ffs(m) - 1;
+        m &= m - 1;
+        const int pos = clist[tid + 256 * it];
+        const int zy = pos / kMaxCell, zx = pos % kMaxCell;
+        const int slot = atomicAdd(&s_slot, 1);
+        if (s_base + slot < L.cand_cap)
+            out[slot] = (uint32_t)(c.x0 + zx) | ((uint32_t)(c.y0 + zy) << 12) | ((uint32_t)score[pos] << 24);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: quadtree distribution, one CTA per (frame, level)
+// ------------------------------------------------------------------------------------------------------
+// The reference keeps a std::list of nodes; children are pushed to the FRONT in the order TL,TR,BL,BR and the
+// parent is erased.  Here the list is an array in list order (front = index 0).  Per round:
+//   * all threads histogram the keys of every splittable node into its 4 quadrants (shared atomics),
+//   * thread 0 replays the list bookkeeping (<= quota+3 live nodes) and lays out the next list,
+//   * all threads move their keys to the new node positions.
+// Phase 2 ("expand the biggest first", ORBextractor.cc:671-735) sorts the splittable nodes by
+// (key count, creation order) with a parallel rank sort; ties: later created node first (the oracle's
+// documented stand-in for the reference's pointer comparison).
+struct OctShared {
+    int M, mode, nE, cur;
+};
+enum { OCT_PHASE1 = 0, OCT_PHASE2 = 1, OCT_DONE = 2 };
+enum { NODE_LEAF = 1 };
+
+__device__ __forceinline__ int oct_quadrant(int kx, int ky, const short* r) {
+    const int hx = (r[2] - r[0] + 1) >> 1, hy = (r[3] - r[1] + 1) >> 1;  // ceil(w/2), ceil(h/2)
+    return (kx < r[0] + hx ? 0 : 1) + (ky < r[1] + hy ? 0 : 2);
+}
+__device__ __forceinline__ void oct_child_rect(const short* r, int q, short* o) {
+    const int hx = (r[2] - r[0] + 1) >> 1, hy = (r[3] - r[1] + 1) >> 1;
+    o[0] = (q & 1) ? r[0] + hx : r[0];
+    o[2] = (q & 1) ? r[2] : r[0] + hx;
+    o[1] = (q & 2) ? r[1] + hy : r[1];
+    o[3] = (q & 2) ? r[3] : r[1] + hy;
+}
+
+__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom g, const uint32_t* __restrict__ cand_all,
+                                                const int* __restrict__ ncand, uint16_t* __restrict__ knode_all,
+                                                uint32_t* __restrict__ okp_all, int* __restrict__ on, int cap_nodes,
+                                                int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char oct_smem[];
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    const LevelGeom& L = g.lv[l];
+    const int N = L.quota;
+    int n = ncand[f * g.nlevels + l];
+    if (n > L.cand_cap) n = L.cand_cap;
+    if (n == 0 || L.nIni < 1 || L.nIni > cap_nodes) {
+        if (tid == 0) on[f * g.nlevels + l] = 0;
+        return;
+    }
+    const uint32_t* cand = cand_all + (long long)f * g.cand_total + L.cand_off;
+    uint16_t* knode = knode_all + (long long)f * g.cand_total + L.cand_off;
+    uint32_t* okp = okp_all + (long long)f * g.kp_total + L.kp_off;
+
+    // shared layout (cap_nodes = quota + 8 entries each)
+    const int CN = cap_nodes;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(oct_smem);  // [CN]
+    int* cnt4 = reinterpret_cast<int*>(best + CN);                                // [CN][4]
+    int* size0 = cnt4 + 4 * CN;                                                   // [2][CN]
+    int* e_size = size0 + 2 * CN;                                                 // [CN]
+    int* e_pos = e_size + CN;                                                     // [CN]
+    int* e_sorted = e_pos + CN;                                                   // [CN]
+    short* rect0 = reinterpret_cast<short*>(e_sorted + CN);                       // [2][CN][4]
+    short* childpos = rect0 + 2 * CN * 4;                                         // [CN][4]
+    short* newpos = childpos + CN * 4;                                            // [CN]
+    unsigned char* flags0 = reinterpret_cast<unsigned char*>(newpos + CN);        // [2][CN]
+    unsigned char* divided = flags0 + 2 * CN;                                     // [CN]
+    __shared__ OctShared S;
+
+    // ---- roots (ORBextractor.cc:541-589) ----
+    if (tid == 0) { S.cur = 0; S.M = L.nIni; S.mode = OCT_PHASE1; S.nE = 0; }
+    for (int i = tid; i < L.nIni; i += nt) {
+        short* r = rect0 + i * 4;
+        r[0] = (short)(int)__fmul_rn(L.hX, (float)i);
+        r[2] = (short)(int)__fmul_rn(L.hX, (float)(i + 1));
+        r[1] = 0;
+        r[3] = (short)(L.maxBY - L.minBY);
+        size0[i] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const uint32_t c = cand[k];
+        const int kx = (int)(c & 0xfff) - L.minBX;
+        int r = (int)__fdiv_rn((float)kx, L.hX);
+        r = min(r, L.nIni - 1);
+        knode[k] = (uint16_t)r;
+        atomicAdd(&size0[r], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int pos = 0;
+        for (int r = 0; r < L.nIni; ++r) {
+            if (size0[r] == 0) { newpos[r] = -1; continue; }
+            newpos[r] = (short)pos;
+            for (int j = 0; j < 4; ++j) rect0[(CN + pos) * 4 + j] = rect0[r * 4 + j];
+            size0[CN + pos] = size0[r];
+            flags0[CN + pos] = size0[r] == 1 ? NODE_LEAF : 0;
+            ++pos;
+        }
+        S.M = pos;
+        S.cur = 1;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) knode[k] = (uint16_t)newpos[knode[k]];
+    __syncthreads();
+
+    // ---- rounds ----
+    while (S.mode != OCT_DONE) {
+        const int cur = S.cur, M = S.M, mode = S.mode, nE = S.nE;
+        short* rect = rect0 + cur * CN * 4;
+        short* nrect = rect0 + (cur ^ 1) * CN * 4;
+        int* size = size0 + cur * CN;
+        int* nsize = size0 + (cur ^ 1) * CN;
+        unsigned char* flags = flags0 + cur * CN;
+        unsigned char* nflags = flags0 + (cur ^ 1) * CN;
+
+        for (int i = tid; i < 4 * M; i += nt) cnt4[i] = 0;
+        for (int i = tid; i < M; i += nt) divided[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) {
+            const int p = knode[k] & 0x3fff;
+            if (!(flags[p] & NODE_LEAF)) {
+                const uint32_t c = cand[k];
+                const int q = oct_quadrant((int)(c & 0xfff) - L.minBX, (int)((c >> 12) & 0xfff) - L.minBY, rect + p * 4);
+                atomicAdd(&cnt4[p * 4 + q], 1);
+                knode[k] = (uint16_t)(p | (q << 14));
+            }
+        }
+        if (mode == OCT_PHASE2) {
+            // rank sort of the splittable nodes by (size, creation order) ascending
+            for (int e = tid; e < nE; e += nt) {
+                const int se = e_size[e];
+                int rank = 0;
+                for (int j = 0; j < nE; ++j) {
+                    const int sj = e_size[j];
+                    rank += (sj < se || (sj == se && j < e)) ? 1 : 0;
+                }
+                e_sorted[rank] = e;
+            }
+        }
+        __syncthreads();
+
+        if (tid == 0) {
+            int C = 0, newM, nExp = 0, newE = 0;
+            if (mode == OCT_PHASE1) {
+                // every non-leaf node splits, in list order
+                int nLeaf = 0;
+                for (int p = 0; p < M; ++p) {
+                    if (flags[p] & NODE_LEAF) { newpos[p] = (short)nLeaf++; continue; }
+                    divided[p] = 1;
+                    for (int q = 0; q < 4; ++q)
+                        if (cnt4[p * 4 + q] > 0) childpos[p * 4 + q] = (short)C++;
+                }
+                newM = C + nLeaf;
+                for (int p = 0; p < M; ++p) {
+                    if (flags[p] & NODE_LEAF) {
+                        const int dst = C + newpos[p];
+                        newpos[p] = (short)dst;
+                        for (int j = 0; j < 4; ++j) nrect[dst * 4 + j] = rect[p * 4 + j];
+                        nsize[dst] = size[p];
+                        nflags[dst] = NODE_LEAF;
+                    } else {
+                        for (int q = 0; q < 4; ++q) {
+                            const int cnt = cnt4[p * 4 + q];
+                            if (cnt == 0) continue;
+                            const int dst = C - 1 - childpos[p * 4 + q];
+                            childpos[p * 4 + q] = (short)dst;
+                            oct_child_rect(rect + p * 4, q, nrect + dst * 4);
+                            nsize[dst] = cnt;
+                            nflags[dst] = cnt == 1 ? NODE_LEAF : 0;
+                            if (cnt > 1) { ++nExp; e_size[newE] = cnt; e_pos[newE] = dst; ++newE; }
+                        }
+                    }
+                }
+                if (newM >= N || newM == M) S.mode = OCT_DONE;
+                else if (newM + 3 * nExp > N) S.mode = OCT_PHASE2;
+            } else {
+                // split the biggest splittable nodes first until the list holds >= N nodes
+                int count = M, jstop = nE;  // nodes e_sorted[jstop..nE) get split
+                for (int j = nE - 1; j >= 0; --j) {
+                    const int p = e_pos[e_sorted[j]];
+                    int nchild = 0;
+                    for (int q = 0; q < 4; ++q)
+                        if (cnt4[p * 4 + q] > 0) { childpos[p * 4 + q] = (short)C++; ++nchild; }
+                    divided[p] = 1;
+                    count += nchild - 1;
+                    jstop = j;
+                    if (count >= N) break;
+                }
+                newM = count;
+                int pos = C;
+                for (int p = 0; p < M; ++p) {
+                    if (divided[p]) continue;
+                    newpos[p] = (short)pos;
+                    for (int j = 0; j < 4; ++j) nrect[pos * 4 + j] = rect[p * 4 + j];
+                    nsize[pos] = size[p];
+                    nflags[pos] = flags[p];
+                    ++pos;
+                }
+                for (int j = nE - 1; j >= jstop; --j) {
+                    const int p = e_pos[e_sorted[j]];
+                    for (int q = 0; q < 4; ++q) {
+                        const int cnt = cnt4[p * 4 + q];
+                        if (cnt == 0) continue;
+                        const int dst = C - 1 - childpos[p * 4 + q];
+                        childpos[p * 4 + q] = (short)dst;
+                        oct_child_rect(rect + p * 4, q, nrect + dst * 4);
+                        nsize[dst] = cnt;
+                        nflags[dst] = cnt == 1 ? NODE_LEAF : 0;
+                    }
+                }
+                // new splittable list in creation order (= dst descending from C-1 to 0); e_* are free to overwrite now
+                for (int dst = C - 1; dst >= 0; --dst)
+                    if (!(nflags[dst] & NODE_LEAF)) { e_size[newE] = nsize[dst]; e_pos[newE] = dst; ++newE; }
+                if (newM >= N || newM == M) S.mode = OCT_DONE;
+            }
+            S.M = newM;
+            S.nE = newE;
+            S.cur = cur ^ 1;
+        }
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) {
+            const int kn = knode[k], p = kn & 0x3fff, q = kn >> 14;
+            knode[k] = (uint16_t)(divided[p] ? childpos[p * 4 + q] : newpos[p]);
+        }
+        __syncthreads();
+    }
+
+    // ---- best key per node: max response, ties -> earliest in the reference's candidate order ----
+    const int M = S.M;
+    for (int i = tid; i < M; i += nt) best[i] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const uint32_t c = cand[k];
+        const int x = c & 0xfff, y = (c >> 12) & 0xfff, s = c >> 24;
+        const int ci = (y - L.minBY - 3) / L.hCell, cj = (x - L.minBX - 3) / L.wCell;
+        const unsigned long long order = ((unsigned long long)(ci * L.nCols + cj) << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+        const unsigned long long key = ((unsigned long long)s << 48) | (0xffffffffffffull - order);
+        atomicMax(&best[knode[k] & 0x3fff], key);
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const uint32_t c = cand[k];
+        const int x = c & 0xfff, y = (c >> 12) & 0xfff, s = c >> 24;
+        const int ci = (y - L.minBY - 3) / L.hCell, cj = (x - L.minBX - 3) / L.wCell;
+        const unsigned long long order = ((unsigned long long)(ci * L.nCols + cj) << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+        const unsigned long long key = ((unsigned long long)s << 48) | (0xffffffffffffull - order);
+        const int p = knode[k] & 0x3fff;
+        if (best[p] == key && p < L.kp_cap) okp[p] = c;
+    }
+    if (tid == 0) {
+        on[f * g.nlevels + l] = min(M, L.kp_cap);
+        if (M > L.kp_cap) atomicExch(err, HVO_ERR_OVERFLOW);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: orientation + on-the-fly blur + rBRIEF + output assembly, one warp per keypoint
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = 57.295779513082320876798154814105f;  // (float)(180 / CV_PI)
+    const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale),
+                p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = (float)DBL_EPSILON;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+static const int kPR = 21;             // patch radius: 18 (max |rBRIEF sample offset|) + 3 (blur)
+static const int kPW = 2 * kPR + 1;    // 43
+static const int kRawStride = 44;
+static const int kBW = 37;             // blurred window 37x37
+static const int kHbStride = 38;
+static const int kBlStride = 40;
+static const int kDescWarps = 4;
+
+__global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_constant__ OrbGeom g, ImgSrc src,
+                                                              const uint32_t* __restrict__ okp_all,
+                                                              const int* __restrict__ on, hvo_keypoint* __restrict__ kps,
+                                                              uint8_t* __restrict__ desc, int32_t* __restrict__ counts,
+                                                              const uint16_t* __restrict__ depth16, float depth_factor,
+                                                              float bf, float* __restrict__ kp_depth,
+                                                              float* __restrict__ kp_uright) {
+    __shared__ uint8_t s_raw[kDescWarps][kPW * kRawStride];
+    __shared__ uint16_t s_hb[kDescWarps][kPW * kHbStride];
+    __shared__ uint8_t s_bl[kDescWarps][kBW * kBlStride];
+    __shared__ int8_t s_pat[1024];
+    const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
+    __syncthreads();
+
+    // locate keypoint gi (level-major) of frame f
+    const int gi = blockIdx.x * kDescWarps + warp;
+    int total = 0, lvl = -1, idx = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const int nl = on[f * g.nlevels + l];
+        if (lvl < 0 && gi < total + nl) { lvl = l; idx = gi - total; }
+        total += nl;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[f] = min(total, g.out_cap);
+    if (lvl < 0 || gi >= g.out_cap) return;
+
+    const LevelGeom& L = g.lv[lvl];
+    const uint32_t c = okp_all[(long long)f * g.kp_total + L.kp_off + idx];
+    const int cx = c & 0xfff, cy = (c >> 12) & 0xfff, resp = c >> 24;
+    int pitch;
+    const uint8_t* img = level_ptr(g, src, lvl, f, pitch);
+    uint8_t* raw = s_raw[warp];
+    uint16_t* hb = s_hb[warp];
+    uint8_t* bl = s_bl[warp];
+
+    // raw 43x43 patch, BORDER_REFLECT_101 at the level edges
+    for (int r = 0; r < kPW; ++r) {
+        const int yy = reflect101(cy - kPR + r, L.h);
+        const uint8_t* row = img + (long long)yy * pitch;
+        for (int cc = lane; cc < kPW; cc += 32) raw[r * kRawStride + cc] = __ldg(row + reflect101(cx - kPR + cc, L.w));
+    }
+    __syncwarp();
+
+    // IC_Angle: lane <-> column u = lane - 15
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - 15, au = abs(u);
+        for (int v = -15; v <= 15; ++v) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = raw[(kPR + v) * kRawStride + kPR + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // separable 7x7 sigma-2 Gaussian in Q8 (kernel 18,34,48,56,48,34,18), rows 0..42 x cols 3..39 then rows 3..39
+    for (int i = lane; i < kPW * kBW; i += 32) {
+        const int r = i / kBW, cc = i - r * kBW;
+        const uint8_t* p = raw + r * kRawStride + cc;
+        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+        hb[r * kHbStride + cc] = (uint16_t)acc;
+    }
+    __syncwarp();
+    for (int i = lane; i < kBW * kBW; i += 32) {
+        const int r = i / kBW, cc = i - r * kBW;
+        const uint16_t* p = hb + r * kHbStride + cc;
+        const uint32_t acc = 18u * (p[0] + p[6 * kHbStride]) + 34u * (p[kHbStride] + p[5 * kHbStride]) +
+                             48u * (p[2 * kHbStride] + p[4 * kHbStride]) + 56u * p[3 * kHbStride];
+        bl[r * kBlStride + cc] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncwarp();
+
+    // steered rBRIEF: lane i -> descriptor byte i
+    const float factorPI = 0.017453292519943295769236907684886f;  // (float)(CV_PI / 180.f)
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* ctr = bl + 18 * kBlStride + 18;
+    const int8_t* pt = s_pat + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float ax = pt[4 * t], ay = pt[4 * t + 1], bx = pt[4 * t + 2], by = pt[4 * t + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(ax, b), __fmul_rn(ay, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(ax, a), __fmul_rn(ay, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(bx, b), __fmul_rn(by, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(bx, a), __fmul_rn(by, b)));
+        const int t0 = ctr[r0 * kBlStride + c0], t1 = ctr[r1 * kBlStride + c1];
+        val |= (t0 < t1 ? 1 : 0) << t;
+    }
+    const long long o = (long long)f * g.out_cap + gi;
+    desc[o * 32 + lane] = (uint8_t)val;
+
+    if (lane == 0) {
+        float x = (float)cx, y = (float)cy;
+        if (lvl != 0) { x = __fmul_rn(x, L.scale); y = __fmul_rn(y, L.scale); }
+        hvo_keypoint k;
+        k.x = x; k.y = y; k.size = L.kp_size; k.angle = angle; k.response = (float)resp; k.octave = lvl; k.class_id = -1;
+        kps[o] = k;
+        if (depth16 != nullptr) {
+            const int u = min((int)x, g.width - 1), v = min((int)y, g.height - 1);
+            const float d = __fmul_rn((float)depth16[((long long)f * g.height + v) * g.width + u], depth_factor);
+            const bool ok = d > 0.f && d < 7.0f;
+            kp_depth[o] = ok ? d : -1.f;
+            kp_uright[o] = ok ? __fsub_rn(x, __fdiv_rn(bf, d)) : -1.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+static short sat_short_round(float v) {
+    int i = (int)lrintf(v);
+    return (short)std::min(32767, std::max(-32768, i));
+}
+
+}  // namespace hvo
+
+using namespace hvo;
+
+int hvo_orb::init() {
+    const int n = p.nlevels;
+    // ---- scale tables and per-level quotas (ORBextractor.cc:408-444) ----
+    const double sfd = (double)p.scale_factor;
+    sf.assign(n, 1.f); isf.assign(n, 1.f); sigma2.assign(n, 1.f); isigma2.assign(n, 1.f);
+    for (int i = 1; i < n; ++i) {
+        sf[i] = (float)((double)sf[i - 1] * sfd);
+        sigma2[i] = sf[i] * sf[i];
+    }
+    for (int i = 0; i < n; ++i) { isf[i] = 1.0f / sf[i]; isigma2[i] = 1.0f / sigma2[i]; }
+    nfeat.assign(n, 0);
+    {
+        const float factor = (float)(1.0 / sfd);
+        float want = (float)p.nfeatures * (1.f - factor) / (1.f - (float)std::pow((double)factor, (double)n));
+        int sum = 0;
+        for (int l = 0; l < n - 1; ++l) {
+            nfeat[l] = cv_round_f(want);
+            sum += nfeat[l];
+            want *= factor;
+        }
+        nfeat[n - 1] = std::max(p.nfeatures - sum, 0);
+    }
+    umax.assign(h_umax, h_umax + 16);
+
+    // ---- level geometry ----
+    std::memset(&g, 0, sizeof(g));
+    g.nlevels = n; g.width = width; g.height = height;
+    long long off = 0;
+    int cand_off = 0, kp_off = 0;
+    std::vector<CellDesc> cells;
+    max_zw = max_zh = max_quota = 0;
+    for (int l = 0; l < n; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.w = cv_round_f((float)width * isf[l]);
+        L.h = cv_round_f((float)height * isf[l]);
+        if (L.w > 4095 || L.h > 4095) { set_error("image too large (max 4095 px per side)"); return HVO_ERR_ARG; }
+        if (l == 0) { L.pitch = width; L.img_off = 0; }
+        else { L.pitch = (int)align_up((size_t)L.w, 128); L.img_off = off; off += (long long)L.pitch * L.h; }
+        L.minBX = kEdge - 3; L.minBY = kEdge - 3; L.maxBX = L.w - kEdge + 3; L.maxBY = L.h - kEdge + 3;
+        L.quota = nfeat[l];
+        L.scale = sf[l];
+        L.kp_size = (float)(int)(31 * sf[l]);
+        const float fw = (float)(L.maxBX - L.minBX), fh = (float)(L.maxBY - L.minBY);
+        L.nCols = (int)(fw / 30.f); L.nRows = (int)(fh / 30.f);
+        L.cand_off = cand_off; L.cand_cap = 0;
+        L.kp_off = kp_off; L.kp_cap = L.quota + 4;
+        kp_off += L.kp_cap;
+        max_quota = std::max(max_quota, L.quota);
+        if (L.nCols < 1 || L.nRows < 1 || L.maxBX <= L.minBX || L.maxBY <= L.minBY) {
+            // level too small for a single 30-px cell: the reference divides by zero here; produce no keypoints
+            L.nCols = L.nRows = 0; L.wCell = L.hCell = 1; L.nIni = 0; L.hX = 1.f;
+            continue;
+        }
+        L.wCell = (int)std::ceil(fw / L.nCols); L.hCell = (int)std::ceil(fh / L.nRows);
+        L.nIni = (int)std::round((float)(L.maxBX - L.minBX) / (L.maxBY - L.minBY));
+        L.hX = L.nIni > 0 ? (float)(L.maxBX - L.minBX) / L.nIni : 1.f;
+        for (int i = 0; i < L.nRows; ++i) {
+            const float iniY = (float)(L.minBY + i * L.hCell);
+            float maxY = iniY + L.hCell + 6;
+            if (iniY >= L.maxBY - 3) continue;
+            if (maxY > L.maxBY) maxY = (float)L.maxBY;
+            for (int j = 0; j < L.nCols; ++j) {
+                const float iniX = (float)(L.minBX + j * L.wCell);
+                float maxX = iniX + L.wCell + 6;
+                if (iniX >= L.maxBX - 6) continue;
+                if (maxX > L.maxBX) maxX = (float)L.maxBX;
+                CellDesc c;
+                c.level = (short)l; c.x0 = (short)((int)iniX + 3); c.y0 = (short)((int)iniY + 3);
+                c.zw = (short)((int)maxX - (int)iniX - 6); c.zh = (short)((int)maxY - (int)iniY - 6); c.pad = 0;
+                if (c.zw <= 0 || c.zh <= 0) continue;
+                if (c.zw > kMaxCell || c.zh > kMaxCell) { set_error("internal: FAST cell larger than %d", kMaxCell); return HVO_ERR_ARG; }
+                max_zw = std::max(max_zw, (int)c.zw); max_zh = std::max(max_zh, (int)c.zh);
+                L.cand_cap += ((c.zw + 1) / 2) * ((c.zh + 1) / 2);  // NMS survivors are never 8-adjacent
+                cells.push_back(c);
+            }
+        }
+        cand_off += L.cand_cap;
+    }
+    if (max_quota + 8 > 16383) { set_error("nfeatures too large"); return HVO_ERR_ARG; }
+    g.pyr_frame_bytes = (long long)align_up((size_t)off, 256);
+    g.cand_total = std::max(cand_off, 1);
+    g.kp_total = kp_off;
+    g.out_cap = kp_off;
+    ncells = (int)cells.size();
+
+    // ---- CUDA resources ----
+    HVO_CUDA(cudaSetDevice(device));
+    HVO_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) HVO_CUDA(cudaEventCreate(&e));
+    for (auto& e : tev) HVO_CUDA(cudaEventCreate(&e));
+    const size_t B = (size_t)max_batch;
+    HVO_CUDA(cudaMalloc(&d_pyr, std::max<size_t>(B * (size_t)g.pyr_frame_bytes, 256)));
+    HVO_CUDA(cudaMalloc(&d_cand, B * g.cand_total * sizeof(uint32_t)));
+    HVO_CUDA(cudaMalloc(&d_knode, B * g.cand_total * sizeof(uint16_t)));
+    HVO_CUDA(cudaMalloc(&d_ncand, B * n * sizeof(int)));
+    HVO_CUDA(cudaMalloc(&d_okp, B * g.kp_total * sizeof(uint32_t)));
+    HVO_CUDA(cudaMalloc(&d_on, B * n * sizeof(int)));
+    HVO_CUDA(cudaMalloc(&d_err, sizeof(int)));
+    HVO_CUDA(cudaMemset(d_err, 0, sizeof(int)));
+    HVO_CUDA(cudaMalloc(&d_cells, std::max<size_t>(cells.size(), 1) * sizeof(CellDesc)));
+    if (!cells.empty()) HVO_CUDA(cudaMemcpy(d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+
+    // ---- resize tables (cv::resize INTER_LINEAR 8U coefficient generation, oracle/cvprims.hpp) ----
+    std::vector<int2> xt;
+    std::vector<int4> yt;
+    xtab_off.assign(n, 0); ytab_off.assign(n, 0);
+    for (int l = 1; l < n; ++l) {
+        const LevelGeom& S = g.lv[l - 1];
+        const LevelGeom& D = g.lv[l];
+        xtab_off[l] = (int)xt.size(); ytab_off[l] = (int)yt.size();
+        const double scale_x = 1.0 / ((double)D.w / S.w), scale_y = 1.0 / ((double)D.h / S.h);
+        for (int dx = 0; dx < D.w; ++dx) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)std::floor(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+            const short w0 = sat_short_round((1.f - fx) * 2048.f), w1 = sat_short_round(fx * 2048.f);
+            xt.push_back(make_int2(sx, (int)(unsigned short)w0 | ((int)w1 << 16)));
+        }
+        for (int dy = 0; dy < D.h; ++dy) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            int sy = (int)std::floor(fy);
+            fy -= sy;
+            const short b0 = sat_short_round((1.f - fy) * 2048.f), b1 = sat_short_round(fy * 2048.f);
+            const int sy0 = std::min(std::max(sy, 0), S.h - 1), sy1 = std::min(std::max(sy + 1, 0), S.h - 1);
+            yt.push_back(make_int4(sy0, sy1, b0, b1));
+        }
+    }
+    HVO_CUDA(cudaMalloc(&d_xtab, std::max<size_t>(xt.size(), 1) * sizeof(int2)));
+    HVO_CUDA(cudaMalloc(&d_ytab, std::max<size_t>(yt.size(), 1) * sizeof(int4)));
+    if (!xt.empty()) HVO_CUDA(cudaMemcpy(d_xtab, xt.data(), xt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    if (!yt.empty()) HVO_CUDA(cudaMemcpy(d_ytab, yt.data(), yt.size() * sizeof(int4), cudaMemcpyHostToDevice));
+
+    // quadtree shared memory: see the layout in k_octree
+    const size_t CN = (size_t)max_quota + 8;
+    oct_smem = CN * (8 + 16 + 8 + 4 + 4 + 4 + 16 + 8 + 2 + 2 + 1) + 64;
+    if (oct_smem > 200 * 1024) { set_error("nfeatures too large for the quadtree kernel"); return HVO_ERR_ARG; }
+    HVO_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
+    return HVO_OK;
+}
+
+void hvo_orb::release() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    void* bufs[] = {d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_cells, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
+                    d_kps, d_desc, d_counts, d_kpdepth, d_kpuright};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : tev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, uint8_t* d_desc_out, int32_t* d_counts_out,
+                 const uint16_t* d_depth16, const hvo_rgbd_params* rgbd, float* d_kp_depth, float* d_kp_uright) {
+    const int n = p.nlevels, B = nframes;
+    int launches = 0;
+    ImgSrc src;
+    src.l0 = d_gray; src.l0_frame = (long long)width * height; src.l0_pitch = width; src.pyr = d_pyr;
+    last_l0 = d_gray;
+    last_nframes = nframes;
+    if (profiling) HVO_CUDA(cudaEventRecord(ev[0], stream));
+    HVO_CUDA(cudaMemsetAsync(d_ncand, 0, (size_t)B * n * sizeof(int), stream));
+    // K1: pyramid, level l from level l-1
+    for (int l = 1; l < n; ++l) {
+        const LevelGeom& S = g.lv[l - 1];
+        const LevelGeom& D = g.lv[l];
+        const uint8_t* sp = l == 1 ? d_gray : d_pyr + S.img_off;
+        const long long sframe = l == 1 ? src.l0_frame : g.pyr_frame_bytes;
+        dim3 blk(32, 8), grd(div_up(div_up(D.w, 4), 32), div_up(D.h, 8), B);
+        k_resize<<<grd, blk, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
+                                          d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
+        ++launches;
+    }
+    if (profiling) HVO_CUDA(cudaEventRecord(ev[1], stream));
+    // K2: FAST cells
+    if (ncells > 0) {
+        k_fast_cells<<<dim3(ncells, B), 256, 0, stream>>>(g, src, d_cells, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
+        ++launches;
+    }
+    if (profiling) HVO_CUDA(cudaEventRecord(ev[2], stream));
+    // K3: quadtree
+    k_octree<<<dim3(n, B), 256, oct_smem, stream>>>(g, d_cand, d_ncand, d_knode, d_okp, d_on, max_quota + 8, d_err);
+    ++launches;
+    if (profiling) HVO_CUDA(cudaEventRecord(ev[3], stream));
+    // K4: describe
+    const bool rgbd_on = d_depth16 != nullptr && rgbd != nullptr && d_kp_depth != nullptr && d_kp_uright != nullptr;
+    k_describe<<<dim3(div_up(g.out_cap, kDescWarps), B), kDescWarps * 32, 0, stream>>>(
+        g, src, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
+        rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, d_kp_depth, d_kp_uright);
+    ++launches;
+    if (profiling) { HVO_CUDA(cudaEventRecord(ev[4], stream)); have_stage_times = true; }
+    HVO_CUDA(cudaGetLastError());
+    last_launches = launches;
+    return HVO_OK;
+}

@@ -1,0 +1,117 @@
+/* hvo_capi.h — C ABI of libhvofront.so, the B200-native (sm_100a) feature front-end.
+ *
+ * The reference (ORB-SLAM2-derived hybrid VO) has no plugin/FFI registry; its boundary for this path is the
+ * public C++ class surface called by Frame/Tracking.  Each entry point below names the reference interface
+ * it replaces (paths relative to the reference tree).  The C++ shim classes under
+ * a-low-texture-robust-hybrid-feature-based-visual-odometry_b200/shim/ keep the reference's signatures and
+ * forward here; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: every call returns an int status (HVO_OK == 0); hvo_last_error() returns a thread-local
+ * message for the last non-zero status; no exceptions cross the ABI; the caller owns every buffer it
+ * passes; a handle owns its device buffers and one non-blocking CUDA stream; calls on different handles
+ * are thread-safe, calls on one handle must be serialised by the caller (the reference's usage model:
+ * one long-lived extractor per Tracking thread, src/Tracking.cc:124).  There is NO CPU fallback: without a
+ * CUDA device every create call fails with HVO_ERR_CUDA.
+ */
+#ifndef HVO_CAPI_H
+#define HVO_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVO_OK 0
+#define HVO_ERR_ARG 1      /* bad argument (null pointer, size out of range, capacity too small) */
+#define HVO_ERR_CUDA 2     /* CUDA runtime / launch failure, or no device */
+#define HVO_ERR_STATE 3    /* call not valid in the handle's current state */
+#define HVO_ERR_OVERFLOW 4 /* an internal fixed-capacity buffer would overflow (reported, never silent) */
+
+#define HVO_MAX_LEVELS 12
+
+const char* hvo_last_error(void);
+int hvo_device_count(int* n_out);
+/* library build info, e.g. "hvofront sm_100a <date>" */
+const char* hvo_version(void);
+
+/* ------------------------------------------------------------------------------------------------ ORB
+ * Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:46-110, src/ORBextractor.cc).              */
+
+typedef struct hvo_orb hvo_orb;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)  ORBextractor.h:51-52 */
+typedef struct hvo_orb_params {
+    int nfeatures;
+    float scale_factor;
+    int nlevels;
+    int ini_th_fast;
+    int min_th_fast;
+} hvo_orb_params;
+
+/* cv::KeyPoint POD layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct hvo_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} hvo_keypoint;
+
+/* Optional RGB-D epilogue = Frame::ComputeStereoFromRGBD (src/Frame.cc:1940-1961) fused after extraction.
+ * depth is raw 16-bit (TUM: metres*5000); depth_factor = 1/DepthMapFactor (src/Tracking.cc:156-160). */
+typedef struct hvo_rgbd_params {
+    float depth_factor; /* metres per raw unit, e.g. 1/5000 */
+    float bf;           /* stereo baseline * fx (Camera.bf) */
+} hvo_rgbd_params;
+
+/* Create an extractor for frames of width x height, up to max_batch frames per call, on CUDA `device`. */
+int hvo_orb_create(const hvo_orb_params* params, int width, int height, int max_batch, int device, hvo_orb** out);
+void hvo_orb_destroy(hvo_orb* h);
+
+/* Upper bound on keypoints per frame (rows of the caller's kps / desc buffers per frame). */
+int hvo_orb_capacity(const hvo_orb* h);
+
+/* Getters of ORBextractor.h:63-83.  Each array has nlevels entries. */
+int hvo_orb_get_tables(const hvo_orb* h, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                       float* inv_level_sigma2, int32_t* features_per_level);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)  ORBextractor.h:59-61, .cc:1041-1103.
+ * gray: host, 8-bit, `stride` bytes per row.  kps/desc: host, `capacity` rows (desc rows are 32 bytes).
+ * Empty image (null / zero size) returns HVO_OK with *n_out = 0, as the reference does (.cc:1044-1045). */
+int hvo_orb_extract(hvo_orb* h, const uint8_t* gray, size_t stride, hvo_keypoint* kps, uint8_t* desc, int capacity,
+                    int* n_out);
+
+/* Batched variant for offline sequences: nframes tightly packed [n][height][width] host frames; outputs are
+ * [n][capacity] rows; counts[n].  depth16 (optional, [n][height][width] uint16) enables the RGB-D epilogue:
+ * kp_depth / kp_uright are [n][capacity] floats (-1 where depth is invalid). */
+int hvo_orb_extract_batch(hvo_orb* h, const uint8_t* gray, int nframes, hvo_keypoint* kps, uint8_t* desc,
+                          int32_t* counts, const uint16_t* depth16, const hvo_rgbd_params* rgbd, float* kp_depth,
+                          float* kp_uright);
+
+/* Same, all pointers in device memory on the handle's device; asynchronous on the handle's stream. */
+int hvo_orb_extract_batch_device(hvo_orb* h, const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps, uint8_t* d_desc,
+                                 int32_t* d_counts, const uint16_t* d_depth16, const hvo_rgbd_params* rgbd,
+                                 float* d_kp_depth, float* d_kp_uright);
+int hvo_orb_sync(hvo_orb* h);
+
+/* Stream timing for benchmarks: records CUDA events on the handle's stream. */
+int hvo_orb_timer_start(hvo_orb* h);
+int hvo_orb_timer_stop(hvo_orb* h, float* ms_out); /* synchronises */
+/* Per-stage device time of the last *_batch call made with profiling enabled (ms): pyramid, fast, octree,
+ * describe.  Enabling inserts events between stages; leave off for throughput runs. */
+int hvo_orb_set_profiling(hvo_orb* h, int enable);
+int hvo_orb_stage_times(hvo_orb* h, float* ms4);
+/* Number of kernel launches issued by the last extract call. */
+int hvo_orb_last_launches(const hvo_orb* h);
+
+/* ORBextractor::mvImagePyramid (ORBextractor.h:85): copy level `level` of frame `frame` of the last call. */
+int hvo_orb_level_size(const hvo_orb* h, int level, int* w, int* h_out);
+int hvo_orb_get_pyramid_level(hvo_orb* h, int frame, int level, uint8_t* out, size_t out_stride);
+
+/* Inspection of intermediates (tests): pre-quadtree FAST candidates of a level, unordered;
+ * xys = [cap][3] int32 (x, y in level coordinates, score). */
+int hvo_orb_get_candidates(hvo_orb* h, int frame, int level, int32_t* xys, int cap, int* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVO_CAPI_H */

@@ -1,0 +1,95 @@
+"""Generates the committed golden fixtures.  Run in the build container (needs cv2 4.13.0 and, for the ORB
+fixture, oracle/_ref/ref_orb = the reference's own src/ORBextractor.cc built by oracle/Makefile):
+
+    python tests/golden/make_golden.py
+
+prims_cv2.npz  inputs + outputs of the OpenCV primitives the reference calls (cv2 4.13.0 is the pin)
+orb_ref.npz    inputs + outputs of the reference's ORBextractor.cc on small frames
+"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import hvo_b200  # noqa: E402
+from hvo_b200 import synth  # noqa: E402
+import oracle  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def prims():
+    assert cv2.__version__ == '4.13.0', cv2.__version__
+    cv2.setNumThreads(1)
+    img = synth.noise_frame(160, 120, 11)
+    out = dict(img=img, cv2_version=np.array(cv2.__version__))
+    sizes = [(133, 100), (111, 83), (93, 69), (77, 58), (150, 113), (81, 61)]
+    cur = img
+    for i, (w, h) in enumerate(sizes[:4]):  # cascade, as the pyramid does
+        cur = cv2.resize(cur, (w, h), interpolation=cv2.INTER_LINEAR)
+        out[f'resize_cascade_{i}'] = cur
+    for i, (w, h) in enumerate(sizes[4:]):
+        out[f'resize_single_{i}'] = cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+    out['blur7'] = cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    out['blur5'] = cv2.GaussianBlur(img, (5, 5), 1, 1, borderType=cv2.BORDER_REFLECT_101)
+    out['sobel_dx'] = cv2.Sobel(img, cv2.CV_16S, 1, 0, ksize=3)
+    out['sobel_dy'] = cv2.Sobel(img, cv2.CV_16S, 0, 1, ksize=3)
+    r = np.random.RandomState(5)
+    rois = [(0, 0, 160, 120)] + [(r.randint(0, 110), r.randint(0, 80), r.randint(7, 44), r.randint(7, 40)) for _ in range(40)]
+    out['fast_rois'] = np.array(rois, np.int32)
+    for thr in (20, 7):
+        det = cv2.FastFeatureDetector_create(threshold=thr, nonmaxSuppression=True)
+        allk, offs = [], [0]
+        for (x, y, w, h) in rois:
+            ks = det.detect(img[y:y + h, x:x + w])
+            allk += [[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in ks]
+            offs.append(len(allk))
+        out[f'fast_{thr}_kps'] = np.array(allk, np.int32).reshape(-1, 3)
+        out[f'fast_{thr}_offs'] = np.array(offs, np.int32)
+    yy = (r.randn(4000) * 500).astype(np.float32)
+    xx = (r.randn(4000) * 500).astype(np.float32)
+    yy[:8] = [0, 0, 1, -1, 5, -5, 0, 3]
+    xx[:8] = [0, 1, 0, 0, 5, -5, -2, -3]
+    out['atan2_y'], out['atan2_x'] = yy, xx
+    out['atan2'] = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(yy, xx)], np.float32)
+    # brute-force Hamming knn-2 (what LSDmatcher uses: src/LSDmatcher.cpp:811-812), with planted ties
+    q = r.randint(0, 256, (60, 32)).astype(np.uint8)
+    t = r.randint(0, 256, (300, 32)).astype(np.uint8)
+    t[17] = t[5]; t[200] = q[3]; t[201] = q[3]; t[77] = q[9]
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(q, t, k=2)
+    out['knn_q'], out['knn_t'] = q, t
+    out['knn_idx'] = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    out['knn_dist'] = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    np.savez_compressed(os.path.join(OUT, 'prims_cv2.npz'), **out)
+    print('prims_cv2.npz written')
+
+
+def orb():
+    if oracle.ref_orb_path() is None:
+        print('oracle/_ref/ref_orb missing: run make -C oracle first')
+        return
+    cases = []
+    g1, _ = synth.frame('S1', 0)
+    g2, _ = synth.frame('S2', 1)
+    cases.append(('s1_crop', g1[100:340, 150:470].copy(), dict(nfeatures=300, scale_factor=1.2, nlevels=6, ini_th=20, min_th=7)))
+    cases.append(('s2_crop', g2[120:360, 200:520].copy(), dict(nfeatures=300, scale_factor=1.2, nlevels=6, ini_th=20, min_th=7)))
+    cases.append(('noise', synth.noise_frame(256, 192, 3), dict(nfeatures=500, scale_factor=1.2, nlevels=5, ini_th=20, min_th=7)))
+    out = {}
+    for name, img, p in cases:
+        (kps, desc), = oracle.ref_orb_extract(img[None], **p)
+        out[name + '_img'] = img
+        out[name + '_params'] = np.array([p['nfeatures'], p['nlevels'], p['ini_th'], p['min_th']], np.int32)
+        out[name + '_scale'] = np.float32(p['scale_factor'])
+        out[name + '_kps'] = kps
+        out[name + '_desc'] = desc
+        print(name, len(kps))
+    np.savez_compressed(os.path.join(OUT, 'orb_ref.npz'), **out)
+    print('orb_ref.npz written')
+
+
+if __name__ == '__main__':
+    prims()
+    orb()
