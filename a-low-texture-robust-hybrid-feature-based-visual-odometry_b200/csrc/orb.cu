@@ -772,7 +772,13 @@ int hvo_orb::init() {
     const size_t CN = (size_t)max_quota + 8;
     oct_smem = CN * (8 + 16 + 8 + 4 + 4 + 4 + 16 + 8 + 2 + 2 + 1) + 64;
     if (oct_smem > 200 * 1024) { set_error("nfeatures too large for the quadtree kernel"); return HVO_ERR_ARG; }
-    HVO_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
+    // the attribute is per function (shared by all handles on the device): only ever raise it
+    static size_t s_oct_smem_max[64] = {0};
+    const size_t want = std::max<size_t>(oct_smem, 48 * 1024);
+    if (device < 64 && want > s_oct_smem_max[device]) {
+        HVO_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+        s_oct_smem_max[device] = want;
+    }
     return HVO_OK;
 }
 
