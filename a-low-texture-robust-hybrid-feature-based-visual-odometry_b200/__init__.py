@@ -233,9 +233,9 @@ class ORBextractor:
         _check(lib().hvo_orb_set_profiling(self._h, int(on)))
 
     def stage_times(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         _check(lib().hvo_orb_stage_times(self._h, ms))
-        return dict(zip(('pyramid', 'fast', 'octree', 'describe'), [float(v) for v in ms]))
+        return dict(zip(('pyramid', 'fast', 'octree', 'blur', 'describe'), [float(v) for v in ms]))
 
     def last_launches(self):
         return lib().hvo_orb_last_launches(self._h)

@@ -34,7 +34,7 @@ int hvo_orb_create(const hvo_orb_params* params, int width, int height, int max_
     *out = nullptr;
     HVO_CHECK_ARG(params->nlevels >= 1 && params->nlevels <= HVO_MAX_LEVELS, "nlevels out of range");
     HVO_CHECK_ARG(params->nfeatures >= 1, "nfeatures < 1");
-    HVO_CHECK_ARG(params->scale_factor > 1.0f, "scale_factor must be > 1");
+    HVO_CHECK_ARG(params->scale_factor > 1.0f && params->scale_factor <= 2.0f, "scale_factor must be in (1, 2]");
     HVO_CHECK_ARG(params->ini_th_fast >= 1 && params->min_th_fast >= 1 && params->ini_th_fast <= 254 &&
                       params->min_th_fast <= 254, "FAST thresholds must be in [1,254]");
     HVO_CHECK_ARG(width >= 64 && height >= 64, "image smaller than 64x64");
@@ -192,12 +192,12 @@ int hvo_orb_set_profiling(hvo_orb* h, int enable) {
     h->have_stage_times = false;
     return HVO_OK;
 }
-int hvo_orb_stage_times(hvo_orb* h, float* ms4) {
-    HVO_CHECK_ARG(h && ms4, "null handle / ms4");
+int hvo_orb_stage_times(hvo_orb* h, float* ms5) {
+    HVO_CHECK_ARG(h && ms5, "null handle / ms5");
     if (!h->have_stage_times) { set_error("no profiled call recorded"); return HVO_ERR_STATE; }
     HVO_CUDA(cudaSetDevice(h->device));
-    HVO_CUDA(cudaEventSynchronize(h->ev[4]));
-    for (int i = 0; i < 4; ++i) HVO_CUDA(cudaEventElapsedTime(&ms4[i], h->ev[i], h->ev[i + 1]));
+    HVO_CUDA(cudaEventSynchronize(h->ev[5]));
+    for (int i = 0; i < 5; ++i) HVO_CUDA(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
     return HVO_OK;
 }
 int hvo_orb_last_launches(const hvo_orb* h) { return h ? h->last_launches : 0; }

@@ -44,39 +44,62 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbGeom& g, const ImgS
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1: bilinear resize, 4 output pixels per thread
+// K1: bilinear resize.  One CTA = 128 x 32 destination pixels.  Pass H interpolates every source row the
+// tile needs once (thread <-> destination column, coefficients in registers) into shared memory as
+// (S0*w0 + S1*w1) >> 4 (15 bits); pass V blends two such rows per destination row and stores 4 px / thread.
 // ------------------------------------------------------------------------------------------------------
+static const int kRsW = 128, kRsH = 32, kRsMaxSrcRows = 72;
+
 __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int spitch, long long sframe, int sw,
                                                 uint8_t* __restrict__ dst, int dpitch, long long dframe, int dw, int dh,
                                                 const int2* __restrict__ xtab, const int4* __restrict__ ytab) {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= dw || y >= dh) return;
-    const int f = blockIdx.z;
-    const int4 yt = __ldg(&ytab[y]);
-    const uint8_t* S0 = src + (long long)f * sframe + (long long)yt.x * spitch;
-    const uint8_t* S1 = src + (long long)f * sframe + (long long)yt.y * spitch;
-    uint32_t packed = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int x = x0 + i;
+    __shared__ __align__(8) uint16_t hrow[kRsMaxSrcRows * kRsW];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int tx = blockIdx.x * kRsW, ty = blockIdx.y * kRsH;
+    const int ylast = min(ty + kRsH, dh) - 1;
+    const int s_base = __ldg(&ytab[ty]).x;
+    const int ns = min(__ldg(&ytab[ylast]).y - s_base + 1, kRsMaxSrcRows);
+    const uint8_t* S = src + (long long)f * sframe;
+    {   // pass H
+        const int col = tid & (kRsW - 1), half = tid >> 7;
+        const int x = tx + col;
         if (x < dw) {
             const int2 xt = __ldg(&xtab[x]);
-            const int sx = xt.x;
-            const int s1 = min(sx + 1, sw - 1);
+            const int sx = xt.x, s1 = min(sx + 1, sw - 1);
             const int w0 = (int)(short)(xt.y & 0xffff), w1 = xt.y >> 16;
-            const int r0 = S0[sx] * w0 + S0[s1] * w1;
-            const int r1 = S1[sx] * w0 + S1[s1] * w1;
-            int v = (((yt.z * (r0 >> 4)) >> 16) + ((yt.w * (r1 >> 4)) >> 16) + 2) >> 2;
-            v = min(255, max(0, v));
-            packed |= (uint32_t)v << (8 * i);
+            for (int r = half; r < ns; r += 2) {
+                const uint8_t* row = S + (long long)(s_base + r) * spitch;
+                hrow[r * kRsW + col] = (uint16_t)((__ldg(row + sx) * w0 + __ldg(row + s1) * w1) >> 4);
+            }
         }
     }
-    uint8_t* D = dst + (long long)f * dframe + (long long)y * dpitch + x0;
-    if (x0 + 3 < dw) {
-        *reinterpret_cast<uint32_t*>(D) = packed;  // dpitch and x0 are multiples of 4
-    } else {
-        for (int i = 0; x0 + i < dw; ++i) D[i] = (uint8_t)(packed >> (8 * i));
+    __syncthreads();
+    {   // pass V
+        const int cg = tid & 31, rs = tid >> 5;
+        const int x0 = tx + 4 * cg;
+        if (x0 < dw) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int y = ty + rs * 4 + j;
+                if (y < dh) {
+                    const int4 yt = __ldg(&ytab[y]);
+                    const uint2 a = *reinterpret_cast<const uint2*>(&hrow[(yt.x - s_base) * kRsW + 4 * cg]);
+                    const uint2 b = *reinterpret_cast<const uint2*>(&hrow[(yt.y - s_base) * kRsW + 4 * cg]);
+                    const int h0[4] = {(int)(a.x & 0xffff), (int)(a.x >> 16), (int)(a.y & 0xffff), (int)(a.y >> 16)};
+                    const int h1[4] = {(int)(b.x & 0xffff), (int)(b.x >> 16), (int)(b.y & 0xffff), (int)(b.y >> 16)};
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int v = (((yt.z * h0[i]) >> 16) + ((yt.w * h1[i]) >> 16) + 2) >> 2;
+                        v = min(255, max(0, v));
+                        packed |= (uint32_t)v << (8 * i);
+                    }
+                    uint8_t* D = dst + (long long)f * dframe + (long long)y * dpitch + x0;
+                    if (x0 + 3 < dw) *reinterpret_cast<uint32_t*>(D) = packed;  // dpitch and x0 are multiples of 4
+                    else for (int i = 0; x0 + i < dw; ++i) D[i] = (uint8_t)(packed >> (8 * i));
+                }
+            }
+        }
     }
 }
 
@@ -127,64 +150,135 @@ __device__ __forceinline__ int fast_strength(const int (&d)[16]) {
      : (k) == 11 ? (p)[-(st) - 3] : (k) == 12 ? (p)[-3] : (k) == 13 ? (p)[(st) - 3] : (k) == 14 ? (p)[2 * (st) - 2]    \
                                                                                                 : (p)[3 * (st) - 1])
 
-static const int kTileStride = kMaxCell + 8;  // 72
+static const int kTW = 20;                 // tile row stride in 32-bit words: (60 + 6 + 3 alignment) bytes <= 72
+static const int kTileBytes = kTW * 4;     // 80
+
+// Packed 4-pixel FAST ring compare.  `lo`/`hi` are two consecutive tile words of one row; returns the 4 ring
+// bytes seen by the 4 pixels of the group at horizontal offset dx (-3..3).
+__device__ __forceinline__ uint32_t ring4(const uint32_t* row, int g, int dx) {
+    switch (dx) {
+        case 0: return row[g];
+        case 1: return __byte_perm(row[g], row[g + 1], 0x4321);
+        case 2: return __byte_perm(row[g], row[g + 1], 0x5432);
+        case 3: return __byte_perm(row[g], row[g + 1], 0x6543);
+        case -1: return __byte_perm(row[g - 1], row[g], 0x6543);
+        case -2: return __byte_perm(row[g - 1], row[g], 0x5432);
+        default: return __byte_perm(row[g - 1], row[g], 0x4321);
+    }
+}
+
+// byte-sliced "9 contiguous of 16": m[k] holds 0xFF in byte j iff ring position k passes for pixel j
+__device__ __forceinline__ uint32_t run9_sliced(const uint32_t (&m)[16]) {
+    uint32_t t3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t3[k] = m[k] & m[(k + 1) & 15] & m[(k + 2) & 15];
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) any |= t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+    return any;
+}
 
 __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbGeom g, ImgSrc src,
                                                     const CellDesc* __restrict__ cells, uint32_t* __restrict__ cand,
                                                     int* __restrict__ ncand, int ini_th, int min_th) {
-    __shared__ uint8_t tile[(kMaxCell + 6) * kTileStride];
+    // tile words are stored from index 1 so that group g may read word g-1 (content unused when g == 0)
+    __shared__ uint32_t tile_w[1 + (kMaxCell + 6) * kTW + 2];
     __shared__ uint8_t score[kMaxCell * kMaxCell];
     __shared__ uint16_t clist[kMaxCell * kMaxCell];
     __shared__ int s_ncorner, s_nini, s_nmin, s_base, s_slot;
 
     const CellDesc c = cells[blockIdx.x];
-    const int f = blockIdx.y, tid = threadIdx.x;
+    const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const LevelGeom& L = g.lv[c.level];
     int pitch;
     const uint8_t* img = level_ptr(g, src, c.level, f, pitch);
     const int zw = c.zw, zh = c.zh, tw = zw + 6, th = zh + 6;
     const int low_th = min(ini_th, min_th);
+    uint32_t* tile = tile_w + 1;
 
-    const uint8_t* org = img + (long long)(c.y0 - 3) * pitch + (c.x0 - 3);
-    for (int i = tid; i < tw * th; i += 256) {
-        const int ty = i / tw, tx = i - ty * tw;
-        tile[ty * kTileStride + tx] = __ldg(org + (long long)ty * pitch + tx);
+    // ---- tile (zone + 3-px ring) -> shared memory, as aligned 32-bit words ----
+    const int tx0 = c.x0 - 3, ty0 = c.y0 - 3;
+    const int xal = tx0 & ~3;              // word-aligned tile origin (>= 12: the search window starts at x = 16)
+    const int sh = tx0 - xal;              // 0..3
+    const int nw = (sh + tw + 3) >> 2;     // words per tile row (all inside the image row: x < w - 13)
+    const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    for (int r = warp; r < th; r += 8) {
+        if (lane < nw) {
+            const uint8_t* p = img + (long long)(ty0 + r) * pitch + xal + 4 * lane;
+            uint32_t w;
+            if (aligned) w = __ldg(reinterpret_cast<const uint32_t*>(p));
+            else w = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+            tile[r * kTW + lane] = w;
+        }
     }
-    for (int i = tid; i < zh * kMaxCell; i += 256) score[i] = 0;
+    for (int i = tid; i < zh * (kMaxCell / 4); i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
     if (tid == 0) { s_ncorner = 0; s_nini = 0; s_nmin = 0; s_slot = 0; }
     __syncthreads();
 
-    // pass 1: which zone pixels are FAST corners at the lower threshold (bit test for a run of 9)
-    const int npx = zw * zh;
-    for (int i = tid; i < npx; i += 256) {
-        const int zy = i / zw, zx = i - zy * zw;
-        const uint8_t* p = &tile[(zy + 3) * kTileStride + zx + 3];
-        const int v = *p;
-        uint32_t bright = 0, dark = 0;
+    // ---- pass 1: corner test at the lower threshold, 4 pixels per thread with packed byte compares ----
+    const int zb0 = sh + 3;                          // tile byte column of the first zone pixel
+    const int g0 = zb0 >> 2, g1 = (zb0 + zw - 1) >> 2, ng = g1 - g0 + 1;
+    const uint32_t magic = (65536u + ng - 1) / ng;  // i / ng for i < 4096
+    const uint32_t T4 = (uint32_t)low_th * 0x01010101u;
+    for (int i = tid; i < ng * zh; i += 256) {
+        int zy = (int)(((uint32_t)i * magic) >> 16);
+        if (zy * ng > i) --zy;
+        const int gi = g0 + (i - zy * ng);
+        const uint32_t* r0 = tile + (zy + 3) * kTW;
+        const uint32_t v4 = r0[gi];
+        const uint32_t vp = __vaddus4(v4, T4), vm = __vsubus4(v4, T4);
+        // zone mask of this group's 4 bytes
+        uint32_t zmask = 0xffffffffu;
+        const int b0 = 4 * gi;
+        if (b0 < zb0) zmask &= 0xffffffffu << (8 * (zb0 - b0));
+        if (b0 + 3 > zb0 + zw - 1) zmask &= 0xffffffffu >> (8 * (b0 + 3 - (zb0 + zw - 1)));
+        // quick reject on the 4 cardinal ring points: a 9-arc always holds two adjacent cardinals
+        const uint32_t c0 = (tile + (zy + 6) * kTW)[gi], c8 = (tile + zy * kTW)[gi];
+        const uint32_t c4 = ring4(r0, gi, 3), c12 = ring4(r0, gi, -3);
+        const uint32_t d0 = __vcmpgtu4(vm, c0), d4 = __vcmpgtu4(vm, c4), d8 = __vcmpgtu4(vm, c8), d12 = __vcmpgtu4(vm, c12);
+        const uint32_t e0 = __vcmpgtu4(c0, vp), e4 = __vcmpgtu4(c4, vp), e8 = __vcmpgtu4(c8, vp), e12 = __vcmpgtu4(c12, vp);
+        const uint32_t maybe = (((d0 | d8) & (d4 | d12)) | ((e0 | e8) & (e4 | e12))) & zmask;
+        if (maybe == 0) continue;
+        // full 16-point test, still packed
+        uint32_t m[16], corner;
+        {
+            const uint32_t* rp3 = tile + (zy + 6) * kTW; const uint32_t* rp2 = tile + (zy + 5) * kTW;
+            const uint32_t* rp1 = tile + (zy + 4) * kTW; const uint32_t* rm1 = tile + (zy + 2) * kTW;
+            const uint32_t* rm2 = tile + (zy + 1) * kTW; const uint32_t* rm3 = tile + zy * kTW;
+            uint32_t q[16];
+            q[0] = c0;                  q[1] = ring4(rp3, gi, 1);   q[2] = ring4(rp2, gi, 2);   q[3] = ring4(rp1, gi, 3);
+            q[4] = c4;                  q[5] = ring4(rm1, gi, 3);   q[6] = ring4(rm2, gi, 2);   q[7] = ring4(rm3, gi, 1);
+            q[8] = c8;                  q[9] = ring4(rm3, gi, -1);  q[10] = ring4(rm2, gi, -2); q[11] = ring4(rm1, gi, -3);
+            q[12] = c12;                q[13] = ring4(rp1, gi, -3); q[14] = ring4(rp2, gi, -2); q[15] = ring4(rp3, gi, -1);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int d = v - (int)HVO_RING(p, kTileStride, k);
-            bright |= (d > low_th ? 1u : 0u) << k;
-            dark |= (d < -low_th ? 1u : 0u) << k;
+            for (int k = 0; k < 16; ++k) m[k] = __vcmpgtu4(vm, q[k]);
+            corner = run9_sliced(m);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[k] = __vcmpgtu4(q[k], vp);
+            corner |= run9_sliced(m);
         }
-        if (has_run9(bright) || has_run9(dark)) clist[atomicAdd(&s_ncorner, 1)] = (uint16_t)(zy * kMaxCell + zx);
+        corner &= maybe;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((corner >> (8 * j)) & 1u) clist[atomicAdd(&s_ncorner, 1)] = (uint16_t)(zy * kMaxCell + (b0 + j - zb0));
     }
     __syncthreads();
 
-    // pass 2: exact strength, only for corners, densely packed over threads
+    // ---- pass 2: exact strength, only for corners, densely packed over threads ----
+    const uint8_t* tile_b = reinterpret_cast<const uint8_t*>(tile);
     const int ncorner = s_ncorner;
     for (int i = tid; i < ncorner; i += 256) {
         const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
-        const uint8_t* p = &tile[(zy + 3) * kTileStride + zx + 3];
+        const uint8_t* p = tile_b + (zy + 3) * kTileBytes + zb0 + zx;
         const int v = *p;
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, kTileStride, k);
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, kTileBytes, k);
         score[pos] = (uint8_t)fast_strength(d);  // in [low_th, 254]
     }
     __syncthreads();
 
-    // pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the zone counts as 0)
+    // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the zone counts as 0) ----
     uint32_t f_ini = 0, f_min = 0;
     for (int i = tid, it = 0; i < ncorner; i += 256, ++it) {
         const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
@@ -497,24 +591,100 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-static const int kPR = 21;             // patch radius: 18 (max |rBRIEF sample offset|) + 3 (blur)
-static const int kPW = 2 * kPR + 1;    // 43
-static const int kRawStride = 44;
-static const int kBW = 37;             // blurred window 37x37
-static const int kHbStride = 38;
-static const int kBlStride = 40;
-static const int kDescWarps = 4;
+// ------------------------------------------------------------------------------------------------------
+// K4: 7x7 sigma-2 Gaussian of every level (cv::GaussianBlur fixed point: Q8 kernel 18,34,48,56,48,34,18,
+// horizontal pass exact in 16 bits, vertical pass rounded (v + 2^15) >> 16, BORDER_REFLECT_101).
+// One CTA = 128 x 32 output pixels; horizontal pass with __dp4a on aligned words, vertical pass 4x4 px / thread.
+// ------------------------------------------------------------------------------------------------------
+static const int kBlW = 128, kBlH = 32, kBlRawStride = 35, kBlHbStride = 66;
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, ImgSrc src,
+                                              const TileDesc* __restrict__ tiles, uint8_t* __restrict__ blur) {
+    __shared__ uint32_t raw[(kBlH + 6) * kBlRawStride];
+    __shared__ __align__(8) uint32_t hb[(kBlH + 6) * kBlHbStride];
+    const TileDesc t = tiles[blockIdx.x];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom& L = g.lv[t.level];
+    int pitch;
+    const uint8_t* img = level_ptr(g, src, t.level, f, pitch);
+    const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    const int tx = t.tx, ty = t.ty;
+    for (int idx = tid; idx < (kBlH + 6) * 34; idx += 256) {
+        const int r = idx / 34, wi = idx - r * 34;
+        const int y = reflect101(ty - 3 + r, L.h);
+        const int x = tx - 4 + 4 * wi;
+        const uint8_t* row = img + (long long)y * pitch;
+        uint32_t w = 0;
+        if (aligned && x >= 0 && x + 3 < L.w) {
+            w = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = min(max(reflect101(x + j, L.w), 0), L.w - 1);
+                w |= (uint32_t)__ldg(row + xx) << (8 * j);
+            }
+        }
+        raw[r * kBlRawStride + wi] = w;
+    }
+    __syncthreads();
+    const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
+    for (int idx = tid; idx < (kBlH + 6) * 32; idx += 256) {
+        const int r = idx >> 5, gq = idx & 31;
+        const uint32_t a = raw[r * kBlRawStride + gq], b = raw[r * kBlRawStride + gq + 1], c = raw[r * kBlRawStride + gq + 2];
+        // output x = 4gq + j reads tile bytes 4gq + j + 1 .. + 7
+        const uint32_t o0 = __dp4a(__byte_perm(a, b, 0x4321), K0123, __dp4a(__byte_perm(b, c, 0x4321), K456, 0u));
+        const uint32_t o1 = __dp4a(__byte_perm(a, b, 0x5432), K0123, __dp4a(__byte_perm(b, c, 0x5432), K456, 0u));
+        const uint32_t o2 = __dp4a(__byte_perm(a, b, 0x6543), K0123, __dp4a(__byte_perm(b, c, 0x6543), K456, 0u));
+        const uint32_t o3 = __dp4a(b, K0123, __dp4a(c, K456, 0u));
+        *reinterpret_cast<uint2*>(&hb[r * kBlHbStride + 2 * gq]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    }
+    __syncthreads();
+    {
+        const int q = tid & 31, sgm = tid >> 5;  // 4 columns x 4 rows per thread
+        const int x0 = tx + 4 * q;
+        if (x0 < L.w) {
+            uint32_t col[10][2];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const uint2 v = *reinterpret_cast<const uint2*>(&hb[(4 * sgm + r) * kBlHbStride + 2 * q]);
+                col[r][0] = v.x; col[r][1] = v.y;
+            }
+            uint8_t* out = blur + (long long)f * g.blur_frame_bytes + L.blur_off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int y = ty + 4 * sgm + j;
+                uint32_t packed = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t h[7];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) h[k] = (i & 1) ? (col[j + k][i >> 1] >> 16) : (col[j + k][i >> 1] & 0xffffu);
+                    const uint32_t acc = 18u * (h[0] + h[6]) + 34u * (h[1] + h[5]) + 48u * (h[2] + h[4]) + 56u * h[3];
+                    packed |= ((acc + 32768u) >> 16) << (8 * i);
+                }
+                if (y < L.h) {
+                    uint8_t* D = out + (long long)y * L.bpitch + x0;
+                    if (x0 + 3 < L.w) *reinterpret_cast<uint32_t*>(D) = packed;
+                    else for (int i = 0; x0 + i < L.w; ++i) D[i] = (uint8_t)(packed >> (8 * i));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5: orientation + steered rBRIEF + output assembly, one warp per keypoint
+// ------------------------------------------------------------------------------------------------------
+static const int kDescWarps = 8;
 
 __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_constant__ OrbGeom g, ImgSrc src,
+                                                              const uint8_t* __restrict__ blur,
                                                               const uint32_t* __restrict__ okp_all,
                                                               const int* __restrict__ on, hvo_keypoint* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int32_t* __restrict__ counts,
                                                               const uint16_t* __restrict__ depth16, float depth_factor,
                                                               float bf, float* __restrict__ kp_depth,
                                                               float* __restrict__ kp_uright) {
-    __shared__ uint8_t s_raw[kDescWarps][kPW * kRawStride];
-    __shared__ uint16_t s_hb[kDescWarps][kPW * kHbStride];
-    __shared__ uint8_t s_bl[kDescWarps][kBW * kBlStride];
     __shared__ int8_t s_pat[1024];
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
@@ -536,25 +706,16 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
     const int cx = c & 0xfff, cy = (c >> 12) & 0xfff, resp = c >> 24;
     int pitch;
     const uint8_t* img = level_ptr(g, src, lvl, f, pitch);
-    uint8_t* raw = s_raw[warp];
-    uint16_t* hb = s_hb[warp];
-    uint8_t* bl = s_bl[warp];
 
-    // raw 43x43 patch, BORDER_REFLECT_101 at the level edges
-    for (int r = 0; r < kPW; ++r) {
-        const int yy = reflect101(cy - kPR + r, L.h);
-        const uint8_t* row = img + (long long)yy * pitch;
-        for (int cc = lane; cc < kPW; cc += 32) raw[r * kRawStride + cc] = __ldg(row + reflect101(cx - kPR + cc, L.w));
-    }
-    __syncwarp();
-
-    // IC_Angle: lane <-> column u = lane - 15
+    // IC_Angle on the unblurred level: lane <-> column u = lane - 15, rows are coalesced 31-byte reads
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = abs(u);
+        const uint8_t* p = img + (long long)cy * pitch + cx + u;
+#pragma unroll
         for (int v = -15; v <= 15; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = raw[(kPR + v) * kRawStride + kPR + u];
+            if (au <= c_umax[v < 0 ? -v : v]) {
+                const int val = __ldg(p + (long long)v * pitch);
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -567,30 +728,14 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // separable 7x7 sigma-2 Gaussian in Q8 (kernel 18,34,48,56,48,34,18), rows 0..42 x cols 3..39 then rows 3..39
-    for (int i = lane; i < kPW * kBW; i += 32) {
-        const int r = i / kBW, cc = i - r * kBW;
-        const uint8_t* p = raw + r * kRawStride + cc;
-        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        hb[r * kHbStride + cc] = (uint16_t)acc;
-    }
-    __syncwarp();
-    for (int i = lane; i < kBW * kBW; i += 32) {
-        const int r = i / kBW, cc = i - r * kBW;
-        const uint16_t* p = hb + r * kHbStride + cc;
-        const uint32_t acc = 18u * (p[0] + p[6 * kHbStride]) + 34u * (p[kHbStride] + p[5 * kHbStride]) +
-                             48u * (p[2 * kHbStride] + p[4 * kHbStride]) + 56u * p[3 * kHbStride];
-        bl[r * kBlStride + cc] = (uint8_t)((acc + 32768u) >> 16);
-    }
-    __syncwarp();
-
-    // steered rBRIEF: lane i -> descriptor byte i
+    // steered rBRIEF on the blurred level: lane i -> descriptor byte i
     const float factorPI = 0.017453292519943295769236907684886f;  // (float)(CV_PI / 180.f)
     const float ang = __fmul_rn(angle, factorPI);
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t* ctr = bl + 18 * kBlStride + 18;
+    const uint8_t* ctr = blur + (long long)f * g.blur_frame_bytes + L.blur_off + (long long)cy * L.bpitch + cx;
+    const int bp = L.bpitch;
     const int8_t* pt = s_pat + lane * 32;
-    int val = 0;
+    int t0v[8], t1v[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const float ax = pt[4 * t], ay = pt[4 * t + 1], bx = pt[4 * t + 2], by = pt[4 * t + 3];
@@ -598,9 +743,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(ax, a), __fmul_rn(ay, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(bx, b), __fmul_rn(by, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(bx, a), __fmul_rn(by, b)));
-        const int t0 = ctr[r0 * kBlStride + c0], t1 = ctr[r1 * kBlStride + c1];
-        val |= (t0 < t1 ? 1 : 0) << t;
+        t0v[t] = __ldg(ctr + r0 * bp + c0);
+        t1v[t] = __ldg(ctr + r1 * bp + c1);
     }
+    int val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) val |= (t0v[t] < t1v[t] ? 1 : 0) << t;
     const long long o = (long long)f * g.out_cap + gi;
     desc[o * 32 + lane] = (uint8_t)val;
 
@@ -661,8 +809,9 @@ int hvo_orb::init() {
     // ---- level geometry ----
     std::memset(&g, 0, sizeof(g));
     g.nlevels = n; g.width = width; g.height = height;
-    long long off = 0;
+    long long off = 0, boff = 0;
     int cand_off = 0, kp_off = 0;
+    std::vector<TileDesc> btiles;
     std::vector<CellDesc> cells;
     max_zw = max_zh = max_quota = 0;
     for (int l = 0; l < n; ++l) {
@@ -678,6 +827,9 @@ int hvo_orb::init() {
         L.kp_size = (float)(int)(31 * sf[l]);
         const float fw = (float)(L.maxBX - L.minBX), fh = (float)(L.maxBY - L.minBY);
         L.nCols = (int)(fw / 30.f); L.nRows = (int)(fh / 30.f);
+        L.bpitch = (int)align_up((size_t)L.w, 128); L.blur_off = boff; boff += (long long)L.bpitch * L.h;
+        for (int yy = 0; yy < L.h; yy += kBlH)
+            for (int xx = 0; xx < L.w; xx += kBlW) { TileDesc t; t.level = (short)l; t.tx = (short)xx; t.ty = (short)yy; t.pad = 0; btiles.push_back(t); }
         L.cand_off = cand_off; L.cand_cap = 0;
         L.kp_off = kp_off; L.kp_cap = L.quota + 4;
         kp_off += L.kp_cap;
@@ -714,6 +866,8 @@ int hvo_orb::init() {
     }
     if (max_quota + 8 > 16383) { set_error("nfeatures too large"); return HVO_ERR_ARG; }
     g.pyr_frame_bytes = (long long)align_up((size_t)off, 256);
+    g.blur_frame_bytes = (long long)align_up((size_t)boff, 256);
+    nbtiles = (int)btiles.size();
     g.cand_total = std::max(cand_off, 1);
     g.kp_total = kp_off;
     g.out_cap = kp_off;
@@ -726,6 +880,9 @@ int hvo_orb::init() {
     for (auto& e : tev) HVO_CUDA(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch;
     HVO_CUDA(cudaMalloc(&d_pyr, std::max<size_t>(B * (size_t)g.pyr_frame_bytes, 256)));
+    HVO_CUDA(cudaMalloc(&d_blur, B * (size_t)g.blur_frame_bytes));
+    HVO_CUDA(cudaMalloc(&d_btiles, btiles.size() * sizeof(TileDesc)));
+    HVO_CUDA(cudaMemcpy(d_btiles, btiles.data(), btiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
     HVO_CUDA(cudaMalloc(&d_cand, B * g.cand_total * sizeof(uint32_t)));
     HVO_CUDA(cudaMalloc(&d_knode, B * g.cand_total * sizeof(uint16_t)));
     HVO_CUDA(cudaMalloc(&d_ncand, B * n * sizeof(int)));
@@ -785,7 +942,7 @@ int hvo_orb::init() {
 void hvo_orb::release() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    void* bufs[] = {d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_cells, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
+    void* bufs[] = {d_blur, d_btiles, d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_cells, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
                     d_kps, d_desc, d_counts, d_kpdepth, d_kpuright};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -809,8 +966,8 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
         const LevelGeom& D = g.lv[l];
         const uint8_t* sp = l == 1 ? d_gray : d_pyr + S.img_off;
         const long long sframe = l == 1 ? src.l0_frame : g.pyr_frame_bytes;
-        dim3 blk(32, 8), grd(div_up(div_up(D.w, 4), 32), div_up(D.h, 8), B);
-        k_resize<<<grd, blk, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
+        dim3 grd(div_up(D.w, kRsW), div_up(D.h, kRsH), B);
+        k_resize<<<grd, 256, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
                                           d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
         ++launches;
     }
@@ -825,13 +982,16 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     k_octree<<<dim3(n, B), 256, oct_smem, stream>>>(g, d_cand, d_ncand, d_knode, d_okp, d_on, max_quota + 8, d_err);
     ++launches;
     if (profiling) HVO_CUDA(cudaEventRecord(ev[3], stream));
-    // K4: describe
+    // K4: blur of every level, K5: describe
+    k_blur<<<dim3(nbtiles, B), 256, 0, stream>>>(g, src, d_btiles, d_blur);
+    ++launches;
+    if (profiling) HVO_CUDA(cudaEventRecord(ev[4], stream));
     const bool rgbd_on = d_depth16 != nullptr && rgbd != nullptr && d_kp_depth != nullptr && d_kp_uright != nullptr;
     k_describe<<<dim3(div_up(g.out_cap, kDescWarps), B), kDescWarps * 32, 0, stream>>>(
-        g, src, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
+        g, src, d_blur, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
         rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, d_kp_depth, d_kp_uright);
     ++launches;
-    if (profiling) { HVO_CUDA(cudaEventRecord(ev[4], stream)); have_stage_times = true; }
+    if (profiling) { HVO_CUDA(cudaEventRecord(ev[5], stream)); have_stage_times = true; }
     HVO_CUDA(cudaGetLastError());
     last_launches = launches;
     return HVO_OK;

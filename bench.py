@@ -35,7 +35,7 @@ METRIC = 'front-end frames/s @640x480'
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
 DEPTH_FACTOR, BF = 1.0 / 5000.0, 40.0
 # algorithmic bytes per 640x480 frame (SURVEY.md section 8d / BASELINE.md section 5)
-BYTES_PYRAMID, BYTES_FAST, BYTES_DESCRIBE_PATCH, BYTES_OUT = 1569878, 950532, 1922000, 60000
+BYTES_PYRAMID, BYTES_FAST, BYTES_BLUR, BYTES_DESCRIBE_PATCH, BYTES_OUT = 1569878, 950532, 1901064, 1922000, 60000
 
 
 def _gen(args):
@@ -256,7 +256,7 @@ def main():
 
     # ---- per-stage device times (separate, profiled pass; events between stages) ----
     ex.set_profiling(True)
-    stage = {k: 0.0 for k in ('pyramid', 'fast', 'octree', 'describe')}
+    stage = {k: 0.0 for k in ('pyramid', 'fast', 'octree', 'blur', 'describe')}
     reps = 5
     for _ in range(reps):
         step_device()
@@ -264,11 +264,11 @@ def main():
         for k, v in ex.stage_times().items():
             stage[k] += v / reps
     ex.set_profiling(False)
-    alg = {'pyramid': BYTES_PYRAMID, 'fast': BYTES_FAST, 'describe': BYTES_DESCRIBE_PATCH + BYTES_OUT}
-    dom = max(('pyramid', 'fast', 'describe'), key=lambda k: stage[k])
+    alg = {'pyramid': BYTES_PYRAMID, 'fast': BYTES_FAST, 'blur': BYTES_BLUR, 'describe': BYTES_DESCRIBE_PATCH + BYTES_OUT}
+    dom = max(('pyramid', 'fast', 'blur', 'describe'), key=lambda k: stage[k])
     peak, peak_src = measured_peak()
     achieved = alg[dom] * B / (stage[dom] * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel={'pyramid': 'k_resize x7', 'fast': 'k_fast_cells', 'describe': 'k_describe'}[dom],
+    roofline = dict(bound='hbm', kernel={'pyramid': 'k_resize x7', 'fast': 'k_fast_cells', 'blur': 'k_blur', 'describe': 'k_describe'}[dom],
                     achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg[dom] * B,
                     stage_ms={k: round(v, 4) for k, v in stage.items()},

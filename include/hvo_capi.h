@@ -97,9 +97,9 @@ int hvo_orb_sync(hvo_orb* h);
 int hvo_orb_timer_start(hvo_orb* h);
 int hvo_orb_timer_stop(hvo_orb* h, float* ms_out); /* synchronises */
 /* Per-stage device time of the last *_batch call made with profiling enabled (ms): pyramid, fast, octree,
- * describe.  Enabling inserts events between stages; leave off for throughput runs. */
+ * blur, describe.  Enabling inserts events between stages; leave off for throughput runs. */
 int hvo_orb_set_profiling(hvo_orb* h, int enable);
-int hvo_orb_stage_times(hvo_orb* h, float* ms4);
+int hvo_orb_stage_times(hvo_orb* h, float* ms5);
 /* Number of kernel launches issued by the last extract call. */
 int hvo_orb_last_launches(const hvo_orb* h);
 
