@@ -63,6 +63,14 @@ ABI = {
     'hvo_orb_level_size': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_orb_get_pyramid_level': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t]),
     'hvo_orb_get_candidates': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_matcher_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    'hvo_matcher_destroy': (None, [_vp]),
+    'hvo_hamming_distance': (C.c_int, [_vp, _vp]),
+    'hvo_match_knn2': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    'hvo_match_knn2_device': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    'hvo_matcher_sync': (C.c_int, [_vp]),
+    'hvo_matcher_timer_start': (C.c_int, [_vp]),
+    'hvo_matcher_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 
@@ -261,3 +269,95 @@ class ORBextractor:
         n = C.c_int(0)
         _check(lib().hvo_orb_get_candidates(self._h, frame, level, _np_ptr(out), cap, C.byref(n)))
         return out[:min(n.value, cap)].copy()
+
+
+class BFMatcherHamming:
+    """cv::BFMatcher(NORM_HAMMING, crossCheck=false).knnMatch(k=2) on the GPU (hvo_match_knn2)."""
+
+    def __init__(self, device=0):
+        out = _vp()
+        _check(lib().hvo_matcher_create(int(device), C.byref(out)))
+        self._h = out
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def knnMatch2(self, desc1, desc2):
+        """(idx [n1,2] int32, dist [n1,2] int32); ties resolve to the lower train index; -1 where desc2 has < 2 rows."""
+        q = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        idx = np.empty((len(q), 2), np.int32)
+        dist = np.empty((len(q), 2), np.int32)
+        _check(lib().hvo_match_knn2(self._h, _np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(idx), _np_ptr(dist)))
+        return idx, dist
+
+    def knn2_device(self, d_q, nq, d_t, nt, d_idx, d_dist):
+        _check(lib().hvo_match_knn2_device(self._h, _vp(d_q), nq, _vp(d_t), nt, _vp(d_idx), _vp(d_dist)))
+
+    def sync(self):
+        _check(lib().hvo_matcher_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_matcher_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_matcher_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
+class LSDmatcher:
+    """Mirror of the brute-force part of ORB_SLAM2::LSDmatcher (reference include/LSDmatcher.h:23-60):
+    match / matchNNR (src/LSDmatcher.cpp:803-863), FrameBFMatch + lineDescriptorMAD (:942-966, :1110-1135),
+    DescriptorDistance (:1137-1153).  Distances run on the GPU; the ratio / MAD filters are the reference's
+    float arithmetic on the host."""
+    TH_HIGH, TH_LOW = 80, 50
+
+    def __init__(self, nnratio=0.95, checkOri=True, device=0):
+        self.mfNNratio = np.float32(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._bf = BFMatcherHamming(device)
+
+    def close(self):
+        self._bf.close()
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return int(lib().hvo_hamming_distance(_np_ptr(a), _np_ptr(b)))
+
+    def matchNNR(self, desc1, desc2, nnr):
+        """returns (number of matches, matches_12) with matches_12[i] = train index or -1."""
+        if len(desc2) < 2:
+            raise HvoError(HVO_ERR_ARG, 'matchNNR needs at least two train descriptors (the reference reads matches_[idx][1])')
+        idx, dist = self._bf.knnMatch2(desc1, desc2)
+        ok = dist[:, 0].astype(np.float32) < dist[:, 1].astype(np.float32) * np.float32(nnr)
+        m = np.where(ok, idx[:, 0], -1).astype(np.int32)
+        return int(ok.sum()), m
+
+    def match(self, desc1, desc2, nnr):
+        return self.matchNNR(desc1, desc2, nnr)  # the two-way branch is disabled in the reference (`if (false)`)
+
+    def FrameBFMatch(self, ldesc1, ldesc2, TH):
+        n = len(ldesc1)
+        out = np.full(n, -1, np.int32)
+        if n == 0:
+            return out
+        idx, dist = self._bf.knnMatch2(ldesc1, ldesc2)
+        d0, d1 = dist[:, 0].astype(np.float32), dist[:, 1].astype(np.float32)
+        gap = d1 - d0
+        med = np.float64(np.sort(gap)[::-1][n // 2])
+        dev = np.abs((gap.astype(np.float64) - med).astype(np.float32))
+        nn12_th = 1.4826 * np.float64(np.sort(dev)[n // 2]) * 0.5
+        ok = (gap.astype(np.float64) > nn12_th) & (d0 < np.float32(TH)) & (d0 < self.mfNNratio * d1)
+        out[ok] = idx[ok, 0]
+        return out

@@ -111,6 +111,31 @@ int hvo_orb_get_pyramid_level(hvo_orb* h, int frame, int level, uint8_t* out, si
  * xys = [cap][3] int32 (x, y in level coordinates, score). */
 int hvo_orb_get_candidates(hvo_orb* h, int frame, int level, int32_t* xys, int cap, int* n_out);
 
+/* ---------------------------------------------------------------------------------------------- MATCH
+ * Brute-force Hamming matching of 256-bit descriptors (rows of 32 bytes, ORB and LBD alike).          */
+
+typedef struct hvo_matcher hvo_matcher;
+int hvo_matcher_create(int device, hvo_matcher** out);
+void hvo_matcher_destroy(hvo_matcher* m);
+
+/* int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&)   src/ORBmatcher.cc:1676-1692
+ * int LSDmatcher::DescriptorDistance(const Mat&, const Mat&)           src/LSDmatcher.cpp:1137-1153
+ * (host helper: one pair is not worth a launch; the kernels below use the same 8 x popc32) */
+int hvo_hamming_distance(const uint8_t* a, const uint8_t* b);
+
+/* cv::BFMatcher(NORM_HAMMING, false).knnMatch(desc1, desc2, matches, 2) as used by LSDmatcher::matchNNR
+ * (src/LSDmatcher.cpp:811-812) and FrameBFMatch (:948-949).  For query i: idx2[2i], idx2[2i+1] are the train
+ * indices of the nearest and second nearest descriptor (ties: lower train index first), dist2 the integer
+ * Hamming distances (cv::DMatch::distance is this integer as a float); -1 where the train set is too small.
+ * q, t: host arrays of nq / nt rows of 32 bytes. */
+int hvo_match_knn2(hvo_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2);
+/* Same with 16-byte aligned device pointers; asynchronous on the matcher's stream. */
+int hvo_match_knn2_device(hvo_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx2,
+                          int32_t* d_dist2);
+int hvo_matcher_sync(hvo_matcher* m);
+int hvo_matcher_timer_start(hvo_matcher* m);
+int hvo_matcher_timer_stop(hvo_matcher* m, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

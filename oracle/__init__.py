@@ -202,3 +202,31 @@ def ref_orb_extract(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=
         off += 32 * k
         out.append((kps, desc))
     return out
+
+
+# ---- matching ------------------------------------------------------------------------------------------
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orc_hamming(_p(a), _p(b)))
+
+
+def knn2(q, t):
+    """BFMatcher(NORM_HAMMING).knnMatch(k=2): (idx [nq,2], dist [nq,2]) with ties -> lower train index."""
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
+    lib().orc_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def match_nnr(q, t, nnr):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    m = np.empty(len(q), np.int32)
+    n = lib().orc_match_nnr(_p(q), len(q), _p(t), len(t), C.c_float(nnr), _p(m))
+    return int(n), m
+
+
+def frame_bf_match(q, t, nnratio, TH):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    m = np.empty(len(q), np.int32)
+    lib().orc_frame_bf_match(_p(q), len(q), _p(t), len(t), C.c_float(nnratio), C.c_float(TH), _p(m))
+    return m
