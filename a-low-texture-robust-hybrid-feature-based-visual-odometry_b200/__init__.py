@@ -71,6 +71,15 @@ ABI = {
     'hvo_matcher_sync': (C.c_int, [_vp]),
     'hvo_matcher_timer_start': (C.c_int, [_vp]),
     'hvo_matcher_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_lbd_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_lbd_destroy': (None, [_vp]),
+    'hvo_lbd_compute': (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
+    'hvo_lbd_compute_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'hvo_lbd_compute_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    'hvo_lbd_get_gradients': (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    'hvo_lbd_sync': (C.c_int, [_vp]),
+    'hvo_lbd_timer_start': (C.c_int, [_vp]),
+    'hvo_lbd_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 
@@ -269,6 +278,77 @@ class ORBextractor:
         n = C.c_int(0)
         _check(lib().hvo_orb_get_candidates(self._h, frame, level, _np_ptr(out), cap, C.byref(n)))
         return out[:min(n.value, cap)].copy()
+
+
+KL_DTYPE = np.dtype([('angle', '<f4'), ('class_id', '<i4'), ('octave', '<i4'), ('pt_x', '<f4'), ('pt_y', '<f4'),
+                     ('response', '<f4'), ('size', '<f4'), ('startPointX', '<f4'), ('startPointY', '<f4'),
+                     ('endPointX', '<f4'), ('endPointY', '<f4'), ('sPointInOctaveX', '<f4'), ('sPointInOctaveY', '<f4'),
+                     ('ePointInOctaveX', '<f4'), ('ePointInOctaveY', '<f4'), ('lineLength', '<f4'), ('numOfPixels', '<i4')])
+
+
+class BinaryDescriptor:
+    """Mirror of cv::line_descriptor::BinaryDescriptor::compute(image, keylines, descriptors) (LBD) as the
+    reference calls it (src/LineExtractor.cpp:361-363, src/Frame.cc:1094-1096)."""
+
+    def __init__(self, width, height, max_lines=512, max_batch=1, device=0):
+        out = _vp()
+        _check(lib().hvo_lbd_create(int(width), int(height), int(max_batch), int(max_lines), int(device), C.byref(out)))
+        self._h, self.w, self.h, self.max_lines, self.max_batch = out, int(width), int(height), int(max_lines), int(max_batch)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_lbd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, image, keylines):
+        """descriptors [n,32] uint8.  An empty keyline list returns an empty matrix (the reference prints
+        'keypoint list is empty' and leaves the output untouched)."""
+        kl = np.ascontiguousarray(keylines, KL_DTYPE)
+        if image.dtype != np.uint8 or image.ndim != 2 or image.shape != (self.h, self.w):
+            raise HvoError(HVO_ERR_ARG, 'image must be 8-bit single channel of the size given at construction')
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        desc = np.empty((len(kl), 32), np.uint8)
+        _check(lib().hvo_lbd_compute(self._h, _vp(image.ctypes.data), image.strides[0], _np_ptr(kl), len(kl), _np_ptr(desc)))
+        return desc
+
+    def compute_batch(self, frames, keylines, counts, want_float=False):
+        """frames [n,h,w]; keylines [n,max_lines] KL_DTYPE; counts [n] -> desc [n,max_lines,32] (+ float [n,max_lines,72])."""
+        n = len(frames)
+        frames = np.ascontiguousarray(frames, np.uint8)
+        kl = np.ascontiguousarray(keylines, KL_DTYPE).reshape(n, self.max_lines)
+        counts = np.ascontiguousarray(counts, np.int32)
+        desc = np.empty((n, self.max_lines, 32), np.uint8)
+        fdesc = np.empty((n, self.max_lines, 72), np.float32) if want_float else None
+        _check(lib().hvo_lbd_compute_batch(self._h, _np_ptr(frames), n, _np_ptr(kl), _np_ptr(counts), _np_ptr(desc),
+                                           _np_ptr(fdesc) if want_float else None))
+        return (desc, fdesc) if want_float else desc
+
+    def compute_batch_device(self, d_gray, nframes, d_keylines, d_counts, d_desc):
+        _check(lib().hvo_lbd_compute_batch_device(self._h, _vp(d_gray), nframes, _vp(d_keylines), _vp(d_counts), _vp(d_desc)))
+
+    def gradients(self, frame=0):
+        dx = np.empty((self.h, self.w), np.int16)
+        dy = np.empty((self.h, self.w), np.int16)
+        _check(lib().hvo_lbd_get_gradients(self._h, frame, _np_ptr(dx), _np_ptr(dy)))
+        return dx, dy
+
+    def sync(self):
+        _check(lib().hvo_lbd_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_lbd_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_lbd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
 
 class BFMatcherHamming:

@@ -136,6 +136,41 @@ int hvo_matcher_sync(hvo_matcher* m);
 int hvo_matcher_timer_start(hvo_matcher* m);
 int hvo_matcher_timer_stop(hvo_matcher* m, float* ms_out);
 
+/* ------------------------------------------------------------------------------------------------ LBD
+ * Replaces cv::line_descriptor::BinaryDescriptor::compute(image, keylines, descriptors) as called at
+ * src/LineExtractor.cpp:361-363 and src/Frame.cc:1094-1096 (vendored algorithm:
+ * Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:539-687, 1026-1372).  Single octave
+ * (LINE.nLevels = 1 in every shipped YAML); keylines must carry octave 0 and distinct class_id, as
+ * LINEextractor::operator() and Frame::cullingLine produce them.                                       */
+
+/* cv::line_descriptor::KeyLine POD layout (68 bytes), descriptor_custom.hpp:105-144 */
+typedef struct hvo_keyline {
+    float angle;
+    int32_t class_id, octave;
+    float pt_x, pt_y, response, size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength;
+    int32_t numOfPixels;
+} hvo_keyline;
+
+typedef struct hvo_lbd hvo_lbd;
+int hvo_lbd_create(int width, int height, int max_batch, int max_lines, int device, hvo_lbd** out);
+void hvo_lbd_destroy(hvo_lbd* h);
+/* One image: desc = n x 32 bytes.  n == 0 mirrors the reference's "keypoint list is empty" early return. */
+int hvo_lbd_compute(hvo_lbd* h, const uint8_t* gray, size_t stride, const hvo_keyline* keylines, int n, uint8_t* desc);
+/* Batch: gray [n][H][W], keylines [n][max_lines], counts [n], desc [n][max_lines][32]; fdesc (optional)
+ * [n][max_lines][72] = the normalised float LBD before binarisation. */
+int hvo_lbd_compute_batch(hvo_lbd* h, const uint8_t* gray, int nframes, const hvo_keyline* keylines, const int32_t* counts,
+                          uint8_t* desc, float* fdesc);
+int hvo_lbd_compute_batch_device(hvo_lbd* h, const uint8_t* d_gray, int nframes, const hvo_keyline* d_keylines,
+                                 const int32_t* d_counts, uint8_t* d_desc);
+/* dxImg / dyImg of BinaryDescriptor::computeSobel (:377-398) for a frame of the last call: H x W int16 each */
+int hvo_lbd_get_gradients(hvo_lbd* h, int frame, int16_t* dx, int16_t* dy);
+int hvo_lbd_sync(hvo_lbd* h);
+int hvo_lbd_timer_start(hvo_lbd* h);
+int hvo_lbd_timer_stop(hvo_lbd* h, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -230,3 +230,35 @@ def frame_bf_match(q, t, nnratio, TH):
     m = np.empty(len(q), np.int32)
     lib().orc_frame_bf_match(_p(q), len(q), _p(t), len(t), C.c_float(nnratio), C.c_float(TH), _p(m))
     return m
+
+
+# ---- lines: LSD wrapper fields + LBD ---------------------------------------------------------------------
+KL_DTYPE = np.dtype([('angle', '<f4'), ('class_id', '<i4'), ('octave', '<i4'), ('pt_x', '<f4'), ('pt_y', '<f4'),
+                     ('response', '<f4'), ('size', '<f4'), ('startPointX', '<f4'), ('startPointY', '<f4'),
+                     ('endPointX', '<f4'), ('endPointY', '<f4'), ('sPointInOctaveX', '<f4'), ('sPointInOctaveY', '<f4'),
+                     ('ePointInOctaveX', '<f4'), ('ePointInOctaveY', '<f4'), ('lineLength', '<f4'), ('numOfPixels', '<i4')])
+assert KL_DTYPE.itemsize == 68
+
+
+def keylines_from_segments(seg, w, h):
+    """LSDDetector::detectImpl keyline fields (single octave) from [n,4] float32 segments x1,y1,x2,y2."""
+    seg = np.ascontiguousarray(seg, np.float32).reshape(-1, 4)
+    out = np.empty(len(seg), KL_DTYPE)
+    lib().orc_keylines_from_segments(_p(seg), len(seg), w, h, _p(out))
+    return out
+
+
+def lbd_gradients(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    dx = np.empty(gray.shape, np.int16); dy = np.empty(gray.shape, np.int16)
+    lib().orc_lbd_gradients(_p(gray), gray.shape[1], gray.shape[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def lbd_compute(gray, keylines, want_float=False):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    kl = np.ascontiguousarray(keylines, KL_DTYPE)
+    desc = np.empty((len(kl), 32), np.uint8)
+    fdesc = np.empty((len(kl), 72), np.float32) if want_float else None
+    lib().orc_lbd_compute(_p(gray), gray.shape[1], gray.shape[0], _p(kl), len(kl), _p(desc), _p(fdesc) if want_float else None)
+    return (desc, fdesc) if want_float else desc
