@@ -80,6 +80,15 @@ ABI = {
     'hvo_lbd_sync': (C.c_int, [_vp]),
     'hvo_lbd_timer_start': (C.c_int, [_vp]),
     'hvo_lbd_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_plane_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_plane_destroy': (None, [_vp]),
+    'hvo_plane_detect': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'hvo_plane_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'hvo_plane_blocks_device': (C.c_int, [_vp, _vp, C.c_int]),
+    'hvo_plane_get_blocks': (C.c_int, [_vp, C.c_int, _vp]),
+    'hvo_plane_sync': (C.c_int, [_vp]),
+    'hvo_plane_timer_start': (C.c_int, [_vp]),
+    'hvo_plane_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 
@@ -348,6 +357,93 @@ class BinaryDescriptor:
     def timer_stop(self):
         ms = C.c_float(0)
         _check(lib().hvo_lbd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
+class _PlaneParams(C.Structure):
+    _fields_ = [('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('depth_factor', C.c_float)]
+
+
+class PlaneDetection:
+    """Mirror of the reference's PlaneDetection (include/PlaneExtractor.h:36-56): readDepthImage(depth16U, K, factor)
+    followed by runPlaneDetection(H, W); results as plane_num_, plane normals/centers, plane_vertices_, membership."""
+    MAX_PLANES = 64
+
+    def __init__(self, width, height, max_batch=1, device=0):
+        self.w, self.h, self.max_batch, self.device = int(width), int(height), int(max_batch), int(device)
+        self._h = None
+        self._depth = None
+        self.plane_num_ = 0
+        self.plane_vertices_ = []
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_plane_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def readDepthImage(self, depthImg, K, kScaleFactor):
+        """K: 3x3 (only fx, fy, cx, cy are read, as float32).  Returns False on a non-16U image, as the reference."""
+        if depthImg is None or depthImg.size == 0 or depthImg.dtype != np.uint16:
+            print('WARNING: cannot read depth image. No such a file, or the image format is not 16UC1')
+            return False
+        K = np.asarray(K, np.float32)
+        params = _PlaneParams(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), float(np.float32(kScaleFactor)))
+        key = (params.fx, params.fy, params.cx, params.cy, params.depth_factor)
+        if self._h is None or getattr(self, '_key', None) != key:
+            self.close()
+            out = _vp()
+            _check(lib().hvo_plane_create(C.byref(params), self.w, self.h, self.max_batch, self.device, C.byref(out)))
+            self._h, self._key = out, key
+        self._depth = np.ascontiguousarray(depthImg)
+        return True
+
+    def runPlaneDetection(self, kDepthHeight=None, kDepthWidth=None):
+        assert self._depth is not None and self._depth.shape == (self.h, self.w)
+        n = np.zeros(1, np.int32)
+        planes = np.zeros((self.MAX_PLANES, 7), np.float64)
+        self.membership = np.empty(self.h * self.w, np.int32)
+        _check(lib().hvo_plane_detect(self._h, _np_ptr(self._depth), _np_ptr(n), _np_ptr(planes), self.MAX_PLANES, _np_ptr(self.membership)))
+        self.plane_num_ = int(n[0])
+        self.normals = planes[:self.plane_num_, 0:3].copy()
+        self.centers = planes[:self.plane_num_, 3:6].copy()
+        self.supports = planes[:self.plane_num_, 6].astype(np.int64)
+        self.plane_vertices_ = [np.nonzero(self.membership == i)[0] for i in range(self.plane_num_)]
+        return self.plane_num_
+
+    def detect_batch(self, depths):
+        """depths [n,h,w] uint16 -> (n_planes [n], planes [n,MAX,7], membership [n,h*w])"""
+        depths = np.ascontiguousarray(depths, np.uint16)
+        nf = len(depths)
+        n = np.zeros(nf, np.int32)
+        planes = np.zeros((nf, self.MAX_PLANES, 7), np.float64)
+        mem = np.empty((nf, self.h * self.w), np.int32)
+        _check(lib().hvo_plane_detect_batch(self._h, _np_ptr(depths), nf, _np_ptr(n), _np_ptr(planes), self.MAX_PLANES, _np_ptr(mem)))
+        return n, planes, mem
+
+    def blocks(self, frame=0):
+        """initial graph nodes of the last call: [Nh*Nw, 9] = queued, N, center(3), normal(3), mse"""
+        out = np.empty(((self.h // 10) * (self.w // 10), 9), np.float64)
+        _check(lib().hvo_plane_get_blocks(self._h, frame, _np_ptr(out)))
+        return out
+
+    def blocks_device(self, d_depth, nframes):
+        _check(lib().hvo_plane_blocks_device(self._h, _vp(d_depth), nframes))
+
+    def sync(self):
+        _check(lib().hvo_plane_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_plane_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_plane_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
 

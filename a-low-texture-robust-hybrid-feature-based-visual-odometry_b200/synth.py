@@ -6,7 +6,7 @@ S3  RealSense-shaped 1280x720, 2000 ORB
 S4  matching stress descriptors (2000 x 50 000 ORB, 200 x 5 000 LBD)
 
 Every frame is a ray-cast box room (floor, ceiling, two side walls, back wall) seen from a camera on a
-smooth path; frame i of a sequence uses seed 1000+i for its pixel noise and depth holes, so the same
+smooth path; frame i of a sequence uses seed 1000+i for its pixel noise and (clustered) depth holes, so the same
 (config, index) always yields the same bytes on every machine.
 """
 import numpy as np
@@ -102,9 +102,17 @@ def frame(config='S1', index=0):
     gray = gray * shade + r.randn(h, w).astype(np.float32) * 2.0
     gray = np.clip(_blur3(gray) + 0.5, 0, 255).astype(np.uint8)
     z = best_t  # camera-frame ray has unit z, so depth == ray parameter
+    # structured-light style depth: disparity (fb / z, fb = 42.75 m px) with Gaussian noise, quantised to 1/8 px
+    with np.errstate(divide='ignore', invalid='ignore'):
+        disp = 42.75 / z + r.randn(h, w) * 0.06
+        z = 42.75 / (np.round(disp * 8.0) / 8.0)
     raw = np.floor(z * c['factor'] + 0.5)
     raw = np.where(np.isfinite(raw) & (raw < 65535), raw, 0).astype(np.uint16)
-    raw[r.rand(h, w) < 0.01] = 0  # 1 % holes
+    # ~1 % holes, clustered as on a real structured-light sensor (blobs), not i.i.d. pixels
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(max(8, (w * h) // 12000)):
+        cxh, cyh, rad = r.randint(0, w), r.randint(0, h), r.randint(2, 9)
+        raw[(xx - cxh) ** 2 + (yy - cyh) ** 2 <= rad * rad] = 0
     return gray, raw
 
 

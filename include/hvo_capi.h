@@ -171,6 +171,35 @@ int hvo_lbd_sync(hvo_lbd* h);
 int hvo_lbd_timer_start(hvo_lbd* h);
 int hvo_lbd_timer_stop(hvo_lbd* h, float* ms_out);
 
+/* ---------------------------------------------------------------------------------------------- PLANE
+ * Replaces PlaneDetection::readDepthImage(depth16U, K, factor) + runPlaneDetection(H, W)
+ * (src/PlaneExtractor.cpp:26-66, include/PlaneExtractor.h:36-56) and the ahc::PlaneFitter behind them
+ * (include/peac/).  Results correspond to plane_num_, plane_filter.extractedPlanes[i]->normal/center and the
+ * pixel membership from which plane_vertices_ is listed (ascending pixel index per plane).                */
+
+typedef struct hvo_plane_params {
+    float fx, fy, cx, cy; /* K as read by readDepthImage (K.at<float>) */
+    float depth_factor;   /* kScaleFactor = 1 / DepthMapFactor */
+} hvo_plane_params;
+
+typedef struct hvo_plane hvo_plane;
+int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_batch, int device, hvo_plane** out);
+void hvo_plane_destroy(hvo_plane* h);
+/* depth16: host [H][W] uint16.  planes7: [max_planes][7] doubles = normal(3), center(3), N.  membership: [H*W]
+ * int32 = plane id or -1.  *n_planes may exceed max_planes (only the first max_planes are written). */
+int hvo_plane_detect(hvo_plane* h, const uint16_t* depth16, int32_t* n_planes, double* planes7, int max_planes,
+                     int32_t* membership);
+int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, int32_t* n_planes, double* planes7,
+                           int max_planes, int32_t* membership);
+/* Device leg only (initial graph nodes, AHCPlaneFitter.hpp:786-826 / AHCPlaneSeg.hpp:211-284) on device-resident
+ * depth; asynchronous.  hvo_plane_get_blocks copies one frame's result: per 10x10 block 9 doubles =
+ * {queued, N, center(3), normal(3), mse}. */
+int hvo_plane_blocks_device(hvo_plane* h, const uint16_t* d_depth16, int nframes);
+int hvo_plane_get_blocks(hvo_plane* h, int frame, double* out9);
+int hvo_plane_sync(hvo_plane* h);
+int hvo_plane_timer_start(hvo_plane* h);
+int hvo_plane_timer_stop(hvo_plane* h, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

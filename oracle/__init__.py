@@ -262,3 +262,30 @@ def lbd_compute(gray, keylines, want_float=False):
     fdesc = np.empty((len(kl), 72), np.float32) if want_float else None
     lib().orc_lbd_compute(_p(gray), gray.shape[1], gray.shape[0], _p(kl), len(kl), _p(desc), _p(fdesc) if want_float else None)
     return (desc, fdesc) if want_float else desc
+
+
+# ---- planes (PEAC) ----------------------------------------------------------------------------------------
+def plane_blocks(depth16, factor, fx, fy, cx, cy):
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    out = np.empty(((h // 10) * (w // 10), 9), np.float64)
+    lib().orc_plane_blocks(_p(d), w, h, C.c_float(factor), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(out))
+    return out
+
+
+def plane_detect(depth16, factor, fx, fy, cx, cy, max_planes=64):
+    """(n_planes, planes [n,7] = normal, center, N, membership [h*w])"""
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    planes = np.zeros((max_planes, 7), np.float64)
+    mem = np.empty(h * w, np.int32)
+    n = lib().orc_plane_detect(_p(d), w, h, C.c_float(factor), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                               _p(planes), max_planes, _p(mem))
+    return int(n), planes[:n].copy(), mem
+
+
+def eig33sym(K):
+    K = np.ascontiguousarray(K, np.float64)
+    s = np.empty(3, np.float64); V = np.empty((3, 3), np.float64)
+    lib().orc_eig33sym(_p(K), _p(s), _p(V))
+    return s, V
