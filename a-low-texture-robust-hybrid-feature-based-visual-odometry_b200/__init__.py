@@ -89,6 +89,15 @@ ABI = {
     'hvo_plane_sync': (C.c_int, [_vp]),
     'hvo_plane_timer_start': (C.c_int, [_vp]),
     'hvo_plane_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_normals_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_normals_destroy': (None, [_vp]),
+    'hvo_normals_count': (C.c_int, [_vp]),
+    'hvo_normals_compute_batch': (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    'hvo_normals_compute_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    'hvo_normals_get_distance_map': (C.c_int, [_vp, C.c_int, _vp]),
+    'hvo_normals_sync': (C.c_int, [_vp]),
+    'hvo_normals_timer_start': (C.c_int, [_vp]),
+    'hvo_normals_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 
@@ -444,6 +453,62 @@ class PlaneDetection:
     def timer_stop(self):
         ms = C.c_float(0)
         _check(lib().hvo_plane_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
+class _NormalsParams(C.Structure):
+    _fields_ = [('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('depth_factor', C.c_float),
+                ('max_depth_change_factor', C.c_float), ('normal_smoothing_size', C.c_float)]
+
+
+class SurfaceNormals:
+    """The surface-normal block of Frame::ComputePlanes (reference src/Frame.cc:2155-2212): returns the
+    std::vector<SurfaceNormal> as an [n,8] float32 array = normal.xyz, cameraPosition.xyz, FramePosition.xy."""
+
+    def __init__(self, width, height, fx, fy, cx, cy, depth_factor, max_depth_change=0.05, smoothing=10.0, max_batch=1, device=0):
+        prm = _NormalsParams(fx, fy, cx, cy, float(np.float32(depth_factor)), max_depth_change, smoothing)
+        out = _vp()
+        _check(lib().hvo_normals_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
+        self._h, self.w, self.h = out, int(width), int(height)
+        self.count = lib().hvo_normals_count(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_normals_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, depth16):
+        d = np.ascontiguousarray(depth16, np.uint16)
+        batched = d.ndim == 3
+        d3 = d if batched else d[None]
+        out = np.empty((len(d3), self.count, 8), np.float32)
+        _check(lib().hvo_normals_compute_batch(self._h, _np_ptr(d3), len(d3), _np_ptr(out)))
+        return out if batched else out[0]
+
+    def compute_device(self, d_depth, nframes, d_out):
+        _check(lib().hvo_normals_compute_batch_device(self._h, _vp(d_depth), nframes, _vp(d_out)))
+
+    def distance_map(self, frame=0):
+        cw, ch = -(-self.w // 3), -(-self.h // 3)
+        out = np.empty((ch, cw), np.float32)
+        _check(lib().hvo_normals_get_distance_map(self._h, frame, _np_ptr(out)))
+        return out
+
+    def sync(self):
+        _check(lib().hvo_normals_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_normals_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_normals_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
 

@@ -200,6 +200,30 @@ int hvo_plane_sync(hvo_plane* h);
 int hvo_plane_timer_start(hvo_plane* h);
 int hvo_plane_timer_stop(hvo_plane* h, float* ms_out);
 
+/* -------------------------------------------------------------------------------------------- NORMALS
+ * Replaces the surface-normal block of Frame::ComputePlanes (src/Frame.cc:2155-2212): every 3rd pixel of the float
+ * depth image -> organised cloud -> pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT, MaxDepthChangeFactor
+ * 0.05, NormalSmoothingSize 10) -> entries at odd (row, col) -> std::vector<SurfaceNormal> (include/SurfaceNormal.h).
+ * One output entry = 8 floats: normal.xyz (NaN where PCL yields NaN), cameraPosition.xyz, FramePosition.x, .y.      */
+
+typedef struct hvo_normals_params {
+    float fx, fy, cx, cy;
+    float depth_factor;            /* metres per raw depth unit */
+    float max_depth_change_factor; /* ne.setMaxDepthChangeFactor(0.05f)  Frame.cc:2179 */
+    float normal_smoothing_size;   /* ne.setNormalSmoothingSize(10.0f)   Frame.cc:2180 */
+} hvo_normals_params;
+
+typedef struct hvo_normals hvo_normals;
+int hvo_normals_create(const hvo_normals_params* p, int width, int height, int max_batch, int device, hvo_normals** out);
+void hvo_normals_destroy(hvo_normals* h);
+int hvo_normals_count(const hvo_normals* h); /* entries per frame = (ceil(H/3)/2) * (ceil(W/3)/2) */
+int hvo_normals_compute_batch(hvo_normals* h, const uint16_t* depth16, int nframes, float* out8);
+int hvo_normals_compute_batch_device(hvo_normals* h, const uint16_t* d_depth16, int nframes, float* d_out8);
+int hvo_normals_get_distance_map(hvo_normals* h, int frame, float* out); /* ceil(H/3) x ceil(W/3) floats */
+int hvo_normals_sync(hvo_normals* h);
+int hvo_normals_timer_start(hvo_normals* h);
+int hvo_normals_timer_stop(hvo_normals* h, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

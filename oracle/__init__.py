@@ -289,3 +289,16 @@ def eig33sym(K):
     s = np.empty(3, np.float64); V = np.empty((3, 3), np.float64)
     lib().orc_eig33sym(_p(K), _p(s), _p(V))
     return s, V
+
+
+# ---- surface normals (PCL integral-image style, Frame.cc:2155-2212) -------------------------------------------
+def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    cw, ch = -(-w // 3), -(-h // 3)
+    out = np.empty(((ch // 2) * (cw // 2), 8), np.float32)
+    dist = np.empty((ch, cw), np.float32)
+    n = lib().orc_surface_normals(_p(d), w, h, C.c_float(factor), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                  C.c_float(max_depth_change), C.c_float(smoothing), _p(out), _p(dist))
+    assert n == len(out)
+    return (out, dist) if want_dist else out
