@@ -80,6 +80,23 @@ ABI = {
     'hvo_lbd_sync': (C.c_int, [_vp]),
     'hvo_lbd_timer_start': (C.c_int, [_vp]),
     'hvo_lbd_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_line_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_line_destroy': (None, [_vp]),
+    'hvo_line_max_lines': (C.c_int, [_vp]),
+    'hvo_line_segment_capacity': (C.c_int, [_vp]),
+    'hvo_line_scaled_size': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'hvo_line_extract': (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_line_extract_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'hvo_line_extract_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'hvo_line_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
+    'hvo_line_get_scaled': (C.c_int, [_vp, C.c_int, _vp]),
+    'hvo_line_get_seed_order': (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_line_set_profiling': (C.c_int, [_vp, C.c_int]),
+    'hvo_line_stage_times': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_line_last_launches': (C.c_int, [_vp]),
+    'hvo_line_sync': (C.c_int, [_vp]),
+    'hvo_line_timer_start': (C.c_int, [_vp]),
+    'hvo_line_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_plane_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'hvo_plane_destroy': (None, [_vp]),
     'hvo_plane_detect': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
@@ -366,6 +383,136 @@ class BinaryDescriptor:
     def timer_stop(self):
         ms = C.c_float(0)
         _check(lib().hvo_lbd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
+class _LineParams(C.Structure):
+    _fields_ = [('n_octaves', C.c_int), ('scale', C.c_float), ('n_features', C.c_int), ('min_line_length', C.c_double)]
+
+
+class LINEextractor:
+    """Mirror of ORB_SLAM2::LINEextractor (reference include/LineExtractor.h:187-262).
+
+        LINEextractor(numOctaves, scale, nLSDFeature, min_line_length)          LineExtractor.h:190
+        __call__(image, mask) -> (keylines, descriptors, lineVec2d)             LineExtractor.h:193, .cpp:329-380
+
+    keylines is a KL_DTYPE array (cv::line_descriptor::KeyLine POD), descriptors n x 32 uint8, lineVec2d n x 3 float64.
+    """
+
+    def __init__(self, numOctaves=1, scale=1.2, nLSDFeature=200, min_line_length=0.125, width=None, height=None, max_batch=1,
+                 device=0):
+        self.numOctaves, self.scale, self.nLSDFeature, self.min_line_length = int(numOctaves), float(scale), int(nLSDFeature), float(min_line_length)
+        self.max_batch, self.device = int(max_batch), int(device)
+        self._h = None
+        self.w = self.h = None
+        if width is not None:
+            self._create(int(width), int(height))
+
+    def _create(self, w, h):
+        self.close()
+        prm = _LineParams(self.numOctaves, self.scale, self.nLSDFeature, self.min_line_length)
+        out = _vp()
+        _check(lib().hvo_line_create(C.byref(prm), w, h, self.max_batch, self.device, C.byref(out)))
+        self._h, self.w, self.h = out, w, h
+        self.max_lines = lib().hvo_line_max_lines(out)
+        self.segment_capacity = lib().hvo_line_segment_capacity(out)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_line_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # getters of LineExtractor.h:239-261
+    def GetLevels(self):
+        return self.numOctaves
+
+    def GetScaleFactor(self):
+        return self.scale
+
+    def __call__(self, image, mask=None):
+        if image is None or image.size == 0:  # LineExtractor.cpp:331-332
+            return np.empty(0, KL_DTYPE), np.empty((0, 32), np.uint8), np.empty((0, 3), np.float64)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise HvoError(HVO_ERR_ARG, 'image must be 8-bit single channel (assert(image.type() == CV_8UC1))')
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        if self._h is None or (self.h, self.w) != image.shape:
+            self._create(image.shape[1], image.shape[0])
+        kl = np.empty(self.max_lines, KL_DTYPE)
+        desc = np.empty((self.max_lines, 32), np.uint8)
+        lv = np.empty((self.max_lines, 3), np.float64)
+        n = C.c_int(0)
+        _check(lib().hvo_line_extract(self._h, _vp(image.ctypes.data), image.strides[0], _np_ptr(kl), _np_ptr(desc), _np_ptr(lv),
+                                      self.max_lines, C.byref(n)))
+        return kl[:n.value].copy(), desc[:n.value].copy(), lv[:n.value].copy()
+
+    def extract_batch(self, frames, out=None):
+        """frames [n,h,w] uint8 -> dict(counts [n], keylines [n,max_lines], desc [n,max_lines,32], linevec [n,max_lines,3])"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = len(frames)
+        if out is None:
+            out = dict(counts=np.zeros(n, np.int32), keylines=np.empty((n, self.max_lines), KL_DTYPE),
+                       desc=np.empty((n, self.max_lines, 32), np.uint8), linevec=np.empty((n, self.max_lines, 3), np.float64))
+        _check(lib().hvo_line_extract_batch(self._h, _np_ptr(frames), n, _np_ptr(out['keylines']), _np_ptr(out['desc']),
+                                            _np_ptr(out['linevec']), _np_ptr(out['counts'])))
+        return out
+
+    def extract_batch_device(self, d_gray, nframes, d_keylines, d_desc, d_linevec, d_counts):
+        _check(lib().hvo_line_extract_batch_device(self._h, _vp(d_gray), nframes, _vp(d_keylines), _vp(d_desc), _vp(d_linevec), _vp(d_counts)))
+
+    def detect_segments(self, frames):
+        """cv::LineSegmentDetector::detect on each frame: list of [k,4] float32 arrays (x1,y1,x2,y2)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n = len(frames)
+        cap = self.segment_capacity
+        seg = np.empty((n, cap, 4), np.float32)
+        counts = np.zeros(n, np.int32)
+        _check(lib().hvo_line_detect_batch(self._h, _np_ptr(frames), n, _np_ptr(seg), cap, _np_ptr(counts)))
+        return [seg[i, :counts[i]].copy() for i in range(n)]
+
+    def scaled_image(self, frame=0):
+        sw, sh = C.c_int(0), C.c_int(0)
+        _check(lib().hvo_line_scaled_size(self._h, C.byref(sw), C.byref(sh)))
+        out = np.empty((sh.value, sw.value), np.uint8)
+        _check(lib().hvo_line_get_scaled(self._h, frame, _np_ptr(out)))
+        return out
+
+    def seed_order(self, frame=0):
+        sw, sh = C.c_int(0), C.c_int(0)
+        _check(lib().hvo_line_scaled_size(self._h, C.byref(sw), C.byref(sh)))
+        out = np.empty(sw.value * sh.value, np.uint32)
+        n = C.c_int(0)
+        _check(lib().hvo_line_get_seed_order(self._h, frame, _np_ptr(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_profiling(self, on):
+        _check(lib().hvo_line_set_profiling(self._h, int(bool(on))))
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        _check(lib().hvo_line_stage_times(self._h, ms))
+        return dict(prep=ms[0], order=ms[1], grow=ms[2], keylines_lbd=ms[3])
+
+    def last_launches(self):
+        return lib().hvo_line_last_launches(self._h)
+
+    def sync(self):
+        _check(lib().hvo_line_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_line_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_line_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
 

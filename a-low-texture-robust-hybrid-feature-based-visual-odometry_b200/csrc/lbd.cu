@@ -195,17 +195,29 @@ struct hvo_lbd {
     int last_launches = 0;
 };
 
-static int lbd_run(hvo_lbd* h, const uint8_t* d_gray, int nframes, const KeyLineDev* d_kl, const int32_t* d_counts, uint8_t* d_desc,
-                   float* d_fdesc) {
+static int lbd_run_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray, int nframes, const KeyLineDev* d_kl,
+                          const int32_t* d_counts, uint8_t* d_desc, float* d_fdesc) {
     const long long fpx = (long long)h->width * h->height;
-    k_lbd_grad<<<dim3(div_up(h->width, kGW), div_up(h->height, kGH), nframes), 256, 0, h->stream>>>(d_gray, h->width, h->height, fpx,
-                                                                                                 h->d_dx, h->d_dy);
-    k_lbd_describe<<<dim3(h->max_lines, nframes), 96, 0, h->stream>>>(h->d_dx, h->d_dy, h->width, h->height, fpx, d_kl, d_counts,
-                                                                      h->max_lines, h->W, d_desc, d_fdesc);
+    k_lbd_grad<<<dim3(div_up(h->width, kGW), div_up(h->height, kGH), nframes), 256, 0, stream>>>(d_gray, h->width, h->height, fpx,
+                                                                                              h->d_dx, h->d_dy);
+    k_lbd_describe<<<dim3(h->max_lines, nframes), 96, 0, stream>>>(h->d_dx, h->d_dy, h->width, h->height, fpx, d_kl, d_counts,
+                                                                   h->max_lines, h->W, d_desc, d_fdesc);
     h->last_launches = 2;
     HVO_CUDA(cudaGetLastError());
     return HVO_OK;
 }
+static int lbd_run(hvo_lbd* h, const uint8_t* d_gray, int nframes, const KeyLineDev* d_kl, const int32_t* d_counts, uint8_t* d_desc,
+                   float* d_fdesc) {
+    return lbd_run_stream(h, h->stream, d_gray, nframes, d_kl, d_counts, d_desc, d_fdesc);
+}
+
+// Internal (lsd.cu): LBD of device-resident keylines on the caller's stream (the line extractor chains it after LSD).
+namespace hvo {
+int lbd_compute_on_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray, int nframes, const hvo_keyline* d_keylines,
+                          const int32_t* d_counts, uint8_t* d_desc) {
+    return lbd_run_stream(h, stream, d_gray, nframes, reinterpret_cast<const KeyLineDev*>(d_keylines), d_counts, d_desc, nullptr);
+}
+}  // namespace hvo
 
 extern "C" {
 

@@ -1,0 +1,855 @@
+// Line extractor for sm_100a.  Replaces ORB_SLAM2::LINEextractor::operator() (reference src/LineExtractor.cpp:329-380):
+//   line_descriptor::LSDDetector::detect (Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:105-215), which runs
+//   cv::createLineSegmentDetector()->detect() (OpenCV imgproc LSD, default parameters) on octave 0 and fills KeyLines,
+//   the response sort + truncation to nLSDFeature (:351-360), LBD (lbd.cu) and the 2-D line functions (:365-377).
+//
+//   k_lsd_prep      fused cv::GaussianBlur(7x7, sigma 0.75; Q8 taps 0,4,56,136,56,4,0) + cv::resize(0.8, INTER_LINEAR_EXACT,
+//                   8.8 fixed point) + LSD ll_angle: 2x2 gradient, level-line angle (cv::fastAtan2), cosf/sinf of the angle;
+//                   one shared-memory tile per CTA; 16 B per scaled pixel go to HBM {angle, cos, sin, gx|gy}
+//   k_lsd_order     one CTA per frame: stable counting sort of the defined pixels into 1024 gradient-magnitude bins,
+//                   descending (warp-private histograms in shared memory, match_any ranks) = LSD's seed order
+//   k_lsd_grow      one warp per frame: the ordered, inherently sequential part (region growing with a running mean
+//                   angle, rectangle fit, density refinement).  Lanes hold the 8 neighbours of three consecutive region
+//                   points; the `used` map is a bitmap in shared memory; sums over a region are warp reductions.
+//                   Frames are independent, so a batch fills the machine with one warp per frame.
+//   k_line_keylines one CTA per frame: KeyLine fields, rank by response (ties: detection order), keep nLSDFeature,
+//                   2-D line functions
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "hvo_common.cuh"
+
+struct hvo_lbd;
+namespace hvo {
+int lbd_compute_on_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray, int nframes, const hvo_keyline* d_keylines,
+                          const int32_t* d_counts, uint8_t* d_desc);
+
+static const double kLsdPi = 3.1415926535897932384626433832795;
+#define LSD_NOTDEF (-1024.0f)
+#define LSD_DEG2RAD (3.1415926535897932384626433832795 / 180)
+#define LSD_2PI (2 * 3.1415926535897932384626433832795)
+#define LSD_32PI ((3 * 3.1415926535897932384626433832795) / 2)
+#define LSD_PI 3.1415926535897932384626433832795
+static const unsigned kFull = 0xffffffffu;
+
+struct __align__(16) LsdPix {
+    float ang;  // level-line angle in degrees (cv::fastAtan2), LSD_NOTDEF where the gradient is below threshold
+    float c, s; // cosf / sinf of float(angle in radians)
+    int gxgy;   // gx (low 16) | gy (high 16): modgrad = sqrt((gx^2 + gy^2) / 4.0)
+};
+
+struct LinCoef { int ofs; uint16_t c1; uint16_t mode; };  // INTER_LINEAR_EXACT: mode 0 interior, 1 low border, 2 high border
+
+static const int kPW = 64, kPH = 16;                 // scaled-pixel tile of k_lsd_prep
+static const int kSrcW = 88, kSrcH = 28;             // raw tile capacity (scale 0.8: 1.25 * (tile + 1) + 2 + 4 halo)
+
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gray, int W, int H, long long frame_px, int sw, int sh,
+                                                  const LinCoef* __restrict__ cx, const LinCoef* __restrict__ cy,
+                                                  const float2* __restrict__ cstab, double rho, LsdPix* __restrict__ pix,
+                                                  uint8_t* __restrict__ scaled_out, int* __restrict__ maxsq) {
+    __shared__ uint8_t raw[kSrcH][kSrcW];
+    __shared__ uint16_t hb[kSrcH][kSrcW];
+    __shared__ uint8_t bl[kSrcH][kSrcW];
+    __shared__ uint16_t hr[kSrcH][kPW + 2];
+    __shared__ uint8_t sc[kPH + 1][kPW + 4];
+    __shared__ int s_max;
+    const int x0 = blockIdx.x * kPW, y0 = blockIdx.y * kPH, f = blockIdx.z, tid = threadIdx.x;
+    const uint8_t* img = gray + (long long)f * frame_px;
+    const int x1 = min(x0 + kPW, sw - 1), y1 = min(y0 + kPH, sh - 1);  // last scaled col / row needed (incl. +1 halo)
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1;
+    // blurred source window needed by the resize taps
+    const int bx0 = cx[x0].ofs, bx1 = min(cx[x1].ofs + 1, W - 1), by0 = cy[y0].ofs, by1 = min(cy[y1].ofs + 1, H - 1);
+    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;  // <= kSrcW - 4, kSrcH - 4
+    const int rw = bw + 4, rh = bh + 4;
+    if (tid == 0) s_max = 0;
+    for (int i = tid; i < rw * rh; i += 256) {
+        const int r = i / rw, c = i - r * rw;
+        const int y = reflect101(by0 - 2 + r, H), x = reflect101(bx0 - 2 + c, W);
+        raw[r][c] = __ldg(img + (long long)y * W + x);
+    }
+    __syncthreads();
+    for (int i = tid; i < bw * rh; i += 256) {  // horizontal taps 4,56,136,56,4 (the 7-tap kernel's outer taps are 0)
+        const int r = i / bw, c = i - r * bw;
+        const uint8_t* p = &raw[r][c];
+        hb[r][c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
+    }
+    __syncthreads();
+    for (int i = tid; i < bw * bh; i += 256) {
+        const int r = i / bw, c = i - r * bw;
+        const uint32_t acc = 4u * (hb[r][c] + hb[r + 4][c]) + 56u * (hb[r + 1][c] + hb[r + 3][c]) + 136u * hb[r + 2][c];
+        bl[r][c] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncthreads();
+    for (int i = tid; i < nx * bh; i += 256) {  // horizontal resize, 8.8 fixed point
+        const int r = i / nx, c = i - r * nx;
+        const LinCoef k = cx[x0 + c];
+        uint16_t v;
+        if (k.mode == 0) v = (uint16_t)(bl[r][k.ofs - bx0] * (256 - k.c1) + bl[r][k.ofs - bx0 + 1] * k.c1);
+        else v = (uint16_t)(bl[r][k.ofs - bx0] << 8);  // ofs = 0 (low border) or W-1 (high border)
+        hr[r][c] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < nx * ny; i += 256) {  // vertical resize
+        const int r = i / nx, c = i - r * nx;
+        const LinCoef k = cy[y0 + r];
+        uint8_t v;
+        if (k.mode == 0) v = (uint8_t)((hr[k.ofs - by0][c] * (256u - k.c1) + hr[k.ofs - by0 + 1][c] * (uint32_t)k.c1 + 32768u) >> 16);
+        else v = (uint8_t)((hr[k.ofs - by0][c] + 128) >> 8);
+        sc[r][c] = v;
+    }
+    __syncthreads();
+    int lmax = 0;
+    for (int i = tid; i < kPW * kPH; i += 256) {
+        const int r = i / kPW, c = i - r * kPW;
+        const int x = x0 + c, y = y0 + r;
+        if (x >= sw || y >= sh) continue;
+        LsdPix p;
+        p.ang = LSD_NOTDEF; p.c = 0.f; p.s = 0.f; p.gxgy = 0;
+        if (x < sw - 1 && y < sh - 1) {
+            const int DA = sc[r + 1][c + 1] - sc[r][c], BC = sc[r][c + 1] - sc[r + 1][c];
+            const int gx = DA + BC, gy = DA - BC;
+            const int sq = gx * gx + gy * gy;
+            p.gxgy = (gx & 0xffff) | (gy << 16);
+            const double norm = sqrt((double)sq / 4.0);
+            if (!(norm <= rho)) {
+                p.ang = fast_atan2_deg((float)gx, (float)-gy);
+                const float2 cs = __ldg(&cstab[(gx + 510) * 1021 + (gy + 510)]);
+                p.c = cs.x; p.s = cs.y;
+                lmax = max(lmax, sq);
+            }
+        }
+        const long long o = (long long)f * sw * sh + (long long)y * sw + x;
+        pix[o] = p;
+        if (scaled_out) scaled_out[o] = sc[r][c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(kFull, lmax, o));
+    if ((tid & 31) == 0 && lmax > 0) atomicMax(&s_max, lmax);
+    __syncthreads();
+    if (tid == 0 && s_max > 0) atomicMax(&maxsq[f], s_max);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Seed order = cv::LineSegmentDetector's ordered_points restricted to the defined pixels: bin = int(modgrad * 1023 /
+// max_grad), descending; scan order inside a bin.  (Undefined pixels are skipped by the seed loop, so they are not listed.)
+static const int kOrdWarps = 32, kBins = 1024;
+
+__device__ __forceinline__ int lsd_bin(const LsdPix& p, double bin_coef) {
+    const int gx = (int)(short)(p.gxgy & 0xffff), gy = p.gxgy >> 16;
+    return (int)(sqrt((double)(gx * gx + gy * gy) / 4.0) * bin_coef);
+}
+
+__global__ void __launch_bounds__(1024) k_lsd_order(const LsdPix* __restrict__ pix, int npix, const int* __restrict__ maxsq,
+                                                     uint32_t* __restrict__ order, int* __restrict__ norder) {
+    extern __shared__ uint32_t hist[];  // [kOrdWarps][kBins]
+    __shared__ uint32_t s_warp[32];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const LsdPix* P = pix + (long long)f * npix;
+    uint32_t* out = order + (long long)f * npix;
+    const int mq = maxsq[f];
+    if (mq <= 0) { if (tid == 0) norder[f] = 0; return; }
+    const double bin_coef = (double)(kBins - 1) / sqrt((double)mq / 4.0);
+    for (int i = tid; i < kOrdWarps * kBins; i += 1024) hist[i] = 0;
+    __syncthreads();
+    const int seg = (npix + kOrdWarps - 1) / kOrdWarps, s0 = wid * seg, s1 = min(npix, s0 + seg);
+    uint32_t* myh = hist + wid * kBins;
+    for (int i = s0 + lane; i < s1; i += 32) {
+        const LsdPix p = P[i];
+        if (p.ang != LSD_NOTDEF) atomicAdd(&myh[lsd_bin(p, bin_coef)], 1u);
+    }
+    __syncthreads();
+    {   // thread t owns bin (kBins-1-t): descending bins <-> ascending t
+        const int b = kBins - 1 - tid;
+        uint32_t run = 0;
+        for (int w = 0; w < kOrdWarps; ++w) { const uint32_t c = hist[w * kBins + b]; hist[w * kBins + b] = run; run += c; }
+        // exclusive scan of the bin totals over tid
+        uint32_t v = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(kFull, v, o); if (lane >= o) v += n; }
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t wv = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(kFull, wv, o); if (lane >= o) wv += n; }
+            s_warp[lane] = wv;
+        }
+        __syncthreads();
+        const uint32_t base = v - run + (wid ? s_warp[wid - 1] : 0);
+        if (tid == 1023) norder[f] = (int)(base + run);
+        for (int w = 0; w < kOrdWarps; ++w) hist[w * kBins + b] += base;
+    }
+    __syncthreads();
+    for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int i = i0 + lane;
+        int bin = -1;
+        if (i < s1) { const LsdPix p = P[i]; if (p.ang != LSD_NOTDEF) bin = lsd_bin(p, bin_coef); }
+        const unsigned peers = __match_any_sync(kFull, bin);
+        uint32_t pos = 0;
+        if (bin >= 0) pos = myh[bin] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (bin >= 0) {
+            out[pos] = (uint32_t)i;
+            if ((int)(__ffs(peers) - 1) == lane) myh[bin] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+struct LsdRect { double x1, y1, x2, y2, width; };
+
+__device__ __forceinline__ bool lsd_aligned(double theta, double a, double prec) {
+    double n = theta - a;
+    if (n < 0) n = -n;
+    if (n > LSD_32PI) { n -= LSD_2PI; if (n < 0) n = -n; }
+    return n <= prec;
+}
+__device__ __forceinline__ double lsd_angle_diff_signed(double a, double b) {
+    double d = a - b;
+    while (d <= -LSD_PI) d += LSD_2PI;
+    while (d > LSD_PI) d -= LSD_2PI;
+    return d;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ bool used_get(const uint32_t* used, int i) { return (used[i >> 5] >> (i & 31)) & 1u; }
+__device__ __forceinline__ double lsd_modgrad(int gxgy) {
+    const int gx = (int)(short)(gxgy & 0xffff), gy = gxgy >> 16;
+    return sqrt((double)(gx * gx + gy * gy) / 4.0);
+}
+
+// LineSegmentDetectorImpl::region_grow.  Warp-collective; returns the region size, reg[] holds x | y << 16.
+__device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t* reg, uint32_t* used, int w, int h, uint32_t seed_xy,
+                               double prec, double& reg_angle_out, int lane) {
+    const int si = (int)(seed_xy >> 16) * w + (int)(seed_xy & 0xffff);
+    const LsdPix sp = pix[si];
+    double reg_angle = (double)sp.ang * LSD_DEG2RAD;
+    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    if (lane == 0) { reg[0] = seed_xy; used[si >> 5] |= 1u << (si & 31); }
+    __syncwarp();
+    int n = 1, i = 0;
+    const int cidx = lane / 9, k = lane - cidx * 9;
+    const int ddy = k / 3 - 1, ddx = k - (k / 3) * 3 - 1;
+    while (i < n) {
+        const int nb = min(3, n - i);
+        bool def = false;
+        int xx = 0, yy = 0, ni = 0;
+        LsdPix p;
+        p.ang = LSD_NOTDEF; p.c = 0.f; p.s = 0.f;
+        if (cidx < nb && k != 4) {
+            const uint32_t c = reg[i + cidx];
+            xx = (int)(c & 0xffff) + ddx; yy = (int)(c >> 16) + ddy;
+            if (xx >= 0 && yy >= 0 && xx < w && yy < h) {
+                ni = yy * w + xx;
+                p = pix[ni];
+                def = p.ang != LSD_NOTDEF;
+            }
+        }
+        const double a = (double)p.ang * LSD_DEG2RAD;
+        for (int c = 0; c < nb; ++c) {
+            const bool cand = def && cidx == c && !used_get(used, ni);
+            unsigned pending = __ballot_sync(kFull, cand);
+            while (pending) {
+                const bool al = cand && lsd_aligned(reg_angle, a, prec);
+                const unsigned m = __ballot_sync(kFull, al) & pending;
+                if (!m) break;
+                const int j = __ffs(m) - 1;
+                if (lane == j) { used[ni >> 5] |= 1u << (ni & 31); reg[n] = (uint32_t)xx | ((uint32_t)yy << 16); }
+                const float cs = __shfl_sync(kFull, p.c, j), sn = __shfl_sync(kFull, p.s, j);
+                sumdx = __fadd_rn(sumdx, cs);
+                sumdy = __fadd_rn(sumdy, sn);
+                reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * LSD_DEG2RAD;
+                ++n;
+                pending &= ~((2u << j) - 1u);
+            }
+            __syncwarp();
+        }
+        i += nb;
+    }
+    reg_angle_out = reg_angle;
+    return n;
+}
+
+// region2rect + get_theta.  Sums are warp reductions (summation order differs from the sequential reference by
+// rounding only; every decision downstream is made on the same formulas).
+__device__ void lsd_region2rect(const LsdPix* __restrict__ pix, const volatile uint32_t* reg, int n, int w, double reg_angle, double prec,
+                                LsdRect& rec, int lane) {
+    double x = 0, y = 0, sum = 0;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = reg[i];
+        const int px = c & 0xffff, py = c >> 16;
+        const double wt = lsd_modgrad(pix[py * w + px].gxgy);
+        x += (double)px * wt; y += (double)py * wt; sum += wt;
+    }
+    x = warp_sum(x); y = warp_sum(y); sum = warp_sum(sum);
+    x /= sum; y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = reg[i];
+        const int px = c & 0xffff, py = c >> 16;
+        const double wt = lsd_modgrad(pix[py * w + px].gxgy);
+        const double dx = (double)px - x, dy = (double)py - y;
+        Ixx += dy * dy * wt; Iyy += dx * dx * wt; Ixy -= dx * dy * wt;
+    }
+    Ixx = warp_sum(Ixx); Iyy = warp_sum(Iyy); Ixy = warp_sum(Ixy);
+    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+    theta *= LSD_DEG2RAD;
+    if (fabs(lsd_angle_diff_signed(theta, reg_angle)) > prec) theta += LSD_PI;
+    const double dx = cos(theta), dy = sin(theta);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = reg[i];
+        const double rx = (double)(int)(c & 0xffff) - x, ry = (double)(int)(c >> 16) - y;
+        const double l = rx * dx + ry * dy, ww = -rx * dy + ry * dx;
+        l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+        w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
+    }
+    l_max = warp_max(l_max); l_min = warp_min(l_min); w_max = warp_max(w_max); w_min = warp_min(w_min);
+    rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy; rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+    rec.width = w_max - w_min;
+    if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double lsd_density(int n, const LsdRect& r) {
+    const double dx = r.x2 - r.x1, dy = r.y2 - r.y1;
+    return (double)n / (sqrt(dx * dx + dy * dy) * r.width);
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix, int w, int h, const uint32_t* __restrict__ order,
+                                                 const int* __restrict__ norder, uint32_t* __restrict__ regbuf, int min_reg_size,
+                                                 double prec, double density_th, double inv_scale_div, float* __restrict__ seg,
+                                                 int seg_cap, int* __restrict__ nseg) {
+    extern __shared__ uint32_t used[];  // bitmap, 1 = USED
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int npix = w * h;
+    const LsdPix* P = pix + (long long)f * npix;
+    const uint32_t* ord = order + (long long)f * npix;
+    volatile uint32_t* reg = regbuf + (long long)f * npix;
+    float* out = seg + (long long)f * seg_cap * 4;
+    const int nwords = (npix + 31) >> 5;
+    for (int i = lane; i < nwords; i += 32) used[i] = 0;
+    __syncwarp();
+    const int no = norder[f];
+    int ns = 0;
+    for (int base = 0; base < no; base += 32) {
+        const bool valid = base + lane < no;
+        const uint32_t idx = valid ? ord[base + lane] : 0u;
+        unsigned remaining = kFull;
+        while (true) {
+            const unsigned m = __ballot_sync(kFull, valid && !used_get(used, (int)idx)) & remaining;
+            if (!m) break;
+            const int j = __ffs(m) - 1;
+            remaining &= ~((2u << j) - 1u);
+            const uint32_t sidx = __shfl_sync(kFull, idx, j);
+            const uint32_t seed = (sidx % (uint32_t)w) | ((sidx / (uint32_t)w) << 16);
+            double reg_angle;
+            int n = lsd_region_grow(P, reg, used, w, h, seed, prec, reg_angle, lane);
+            if (n < min_reg_size) continue;
+            LsdRect rec;
+            lsd_region2rect(P, reg, n, w, reg_angle, prec, rec, lane);
+            bool ok = true;
+            if (lsd_density(n, rec) < density_th) {
+                // ---- refine: try a tighter angle tolerance around the seed ----
+                const double xc = (double)(seed & 0xffff), yc = (double)(seed >> 16);
+                const double ang_c = (double)P[sidx].ang * LSD_DEG2RAD;
+                double sum = 0, s_sum = 0;
+                int cnt = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const uint32_t c = reg[i];
+                    const int px = c & 0xffff, py = c >> 16, pi = py * w + px;
+                    atomicAnd(&used[pi >> 5], ~(1u << (pi & 31)));
+                    const double ddx = (double)px - xc, ddy = (double)py - yc;
+                    if (sqrt(ddx * ddx + ddy * ddy) < rec.width) {
+                        const double d = lsd_angle_diff_signed((double)P[pi].ang * LSD_DEG2RAD, ang_c);
+                        sum += d; s_sum += d * d; ++cnt;
+                    }
+                }
+                sum = warp_sum(sum); s_sum = warp_sum(s_sum);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+                __syncwarp();
+                const double mean_angle = sum / (double)cnt;
+                const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+                n = lsd_region_grow(P, reg, used, w, h, seed, tau, reg_angle, lane);
+                if (n < 2) ok = false;
+                if (ok) {
+                    lsd_region2rect(P, reg, n, w, reg_angle, prec, rec, lane);
+                    double density = lsd_density(n, rec);
+                    if (density < density_th) {
+                        // ---- reduce_region_radius ----
+                        const double d1x = rec.x1 - xc, d1y = rec.y1 - yc, d2x = rec.x2 - xc, d2y = rec.y2 - yc;
+                        const double r1 = d1x * d1x + d1y * d1y, r2 = d2x * d2x + d2y * d2y;
+                        double rad_sq = r1 > r2 ? r1 : r2;
+                        while (density < density_th) {
+                            rad_sq *= 0.75 * 0.75;
+                            int kept = 0;
+                            for (int i0 = 0; i0 < n; i0 += 32) {
+                                const int i = i0 + lane;
+                                uint32_t c = 0;
+                                bool keep = false;
+                                if (i < n) {
+                                    c = reg[i];
+                                    const int px = c & 0xffff, py = c >> 16;
+                                    const double ddx = (double)px - xc, ddy = (double)py - yc;
+                                    keep = !(ddx * ddx + ddy * ddy > rad_sq);
+                                    if (!keep) { const int pi = py * w + px; atomicAnd(&used[pi >> 5], ~(1u << (pi & 31))); }
+                                }
+                                const unsigned km = __ballot_sync(kFull, keep);
+                                __syncwarp();
+                                if (keep) reg[kept + __popc(km & ((1u << lane) - 1u))] = c;
+                                kept += __popc(km);
+                                __syncwarp();
+                            }
+                            n = kept;
+                            if (n < 2) { ok = false; break; }
+                            lsd_region2rect(P, reg, n, w, reg_angle, prec, rec, lane);
+                            density = lsd_density(n, rec);
+                        }
+                    }
+                }
+            }
+            if (!ok) continue;
+            if (lane == 0 && ns < seg_cap) {
+                out[4 * ns + 0] = (float)((rec.x1 + 0.5) / inv_scale_div);
+                out[4 * ns + 1] = (float)((rec.y1 + 0.5) / inv_scale_div);
+                out[4 * ns + 2] = (float)((rec.x2 + 0.5) / inv_scale_div);
+                out[4 * ns + 3] = (float)((rec.y2 + 0.5) / inv_scale_div);
+            }
+            ++ns;
+        }
+    }
+    if (lane == 0) nseg[f] = ns;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+struct KeyLineOut {  // cv::line_descriptor::KeyLine POD, 68 bytes (hvo_keyline)
+    float angle;
+    int class_id, octave;
+    float pt_x, pt_y, response, size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength;
+    int numOfPixels;
+};
+
+__device__ __forceinline__ void lsd_clamp_extremes(float e[4], int W, int H) {  // checkLineExtremes, LSDDetector_custom.cpp:76-103
+    if (e[0] < 0) e[0] = 0;
+    if (e[0] >= W) e[0] = (float)W - 1.0f;
+    if (e[2] < 0) e[2] = 0;
+    if (e[2] >= W) e[2] = (float)W - 1.0f;
+    if (e[1] < 0) e[1] = 0;
+    if (e[1] >= H) e[1] = (float)H - 1.0f;
+    if (e[3] < 0) e[3] = 0;
+    if (e[3] >= H) e[3] = (float)H - 1.0f;
+}
+__device__ __forceinline__ float lsd_length(const float e[4]) {
+    const double a = (double)__fsub_rn(e[0], e[2]), b = (double)__fsub_rn(e[1], e[3]);
+    return (float)sqrt(a * a + b * b);
+}
+
+__global__ void __launch_bounds__(256) k_line_keylines(const float* __restrict__ seg, int seg_cap, const int* __restrict__ nseg, int W, int H,
+                                                       int nfeat, int max_lines, float* __restrict__ resp, KeyLineOut* __restrict__ kls,
+                                                       double* __restrict__ linevec, int32_t* __restrict__ counts) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(nseg[f], seg_cap);
+    const float* S = seg + (long long)f * seg_cap * 4;
+    float* R = resp + (long long)f * seg_cap;
+    const bool select = n > nfeat;
+    const float inv_max = (float)max(W, H);
+    if (select) {
+        for (int i = tid; i < n; i += 256) {
+            float e[4] = {S[4 * i], S[4 * i + 1], S[4 * i + 2], S[4 * i + 3]};
+            lsd_clamp_extremes(e, W, H);
+            R[i] = __fdiv_rn(lsd_length(e), inv_max);
+        }
+        __syncthreads();
+    }
+    const int nout = select ? nfeat : n;
+    if (tid == 0) counts[f] = min(nout, max_lines);
+    for (int i = tid; i < n; i += 256) {
+        int rank = i;
+        if (select) {  // sort_lines_by_response (LineExtractor.cpp:351-360): response descending; ties keep detection order
+            const float r = R[i];
+            rank = 0;
+            for (int j = 0; j < n; ++j) { const float q = R[j]; rank += (q > r || (q == r && j < i)) ? 1 : 0; }
+            if (rank >= nfeat) continue;
+        }
+        if (rank >= max_lines) continue;
+        float e[4] = {S[4 * i], S[4 * i + 1], S[4 * i + 2], S[4 * i + 3]};
+        lsd_clamp_extremes(e, W, H);
+        KeyLineOut kl;
+        kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];  // octaveScale = pow(scale, 0) = 1
+        kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
+        kl.lineLength = lsd_length(e);
+        const int xa = __float2int_rn(e[0]), ya = __float2int_rn(e[1]), xb = __float2int_rn(e[2]), yb = __float2int_rn(e[3]);
+        kl.numOfPixels = max(abs(xb - xa), abs(yb - ya)) + 1;  // cv::LineIterator(...).count, 8-connected, endpoints inside the image
+        kl.angle = (float)atan2((double)__fsub_rn(e[3], e[1]), (double)__fsub_rn(e[2], e[0]));
+        kl.class_id = rank;
+        kl.octave = 0;
+        kl.size = __fmul_rn(__fsub_rn(e[2], e[0]), __fsub_rn(e[3], e[1]));
+        kl.response = __fdiv_rn(kl.lineLength, inv_max);
+        kl.pt_x = __fdiv_rn(__fadd_rn(e[2], e[0]), 2.f);
+        kl.pt_y = __fdiv_rn(__fadd_rn(e[3], e[1]), 2.f);
+        kls[(long long)f * max_lines + rank] = kl;
+        // lineVec2d (LineExtractor.cpp:365-377): (sp x ep) / sqrt(l0^2 + l1^2), doubles
+        const double sx = e[0], sy = e[1], ex = e[2], ey = e[3];
+        const double l0 = sy - ey, l1 = ex - sx, l2 = sx * ey - sy * ex;
+        const double nn = sqrt(l0 * l0 + l1 * l1);
+        double* lv = linevec + ((long long)f * max_lines + rank) * 3;
+        lv[0] = l0 / nn; lv[1] = l1 / nn; lv[2] = l2 / nn;
+    }
+}
+
+}  // namespace hvo
+
+using namespace hvo;
+
+extern "C" {
+int hvo_lbd_create(int width, int height, int max_batch, int max_lines, int device, hvo_lbd** out);
+void hvo_lbd_destroy(hvo_lbd* h);
+}
+
+struct hvo_line {
+    int device = 0, width = 0, height = 0, max_batch = 0, nfeat = 0;
+    int sw = 0, sh = 0, seg_cap = 0, min_reg_size = 0;
+    double rho = 0, prec = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    cudaEvent_t sev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false;
+    float stage_ms[4] = {0, 0, 0, 0};
+    hvo_lbd* lbd = nullptr;
+    uint8_t* d_gray = nullptr;
+    LinCoef *d_cx = nullptr, *d_cy = nullptr;
+    float2* d_cstab = nullptr;
+    LsdPix* d_pix = nullptr;
+    uint8_t* d_scaled = nullptr;
+    int* d_maxsq = nullptr;
+    uint32_t *d_order = nullptr, *d_reg = nullptr;
+    int *d_norder = nullptr, *d_nseg = nullptr;
+    float *d_seg = nullptr, *d_resp = nullptr;
+    KeyLineOut* d_kl = nullptr;
+    double* d_linevec = nullptr;
+    int32_t* d_counts = nullptr;
+    uint8_t* d_desc = nullptr;
+    int last_launches = 0;
+};
+
+// cv::fastAtan2 on the host (this file is compiled with -ffp-contract=off: every operation individually rounded)
+static float host_fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / kLsdPi);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
+                p7 = -0.04432655554792128f * scale;
+    const float ax = std::fabs(x), ay = std::fabs(y);
+    float a, c, c2;
+    if (ax >= ay) { c = ay / (ax + (float)DBL_EPSILON); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    else { c = ax / (ay + (float)DBL_EPSILON); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+static void lsd_exact_coeffs(int src, int dst, double inv_scale, std::vector<LinCoef>& out) {
+    // cv::resize INTER_LINEAR_EXACT coefficient rule (8.8 fixed point): see oracle/lsd_oracle.cpp for the cv2 pin
+    const double scale = 1.0 / inv_scale;
+    out.resize(dst);
+    for (int v = 0; v < dst; ++v) {
+        const double f = scale * ((double)v + 0.5) - 0.5;
+        const int i = (int)std::floor(f);
+        LinCoef c{0, 0, 1};
+        if (i >= 0 && src > 1) {
+            if (i < src - 1) { c.ofs = i; c.c1 = (uint16_t)std::lrint((f - (double)i) * 256.0); c.mode = 0; }
+            else { c.ofs = src - 1; c.mode = 2; }
+        }
+        out[v] = c;
+    }
+}
+
+static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
+    const int npix = h->sw * h->sh;
+    cudaStream_t s = h->stream;
+    if (h->profiling) cudaEventRecord(h->sev[0], s);
+    HVO_CUDA(cudaMemsetAsync(h->d_maxsq, 0, (size_t)nframes * sizeof(int), s));
+    k_lsd_prep<<<dim3(div_up(h->sw, kPW), div_up(h->sh, kPH), nframes), 256, 0, s>>>(
+        d_gray, h->width, h->height, (long long)h->width * h->height, h->sw, h->sh, h->d_cx, h->d_cy, h->d_cstab, h->rho, h->d_pix,
+        h->d_scaled, h->d_maxsq);
+    if (h->profiling) cudaEventRecord(h->sev[1], s);
+    k_lsd_order<<<nframes, 1024, kOrdWarps * kBins * sizeof(uint32_t), s>>>(h->d_pix, npix, h->d_maxsq, h->d_order, h->d_norder);
+    if (h->profiling) cudaEventRecord(h->sev[2], s);
+    const size_t bm = (size_t)((npix + 31) / 32) * 4;
+    k_lsd_grow<<<nframes, 32, bm, s>>>(h->d_pix, h->sw, h->sh, h->d_order, h->d_norder, h->d_reg, h->min_reg_size, h->prec, 0.7, 0.8,
+                                       h->d_seg, h->seg_cap, h->d_nseg);
+    if (h->profiling) cudaEventRecord(h->sev[3], s);
+    h->last_launches = 3;
+    HVO_CUDA(cudaGetLastError());
+    return HVO_OK;
+}
+
+static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, KeyLineOut* d_kl, uint8_t* d_desc, double* d_linevec,
+                               int32_t* d_counts) {
+    int st = line_detect_device(h, d_gray, nframes);
+    if (st != HVO_OK) return st;
+    k_line_keylines<<<nframes, 256, 0, h->stream>>>(h->d_seg, h->seg_cap, h->d_nseg, h->width, h->height, h->nfeat, h->nfeat, h->d_resp,
+                                                    d_kl, d_linevec, d_counts);
+    HVO_CUDA(cudaGetLastError());
+    st = lbd_compute_on_stream(h->lbd, h->stream, d_gray, nframes, reinterpret_cast<const hvo_keyline*>(d_kl), d_counts, d_desc);
+    if (h->profiling) cudaEventRecord(h->sev[4], h->stream);
+    h->last_launches = 6;
+    return st;
+}
+
+extern "C" {
+
+int hvo_line_create(const hvo_line_params* p, int width, int height, int max_batch, int device, hvo_line** out) {
+    HVO_CHECK_ARG(out, "null out");
+    *out = nullptr;
+    HVO_CHECK_ARG(p, "null params");
+    HVO_CHECK_ARG(width >= 16 && height >= 16 && width <= 8192 && height <= 8192, "image size out of range");
+    HVO_CHECK_ARG(max_batch >= 1, "max_batch < 1");
+    HVO_CHECK_ARG(p->n_features >= 1 && p->n_features <= 4096, "n_features out of range");
+    HVO_CHECK_ARG(p->n_octaves == 1, "only LINE.nLevels = 1 is supported (every shipped YAML; see DESIGN.md)");
+    int ndev = 0;
+    HVO_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { set_error("no CUDA device: libhvofront has no CPU fallback"); return HVO_ERR_CUDA; }
+    HVO_CHECK_ARG(device >= 0 && device < ndev, "device index out of range");
+    hvo_line* h = new (std::nothrow) hvo_line();
+    if (!h) { set_error("out of host memory"); return HVO_ERR_ARG; }
+    h->device = device; h->width = width; h->height = height; h->max_batch = max_batch; h->nfeat = p->n_features;
+    h->sw = (int)std::lrint((double)width * 0.8);
+    h->sh = (int)std::lrint((double)height * 0.8);
+    h->prec = kLsdPi * 22.5 / 180;
+    h->rho = 2.0 / std::sin(h->prec);
+    const double log_nt = 5 * (std::log10((double)h->sw) + std::log10((double)h->sh)) / 2 + std::log10(11.0);
+    h->min_reg_size = (int)(size_t)(-log_nt / std::log10(22.5 / 180));
+    h->seg_cap = ((h->sw - 1) * (h->sh - 1)) / (h->min_reg_size > 0 ? h->min_reg_size : 1) + 1;  // every segment owns >= min_reg_size pixels
+    std::vector<LinCoef> cx, cy;
+    lsd_exact_coeffs(width, h->sw, 0.8, cx);
+    lsd_exact_coeffs(height, h->sh, 0.8, cy);
+    // cosf/sinf of float(angle) for every possible gradient (gx, gy in [-510, 510]): region_grow accumulates them in
+    // float, and libm's cosf/sinf are not correctly rounded, so the table is built by the same libm the CPU path calls.
+    std::vector<float2> tab((size_t)1021 * 1021);
+    for (int gx = -510; gx <= 510; ++gx)
+        for (int gy = -510; gy <= 510; ++gy) {
+            const float fa = (float)((double)host_fast_atan2_deg((float)gx, (float)-gy) * (kLsdPi / 180));
+            tab[(size_t)(gx + 510) * 1021 + (gy + 510)] = make_float2(cosf(fa), sinf(fa));
+        }
+    // the shared-memory tiles of k_lsd_prep are sized for the 0.8 scale; verify the source window of every tile fits
+    for (int x0 = 0; x0 < h->sw; x0 += kPW) {
+        const int x1 = std::min(x0 + kPW, h->sw - 1);
+        if (std::min(cx[x1].ofs + 1, width - 1) - cx[x0].ofs + 1 + 4 > kSrcW) { set_error("internal: prep tile too wide"); delete h; return HVO_ERR_ARG; }
+    }
+    for (int y0 = 0; y0 < h->sh; y0 += kPH) {
+        const int y1 = std::min(y0 + kPH, h->sh - 1);
+        if (std::min(cy[y1].ofs + 1, height - 1) - cy[y0].ofs + 1 + 4 > kSrcH) { set_error("internal: prep tile too tall"); delete h; return HVO_ERR_ARG; }
+    }
+    int st = HVO_OK;
+    do {
+#define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
+        HVO_TRY(cudaSetDevice(device));
+        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& e : h->tev) HVO_TRY(cudaEventCreate(&e));
+        if (st != HVO_OK) break;
+        for (auto& e : h->sev) HVO_TRY(cudaEventCreate(&e));
+        if (st != HVO_OK) break;
+        const size_t B = (size_t)max_batch, px = (size_t)width * height, spx = (size_t)h->sw * h->sh, ml = (size_t)h->nfeat;
+        HVO_TRY(cudaMalloc(&h->d_gray, B * px));
+        HVO_TRY(cudaMalloc(&h->d_cx, cx.size() * sizeof(LinCoef)));
+        HVO_TRY(cudaMalloc(&h->d_cy, cy.size() * sizeof(LinCoef)));
+        HVO_TRY(cudaMalloc(&h->d_cstab, tab.size() * sizeof(float2)));
+        HVO_TRY(cudaMalloc(&h->d_pix, B * spx * sizeof(LsdPix)));
+        HVO_TRY(cudaMalloc(&h->d_scaled, B * spx));
+        HVO_TRY(cudaMalloc(&h->d_maxsq, B * sizeof(int)));
+        HVO_TRY(cudaMalloc(&h->d_order, B * spx * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_reg, B * spx * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_norder, B * sizeof(int)));
+        HVO_TRY(cudaMalloc(&h->d_nseg, B * sizeof(int)));
+        HVO_TRY(cudaMalloc(&h->d_seg, B * (size_t)h->seg_cap * 4 * sizeof(float)));
+        HVO_TRY(cudaMalloc(&h->d_resp, B * (size_t)h->seg_cap * sizeof(float)));
+        HVO_TRY(cudaMalloc(&h->d_kl, B * ml * sizeof(KeyLineOut)));
+        HVO_TRY(cudaMalloc(&h->d_linevec, B * ml * 3 * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_counts, B * sizeof(int32_t)));
+        HVO_TRY(cudaMalloc(&h->d_desc, B * ml * 32));
+        HVO_TRY(cudaMemcpy(h->d_cx, cx.data(), cx.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
+        HVO_TRY(cudaMemcpy(h->d_cy, cy.data(), cy.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
+        HVO_TRY(cudaMemcpy(h->d_cstab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        HVO_TRY(cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrdWarps * kBins * (int)sizeof(uint32_t)));
+        const int bm = ((h->sw * h->sh + 31) / 32) * 4;
+        if (bm > 200 * 1024) { set_error("image too large for the shared-memory `used` bitmap"); st = HVO_ERR_ARG; break; }
+        HVO_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, bm));
+#undef HVO_TRY
+    } while (0);
+    if (st == HVO_OK) st = hvo_lbd_create(width, height, max_batch, h->nfeat, device, &h->lbd);
+    if (st != HVO_OK) { hvo_line_destroy(h); return st; }
+    *out = h;
+    return HVO_OK;
+}
+
+void hvo_line_destroy(hvo_line* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->lbd) hvo_lbd_destroy(h->lbd);
+    void* bufs[] = {h->d_gray, h->d_cx, h->d_cy, h->d_cstab, h->d_pix, h->d_scaled, h->d_maxsq, h->d_order, h->d_reg, h->d_norder,
+                    h->d_nseg, h->d_seg, h->d_resp, h->d_kl, h->d_linevec, h->d_counts, h->d_desc};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->sev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int hvo_line_max_lines(const hvo_line* h) { return h ? h->nfeat : 0; }
+int hvo_line_segment_capacity(const hvo_line* h) { return h ? h->seg_cap : 0; }
+int hvo_line_scaled_size(const hvo_line* h, int* sw, int* sh) {
+    HVO_CHECK_ARG(h && sw && sh, "null argument");
+    *sw = h->sw; *sh = h->sh;
+    return HVO_OK;
+}
+
+int hvo_line_detect_batch(hvo_line* h, const uint8_t* gray, int nframes, float* segments4, int seg_capacity, int32_t* counts) {
+    HVO_CHECK_ARG(h && gray && segments4 && counts, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch, "nframes out of range for this handle");
+    HVO_CHECK_ARG(seg_capacity >= 1, "seg_capacity < 1");
+    HVO_CUDA(cudaSetDevice(h->device));
+    const size_t px = (size_t)h->width * h->height;
+    HVO_CUDA(cudaMemcpyAsync(h->d_gray, gray, (size_t)nframes * px, cudaMemcpyHostToDevice, h->stream));
+    int st = line_detect_device(h, h->d_gray, nframes);
+    if (st != HVO_OK) return st;
+    HVO_CUDA(cudaMemcpyAsync(counts, h->d_nseg, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    const int cpy = seg_capacity < h->seg_cap ? seg_capacity : h->seg_cap;
+    HVO_CUDA(cudaMemcpy2DAsync(segments4, (size_t)seg_capacity * 16, h->d_seg, (size_t)h->seg_cap * 16, (size_t)cpy * 16, nframes,
+                               cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
+
+int hvo_line_extract_batch(hvo_line* h, const uint8_t* gray, int nframes, hvo_keyline* keylines, uint8_t* desc, double* linevec3,
+                           int32_t* counts) {
+    HVO_CHECK_ARG(h && gray && keylines && desc && counts, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch, "nframes out of range for this handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    const size_t px = (size_t)h->width * h->height, n = (size_t)nframes, ml = (size_t)h->nfeat;
+    HVO_CUDA(cudaMemcpyAsync(h->d_gray, gray, n * px, cudaMemcpyHostToDevice, h->stream));
+    int st = line_extract_device(h, h->d_gray, nframes, h->d_kl, h->d_desc, h->d_linevec, h->d_counts);
+    if (st != HVO_OK) return st;
+    HVO_CUDA(cudaMemcpyAsync(counts, h->d_counts, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, n * ml * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, n * ml * 32, cudaMemcpyDeviceToHost, h->stream));
+    if (linevec3) HVO_CUDA(cudaMemcpyAsync(linevec3, h->d_linevec, n * ml * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
+
+int hvo_line_extract(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keyline* keylines, uint8_t* desc, double* linevec3, int capacity,
+                     int* n_out) {
+    HVO_CHECK_ARG(h && n_out, "null argument");
+    *n_out = 0;
+    if (!gray) return HVO_OK;  // empty image: the reference returns silently (LineExtractor.cpp:331-332)
+    HVO_CHECK_ARG(keylines && desc, "null argument");
+    HVO_CHECK_ARG(stride >= (size_t)h->width, "stride smaller than width");
+    HVO_CHECK_ARG(capacity >= h->nfeat, "capacity smaller than hvo_line_max_lines()");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaMemcpy2DAsync(h->d_gray, h->width, gray, stride, h->width, h->height, cudaMemcpyHostToDevice, h->stream));
+    int st = line_extract_device(h, h->d_gray, 1, h->d_kl, h->d_desc, h->d_linevec, h->d_counts);
+    if (st != HVO_OK) return st;
+    int32_t cnt = 0;
+    HVO_CUDA(cudaMemcpyAsync(&cnt, h->d_counts, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    if (cnt > 0) {
+        HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, (size_t)cnt * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, h->stream));
+        if (linevec3) HVO_CUDA(cudaMemcpyAsync(linevec3, h->d_linevec, (size_t)cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    *n_out = cnt;
+    return HVO_OK;
+}
+
+int hvo_line_extract_batch_device(hvo_line* h, const uint8_t* d_gray, int nframes, hvo_keyline* d_keylines, uint8_t* d_desc,
+                                  double* d_linevec3, int32_t* d_counts) {
+    HVO_CHECK_ARG(h && d_gray && d_keylines && d_desc && d_linevec3 && d_counts, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch, "nframes out of range for this handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    return line_extract_device(h, d_gray, nframes, reinterpret_cast<KeyLineOut*>(d_keylines), d_desc, d_linevec3, d_counts);
+}
+
+int hvo_line_get_scaled(hvo_line* h, int frame, uint8_t* out) {
+    HVO_CHECK_ARG(h && out, "null argument");
+    HVO_CHECK_ARG(frame >= 0 && frame < h->max_batch, "frame out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    const size_t spx = (size_t)h->sw * h->sh;
+    HVO_CUDA(cudaMemcpyAsync(out, h->d_scaled + frame * spx, spx, cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
+
+int hvo_line_get_seed_order(hvo_line* h, int frame, uint32_t* out, int cap, int* n_out) {
+    HVO_CHECK_ARG(h && out && n_out, "null argument");
+    HVO_CHECK_ARG(frame >= 0 && frame < h->max_batch, "frame out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int n = 0;
+    HVO_CUDA(cudaMemcpyAsync(&n, h->d_norder + frame, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    *n_out = n;
+    const int m = n < cap ? n : cap;
+    if (m > 0) {
+        HVO_CUDA(cudaMemcpyAsync(out, h->d_order + (size_t)frame * h->sw * h->sh, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return HVO_OK;
+}
+
+int hvo_line_set_profiling(hvo_line* h, int enable) {
+    HVO_CHECK_ARG(h, "null handle");
+    h->profiling = enable != 0;
+    return HVO_OK;
+}
+int hvo_line_stage_times(hvo_line* h, float* ms4) {
+    HVO_CHECK_ARG(h && ms4, "null argument");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaEventSynchronize(h->sev[4]));
+    for (int i = 0; i < 4; ++i) HVO_CUDA(cudaEventElapsedTime(&ms4[i], h->sev[i], h->sev[i + 1]));
+    return HVO_OK;
+}
+int hvo_line_last_launches(const hvo_line* h) { return h ? h->last_launches : 0; }
+int hvo_line_sync(hvo_line* h) {
+    HVO_CHECK_ARG(h, "null handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
+int hvo_line_timer_start(hvo_line* h) {
+    HVO_CHECK_ARG(h, "null handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaEventRecord(h->tev[0], h->stream));
+    return HVO_OK;
+}
+int hvo_line_timer_stop(hvo_line* h, float* ms_out) {
+    HVO_CHECK_ARG(h && ms_out, "null argument");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaEventRecord(h->tev[1], h->stream));
+    HVO_CUDA(cudaEventSynchronize(h->tev[1]));
+    HVO_CUDA(cudaEventElapsedTime(ms_out, h->tev[0], h->tev[1]));
+    return HVO_OK;
+}
+
+}  // extern "C"

@@ -549,26 +549,6 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 // ------------------------------------------------------------------------------------------------------
 // K4: orientation + on-the-fly blur + rBRIEF + output assembly, one warp per keypoint
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
-    const float scale = 57.295779513082320876798154814105f;  // (float)(180 / CV_PI)
-    const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale),
-                p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float eps = (float)DBL_EPSILON;
-    float a, c, c2;
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
-}
 
 // ------------------------------------------------------------------------------------------------------
 // K4: 7x7 sigma-2 Gaussian of every level (cv::GaussianBlur fixed point: Q8 kernel 18,34,48,56,48,34,18,

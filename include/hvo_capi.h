@@ -171,6 +171,51 @@ int hvo_lbd_sync(hvo_lbd* h);
 int hvo_lbd_timer_start(hvo_lbd* h);
 int hvo_lbd_timer_stop(hvo_lbd* h, float* ms_out);
 
+/* ----------------------------------------------------------------------------------------------- LINE
+ * Replaces ORB_SLAM2::LINEextractor (include/LineExtractor.h:187-262, src/LineExtractor.cpp:329-380):
+ * line_descriptor::LSDDetector::detect (Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:105-215; segments from
+ * cv::createLineSegmentDetector()->detect with OpenCV's default parameters) -> response sort + truncation to
+ * nLSDFeature -> LBD descriptors -> 2-D line functions.  Single octave (LINE.nLevels = 1 in every shipped YAML; the
+ * float `scale` narrows to int 1 at the reference's call, LineExtractor.cpp:342).                              */
+
+/* LINEextractor::LINEextractor(int numOctaves, float scale, unsigned nLSDFeature, double min_line_length)  LineExtractor.h:190 */
+typedef struct hvo_line_params {
+    int n_octaves;          /* must be 1 */
+    float scale;            /* unused by the reference's single-octave path; kept for the getters */
+    int n_features;         /* nLSDFeature: keep the n_features strongest responses */
+    double min_line_length; /* stored only (the reference's operator() does not use it) */
+} hvo_line_params;
+
+typedef struct hvo_line hvo_line;
+int hvo_line_create(const hvo_line_params* p, int width, int height, int max_batch, int device, hvo_line** out);
+void hvo_line_destroy(hvo_line* h);
+int hvo_line_max_lines(const hvo_line* h);        /* rows per frame of keylines / desc / linevec3 = n_features */
+int hvo_line_segment_capacity(const hvo_line* h); /* upper bound of raw LSD segments per frame */
+int hvo_line_scaled_size(const hvo_line* h, int* sw, int* sh);
+
+/* LINEextractor::operator()(image, mask, keylines, descriptors, lineVec2d)  LineExtractor.h:193 (mask: the reference
+ * always passes an empty mask, Frame.cc:902).  gray: host 8-bit; keylines/desc: `capacity` >= hvo_line_max_lines()
+ * rows; linevec3 (optional): rows of 3 doubles.  gray == NULL mirrors the empty-image early return. */
+int hvo_line_extract(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keyline* keylines, uint8_t* desc, double* linevec3,
+                     int capacity, int* n_out);
+/* Batch: gray [n][H][W]; keylines [n][max_lines]; desc [n][max_lines][32]; linevec3 [n][max_lines][3]; counts [n]. */
+int hvo_line_extract_batch(hvo_line* h, const uint8_t* gray, int nframes, hvo_keyline* keylines, uint8_t* desc, double* linevec3,
+                           int32_t* counts);
+int hvo_line_extract_batch_device(hvo_line* h, const uint8_t* d_gray, int nframes, hvo_keyline* d_keylines, uint8_t* d_desc,
+                                  double* d_linevec3, int32_t* d_counts);
+/* cv::LineSegmentDetector::detect alone: segments4 [n][seg_capacity][4] floats (x1,y1,x2,y2), counts [n] (a count may
+ * exceed seg_capacity; only the first seg_capacity segments of that frame are written). */
+int hvo_line_detect_batch(hvo_line* h, const uint8_t* gray, int nframes, float* segments4, int seg_capacity, int32_t* counts);
+/* Inspection (tests): the blurred + 0.8-resized image LSD works on, and the seed order (pixel indices y*sw+x). */
+int hvo_line_get_scaled(hvo_line* h, int frame, uint8_t* out);
+int hvo_line_get_seed_order(hvo_line* h, int frame, uint32_t* out, int cap, int* n_out);
+int hvo_line_set_profiling(hvo_line* h, int enable);
+int hvo_line_stage_times(hvo_line* h, float* ms4); /* prep, order, grow, keylines+LBD of the last extract call */
+int hvo_line_last_launches(const hvo_line* h);
+int hvo_line_sync(hvo_line* h);
+int hvo_line_timer_start(hvo_line* h);
+int hvo_line_timer_stop(hvo_line* h, float* ms_out);
+
 /* ---------------------------------------------------------------------------------------------- PLANE
  * Replaces PlaneDetection::readDepthImage(depth16U, K, factor) + runPlaneDetection(H, W)
  * (src/PlaneExtractor.cpp:26-66, include/PlaneExtractor.h:36-56) and the ahc::PlaneFitter behind them

@@ -248,6 +248,41 @@ def keylines_from_segments(seg, w, h):
     return out
 
 
+def lsd_detect(gray, want_scaled=False):
+    """cv::createLineSegmentDetector().detect(gray) restated (oracle/lsd_oracle.cpp): [n,4] float32 x1,y1,x2,y2."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = 16384
+    seg = np.empty((cap, 4), np.float32)
+    sw, sh = C.c_int(0), C.c_int(0)
+    sc = np.empty(h * w, np.uint8)
+    n = lib().orc_lsd_detect(_p(gray), w, h, _p(seg), cap, _p(sc), C.byref(sw), C.byref(sh))
+    assert n <= cap
+    if want_scaled:
+        return seg[:n].copy(), sc[:sw.value * sh.value].reshape(sh.value, sw.value).copy()
+    return seg[:n].copy()
+
+
+def line_extract(gray, n_features=200):
+    """LINEextractor::operator() restated: LSD -> keylines -> (if > n_features) response sort, truncate, renumber ->
+    LBD -> line functions.  Returns (keylines, desc, linevec [n,3] float64)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    kl = keylines_from_segments(lsd_detect(gray), w, h)
+    if len(kl) > n_features:  # sort_lines_by_response; ties keep detection order (std::sort leaves them unspecified)
+        order = np.argsort(-kl['response'], kind='stable')[:n_features]
+        kl = kl[order].copy()
+        kl['class_id'] = np.arange(n_features, dtype=np.int32)
+    desc = lbd_compute(gray, kl) if len(kl) else np.empty((0, 32), np.uint8)
+    sx, sy = kl['startPointX'].astype(np.float64), kl['startPointY'].astype(np.float64)
+    ex, ey = kl['endPointX'].astype(np.float64), kl['endPointY'].astype(np.float64)
+    l0, l1, l2 = sy - ey, ex - sx, sx * ey - sy * ex
+    nn = np.sqrt(l0 * l0 + l1 * l1)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        lv = np.stack([l0 / nn, l1 / nn, l2 / nn], axis=1)
+    return kl, desc, lv
+
+
 def lbd_gradients(gray):
     gray = np.ascontiguousarray(gray, np.uint8)
     dx = np.empty(gray.shape, np.int16); dy = np.empty(gray.shape, np.int16)

@@ -5,6 +5,8 @@ fixture, oracle/_ref/ref_orb = the reference's own src/ORBextractor.cc built by 
 
 prims_cv2.npz  inputs + outputs of the OpenCV primitives the reference calls (cv2 4.13.0 is the pin)
 orb_ref.npz    inputs + outputs of the reference's ORBextractor.cc on small frames
+lsd_cv2.npz    inputs + outputs of cv2.createLineSegmentDetector().detect (what LSDDetector_custom.cpp:149,158 calls) and of
+               the two cv2 primitives inside it (GaussianBlur 7x7 sigma 0.75, resize 0.8 INTER_LINEAR_EXACT)
 """
 import os
 import sys
@@ -90,6 +92,32 @@ def orb():
     print('orb_ref.npz written')
 
 
+def lsd():
+    assert cv2.__version__ == '4.13.0', cv2.__version__
+    cv2.setNumThreads(1)
+    det = cv2.createLineSegmentDetector()
+    g1, _ = synth.frame('S1', 3)
+    g2, _ = synth.frame('S2', 4)
+    cases = [('s1_crop', g1[60:300, 100:420].copy()), ('s2_crop', g2[100:340, 160:480].copy()),
+             ('s1_odd', g1[31:232, 17:350].copy()), ('noise', synth.noise_frame(160, 120, 7)),
+             ('flat', np.full((120, 160), 77, np.uint8))]
+    out = dict(cv2_version=np.array(cv2.__version__))
+    for name, img in cases:
+        seg = det.detect(img)[0]
+        seg = np.zeros((0, 4), np.float32) if seg is None else seg.reshape(-1, 4)
+        out[name + '_img'] = img
+        out[name + '_segments'] = seg
+        out[name + '_scaled'] = cv2.resize(cv2.GaussianBlur(img, (7, 7), 0.75), None, fx=0.8, fy=0.8, interpolation=cv2.INTER_LINEAR_EXACT)
+        print(name, img.shape, len(seg))
+    np.savez_compressed(os.path.join(OUT, 'lsd_cv2.npz'), **out)
+    print('lsd_cv2.npz written')
+
+
 if __name__ == '__main__':
-    prims()
-    orb()
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd']
+    if 'prims' in which:
+        prims()
+    if 'orb' in which:
+        orb()
+    if 'lsd' in which:
+        lsd()
