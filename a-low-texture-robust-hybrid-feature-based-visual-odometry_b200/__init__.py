@@ -101,6 +101,8 @@ ABI = {
     'hvo_plane_destroy': (None, [_vp]),
     'hvo_plane_detect': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     'hvo_plane_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'hvo_plane_detect_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'hvo_plane_last_launches': (C.c_int, [_vp]),
     'hvo_plane_blocks_device': (C.c_int, [_vp, _vp, C.c_int]),
     'hvo_plane_get_blocks': (C.c_int, [_vp, C.c_int, _vp]),
     'hvo_plane_sync': (C.c_int, [_vp]),
@@ -587,6 +589,12 @@ class PlaneDetection:
         out = np.empty(((self.h // 10) * (self.w // 10), 9), np.float64)
         _check(lib().hvo_plane_get_blocks(self._h, frame, _np_ptr(out)))
         return out
+
+    def detect_batch_device(self, d_depth, nframes, d_nplanes, d_planes7, max_planes, d_membership):
+        _check(lib().hvo_plane_detect_batch_device(self._h, _vp(d_depth), nframes, _vp(d_nplanes), _vp(d_planes7), max_planes, _vp(d_membership)))
+
+    def last_launches(self):
+        return lib().hvo_plane_last_launches(self._h)
 
     def blocks_device(self, d_depth, nframes):
         _check(lib().hvo_plane_blocks_device(self._h, _vp(d_depth), nframes))

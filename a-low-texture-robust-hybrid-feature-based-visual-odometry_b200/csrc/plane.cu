@@ -2,23 +2,20 @@
 // Replaces PlaneDetection::readDepthImage + runPlaneDetection (reference src/PlaneExtractor.cpp:26-66) and the
 // ahc::PlaneFitter they drive (include/peac/AHCPlaneFitter.hpp, AHCPlaneSeg.hpp, AHCParamSet.hpp).
 //
-//   k_plane_blocks   (device) depth back-projection fused with the 10x10-block plane seeds: validity (missing data,
-//                    right/down depth discontinuity), the nine second-order sums, centre, PCA normal, MSE.  The point
-//                    cloud (7.4 MB / frame in the reference) is never materialised.  One thread per block walks its
-//                    100 pixels in the reference's row-major order, so the double-precision sums are bit-identical.
-//   host             the graph part (edges, min-MSE merge, block erosion, pixel flood fill, last merge, membership
-//                    scan) is sequential and order-defined: it runs on the host from the block
-//                    statistics, one frame per worker thread for batches.
+//   k_plane_blocks   depth back-projection fused with the 10x10-block plane seeds: validity (missing data, right/down
+//                    depth discontinuity), the nine second-order sums, centre, PCA normal, MSE.  The point cloud
+//                    (7.4 MB / frame in the reference) is never materialised.  One thread per block walks its 100 pixels
+//                    in the reference's row-major order, so the double-precision sums are bit-identical.
+//   k_plane_ahc      the graph part, one CTA per frame (frames are independent, a batch fills the machine): initial
+//                    edges, min-MSE agglomerative merging (heap + disjoint set in shared memory, neighbour sets as a
+//                    bit matrix, merge candidates evaluated one per lane with a 3x3 Jacobi eigen-solve each), block
+//                    erosion, the ordered pixel flood fill (8 queue entries x 4 neighbours per warp step, same-pixel
+//                    hits applied in queue order), the last merge and the final relabelling.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <iterator>
 #include <limits>
-#include <map>
 #include <new>
-#include <queue>
-#include <thread>
-#include <vector>
 
 #include "hvo_common.cuh"
 
@@ -119,317 +116,593 @@ __global__ void __launch_bounds__(128) k_plane_blocks(const uint16_t* __restrict
     out[(long long)f * Nw * Nh + b] = o;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// host graph stage (array-based; node ids grow with creation so "set order" == creation order)
-// ------------------------------------------------------------------------------------------------------------
-struct HNode {
-    double s[9];
-    int N, rid;
-    double mse, center[3], normal[3];
-    bool nouse;
-    std::vector<int> nbs;  // sorted ascending, unique
+// --------------------------------------------------------------------------------------------------------------------
+// k_plane_ahc: the graph part of ahc::PlaneFitter::run, one CTA (4 warps) per frame.
+//
+// Node slots == block ids (creation order of the initial nodes == block scan order).  A merged node takes over the slot
+// of the popped node p (p is out of the heap by then, its partner stays in the heap as a `nouse` tombstone, exactly like
+// the reference's lazy deletion), so no slot beyond the initial Nb is ever needed.  `key` keeps the creation order
+// (reference: pointer / id order of std::set iteration, only consulted on exact MSE ties).  The neighbour sets are rows
+// of an Nb x Nb bit matrix in global memory: set union = OR of two rows, erase/insert = one bit.
+// The heap reproduces std::priority_queue (libstdc++ push_heap / pop_heap sift order) on mse.
+// --------------------------------------------------------------------------------------------------------------------
+struct __align__(16) NodeG { double s[9]; double center[3]; double normal[3]; int N; int rid; };  // 128 bytes
+
+static const int kMinSupport = 3000, kAhcThreads = 128;
+#define AHC_TH_MERGE 0.50000000000000011   /* cos(pi/180*60) as computed by std::cos */
+#define AHC_TH_REFINE 0.86602540378443871  /* cos(pi/180*30) */
+
+struct AhcArgs {
+    const uint16_t* depth;   // [B][h][w]
+    const BlockOut* blocks;  // [B][Nb]
+    NodeG* nodes;            // [B][Nb]
+    uint32_t* adj;           // [B][Nb][nw]   (zeroed before launch)
+    uint16_t* key;           // [B][Nb]
+    double* cand;            // [B][Nb]
+    float* dist;             // [B][h*w]
+    uint32_t* queue;         // [B][qcap]
+    int32_t* membership;     // [B][h*w]   working membershipImg, final labels on exit
+    double* planes7;         // [B][planes_stride][7]
+    int32_t* n_planes;       // [B]
+    int32_t* status;         // [B]  0 ok, 1 refinement queue overflow
+    int w, h, Nw, Nh, nw, qcap, max_ext, planes_stride;
+    PlaneCam cam;
+    double th_merge, th_refine;
 };
 
-static void nb_insert(std::vector<int>& v, int x) {
-    auto it = std::lower_bound(v.begin(), v.end(), x);
-    if (it == v.end() || *it != x) v.insert(it, x);
+__device__ __forceinline__ double ahc_t_ang_init(double z) {  // ParamSet::T_ang(P_INIT, z), AHCParamSet.hpp:99-115
+    const double z_near = 500, z_far = 4000, a_near = M_PI / 180.0 * 15.0, a_far = M_PI / 180.0 * 90.0;
+    double cz = fmax(z, z_near);
+    cz = fmin(cz, z_far);
+    const double factor = (a_far - a_near) / (z_far - z_near);
+    return cos(factor * cz + a_near - factor * z_near);
 }
-static void nb_erase(std::vector<int>& v, int x) {
-    auto it = std::lower_bound(v.begin(), v.end(), x);
-    if (it != v.end() && *it == x) v.erase(it);
+
+struct AhcS {  // views into dynamic shared memory
+    double* mse;        // [Nb]
+    uint16_t* heap;     // [Nb]  (aliased by blkmap between the two clustering passes)
+    uint16_t* list;     // [Nb]
+    uint16_t* parent;   // [Nb]
+    uint16_t* ssize;    // [Nb]
+    uint32_t* nouse;    // [ceil(Nb/32)]
+    double* pl;         // [max_ext][7] normal, center, mse of the extracted planes (refinement)
+    uint16_t* ext;      // [max_ext]
+    uint16_t* ext2;     // [max_ext]
+    int16_t* plidmap;   // [max_ext]
+    uint8_t* isvalid;   // [max_ext]
+    int* ctl;           // [8]: 0 heap size, 1 next key, 2 n_ext, 3 n_ext2, 4 queue tail
+};
+
+__device__ __forceinline__ void heap_push(AhcS& S, int v) {  // std::push_heap with comp(a, b) = mse[b] < mse[a]
+    int hole = S.ctl[0]++;
+    const double mv = S.mse[v];
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const int pv = S.heap[parent];
+        if (!(mv < S.mse[pv])) break;
+        S.heap[hole] = (uint16_t)pv;
+        hole = parent;
+    }
+    S.heap[hole] = (uint16_t)v;
 }
+__device__ __forceinline__ int heap_pop(AhcS& S) {  // std::pop_heap + pop_back
+    const int top = S.heap[0];
+    const int len = --S.ctl[0];  // elements remaining
+    if (len == 0) return top;
+    const int value = S.heap[len];
+    int hole = 0, child = 0;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (S.mse[S.heap[child - 1]] < S.mse[S.heap[child]]) --child;  // comp(first[child], first[child-1])
+        S.heap[hole] = S.heap[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        S.heap[hole] = S.heap[child - 1];
+        hole = child - 1;
+    }
+    const double mv = S.mse[value];  // __push_heap(first, hole, 0, value)
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const int pv = S.heap[parent];
+        if (!(mv < S.mse[pv])) break;
+        S.heap[hole] = (uint16_t)pv;
+        hole = parent;
+    }
+    S.heap[hole] = (uint16_t)value;
+    return top;
+}
+__device__ __forceinline__ int ds_find(const uint16_t* parent, int x) {
+    while (parent[x] != x) x = parent[x];
+    return x;
+}
+__device__ __forceinline__ void ds_union(AhcS& S, int x, int y) {  // DisjointSet::Union (union by size, ties keep x's root)
+    const int xr = ds_find(S.parent, x), yr = ds_find(S.parent, y);
+    if (xr == yr) return;
+    if (S.ssize[xr] < S.ssize[yr]) { S.parent[xr] = (uint16_t)yr; S.ssize[yr] = (uint16_t)(S.ssize[yr] + S.ssize[xr]); }
+    else { S.parent[yr] = (uint16_t)xr; S.ssize[xr] = (uint16_t)(S.ssize[xr] + S.ssize[yr]); }
+}
+__device__ __forceinline__ bool nouse_get(const AhcS& S, int i) { return (S.nouse[i >> 5] >> (i & 31)) & 1u; }
 
-struct HostAhc {
-    int width, height, Nw, Nh, minSupport = 3000, maxStep = 100000;
-    PlaneCam cam;
-    const uint16_t* depth;
-    std::vector<HNode> nodes;
-    std::vector<int> extracted, parent, ssize, membershipImg, blkMap;
-    std::vector<std::pair<int, int>> rfQueue;
-    const double th_merge = std::cos(M_PI / 180.0 * 60.0), th_refine = std::cos(M_PI / 180.0 * 30.0);
-
-    struct QCmp {
-        const std::vector<HNode>* n;
-        bool operator()(int a, int b) const { return (*n)[b].mse < (*n)[a].mse; }
-    };
-    typedef std::priority_queue<int, std::vector<int>, QCmp> MinQ;
-
-    int Find(int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
-    void Union(int x, int y) {
-        const int xr = Find(x), yr = Find(y);
-        if (xr == yr) return;
-        if (ssize[xr] < ssize[yr]) { parent[xr] = yr; ssize[yr] += ssize[xr]; }
-        else { parent[yr] = xr; ssize[xr] += ssize[yr]; }
-    }
-    double sim(const HNode& a, const HNode& b) const {
-        return std::abs(a.normal[0] * b.normal[0] + a.normal[1] * b.normal[1] + a.normal[2] * b.normal[2]);
-    }
-    static double t_ang_init(double z) {
-        const double z_near = 500, z_far = 4000, a_near = M_PI / 180.0 * 15.0, a_far = M_PI / 180.0 * 90.0;
-        double cz = std::max(z, z_near);
-        cz = std::min(cz, z_far);
-        const double factor = (a_far - a_near) / (z_far - z_near);
-        return std::cos(factor * cz + a_near - factor * z_near);
-    }
-    static double t_mse_merge(double z) { return std::pow(1.6e-6 * z * z + 8, 2); }
-    void connect(int a, int b) { nb_insert(nodes[a].nbs, b); nb_insert(nodes[b].nbs, a); }
-    void isolate(int a) {
-        for (int nb : nodes[a].nbs) nb_erase(nodes[nb].nbs, a);
-        nodes[a].nbs.clear();
-    }
-    bool point(int row, int col, double pt[3]) const {
-        const double z = (double)depth[(size_t)row * width + col] * cam.factor;
-        if (z == 0) return false;
-        pt[0] = ((double)col - cam.cx) * z / cam.fx;
-        pt[1] = ((double)row - cam.cy) * z / cam.fy;
-        pt[2] = z;
-        return true;
-    }
-
-    void cluster(MinQ& q) {
-        int step = 0;
-        while (!q.empty() && step <= maxStep) {
-            const int p = q.top();
-            q.pop();
-            if (nodes[p].nouse) continue;
-            int best = -1, best_nb = -1;
-            HNode bestNode;
-            const std::vector<int> nbs = nodes[p].nbs;
-            for (int nb : nbs) {
-                if (sim(nodes[p], nodes[nb]) < th_merge) continue;
-                HNode m;
-                for (int k = 0; k < 9; ++k) m.s[k] = nodes[p].s[k] + nodes[nb].s[k];
-                m.N = nodes[p].N + nodes[nb].N;
-                m.rid = nodes[p].N >= nodes[nb].N ? nodes[p].rid : nodes[nb].rid;
-                m.nouse = false;
-                double curv;
-                stats_compute(m.s, m.N, m.center, m.normal, m.mse, curv);
-                if (best < 0 || bestNode.mse > m.mse || (bestNode.mse == m.mse && bestNode.N < m.mse)) {  // N vs mse: AHCPlaneFitter.hpp:1045
-                    best = 1; best_nb = nb; bestNode = m;
+// PlaneFitter::ahCluster (AHCPlaneFitter.hpp:983-1189).  Warp-collective (warp 0); extracted planes appended to out[].
+__device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* adj, uint16_t* key, double* cand, uint16_t* out,
+                            int* n_out, int lane) {
+    const int nw = A.nw;
+    while (true) {
+        int p = -1;
+        if (lane == 0) {
+            while (S.ctl[0] > 0) { const int q = heap_pop(S); if (!nouse_get(S, q)) { p = q; break; } }
+        }
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p < 0) break;
+        uint32_t* rowp = adj + (size_t)p * nw;
+        // neighbour list (ascending slot)
+        int cnt = 0;
+        for (int w0 = 0; w0 < nw; w0 += 32) {
+            uint32_t word = (w0 + lane < nw) ? rowp[w0 + lane] : 0u;
+            const int c = __popc(word);
+            int pre = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            int pos = cnt + pre - c;
+            while (word) { const int b = __ffs(word) - 1; word &= word - 1; S.list[pos++] = (uint16_t)((w0 + lane) * 32 + b); }
+            cnt += total;
+        }
+        __syncwarp();
+        const NodeG P = nodes[p];
+        // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge
+        double bm = INFINITY;
+        for (int base = 0; base < cnt; base += 32) {
+            const int i = base + lane;
+            double m = INFINITY;
+            if (i < cnt) {
+                const NodeG* Q = nodes + S.list[i];
+                const double sim = fabs(P.normal[0] * Q->normal[0] + P.normal[1] * Q->normal[1] + P.normal[2] * Q->normal[2]);
+                if (!(sim < A.th_merge)) {
+                    double s[9], c[3], n[3], curv;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s[k] = P.s[k] + Q->s[k];
+                    stats_compute(s, P.N + Q->N, c, n, m, curv);
+                    if (!(m == m)) m = INFINITY;  // NaN never wins a `>` comparison in the reference either
+                }
+                cand[i] = m;
+            }
+            bm = fmin(bm, m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        __syncwarp();
+        int best_i = -1;
+        if (bm < INFINITY) {
+            int ties = 0, first = 0x7fffffff;
+            for (int base = 0; base < cnt; base += 32) {
+                const int i = base + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, i < cnt && cand[i] == bm);
+                if (m) { ties += __popc(m); first = min(first, base + __ffs(m) - 1); }
+            }
+            if (ties == 1) {
+                best_i = first;
+            } else {
+                // exact MSE tie: the reference folds in set order (creation order) and replaces the incumbent only if
+                // incumbent.N < candidate.mse (sic, AHCPlaneFitter.hpp:1045)
+                if (lane == 0) {
+                    int inc = -1;
+                    unsigned last_key = 0;
+                    for (int t = 0; t < ties; ++t) {
+                        int pick = -1;
+                        unsigned pk = 0xffffffffu;
+                        for (int i = 0; i < cnt; ++i) {
+                            if (cand[i] != bm) continue;
+                            const unsigned k = key[S.list[i]];
+                            if ((t == 0 || k > last_key) && k < pk) { pk = k; pick = i; }
+                        }
+                        last_key = pk;
+                        if (inc < 0 || (double)(P.N + nodes[S.list[inc]].N) < bm) inc = pick;
+                    }
+                    best_i = inc;
+                }
+                best_i = __shfl_sync(0xffffffffu, best_i, 0);
+            }
+        }
+        bool merged = false;
+        int nb = -1;
+        double ms[9], mc[3], mn[3], mm = 0, curv;
+        int mN = 0, mrid = 0;
+        if (best_i >= 0) {
+            nb = S.list[best_i];
+            const NodeG Q = nodes[nb];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ms[k] = P.s[k] + Q.s[k];
+            mN = P.N + Q.N;
+            mrid = P.N >= Q.N ? P.rid : Q.rid;
+            stats_compute(ms, mN, mc, mn, mm, curv);
+            const double t = 1.6e-6 * mc[2] * mc[2] + 8;  // ParamSet::T_mse(P_MERGING)
+            merged = mm < t * t;
+            if (merged && lane == 0) ds_union(S, P.rid, Q.rid);
+        }
+        __syncwarp();
+        if (merged) {
+            uint32_t* rownb = adj + (size_t)nb * nw;
+            // row[p] = (row[p] | row[nb]) \ {p, nb};  row[nb] = {}
+            for (int wi = lane; wi < nw; wi += 32) {
+                uint32_t v = rowp[wi] | rownb[wi];
+                if (wi == (p >> 5)) v &= ~(1u << (p & 31));
+                if (wi == (nb >> 5)) v &= ~(1u << (nb & 31));
+                rowp[wi] = v;
+                rownb[wi] = 0u;
+                // every neighbour x of the merged node: erase nb, insert p
+                while (v) {
+                    const int x = wi * 32 + __ffs(v) - 1;
+                    v &= v - 1;
+                    uint32_t* rx = adj + (size_t)x * nw;
+                    atomicAnd(&rx[nb >> 5], ~(1u << (nb & 31)));
+                    atomicOr(&rx[p >> 5], 1u << (p & 31));
                 }
             }
-            if (best >= 0 && bestNode.mse < t_mse_merge(bestNode.center[2])) {
-                const int nb = best_nb;
-                Union(nodes[p].rid, nodes[nb].rid);
-                std::vector<int> u;
-                std::set_union(nodes[p].nbs.begin(), nodes[p].nbs.end(), nodes[nb].nbs.begin(), nodes[nb].nbs.end(), std::back_inserter(u));
-                nb_erase(u, p);
-                nb_erase(u, nb);
-                bestNode.nbs = u;
-                nodes.push_back(bestNode);
-                const int id = (int)nodes.size() - 1;
-                q.push(id);
-                isolate(p);
-                isolate(nb);
-                for (int x : u) nb_insert(nodes[x].nbs, id);
-                nodes[p].nouse = nodes[nb].nouse = true;
-            } else {
-                if (nodes[p].N >= minSupport) extracted.push_back(p);
-                isolate(p);
+            if (lane == 0) {
+                NodeG M;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) M.s[k] = ms[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { M.center[k] = mc[k]; M.normal[k] = mn[k]; }
+                M.N = mN; M.rid = mrid;
+                nodes[p] = M;
+                S.mse[p] = mm;
+                key[p] = (uint16_t)S.ctl[1]++;
+                S.nouse[nb >> 5] |= 1u << (nb & 31);
+                heap_push(S, p);
             }
-            ++step;
+        } else {
+            if (lane == 0 && P.N >= kMinSupport) out[(*n_out)++] = (uint16_t)p;
+            for (int i = lane; i < cnt; i += 32) {  // disconnectAllNbs
+                uint32_t* rx = adj + (size_t)S.list[i] * nw;
+                atomicAnd(&rx[p >> 5], ~(1u << (p & 31)));
+            }
+            for (int wi = lane; wi < nw; wi += 32) rowp[wi] = 0u;
         }
-        while (!q.empty()) {
-            const int p = q.top();
-            q.pop();
-            if (nodes[p].N >= minSupport) extracted.push_back(p);
-            isolate(p);
+        __threadfence_block();
+        __syncwarp();
+    }
+    // extractedPlanes sorted by N descending (std::sort on <= 16 elements is an insertion sort; kept stable beyond that)
+    if (lane == 0) {
+        const int n = *n_out;
+        for (int i = 1; i < n; ++i) {
+            const uint16_t v = out[i];
+            const int vn = nodes[v].N;
+            int j = i - 1;
+            while (j >= 0 && nodes[out[j]].N < vn) { out[j + 1] = out[j]; --j; }
+            out[j + 1] = v;
         }
-        std::sort(extracted.begin(), extracted.end(), [this](int a, int b) { return nodes[b].N < nodes[a].N; });
     }
+    __syncwarp();
+}
 
-    static int valid4(int i, int j, int H, int W, int nbs[4]) {
-        const int id = i * W + j;
-        int c = 0;
-        if (j > 0) nbs[c++] = id - 1;
-        if (j < W - 1) nbs[c++] = id + 1;
-        if (i > 0) nbs[c++] = id - W;
-        if (i < H - 1) nbs[c++] = id + W;
-        return c;
+__global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh, W = A.w, H = A.h, npix = W * H;
+    AhcS S;
+    {
+        unsigned char* p = smem_raw;
+        S.mse = (double*)p; p += (size_t)Nb * 8;
+        S.pl = (double*)p; p += (size_t)A.max_ext * 7 * 8;
+        S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
+        S.ctl = (int*)p; p += 8 * 4;
+        S.heap = (uint16_t*)p; p += (size_t)Nb * 2;
+        S.list = (uint16_t*)p; p += (size_t)Nb * 2;
+        S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
+        S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
+        S.ext = (uint16_t*)p; p += (size_t)A.max_ext * 2;
+        S.ext2 = (uint16_t*)p; p += (size_t)A.max_ext * 2;
+        S.plidmap = (int16_t*)p; p += (size_t)A.max_ext * 2;
+        S.isvalid = (uint8_t*)p;
     }
+    int16_t* blkmap = (int16_t*)S.heap;  // valid between the two clustering passes only
+    const uint16_t* D = A.depth + (size_t)f * npix;
+    const BlockOut* blocks = A.blocks + (size_t)f * Nb;
+    NodeG* nodes = A.nodes + (size_t)f * Nb;
+    uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
+    uint16_t* key = A.key + (size_t)f * Nb;
+    double* cand = A.cand + (size_t)f * Nb;
+    float* dist = A.dist + (size_t)f * npix;
+    volatile uint32_t* queue = A.queue + (size_t)f * A.qcap;
+    volatile int32_t* mem = A.membership + (size_t)f * npix;
 
-    int run(const BlockOut* blocks, int32_t* membership, double* planes7, int max_planes) {
-        nodes.clear(); extracted.clear(); rfQueue.clear();
-        nodes.reserve(3 * (size_t)Nw * Nh);
-        parent.resize(Nw * Nh); ssize.assign(Nw * Nh, 1);
-        for (int i = 0; i < Nw * Nh; ++i) parent[i] = i;
-        QCmp cmp{&nodes};
-        MinQ q(cmp);
-        // nodes of the initial graph (AHCPlaneFitter.hpp:786-826)
-        std::vector<int> G(Nw * Nh, -1);
-        for (int b = 0; b < Nw * Nh; ++b) {
-            if (!blocks[b].queued) continue;
-            HNode n;
-            std::memcpy(n.s, blocks[b].s, sizeof(n.s));
-            n.N = blocks[b].N; n.rid = b; n.nouse = false;
+    // ---- initial graph nodes (AHCPlaneFitter.hpp:786-826) ----
+    for (int b = tid; b < Nb; b += kAhcThreads) {
+        const BlockOut o = blocks[b];
+        S.parent[b] = (uint16_t)b; S.ssize[b] = 1; key[b] = (uint16_t)b;
+        double m = INFINITY;
+        if (o.queued) {
+            NodeG n;
             double curv;
-            stats_compute(n.s, n.N, n.center, n.normal, n.mse, curv);
-            nodes.push_back(n);
-            G[b] = (int)nodes.size() - 1;
-            q.push(G[b]);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) n.s[k] = o.s[k];
+            n.N = o.N; n.rid = b;
+            stats_compute(n.s, n.N, n.center, n.normal, m, curv);
+            nodes[b] = n;
         }
-        // edges (AHCPlaneFitter.hpp:896-954)
-        for (int i = 0; i < Nh; ++i)
+        S.mse[b] = m;
+    }
+    for (int i = tid; i < (Nb + 31) / 32; i += kAhcThreads) S.nouse[i] = 0u;
+    for (int i = tid; i < A.max_ext; i += kAhcThreads) { S.isvalid[i] = 0; S.plidmap[i] = -1; }
+    if (tid == 0) { S.ctl[0] = 0; S.ctl[1] = Nb; S.ctl[2] = 0; S.ctl[3] = 0; S.ctl[4] = 0; A.status[f] = 0; }
+    __threadfence_block();
+    __syncthreads();
+    if (wid == 0) {
+        if (lane == 0)
+            for (int b = 0; b < Nb; ++b) if (blocks[b].queued) heap_push(S, b);
+        // ---- edges (AHCPlaneFitter.hpp:896-954): rows, then columns ----
+        for (int i = lane; i < Nh; i += 32)
             for (int j = 1; j < Nw; j += 2) {
                 const int c = i * Nw + j;
-                if (G[c - 1] < 0) { --j; continue; }
-                if (G[c] < 0) continue;
-                if (j < Nw - 1 && G[c + 1] < 0) { ++j; continue; }
-                const double th = t_ang_init(nodes[G[c]].center[2]);
-                if ((j < Nw - 1 && sim(nodes[G[c - 1]], nodes[G[c + 1]]) >= th) || (j == Nw - 1 && sim(nodes[G[c]], nodes[G[c - 1]]) >= th)) {
-                    connect(G[c], G[c - 1]);
-                    if (j < Nw - 1) connect(G[c], G[c + 1]);
+                if (!blocks[c - 1].queued) { --j; continue; }
+                if (!blocks[c].queued) continue;
+                if (j < Nw - 1 && !blocks[c + 1].queued) { ++j; continue; }
+                const double th = ahc_t_ang_init(nodes[c].center[2]);
+                const double* n0 = nodes[c - 1].normal;
+                const double* n1 = (j < Nw - 1) ? nodes[c + 1].normal : nodes[c].normal;
+                if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
+                    atomicOr(&adj[(size_t)c * A.nw + ((c - 1) >> 5)], 1u << ((c - 1) & 31));
+                    atomicOr(&adj[(size_t)(c - 1) * A.nw + (c >> 5)], 1u << (c & 31));
+                    if (j < Nw - 1) {
+                        atomicOr(&adj[(size_t)c * A.nw + ((c + 1) >> 5)], 1u << ((c + 1) & 31));
+                        atomicOr(&adj[(size_t)(c + 1) * A.nw + (c >> 5)], 1u << (c & 31));
+                    }
                 } else {
                     --j;
                 }
             }
-        for (int j = 0; j < Nw; ++j)
+        __threadfence_block();
+        __syncwarp();
+        for (int j = lane; j < Nw; j += 32)
             for (int i = 1; i < Nh; i += 2) {
                 const int c = i * Nw + j;
-                if (G[c - Nw] < 0) { --i; continue; }
-                if (G[c] < 0) continue;
-                if (i < Nh - 1 && G[c + Nw] < 0) { ++i; continue; }
-                const double th = t_ang_init(nodes[G[c]].center[2]);
-                if ((i < Nh - 1 && sim(nodes[G[c - Nw]], nodes[G[c + Nw]]) >= th) || (i == Nh - 1 && sim(nodes[G[c]], nodes[G[c - Nw]]) >= th)) {
-                    connect(G[c], G[c - Nw]);
-                    if (i < Nh - 1) connect(G[c], G[c + Nw]);
+                if (!blocks[c - Nw].queued) { --i; continue; }
+                if (!blocks[c].queued) continue;
+                if (i < Nh - 1 && !blocks[c + Nw].queued) { ++i; continue; }
+                const double th = ahc_t_ang_init(nodes[c].center[2]);
+                const double* n0 = nodes[c - Nw].normal;
+                const double* n1 = (i < Nh - 1) ? nodes[c + Nw].normal : nodes[c].normal;
+                if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
+                    atomicOr(&adj[(size_t)c * A.nw + ((c - Nw) >> 5)], 1u << ((c - Nw) & 31));
+                    atomicOr(&adj[(size_t)(c - Nw) * A.nw + (c >> 5)], 1u << (c & 31));
+                    if (i < Nh - 1) {
+                        atomicOr(&adj[(size_t)c * A.nw + ((c + Nw) >> 5)], 1u << ((c + Nw) & 31));
+                        atomicOr(&adj[(size_t)(c + Nw) * A.nw + (c >> 5)], 1u << (c & 31));
+                    }
                 } else {
                     --i;
                 }
             }
-        cluster(q);
-
-        // refineDetails: block erosion + seeds (AHCPlaneFitter.hpp:485-587)
-        std::map<int, int> rid2plid;
-        for (int plid = 0; plid < (int)extracted.size(); ++plid) rid2plid.insert(std::make_pair(nodes[extracted[plid]].rid, plid));
-        membershipImg.assign((size_t)width * height, -1);
-        blkMap.assign(Nw * Nh, -1);
-        std::vector<char> isValid(extracted.size(), 0);
-        for (int i = 0, blkid = 0; i < Nh; ++i)
-            for (int j = 0; j < Nw; ++j, ++blkid) {
-                const int setid = Find(blkid);
-                if (ssize[setid] * 100 >= minSupport) {
-                    int nb4[4];
-                    const int nn = valid4(i, j, Nh, Nw, nb4);
-                    bool same = true;
-                    for (int k = 0; k < nn; ++k)
-                        if (Find(nb4[k]) != setid) { same = false; break; }
-                    const int plid = rid2plid[setid];
-                    if (same && plid < (int)isValid.size()) {
-                        blkMap[blkid] = plid;
-                        for (int y = i * 10; y < (i + 1) * 10; ++y)
-                            for (int x = j * 10; x < (j + 1) * 10; ++x) membershipImg[(size_t)y * width + x] = plid;
-                        isValid[plid] = 1;
-                    }
-                }
-                if (blkMap[blkid] < 0) {
-                    if (i > 0 && blkMap[blkid - Nw] >= 0) {
-                        const int u = blkMap[blkid - Nw], sp = (i * 10 - 1) * width + j * 10;
-                        for (int k = 1; k < 10; ++k) rfQueue.push_back(std::make_pair(sp + k, u));
-                    }
-                    if (j > 0 && blkMap[blkid - 1] >= 0) {
-                        const int l = blkMap[blkid - 1], sp = (i * 10) * width + j * 10 - 1;
-                        for (int k = 0; k < 9; ++k) rfQueue.push_back(std::make_pair(sp + k * width, l));
-                    }
-                } else {
-                    const int plid = blkMap[blkid];
-                    if (i > 0 && blkMap[blkid - Nw] != plid) {
-                        const int sp = (i * 10) * width + j * 10;
-                        for (int k = 0; k < 9; ++k) rfQueue.push_back(std::make_pair(sp + k, plid));
-                    }
-                    if (j > 0 && blkMap[blkid - 1] != plid) {
-                        const int sp = (i * 10) * width + j * 10;
-                        for (int k = 1; k < 10; ++k) rfQueue.push_back(std::make_pair(sp + k * width, plid));
-                    }
-                }
-            }
-        // pixel-level region growing (AHCPlaneFitter.hpp:428-476)
-        {
-            std::vector<float> distMap((size_t)height * width, std::numeric_limits<float>::max());
-            for (size_t k = 0; k < rfQueue.size(); ++k) {
-                const int sIdx = rfQueue[k].first, sy = sIdx / width, sx = sIdx - sy * width, plid = rfQueue[k].second;
-                const HNode& pl = nodes[extracted[plid]];
-                int nb4[4];
-                const int nn = valid4(sy, sx, height, width, nb4);
-                for (int it = 0; it < nn; ++it) {
-                    const int cIdx = nb4[it];
-                    int& trail = membershipImg[cIdx];
-                    if (trail <= -6) continue;
-                    if (trail >= 0 && trail == plid) continue;
-                    const int cy = cIdx / width, cx = cIdx - cy * width;
-                    const int by = cy / 10, bx = cx / 10;
-                    const int blkid = (by < Nh && bx < Nw) ? by * Nw + bx : -1;
-                    if (blkid >= 0 && blkMap[blkid] >= 0) continue;
-                    double pt[3];
-                    float cdist = -1;
-                    bool ok = point(cy, cx, pt);
-                    if (ok) {
-                        cdist = (float)std::abs(pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1]) +
-                                                pl.normal[2] * (pt[2] - pl.center[2]));
-                        ok = std::pow((double)cdist, 2) < 9 * pl.mse + 1e-5;
-                    }
-                    if (ok) {
-                        if (trail >= 0 && sim(pl, nodes[extracted[trail]]) >= th_refine) connect(extracted[trail], extracted[plid]);
-                        float& od = distMap[cIdx];
-                        if (cdist < od) { trail = plid; od = cdist; rfQueue.push_back(std::make_pair(cIdx, plid)); }
-                        else if (trail < 0) trail -= 1;
-                    } else if (trail < 0) {
-                        trail -= 1;
-                    }
-                }
-            }
-        }
-        // last merge among the refined planes, then relabel (AHCPlaneFitter.hpp:317-371)
-        std::vector<int> old;
-        extracted.swap(old);
-        MinQ q2(cmp);
-        for (size_t i = 0; i < old.size(); ++i)
-            if (isValid[i]) q2.push(old[i]);
-        cluster(q2);
-        std::vector<int> plidmap(old.size(), -1);
-        for (size_t i = 0; i < old.size(); ++i) {
-            if (!isValid[i]) continue;
-            const int r = Find(nodes[old[i]].rid);
-            for (size_t j = 0; j < extracted.size(); ++j)
-                if (r == nodes[extracted[j]].rid) { plidmap[i] = (int)j; break; }
-        }
-        for (size_t i = 0; i < membershipImg.size(); ++i) {
-            const int plid = membershipImg[i];
-            membership[i] = (plid >= 0 && plidmap[plid] >= 0) ? plidmap[plid] : -1;
-        }
-        const int n = (int)extracted.size();
-        for (int i = 0; i < n && i < max_planes; ++i) {
-            const HNode& p = nodes[extracted[i]];
-            double* o = planes7 + 7 * (size_t)i;
-            for (int k = 0; k < 3; ++k) { o[k] = p.normal[k]; o[3 + k] = p.center[k]; }
-            o[6] = p.N;
-        }
-        return n;
+        __threadfence_block();
+        __syncwarp();
+        ahc_cluster(A, S, nodes, adj, key, cand, S.ext, &S.ctl[2], lane);
     }
-};
+    __syncthreads();
+    const int ne = S.ctl[2];
+    // ---- refineDetails: findBlockMembership (AHCPlaneFitter.hpp:485-587) ----
+    for (int i = tid; i < ne; i += kAhcThreads) {
+        const NodeG* n = nodes + S.ext[i];
+        double* o = S.pl + 7 * i;
+        o[0] = n->normal[0]; o[1] = n->normal[1]; o[2] = n->normal[2];
+        o[3] = n->center[0]; o[4] = n->center[1]; o[5] = n->center[2];
+        o[6] = S.mse[S.ext[i]];
+    }
+    for (int b = tid; b < Nb; b += kAhcThreads) S.list[b] = (uint16_t)ds_find(S.parent, b);  // set id of every block
+    __syncthreads();
+    for (int b = tid; b < Nb; b += kAhcThreads) {
+        const int i = b / Nw, j = b - i * Nw, setid = S.list[b];
+        int bm = -1;
+        if ((int)S.ssize[setid] * 100 >= kMinSupport) {
+            bool same = true;
+            if (j > 0 && S.list[b - 1] != setid) same = false;
+            if (j < Nw - 1 && S.list[b + 1] != setid) same = false;
+            if (i > 0 && S.list[b - Nw] != setid) same = false;
+            if (i < Nh - 1 && S.list[b + Nw] != setid) same = false;  // ERODE_ALL_BORDER
+            int plid = 0;  // std::map::operator[] yields 0 for an unknown set id (reference quirk)
+            for (int e = 0; e < ne; ++e) if (nodes[S.ext[e]].rid == setid) { plid = e; break; }
+            if (same && plid < ne) { bm = plid; S.isvalid[plid] = 1; }
+        }
+        blkmap[b] = (int16_t)bm;
+    }
+    __syncthreads();
+    // membershipImg: block label inside eroded member blocks, -1 elsewhere; distMap = FLT_MAX
+    for (int y = wid; y < H; y += kAhcThreads / 32) {
+        const int by = y / 10;
+        for (int x = lane; x < W; x += 32) {
+            const int bx = x / 10;
+            mem[(size_t)y * W + x] = (by < Nh && bx < Nw) ? (int)blkmap[by * Nw + bx] : -1;
+            dist[(size_t)y * W + x] = 3.402823466e+38f;
+        }
+    }
+    // refinement seeds, in block scan order
+    if (wid == 0) {
+        int tail = 0;
+        for (int b0 = 0; b0 < Nb; b0 += 32) {
+            const int b = b0 + lane;
+            int c0 = 0, c1 = 0, i = 0, j = 0, me = -1;
+            if (b < Nb) {
+                i = b / Nw; j = b - i * Nw; me = blkmap[b];
+                if (me < 0) { c0 = (i > 0 && blkmap[b - Nw] >= 0); c1 = (j > 0 && blkmap[b - 1] >= 0); }
+                else { c0 = (i > 0 && blkmap[b - Nw] != me); c1 = (j > 0 && blkmap[b - 1] != me); }
+            }
+            const int c = 9 * (c0 + c1);
+            int pre = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            int pos = tail + pre - c;
+            if (c && pos + c <= A.qcap) {
+                if (me < 0) {
+                    if (c0) { const uint32_t u = (uint32_t)blkmap[b - Nw] << 20; const int sp = (i * 10 - 1) * W + j * 10; for (int k = 1; k < 10; ++k) queue[pos++] = (uint32_t)(sp + k) | u; }
+                    if (c1) { const uint32_t l = (uint32_t)blkmap[b - 1] << 20; const int sp = (i * 10) * W + j * 10 - 1; for (int k = 0; k < 9; ++k) queue[pos++] = (uint32_t)(sp + k * W) | l; }
+                } else {
+                    const uint32_t u = (uint32_t)me << 20;
+                    const int sp = (i * 10) * W + j * 10;
+                    if (c0) for (int k = 0; k < 9; ++k) queue[pos++] = (uint32_t)(sp + k) | u;
+                    if (c1) for (int k = 1; k < 10; ++k) queue[pos++] = (uint32_t)(sp + k * W) | u;
+                }
+            }
+            tail += total;
+        }
+        if (lane == 0) S.ctl[4] = tail;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (wid == 0) {
+        // ---- floodFill (AHCPlaneFitter.hpp:428-476): FIFO over (pixel, plane) seeds; 8 queue entries x 4 neighbours per
+        // step; lanes that hit the same pixel in one step are applied in queue order ----
+        int head = 0, tail = S.ctl[4];
+        bool overflow = tail > A.qcap;
+        if (overflow) tail = 0;
+        const int e = lane >> 2, it = lane & 3;
+        while (head < tail) {
+            const int nbat = min(8, tail - head);
+            bool valid = e < nbat;
+            int cIdx = -1, plid = 0;
+            bool ok = false;
+            float cdist = -1.f;
+            if (valid) {
+                const uint32_t q = queue[head + e];
+                const int sIdx = (int)(q & 0xfffffu);
+                plid = (int)(q >> 20);
+                const int sy = sIdx / W, sx = sIdx - sy * W;
+                int nb4[4], c = 0;
+                if (sx > 0) nb4[c++] = sIdx - 1;
+                if (sx < W - 1) nb4[c++] = sIdx + 1;
+                if (sy > 0) nb4[c++] = sIdx - W;
+                if (sy < H - 1) nb4[c++] = sIdx + W;
+                valid = it < c;
+                if (valid) {
+                    cIdx = it == 0 ? nb4[0] : (it == 1 ? nb4[1] : (it == 2 ? nb4[2] : nb4[3]));
+                    const int cy = cIdx / W, cx = cIdx - cy * W;
+                    const int by = cy / 10, bx = cx / 10;
+                    if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) valid = false;  // inside an eroded member block
+                    else {
+                        const double z = (double)D[cIdx] * A.cam.factor;
+                        if (z != 0) {
+                            const double px = ((double)cx - A.cam.cx) * z / A.cam.fx, py = ((double)cy - A.cam.cy) * z / A.cam.fy;
+                            const double* pl = S.pl + 7 * plid;
+                            cdist = (float)fabs(pl[0] * (px - pl[3]) + pl[1] * (py - pl[4]) + pl[2] * (z - pl[5]));
+                            ok = (double)cdist * (double)cdist < 9 * pl[6] + 1e-5;
+                        }
+                    }
+                }
+            }
+            const unsigned grp = __match_any_sync(0xffffffffu, valid ? cIdx : -1 - lane);
+            const int rank = __popc(grp & ((1u << lane) - 1u));
+            int rounds = valid ? __popc(grp) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+            bool push = false;
+            for (int r = 0; r < rounds; ++r) {
+                if (valid && rank == r) {
+                    const int trail = mem[cIdx];
+                    if (trail > -6 && !(trail >= 0 && trail == plid)) {
+                        if (ok) {
+                            if (trail >= 0) {
+                                const double *a = S.pl + 7 * plid, *b = S.pl + 7 * trail;
+                                if (fabs(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) >= A.th_refine) {  // connect(planes)
+                                    const int na = S.ext[trail], nbn = S.ext[plid];
+                                    atomicOr(&adj[(size_t)na * A.nw + (nbn >> 5)], 1u << (nbn & 31));
+                                    atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
+                                }
+                            }
+                            if (cdist < dist[cIdx]) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
+                            else if (trail < 0) mem[cIdx] = trail - 1;
+                        } else if (trail < 0) {
+                            mem[cIdx] = trail - 1;
+                        }
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, push);
+            if (push) {
+                const int pos = tail + __popc(pm & ((1u << lane) - 1u));
+                if (pos < A.qcap) queue[pos] = (uint32_t)cIdx | ((uint32_t)plid << 20);
+            }
+            tail += __popc(pm);
+            if (tail > A.qcap) { overflow = true; tail = A.qcap; }
+            head += nbat;
+            __threadfence_block();
+            __syncwarp();
+        }
+        if (lane == 0 && overflow) A.status[f] = 1;
+        // ---- last merge among the refined planes (AHCPlaneFitter.hpp:317-371) ----
+        if (lane == 0) {
+            S.ctl[0] = 0;
+            for (int i = 0; i < ne; ++i) if (S.isvalid[i]) heap_push(S, S.ext[i]);
+        }
+        __syncwarp();
+        ahc_cluster(A, S, nodes, adj, key, cand, S.ext2, &S.ctl[3], lane);
+        const int ne2 = S.ctl[3];
+        for (int i = lane; i < ne; i += 32) {
+            int m = -1;
+            if (S.isvalid[i]) {
+                const int r = ds_find(S.parent, nodes[S.ext[i]].rid);
+                for (int j = 0; j < ne2; ++j) if (nodes[S.ext2[j]].rid == r) { m = j; break; }
+            }
+            S.plidmap[i] = (int16_t)m;
+        }
+        for (int i = lane; i < ne2 && i < A.planes_stride; i += 32) {
+            const NodeG* n = nodes + S.ext2[i];
+            double* o = A.planes7 + ((size_t)f * A.planes_stride + i) * 7;
+            o[0] = n->normal[0]; o[1] = n->normal[1]; o[2] = n->normal[2];
+            o[3] = n->center[0]; o[4] = n->center[1]; o[5] = n->center[2];
+            o[6] = (double)n->N;
+        }
+        if (lane == 0) A.n_planes[f] = ne2;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- final labels ----
+    for (int i = tid; i < npix; i += kAhcThreads) {
+        const int plid = mem[i];
+        mem[i] = (plid >= 0) ? (int)S.plidmap[plid] : -1;
+    }
+}
 
 }  // namespace hvo
 
 using namespace hvo;
 
 struct hvo_plane {
-    int device = 0, width = 0, height = 0, max_batch = 0, Nw = 0, Nh = 0;
+    int device = 0, width = 0, height = 0, max_batch = 0, Nw = 0, Nh = 0, nw = 0, qcap = 0, max_ext = 0;
+    size_t ahc_smem = 0;
     PlaneCam cam;
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[2] = {nullptr, nullptr};
     uint16_t* d_depth = nullptr;
     BlockOut* d_blocks = nullptr;
-    BlockOut* h_blocks = nullptr;  // pinned
-    int host_threads = 1;
+    BlockOut* h_blocks = nullptr;  // pinned, one frame (inspection)
+    NodeG* d_nodes = nullptr;
+    uint32_t* d_adj = nullptr;
+    uint16_t* d_key = nullptr;
+    double* d_cand = nullptr;
+    float* d_dist = nullptr;
+    uint32_t* d_queue = nullptr;
+    int32_t* d_mem = nullptr;
+    double* d_planes = nullptr;  // [B][max_ext][7]
+    int32_t *d_nplanes = nullptr, *d_status = nullptr;
+    int32_t* h_status = nullptr;  // pinned [B]
+    int last_launches = 0;
 };
 
 extern "C" {
 
 int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_batch, int device, hvo_plane** out) {
-    HVO_CHECK_ARG(p && out, "null argument");
+    HVO_CHECK_ARG(out, "null out");
     *out = nullptr;
-    HVO_CHECK_ARG(width >= 20 && height >= 20 && max_batch >= 1, "size out of range");
-    HVO_CHECK_ARG(p->fx != 0.f && p->fy != 0.f, "focal length is zero");
+    HVO_CHECK_ARG(p, "null params");
+    HVO_CHECK_ARG(width >= 20 && height >= 20 && width <= 8192 && height <= 8192, "image size out of range");
+    HVO_CHECK_ARG((long long)width * height < (1 << 20), "image too large for the 20-bit pixel index of the refinement queue");
+    HVO_CHECK_ARG(max_batch >= 1, "max_batch < 1");
+    HVO_CHECK_ARG(p->fx != 0 && p->fy != 0, "fx / fy must be non-zero");
     int ndev = 0;
     HVO_CUDA(cudaGetDeviceCount(&ndev));
     if (ndev < 1) { set_error("no CUDA device: libhvofront has no CPU fallback"); return HVO_ERR_CUDA; }
@@ -438,17 +711,41 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
     if (!h) { set_error("out of host memory"); return HVO_ERR_ARG; }
     h->device = device; h->width = width; h->height = height; h->max_batch = max_batch;
     h->Nw = width / 10; h->Nh = height / 10;
+    const int Nb = h->Nw * h->Nh;
+    HVO_CHECK_ARG(Nb < 65536, "too many 10x10 blocks for 16-bit node ids");
+    h->nw = (Nb + 31) / 32;
+    h->qcap = 2 * width * height;
+    h->max_ext = Nb * 100 / kMinSupport + 2;
     h->cam.factor = (double)p->depth_factor; h->cam.fx = (double)p->fx; h->cam.fy = (double)p->fy;
     h->cam.cx = (double)p->cx; h->cam.cy = (double)p->cy;
-    h->host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&h->tev[0]);
-    if (e == cudaSuccess) e = cudaEventCreate(&h->tev[1]);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_depth, (size_t)max_batch * width * height * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_blocks, (size_t)max_batch * h->Nw * h->Nh * sizeof(BlockOut));
-    if (e == cudaSuccess) e = cudaMallocHost(&h->h_blocks, (size_t)max_batch * h->Nw * h->Nh * sizeof(BlockOut));
-    if (e != cudaSuccess) { set_error("hvo_plane_create: %s", cudaGetErrorString(e)); hvo_plane_destroy(h); return HVO_ERR_CUDA; }
+    h->ahc_smem = (size_t)Nb * 8 + (size_t)h->max_ext * 56 + (size_t)h->nw * 4 + 32 + (size_t)Nb * 8 + (size_t)h->max_ext * 7 + 16;
+    int st = HVO_OK;
+    do {
+#define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
+        HVO_TRY(cudaSetDevice(device));
+        if (h->ahc_smem > 220 * 1024) { set_error("image too large: the plane graph does not fit shared memory"); st = HVO_ERR_ARG; break; }
+        HVO_TRY(cudaFuncSetAttribute(k_plane_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        HVO_TRY(cudaEventCreate(&h->tev[0]));
+        HVO_TRY(cudaEventCreate(&h->tev[1]));
+        const size_t B = (size_t)max_batch, px = (size_t)width * height;
+        HVO_TRY(cudaMalloc(&h->d_depth, B * px * 2));
+        HVO_TRY(cudaMalloc(&h->d_blocks, B * Nb * sizeof(BlockOut)));
+        HVO_TRY(cudaMallocHost(&h->h_blocks, (size_t)Nb * sizeof(BlockOut)));
+        HVO_TRY(cudaMalloc(&h->d_nodes, B * Nb * sizeof(NodeG)));
+        HVO_TRY(cudaMalloc(&h->d_adj, B * Nb * h->nw * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_key, B * Nb * sizeof(uint16_t)));
+        HVO_TRY(cudaMalloc(&h->d_cand, B * Nb * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_dist, B * px * sizeof(float)));
+        HVO_TRY(cudaMalloc(&h->d_queue, B * (size_t)h->qcap * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_mem, B * px * sizeof(int32_t)));
+        HVO_TRY(cudaMalloc(&h->d_planes, B * (size_t)h->max_ext * 7 * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_nplanes, B * sizeof(int32_t)));
+        HVO_TRY(cudaMalloc(&h->d_status, B * sizeof(int32_t)));
+        HVO_TRY(cudaMallocHost(&h->h_status, B * sizeof(int32_t)));
+#undef HVO_TRY
+    } while (0);
+    if (st != HVO_OK) { hvo_plane_destroy(h); return st; }
     *out = h;
     return HVO_OK;
 }
@@ -457,9 +754,11 @@ void hvo_plane_destroy(hvo_plane* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->d_depth) cudaFree(h->d_depth);
-    if (h->d_blocks) cudaFree(h->d_blocks);
+    void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_dist, h->d_queue, h->d_mem, h->d_planes,
+                    h->d_nplanes, h->d_status};
+    for (void* b : bufs) if (b) cudaFree(b);
     if (h->h_blocks) cudaFreeHost(h->h_blocks);
+    if (h->h_status) cudaFreeHost(h->h_status);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -472,7 +771,28 @@ static int plane_blocks_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     return HVO_OK;
 }
 
-/* device-only leg (bench / roofline): block statistics of nframes device-resident depth images */
+// blocks + graph stage on device-resident depth; results into d_nplanes / d_planes7 ([n][planes_stride][7]) / d_membership
+static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframes, int32_t* d_nplanes, double* d_planes7, int planes_stride,
+                               int32_t* d_membership) {
+    int st = plane_blocks_launch(h, d_depth, nframes);
+    if (st != HVO_OK) return st;
+    const int Nb = h->Nw * h->Nh;
+    HVO_CUDA(cudaMemsetAsync(h->d_adj, 0, (size_t)nframes * Nb * h->nw * sizeof(uint32_t), h->stream));
+    AhcArgs A;
+    A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand;
+    A.dist = h->d_dist; A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
+    A.status = h->d_status;
+    A.w = h->width; A.h = h->height; A.Nw = h->Nw; A.Nh = h->Nh; A.nw = h->nw; A.qcap = h->qcap; A.max_ext = h->max_ext;
+    A.planes_stride = planes_stride; A.cam = h->cam;
+    A.th_merge = std::cos(M_PI / 180.0 * 60.0);   // ParamSet::similarityTh_merge
+    A.th_refine = std::cos(M_PI / 180.0 * 30.0);  // ParamSet::similarityTh_refine
+    k_plane_ahc<<<nframes, kAhcThreads, h->ahc_smem, h->stream>>>(A);
+    HVO_CUDA(cudaGetLastError());
+    h->last_launches = 3;
+    return HVO_OK;
+}
+
+/* device-only leg: block statistics of nframes device-resident depth images (inspection / roofline of k_plane_blocks) */
 int hvo_plane_blocks_device(hvo_plane* h, const uint16_t* d_depth, int nframes) {
     HVO_CHECK_ARG(h && d_depth, "null argument");
     HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch, "nframes out of range for this handle");
@@ -504,40 +824,40 @@ int hvo_plane_get_blocks(hvo_plane* h, int frame, double* out9) {
     return HVO_OK;
 }
 
+int hvo_plane_detect_batch_device(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
+                                  int max_planes, int32_t* d_membership) {
+    HVO_CHECK_ARG(h && d_depth16 && d_n_planes && d_planes7 && d_membership, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch && max_planes >= 1, "nframes / max_planes out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    return plane_detect_launch(h, d_depth16, nframes, d_n_planes, d_planes7, max_planes, d_membership);
+}
+
 int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, int32_t* n_planes, double* planes7, int max_planes,
                            int32_t* membership) {
     HVO_CHECK_ARG(h && depth16 && n_planes && planes7 && membership, "null argument");
     HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch && max_planes >= 1, "nframes / max_planes out of range");
     HVO_CUDA(cudaSetDevice(h->device));
-    const size_t px = (size_t)h->width * h->height, nb = (size_t)h->Nw * h->Nh;
-    HVO_CUDA(cudaMemcpyAsync(h->d_depth, depth16, (size_t)nframes * px * 2, cudaMemcpyHostToDevice, h->stream));
-    int st = plane_blocks_launch(h, h->d_depth, nframes);
+    const size_t px = (size_t)h->width * h->height, n = (size_t)nframes;
+    HVO_CUDA(cudaMemcpyAsync(h->d_depth, depth16, n * px * 2, cudaMemcpyHostToDevice, h->stream));
+    int st = plane_detect_launch(h, h->d_depth, nframes, h->d_nplanes, h->d_planes, h->max_ext, h->d_mem);
     if (st != HVO_OK) return st;
-    HVO_CUDA(cudaMemcpyAsync(h->h_blocks, h->d_blocks, (size_t)nframes * nb * sizeof(BlockOut), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(n_planes, h->d_nplanes, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    const int cp = max_planes < h->max_ext ? max_planes : h->max_ext;
+    HVO_CUDA(cudaMemcpy2DAsync(planes7, (size_t)max_planes * 56, h->d_planes, (size_t)h->max_ext * 56, (size_t)cp * 56, n,
+                               cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(membership, h->d_mem, n * px * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
-    // host graph stage, one frame per worker
-    const int nt = std::min(nframes, h->host_threads);
-    auto work = [&](int t) {
-        HostAhc a;
-        a.width = h->width; a.height = h->height; a.Nw = h->Nw; a.Nh = h->Nh; a.cam = h->cam;
-        for (int f = t; f < nframes; f += nt) {
-            a.depth = depth16 + (size_t)f * px;
-            n_planes[f] = a.run(h->h_blocks + (size_t)f * nb, membership + (size_t)f * px, planes7 + (size_t)f * max_planes * 7, max_planes);
-        }
-    };
-    if (nt <= 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-        for (auto& t : th) t.join();
-    }
+    for (int f = 0; f < nframes; ++f)
+        if (h->h_status[f] != 0) { set_error("plane refinement queue overflow in frame %d", f); return HVO_ERR_OVERFLOW; }
     return HVO_OK;
 }
 
 int hvo_plane_detect(hvo_plane* h, const uint16_t* depth16, int32_t* n_planes, double* planes7, int max_planes, int32_t* membership) {
     return hvo_plane_detect_batch(h, depth16, 1, n_planes, planes7, max_planes, membership);
 }
+
+int hvo_plane_last_launches(const hvo_plane* h) { return h ? h->last_launches : 0; }
 
 int hvo_plane_sync(hvo_plane* h) {
     HVO_CHECK_ARG(h, "null handle");

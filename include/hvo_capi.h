@@ -236,7 +236,12 @@ int hvo_plane_detect(hvo_plane* h, const uint16_t* depth16, int32_t* n_planes, d
                      int32_t* membership);
 int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, int32_t* n_planes, double* planes7,
                            int max_planes, int32_t* membership);
-/* Device leg only (initial graph nodes, AHCPlaneFitter.hpp:786-826 / AHCPlaneSeg.hpp:211-284) on device-resident
+/* Same with every pointer in device memory; asynchronous on the handle's stream.  d_planes7 is [n][max_planes][7];
+ * d_membership doubles as the working membership image. */
+int hvo_plane_detect_batch_device(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
+                                  int max_planes, int32_t* d_membership);
+int hvo_plane_last_launches(const hvo_plane* h);
+/* First kernel only (initial graph nodes, AHCPlaneFitter.hpp:786-826 / AHCPlaneSeg.hpp:211-284) on device-resident
  * depth; asynchronous.  hvo_plane_get_blocks copies one frame's result: per 10x10 block 9 doubles =
  * {queued, N, center(3), normal(3), mse}. */
 int hvo_plane_blocks_device(hvo_plane* h, const uint16_t* d_depth16, int nframes);

@@ -337,3 +337,19 @@ def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoo
                                   C.c_float(max_depth_change), C.c_float(smoothing), _p(out), _p(dist))
     assert n == len(out)
     return (out, dist) if want_dist else out
+
+
+# ---- whole front-end (bench.py CPU arm) ----------------------------------------------------------------------
+def frontend_batch(gray, depth, cam, stages=15, nthreads=1, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                   nlines=200):
+    """Frame-parallel oracle run of ORB (1) | lines (2) | planes (4) | normals (8) over [n,h,w] frames.
+    cam = (depth_factor, fx, fy, cx, cy).  Returns counts [n,4] = keypoints, lines, planes, normals."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    n, h, w = gray.shape
+    counts = np.zeros((n, 4), np.int32)
+    f = C.c_float
+    lib().orc_frontend_batch(_p(gray), _p(depth), C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(nthreads), C.c_int(stages),
+                             C.c_int(nfeatures), f(scale_factor), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), C.c_int(nlines),
+                             f(cam[0]), f(cam[1]), f(cam[2]), f(cam[3]), f(cam[4]), _p(counts))
+    return counts

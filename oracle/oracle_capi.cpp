@@ -1,6 +1,9 @@
 // TEST INFRASTRUCTURE — C entry points of the CPU oracle for ctypes (tests/, bench.py cpu_baseline only).
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <numeric>
 #include <thread>
 #include <vector>
 
@@ -91,6 +94,84 @@ void orc_orb_extract_batch(int nfeatures, float scale, int nlevels, int ini_th, 
                 int m = (int)k.size() < cap ? (int)k.size() : cap;
                 if (kps && m) std::memcpy(kps + (size_t)f * cap, k.data(), (size_t)m * sizeof(orbo::KeyPoint));
                 if (desc && m) std::memcpy(desc + (size_t)f * cap * 32, d.data(), (size_t)m * 32);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+// ---- whole front-end, frame-parallel (CPU baseline of bench.py) ---------------------------------------------
+// Per frame, what Frame::Frame runs on its three threads (src/Frame.cc:205-233) as far as the oracle restates it:
+//   ORBextractor::operator()                                    (orb_oracle.cpp)
+//   LINEextractor::operator(): LSD -> KeyLines -> top-N -> LBD  (lsd_oracle.cpp, lbd_oracle.cpp)
+//   PlaneDetection::readDepthImage + runPlaneDetection          (plane_oracle.cpp)
+//   surface normals of Frame::ComputePlanes                     (normals_oracle.cpp)
+int orc_lsd_detect(const uint8_t* gray, int w, int h, float* segments4, int cap, uint8_t* scaled_out, int* sw, int* sh);
+void orc_keylines_from_segments(const float* seg4, int n, int w, int h, void* keylines_out);
+void orc_lbd_compute(const uint8_t* gray, int w, int h, const void* keylines, int n, uint8_t* desc, float* fdesc);
+int orc_plane_detect(const uint16_t* depth, int w, int h, float factor, float fx, float fy, float cx, float cy, double* planes7,
+                     int max_planes, int32_t* membership);
+int orc_surface_normals(const uint16_t* depth16, int W, int H, float depth_factor, float fx, float fy, float cx, float cy,
+                        float max_depth_change_factor, float smoothing_size, float* out8, float* dist_map_out);
+
+// LINEextractor::operator() (src/LineExtractor.cpp:329-380) on one frame; keylines: cap x 68 B, desc: cap x 32 B.
+int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keylines, uint8_t* desc, int cap) {
+    std::vector<float> seg((size_t)4 * 16384);
+    int n = orc_lsd_detect(gray, w, h, seg.data(), 16384, nullptr, nullptr, nullptr);
+    if (n > 16384) n = 16384;
+    std::vector<uint8_t> kl((size_t)n * 68);
+    orc_keylines_from_segments(seg.data(), n, w, h, kl.data());
+    std::vector<uint8_t> sel;
+    if (n > nfeat) {  // sort_lines_by_response, truncate, renumber class_id (:351-360); ties keep detection order
+        std::vector<int> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        auto resp = [&](int i) { float r; std::memcpy(&r, &kl[(size_t)i * 68 + 20], 4); return r; };
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return resp(a) > resp(b); });
+        sel.resize((size_t)nfeat * 68);
+        for (int i = 0; i < nfeat; ++i) {
+            std::memcpy(&sel[(size_t)i * 68], &kl[(size_t)idx[i] * 68], 68);
+            const int32_t cid = i;
+            std::memcpy(&sel[(size_t)i * 68 + 4], &cid, 4);
+        }
+        kl.swap(sel);
+        n = nfeat;
+    }
+    const int m = n < cap ? n : cap;
+    if (m > 0) {
+        std::vector<uint8_t> d((size_t)n * 32);
+        orc_lbd_compute(gray, w, h, kl.data(), n, d.data(), nullptr);
+        std::memcpy(keylines, kl.data(), (size_t)m * 68);
+        std::memcpy(desc, d.data(), (size_t)m * 32);
+    }
+    return n;
+}
+
+// stages: bit 0 ORB, bit 1 lines, bit 2 planes, bit 3 normals.  counts4[f] = {keypoints, lines, planes, normals}.
+void orc_frontend_batch(const uint8_t* gray, const uint16_t* depth, int nframes, int w, int h, int nthreads, int stages,
+                        int nfeatures, float scale, int nlevels, int ini_th, int min_th, int nlines, float depth_factor, float fx,
+                        float fy, float cx, float cy, int32_t* counts4) {
+    orbo::Params p;
+    p.nfeatures = nfeatures; p.scale_factor = scale; p.nlevels = nlevels; p.ini_th = ini_th; p.min_th = min_th;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() {
+            orbo::Extractor ex(p);
+            std::vector<orbo::KeyPoint> k;
+            std::vector<uint8_t> d;
+            std::vector<uint8_t> kl((size_t)nlines * 68), ld((size_t)nlines * 32);
+            std::vector<double> planes(64 * 7);
+            std::vector<int32_t> mem((size_t)w * h);
+            const int cw = (int)std::ceil(w / 3.0), ch = (int)std::ceil(h / 3.0);
+            std::vector<float> nrm((size_t)(cw / 2) * (ch / 2) * 8), dist((size_t)cw * ch);
+            for (int f = t; f < nframes; f += nthreads) {
+                const uint8_t* g = gray + (size_t)f * w * h;
+                const uint16_t* dp = depth + (size_t)f * w * h;
+                int32_t* c = counts4 + 4 * (size_t)f;
+                c[0] = c[1] = c[2] = c[3] = 0;
+                if (stages & 1) { ex.extract(g, w, h, (size_t)w, k, d); c[0] = (int32_t)k.size(); }
+                if (stages & 2) c[1] = orc_line_extract(g, w, h, nlines, kl.data(), ld.data(), nlines);
+                if (stages & 4) c[2] = orc_plane_detect(dp, w, h, depth_factor, fx, fy, cx, cy, planes.data(), 64, mem.data());
+                if (stages & 8) c[3] = orc_surface_normals(dp, w, h, depth_factor, fx, fy, cx, cy, 0.05f, 10.0f, nrm.data(), dist.data());
             }
         });
     for (auto& t : th) t.join();
