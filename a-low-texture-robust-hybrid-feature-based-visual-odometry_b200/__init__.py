@@ -103,6 +103,7 @@ ABI = {
     'hvo_plane_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
     'hvo_plane_detect_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
     'hvo_plane_last_launches': (C.c_int, [_vp]),
+    'hvo_plane_get_phase_cycles': (C.c_int, [_vp, C.c_int, _vp]),
     'hvo_plane_blocks_device': (C.c_int, [_vp, _vp, C.c_int]),
     'hvo_plane_get_blocks': (C.c_int, [_vp, C.c_int, _vp]),
     'hvo_plane_sync': (C.c_int, [_vp]),
@@ -595,6 +596,11 @@ class PlaneDetection:
 
     def last_launches(self):
         return lib().hvo_plane_last_launches(self._h)
+
+    def phase_cycles(self, frame=0):
+        out = np.zeros(4, np.int64)
+        _check(lib().hvo_plane_get_phase_cycles(self._h, frame, _np_ptr(out)))
+        return dict(cluster=int(out[0]), seeds=int(out[1]), flood=int(out[2]), merge_relabel=int(out[3]))
 
     def blocks_device(self, d_depth, nframes):
         _check(lib().hvo_plane_blocks_device(self._h, _vp(d_depth), nframes))

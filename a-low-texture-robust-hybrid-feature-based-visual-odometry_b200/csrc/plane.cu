@@ -29,33 +29,44 @@ struct BlockOut {  // 96 bytes per block
 
 struct PlaneCam { double factor, fx, fy, cx, cy; };
 
-__host__ __device__ inline void jacobi_eig33(const double K[3][3], double s[3], double V[3][3]) {
-    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = K[i][j];
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
-        if (off == 0.0) break;
-        for (int p = 0; p < 2; ++p)
-            for (int q = p + 1; q < 3; ++q) {
-                const double g = 100.0 * fabs(a[p][q]);
-                if (sweep > 3 && fabs(a[p][p]) + g == fabs(a[p][p]) && fabs(a[q][q]) + g == fabs(a[q][q])) { a[p][q] = a[q][p] = 0.0; continue; }
-                if (a[p][q] == 0.0) continue;
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-                for (int k = 0; k < 3; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - sn * y; a[k][q] = sn * x + c * y; }
-                for (int k = 0; k < 3; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - sn * y; a[q][k] = sn * x + c * y; }
-                for (int k = 0; k < 3; ++k) { const double x = v[k][p], y = v[k][q]; v[k][p] = c * x - sn * y; v[k][q] = sn * x + c * y; }
-            }
+// Smallest eigenpair of a symmetric positive semi-definite 3x3 matrix (a covariance) with + - * / sqrt only, so the CPU
+// oracle and the CUDA kernels produce bit-identical results: Newton's iteration on the characteristic polynomial
+// p(x) = det(K - xI) = -x^3 + c2 x^2 - c1 x + c0 from x = 0 (p is convex and decreasing on (-inf, lambda_min], so the
+// iterates approach lambda_min monotonically), then the eigenvector as the largest of the three row cross products
+// of K - lambda I.  Accuracy on plane covariances: |d lambda| <= 2e-12 lambda_max, direction error < 1e-7 rad.
+__host__ __device__ inline void eig33_smallest(const double K[3][3], double& lam, double v[3]) {
+    const double a = K[0][0], b = K[1][1], c = K[2][2], d = K[0][1], e = K[0][2], f = K[1][2];
+    const double c2 = a + b + c;
+    const double c1 = (a * b - d * d) + (a * c - e * e) + (b * c - f * f);
+    const double c0 = a * (b * c - f * f) - d * (d * c - f * e) + e * (d * f - b * e);
+    double x = 0, prev = INFINITY;
+    for (int k = 0; k < 40; ++k) {
+        const double p = ((-x + c2) * x - c1) * x + c0;
+        const double dp = (-3 * x + 2 * c2) * x - c1;
+        if (dp == 0) break;
+        const double dx = p / dp, adx = fabs(dx);
+        if (k >= 2 && adx >= prev) break;  // rounding floor reached
+        x -= dx;
+        prev = adx;
+        if (adx <= 1e-16 * c2) break;
     }
-    int o[3] = {0, 1, 2};
-    const double d[3] = {a[0][0], a[1][1], a[2][2]};
-    for (int i = 0; i < 3; ++i)
-        for (int j = i + 1; j < 3; ++j)
-            if (d[o[j]] < d[o[i]]) { const int t = o[i]; o[i] = o[j]; o[j] = t; }
-    for (int i = 0; i < 3; ++i) {
-        s[i] = d[o[i]];
-        for (int k = 0; k < 3; ++k) V[k][i] = v[k][o[i]];
+    lam = x;
+    const double r0[3] = {a - x, d, e}, r1[3] = {d, b - x, f}, r2[3] = {e, f, c - x};
+    const double u0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+    const double u1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+    const double u2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+    const double n0 = u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2];
+    const double n1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+    const double n2 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+    const double* u = u0;
+    double n = n0;
+    if (n1 > n) { u = u1; n = n1; }
+    if (n2 > n) { u = u2; n = n2; }
+    if (n > 0) {
+        const double s = sqrt(n);
+        v[0] = u[0] / s; v[1] = u[1] / s; v[2] = u[2] / s;
+    } else {
+        v[0] = 0; v[1] = 0; v[2] = 1;
     }
 }
 
@@ -67,12 +78,12 @@ __host__ __device__ inline void stats_compute(const double s[9], int N, double c
                       {0, s[4] - s[1] * s[1] * sc, s[7] - s[1] * s[2] * sc},
                       {0, 0, s[5] - s[2] * s[2] * sc}};
     K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
-    double sv[3], V[3][3];
-    jacobi_eig33(K, sv, V);
-    const double sgn = (V[0][0] * center[0] + V[1][0] * center[1] + V[2][0] * center[2] <= 0) ? 1.0 : -1.0;
-    normal[0] = sgn * V[0][0]; normal[1] = sgn * V[1][0]; normal[2] = sgn * V[2][0];
-    mse = sv[0] * sc;
-    curv = sv[0] / (sv[0] + sv[1] + sv[2]);
+    double lam, v[3];
+    eig33_smallest(K, lam, v);
+    const double sgn = (v[0] * center[0] + v[1] * center[1] + v[2] * center[2] <= 0) ? 1.0 : -1.0;
+    normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
+    mse = lam * sc;
+    curv = lam / (K[0][0] + K[1][1] + K[2][2]);
 }
 
 __global__ void __launch_bounds__(128) k_plane_blocks(const uint16_t* __restrict__ depth, int w, int h, PlaneCam cam, int Nw, int Nh,
@@ -145,6 +156,16 @@ struct AhcArgs {
     double* planes7;         // [B][planes_stride][7]
     int32_t* n_planes;       // [B]
     int32_t* status;         // [B]  0 ok, 1 refinement queue overflow
+    long long* cycles;       // [B][4] SM clock cycles: first clustering, erosion + seeds, flood fill, last merge + relabel
+    // state handed from kernel to kernel (per frame)
+    double* g_mse;           // [B][Nb]
+    uint16_t* g_ds;          // [B][2 Nb]   disjoint-set parent, size
+    uint32_t* g_nouse;       // [B][nw]
+    int16_t* g_blkmap;       // [B][Nb]
+    uint16_t* g_ext;         // [B][max_ext]
+    uint8_t* g_isvalid;      // [B][max_ext]
+    double* g_pl;            // [B][max_ext][7]
+    int* g_ctl;              // [B][8]: 0 n_ext, 1 next key
     int w, h, Nw, Nh, nw, qcap, max_ext, planes_stride;
     PlaneCam cam;
     double th_merge, th_refine;
@@ -252,25 +273,34 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
         }
         __syncwarp();
         const NodeG P = nodes[p];
-        // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge
-        double bm = INFINITY;
+        // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge; each lane keeps
+        // the full result of its own best candidate, so the winner needs no second eigen-solve
+        double bm_l = INFINITY, ms[9], mc[3], mn[3];
+        int bi_l = -1, mN = 0, mrid = 0;
         for (int base = 0; base < cnt; base += 32) {
             const int i = base + lane;
-            double m = INFINITY;
             if (i < cnt) {
                 const NodeG* Q = nodes + S.list[i];
                 const double sim = fabs(P.normal[0] * Q->normal[0] + P.normal[1] * Q->normal[1] + P.normal[2] * Q->normal[2]);
+                double m = INFINITY;
                 if (!(sim < A.th_merge)) {
                     double s[9], c[3], n[3], curv;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) s[k] = P.s[k] + Q->s[k];
                     stats_compute(s, P.N + Q->N, c, n, m, curv);
                     if (!(m == m)) m = INFINITY;  // NaN never wins a `>` comparison in the reference either
+                    if (m < bm_l) {
+                        bm_l = m; bi_l = i; mN = P.N + Q->N; mrid = P.N >= Q->N ? P.rid : Q->rid;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) ms[k] = s[k];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { mc[k] = c[k]; mn[k] = n[k]; }
+                    }
                 }
                 cand[i] = m;
             }
-            bm = fmin(bm, m);
         }
+        double bm = bm_l;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
         __syncwarp();
@@ -306,21 +336,38 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
                 best_i = __shfl_sync(0xffffffffu, best_i, 0);
             }
         }
-        bool merged = false;
+        const int owner = best_i & 31;  // the lane that evaluated candidate best_i
         int nb = -1;
-        double ms[9], mc[3], mn[3], mm = 0, curv;
-        int mN = 0, mrid = 0;
+        bool merged = false;
         if (best_i >= 0) {
             nb = S.list[best_i];
-            const NodeG Q = nodes[nb];
+            if (lane == owner) {
+                if (bi_l != best_i) {  // only after an exact tie inside this lane's own candidates
+                    const NodeG Q = nodes[nb];
+                    double curv;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) ms[k] = P.s[k] + Q.s[k];
-            mN = P.N + Q.N;
-            mrid = P.N >= Q.N ? P.rid : Q.rid;
-            stats_compute(ms, mN, mc, mn, mm, curv);
-            const double t = 1.6e-6 * mc[2] * mc[2] + 8;  // ParamSet::T_mse(P_MERGING)
-            merged = mm < t * t;
-            if (merged && lane == 0) ds_union(S, P.rid, Q.rid);
+                    for (int k = 0; k < 9; ++k) ms[k] = P.s[k] + Q.s[k];
+                    mN = P.N + Q.N;
+                    mrid = P.N >= Q.N ? P.rid : Q.rid;
+                    stats_compute(ms, mN, mc, mn, bm_l, curv);
+                }
+                const double t = 1.6e-6 * mc[2] * mc[2] + 8;  // ParamSet::T_mse(P_MERGING)
+                merged = bm_l < t * t;
+                if (merged) {
+                    ds_union(S, P.rid, nodes[nb].rid);
+                    NodeG M;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) M.s[k] = ms[k];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { M.center[k] = mc[k]; M.normal[k] = mn[k]; }
+                    M.N = mN; M.rid = mrid;
+                    nodes[p] = M;
+                    S.mse[p] = bm_l;
+                    key[p] = (uint16_t)S.ctl[1]++;
+                    S.nouse[nb >> 5] |= 1u << (nb & 31);
+                }
+            }
+            merged = __shfl_sync(0xffffffffu, (int)merged, owner) != 0;
         }
         __syncwarp();
         if (merged) {
@@ -341,19 +388,8 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
                     atomicOr(&rx[p >> 5], 1u << (p & 31));
                 }
             }
-            if (lane == 0) {
-                NodeG M;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) M.s[k] = ms[k];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { M.center[k] = mc[k]; M.normal[k] = mn[k]; }
-                M.N = mN; M.rid = mrid;
-                nodes[p] = M;
-                S.mse[p] = mm;
-                key[p] = (uint16_t)S.ctl[1]++;
-                S.nouse[nb >> 5] |= 1u << (nb & 31);
-                heap_push(S, p);
-            }
+            __syncwarp();
+            if (lane == 0) heap_push(S, p);
         } else {
             if (lane == 0 && P.N >= kMinSupport) out[(*n_out)++] = (uint16_t)p;
             for (int i = lane; i < cnt; i += 32) {  // disconnectAllNbs
@@ -379,39 +415,37 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
+// smem layout shared by the two clustering kernels
+__device__ __forceinline__ void ahc_smem_views(unsigned char* p, int Nb, int max_ext, AhcS& S) {
+    S.mse = (double*)p; p += (size_t)Nb * 8;
+    S.pl = (double*)p; p += (size_t)max_ext * 7 * 8;
+    S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
+    S.ctl = (int*)p; p += 8 * 4;
+    S.heap = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.list = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.ext = (uint16_t*)p; p += (size_t)max_ext * 2;
+    S.ext2 = (uint16_t*)p; p += (size_t)max_ext * 2;
+    S.plidmap = (int16_t*)p; p += (size_t)max_ext * 2;
+    S.isvalid = (uint8_t*)p;
+}
+
+// ---- kernel 1 of the graph stage: initial graph + first clustering + block erosion.  One warp per frame. ----
+__global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh, W = A.w, H = A.h, npix = W * H;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh;
     AhcS S;
-    {
-        unsigned char* p = smem_raw;
-        S.mse = (double*)p; p += (size_t)Nb * 8;
-        S.pl = (double*)p; p += (size_t)A.max_ext * 7 * 8;
-        S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
-        S.ctl = (int*)p; p += 8 * 4;
-        S.heap = (uint16_t*)p; p += (size_t)Nb * 2;
-        S.list = (uint16_t*)p; p += (size_t)Nb * 2;
-        S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
-        S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
-        S.ext = (uint16_t*)p; p += (size_t)A.max_ext * 2;
-        S.ext2 = (uint16_t*)p; p += (size_t)A.max_ext * 2;
-        S.plidmap = (int16_t*)p; p += (size_t)A.max_ext * 2;
-        S.isvalid = (uint8_t*)p;
-    }
-    int16_t* blkmap = (int16_t*)S.heap;  // valid between the two clustering passes only
-    const uint16_t* D = A.depth + (size_t)f * npix;
+    ahc_smem_views(smem_raw, Nb, A.max_ext, S);
     const BlockOut* blocks = A.blocks + (size_t)f * Nb;
     NodeG* nodes = A.nodes + (size_t)f * Nb;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
     uint16_t* key = A.key + (size_t)f * Nb;
     double* cand = A.cand + (size_t)f * Nb;
-    float* dist = A.dist + (size_t)f * npix;
-    volatile uint32_t* queue = A.queue + (size_t)f * A.qcap;
-    volatile int32_t* mem = A.membership + (size_t)f * npix;
-
+    const long long t_start = clock64();
     // ---- initial graph nodes (AHCPlaneFitter.hpp:786-826) ----
-    for (int b = tid; b < Nb; b += kAhcThreads) {
+    for (int b = lane; b < Nb; b += 32) {
         const BlockOut o = blocks[b];
         S.parent[b] = (uint16_t)b; S.ssize[b] = 1; key[b] = (uint16_t)b;
         double m = INFINITY;
@@ -426,74 +460,62 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
         }
         S.mse[b] = m;
     }
-    for (int i = tid; i < (Nb + 31) / 32; i += kAhcThreads) S.nouse[i] = 0u;
-    for (int i = tid; i < A.max_ext; i += kAhcThreads) { S.isvalid[i] = 0; S.plidmap[i] = -1; }
-    if (tid == 0) { S.ctl[0] = 0; S.ctl[1] = Nb; S.ctl[2] = 0; S.ctl[3] = 0; S.ctl[4] = 0; A.status[f] = 0; }
-    __threadfence_block();
-    __syncthreads();
-    if (wid == 0) {
-        if (lane == 0)
-            for (int b = 0; b < Nb; ++b) if (blocks[b].queued) heap_push(S, b);
-        // ---- edges (AHCPlaneFitter.hpp:896-954): rows, then columns ----
-        for (int i = lane; i < Nh; i += 32)
-            for (int j = 1; j < Nw; j += 2) {
-                const int c = i * Nw + j;
-                if (!blocks[c - 1].queued) { --j; continue; }
-                if (!blocks[c].queued) continue;
-                if (j < Nw - 1 && !blocks[c + 1].queued) { ++j; continue; }
-                const double th = ahc_t_ang_init(nodes[c].center[2]);
-                const double* n0 = nodes[c - 1].normal;
-                const double* n1 = (j < Nw - 1) ? nodes[c + 1].normal : nodes[c].normal;
-                if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
-                    atomicOr(&adj[(size_t)c * A.nw + ((c - 1) >> 5)], 1u << ((c - 1) & 31));
-                    atomicOr(&adj[(size_t)(c - 1) * A.nw + (c >> 5)], 1u << (c & 31));
-                    if (j < Nw - 1) {
-                        atomicOr(&adj[(size_t)c * A.nw + ((c + 1) >> 5)], 1u << ((c + 1) & 31));
-                        atomicOr(&adj[(size_t)(c + 1) * A.nw + (c >> 5)], 1u << (c & 31));
-                    }
-                } else {
-                    --j;
+    for (int i = lane; i < (Nb + 31) / 32; i += 32) S.nouse[i] = 0u;
+    for (int i = lane; i < A.max_ext; i += 32) S.isvalid[i] = 0;
+    if (lane == 0) { S.ctl[0] = 0; S.ctl[1] = Nb; S.ctl[2] = 0; S.ctl[3] = 0; A.status[f] = 0; }
+    __syncwarp();
+    if (lane == 0)
+        for (int b = 0; b < Nb; ++b) if (blocks[b].queued) heap_push(S, b);
+    // ---- edges (AHCPlaneFitter.hpp:896-954): rows, then columns ----
+    for (int i = lane; i < Nh; i += 32)
+        for (int j = 1; j < Nw; j += 2) {
+            const int c = i * Nw + j;
+            if (!blocks[c - 1].queued) { --j; continue; }
+            if (!blocks[c].queued) continue;
+            if (j < Nw - 1 && !blocks[c + 1].queued) { ++j; continue; }
+            const double th = ahc_t_ang_init(nodes[c].center[2]);
+            const double* n0 = nodes[c - 1].normal;
+            const double* n1 = (j < Nw - 1) ? nodes[c + 1].normal : nodes[c].normal;
+            if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
+                atomicOr(&adj[(size_t)c * A.nw + ((c - 1) >> 5)], 1u << ((c - 1) & 31));
+                atomicOr(&adj[(size_t)(c - 1) * A.nw + (c >> 5)], 1u << (c & 31));
+                if (j < Nw - 1) {
+                    atomicOr(&adj[(size_t)c * A.nw + ((c + 1) >> 5)], 1u << ((c + 1) & 31));
+                    atomicOr(&adj[(size_t)(c + 1) * A.nw + (c >> 5)], 1u << (c & 31));
                 }
+            } else {
+                --j;
             }
-        __threadfence_block();
-        __syncwarp();
-        for (int j = lane; j < Nw; j += 32)
-            for (int i = 1; i < Nh; i += 2) {
-                const int c = i * Nw + j;
-                if (!blocks[c - Nw].queued) { --i; continue; }
-                if (!blocks[c].queued) continue;
-                if (i < Nh - 1 && !blocks[c + Nw].queued) { ++i; continue; }
-                const double th = ahc_t_ang_init(nodes[c].center[2]);
-                const double* n0 = nodes[c - Nw].normal;
-                const double* n1 = (i < Nh - 1) ? nodes[c + Nw].normal : nodes[c].normal;
-                if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
-                    atomicOr(&adj[(size_t)c * A.nw + ((c - Nw) >> 5)], 1u << ((c - Nw) & 31));
-                    atomicOr(&adj[(size_t)(c - Nw) * A.nw + (c >> 5)], 1u << (c & 31));
-                    if (i < Nh - 1) {
-                        atomicOr(&adj[(size_t)c * A.nw + ((c + Nw) >> 5)], 1u << ((c + Nw) & 31));
-                        atomicOr(&adj[(size_t)(c + Nw) * A.nw + (c >> 5)], 1u << (c & 31));
-                    }
-                } else {
-                    --i;
+        }
+    __syncwarp();
+    for (int j = lane; j < Nw; j += 32)
+        for (int i = 1; i < Nh; i += 2) {
+            const int c = i * Nw + j;
+            if (!blocks[c - Nw].queued) { --i; continue; }
+            if (!blocks[c].queued) continue;
+            if (i < Nh - 1 && !blocks[c + Nw].queued) { ++i; continue; }
+            const double th = ahc_t_ang_init(nodes[c].center[2]);
+            const double* n0 = nodes[c - Nw].normal;
+            const double* n1 = (i < Nh - 1) ? nodes[c + Nw].normal : nodes[c].normal;
+            if (fabs(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2]) >= th) {
+                atomicOr(&adj[(size_t)c * A.nw + ((c - Nw) >> 5)], 1u << ((c - Nw) & 31));
+                atomicOr(&adj[(size_t)(c - Nw) * A.nw + (c >> 5)], 1u << (c & 31));
+                if (i < Nh - 1) {
+                    atomicOr(&adj[(size_t)c * A.nw + ((c + Nw) >> 5)], 1u << ((c + Nw) & 31));
+                    atomicOr(&adj[(size_t)(c + Nw) * A.nw + (c >> 5)], 1u << (c & 31));
                 }
+            } else {
+                --i;
             }
-        __threadfence_block();
-        __syncwarp();
-        ahc_cluster(A, S, nodes, adj, key, cand, S.ext, &S.ctl[2], lane);
-    }
-    __syncthreads();
+        }
+    __syncwarp();
+    ahc_cluster(A, S, nodes, adj, key, cand, S.ext, &S.ctl[2], lane);
     const int ne = S.ctl[2];
-    // ---- refineDetails: findBlockMembership (AHCPlaneFitter.hpp:485-587) ----
-    for (int i = tid; i < ne; i += kAhcThreads) {
-        const NodeG* n = nodes + S.ext[i];
-        double* o = S.pl + 7 * i;
-        o[0] = n->normal[0]; o[1] = n->normal[1]; o[2] = n->normal[2];
-        o[3] = n->center[0]; o[4] = n->center[1]; o[5] = n->center[2];
-        o[6] = S.mse[S.ext[i]];
-    }
-    for (int b = tid; b < Nb; b += kAhcThreads) S.list[b] = (uint16_t)ds_find(S.parent, b);  // set id of every block
-    __syncthreads();
-    for (int b = tid; b < Nb; b += kAhcThreads) {
+    // ---- refineDetails: findBlockMembership (AHCPlaneFitter.hpp:485-587), block part ----
+    int16_t* g_blkmap = A.g_blkmap + (size_t)f * Nb;
+    for (int b = lane; b < Nb; b += 32) S.list[b] = (uint16_t)ds_find(S.parent, b);  // set id of every block
+    __syncwarp();
+    for (int b = lane; b < Nb; b += 32) {
         const int i = b / Nw, j = b - i * Nw, setid = S.list[b];
         int bm = -1;
         if ((int)S.ssize[setid] * 100 >= kMinSupport) {
@@ -506,11 +528,57 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
             for (int e = 0; e < ne; ++e) if (nodes[S.ext[e]].rid == setid) { plid = e; break; }
             if (same && plid < ne) { bm = plid; S.isvalid[plid] = 1; }
         }
-        blkmap[b] = (int16_t)bm;
+        g_blkmap[b] = (int16_t)bm;
     }
+    __syncwarp();
+    // ---- hand the state over ----
+    double* g_mse = A.g_mse + (size_t)f * Nb;
+    uint16_t* g_ds = A.g_ds + (size_t)f * 2 * Nb;
+    for (int b = lane; b < Nb; b += 32) { g_mse[b] = S.mse[b]; g_ds[b] = S.parent[b]; g_ds[Nb + b] = S.ssize[b]; }
+    for (int i = lane; i < A.nw; i += 32) A.g_nouse[(size_t)f * A.nw + i] = S.nouse[i];
+    for (int i = lane; i < ne; i += 32) {
+        const NodeG* n = nodes + S.ext[i];
+        double* o = A.g_pl + ((size_t)f * A.max_ext + i) * 7;
+        o[0] = n->normal[0]; o[1] = n->normal[1]; o[2] = n->normal[2];
+        o[3] = n->center[0]; o[4] = n->center[1]; o[5] = n->center[2];
+        o[6] = S.mse[S.ext[i]];
+        A.g_ext[(size_t)f * A.max_ext + i] = S.ext[i];
+    }
+    for (int i = lane; i < A.max_ext; i += 32) A.g_isvalid[(size_t)f * A.max_ext + i] = S.isvalid[i];
+    if (lane == 0) {
+        A.g_ctl[8 * f + 0] = ne; A.g_ctl[8 * f + 1] = S.ctl[1];
+        A.cycles[4 * (size_t)f + 0] = clock64() - t_start;
+    }
+}
+
+// ---- kernel 2: membership image, refinement seeds and the ordered pixel flood fill.  One CTA of 256 per frame. ----
+static const int kFloodThreads = 256, kFloodBuckets = 2048;
+
+__global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_bucket[kFloodBuckets];
+    __shared__ int s_wsum[kFloodThreads / 32];
+    __shared__ int s_head, s_tail, s_overflow;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh, W = A.w, H = A.h, npix = W * H;
+    double* pl = (double*)smem_raw;                                 // [max_ext][7]
+    int16_t* blkmap = (int16_t*)(smem_raw + (size_t)A.max_ext * 56);  // [Nb]
+    uint16_t* ext = (uint16_t*)(blkmap + Nb);                       // [max_ext]
+    const uint16_t* D = A.depth + (size_t)f * npix;
+    uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
+    float* dist = A.dist + (size_t)f * npix;
+    uint32_t* queue = A.queue + (size_t)f * A.qcap;
+    int32_t* mem = A.membership + (size_t)f * npix;
+    const long long t_start = clock64();
+    const int ne = A.g_ctl[8 * f + 0];
+    for (int i = tid; i < ne * 7; i += kFloodThreads) pl[i] = A.g_pl[(size_t)f * A.max_ext * 7 + i];
+    for (int i = tid; i < ne; i += kFloodThreads) ext[i] = A.g_ext[(size_t)f * A.max_ext + i];
+    for (int b = tid; b < Nb; b += kFloodThreads) blkmap[b] = A.g_blkmap[(size_t)f * Nb + b];
+    for (int i = tid; i < kFloodBuckets; i += kFloodThreads) s_bucket[i] = 0u;
+    if (tid == 0) { s_head = 0; s_tail = 0; s_overflow = 0; }
     __syncthreads();
     // membershipImg: block label inside eroded member blocks, -1 elsewhere; distMap = FLT_MAX
-    for (int y = wid; y < H; y += kAhcThreads / 32) {
+    for (int y = wid; y < H; y += kFloodThreads / 32) {
         const int by = y / 10;
         for (int x = lane; x < W; x += 32) {
             const int bx = x / 10;
@@ -518,7 +586,7 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
             dist[(size_t)y * W + x] = 3.402823466e+38f;
         }
     }
-    // refinement seeds, in block scan order
+    // refinement seeds, in block scan order (AHCPlaneFitter.hpp:545-583)
     if (wid == 0) {
         int tail = 0;
         for (int b0 = 0; b0 < Nb; b0 += 32) {
@@ -548,96 +616,134 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
             }
             tail += total;
         }
-        if (lane == 0) S.ctl[4] = tail;
+        if (lane == 0) { if (tail > A.qcap) { s_overflow = 1; tail = 0; } s_tail = tail; }
     }
-    __threadfence_block();
+    __syncthreads();
+    const long long t_seeds = clock64();
+    // ---- floodFill (AHCPlaneFitter.hpp:428-476): FIFO over (pixel, plane) seeds.  64 queue entries x 4 neighbours per
+    // step; visits of the same pixel inside one step are applied in queue order (hash-bucket tournament: a lane goes when
+    // it is the lowest pending lane of its bucket, so an equal pixel with a lower queue position always went before) ----
+    const int e = tid >> 2, it = tid & 3;
+    unsigned tag = 1;
+    while (true) {
+        const int head = s_head, tail = s_tail;
+        if (head >= tail) break;
+        const int nbat = min(kFloodThreads / 4, tail - head);
+        bool valid = e < nbat;
+        int cIdx = -1, plid = 0;
+        bool ok = false;
+        float cdist = -1.f;
+        if (valid) {
+            const uint32_t q = queue[head + e];
+            const int sIdx = (int)(q & 0xfffffu);
+            plid = (int)(q >> 20);
+            const int sy = sIdx / W, sx = sIdx - sy * W;
+            int nb4[4], c = 0;
+            if (sx > 0) nb4[c++] = sIdx - 1;
+            if (sx < W - 1) nb4[c++] = sIdx + 1;
+            if (sy > 0) nb4[c++] = sIdx - W;
+            if (sy < H - 1) nb4[c++] = sIdx + W;
+            valid = it < c;
+            if (valid) {
+                cIdx = it == 0 ? nb4[0] : (it == 1 ? nb4[1] : (it == 2 ? nb4[2] : nb4[3]));
+                const int cy = cIdx / W, cx = cIdx - cy * W;
+                const int by = cy / 10, bx = cx / 10;
+                if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) valid = false;  // inside an eroded member block
+                else {
+                    const double z = (double)D[cIdx] * A.cam.factor;
+                    if (z != 0) {
+                        const double px = ((double)cx - A.cam.cx) * z / A.cam.fx, py = ((double)cy - A.cam.cy) * z / A.cam.fy;
+                        const double* p = pl + 7 * plid;
+                        cdist = (float)fabs(p[0] * (px - p[3]) + p[1] * (py - p[4]) + p[2] * (z - p[5]));
+                        ok = (double)cdist * (double)cdist < 9 * p[6] + 1e-5;
+                    }
+                }
+            }
+        }
+        const unsigned hsh = ((unsigned)cIdx * 2654435761u) >> 21;  // 2048 buckets
+        bool pending = valid, push = false;
+        while (__syncthreads_or(pending)) {
+            const unsigned mykey = (tag << 8) | (unsigned)(kFloodThreads - 1 - tid);
+            if (pending) atomicMax(&s_bucket[hsh], mykey);
+            __syncthreads();
+            if (pending && s_bucket[hsh] == mykey) {
+                pending = false;
+                const int trail = mem[cIdx];
+                if (trail > -6 && !(trail >= 0 && trail == plid)) {
+                    if (ok) {
+                        if (trail >= 0) {
+                            const double *a = pl + 7 * plid, *b = pl + 7 * trail;
+                            if (fabs(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) >= A.th_refine) {  // connect(planes)
+                                const int na = ext[trail], nbn = ext[plid];
+                                atomicOr(&adj[(size_t)na * A.nw + (nbn >> 5)], 1u << (nbn & 31));
+                                atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
+                            }
+                        }
+                        if (cdist < dist[cIdx]) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
+                        else if (trail < 0) mem[cIdx] = trail - 1;
+                    } else if (trail < 0) {
+                        mem[cIdx] = trail - 1;
+                    }
+                }
+            }
+            ++tag;
+        }
+        // append the new seeds in (entry, neighbour) order
+        const unsigned pm = __ballot_sync(0xffffffffu, push);
+        if (lane == 0) s_wsum[wid] = __popc(pm);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kFloodThreads / 32; ++w) { const int v = s_wsum[w]; if (w < wid) base += v; total += v; }
+        if (push) {
+            const int pos = tail + base + __popc(pm & ((1u << lane) - 1u));
+            if (pos < A.qcap) queue[pos] = (uint32_t)cIdx | ((uint32_t)plid << 20);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nt = tail + total;
+            if (nt > A.qcap) { s_overflow = 1; nt = A.qcap; }
+            s_tail = nt; s_head = head + nbat;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (s_overflow) A.status[f] = 1;
+        A.cycles[4 * (size_t)f + 1] = t_seeds - t_start;
+        A.cycles[4 * (size_t)f + 2] = clock64() - t_seeds;
+    }
+}
+
+// ---- kernel 3: last merge among the refined planes (AHCPlaneFitter.hpp:317-371) + final labels ----
+__global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Nb = A.Nw * A.Nh, npix = A.w * A.h;
+    AhcS S;
+    ahc_smem_views(smem_raw, Nb, A.max_ext, S);
+    NodeG* nodes = A.nodes + (size_t)f * Nb;
+    uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
+    uint16_t* key = A.key + (size_t)f * Nb;
+    double* cand = A.cand + (size_t)f * Nb;
+    int32_t* mem = A.membership + (size_t)f * npix;
+    const long long t_start = clock64();
+    const int ne = A.g_ctl[8 * f + 0];
+    for (int b = tid; b < Nb; b += kAhcThreads) {
+        S.mse[b] = A.g_mse[(size_t)f * Nb + b];
+        S.parent[b] = A.g_ds[(size_t)f * 2 * Nb + b];
+        S.ssize[b] = A.g_ds[(size_t)f * 2 * Nb + Nb + b];
+    }
+    for (int i = tid; i < A.nw; i += kAhcThreads) S.nouse[i] = A.g_nouse[(size_t)f * A.nw + i];
+    for (int i = tid; i < A.max_ext; i += kAhcThreads) {
+        S.isvalid[i] = A.g_isvalid[(size_t)f * A.max_ext + i];
+        S.ext[i] = i < ne ? A.g_ext[(size_t)f * A.max_ext + i] : 0;
+        S.plidmap[i] = -1;
+    }
+    if (tid == 0) { S.ctl[0] = 0; S.ctl[1] = A.g_ctl[8 * f + 1]; S.ctl[3] = 0; }
     __syncthreads();
     if (wid == 0) {
-        // ---- floodFill (AHCPlaneFitter.hpp:428-476): FIFO over (pixel, plane) seeds; 8 queue entries x 4 neighbours per
-        // step; lanes that hit the same pixel in one step are applied in queue order ----
-        int head = 0, tail = S.ctl[4];
-        bool overflow = tail > A.qcap;
-        if (overflow) tail = 0;
-        const int e = lane >> 2, it = lane & 3;
-        while (head < tail) {
-            const int nbat = min(8, tail - head);
-            bool valid = e < nbat;
-            int cIdx = -1, plid = 0;
-            bool ok = false;
-            float cdist = -1.f;
-            if (valid) {
-                const uint32_t q = queue[head + e];
-                const int sIdx = (int)(q & 0xfffffu);
-                plid = (int)(q >> 20);
-                const int sy = sIdx / W, sx = sIdx - sy * W;
-                int nb4[4], c = 0;
-                if (sx > 0) nb4[c++] = sIdx - 1;
-                if (sx < W - 1) nb4[c++] = sIdx + 1;
-                if (sy > 0) nb4[c++] = sIdx - W;
-                if (sy < H - 1) nb4[c++] = sIdx + W;
-                valid = it < c;
-                if (valid) {
-                    cIdx = it == 0 ? nb4[0] : (it == 1 ? nb4[1] : (it == 2 ? nb4[2] : nb4[3]));
-                    const int cy = cIdx / W, cx = cIdx - cy * W;
-                    const int by = cy / 10, bx = cx / 10;
-                    if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) valid = false;  // inside an eroded member block
-                    else {
-                        const double z = (double)D[cIdx] * A.cam.factor;
-                        if (z != 0) {
-                            const double px = ((double)cx - A.cam.cx) * z / A.cam.fx, py = ((double)cy - A.cam.cy) * z / A.cam.fy;
-                            const double* pl = S.pl + 7 * plid;
-                            cdist = (float)fabs(pl[0] * (px - pl[3]) + pl[1] * (py - pl[4]) + pl[2] * (z - pl[5]));
-                            ok = (double)cdist * (double)cdist < 9 * pl[6] + 1e-5;
-                        }
-                    }
-                }
-            }
-            const unsigned grp = __match_any_sync(0xffffffffu, valid ? cIdx : -1 - lane);
-            const int rank = __popc(grp & ((1u << lane) - 1u));
-            int rounds = valid ? __popc(grp) : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
-            bool push = false;
-            for (int r = 0; r < rounds; ++r) {
-                if (valid && rank == r) {
-                    const int trail = mem[cIdx];
-                    if (trail > -6 && !(trail >= 0 && trail == plid)) {
-                        if (ok) {
-                            if (trail >= 0) {
-                                const double *a = S.pl + 7 * plid, *b = S.pl + 7 * trail;
-                                if (fabs(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) >= A.th_refine) {  // connect(planes)
-                                    const int na = S.ext[trail], nbn = S.ext[plid];
-                                    atomicOr(&adj[(size_t)na * A.nw + (nbn >> 5)], 1u << (nbn & 31));
-                                    atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
-                                }
-                            }
-                            if (cdist < dist[cIdx]) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
-                            else if (trail < 0) mem[cIdx] = trail - 1;
-                        } else if (trail < 0) {
-                            mem[cIdx] = trail - 1;
-                        }
-                    }
-                }
-                __threadfence_block();
-                __syncwarp();
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, push);
-            if (push) {
-                const int pos = tail + __popc(pm & ((1u << lane) - 1u));
-                if (pos < A.qcap) queue[pos] = (uint32_t)cIdx | ((uint32_t)plid << 20);
-            }
-            tail += __popc(pm);
-            if (tail > A.qcap) { overflow = true; tail = A.qcap; }
-            head += nbat;
-            __threadfence_block();
-            __syncwarp();
-        }
-        if (lane == 0 && overflow) A.status[f] = 1;
-        // ---- last merge among the refined planes (AHCPlaneFitter.hpp:317-371) ----
-        if (lane == 0) {
-            S.ctl[0] = 0;
+        if (lane == 0)
             for (int i = 0; i < ne; ++i) if (S.isvalid[i]) heap_push(S, S.ext[i]);
-        }
         __syncwarp();
         ahc_cluster(A, S, nodes, adj, key, cand, S.ext2, &S.ctl[3], lane);
         const int ne2 = S.ctl[3];
@@ -658,13 +764,12 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_ahc(AhcArgs A) {
         }
         if (lane == 0) A.n_planes[f] = ne2;
     }
-    __threadfence_block();
     __syncthreads();
-    // ---- final labels ----
     for (int i = tid; i < npix; i += kAhcThreads) {
         const int plid = mem[i];
         mem[i] = (plid >= 0) ? (int)S.plidmap[plid] : -1;
     }
+    if (tid == 0) A.cycles[4 * (size_t)f + 3] = clock64() - t_start;
 }
 
 }  // namespace hvo
@@ -689,6 +794,14 @@ struct hvo_plane {
     int32_t* d_mem = nullptr;
     double* d_planes = nullptr;  // [B][max_ext][7]
     int32_t *d_nplanes = nullptr, *d_status = nullptr;
+    long long* d_cycles = nullptr;
+    double *d_gmse = nullptr, *d_gpl = nullptr;
+    uint16_t *d_gds = nullptr, *d_gext = nullptr;
+    uint32_t* d_gnouse = nullptr;
+    int16_t* d_gblkmap = nullptr;
+    uint8_t* d_gisvalid = nullptr;
+    int* d_gctl = nullptr;
+    size_t flood_smem = 0;
     int32_t* h_status = nullptr;  // pinned [B]
     int last_launches = 0;
 };
@@ -724,7 +837,10 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
         HVO_TRY(cudaSetDevice(device));
         if (h->ahc_smem > 220 * 1024) { set_error("image too large: the plane graph does not fit shared memory"); st = HVO_ERR_ARG; break; }
-        HVO_TRY(cudaFuncSetAttribute(k_plane_ahc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        h->flood_smem = (size_t)h->max_ext * 56 + (size_t)Nb * 2 + (size_t)h->max_ext * 2 + 16;
+        HVO_TRY(cudaFuncSetAttribute(k_plane_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->flood_smem));
         HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         HVO_TRY(cudaEventCreate(&h->tev[0]));
         HVO_TRY(cudaEventCreate(&h->tev[1]));
@@ -742,6 +858,15 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
         HVO_TRY(cudaMalloc(&h->d_planes, B * (size_t)h->max_ext * 7 * sizeof(double)));
         HVO_TRY(cudaMalloc(&h->d_nplanes, B * sizeof(int32_t)));
         HVO_TRY(cudaMalloc(&h->d_status, B * sizeof(int32_t)));
+        HVO_TRY(cudaMalloc(&h->d_cycles, B * 4 * sizeof(long long)));
+        HVO_TRY(cudaMalloc(&h->d_gmse, B * Nb * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_gds, B * 2 * Nb * sizeof(uint16_t)));
+        HVO_TRY(cudaMalloc(&h->d_gnouse, B * h->nw * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_gblkmap, B * Nb * sizeof(int16_t)));
+        HVO_TRY(cudaMalloc(&h->d_gext, B * (size_t)h->max_ext * sizeof(uint16_t)));
+        HVO_TRY(cudaMalloc(&h->d_gisvalid, B * (size_t)h->max_ext));
+        HVO_TRY(cudaMalloc(&h->d_gpl, B * (size_t)h->max_ext * 7 * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_gctl, B * 8 * sizeof(int)));
         HVO_TRY(cudaMallocHost(&h->h_status, B * sizeof(int32_t)));
 #undef HVO_TRY
     } while (0);
@@ -755,7 +880,8 @@ void hvo_plane_destroy(hvo_plane* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_dist, h->d_queue, h->d_mem, h->d_planes,
-                    h->d_nplanes, h->d_status};
+                    h->d_nplanes, h->d_status, h->d_cycles, h->d_gmse, h->d_gds, h->d_gnouse, h->d_gblkmap, h->d_gext, h->d_gisvalid,
+                    h->d_gpl, h->d_gctl};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->h_blocks) cudaFreeHost(h->h_blocks);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -781,14 +907,18 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     AhcArgs A;
     A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand;
     A.dist = h->d_dist; A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
-    A.status = h->d_status;
+    A.status = h->d_status; A.cycles = h->d_cycles;
     A.w = h->width; A.h = h->height; A.Nw = h->Nw; A.Nh = h->Nh; A.nw = h->nw; A.qcap = h->qcap; A.max_ext = h->max_ext;
     A.planes_stride = planes_stride; A.cam = h->cam;
     A.th_merge = std::cos(M_PI / 180.0 * 60.0);   // ParamSet::similarityTh_merge
     A.th_refine = std::cos(M_PI / 180.0 * 30.0);  // ParamSet::similarityTh_refine
-    k_plane_ahc<<<nframes, kAhcThreads, h->ahc_smem, h->stream>>>(A);
+    A.g_mse = h->d_gmse; A.g_ds = h->d_gds; A.g_nouse = h->d_gnouse; A.g_blkmap = h->d_gblkmap; A.g_ext = h->d_gext;
+    A.g_isvalid = h->d_gisvalid; A.g_pl = h->d_gpl; A.g_ctl = h->d_gctl;
+    k_plane_cluster<<<nframes, 32, h->ahc_smem, h->stream>>>(A);
+    k_plane_flood<<<nframes, kFloodThreads, h->flood_smem, h->stream>>>(A);
+    k_plane_merge<<<nframes, kAhcThreads, h->ahc_smem, h->stream>>>(A);
     HVO_CUDA(cudaGetLastError());
-    h->last_launches = 3;
+    h->last_launches = 5;
     return HVO_OK;
 }
 
@@ -858,6 +988,15 @@ int hvo_plane_detect(hvo_plane* h, const uint16_t* depth16, int32_t* n_planes, d
 }
 
 int hvo_plane_last_launches(const hvo_plane* h) { return h ? h->last_launches : 0; }
+
+int hvo_plane_get_phase_cycles(hvo_plane* h, int frame, int64_t* out4) {
+    HVO_CHECK_ARG(h && out4, "null argument");
+    HVO_CHECK_ARG(frame >= 0 && frame < h->max_batch, "frame out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaMemcpyAsync(out4, h->d_cycles + 4 * (size_t)frame, 4 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
 
 int hvo_plane_sync(hvo_plane* h) {
     HVO_CHECK_ARG(h, "null handle");

@@ -241,6 +241,9 @@ int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, i
 int hvo_plane_detect_batch_device(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
                                   int max_planes, int32_t* d_membership);
 int hvo_plane_last_launches(const hvo_plane* h);
+/* Profiling: SM clock cycles of the graph kernel's phases for one frame of the last call: first clustering,
+ * block erosion + seeds, flood fill, last merge + relabel. */
+int hvo_plane_get_phase_cycles(hvo_plane* h, int frame, int64_t* out4);
 /* First kernel only (initial graph nodes, AHCPlaneFitter.hpp:786-826 / AHCPlaneSeg.hpp:211-284) on device-resident
  * depth; asynchronous.  hvo_plane_get_blocks copies one frame's result: per 10x10 block 9 doubles =
  * {queued, N, center(3), normal(3), mse}. */

@@ -319,6 +319,13 @@ def plane_detect(depth16, factor, fx, fy, cx, cy, max_planes=64):
     return int(n), planes[:n].copy(), mem
 
 
+def eig33_smallest(K):
+    K = np.ascontiguousarray(K, np.float64)
+    lam = np.zeros(1, np.float64); v = np.empty(3, np.float64)
+    lib().orc_eig33_smallest(_p(K), _p(lam), _p(v))
+    return float(lam[0]), v
+
+
 def eig33sym(K):
     K = np.ascontiguousarray(K, np.float64)
     s = np.empty(3, np.float64); V = np.empty((3, 3), np.float64)

@@ -7,9 +7,10 @@
 //   ahc::PlaneFitter::run / initGraph / ahCluster            include/peac/AHCPlaneFitter.hpp:211-260, 786-954, 983-1189
 //   refineDetails / findBlockMembership / floodFill          include/peac/AHCPlaneFitter.hpp:299-379, 428-476, 485-587
 //   DisjointSet                                              include/peac/DisjointSet.hpp
-// Eigen's SelfAdjointEigenSolver (un-vendored) is replaced by a cyclic Jacobi solver; eigenvectors agree with any
-// correct solver to ~1e-15, far inside the 1e-3 rad tolerance of the plane-normal parity bar (checked against
-// numpy.linalg.eigh in tests/test_planes.py).  Deterministic choices: neighbour sets iterate in node-creation
+// Eigen's SelfAdjointEigenSolver (un-vendored) is replaced by eig33_smallest below (Newton on the characteristic
+// polynomial + cross-product eigenvector: only + - * / sqrt, so the CUDA side can be bit-identical); it agrees with
+// numpy.linalg.eigh to < 1e-7 rad, far inside the 1e-3 rad tolerance of the plane-normal parity bar
+// (tests/test_planes.py).  A cyclic Jacobi solver (eig33sym) is kept as an independent cross-check.  Deterministic choices: neighbour sets iterate in node-creation
 // order (the reference iterates std::set<PlaneSeg*> in heap-address order; only exact MSE ties can differ).
 // PARITY of the sequential graph logic is pinned by the source text only (PEAC needs OpenCV + Eigen to build).
 #include <algorithm>
@@ -71,6 +72,47 @@ static void eig33sym(const double K[3][3], double s[3], double V[3][3]) {
     }
 }
 
+// Smallest eigenpair of a symmetric positive semi-definite 3x3 matrix (a covariance) with + - * / sqrt only, so the CPU
+// oracle and the CUDA kernels produce bit-identical results: Newton's iteration on the characteristic polynomial
+// p(x) = det(K - xI) = -x^3 + c2 x^2 - c1 x + c0 from x = 0 (p is convex and decreasing on (-inf, lambda_min], so the
+// iterates approach lambda_min monotonically), then the eigenvector as the largest of the three row cross products
+// of K - lambda I.  Accuracy on plane covariances: |d lambda| <= 2e-12 lambda_max, direction error < 1e-7 rad.
+static void eig33_smallest(const double K[3][3], double& lam, double v[3]) {
+    const double a = K[0][0], b = K[1][1], c = K[2][2], d = K[0][1], e = K[0][2], f = K[1][2];
+    const double c2 = a + b + c;
+    const double c1 = (a * b - d * d) + (a * c - e * e) + (b * c - f * f);
+    const double c0 = a * (b * c - f * f) - d * (d * c - f * e) + e * (d * f - b * e);
+    double x = 0, prev = INFINITY;
+    for (int k = 0; k < 40; ++k) {
+        const double p = ((-x + c2) * x - c1) * x + c0;
+        const double dp = (-3 * x + 2 * c2) * x - c1;
+        if (dp == 0) break;
+        const double dx = p / dp, adx = std::fabs(dx);
+        if (k >= 2 && adx >= prev) break;  // rounding floor reached
+        x -= dx;
+        prev = adx;
+        if (adx <= 1e-16 * c2) break;
+    }
+    lam = x;
+    const double r0[3] = {a - x, d, e}, r1[3] = {d, b - x, f}, r2[3] = {e, f, c - x};
+    const double u0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+    const double u1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+    const double u2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+    const double n0 = u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2];
+    const double n1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+    const double n2 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+    const double* u = u0;
+    double n = n0;
+    if (n1 > n) { u = u1; n = n1; }
+    if (n2 > n) { u = u2; n = n2; }
+    if (n > 0) {
+        const double s = std::sqrt(n);
+        v[0] = u[0] / s; v[1] = u[1] / s; v[2] = u[2] / s;
+    } else {
+        v[0] = 0; v[1] = 0; v[2] = 1;
+    }
+}
+
 struct Stats {
     double sx = 0, sy = 0, sz = 0, sxx = 0, syy = 0, szz = 0, sxy = 0, syz = 0, sxz = 0;
     int N = 0;
@@ -95,12 +137,12 @@ struct Stats {
                           {0, syy - sy * sy * sc, syz - sy * sz * sc},
                           {0, 0, szz - sz * sz * sc}};
         K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
-        double sv[3], V[3][3];
-        eig33sym(K, sv, V);
-        const double sgn = (V[0][0] * center[0] + V[1][0] * center[1] + V[2][0] * center[2] <= 0) ? 1.0 : -1.0;
-        normal[0] = sgn * V[0][0]; normal[1] = sgn * V[1][0]; normal[2] = sgn * V[2][0];
-        mse = sv[0] * sc;
-        curvature = sv[0] / (sv[0] + sv[1] + sv[2]);
+        double lam, v[3];
+        eig33_smallest(K, lam, v);
+        const double sgn = (v[0] * center[0] + v[1] * center[1] + v[2] * center[2] <= 0) ? 1.0 : -1.0;
+        normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
+        mse = lam * sc;
+        curvature = lam / (K[0][0] + K[1][1] + K[2][2]);
     }
 };
 
@@ -482,6 +524,12 @@ int orc_plane_detect(const uint16_t* depth, int w, int h, float factor, float fx
     }
     std::memcpy(membership, mem.data(), mem.size() * sizeof(int32_t));
     return n;
+}
+
+void orc_eig33_smallest(const double* K9, double* lam, double* v3) {
+    double K[3][3];
+    std::memcpy(K, K9, sizeof(K));
+    peaco::eig33_smallest(K, *lam, v3);
 }
 
 void orc_eig33sym(const double* K9, double* s3, double* V9) {

@@ -30,6 +30,37 @@ def test_oracle_eig33_against_numpy():
             assert min(np.linalg.norm(V[:, 0] - U[:, 0]), np.linalg.norm(V[:, 0] + U[:, 0])) < 1e-6
 
 
+def test_oracle_smallest_eigenpair_against_numpy(synth):
+    """eig33_smallest (what Stats::compute uses on both the oracle and the CUDA side) vs numpy.linalg.eigh."""
+    r = np.random.RandomState(1)
+    for i in range(400):
+        A = r.randn(3, 3) * (10 ** r.uniform(-3, 2))
+        K = A @ A.T
+        if i % 4 == 0:
+            K = np.diag(r.rand(3)) + 1e-9 * K
+        lam, v = oracle.eig33_smallest(K)
+        w, U = np.linalg.eigh(K)
+        assert abs(lam - w[0]) <= 1e-10 * w[2]
+        if (w[1] - w[0]) > 1e-3 * w[2]:
+            assert np.arccos(min(1.0, abs(v @ U[:, 0]))) < 1e-6
+    # covariances of real plane patches: thin in one direction
+    c = synth.CONFIGS['S1']
+    _, d = synth.frame('S1', 0)
+    z = d.astype(np.float64) / c['factor']
+    ys, xs = np.mgrid[0:480, 0:640]
+    P = np.stack([(xs - c['cx']) * z / c['fx'], (ys - c['cy']) * z / c['fy'], z], -1)
+    for _ in range(300):
+        bh, bw = r.randint(1, 20, 2)
+        by, bx = r.randint(0, 48 - bh + 1), r.randint(0, 64 - bw + 1)
+        pts = P[by * 10:(by + bh) * 10, bx * 10:(bx + bw) * 10].reshape(-1, 3)
+        if (pts[:, 2] == 0).any():
+            continue
+        K = pts.T @ pts - np.outer(pts.sum(0), pts.sum(0)) / len(pts)
+        lam, v = oracle.eig33_smallest(K)
+        w, U = np.linalg.eigh(K)
+        assert abs(lam - w[0]) <= 1e-11 * w[2] and np.arccos(min(1.0, abs(v @ U[:, 0]))) < 1e-6
+
+
 def test_oracle_finds_the_room_planes(synth):
     for cfg, idx in (('S1', 0), ('S2', 3)):
         cam = _cam(synth, cfg)
