@@ -118,6 +118,15 @@ ABI = {
     'hvo_normals_sync': (C.c_int, [_vp]),
     'hvo_normals_timer_start': (C.c_int, [_vp]),
     'hvo_normals_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_frame_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_frame_destroy': (None, [_vp]),
+    'hvo_frame_capacities': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'hvo_frame_extract_batch': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'hvo_frame_extract_batch_device': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'hvo_frame_last_launches': (C.c_int, [_vp]),
+    'hvo_frame_sync': (C.c_int, [_vp]),
+    'hvo_frame_timer_start': (C.c_int, [_vp]),
+    'hvo_frame_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 
@@ -763,3 +772,102 @@ class LSDmatcher:
         ok = (gap.astype(np.float64) > nn12_th) & (d0 < np.float32(TH)) & (d0 < self.mfNNratio * d1)
         out[ok] = idx[ok, 0]
         return out
+
+
+# ---- Frame-level front-end ----------------------------------------------------------------------------------------
+STAGE_ORB, STAGE_LINES, STAGE_PLANES, STAGE_NORMALS, STAGE_ALL = 1, 2, 4, 8, 15
+
+
+class _FrameParams(C.Structure):
+    _fields_ = [('orb', _OrbParams), ('line', _LineParams), ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
+                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int)]
+
+
+class _FrameOutputs(C.Structure):
+    _fields_ = [(n, _vp) for n in ('kps', 'desc', 'kp_counts', 'kp_depth', 'kp_uright', 'keylines', 'line_desc', 'linevec3',
+                                   'line_counts', 'n_planes', 'planes7', 'membership', 'normals8')]
+
+
+class FrameFrontEnd:
+    """The extraction part of ORB_SLAM2::Frame::Frame(imGray, imDepth, ...) (reference src/Frame.cc:188-233): ORB + RGB-D
+    depth lookup, LSD/LBD lines, PEAC planes and surface normals of a batch of frames, three concurrent CUDA streams."""
+    FIELDS = [f[0] for f in _FrameOutputs._fields_]
+
+    def __init__(self, width, height, fx, fy, cx, cy, depth_factor, bf=40.0, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
+                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0):
+        prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
+                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes)
+        out = _vp()
+        _check(lib().hvo_frame_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
+        self._h = out
+        self.w, self.h, self.max_batch, self.stages, self.max_planes = int(width), int(height), int(max_batch), stages, max_planes
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().hvo_frame_capacities(out, C.byref(a), C.byref(b), C.byref(c)))
+        self.orb_capacity, self.max_lines, self.normals_count = a.value, b.value, c.value
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_frame_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def output_shapes(self, n):
+        """name -> (shape, numpy dtype) of every output of an n-frame batch (for the selected stages)."""
+        sh = {}
+        if self.stages & STAGE_ORB:
+            c = self.orb_capacity
+            sh.update(kps=((n, c), KP_DTYPE), desc=((n, c, 32), np.uint8), kp_counts=((n,), np.int32), kp_depth=((n, c), np.float32),
+                      kp_uright=((n, c), np.float32))
+        if self.stages & STAGE_LINES:
+            c = self.max_lines
+            sh.update(keylines=((n, c), KL_DTYPE), line_desc=((n, c, 32), np.uint8), linevec3=((n, c, 3), np.float64),
+                      line_counts=((n,), np.int32))
+        if self.stages & STAGE_PLANES:
+            sh.update(n_planes=((n,), np.int32), planes7=((n, self.max_planes, 7), np.float64), membership=((n, self.h * self.w), np.int32))
+        if self.stages & STAGE_NORMALS:
+            sh.update(normals8=((n, self.normals_count, 8), np.float32))
+        return sh
+
+    def alloc_host(self, n):
+        return {k: np.empty(s, d) for k, (s, d) in self.output_shapes(n).items()}
+
+    def _outputs(self, ptrs):
+        o = _FrameOutputs()
+        for k in self.FIELDS:
+            setattr(o, k, ptrs.get(k))
+        return o
+
+    def extract_batch(self, gray, depth16, out=None):
+        """gray [n,h,w] uint8, depth16 [n,h,w] uint16 (host) -> dict of host arrays (see output_shapes)."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth16 = np.ascontiguousarray(depth16, np.uint16)
+        n = len(gray)
+        if out is None:
+            out = self.alloc_host(n)
+        o = self._outputs({k: v.ctypes.data for k, v in out.items()})
+        _check(lib().hvo_frame_extract_batch(self._h, _np_ptr(gray), _np_ptr(depth16), n, C.byref(o)))
+        return out
+
+    def extract_batch_device(self, d_gray, d_depth16, n, d_ptrs):
+        """d_ptrs: name -> device pointer (int) for every output of output_shapes(n).  Asynchronous."""
+        o = self._outputs(d_ptrs)
+        _check(lib().hvo_frame_extract_batch_device(self._h, _vp(d_gray), _vp(d_depth16), n, C.byref(o)))
+
+    def last_launches(self):
+        return lib().hvo_frame_last_launches(self._h)
+
+    def sync(self):
+        _check(lib().hvo_frame_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_frame_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_frame_timer_stop(self._h, C.byref(ms)))
+        return ms.value

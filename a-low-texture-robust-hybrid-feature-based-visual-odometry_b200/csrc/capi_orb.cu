@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
 
 using namespace hvo;
 
+namespace hvo {
+cudaStream_t orb_stream(hvo_orb* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+}
+
 extern "C" {
 
 const char* hvo_last_error(void) { return g_err; }

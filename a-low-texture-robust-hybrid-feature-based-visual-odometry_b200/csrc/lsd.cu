@@ -617,6 +617,10 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
     return st;
 }
 
+namespace hvo {
+cudaStream_t line_stream(hvo_line* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+}
+
 extern "C" {
 
 int hvo_line_create(const hvo_line_params* p, int width, int height, int max_batch, int device, hvo_line** out) {

@@ -192,6 +192,10 @@ static int sn_run(hvo_normals* h, const uint16_t* d_depth, int nf, float* d_out)
     return HVO_OK;
 }
 
+namespace hvo {
+cudaStream_t normals_stream(hvo_normals* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+}
+
 extern "C" {
 
 int hvo_normals_create(const hvo_normals_params* p, int width, int height, int max_batch, int device, hvo_normals** out) {

@@ -806,6 +806,10 @@ struct hvo_plane {
     int last_launches = 0;
 };
 
+namespace hvo {
+cudaStream_t plane_stream(hvo_plane* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+}
+
 extern "C" {
 
 int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_batch, int device, hvo_plane** out) {

@@ -33,9 +33,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'front-end frames/s @640x480'
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
-DEPTH_FACTOR, BF = 1.0 / 5000.0, 40.0
-# algorithmic bytes per 640x480 frame (SURVEY.md section 8d / BASELINE.md section 5)
-BYTES_PYRAMID, BYTES_FAST, BYTES_BLUR, BYTES_DESCRIBE_PATCH, BYTES_OUT = 1569878, 950532, 1901064, 1922000, 60000
+CAM = dict(fx=535.4, fy=539.2, cx=320.1, cy=247.6)                             # TUM3.yaml:8-11
+DEPTH_FACTOR, BF, NLINES = 1.0 / 5000.0, 40.0, 200                             # TUM3.yaml:34, Camera.bf, LINE.nFeatures
+ORACLE_CAM = (DEPTH_FACTOR, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'])
+STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + rBRIEF + RGB-D depth lookup',
+          'lines: LSD (blur, 0.8 resize, gradient, ordered region growing, rectangles) + KeyLines + top-200 + LBD + line functions',
+          'planes: depth back-projection + 10x10 block fits + AHC merging + block erosion + ordered pixel flood fill + last merge',
+          'normals: 3x subsampled cloud + integral-image normals (PCL AVERAGE_3D_GRADIENT restatement)']
+# algorithmic bytes per 640x480 frame of the HBM-bound kernels
+ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_cells': 950532, 'k_describe': 1922000 + 60000,
+             'k_lsd_prep': 307200 + 16 * 512 * 384, 'k_plane_blocks': 614400 + 3072 * 96}
 
 
 def _gen(args):
@@ -123,45 +130,50 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-def cpu_baseline(gray, target_s=12.0):
-    """The oracle port timed on the host cores: frame-parallel over all cores (frames are independent)."""
+def cpu_baseline(gray, depth, target_s=15.0):
+    """The oracle port of the whole front-end timed on the host cores: frame-parallel over all cores."""
     import oracle
     cores = os.cpu_count() or 1
-    oracle.orb_extract_batch(gray[:cores], nthreads=cores, **ORB)  # warm-up / page-in
+    ns = min(len(gray), 2 * cores)
+    g, d = gray[:ns], depth[:ns]
+    oracle.frontend_batch(g[:cores], d[:cores], ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)  # warm-up / page-in
     n, dt, counts = 0, 0.0, []
     t0 = time.perf_counter()
     while dt < target_s:  # bounded sample: whole passes over the same frames until ~target_s of CPU work
-        counts.append(oracle.orb_extract_batch(gray, nthreads=cores, **ORB))
-        n += len(gray)
+        counts.append(oracle.frontend_batch(g, d, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB).mean(axis=0))
+        n += ns
         dt = time.perf_counter() - t0
+    c = np.mean(counts, axis=0)
     return dict(value=n / dt, unit='frames/s', cores=cores, kind='port',
-                sample=f'{n} frames ({n // len(gray)} passes over the same {len(gray)} synthetic 640x480 frames), ORB stage, oracle '
-                       f'C++ port (-O3), one frame per thread on {cores} threads, {dt:.1f} s, '
-                       f'mean {float(np.mean(counts)):.0f} keypoints/frame')
+                sample=f'{n} frames ({n // ns} passes over the same {ns} synthetic 640x480 RGB-D frames), whole front-end (ORB + LSD/LBD lines '
+                       f'+ PEAC planes + surface normals), oracle C++ port (-O3), one frame per thread on {cores} threads, {dt:.1f} s; '
+                       f'mean per frame: {c[0]:.0f} keypoints, {c[1]:.0f} lines, {c[2]:.1f} planes, {c[3]:.0f} normals')
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on all host cores; rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port of the whole front-end) on all host cores; rank 0 only."""
     if rank != 0:
         return
     import oracle
     cores = os.cpu_count() or 1
-    sample = max(cores, min(args.batch, 4 * cores))
-    gray, _ = make_frames(sample)
+    sample = max(cores, min(args.batch, 2 * cores))
+    gray, depth = make_frames(sample)
     for _ in range(args.warmup):
-        oracle.orb_extract_batch(gray, nthreads=cores, **ORB)
+        oracle.frontend_batch(gray, depth, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)
     t = time.perf_counter()
     for _ in range(args.steps):
-        oracle.orb_extract_batch(gray, nthreads=cores, **ORB)
+        oracle.frontend_batch(gray, depth, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)
     dt = time.perf_counter() - t
     v = sample * args.steps / dt
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480, ORB 1000 features 8 levels x1.2; bounded sample of {sample} frames/step',
-                   'stages': ['orb'], 'note': 'reference CPU path = oracle port (bit-identical to the reference ORBextractor.cc built in oracle/_ref); '
-                                              'the reference binary needs OpenCV/PCL/Eigen/Pangolin, absent here'},
+        'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D, whole front-end (ORB 1000 features 8 levels x1.2, <=200 LSD/LBD '
+                               f'lines, PEAC planes, surface normals); bounded sample of {sample} frames/step',
+                   'stages': STAGES, 'note': 'reference CPU path = oracle port (ORB bit-identical to the reference ORBextractor.cc built in '
+                                             'oracle/_ref; LSD bit-identical to cv2 4.13.0); the reference binary needs OpenCV/PCL/Eigen/'
+                                             'Pangolin, absent here'},
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': f'{sample} frames x {args.steps} steps'},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -171,10 +183,11 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=1024, help='frames per GPU per step')
+    ap.add_argument('--stages', type=int, default=15, help='bit 0 ORB, 1 lines, 2 planes, 3 normals (profiling aid; the metric is 15)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--device-only', action='store_true', help='profiling aid: only the device-resident loop')
     args = ap.parse_args()
@@ -199,22 +212,19 @@ def main():
 
     B, W, H = args.batch, 640, 480
     gray, depth = make_frames(B, start=rank * B)  # every rank gets its own frames (frame-sharded, weak scaling)
-    ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'],
-                          width=W, height=H, max_batch=B, device=local_rank)
-    cap = ex.capacity
+    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages,
+                           max_batch=B, device=local_rank, nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'],
+                           nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
     dev = torch.device('cuda', local_rank)
     d_gray = torch.from_numpy(gray).to(dev)
     d_depth = torch.from_numpy(depth.view(np.int16)).to(dev)
-    d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
-    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
-    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    d_kd = torch.empty((B, cap), dtype=torch.float32, device=dev)
-    d_ku = torch.empty((B, cap), dtype=torch.float32, device=dev)
+    shapes = fe.output_shapes(B)
+    d_out = {k: torch.empty(int(np.prod(sh)) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, (sh, dt) in shapes.items()}
+    d_ptrs = {k: v.data_ptr() for k, v in d_out.items()}
     torch.cuda.synchronize()
 
     def step_device():
-        ex.extract_batch_device(d_gray.data_ptr(), B, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr(),
-                                d_depth.data_ptr(), DEPTH_FACTOR, BF, d_kd.data_ptr(), d_ku.data_ptr())
+        fe.extract_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), B, d_ptrs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,100 +239,168 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def d_counts(name):
+        return d_out[name].view(torch.int32).float().mean().item() if name in d_out else None
+
     # ---- value: inputs resident in HBM ----
     for _ in range(args.warmup):
         step_device()
-    ex.sync()
+    fe.sync()
     clocks = ClockSampler(local_rank)
     clocks.start()
     time.sleep(0.25)
     barrier()
     t0 = time.time()
-    ex.timer_start()
+    fe.timer_start()
     for _ in range(args.steps):
         step_device()
-    ms = ex.timer_stop()
+    ms = fe.timer_stop()
     t1 = time.time()
     barrier()
     clk = clocks.stop(t0, t1)
     ms = max_over_ranks(ms)
-    launches_per_step = ex.last_launches()
+    launches_per_step = fe.last_launches()
     value = world * B * args.steps / (ms * 1e-3)
-    mean_kp = float(d_counts.float().mean().item())
+    means = dict(keypoints=d_counts('kp_counts'), lines=d_counts('line_counts'), planes=d_counts('n_planes'))
 
     if args.device_only:
-        print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True}))
+        print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
+                          'stages': args.stages, 'means': means}))
         return
 
-    # ---- per-stage device times (separate, profiled pass; events between stages) ----
+    # ---- per-stage device times: every pipeline alone on the same batch (standalone handles, smaller batch) ----
+    Bs = min(B, 256)
+    stage_ms, kern_ms = {}, {}
+    ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'], width=W, height=H,
+                          max_batch=Bs, device=local_rank)
+    kp = d_ptrs
+
+    def orb_step():
+        ex.extract_batch_device(d_gray.data_ptr(), Bs, kp['kps'], kp['desc'], kp['kp_counts'], d_depth.data_ptr(), DEPTH_FACTOR, BF,
+                                kp['kp_depth'], kp['kp_uright'])
+    for _ in range(2):
+        orb_step()
+    ex.sync()
+    ex.timer_start()
+    for _ in range(5):
+        orb_step()
+    stage_ms['orb'] = ex.timer_stop() / 5
     ex.set_profiling(True)
-    stage = {k: 0.0 for k in ('pyramid', 'fast', 'octree', 'blur', 'describe')}
-    reps = 5
-    for _ in range(reps):
-        step_device()
+    acc = {}
+    for _ in range(5):
+        orb_step()
         ex.sync()
         for k, v in ex.stage_times().items():
-            stage[k] += v / reps
-    ex.set_profiling(False)
-    alg = {'pyramid': BYTES_PYRAMID, 'fast': BYTES_FAST, 'blur': BYTES_BLUR, 'describe': BYTES_DESCRIBE_PATCH + BYTES_OUT}
-    dom = max(('pyramid', 'fast', 'blur', 'describe'), key=lambda k: stage[k])
+            acc[k] = acc.get(k, 0.0) + v / 5
+    ex.close()
+    kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_cells': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
+
+    le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
+
+    def line_step():
+        le.extract_batch_device(d_gray.data_ptr(), Bs, kp['keylines'], kp['line_desc'], kp['linevec3'], kp['line_counts'])
+    line_step()
+    le.sync()
+    le.timer_start()
+    for _ in range(3):
+        line_step()
+    stage_ms['lines'] = le.timer_stop() / 3
+    le.set_profiling(True)
+    line_step()
+    le.sync()
+    lt = le.stage_times()
+    le.close()
+    kern_ms.update({'k_lsd_prep': lt['prep'], 'k_lsd_order': lt['order'], 'k_lsd_grow': lt['grow'], 'k_line_keylines + k_lbd_*': lt['keylines_lbd']})
+
+    pd = hvo.PlaneDetection(W, H, max_batch=Bs, device=local_rank)
+    pd.readDepthImage(depth[0], np.array([[CAM['fx'], 0, CAM['cx']], [0, CAM['fy'], CAM['cy']], [0, 0, 1]], np.float32), np.float32(DEPTH_FACTOR))
+
+    def plane_step():
+        pd.detect_batch_device(d_depth.data_ptr(), Bs, kp['n_planes'], kp['planes7'], fe.max_planes, kp['membership'])
+    plane_step()
+    pd.sync()
+    pd.timer_start()
+    for _ in range(3):
+        plane_step()
+    stage_ms['planes'] = pd.timer_stop() / 3
+    pd.timer_start()
+    for _ in range(5):
+        pd.blocks_device(d_depth.data_ptr(), Bs)
+    kern_ms['k_plane_blocks'] = pd.timer_stop() / 5
+    kern_ms['k_plane_cluster + k_plane_flood + k_plane_merge'] = stage_ms['planes'] - kern_ms['k_plane_blocks']
+    pd.close()
+
+    sn = hvo.SurfaceNormals(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, max_batch=Bs, device=local_rank)
+    sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
+    sn.sync()
+    sn.timer_start()
+    for _ in range(5):
+        sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
+    stage_ms['normals'] = sn.timer_stop() / 5
+    sn.close()
+
+    # roofline: the dominant kernel among the HBM-bound (stencil / streaming) kernels; the ordered graph kernels
+    # (k_octree, k_lsd_grow, k_plane_cluster/flood/merge) are latency-bound by construction and are listed beside it
     peak, peak_src = measured_peak()
-    achieved = alg[dom] * B / (stage[dom] * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel={'pyramid': 'k_resize x7', 'fast': 'k_fast_cells', 'blur': 'k_blur', 'describe': 'k_describe'}[dom],
-                    achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=alg[dom] * B,
-                    stage_ms={k: round(v, 4) for k, v in stage.items()},
-                    stage_frac_of_hbm={k: round(alg[k] * B / (stage[k] * 1e-3) / 1e9 / peak, 4) for k in alg})
+    dom = max(ALG_BYTES, key=lambda k: kern_ms[k])
+    achieved = ALG_BYTES[dom] * Bs / (kern_ms[dom] * 1e-3) / 1e9
+    roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
+                    peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
+                    kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
+                    frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
+                    stage_ms_alone={k: round(v, 3) for k, v in stage_ms.items()},
+                    serial_kernels='k_lsd_grow, k_plane_cluster, k_plane_flood, k_plane_merge and k_octree run the reference\'s ordered '
+                                   '(sequential) algorithms, one warp/CTA per frame; they are latency-bound, not HBM-bound, and dominate the step '
+                                   '(see kernel_ms); their throughput comes from the batch (frames in flight), not from bandwidth')
 
     # ---- e2e: host (pinned) buffers through the C-ABI call, copies inside the timed region ----
     def pinned(shape, dtype):
-        t = torch.empty(shape, dtype=dtype, pin_memory=True)
-        return t, t.numpy()
-    _, h_gray = pinned((B, H, W), torch.uint8)
-    _, h_depth_i16 = pinned((B, H, W), torch.int16)
-    h_depth = h_depth_i16.view(np.uint16)
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return t.numpy().view(dtype).reshape(shape)
+    h_gray = pinned((B, H, W), np.uint8)
+    h_depth = pinned((B, H, W), np.uint16)
     h_gray[:] = gray
     h_depth[:] = depth
-    out = dict(counts=pinned((B,), torch.int32)[1], kps=pinned((B, cap, 7), torch.float32)[1].view(hvo.KP_DTYPE).reshape(B, cap),
-               desc=pinned((B, cap, 32), torch.uint8)[1], depth=pinned((B, cap), torch.float32)[1],
-               uright=pinned((B, cap), torch.float32)[1])
-    for _ in range(args.warmup):
-        ex.extract_batch(h_gray, depth16=h_depth, depth_factor=DEPTH_FACTOR, bf=BF, out=out)
+    out = {k: pinned(sh, dt) for k, (sh, dt) in shapes.items()}
+    for _ in range(2):
+        fe.extract_batch(h_gray, h_depth, out=out)
     barrier()
-    ex.timer_start()
-    for _ in range(args.steps):
-        ex.extract_batch(h_gray, depth16=h_depth, depth_factor=DEPTH_FACTOR, bf=BF, out=out)
-    e2e_ms = max_over_ranks(ex.timer_stop())
+    e2e_steps = max(3, args.steps // 2)
+    fe.timer_start()
+    for _ in range(e2e_steps):
+        fe.extract_batch(h_gray, h_depth, out=out)
+    e2e_ms = max_over_ranks(fe.timer_stop())
     barrier()
-    e2e = dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit='frames/s',
+    e2e = dict(value=world * B * e2e_steps / (e2e_ms * 1e-3), unit='frames/s',
                h2d_bytes_per_step=int(h_gray.nbytes + h_depth.nbytes),
-               d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())), ms_per_step=e2e_ms / args.steps)
+               d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())), ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps)
 
-    # ---- single-frame latency through operator() (p50) ----
-    ex1 = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'],
-                           width=W, height=H, max_batch=1, device=local_rank)
+    # ---- single-frame latency through the host call (p50) ----
+    fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages,
+                            max_batch=1, device=local_rank)
+    out1 = fe1.alloc_host(1)
     lat = []
-    for i in range(40):
+    for i in range(24):
         t = time.perf_counter()
-        ex1(gray[i % B])
+        fe1.extract_batch(gray[i % B][None], depth[i % B][None], out=out1)
         lat.append(1e3 * (time.perf_counter() - t))
-    p50 = float(np.median(lat[8:]))
-    ex1.close()
+    p50 = float(np.median(lat[4:]))
+    fe1.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(gray)
+        cpu = cpu_baseline(gray, depth)
 
     if rank == 0:
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic',
-            'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames, ORB 1000 features 8 levels x1.2 (TUM3.yaml), '
-                                   f'{B} distinct frames per GPU per step, frame-sharded over {world} GPU(s)',
-                       'stages': ['orb: pyramid + per-cell FAST + quadtree + IC_Angle + blur + rBRIEF + RGB-D depth lookup'],
-                       'batch_per_gpu': B, 'mean_keypoints_per_frame': mean_kp,
-                       'l2': f'inputs larger than L2: per-step working set {B} frames x ~2.2 MB (gray, pyramid, candidates) >> 126 MB'},
+            'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames (TUM3.yaml: ORB 1000 features 8 levels x1.2, LINE 200), '
+                                   f'whole front-end of Frame::Frame, {B} distinct frames per GPU per step, frame-sharded over {world} GPU(s)',
+                       'stages': STAGES, 'batch_per_gpu': B, 'mean_per_frame': means,
+                       'l2': f'inputs larger than L2: per-step inputs {B} x 0.92 MB and working set ~{B} x 17 MB >> 126 MB'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step, 'clocks': clk, 'p50_latency_ms_single_frame': p50,
         }))

@@ -277,6 +277,61 @@ int hvo_normals_sync(hvo_normals* h);
 int hvo_normals_timer_start(hvo_normals* h);
 int hvo_normals_timer_stop(hvo_normals* h, float* ms_out);
 
+/* ---------------------------------------------------------------------------------------------- FRAME
+ * The extraction part of Frame::Frame(imGray, imDepth, timeStamp, extractors, ...) (src/Frame.cc:188-233): the reference
+ * runs three std::threads on one frame — ExtractORBNDepth (:874-884), ExtractLSD (:895-903), ComputePlanes
+ * (:2104-2212).  hvo_frame uploads the frame (gray + raw 16-bit depth) once and runs the same three pipelines on three
+ * CUDA streams, for a batch of frames per call.                                                               */
+
+#define HVO_STAGE_ORB 1
+#define HVO_STAGE_LINES 2
+#define HVO_STAGE_PLANES 4
+#define HVO_STAGE_NORMALS 8
+#define HVO_STAGE_ALL 15
+
+typedef struct hvo_frame_params {
+    hvo_orb_params orb;   /* ORBextractor.* of the settings file */
+    hvo_line_params line; /* LINE.* */
+    float fx, fy, cx, cy; /* Camera.* */
+    float depth_factor;   /* 1 / DepthMapFactor */
+    float bf;             /* Camera.bf */
+    int stages;           /* HVO_STAGE_* bits */
+    int max_planes;       /* rows of planes7 per frame */
+} hvo_frame_params;
+
+/* Output arrays of a batch of n frames.  Host pointers for hvo_frame_extract_batch, device pointers for
+ * hvo_frame_extract_batch_device.  Row counts per frame come from hvo_frame_capacities(). */
+typedef struct hvo_frame_outputs {
+    hvo_keypoint* kps;     /* [n][orb_capacity]      mvKeys                                       */
+    uint8_t* desc;         /* [n][orb_capacity][32]  mDescriptors                                 */
+    int32_t* kp_counts;    /* [n]                    N                                            */
+    float* kp_depth;       /* [n][orb_capacity]      mvDepth  (-1 invalid)   optional on the host */
+    float* kp_uright;      /* [n][orb_capacity]      mvuRight (-1 invalid)   optional on the host */
+    hvo_keyline* keylines; /* [n][max_lines]         mvKeylinesUn                                 */
+    uint8_t* line_desc;    /* [n][max_lines][32]     mLdesc                                       */
+    double* linevec3;      /* [n][max_lines][3]      mvKeyLineFunctions      optional on the host */
+    int32_t* line_counts;  /* [n]                    NL                                           */
+    int32_t* n_planes;     /* [n]                    plane_num_                                   */
+    double* planes7;       /* [n][max_planes][7]     normal, center, N of extractedPlanes         */
+    int32_t* membership;   /* [n][H*W]               plane id per pixel or -1 (-> plane_vertices_) */
+    float* normals8;       /* [n][normals_count][8]  std::vector<SurfaceNormal>                   */
+} hvo_frame_outputs;
+
+typedef struct hvo_frame hvo_frame;
+int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_batch, int device, hvo_frame** out);
+void hvo_frame_destroy(hvo_frame* h);
+int hvo_frame_capacities(const hvo_frame* h, int* orb_capacity, int* max_lines, int* normals_count);
+/* gray [n][H][W] uint8 and depth16 [n][H][W] uint16 in host memory (pinned memory makes the copies asynchronous);
+ * returns when every output has been written. */
+int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out);
+/* Everything device-resident; asynchronous.  hvo_frame_sync / hvo_frame_timer_stop wait for all three pipelines. */
+int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const uint16_t* d_depth16, int nframes,
+                                   const hvo_frame_outputs* d_out);
+int hvo_frame_last_launches(const hvo_frame* h);
+int hvo_frame_sync(hvo_frame* h);
+int hvo_frame_timer_start(hvo_frame* h);
+int hvo_frame_timer_stop(hvo_frame* h, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

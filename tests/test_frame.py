@@ -1,0 +1,73 @@
+"""Frame-level front-end (hvo_frame_*): one call runs ORB + lines + planes + normals of a batch on three CUDA streams.
+Bar: every output equals what the standalone extractors produce (which are checked against the oracle in their own
+tests), and ORB / planes / normals also directly against the oracle here."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _cam(synth, cfg):
+    c = synth.CONFIGS[cfg]
+    return c['fx'], c['fy'], c['cx'], c['cy'], 1.0 / c['factor']
+
+
+@pytest.mark.gpu
+def test_gpu_frame_front_end_matches_oracle_and_standalone(hvo, synth):
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 3, start=40)
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, bf=40.0, max_batch=3)
+    out = fe.extract_batch(gray, depth)
+    ex = hvo.LINEextractor(1, 1.2, 200, 0.125)
+    for f in range(3):
+        # ORB: bit-exact vs the oracle
+        ok, od = oracle.OrbOracle().extract(gray[f])
+        n = int(out['kp_counts'][f])
+        assert n == len(ok) and out['kps'][f, :n].tobytes() == ok.tobytes() and np.array_equal(out['desc'][f, :n], od)
+        # ComputeStereoFromRGBD (Frame.cc:1940-1961)
+        u, v = ok['x'].astype(np.int32), ok['y'].astype(np.int32)
+        d = depth[f][v, u].astype(np.float32) * np.float32(df)
+        valid = d > 0
+        assert np.array_equal(out['kp_depth'][f, :n][valid], d[valid]) and np.all(out['kp_depth'][f, :n][~valid] == -1)
+        # lines: same as the standalone extractor
+        kl, desc, lv = ex(gray[f])
+        nl = int(out['line_counts'][f])
+        assert nl == len(kl) and out['keylines'][f, :nl].tobytes() == kl.tobytes()
+        assert np.array_equal(out['line_desc'][f, :nl], desc) and np.array_equal(out['linevec3'][f, :nl], lv)
+        # planes: vs the oracle
+        on, op, om = oracle.plane_detect(depth[f], np.float32(df), fx, fy, cx, cy)
+        assert int(out['n_planes'][f]) == on and np.array_equal(out['membership'][f], om)
+        assert np.allclose(out['planes7'][f, :on, :6], op[:, :6], atol=1e-9)
+        # normals: vs the oracle (NaN-aware)
+        ref = oracle.surface_normals(depth[f], np.float32(df), fx, fy, cx, cy)
+        got = out['normals8'][f]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert np.allclose(np.nan_to_num(got), np.nan_to_num(ref), atol=2e-5)
+    fe.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frame_stage_subsets_and_errors(hvo, synth):
+    fx, fy, cx, cy, df = _cam(synth, 'S2')
+    gray, depth = synth.sequence('S2', 2, start=5)
+    full = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=2).extract_batch(gray, depth)
+    for stages, keys in ((hvo.STAGE_ORB, ('kps', 'desc', 'kp_counts')), (hvo.STAGE_LINES | hvo.STAGE_NORMALS, ('keylines', 'normals8')),
+                         (hvo.STAGE_PLANES, ('n_planes', 'membership'))):
+        fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, stages=stages, max_batch=2)
+        out = fe.extract_batch(gray, depth)
+        for k in keys:
+            if k in ('kps', 'desc'):
+                for f in range(2):
+                    n = int(out['kp_counts'][f])
+                    assert out[k][f, :n].tobytes() == full[k][f, :n].tobytes()
+            elif k == 'keylines':
+                for f in range(2):
+                    n = int(out['line_counts'][f])
+                    assert n == int(full['line_counts'][f]) and out[k][f, :n].tobytes() == full[k][f, :n].tobytes()
+            else:
+                assert np.array_equal(out[k], full[k], equal_nan=True)
+        with pytest.raises(hvo.HvoError):
+            fe.extract_batch(np.concatenate([gray, gray]), np.concatenate([depth, depth]))   # more frames than max_batch
+        fe.close()
+    with pytest.raises(hvo.HvoError):
+        hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, stages=0)
