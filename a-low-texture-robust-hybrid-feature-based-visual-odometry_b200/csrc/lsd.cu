@@ -10,7 +10,8 @@
 //                   descending (warp-private histograms in shared memory, match_any ranks) = LSD's seed order
 //   k_lsd_grow      one warp per frame: the ordered, inherently sequential part (region growing with a running mean
 //                   angle, rectangle fit, density refinement).  Lanes hold the 8 neighbours of three consecutive region
-//                   points; the `used` map is a bitmap in shared memory; sums over a region are warp reductions.
+//                   points; the `used` map is a bitmap in global memory (no shared memory: 32 frames per SM, and the
+//                   kernel co-resides with the other pipelines); sums over a region are warp reductions.
 //                   Frames are independent, so a batch fills the machine with one warp per frame.
 //   k_line_keylines one CTA per frame: KeyLine fields, rank by response (ties: detection order), keep nLSDFeature,
 //                   2-D line functions
@@ -337,10 +338,12 @@ __device__ __forceinline__ double lsd_density(int n, const LsdRect& r) {
 __global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix, int w, int h, const uint32_t* __restrict__ order,
                                                  const int* __restrict__ norder, uint32_t* __restrict__ regbuf, int min_reg_size,
                                                  double prec, double density_th, double inv_scale_div, float* __restrict__ seg,
-                                                 int seg_cap, int* __restrict__ nseg) {
-    extern __shared__ uint32_t used[];  // bitmap, 1 = USED
+                                                 int seg_cap, int* __restrict__ nseg, uint32_t* __restrict__ usedbuf) {
     const int f = blockIdx.x, lane = threadIdx.x;
     const int npix = w * h;
+    // `used` map: one bit per pixel in global memory (L1/L2 resident, touched only around the growing region).  Keeping it
+    // out of shared memory lets 32 frames share an SM and lets this latency-bound kernel co-reside with the other pipelines.
+    uint32_t* used = usedbuf + (size_t)f * ((npix + 31) >> 5);
     const LsdPix* P = pix + (long long)f * npix;
     const uint32_t* ord = order + (long long)f * npix;
     volatile uint32_t* reg = regbuf + (long long)f * npix;
@@ -544,7 +547,7 @@ struct hvo_line {
     LsdPix* d_pix = nullptr;
     uint8_t* d_scaled = nullptr;
     int* d_maxsq = nullptr;
-    uint32_t *d_order = nullptr, *d_reg = nullptr;
+    uint32_t *d_order = nullptr, *d_reg = nullptr, *d_used = nullptr;
     int *d_norder = nullptr, *d_nseg = nullptr;
     float *d_seg = nullptr, *d_resp = nullptr;
     KeyLineOut* d_kl = nullptr;
@@ -595,9 +598,8 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
     if (h->profiling) cudaEventRecord(h->sev[1], s);
     k_lsd_order<<<nframes, 1024, kOrdWarps * kBins * sizeof(uint32_t), s>>>(h->d_pix, npix, h->d_maxsq, h->d_order, h->d_norder);
     if (h->profiling) cudaEventRecord(h->sev[2], s);
-    const size_t bm = (size_t)((npix + 31) / 32) * 4;
-    k_lsd_grow<<<nframes, 32, bm, s>>>(h->d_pix, h->sw, h->sh, h->d_order, h->d_norder, h->d_reg, h->min_reg_size, h->prec, 0.7, 0.8,
-                                       h->d_seg, h->seg_cap, h->d_nseg);
+    k_lsd_grow<<<nframes, 32, 0, s>>>(h->d_pix, h->sw, h->sh, h->d_order, h->d_norder, h->d_reg, h->min_reg_size, h->prec, 0.7, 0.8,
+                                      h->d_seg, h->seg_cap, h->d_nseg, h->d_used);
     if (h->profiling) cudaEventRecord(h->sev[3], s);
     h->last_launches = 3;
     HVO_CUDA(cudaGetLastError());
@@ -684,6 +686,7 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
         HVO_TRY(cudaMalloc(&h->d_maxsq, B * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_order, B * spx * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_reg, B * spx * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_used, B * ((spx + 31) / 32) * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_norder, B * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_nseg, B * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_seg, B * (size_t)h->seg_cap * 4 * sizeof(float)));
@@ -696,9 +699,6 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
         HVO_TRY(cudaMemcpy(h->d_cy, cy.data(), cy.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
         HVO_TRY(cudaMemcpy(h->d_cstab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
         HVO_TRY(cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrdWarps * kBins * (int)sizeof(uint32_t)));
-        const int bm = ((h->sw * h->sh + 31) / 32) * 4;
-        if (bm > 200 * 1024) { set_error("image too large for the shared-memory `used` bitmap"); st = HVO_ERR_ARG; break; }
-        HVO_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, bm));
 #undef HVO_TRY
     } while (0);
     if (st == HVO_OK) st = hvo_lbd_create(width, height, max_batch, h->nfeat, device, &h->lbd);
@@ -712,7 +712,7 @@ void hvo_line_destroy(hvo_line* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->lbd) hvo_lbd_destroy(h->lbd);
-    void* bufs[] = {h->d_gray, h->d_cx, h->d_cy, h->d_cstab, h->d_pix, h->d_scaled, h->d_maxsq, h->d_order, h->d_reg, h->d_norder,
+    void* bufs[] = {h->d_gray, h->d_cx, h->d_cy, h->d_cstab, h->d_pix, h->d_scaled, h->d_maxsq, h->d_order, h->d_reg, h->d_used, h->d_norder,
                     h->d_nseg, h->d_seg, h->d_resp, h->d_kl, h->d_linevec, h->d_counts, h->d_desc};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);

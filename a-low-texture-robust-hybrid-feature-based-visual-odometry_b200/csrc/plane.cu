@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128) k_plane_blocks(const uint16_t* __restrict
 struct __align__(16) NodeG { double s[9]; double center[3]; double normal[3]; int N; int rid; };  // 128 bytes
 
 static const int kMinSupport = 3000, kAhcThreads = 128;
+static const int kRowW = 9;  // neighbour-matrix row words per lane: up to 9 * 32 * 32 = 9216 blocks (1280x720)
 #define AHC_TH_MERGE 0.50000000000000011   /* cos(pi/180*60) as computed by std::cos */
 #define AHC_TH_REFINE 0.86602540378443871  /* cos(pi/180*30) */
 
@@ -179,9 +180,11 @@ __device__ __forceinline__ double ahc_t_ang_init(double z) {  // ParamSet::T_ang
     return cos(factor * cz + a_near - factor * z_near);
 }
 
-struct AhcS {  // views into dynamic shared memory
-    double* mse;        // [Nb]
-    uint16_t* heap;     // [Nb]  (aliased by blkmap between the two clustering passes)
+
+struct AhcS {  // working set of the clustering kernels (shared memory unless noted)
+    double* mse;        // [Nb]  global: exact MSE of every node
+    float* hkey;        // [Nb]  heap: float(mse) of the entry (monotone in mse; exact double compare only when two keys are equal)
+    uint16_t* hid;      // [Nb]  heap: node id of the entry
     uint16_t* list;     // [Nb]
     uint16_t* parent;   // [Nb]
     uint16_t* ssize;    // [Nb]
@@ -194,44 +197,53 @@ struct AhcS {  // views into dynamic shared memory
     int* ctl;           // [8]: 0 heap size, 1 next key, 2 n_ext, 3 n_ext2, 4 queue tail
 };
 
+// a < b in the order of the reference's priority queue (smaller MSE first)
+__device__ __forceinline__ bool heap_less(const AhcS& S, float ka, int ia, float kb, int ib) {
+    if (ka != kb) return ka < kb;
+    return S.mse[ia] < S.mse[ib];
+}
 __device__ __forceinline__ void heap_push(AhcS& S, int v) {  // std::push_heap with comp(a, b) = mse[b] < mse[a]
     int hole = S.ctl[0]++;
-    const double mv = S.mse[v];
+    const float kv = (float)S.mse[v];
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const int pv = S.heap[parent];
-        if (!(mv < S.mse[pv])) break;
-        S.heap[hole] = (uint16_t)pv;
+        const float kp = S.hkey[parent];
+        const int ip = S.hid[parent];
+        if (!heap_less(S, kv, v, kp, ip)) break;
+        S.hkey[hole] = kp; S.hid[hole] = (uint16_t)ip;
         hole = parent;
     }
-    S.heap[hole] = (uint16_t)v;
+    S.hkey[hole] = kv; S.hid[hole] = (uint16_t)v;
 }
 __device__ __forceinline__ int heap_pop(AhcS& S) {  // std::pop_heap + pop_back
-    const int top = S.heap[0];
+    const int top = S.hid[0];
     const int len = --S.ctl[0];  // elements remaining
     if (len == 0) return top;
-    const int value = S.heap[len];
+    const float kv = S.hkey[len];
+    const int iv = S.hid[len];
     int hole = 0, child = 0;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        if (S.mse[S.heap[child - 1]] < S.mse[S.heap[child]]) --child;  // comp(first[child], first[child-1])
-        S.heap[hole] = S.heap[child];
+        const float kr = S.hkey[child], kl = S.hkey[child - 1];
+        const int ir = S.hid[child], il = S.hid[child - 1];
+        if (heap_less(S, kl, il, kr, ir)) { S.hkey[hole] = kl; S.hid[hole] = (uint16_t)il; --child; }  // comp(first[child], first[child-1])
+        else { S.hkey[hole] = kr; S.hid[hole] = (uint16_t)ir; }
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        S.heap[hole] = S.heap[child - 1];
+        S.hkey[hole] = S.hkey[child - 1]; S.hid[hole] = S.hid[child - 1];
         hole = child - 1;
     }
-    const double mv = S.mse[value];  // __push_heap(first, hole, 0, value)
-    while (hole > 0) {
+    while (hole > 0) {  // __push_heap(first, hole, 0, value)
         const int parent = (hole - 1) >> 1;
-        const int pv = S.heap[parent];
-        if (!(mv < S.mse[pv])) break;
-        S.heap[hole] = (uint16_t)pv;
+        const float kp = S.hkey[parent];
+        const int ip = S.hid[parent];
+        if (!heap_less(S, kv, iv, kp, ip)) break;
+        S.hkey[hole] = kp; S.hid[hole] = (uint16_t)ip;
         hole = parent;
     }
-    S.heap[hole] = (uint16_t)value;
+    S.hkey[hole] = kv; S.hid[hole] = (uint16_t)iv;
     return top;
 }
 __device__ __forceinline__ int ds_find(const uint16_t* parent, int x) {
@@ -258,65 +270,70 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p < 0) break;
         uint32_t* rowp = adj + (size_t)p * nw;
-        // neighbour list (ascending slot)
+        // row p of the neighbour matrix -> registers (one round trip), then the neighbour list (ascending slot)
+        uint32_t rw[kRowW];
+#pragma unroll
+        for (int k = 0; k < kRowW; ++k) { const int wi = k * 32 + lane; rw[k] = (wi < nw) ? rowp[wi] : 0u; }
+        const NodeG P = nodes[p];
         int cnt = 0;
-        for (int w0 = 0; w0 < nw; w0 += 32) {
-            uint32_t word = (w0 + lane < nw) ? rowp[w0 + lane] : 0u;
+#pragma unroll
+        for (int k = 0; k < kRowW; ++k) {
+            if (k * 32 >= nw) break;
+            uint32_t word = rw[k];
             const int c = __popc(word);
             int pre = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
             const int total = __shfl_sync(0xffffffffu, pre, 31);
             int pos = cnt + pre - c;
-            while (word) { const int b = __ffs(word) - 1; word &= word - 1; S.list[pos++] = (uint16_t)((w0 + lane) * 32 + b); }
+            while (word) { const int b = __ffs(word) - 1; word &= word - 1; S.list[pos++] = (uint16_t)((k * 32 + lane) * 32 + b); }
             cnt += total;
         }
         __syncwarp();
-        const NodeG P = nodes[p];
         // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge; each lane keeps
         // the full result of its own best candidate, so the winner needs no second eigen-solve
         double bm_l = INFINITY, ms[9], mc[3], mn[3];
-        int bi_l = -1, mN = 0, mrid = 0;
+        int bi_l = -1, mN = 0, mrid = 0, nmin_l = 0;
         for (int base = 0; base < cnt; base += 32) {
             const int i = base + lane;
             if (i < cnt) {
-                const NodeG* Q = nodes + S.list[i];
-                const double sim = fabs(P.normal[0] * Q->normal[0] + P.normal[1] * Q->normal[1] + P.normal[2] * Q->normal[2]);
+                const NodeG Q = nodes[S.list[i]];
+                const double sim = fabs(P.normal[0] * Q.normal[0] + P.normal[1] * Q.normal[1] + P.normal[2] * Q.normal[2]);
                 double m = INFINITY;
                 if (!(sim < A.th_merge)) {
                     double s[9], c[3], n[3], curv;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) s[k] = P.s[k] + Q->s[k];
-                    stats_compute(s, P.N + Q->N, c, n, m, curv);
+                    for (int k = 0; k < 9; ++k) s[k] = P.s[k] + Q.s[k];
+                    stats_compute(s, P.N + Q.N, c, n, m, curv);
                     if (!(m == m)) m = INFINITY;  // NaN never wins a `>` comparison in the reference either
                     if (m < bm_l) {
-                        bm_l = m; bi_l = i; mN = P.N + Q->N; mrid = P.N >= Q->N ? P.rid : Q->rid;
+                        bm_l = m; bi_l = i; nmin_l = 1; mN = P.N + Q.N; mrid = P.N >= Q.N ? P.rid : Q.rid;
 #pragma unroll
                         for (int k = 0; k < 9; ++k) ms[k] = s[k];
 #pragma unroll
                         for (int k = 0; k < 3; ++k) { mc[k] = c[k]; mn[k] = n[k]; }
+                    } else if (m == bm_l && m < INFINITY) {
+                        ++nmin_l;
                     }
                 }
-                cand[i] = m;
+                cand[i] = m;  // only read back on an exact tie
             }
         }
         double bm = bm_l;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
-        __syncwarp();
         int best_i = -1;
         if (bm < INFINITY) {
-            int ties = 0, first = 0x7fffffff;
-            for (int base = 0; base < cnt; base += 32) {
-                const int i = base + lane;
-                const unsigned m = __ballot_sync(0xffffffffu, i < cnt && cand[i] == bm);
-                if (m) { ties += __popc(m); first = min(first, base + __ffs(m) - 1); }
-            }
+            const unsigned holders = __ballot_sync(0xffffffffu, bm_l == bm);
+            int ties = (bm_l == bm) ? nmin_l : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
             if (ties == 1) {
-                best_i = first;
+                best_i = __shfl_sync(0xffffffffu, bi_l, __ffs(holders) - 1);
             } else {
                 // exact MSE tie: the reference folds in set order (creation order) and replaces the incumbent only if
                 // incumbent.N < candidate.mse (sic, AHCPlaneFitter.hpp:1045)
+                __syncwarp();
                 if (lane == 0) {
                     int inc = -1;
                     unsigned last_key = 0;
@@ -372,14 +389,19 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
         __syncwarp();
         if (merged) {
             uint32_t* rownb = adj + (size_t)nb * nw;
-            // row[p] = (row[p] | row[nb]) \ {p, nb};  row[nb] = {}
-            for (int wi = lane; wi < nw; wi += 32) {
-                uint32_t v = rowp[wi] | rownb[wi];
+            // row[p] = (row[p] | row[nb]) \ {p, nb};  row[nb] = {};  every neighbour x of the merged node: erase nb, insert p
+            uint32_t rn[kRowW];
+#pragma unroll
+            for (int k = 0; k < kRowW; ++k) { const int wi = k * 32 + lane; rn[k] = (wi < nw) ? rownb[wi] : 0u; }
+#pragma unroll
+            for (int k = 0; k < kRowW; ++k) {
+                const int wi = k * 32 + lane;
+                if (wi >= nw) break;
+                uint32_t v = rw[k] | rn[k];
                 if (wi == (p >> 5)) v &= ~(1u << (p & 31));
                 if (wi == (nb >> 5)) v &= ~(1u << (nb & 31));
                 rowp[wi] = v;
                 rownb[wi] = 0u;
-                // every neighbour x of the merged node: erase nb, insert p
                 while (v) {
                     const int x = wi * 32 + __ffs(v) - 1;
                     v &= v - 1;
@@ -398,7 +420,6 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
             }
             for (int wi = lane; wi < nw; wi += 32) rowp[wi] = 0u;
         }
-        __threadfence_block();
         __syncwarp();
     }
     // extractedPlanes sorted by N descending (std::sort on <= 16 elements is an insertion sort; kept stable beyond that)
@@ -417,11 +438,10 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
 
 // smem layout shared by the two clustering kernels
 __device__ __forceinline__ void ahc_smem_views(unsigned char* p, int Nb, int max_ext, AhcS& S) {
-    S.mse = (double*)p; p += (size_t)Nb * 8;
-    S.pl = (double*)p; p += (size_t)max_ext * 7 * 8;
     S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
     S.ctl = (int*)p; p += 8 * 4;
-    S.heap = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.hkey = (float*)p; p += (size_t)Nb * 4;
+    S.hid = (uint16_t*)p; p += (size_t)Nb * 2;
     S.list = (uint16_t*)p; p += (size_t)Nb * 2;
     S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
     S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
@@ -429,6 +449,7 @@ __device__ __forceinline__ void ahc_smem_views(unsigned char* p, int Nb, int max
     S.ext2 = (uint16_t*)p; p += (size_t)max_ext * 2;
     S.plidmap = (int16_t*)p; p += (size_t)max_ext * 2;
     S.isvalid = (uint8_t*)p;
+    S.pl = nullptr;
 }
 
 // ---- kernel 1 of the graph stage: initial graph + first clustering + block erosion.  One warp per frame. ----
@@ -438,6 +459,7 @@ __global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
     const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh;
     AhcS S;
     ahc_smem_views(smem_raw, Nb, A.max_ext, S);
+    S.mse = A.g_mse + (size_t)f * Nb;
     const BlockOut* blocks = A.blocks + (size_t)f * Nb;
     NodeG* nodes = A.nodes + (size_t)f * Nb;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
@@ -532,9 +554,8 @@ __global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
     }
     __syncwarp();
     // ---- hand the state over ----
-    double* g_mse = A.g_mse + (size_t)f * Nb;
     uint16_t* g_ds = A.g_ds + (size_t)f * 2 * Nb;
-    for (int b = lane; b < Nb; b += 32) { g_mse[b] = S.mse[b]; g_ds[b] = S.parent[b]; g_ds[Nb + b] = S.ssize[b]; }
+    for (int b = lane; b < Nb; b += 32) { g_ds[b] = S.parent[b]; g_ds[Nb + b] = S.ssize[b]; }
     for (int i = lane; i < A.nw; i += 32) A.g_nouse[(size_t)f * A.nw + i] = S.nouse[i];
     for (int i = lane; i < ne; i += 32) {
         const NodeG* n = nodes + S.ext[i];
@@ -625,6 +646,8 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
     // it is the lowest pending lane of its bucket, so an equal pixel with a lower queue position always went before) ----
     const int e = tid >> 2, it = tid & 3;
     unsigned tag = 1;
+    uint32_t q_next = 0;      // queue entry of the next step, fetched one step ahead when it already exists
+    bool have_next = false;
     while (true) {
         const int head = s_head, tail = s_tail;
         if (head >= tail) break;
@@ -633,8 +656,12 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
         int cIdx = -1, plid = 0;
         bool ok = false;
         float cdist = -1.f;
+        int trail0 = 0;
+        float dist0 = 0.f;
+        const uint32_t q = valid ? (have_next ? q_next : queue[head + e]) : 0u;
+        have_next = head + nbat + e < tail;
+        if (have_next) q_next = queue[head + nbat + e];
         if (valid) {
-            const uint32_t q = queue[head + e];
             const int sIdx = (int)(q & 0xfffffu);
             plid = (int)(q >> 20);
             const int sy = sIdx / W, sx = sIdx - sy * W;
@@ -650,6 +677,8 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
                 const int by = cy / 10, bx = cx / 10;
                 if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) valid = false;  // inside an eroded member block
                 else {
+                    trail0 = mem[cIdx];      // speculative: exact for the lanes that go in the first round
+                    dist0 = dist[cIdx];
                     const double z = (double)D[cIdx] * A.cam.factor;
                     if (z != 0) {
                         const double px = ((double)cx - A.cam.cx) * z / A.cam.fx, py = ((double)cy - A.cam.cy) * z / A.cam.fy;
@@ -661,14 +690,14 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
             }
         }
         const unsigned hsh = ((unsigned)cIdx * 2654435761u) >> 21;  // 2048 buckets
-        bool pending = valid, push = false;
+        bool pending = valid, push = false, first = true;
         while (__syncthreads_or(pending)) {
             const unsigned mykey = (tag << 8) | (unsigned)(kFloodThreads - 1 - tid);
             if (pending) atomicMax(&s_bucket[hsh], mykey);
             __syncthreads();
             if (pending && s_bucket[hsh] == mykey) {
                 pending = false;
-                const int trail = mem[cIdx];
+                const int trail = first ? trail0 : mem[cIdx];
                 if (trail > -6 && !(trail >= 0 && trail == plid)) {
                     if (ok) {
                         if (trail >= 0) {
@@ -679,13 +708,15 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
                                 atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
                             }
                         }
-                        if (cdist < dist[cIdx]) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
+                        const float od = first ? dist0 : dist[cIdx];
+                        if (cdist < od) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
                         else if (trail < 0) mem[cIdx] = trail - 1;
                     } else if (trail < 0) {
                         mem[cIdx] = trail - 1;
                     }
                 }
             }
+            first = false;
             ++tag;
         }
         // append the new seeds in (entry, neighbour) order
@@ -721,6 +752,7 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     const int Nb = A.Nw * A.Nh, npix = A.w * A.h;
     AhcS S;
     ahc_smem_views(smem_raw, Nb, A.max_ext, S);
+    S.mse = A.g_mse + (size_t)f * Nb;
     NodeG* nodes = A.nodes + (size_t)f * Nb;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
     uint16_t* key = A.key + (size_t)f * Nb;
@@ -729,7 +761,6 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     const long long t_start = clock64();
     const int ne = A.g_ctl[8 * f + 0];
     for (int b = tid; b < Nb; b += kAhcThreads) {
-        S.mse[b] = A.g_mse[(size_t)f * Nb + b];
         S.parent[b] = A.g_ds[(size_t)f * 2 * Nb + b];
         S.ssize[b] = A.g_ds[(size_t)f * 2 * Nb + Nb + b];
     }
@@ -829,13 +860,13 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
     h->device = device; h->width = width; h->height = height; h->max_batch = max_batch;
     h->Nw = width / 10; h->Nh = height / 10;
     const int Nb = h->Nw * h->Nh;
-    HVO_CHECK_ARG(Nb < 65536, "too many 10x10 blocks for 16-bit node ids");
+    HVO_CHECK_ARG(Nb <= kRowW * 1024, "too many 10x10 blocks (max 9216, i.e. 1280x720)");
     h->nw = (Nb + 31) / 32;
     h->qcap = 2 * width * height;
     h->max_ext = Nb * 100 / kMinSupport + 2;
     h->cam.factor = (double)p->depth_factor; h->cam.fx = (double)p->fx; h->cam.fy = (double)p->fy;
     h->cam.cx = (double)p->cx; h->cam.cy = (double)p->cy;
-    h->ahc_smem = (size_t)Nb * 8 + (size_t)h->max_ext * 56 + (size_t)h->nw * 4 + 32 + (size_t)Nb * 8 + (size_t)h->max_ext * 7 + 16;
+    h->ahc_smem = (size_t)h->nw * 4 + 32 + (size_t)Nb * 12 + (size_t)h->max_ext * 7 + 16;
     int st = HVO_OK;
     do {
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
