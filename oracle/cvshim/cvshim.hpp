@@ -17,6 +17,13 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_16U 2
+#define CV_16UC1 2
+#define CV_32F 5
+#define CV_32FC1 5
+#define CV_64F 6
+#define CV_64FC1 6
+static inline size_t cvshim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_32F ? 4 : 8)); }
 
 static inline int cvRound(double v) { return cvp::cv_round(v); }
 static inline int cvRound(float v) { return cvp::cv_round(v); }
@@ -85,19 +92,17 @@ public:
     Mat(Size s, int type) : rows(0), cols(0), data(nullptr) { create(s.height, s.width, type); }
     Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr) { create(r, c, type); }
     // external (non-owning) buffer
-    Mat(int r, int c, int type, void* ext, size_t st) : rows(r), cols(c), data((uchar*)ext) {
-        (void)type;
+    Mat(int r, int c, int type, void* ext, size_t st) : rows(r), cols(c), data((uchar*)ext), type_(type) {
         step.v = st;
     }
     void create(int r, int c, int type) {
-        assert(type == CV_8UC1);
-        (void)type;
-        if (data && r == rows && c == cols) return;
-        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * c);
+        if (data && r == rows && c == cols && type == type_) return;
+        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * c * cvshim_elem_size(type));
         rows = r;
         cols = c;
+        type_ = type;
         data = buf_->data();
-        step.v = (size_t)c;
+        step.v = (size_t)c * cvshim_elem_size(type);
     }
     void release() { buf_.reset(); rows = cols = 0; data = nullptr; step.v = 0; }
     Mat& operator=(const MatZerosExpr& z) {
@@ -108,7 +113,7 @@ public:
     static MatZerosExpr zeros(int r, int c, int type) { return MatZerosExpr{r, c, type}; }
     Mat operator()(const Rect& r) const {
         Mat m(*this);
-        m.data = data + (size_t)r.y * step.v + r.x;
+        m.data = data + (size_t)r.y * step.v + r.x * cvshim_elem_size(type_);
         m.rows = r.height;
         m.cols = r.width;
         return m;
@@ -116,11 +121,13 @@ public:
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     Mat clone() const {
-        Mat m(rows, cols, CV_8UC1);
-        for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step.v, data + (size_t)y * step.v, (size_t)cols);
+        Mat m(rows, cols, type_);
+        for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step.v, data + (size_t)y * step.v, (size_t)cols * cvshim_elem_size(type_));
         return m;
     }
-    int type() const { return CV_8UC1; }
+    int type() const { return type_; }
+    template <typename T> T* ptr(int y) { return (T*)(data + (size_t)y * step.v); }
+    template <typename T> const T* ptr(int y) const { return (const T*)(data + (size_t)y * step.v); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     size_t step1() const { return step.v; }
     template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step.v + x * sizeof(T)); }
@@ -129,6 +136,7 @@ public:
     const uchar* ptr(int y = 0) const { return data + (size_t)y * step.v; }
 
 private:
+    int type_ = CV_8UC1;
     std::shared_ptr<std::vector<uchar>> buf_;
 };
 

@@ -53,3 +53,70 @@ def test_shim_binary_equals_oracle_bytes(synth):
         k, d = o.extract(f)
         exp += struct.pack('<i', len(k)) + k.tobytes() + d.tobytes()
     assert raw == exp
+
+
+# ---- lines / planes / brute-force matcher bridges -----------------------------------------------------------------
+EXE2 = os.path.join(ROOT, 'tests', 'cpp', 'shim_front')
+
+
+def _build_front():
+    src = os.path.join(ROOT, 'tests', 'cpp', 'shim_front_main.cpp')
+    if not os.path.exists(os.path.join(PKG, 'libhvofront.so')):
+        import __graft_entry__
+        __graft_entry__.build()
+    subprocess.check_call(['g++', '-O2', '-std=c++14', '-I' + os.path.join(ROOT, 'oracle', 'cvshim'), '-I' + os.path.join(ROOT, 'tests', 'cpp', 'standins'),
+                           '-I' + os.path.join(PKG, 'shim'), '-I' + os.path.join(ROOT, 'include'), src, '-o', EXE2, '-L' + PKG, '-lhvofront',
+                           '-Wl,-rpath,' + PKG])
+    return EXE2
+
+
+def test_front_shims_compile_against_reference_call_pattern():
+    assert os.path.exists(_build_front())
+
+
+@pytest.mark.gpu
+def test_front_shims_equal_python_mirror(hvo, synth):
+    exe = EXE2 if os.path.exists(EXE2) else _build_front()
+    gray, depth = synth.frame('S1', 6)
+    c = synth.CONFIGS['S1']
+    cam = np.array([c['fx'], c['fy'], c['cx'], c['cy'], 1.0 / c['factor']], np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('<3i', 0x46524e54, 640, 480) + gray.tobytes() + depth.tobytes() + cam.tobytes())
+        subprocess.check_call([exe, fi, fo])
+        raw = open(fo, 'rb').read()
+    kl, desc, lv = hvo.LINEextractor(1, 1.2, 200, 0.125)(gray)
+    nl = struct.unpack_from('<i', raw, 0)[0]
+    off = 4
+    assert nl == len(kl) and raw[off:off + 68 * nl] == kl.tobytes()
+    off += 68 * nl
+    assert raw[off:off + 32 * nl] == desc.tobytes()
+    off += 32 * nl
+    assert raw[off:off + 24 * nl] == lv.tobytes()
+    off += 24 * nl
+    assert raw[off:off + 32 * nl] == desc.tobytes()          # LBD recomputed on the same keylines (Frame.cc:1094-1096 path)
+    off += 32 * nl
+    pd = hvo.PlaneDetection(640, 480)
+    K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+    pd.readDepthImage(depth, K, cam[4])
+    n = pd.runPlaneDetection(480, 640)
+    npl = struct.unpack_from('<i', raw, off)[0]
+    off += 4
+    assert npl == n and n >= 3
+    for i in range(n):
+        normal = np.frombuffer(raw, np.float64, 3, off); center = np.frombuffer(raw, np.float64, 3, off + 24)
+        N, nv = struct.unpack_from('<2i', raw, off + 48)
+        xyz = np.frombuffer(raw, np.float64, 3, off + 56)
+        off += 80
+        assert np.array_equal(normal, pd.normals[i]) and np.array_equal(center, pd.centers[i]) and N == pd.supports[i]
+        assert nv == len(pd.plane_vertices_[i])
+        j = int(pd.plane_vertices_[i][0])
+        z = float(depth.ravel()[j]) * float(cam[4])
+        assert abs(xyz[2] - z) < 1e-12 and abs(xyz[0] - ((j % 640) - float(cam[2])) * z / float(cam[0])) < 1e-12
+    mem = np.frombuffer(raw, np.int32, 640 * 480, off)
+    off += 4 * 640 * 480
+    assert np.array_equal(mem, pd.membership)
+    m12 = np.frombuffer(raw, np.int32, nl, off)
+    cnt, ref = oracle.match_nnr(desc, desc[::-1].copy(), 0.95)
+    assert np.array_equal(m12, ref)
