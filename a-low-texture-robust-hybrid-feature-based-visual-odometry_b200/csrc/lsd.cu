@@ -237,13 +237,28 @@ __device__ __forceinline__ double lsd_modgrad(int gxgy) {
 }
 
 // LineSegmentDetectorImpl::region_grow.  Warp-collective; returns the region size, reg[] holds x | y << 16.
-__device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t* reg, uint32_t* used, int w, int h, uint32_t seed_xy,
-                               double prec, double& reg_angle_out, int lane) {
+static const int kRing = 256;  // most recent region points, kept in shared memory (the frontier is read from here)
+
+__device__ __forceinline__ void lsd_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// a pixel joined the region: it will be a centre a few steps from now; pull the records of its 3x3 neighbourhood into L1
+__device__ __forceinline__ void lsd_prefetch_nbhd(const LsdPix* __restrict__ pix, int w, int h, int xx, int yy) {
+    const int x0 = max(xx - 1, 0), x1 = min(xx + 1, w - 1);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int y = yy + dy;
+        if (y < 0 || y >= h) continue;
+        lsd_prefetch_l1(pix + y * w + x0);
+        lsd_prefetch_l1(pix + y * w + x1);
+    }
+}
+
+__device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t* reg, volatile uint32_t* ring, uint32_t* used, int w,
+                               int h, uint32_t seed_xy, double prec, double& reg_angle_out, int lane) {
     const int si = (int)(seed_xy >> 16) * w + (int)(seed_xy & 0xffff);
     const LsdPix sp = pix[si];
     double reg_angle = (double)sp.ang * LSD_DEG2RAD;
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-    if (lane == 0) { reg[0] = seed_xy; used[si >> 5] |= 1u << (si & 31); }
+    if (lane == 0) { reg[0] = seed_xy; ring[0] = seed_xy; used[si >> 5] |= 1u << (si & 31); }
     __syncwarp();
     int n = 1, i = 0;
     const int cidx = lane / 9, k = lane - cidx * 9;
@@ -255,7 +270,8 @@ __device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t
         LsdPix p;
         p.ang = LSD_NOTDEF; p.c = 0.f; p.s = 0.f;
         if (cidx < nb && k != 4) {
-            const uint32_t c = reg[i + cidx];
+            const int ci = i + cidx;
+            const uint32_t c = (n - ci <= kRing) ? ring[ci & (kRing - 1)] : reg[ci];
             xx = (int)(c & 0xffff) + ddx; yy = (int)(c >> 16) + ddy;
             if (xx >= 0 && yy >= 0 && xx < w && yy < h) {
                 ni = yy * w + xx;
@@ -272,7 +288,13 @@ __device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t
                 const unsigned m = __ballot_sync(kFull, al) & pending;
                 if (!m) break;
                 const int j = __ffs(m) - 1;
-                if (lane == j) { used[ni >> 5] |= 1u << (ni & 31); reg[n] = (uint32_t)xx | ((uint32_t)yy << 16); }
+                if (lane == j) {
+                    const uint32_t packed = (uint32_t)xx | ((uint32_t)yy << 16);
+                    used[ni >> 5] |= 1u << (ni & 31);
+                    reg[n] = packed;
+                    ring[n & (kRing - 1)] = packed;
+                    lsd_prefetch_nbhd(pix, w, h, xx, yy);
+                }
                 const float cs = __shfl_sync(kFull, p.c, j), sn = __shfl_sync(kFull, p.s, j);
                 sumdx = __fadd_rn(sumdx, cs);
                 sumdy = __fadd_rn(sumdy, sn);
@@ -339,6 +361,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix,
                                                  const int* __restrict__ norder, uint32_t* __restrict__ regbuf, int min_reg_size,
                                                  double prec, double density_th, double inv_scale_div, float* __restrict__ seg,
                                                  int seg_cap, int* __restrict__ nseg, uint32_t* __restrict__ usedbuf) {
+    __shared__ uint32_t ring[kRing];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int npix = w * h;
     // `used` map: one bit per pixel in global memory (L1/L2 resident, touched only around the growing region).  Keeping it
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix,
             const uint32_t sidx = __shfl_sync(kFull, idx, j);
             const uint32_t seed = (sidx % (uint32_t)w) | ((sidx / (uint32_t)w) << 16);
             double reg_angle;
-            int n = lsd_region_grow(P, reg, used, w, h, seed, prec, reg_angle, lane);
+            int n = lsd_region_grow(P, reg, ring, used, w, h, seed, prec, reg_angle, lane);
             if (n < min_reg_size) continue;
             LsdRect rec;
             lsd_region2rect(P, reg, n, w, reg_angle, prec, rec, lane);
@@ -392,7 +415,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix,
                 __syncwarp();
                 const double mean_angle = sum / (double)cnt;
                 const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-                n = lsd_region_grow(P, reg, used, w, h, seed, tau, reg_angle, lane);
+                n = lsd_region_grow(P, reg, ring, used, w, h, seed, tau, reg_angle, lane);
                 if (n < 2) ok = false;
                 if (ok) {
                     lsd_region2rect(P, reg, n, w, reg_angle, prec, rec, lane);

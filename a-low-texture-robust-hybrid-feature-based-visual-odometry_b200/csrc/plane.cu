@@ -421,6 +421,14 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
             for (int wi = lane; wi < nw; wi += 32) rowp[wi] = 0u;
         }
         __syncwarp();
+        // the next node to be popped is known now (heap top): pull its neighbour row and its record towards L1 while
+        // lane 0 runs the next pop's sift loop
+        if (S.ctl[0] > 0) {
+            const int q = S.hid[0];
+            const char* rq = (const char*)(adj + (size_t)q * nw);
+            if (lane * 128 < nw * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(rq + lane * 128));
+            if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)(nodes + q)));
+        }
     }
     // extractedPlanes sorted by N descending (std::sort on <= 16 elements is an insertion sort; kept stable beyond that)
     if (lane == 0) {
