@@ -34,8 +34,7 @@ struct PlaneCam { double factor, fx, fy, cx, cy; };
 // p(x) = det(K - xI) = -x^3 + c2 x^2 - c1 x + c0 from x = 0 (p is convex and decreasing on (-inf, lambda_min], so the
 // iterates approach lambda_min monotonically), then the eigenvector as the largest of the three row cross products
 // of K - lambda I.  Accuracy on plane covariances: |d lambda| <= 2e-12 lambda_max, direction error < 1e-7 rad.
-__host__ __device__ inline void eig33_smallest(const double K[3][3], double& lam, double v[3]) {
-    const double a = K[0][0], b = K[1][1], c = K[2][2], d = K[0][1], e = K[0][2], f = K[1][2];
+__host__ __device__ inline double eig33_lambda_min(double a, double b, double c, double d, double e, double f) {
     const double c2 = a + b + c;
     const double c1 = (a * b - d * d) + (a * c - e * e) + (b * c - f * f);
     const double c0 = a * (b * c - f * f) - d * (d * c - f * e) + e * (d * f - b * e);
@@ -50,7 +49,9 @@ __host__ __device__ inline void eig33_smallest(const double K[3][3], double& lam
         prev = adx;
         if (adx <= 1e-16 * c2) break;
     }
-    lam = x;
+    return x;
+}
+__host__ __device__ inline void eig33_vector(double a, double b, double c, double d, double e, double f, double x, double v[3]) {
     const double r0[3] = {a - x, d, e}, r1[3] = {d, b - x, f}, r2[3] = {e, f, c - x};
     const double u0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
     const double u1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
@@ -69,21 +70,39 @@ __host__ __device__ inline void eig33_smallest(const double K[3][3], double& lam
         v[0] = 0; v[1] = 0; v[2] = 1;
     }
 }
+__host__ __device__ inline void eig33_smallest(const double K[3][3], double& lam, double v[3]) {
+    lam = eig33_lambda_min(K[0][0], K[1][1], K[2][2], K[0][1], K[0][2], K[1][2]);
+    eig33_vector(K[0][0], K[1][1], K[2][2], K[0][1], K[0][2], K[1][2], lam, v);
+}
 
-// Stats::compute (AHCPlaneSeg.hpp:125-163)
-__host__ __device__ inline void stats_compute(const double s[9], int N, double center[3], double normal[3], double& mse, double& curv) {
+// Stats::compute (AHCPlaneSeg.hpp:125-163), split so that the merge loop can rank candidates by MSE (eigenvalue only) and
+// compute the eigenvector for the winner alone.  K6 = {Kxx, Kyy, Kzz, Kxy, Kxz, Kyz}; same operations in the same order as
+// stats_compute, so the two routes are bit-identical.
+__host__ __device__ inline void stats_cov(const double s[9], int N, double K6[6]) {
+    const double sc = 1.0 / N;
+    K6[0] = s[3] - s[0] * s[0] * sc; K6[3] = s[6] - s[0] * s[1] * sc; K6[4] = s[8] - s[0] * s[2] * sc;
+    K6[1] = s[4] - s[1] * s[1] * sc; K6[5] = s[7] - s[1] * s[2] * sc;
+    K6[2] = s[5] - s[2] * s[2] * sc;
+}
+__host__ __device__ inline double stats_mse(const double s[9], int N, double K6[6], double& lam) {
+    const double sc = 1.0 / N;
+    stats_cov(s, N, K6);
+    lam = eig33_lambda_min(K6[0], K6[1], K6[2], K6[3], K6[4], K6[5]);
+    return lam * sc;
+}
+__host__ __device__ inline void stats_finish(const double s[9], int N, const double K6[6], double lam, double center[3], double normal[3]) {
     const double sc = 1.0 / N;
     center[0] = s[0] * sc; center[1] = s[1] * sc; center[2] = s[2] * sc;
-    double K[3][3] = {{s[3] - s[0] * s[0] * sc, s[6] - s[0] * s[1] * sc, s[8] - s[0] * s[2] * sc},
-                      {0, s[4] - s[1] * s[1] * sc, s[7] - s[1] * s[2] * sc},
-                      {0, 0, s[5] - s[2] * s[2] * sc}};
-    K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
-    double lam, v[3];
-    eig33_smallest(K, lam, v);
+    double v[3];
+    eig33_vector(K6[0], K6[1], K6[2], K6[3], K6[4], K6[5], lam, v);
     const double sgn = (v[0] * center[0] + v[1] * center[1] + v[2] * center[2] <= 0) ? 1.0 : -1.0;
     normal[0] = sgn * v[0]; normal[1] = sgn * v[1]; normal[2] = sgn * v[2];
-    mse = lam * sc;
-    curv = lam / (K[0][0] + K[1][1] + K[2][2]);
+}
+__host__ __device__ inline void stats_compute(const double s[9], int N, double center[3], double normal[3], double& mse, double& curv) {
+    double K6[6], lam;
+    mse = stats_mse(s, N, K6, lam);
+    stats_finish(s, N, K6, lam, center, normal);
+    curv = lam / (K6[0] + K6[1] + K6[2]);
 }
 
 __global__ void __launch_bounds__(128) k_plane_blocks(const uint16_t* __restrict__ depth, int w, int h, PlaneCam cam, int Nw, int Nh,
@@ -139,6 +158,9 @@ __global__ void __launch_bounds__(128) k_plane_blocks(const uint16_t* __restrict
 // --------------------------------------------------------------------------------------------------------------------
 struct __align__(16) NodeG { double s[9]; double center[3]; double normal[3]; int N; int rid; };  // 128 bytes
 
+#ifndef HVO_AHC_MINBLOCKS
+#define HVO_AHC_MINBLOCKS 15  /* resident k_plane_cluster warps per SM the register budget is sized for */
+#endif
 static const int kMinSupport = 3000, kAhcThreads = 128;
 static const int kRowW = 9;  // neighbour-matrix row words per lane: up to 9 * 32 * 32 = 9216 blocks (1280x720)
 #define AHC_TH_MERGE 0.50000000000000011   /* cos(pi/180*60) as computed by std::cos */
@@ -151,6 +173,8 @@ struct AhcArgs {
     uint32_t* adj;           // [B][Nb][nw]   (zeroed before launch)
     uint16_t* key;           // [B][Nb]
     double* cand;            // [B][Nb]
+    uint32_t* ulog;          // [B][Nb]  union log of the first clustering
+    uint16_t* cnode;         // [B][Nb]  node of candidate i
     float* dist;             // [B][h*w]
     uint32_t* queue;         // [B][qcap]
     int32_t* membership;     // [B][h*w]   working membershipImg, final labels on exit
@@ -183,67 +207,88 @@ __device__ __forceinline__ double ahc_t_ang_init(double z) {  // ParamSet::T_ang
 
 struct AhcS {  // working set of the clustering kernels (shared memory unless noted)
     double* mse;        // [Nb]  global: exact MSE of every node
-    float* hkey;        // [Nb]  heap: float(mse) of the entry (monotone in mse; exact double compare only when two keys are equal)
-    uint16_t* hid;      // [Nb]  heap: node id of the entry
-    uint16_t* list;     // [Nb]
-    uint16_t* parent;   // [Nb]
+    uint32_t* heap;     // [hcap] heap entries (see heap_entry)
+    uint32_t idmask;    // low bits of a heap entry that hold the node id
+    int idbits;
+    uint16_t* stage;    // [32]  the neighbours evaluated in the current round (one per lane)
+    uint16_t* parent;   // [Nb]  disjoint set (k_plane_cluster: overlays the heap once it has drained)
     uint16_t* ssize;    // [Nb]
     uint32_t* nouse;    // [ceil(Nb/32)]
-    double* pl;         // [max_ext][7] normal, center, mse of the extracted planes (refinement)
     uint16_t* ext;      // [max_ext]
     uint16_t* ext2;     // [max_ext]
     int16_t* plidmap;   // [max_ext]
     uint8_t* isvalid;   // [max_ext]
-    int* ctl;           // [8]: 0 heap size, 1 next key, 2 n_ext, 3 n_ext2, 4 queue tail
+    int* ctl;           // [8]: 0 heap size, 1 next key, 2 n_ext, 3 n_ext2, 5 union-log length
+    uint32_t* ulog;     // global [Nb]: k_plane_cluster logs DisjointSet::Union(x, y) as x | y << 16 and replays the log afterwards
+    uint16_t* cnode;    // global [Nb]: node of candidate i (read back only on an exact MSE tie)
 };
 
-// a < b in the order of the reference's priority queue (smaller MSE first)
-__device__ __forceinline__ bool heap_less(const AhcS& S, float ka, int ia, float kb, int ib) {
-    if (ka != kb) return ka < kb;
-    return S.mse[ia] < S.mse[ib];
+// Heap entries are one 32-bit word: a monotone quantisation of the MSE (5 exponent bits covering [2^-24, 2^8), the
+// remaining bits mantissa; everything below maps to the smallest key, everything above to the largest) with the node id
+// in the low `idbits` bits.  Two entries whose keys differ compare as plain unsigned integers; equal keys fall back to the
+// exact double MSEs in global memory, so the order is exactly the reference's whatever the quantiser does.  Both children
+// of a slot sit in one aligned 8-byte word (the array starts at an address = 4 mod 8).
+__device__ __forceinline__ uint32_t heap_entry(const AhcS& S, int v, double mv) {
+    const long long b = __double_as_longlong(mv);
+    const int e = (int)(b >> 52) - (1023 - 24);  // negative values have a negative exponent field here
+    const int mbits = 27 - S.idbits;
+    uint32_t key;
+    if (e < 0) key = 0u;
+    else if (e >= 32) key = (1u << (mbits + 5)) - 1u;
+    else key = ((uint32_t)e << mbits) | (uint32_t)((b & 0xfffffffffffffLL) >> (52 - mbits));
+    return (key << S.idbits) | (uint32_t)v;
 }
-__device__ __forceinline__ void heap_push(AhcS& S, int v) {  // std::push_heap with comp(a, b) = mse[b] < mse[a]
+#ifdef HVO_AHC_PROF
+__device__ int g_less_calls, g_less_ties, g_pops;
+#endif
+__device__ __forceinline__ bool heap_less(const AhcS& S, uint32_t ea, uint32_t eb) {
+#ifdef HVO_AHC_PROF
+    ++g_less_calls;
+#endif
+    if ((ea ^ eb) & ~S.idmask) return ea < eb;
+#ifdef HVO_AHC_PROF
+    ++g_less_ties;
+#endif
+    return S.mse[ea & S.idmask] < S.mse[eb & S.idmask];
+}
+__device__ __forceinline__ void heap_push(AhcS& S, int v, double mv) {  // std::push_heap with comp(a, b) = mse[b] < mse[a]; mv == S.mse[v]
     int hole = S.ctl[0]++;
-    const float kv = (float)S.mse[v];
+    const uint32_t ev = heap_entry(S, v, mv);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const float kp = S.hkey[parent];
-        const int ip = S.hid[parent];
-        if (!heap_less(S, kv, v, kp, ip)) break;
-        S.hkey[hole] = kp; S.hid[hole] = (uint16_t)ip;
+        const uint32_t ep = S.heap[parent];
+        if (!heap_less(S, ev, ep)) break;
+        S.heap[hole] = ep;
         hole = parent;
     }
-    S.hkey[hole] = kv; S.hid[hole] = (uint16_t)v;
+    S.heap[hole] = ev;
 }
 __device__ __forceinline__ int heap_pop(AhcS& S) {  // std::pop_heap + pop_back
-    const int top = S.hid[0];
+    const int top = (int)(S.heap[0] & S.idmask);
     const int len = --S.ctl[0];  // elements remaining
     if (len == 0) return top;
-    const float kv = S.hkey[len];
-    const int iv = S.hid[len];
+    const uint32_t ev = S.heap[len];
     int hole = 0, child = 0;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        const float kr = S.hkey[child], kl = S.hkey[child - 1];
-        const int ir = S.hid[child], il = S.hid[child - 1];
-        if (heap_less(S, kl, il, kr, ir)) { S.hkey[hole] = kl; S.hid[hole] = (uint16_t)il; --child; }  // comp(first[child], first[child-1])
-        else { S.hkey[hole] = kr; S.hid[hole] = (uint16_t)ir; }
+        const uint2 lr = *reinterpret_cast<const uint2*>(S.heap + child - 1);  // left = child - 1, right = child
+        if (heap_less(S, lr.x, lr.y)) { S.heap[hole] = lr.x; --child; }  // comp(first[child], first[child-1])
+        else S.heap[hole] = lr.y;
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        S.hkey[hole] = S.hkey[child - 1]; S.hid[hole] = S.hid[child - 1];
+        S.heap[hole] = S.heap[child - 1];
         hole = child - 1;
     }
     while (hole > 0) {  // __push_heap(first, hole, 0, value)
         const int parent = (hole - 1) >> 1;
-        const float kp = S.hkey[parent];
-        const int ip = S.hid[parent];
-        if (!heap_less(S, kv, iv, kp, ip)) break;
-        S.hkey[hole] = kp; S.hid[hole] = (uint16_t)ip;
+        const uint32_t ep = S.heap[parent];
+        if (!heap_less(S, ev, ep)) break;
+        S.heap[hole] = ep;
         hole = parent;
     }
-    S.hkey[hole] = kv; S.hid[hole] = (uint16_t)iv;
+    S.heap[hole] = ev;
     return top;
 }
 __device__ __forceinline__ int ds_find(const uint16_t* parent, int x) {
@@ -259,69 +304,95 @@ __device__ __forceinline__ void ds_union(AhcS& S, int x, int y) {  // DisjointSe
 __device__ __forceinline__ bool nouse_get(const AhcS& S, int i) { return (S.nouse[i >> 5] >> (i & 31)) & 1u; }
 
 // PlaneFitter::ahCluster (AHCPlaneFitter.hpp:983-1189).  Warp-collective (warp 0); extracted planes appended to out[].
+// kLogUnions: the disjoint set is not resident (its shared memory is the heap's); unions are logged and replayed later.
+#ifdef HVO_AHC_PROF
+#define AHC_T(k) { const long long t_ = clock64(); prof[k] += t_ - tl; tl = t_; }
+#else
+#define AHC_T(k)
+#endif
+template <bool kLogUnions, int RW>
 __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* adj, uint16_t* key, double* cand, uint16_t* out,
                             int* n_out, int lane) {
     const int nw = A.nw;
+#ifdef HVO_AHC_PROF
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
+#endif
     while (true) {
         int p = -1;
         if (lane == 0) {
             while (S.ctl[0] > 0) { const int q = heap_pop(S); if (!nouse_get(S, q)) { p = q; break; } }
         }
         p = __shfl_sync(0xffffffffu, p, 0);
+        AHC_T(0)
         if (p < 0) break;
         uint32_t* rowp = adj + (size_t)p * nw;
-        // row p of the neighbour matrix -> registers (one round trip), then the neighbour list (ascending slot)
-        uint32_t rw[kRowW];
+        // row p of the neighbour matrix -> registers (one round trip); neighbour i (ascending slot order) = i-th set bit
+        uint32_t rw[RW], rem[RW];
+        int pos[RW];
 #pragma unroll
-        for (int k = 0; k < kRowW; ++k) { const int wi = k * 32 + lane; rw[k] = (wi < nw) ? rowp[wi] : 0u; }
+        for (int k = 0; k < RW; ++k) { const int wi = k * 32 + lane; rw[k] = (wi < nw) ? rowp[wi] : 0u; }
         const NodeG P = nodes[p];
         int cnt = 0;
 #pragma unroll
-        for (int k = 0; k < kRowW; ++k) {
-            if (k * 32 >= nw) break;
-            uint32_t word = rw[k];
-            const int c = __popc(word);
+        for (int k = 0; k < RW; ++k) {
+            rem[k] = rw[k]; pos[k] = 0;
+            if (k * 32 >= nw) continue;
+            const int c = __popc(rw[k]);
             int pre = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
             const int total = __shfl_sync(0xffffffffu, pre, 31);
-            int pos = cnt + pre - c;
-            while (word) { const int b = __ffs(word) - 1; word &= word - 1; S.list[pos++] = (uint16_t)((k * 32 + lane) * 32 + b); }
+            pos[k] = cnt + pre - c;
             cnt += total;
         }
-        __syncwarp();
-        // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge; each lane keeps
-        // the full result of its own best candidate, so the winner needs no second eigen-solve
-        double bm_l = INFINITY, ms[9], mc[3], mn[3];
-        int bi_l = -1, mN = 0, mrid = 0, nmin_l = 0;
+        AHC_T(1)
+        // candidate merges: MSE of p + nb for every neighbour with |n_p . n_nb| >= similarityTh_merge, 32 neighbours per
+        // round.  Only the eigenvalue is needed to rank them; each lane keeps the sums of its own best candidate and the
+        // winning lane finishes the node (eigenvector) alone.
+        double bm_l = INFINITY, blam = 0, ms[9];
+        int bi_l = -1, mN = 0, mrid = 0, qrid = 0, bnode = -1, nmin_l = 0;
         for (int base = 0; base < cnt; base += 32) {
+#pragma unroll
+            for (int k = 0; k < RW; ++k) {
+                if (k * 32 >= nw) continue;
+                while (rem[k] && pos[k] < base + 32) {
+                    const int b = __ffs(rem[k]) - 1;
+                    rem[k] &= rem[k] - 1;
+                    S.stage[pos[k] - base] = (uint16_t)((k * 32 + lane) * 32 + b);
+                    ++pos[k];
+                }
+            }
+            __syncwarp();
             const int i = base + lane;
             if (i < cnt) {
-                const NodeG Q = nodes[S.list[i]];
+                const int q = S.stage[lane];
+                const NodeG Q = nodes[q];
                 const double sim = fabs(P.normal[0] * Q.normal[0] + P.normal[1] * Q.normal[1] + P.normal[2] * Q.normal[2]);
                 double m = INFINITY;
                 if (!(sim < A.th_merge)) {
-                    double s[9], c[3], n[3], curv;
+                    double s[9], K6[6], lam;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) s[k] = P.s[k] + Q.s[k];
-                    stats_compute(s, P.N + Q.N, c, n, m, curv);
+                    m = stats_mse(s, P.N + Q.N, K6, lam);
                     if (!(m == m)) m = INFINITY;  // NaN never wins a `>` comparison in the reference either
                     if (m < bm_l) {
-                        bm_l = m; bi_l = i; nmin_l = 1; mN = P.N + Q.N; mrid = P.N >= Q.N ? P.rid : Q.rid;
+                        bm_l = m; blam = lam; bi_l = i; nmin_l = 1; mN = P.N + Q.N; mrid = P.N >= Q.N ? P.rid : Q.rid;
+                        qrid = Q.rid; bnode = q;
 #pragma unroll
                         for (int k = 0; k < 9; ++k) ms[k] = s[k];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { mc[k] = c[k]; mn[k] = n[k]; }
                     } else if (m == bm_l && m < INFINITY) {
                         ++nmin_l;
                     }
                 }
                 cand[i] = m;  // only read back on an exact tie
+                S.cnode[i] = (uint16_t)q;
             }
+            __syncwarp();
         }
         double bm = bm_l;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        AHC_T(2)
         int best_i = -1;
         if (bm < INFINITY) {
             const unsigned holders = __ballot_sync(0xffffffffu, bm_l == bm);
@@ -342,11 +413,11 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
                         unsigned pk = 0xffffffffu;
                         for (int i = 0; i < cnt; ++i) {
                             if (cand[i] != bm) continue;
-                            const unsigned k = key[S.list[i]];
+                            const unsigned k = key[S.cnode[i]];
                             if ((t == 0 || k > last_key) && k < pk) { pk = k; pick = i; }
                         }
                         last_key = pk;
-                        if (inc < 0 || (double)(P.N + nodes[S.list[inc]].N) < bm) inc = pick;
+                        if (inc < 0 || (double)(P.N + nodes[S.cnode[inc]].N) < bm) inc = pick;
                     }
                     best_i = inc;
                 }
@@ -356,45 +427,53 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
         const int owner = best_i & 31;  // the lane that evaluated candidate best_i
         int nb = -1;
         bool merged = false;
+        double K6[6];
         if (best_i >= 0) {
-            nb = S.list[best_i];
             if (lane == owner) {
                 if (bi_l != best_i) {  // only after an exact tie inside this lane's own candidates
-                    const NodeG Q = nodes[nb];
-                    double curv;
+                    bnode = S.cnode[best_i];
+                    const NodeG Q = nodes[bnode];
 #pragma unroll
                     for (int k = 0; k < 9; ++k) ms[k] = P.s[k] + Q.s[k];
                     mN = P.N + Q.N;
                     mrid = P.N >= Q.N ? P.rid : Q.rid;
-                    stats_compute(ms, mN, mc, mn, bm_l, curv);
+                    qrid = Q.rid;
+                    bm_l = stats_mse(ms, mN, K6, blam);
+                } else {
+                    stats_cov(ms, mN, K6);  // same bits as the ranking pass
                 }
-                const double t = 1.6e-6 * mc[2] * mc[2] + 8;  // ParamSet::T_mse(P_MERGING)
+                const double cz = ms[2] * (1.0 / mN);
+                const double t = 1.6e-6 * cz * cz + 8;  // ParamSet::T_mse(P_MERGING)
                 merged = bm_l < t * t;
-                if (merged) {
-                    ds_union(S, P.rid, nodes[nb].rid);
-                    NodeG M;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) M.s[k] = ms[k];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { M.center[k] = mc[k]; M.normal[k] = mn[k]; }
-                    M.N = mN; M.rid = mrid;
-                    nodes[p] = M;
-                    S.mse[p] = bm_l;
-                    key[p] = (uint16_t)S.ctl[1]++;
-                    S.nouse[nb >> 5] |= 1u << (nb & 31);
-                }
             }
             merged = __shfl_sync(0xffffffffu, (int)merged, owner) != 0;
+            nb = __shfl_sync(0xffffffffu, bnode, owner);
         }
-        __syncwarp();
+        AHC_T(3)
         if (merged) {
             uint32_t* rownb = adj + (size_t)nb * nw;
-            // row[p] = (row[p] | row[nb]) \ {p, nb};  row[nb] = {};  every neighbour x of the merged node: erase nb, insert p
-            uint32_t rn[kRowW];
+            // row[p] = (row[p] | row[nb]) \ {p, nb};  row[nb] = {};  every neighbour x of the merged node: erase nb, insert p.
+            // The row of nb is requested first; the owner finishes the merged node while it is in flight.
+            uint32_t rn[RW];
 #pragma unroll
-            for (int k = 0; k < kRowW; ++k) { const int wi = k * 32 + lane; rn[k] = (wi < nw) ? rownb[wi] : 0u; }
+            for (int k = 0; k < RW; ++k) { const int wi = k * 32 + lane; rn[k] = (wi < nw) ? rownb[wi] : 0u; }
+            double mv = 0;
+            if (lane == owner) {
+                NodeG M;
 #pragma unroll
-            for (int k = 0; k < kRowW; ++k) {
+                for (int k = 0; k < 9; ++k) M.s[k] = ms[k];
+                stats_finish(ms, mN, K6, blam, M.center, M.normal);
+                M.N = mN; M.rid = mrid;
+                nodes[p] = M;
+                S.mse[p] = bm_l;
+                mv = bm_l;
+                key[p] = (uint16_t)S.ctl[1]++;
+                S.nouse[nb >> 5] |= 1u << (nb & 31);
+                if (kLogUnions) S.ulog[S.ctl[5]++] = (uint32_t)P.rid | ((uint32_t)qrid << 16);
+                else ds_union(S, P.rid, qrid);
+            }
+#pragma unroll
+            for (int k = 0; k < RW; ++k) {
                 const int wi = k * 32 + lane;
                 if (wi >= nw) break;
                 uint32_t v = rw[k] | rn[k];
@@ -410,26 +489,41 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
                     atomicOr(&rx[p >> 5], 1u << (p & 31));
                 }
             }
+            mv = __shfl_sync(0xffffffffu, mv, owner);
             __syncwarp();
-            if (lane == 0) heap_push(S, p);
+            AHC_T(4)
+            if (lane == 0) heap_push(S, p, mv);
+            __syncwarp();
+            AHC_T(5)
         } else {
             if (lane == 0 && P.N >= kMinSupport) out[(*n_out)++] = (uint16_t)p;
-            for (int i = lane; i < cnt; i += 32) {  // disconnectAllNbs
-                uint32_t* rx = adj + (size_t)S.list[i] * nw;
-                atomicAnd(&rx[p >> 5], ~(1u << (p & 31)));
+#pragma unroll
+            for (int k = 0; k < RW; ++k) {  // disconnectAllNbs
+                const int wi = k * 32 + lane;
+                if (wi >= nw) break;
+                uint32_t v = rw[k];
+                while (v) {
+                    const int x = wi * 32 + __ffs(v) - 1;
+                    v &= v - 1;
+                    atomicAnd(&adj[(size_t)x * nw + (p >> 5)], ~(1u << (p & 31)));
+                }
+                rowp[wi] = 0u;
             }
-            for (int wi = lane; wi < nw; wi += 32) rowp[wi] = 0u;
         }
         __syncwarp();
         // the next node to be popped is known now (heap top): pull its neighbour row and its record towards L1 while
         // lane 0 runs the next pop's sift loop
         if (S.ctl[0] > 0) {
-            const int q = S.hid[0];
+            const int q = (int)(S.heap[0] & S.idmask);
             const char* rq = (const char*)(adj + (size_t)q * nw);
             if (lane * 128 < nw * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(rq + lane * 128));
             if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)(nodes + q)));
         }
+        AHC_T(6)
     }
+#ifdef HVO_AHC_PROF
+    if (lane == 0 && kLogUnions) { for (int k = 0; k < 7; ++k) printf("ahc prof[%d] = %lld\n", k, prof[k]); printf("less calls %d ties %d\n", g_less_calls, g_less_ties); }
+#endif
     // extractedPlanes sorted by N descending (std::sort on <= 16 elements is an insertion sort; kept stable beyond that)
     if (lane == 0) {
         const int n = *n_out;
@@ -444,58 +538,95 @@ __device__ void ahc_cluster(const AhcArgs& A, AhcS& S, NodeG* nodes, uint32_t* a
     __syncwarp();
 }
 
-// smem layout shared by the two clustering kernels
-__device__ __forceinline__ void ahc_smem_views(unsigned char* p, int Nb, int max_ext, AhcS& S) {
+// shared memory of k_plane_cluster: the heap spans every block; the disjoint set reuses the heap's bytes once it has drained
+__host__ __device__ inline size_t ahc_cluster_smem_bytes(int Nb, int max_ext) {
+    return (size_t)((Nb + 31) / 32) * 4 + 32 + 8 + (size_t)Nb * 4 + 64 + (size_t)max_ext * 7 + 16;
+}
+__device__ __forceinline__ void ahc_cluster_smem_views(unsigned char* p, int Nb, int max_ext, AhcS& S) {
     S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
     S.ctl = (int*)p; p += 8 * 4;
-    S.hkey = (float*)p; p += (size_t)Nb * 4;
-    S.hid = (uint16_t*)p; p += (size_t)Nb * 2;
-    S.list = (uint16_t*)p; p += (size_t)Nb * 2;
-    S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
-    S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
+    p += (((size_t)p & 7) == 4) ? 0 : 4;  // heap base = 4 mod 8
+    S.heap = (uint32_t*)p; S.parent = (uint16_t*)p; S.ssize = S.parent + Nb; p += (size_t)Nb * 4;
+    p += 4;
+    S.stage = (uint16_t*)p; p += 64;
     S.ext = (uint16_t*)p; p += (size_t)max_ext * 2;
     S.ext2 = (uint16_t*)p; p += (size_t)max_ext * 2;
     S.plidmap = (int16_t*)p; p += (size_t)max_ext * 2;
     S.isvalid = (uint8_t*)p;
-    S.pl = nullptr;
+    S.idbits = 32 - __clz(Nb - 1);
+    S.idmask = (1u << S.idbits) - 1u;
+}
+// shared memory of k_plane_merge: a heap of at most max_ext planes, the disjoint set resident
+__host__ __device__ inline size_t ahc_merge_smem_bytes(int Nb, int max_ext) {
+    return (size_t)((Nb + 31) / 32) * 4 + 32 + 8 + (size_t)max_ext * 4 + 8 + (size_t)Nb * 4 + 64 + (size_t)max_ext * 7 + 16;
+}
+__device__ __forceinline__ void ahc_merge_smem_views(unsigned char* p, int Nb, int max_ext, AhcS& S) {
+    S.nouse = (uint32_t*)p; p += (size_t)((Nb + 31) / 32) * 4;
+    S.ctl = (int*)p; p += 8 * 4;
+    p += (((size_t)p & 7) == 4) ? 0 : 4;  // heap base = 4 mod 8
+    S.heap = (uint32_t*)p; p += (size_t)max_ext * 4;
+    p += (((size_t)p & 3) ? 4 - ((size_t)p & 3) : 0);
+    S.parent = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.ssize = (uint16_t*)p; p += (size_t)Nb * 2;
+    S.stage = (uint16_t*)p; p += 64;
+    S.ext = (uint16_t*)p; p += (size_t)max_ext * 2;
+    S.ext2 = (uint16_t*)p; p += (size_t)max_ext * 2;
+    S.plidmap = (int16_t*)p; p += (size_t)max_ext * 2;
+    S.isvalid = (uint8_t*)p;
+    S.idbits = 32 - __clz(Nb - 1);
+    S.idmask = (1u << S.idbits) - 1u;
 }
 
 // ---- kernel 1 of the graph stage: initial graph + first clustering + block erosion.  One warp per frame. ----
-__global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
+template <int RW>
+__global__ void __launch_bounds__(32, HVO_AHC_MINBLOCKS) k_plane_cluster(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh;
     AhcS S;
-    ahc_smem_views(smem_raw, Nb, A.max_ext, S);
+    ahc_cluster_smem_views(smem_raw, Nb, A.max_ext, S);
     S.mse = A.g_mse + (size_t)f * Nb;
+    S.ulog = A.ulog + (size_t)f * Nb;
+    S.cnode = A.cnode + (size_t)f * Nb;
     const BlockOut* blocks = A.blocks + (size_t)f * Nb;
     NodeG* nodes = A.nodes + (size_t)f * Nb;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
     uint16_t* key = A.key + (size_t)f * Nb;
     double* cand = A.cand + (size_t)f * Nb;
     const long long t_start = clock64();
-    // ---- initial graph nodes (AHCPlaneFitter.hpp:786-826) ----
-    for (int b = lane; b < Nb; b += 32) {
-        const BlockOut o = blocks[b];
-        S.parent[b] = (uint16_t)b; S.ssize[b] = 1; key[b] = (uint16_t)b;
-        double m = INFINITY;
-        if (o.queued) {
-            NodeG n;
-            double curv;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) n.s[k] = o.s[k];
-            n.N = o.N; n.rid = b;
-            stats_compute(n.s, n.N, n.center, n.normal, m, curv);
-            nodes[b] = n;
-        }
-        S.mse[b] = m;
-    }
     for (int i = lane; i < (Nb + 31) / 32; i += 32) S.nouse[i] = 0u;
     for (int i = lane; i < A.max_ext; i += 32) S.isvalid[i] = 0;
-    if (lane == 0) { S.ctl[0] = 0; S.ctl[1] = Nb; S.ctl[2] = 0; S.ctl[3] = 0; A.status[f] = 0; }
+    if (lane == 0) { S.ctl[0] = 0; S.ctl[1] = Nb; S.ctl[2] = 0; S.ctl[3] = 0; S.ctl[5] = 0; A.status[f] = 0; }
     __syncwarp();
-    if (lane == 0)
-        for (int b = 0; b < Nb; ++b) if (blocks[b].queued) heap_push(S, b);
+    // ---- initial graph nodes (AHCPlaneFitter.hpp:786-826), pushed in block order ----
+    for (int b0 = 0; b0 < Nb; b0 += 32) {
+        const int b = b0 + lane;
+        double m = INFINITY;
+        bool queued = false;
+        if (b < Nb) {
+            const BlockOut o = blocks[b];
+            key[b] = (uint16_t)b;
+            queued = o.queued != 0;
+            if (queued) {
+                NodeG n;
+                double curv;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) n.s[k] = o.s[k];
+                n.N = o.N; n.rid = b;
+                stats_compute(n.s, n.N, n.center, n.normal, m, curv);
+                nodes[b] = n;
+            }
+            S.mse[b] = m;
+        }
+        unsigned qm = __ballot_sync(0xffffffffu, queued);
+        while (qm) {
+            const int j = __ffs(qm) - 1;
+            qm &= qm - 1;
+            const double mj = __shfl_sync(0xffffffffu, m, j);
+            if (lane == 0) heap_push(S, b0 + j, mj);
+        }
+        __syncwarp();
+    }
     // ---- edges (AHCPlaneFitter.hpp:896-954): rows, then columns ----
     for (int i = lane; i < Nh; i += 32)
         for (int j = 1; j < Nw; j += 2) {
@@ -539,21 +670,40 @@ __global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
             }
         }
     __syncwarp();
-    ahc_cluster(A, S, nodes, adj, key, cand, S.ext, &S.ctl[2], lane);
+    ahc_cluster<true, RW>(A, S, nodes, adj, key, cand, S.ext, &S.ctl[2], lane);
     const int ne = S.ctl[2];
-    // ---- refineDetails: findBlockMembership (AHCPlaneFitter.hpp:485-587), block part ----
-    int16_t* g_blkmap = A.g_blkmap + (size_t)f * Nb;
-    for (int b = lane; b < Nb; b += 32) S.list[b] = (uint16_t)ds_find(S.parent, b);  // set id of every block
+    // ---- the heap has drained: its bytes now hold the disjoint set; replay the logged unions in order ----
+    for (int b = lane; b < Nb; b += 32) { S.parent[b] = (uint16_t)b; S.ssize[b] = 1; }
     __syncwarp();
+    if (lane == 0) {
+        const int nu = S.ctl[5];
+        uint32_t u = nu > 0 ? S.ulog[0] : 0u;
+        for (int i = 0; i < nu; ++i) {
+            const uint32_t un = (i + 1 < nu) ? S.ulog[i + 1] : 0u;
+            ds_union(S, (int)(u & 0xffffu), (int)(u >> 16));
+            u = un;
+        }
+    }
+    __syncwarp();
+    // ---- hand the disjoint set over, then flatten it in place: parent[b] becomes the set id of block b (concurrent
+    // pointer jumping is safe: a chain read meets either the old parent or the root, both lead to the same root) ----
+    uint16_t* g_ds = A.g_ds + (size_t)f * 2 * Nb;
+    for (int b = lane; b < Nb; b += 32) { g_ds[b] = S.parent[b]; g_ds[Nb + b] = S.ssize[b]; }
+    __syncwarp();
+    for (int b = lane; b < Nb; b += 32) { const int r = ds_find(S.parent, b); if (r != b) S.parent[b] = (uint16_t)r; }
+    __syncwarp();
+    // ---- refineDetails: findBlockMembership (AHCPlaneFitter.hpp:485-587), block part ----
+    const uint16_t* setids = S.parent;
+    int16_t* g_blkmap = A.g_blkmap + (size_t)f * Nb;
     for (int b = lane; b < Nb; b += 32) {
-        const int i = b / Nw, j = b - i * Nw, setid = S.list[b];
+        const int i = b / Nw, j = b - i * Nw, setid = setids[b];
         int bm = -1;
         if ((int)S.ssize[setid] * 100 >= kMinSupport) {
             bool same = true;
-            if (j > 0 && S.list[b - 1] != setid) same = false;
-            if (j < Nw - 1 && S.list[b + 1] != setid) same = false;
-            if (i > 0 && S.list[b - Nw] != setid) same = false;
-            if (i < Nh - 1 && S.list[b + Nw] != setid) same = false;  // ERODE_ALL_BORDER
+            if (j > 0 && setids[b - 1] != setid) same = false;
+            if (j < Nw - 1 && setids[b + 1] != setid) same = false;
+            if (i > 0 && setids[b - Nw] != setid) same = false;
+            if (i < Nh - 1 && setids[b + Nw] != setid) same = false;  // ERODE_ALL_BORDER
             int plid = 0;  // std::map::operator[] yields 0 for an unknown set id (reference quirk)
             for (int e = 0; e < ne; ++e) if (nodes[S.ext[e]].rid == setid) { plid = e; break; }
             if (same && plid < ne) { bm = plid; S.isvalid[plid] = 1; }
@@ -561,9 +711,7 @@ __global__ void __launch_bounds__(32) k_plane_cluster(AhcArgs A) {
         g_blkmap[b] = (int16_t)bm;
     }
     __syncwarp();
-    // ---- hand the state over ----
-    uint16_t* g_ds = A.g_ds + (size_t)f * 2 * Nb;
-    for (int b = lane; b < Nb; b += 32) { g_ds[b] = S.parent[b]; g_ds[Nb + b] = S.ssize[b]; }
+    // ---- hand the rest of the state over ----
     for (int i = lane; i < A.nw; i += 32) A.g_nouse[(size_t)f * A.nw + i] = S.nouse[i];
     for (int i = lane; i < ne; i += 32) {
         const NodeG* n = nodes + S.ext[i];
@@ -754,13 +902,16 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
 }
 
 // ---- kernel 3: last merge among the refined planes (AHCPlaneFitter.hpp:317-371) + final labels ----
+template <int RW>
 __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Nb = A.Nw * A.Nh, npix = A.w * A.h;
     AhcS S;
-    ahc_smem_views(smem_raw, Nb, A.max_ext, S);
+    ahc_merge_smem_views(smem_raw, Nb, A.max_ext, S);
     S.mse = A.g_mse + (size_t)f * Nb;
+    S.ulog = nullptr;
+    S.cnode = A.cnode + (size_t)f * Nb;
     NodeG* nodes = A.nodes + (size_t)f * Nb;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
     uint16_t* key = A.key + (size_t)f * Nb;
@@ -782,9 +933,9 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     __syncthreads();
     if (wid == 0) {
         if (lane == 0)
-            for (int i = 0; i < ne; ++i) if (S.isvalid[i]) heap_push(S, S.ext[i]);
+            for (int i = 0; i < ne; ++i) if (S.isvalid[i]) heap_push(S, S.ext[i], S.mse[S.ext[i]]);
         __syncwarp();
-        ahc_cluster(A, S, nodes, adj, key, cand, S.ext2, &S.ctl[3], lane);
+        ahc_cluster<false, RW>(A, S, nodes, adj, key, cand, S.ext2, &S.ctl[3], lane);
         const int ne2 = S.ctl[3];
         for (int i = lane; i < ne; i += 32) {
             int m = -1;
@@ -817,7 +968,7 @@ using namespace hvo;
 
 struct hvo_plane {
     int device = 0, width = 0, height = 0, max_batch = 0, Nw = 0, Nh = 0, nw = 0, qcap = 0, max_ext = 0;
-    size_t ahc_smem = 0;
+    size_t ahc_smem = 0, merge_smem = 0;
     PlaneCam cam;
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[2] = {nullptr, nullptr};
@@ -828,6 +979,8 @@ struct hvo_plane {
     uint32_t* d_adj = nullptr;
     uint16_t* d_key = nullptr;
     double* d_cand = nullptr;
+    uint32_t* d_ulog = nullptr;
+    uint16_t* d_cnode = nullptr;
     float* d_dist = nullptr;
     uint32_t* d_queue = nullptr;
     int32_t* d_mem = nullptr;
@@ -874,14 +1027,17 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
     h->max_ext = Nb * 100 / kMinSupport + 2;
     h->cam.factor = (double)p->depth_factor; h->cam.fx = (double)p->fx; h->cam.fy = (double)p->fy;
     h->cam.cx = (double)p->cx; h->cam.cy = (double)p->cy;
-    h->ahc_smem = (size_t)h->nw * 4 + 32 + (size_t)Nb * 12 + (size_t)h->max_ext * 7 + 16;
+    h->ahc_smem = ahc_cluster_smem_bytes(Nb, h->max_ext);
+    h->merge_smem = ahc_merge_smem_bytes(Nb, h->max_ext);
     int st = HVO_OK;
     do {
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
         HVO_TRY(cudaSetDevice(device));
         if (h->ahc_smem > 220 * 1024) { set_error("image too large: the plane graph does not fit shared memory"); st = HVO_ERR_ARG; break; }
-        HVO_TRY(cudaFuncSetAttribute(k_plane_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
-        HVO_TRY(cudaFuncSetAttribute(k_plane_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_cluster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_cluster<kRowW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_merge<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->merge_smem));
+        HVO_TRY(cudaFuncSetAttribute(k_plane_merge<kRowW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->merge_smem));
         h->flood_smem = (size_t)h->max_ext * 56 + (size_t)Nb * 2 + (size_t)h->max_ext * 2 + 16;
         HVO_TRY(cudaFuncSetAttribute(k_plane_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->flood_smem));
         HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -895,6 +1051,8 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
         HVO_TRY(cudaMalloc(&h->d_adj, B * Nb * h->nw * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_key, B * Nb * sizeof(uint16_t)));
         HVO_TRY(cudaMalloc(&h->d_cand, B * Nb * sizeof(double)));
+        HVO_TRY(cudaMalloc(&h->d_ulog, B * Nb * sizeof(uint32_t)));
+        HVO_TRY(cudaMalloc(&h->d_cnode, B * Nb * sizeof(uint16_t)));
         HVO_TRY(cudaMalloc(&h->d_dist, B * px * sizeof(float)));
         HVO_TRY(cudaMalloc(&h->d_queue, B * (size_t)h->qcap * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_mem, B * px * sizeof(int32_t)));
@@ -922,7 +1080,7 @@ void hvo_plane_destroy(hvo_plane* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_dist, h->d_queue, h->d_mem, h->d_planes,
+    void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_ulog, h->d_cnode, h->d_dist, h->d_queue, h->d_mem, h->d_planes,
                     h->d_nplanes, h->d_status, h->d_cycles, h->d_gmse, h->d_gds, h->d_gnouse, h->d_gblkmap, h->d_gext, h->d_gisvalid,
                     h->d_gpl, h->d_gctl};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -948,7 +1106,7 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     const int Nb = h->Nw * h->Nh;
     HVO_CUDA(cudaMemsetAsync(h->d_adj, 0, (size_t)nframes * Nb * h->nw * sizeof(uint32_t), h->stream));
     AhcArgs A;
-    A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand;
+    A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand; A.ulog = h->d_ulog; A.cnode = h->d_cnode;
     A.dist = h->d_dist; A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
     A.status = h->d_status; A.cycles = h->d_cycles;
     A.w = h->width; A.h = h->height; A.Nw = h->Nw; A.Nh = h->Nh; A.nw = h->nw; A.qcap = h->qcap; A.max_ext = h->max_ext;
@@ -957,9 +1115,12 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     A.th_refine = std::cos(M_PI / 180.0 * 30.0);  // ParamSet::similarityTh_refine
     A.g_mse = h->d_gmse; A.g_ds = h->d_gds; A.g_nouse = h->d_gnouse; A.g_blkmap = h->d_gblkmap; A.g_ext = h->d_gext;
     A.g_isvalid = h->d_gisvalid; A.g_pl = h->d_gpl; A.g_ctl = h->d_gctl;
-    k_plane_cluster<<<nframes, 32, h->ahc_smem, h->stream>>>(A);
+    const bool small = h->nw <= 3 * 32;  // row words per lane: 3 up to 3072 blocks (640x480), kRowW beyond
+    if (small) k_plane_cluster<3><<<nframes, 32, h->ahc_smem, h->stream>>>(A);
+    else k_plane_cluster<kRowW><<<nframes, 32, h->ahc_smem, h->stream>>>(A);
     k_plane_flood<<<nframes, kFloodThreads, h->flood_smem, h->stream>>>(A);
-    k_plane_merge<<<nframes, kAhcThreads, h->ahc_smem, h->stream>>>(A);
+    if (small) k_plane_merge<3><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
+    else k_plane_merge<kRowW><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
     HVO_CUDA(cudaGetLastError());
     h->last_launches = 5;
     return HVO_OK;

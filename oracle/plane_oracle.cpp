@@ -20,6 +20,8 @@
 #include <limits>
 #include <map>
 #include <queue>
+#include <cstdio>
+#include <cstdlib>
 #include <set>
 #include <vector>
 
@@ -285,6 +287,7 @@ struct Fitter {
             }
     }
 
+    long st_pops = 0, st_merges = 0, st_nbs = 0, st_batches = 0;  // diagnostics (HVO_ORACLE_STATS=1)
     int ahCluster(MinQ& minQ) {
         int step = 0;
         while (!minQ.empty() && step <= maxStep) {
@@ -293,6 +296,7 @@ struct Fitter {
             if (nodes[p].nouse) continue;
             int cand = -1, cand_nb = -1;
             const std::vector<int> nbs(nodes[p].nbs.begin(), nodes[p].nbs.end());
+            ++st_pops; st_nbs += (long)nbs.size(); st_batches += ((long)nbs.size() + 31) / 32;
             for (int nb : nbs) {
                 if (similarity(nodes[p], nodes[nb]) < params.similarityTh_merge) continue;
                 Seg m;
@@ -310,7 +314,7 @@ struct Fitter {
                 }
             }
             if (cand >= 0 && nodes[cand].mse < params.T_mse_merge(nodes[cand].center[2])) {
-                minQ.push(cand);
+                minQ.push(cand); ++st_merges;
                 ds->Union(nodes[p].rid, nodes[cand_nb].rid);
                 std::set<int>& n = nodes[cand].nbs;
                 n.insert(nodes[p].nbs.begin(), nodes[p].nbs.end());
@@ -462,6 +466,8 @@ struct Fitter {
         std::vector<bool> isValid;
         findBlockMembership(isValid);
         floodFill();
+        if (std::getenv("HVO_ORACLE_STATS"))
+            std::fprintf(stderr, "[plane_oracle] pops %ld merges %ld nbs %ld batches %ld flood_queue %zu\n", st_pops, st_merges, st_nbs, st_batches, rfQueue.size());
         std::vector<int> old;
         extracted.swap(old);
         MinQ minQ2(cmp);
