@@ -89,6 +89,9 @@ ABI = {
     'hvo_line_extract_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     'hvo_line_extract_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     'hvo_line_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
+    'hvo_line_set_culling': (C.c_int, [_vp, C.c_int]),
+    'hvo_line_cull': (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_int, _vp, C.POINTER(C.c_int)]),
+    'hvo_line_cull_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     'hvo_line_get_scaled': (C.c_int, [_vp, C.c_int, _vp]),
     'hvo_line_get_seed_order': (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
     'hvo_line_set_profiling': (C.c_int, [_vp, C.c_int]),
@@ -464,6 +467,25 @@ class LINEextractor:
                                       self.max_lines, C.byref(n)))
         return kl[:n.value].copy(), desc[:n.value].copy(), lv[:n.value].copy()
 
+    def set_culling(self, enable):
+        """True: every extraction also runs Frame::cullingLine (src/Frame.cc:939, 952-1116) as Frame::ExtractLSD does."""
+        if self._h is None:
+            raise HvoError(HVO_ERR_ARG, 'create the extractor with width/height first')
+        _check(lib().hvo_line_set_culling(self._h, int(bool(enable))))
+
+    def cullingLine(self, image, keylines, lineVec2d):
+        """Frame::cullingLine(imGray, 5, 2.5, 15, 30): (keylines, descriptors, lineVec2d) after merging."""
+        image = np.ascontiguousarray(image, np.uint8)
+        if self._h is None or (self.h, self.w) != image.shape:
+            self._create(image.shape[1], image.shape[0])
+        n = len(keylines)
+        kl = np.zeros(self.max_lines, KL_DTYPE); kl[:n] = keylines
+        lv = np.zeros((self.max_lines, 3), np.float64); lv[:n] = lineVec2d
+        desc = np.empty((self.max_lines, 32), np.uint8)
+        m = C.c_int(0)
+        _check(lib().hvo_line_cull(self._h, _vp(image.ctypes.data), image.strides[0], _np_ptr(kl), _np_ptr(lv), n, _np_ptr(desc), C.byref(m)))
+        return kl[:m.value].copy(), desc[:m.value].copy(), lv[:m.value].copy()
+
     def extract_batch(self, frames, out=None):
         """frames [n,h,w] uint8 -> dict(counts [n], keylines [n,max_lines], desc [n,max_lines,32], linevec [n,max_lines,3])"""
         frames = np.ascontiguousarray(frames, np.uint8)
@@ -780,7 +802,7 @@ STAGE_ORB, STAGE_LINES, STAGE_PLANES, STAGE_NORMALS, STAGE_ALL = 1, 2, 4, 8, 15
 
 class _FrameParams(C.Structure):
     _fields_ = [('orb', _OrbParams), ('line', _LineParams), ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
-                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int)]
+                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int), ('line_cull', C.c_int)]
 
 
 class _FrameOutputs(C.Structure):
@@ -794,9 +816,9 @@ class FrameFrontEnd:
     FIELDS = [f[0] for f in _FrameOutputs._fields_]
 
     def __init__(self, width, height, fx, fy, cx, cy, depth_factor, bf=40.0, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
-                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0):
+                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False):
         prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
-                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes)
+                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes, int(bool(line_cull)))
         out = _vp()
         _check(lib().hvo_frame_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
         self._h = out

@@ -122,6 +122,7 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
     int st = HVO_OK;
     if (st == HVO_OK && (p->stages & ST_ORB)) st = hvo_orb_create(&p->orb, width, height, max_batch, device, &h->orb);
     if (st == HVO_OK && (p->stages & ST_LINE)) st = hvo_line_create(&p->line, width, height, max_batch, device, &h->line);
+    if (st == HVO_OK && h->line) st = hvo_line_set_culling(h->line, p->line_cull);
     if (st == HVO_OK && (p->stages & ST_PLANE)) {
         hvo_plane_params pp{p->fx, p->fy, p->cx, p->cy, p->depth_factor};
         st = hvo_plane_create(&pp, width, height, max_batch, device, &h->plane);

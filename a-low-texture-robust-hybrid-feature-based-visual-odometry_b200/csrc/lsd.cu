@@ -545,6 +545,230 @@ __global__ void __launch_bounds__(256) k_line_keylines(const float* __restrict__
     }
 }
 
+
+// --------------------------------------------------------------------------------------------------------------------
+// Frame::cullingLine (reference src/Frame.cc:952-1116): merge near-collinear KeyLines, rebuild the KeyLines, sort by
+// response.  One warp per frame.  Pair tests of one leader i run 32 candidates j at a time (a candidate's outcome depends
+// only on tags set by earlier leaders); the per-line terms of PointLineDistance (:1117-1126) and TwoLineAngle
+// (:1127-1140) are computed once per line with the reference's own operation order.  Each group is then folded with
+// MergeTwoLines (:1141-1203) by one lane.  The LBD pass on the new KeyLines (:1094-1096) follows on the same stream.
+struct CullLine {  // per input line: 72 bytes
+    double A, B, C, den;   // (y2 - y1), (x1 - x2), (x2 y1 - x1 y2), sqrt((y2 - y1)^2 + (x1 - x2)^2)
+    double a0, a1, nrm;    // line function after the two divisions by its third component; its norm
+    float m12x, m12y, m21x, m21y;  // (start + end) / 2 and (end + start) / 2 + start (sic, :975)
+};
+
+__device__ __forceinline__ void cull_merge_two(const float l1[4], const float l2[4], float out[4]) {  // MergeTwoLines
+    const float ax = l1[0], ay = l1[1], bx = l1[2], by = l1[3];
+    const float cx = l2[0], cy = l2[1], dx = l2[2], dy = l2[3];
+    const float dlix = __fsub_rn(bx, ax), dliy = __fsub_rn(by, ay), dljx = __fsub_rn(dx, cx), dljy = __fsub_rn(dy, cy);
+    const double li = sqrt((double)__fmul_rn(dlix, dlix) + (double)__fmul_rn(dliy, dliy));
+    const double lj = sqrt((double)__fmul_rn(dljx, dljx) + (double)__fmul_rn(dljy, dljy));
+    const double xg = (li * (double)__fadd_rn(ax, bx) + lj * (double)__fadd_rn(cx, dx)) / (2.0 * (li + lj));
+    const double yg = (li * (double)__fadd_rn(ay, by) + lj * (double)__fadd_rn(cy, dy)) / (2.0 * (li + lj));
+    const double kPi = 3.1415926535897932384626433832795;
+    double thi, thj, thr;
+    if (dlix == 0.0f) thi = kPi / 2.0;
+    else thi = atan((double)__fdiv_rn(dliy, dlix));
+    if (dljx == 0.0f) thj = kPi / 2.0;
+    else thj = atan((double)__fdiv_rn(dljy, dljx));
+    if (fabs(thi - thj) <= kPi / 2.0) {
+        thr = (li * thi + lj * thj) / (li + lj);
+    } else {
+        const double tmp = thj - kPi * (thj / fabs(thj));
+        thr = li * thi + lj * tmp;
+        thr /= (li + lj);
+    }
+    const double s = sin(thr), c = cos(thr);
+    const double axg = ((double)ay - yg) * s + ((double)ax - xg) * c;
+    const double bxg = ((double)by - yg) * s + ((double)bx - xg) * c;
+    const double cxg = ((double)cy - yg) * s + ((double)cx - xg) * c;
+    const double dxg = ((double)dy - yg) * s + ((double)dx - xg) * c;
+    const double d1 = fmin(axg, fmin(bxg, fmin(cxg, dxg)));
+    const double d2 = fmax(axg, fmax(bxg, fmax(cxg, dxg)));
+    out[0] = (float)(d1 * c + xg);
+    out[1] = (float)(d1 * s + yg);
+    out[2] = (float)(d2 * c + xg);
+    out[3] = (float)(d2 * s + yg);
+}
+
+// cv::clipLine on 64-bit points (OpenCV imgproc drawing.cpp, un-vendored; the oracle's restatement is pinned to cv2)
+__device__ bool cull_clip_line(long long width, long long height, long long& x1, long long& y1, long long& x2, long long& y2) {
+    const long long right = width - 1, bottom = height - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+__device__ int cull_line_count(int W, int H, const float e[4]) {  // cv::LineIterator(img, Point(p1), Point(p2)).count, 8-connected
+    long long x1 = __float2int_rn(e[0]), y1 = __float2int_rn(e[1]), x2 = __float2int_rn(e[2]), y2 = __float2int_rn(e[3]);
+    if ((unsigned long long)x1 >= (unsigned long long)W || (unsigned long long)x2 >= (unsigned long long)W ||
+        (unsigned long long)y1 >= (unsigned long long)H || (unsigned long long)y2 >= (unsigned long long)H) {
+        if (!cull_clip_line(W, H, x1, y1, x2, y2)) return 0;
+    }
+    const long long dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
+    return (int)(dx > dy ? dx : dy) + 1;
+}
+
+__global__ void __launch_bounds__(32) k_line_cull(KeyLineOut* __restrict__ kls, double* __restrict__ linevec, int32_t* __restrict__ counts,
+                                                 int max_lines, int W, int H, double dis, double cos_th, double endpoint_dis,
+                                                 CullLine* __restrict__ scratch, float* __restrict__ newline) {
+    extern __shared__ int16_t cull_sm[];  // grp[max_lines] (leader of a merged line, -1 none), then tag bytes
+    int16_t* grp = cull_sm;
+    uint8_t* tag = (uint8_t*)(cull_sm + max_lines);
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int n = min(counts[f], max_lines);
+    KeyLineOut* K = kls + (long long)f * max_lines;
+    double* LV = linevec + (long long)f * max_lines * 3;
+    CullLine* S = scratch + (long long)f * max_lines;
+    float* NL = newline + (long long)f * max_lines * 5;  // x1 y1 x2 y2 response
+    for (int i = lane; i < n; i += 32) {
+        const KeyLineOut k = K[i];
+        CullLine c;
+        const double x1 = k.startPointX, y1 = k.startPointY, x2 = k.endPointX, y2 = k.endPointY;
+        c.A = y2 - y1; c.B = x1 - x2; c.C = (x2 * y1) - (x1 * y2);
+        c.den = sqrt((y2 - y1) * (y2 - y1) + (x1 - x2) * (x1 - x2));
+        double v0 = LV[3 * i], v1 = LV[3 * i + 1];
+        const double v2 = LV[3 * i + 2];
+        v0 /= v2; v1 /= v2;
+        c.a0 = v0 / v2; c.a1 = v1 / v2;
+        c.nrm = sqrt(c.a0 * c.a0 + c.a1 * c.a1);
+        c.m12x = __fmul_rn(__fadd_rn(k.startPointX, k.endPointX), 0.5f);
+        c.m12y = __fmul_rn(__fadd_rn(k.startPointY, k.endPointY), 0.5f);
+        c.m21x = __fadd_rn(__fmul_rn(__fadd_rn(k.endPointX, k.startPointX), 0.5f), k.startPointX);
+        c.m21y = __fadd_rn(__fmul_rn(__fadd_rn(k.endPointY, k.startPointY), 0.5f), k.startPointY);
+        S[i] = c;
+        grp[i] = -1; tag[i] = 0;
+    }
+    __syncwarp();
+    // ---- step 1: pair tests ----
+    for (int i = 0; i < n; ++i) {
+        if (tag[i]) continue;  // warp-uniform (shared memory)
+        const CullLine ci = S[i];
+        const KeyLineOut ki = K[i];
+        bool any = false;
+        for (int base = i + 1; base < n; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            if (j < n && !tag[j]) {
+                const CullLine cj = S[j];
+                const double dis12 = fabs(cj.A * (double)ci.m12x + cj.B * (double)ci.m12y + cj.C) / cj.den;
+                const double dis21 = fabs(ci.A * (double)cj.m21x + ci.B * (double)cj.m21y + ci.C) / ci.den;
+                if (dis12 < dis || dis21 < dis) {
+                    const double a = ci.a0 * cj.a0 + ci.a1 * cj.a1;
+                    const double ang = fabs(a / (ci.nrm * cj.nrm));
+                    if (fabs(ang) > cos_th) {
+                        const KeyLineOut kj = K[j];
+                        const double x11 = ki.startPointX, x12 = ki.endPointX, y11 = ki.startPointY, y12 = ki.endPointY;
+                        const double x21 = kj.startPointX, x22 = kj.endPointX, y21 = kj.startPointY, y22 = kj.endPointY;
+                        // sorted extents: [min, second, third, max] of the four x (y) coordinates
+                        const double xlo1 = fmin(x11, x12), xhi1 = fmax(x11, x12), xlo2 = fmin(x21, x22), xhi2 = fmax(x21, x22);
+                        const double ylo1 = fmin(y11, y12), yhi1 = fmax(y11, y12), ylo2 = fmin(y21, y22), yhi2 = fmax(y21, y22);
+                        const double bx0 = fmin(xlo1, xlo2), bx3 = fmax(xhi1, xhi2), bx1 = fmin(fmax(xlo1, xlo2), fmin(xhi1, xhi2)),
+                                     bx2 = fmax(fmax(xlo1, xlo2), fmin(xhi1, xhi2));
+                        const double by0 = fmin(ylo1, ylo2), by3 = fmax(yhi1, yhi2), by1 = fmin(fmax(ylo1, ylo2), fmin(yhi1, yhi2)),
+                                     by2 = fmax(fmax(ylo1, ylo2), fmin(yhi1, yhi2));
+                        hit = true;
+                        if (bx3 - bx0 > fabs(x11 - x12) + fabs(x21 - x22) && bx2 - bx1 > endpoint_dis) hit = false;
+                        if (hit && by3 - by0 > fabs(y11 - y12) + fabs(y21 - y22) && by2 - by1 > endpoint_dis) hit = false;
+                    }
+                }
+            }
+            if (hit) { grp[j] = (int16_t)i; tag[j] = 1; }
+            any |= __any_sync(kFull, hit);
+        }
+        if (any && lane == 0) { tag[i] = 1; grp[i] = (int16_t)i; }
+        __syncwarp();
+    }
+    // ---- step 2: fold every group (one lane per leader), keep the untouched lines; output order = index order ----
+    int nout = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool keep = false;
+        float cur[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < n) {
+            const KeyLineOut k = K[i];
+            cur[0] = k.startPointX; cur[1] = k.startPointY; cur[2] = k.endPointX; cur[3] = k.endPointY;
+            if (grp[i] == i) {
+                keep = true;
+                for (int j = i + 1; j < n; ++j) {
+                    if (grp[j] != i) continue;
+                    const KeyLineOut kj = K[j];
+                    const float y1[4] = {kj.startPointX, kj.startPointY, kj.endPointX, kj.endPointY};
+                    float m[4];
+                    cull_merge_two(cur, y1, m);
+                    cur[0] = m[0]; cur[1] = m[1]; cur[2] = m[2]; cur[3] = m[3];
+                }
+            } else if (!tag[i]) {
+                keep = true;
+            }
+        }
+        const unsigned km = __ballot_sync(kFull, keep);
+        if (keep) {
+            const int o = nout + __popc(km & ((1u << lane) - 1u));
+            const double a = (double)__fsub_rn(cur[0], cur[2]), b = (double)__fsub_rn(cur[1], cur[3]);
+            const float len = (float)sqrt(a * a + b * b);
+            NL[5 * o] = cur[0]; NL[5 * o + 1] = cur[1]; NL[5 * o + 2] = cur[2]; NL[5 * o + 3] = cur[3];
+            NL[5 * o + 4] = __fdiv_rn(len, (float)max(W, H));
+        }
+        nout += __popc(km);
+    }
+    __syncwarp();
+    // ---- step 3: KeyLines of the new segments at their response rank (descending, ties keep creation order) ----
+    for (int i = lane; i < nout; i += 32) {
+        const float e[4] = {NL[5 * i], NL[5 * i + 1], NL[5 * i + 2], NL[5 * i + 3]};
+        const float r = NL[5 * i + 4];
+        int rank = 0;
+        for (int j = 0; j < nout; ++j) { const float q = NL[5 * j + 4]; rank += (q > r || (q == r && j < i)) ? 1 : 0; }
+        KeyLineOut kl;
+        kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];
+        kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
+        kl.lineLength = lsd_length(e);
+        kl.octave = 0;
+        kl.angle = (float)atan2((double)__fsub_rn(e[3], e[1]), (double)__fsub_rn(e[2], e[0]));  // reference: atan2f
+        kl.size = __fmul_rn(__fsub_rn(e[2], e[0]), __fsub_rn(e[3], e[1]));
+        kl.pt_x = __fdiv_rn(__fadd_rn(e[2], e[0]), 2.f);
+        kl.pt_y = __fdiv_rn(__fadd_rn(e[3], e[1]), 2.f);
+        kl.numOfPixels = cull_line_count(W, H, e);
+        kl.response = r;
+        kl.class_id = rank;
+        K[rank] = kl;
+        const double sx = e[0], sy = e[1], ex = e[2], ey = e[3];
+        const double l0 = sy - ey, l1 = ex - sx, l2 = sx * ey - sy * ex;
+        const double nn = sqrt(l0 * l0 + l1 * l1);
+        LV[3 * rank] = l0 / nn; LV[3 * rank + 1] = l1 / nn; LV[3 * rank + 2] = l2 / nn;
+    }
+    if (lane == 0) counts[f] = nout;
+}
+
 }  // namespace hvo
 
 using namespace hvo;
@@ -577,6 +801,9 @@ struct hvo_line {
     double* d_linevec = nullptr;
     int32_t* d_counts = nullptr;
     uint8_t* d_desc = nullptr;
+    bool cull = false;               // run Frame::cullingLine after the extractor (hvo_line_set_culling)
+    CullLine* d_cull = nullptr;      // [B][nfeat]
+    float* d_newline = nullptr;      // [B][nfeat][5]
     int last_launches = 0;
 };
 
@@ -629,6 +856,16 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
     return HVO_OK;
 }
 
+// Frame::cullingLine(im, 5, 2.5, 15, 30) (src/Frame.cc:939) on device-resident KeyLines, in place, then LBD on the result
+static int line_cull_device(hvo_line* h, const uint8_t* d_gray, int nframes, KeyLineOut* d_kl, uint8_t* d_desc, double* d_linevec,
+                            int32_t* d_counts) {
+    const size_t sm = (size_t)h->nfeat * 3 + 16;
+    k_line_cull<<<nframes, 32, sm, h->stream>>>(d_kl, d_linevec, d_counts, h->nfeat, h->width, h->height, 5.0, std::cos(2.5 * 0.0174533),
+                                                15.0, h->d_cull, h->d_newline);
+    HVO_CUDA(cudaGetLastError());
+    return lbd_compute_on_stream(h->lbd, h->stream, d_gray, nframes, reinterpret_cast<const hvo_keyline*>(d_kl), d_counts, d_desc);
+}
+
 static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, KeyLineOut* d_kl, uint8_t* d_desc, double* d_linevec,
                                int32_t* d_counts) {
     int st = line_detect_device(h, d_gray, nframes);
@@ -636,9 +873,16 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
     k_line_keylines<<<nframes, 256, 0, h->stream>>>(h->d_seg, h->seg_cap, h->d_nseg, h->width, h->height, h->nfeat, h->nfeat, h->d_resp,
                                                     d_kl, d_linevec, d_counts);
     HVO_CUDA(cudaGetLastError());
-    st = lbd_compute_on_stream(h->lbd, h->stream, d_gray, nframes, reinterpret_cast<const hvo_keyline*>(d_kl), d_counts, d_desc);
+    if (h->cull) {
+        // the reference computes LBD twice (LineExtractor.cpp:361-363, Frame.cc:1094-1096) and discards the first result;
+        // only the descriptors of the culled KeyLines survive, so only those are computed
+        st = line_cull_device(h, d_gray, nframes, d_kl, d_desc, d_linevec, d_counts);
+        h->last_launches = 7;
+    } else {
+        st = lbd_compute_on_stream(h->lbd, h->stream, d_gray, nframes, reinterpret_cast<const hvo_keyline*>(d_kl), d_counts, d_desc);
+        h->last_launches = 6;
+    }
     if (h->profiling) cudaEventRecord(h->sev[4], h->stream);
-    h->last_launches = 6;
     return st;
 }
 
@@ -718,6 +962,8 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
         HVO_TRY(cudaMalloc(&h->d_linevec, B * ml * 3 * sizeof(double)));
         HVO_TRY(cudaMalloc(&h->d_counts, B * sizeof(int32_t)));
         HVO_TRY(cudaMalloc(&h->d_desc, B * ml * 32));
+        HVO_TRY(cudaMalloc(&h->d_cull, B * ml * sizeof(CullLine)));
+        HVO_TRY(cudaMalloc(&h->d_newline, B * ml * 5 * sizeof(float)));
         HVO_TRY(cudaMemcpy(h->d_cx, cx.data(), cx.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
         HVO_TRY(cudaMemcpy(h->d_cy, cy.data(), cy.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
         HVO_TRY(cudaMemcpy(h->d_cstab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -736,12 +982,55 @@ void hvo_line_destroy(hvo_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->lbd) hvo_lbd_destroy(h->lbd);
     void* bufs[] = {h->d_gray, h->d_cx, h->d_cy, h->d_cstab, h->d_pix, h->d_scaled, h->d_maxsq, h->d_order, h->d_reg, h->d_used, h->d_norder,
-                    h->d_nseg, h->d_seg, h->d_resp, h->d_kl, h->d_linevec, h->d_counts, h->d_desc};
+                    h->d_nseg, h->d_seg, h->d_resp, h->d_kl, h->d_linevec, h->d_counts, h->d_desc, h->d_cull, h->d_newline};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     for (auto& e : h->sev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int hvo_line_set_culling(hvo_line* h, int enable) {
+    HVO_CHECK_ARG(h, "null handle");
+    h->cull = enable != 0;
+    return HVO_OK;
+}
+
+int hvo_line_cull_batch_device(hvo_line* h, const uint8_t* d_gray, int nframes, hvo_keyline* d_keylines, uint8_t* d_desc, double* d_linevec3,
+                               int32_t* d_counts) {
+    HVO_CHECK_ARG(h && d_gray && d_keylines && d_desc && d_linevec3 && d_counts, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch, "nframes out of range for this handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    return line_cull_device(h, d_gray, nframes, reinterpret_cast<KeyLineOut*>(d_keylines), d_desc, d_linevec3, d_counts);
+}
+
+int hvo_line_cull(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keyline* keylines, double* linevec3, int n, uint8_t* desc,
+                  int* n_out) {
+    HVO_CHECK_ARG(h && n_out, "null argument");
+    *n_out = 0;
+    if (!gray || n <= 0) return HVO_OK;
+    HVO_CHECK_ARG(keylines && linevec3 && desc, "null argument");
+    HVO_CHECK_ARG(stride >= (size_t)h->width, "stride smaller than width");
+    HVO_CHECK_ARG(n <= h->nfeat, "more KeyLines than hvo_line_max_lines()");
+    HVO_CUDA(cudaSetDevice(h->device));
+    const int32_t cnt_in = n;
+    HVO_CUDA(cudaMemcpy2DAsync(h->d_gray, h->width, gray, stride, h->width, h->height, cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(h->d_kl, keylines, (size_t)n * sizeof(KeyLineOut), cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(h->d_linevec, linevec3, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(h->d_counts, &cnt_in, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int st = line_cull_device(h, h->d_gray, 1, h->d_kl, h->d_desc, h->d_linevec, h->d_counts);
+    if (st != HVO_OK) return st;
+    int32_t cnt = 0;
+    HVO_CUDA(cudaMemcpyAsync(&cnt, h->d_counts, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    if (cnt > 0) {
+        HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, (size_t)cnt * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaMemcpyAsync(linevec3, h->d_linevec, (size_t)cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        HVO_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    *n_out = cnt;
+    return HVO_OK;
 }
 
 int hvo_line_max_lines(const hvo_line* h) { return h ? h->nfeat : 0; }

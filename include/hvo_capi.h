@@ -189,6 +189,17 @@ typedef struct hvo_line_params {
 typedef struct hvo_line hvo_line;
 int hvo_line_create(const hvo_line_params* p, int width, int height, int max_batch, int device, hvo_line** out);
 void hvo_line_destroy(hvo_line* h);
+/* Frame::cullingLine(imGray, 5, 2.5, 15, 30) (src/Frame.cc:939, :952-1116), which Frame::ExtractLSD runs on the extractor's
+ * output: merge near-collinear KeyLines (MergeTwoLines :1141-1203), rebuild the KeyLines, sort by response, LBD again
+ * (:1094-1096), line functions again (:1097-1108).  enable != 0: every hvo_line_extract* call returns the culled set (the state
+ * of mvKeylinesUn / mLdesc / mvKeyLineFunctions after ExtractLSD's cullingLine). */
+int hvo_line_set_culling(hvo_line* h, int enable);
+/* cullingLine alone, in place: keylines / linevec3 hold n rows on entry and *n_out rows on return; desc receives *n_out x 32. */
+int hvo_line_cull(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keyline* keylines, double* linevec3, int n, uint8_t* desc,
+                  int* n_out);
+/* device-resident, batched: d_keylines [n][max_lines], d_linevec3 [n][max_lines][3], d_counts [n] are read and overwritten */
+int hvo_line_cull_batch_device(hvo_line* h, const uint8_t* d_gray, int nframes, hvo_keyline* d_keylines, uint8_t* d_desc,
+                               double* d_linevec3, int32_t* d_counts);
 int hvo_line_max_lines(const hvo_line* h);        /* rows per frame of keylines / desc / linevec3 = n_features */
 int hvo_line_segment_capacity(const hvo_line* h); /* upper bound of raw LSD segments per frame */
 int hvo_line_scaled_size(const hvo_line* h, int* sw, int* sh);
@@ -297,6 +308,7 @@ typedef struct hvo_frame_params {
     float bf;             /* Camera.bf */
     int stages;           /* HVO_STAGE_* bits */
     int max_planes;       /* rows of planes7 per frame */
+    int line_cull;        /* != 0: Frame::cullingLine after the line extractor, as Frame::ExtractLSD does (src/Frame.cc:939) */
 } hvo_frame_params;
 
 /* Output arrays of a batch of n frames.  Host pointers for hvo_frame_extract_batch, device pointers for

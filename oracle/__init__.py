@@ -283,6 +283,46 @@ def line_extract(gray, n_features=200):
     return kl, desc, lv
 
 
+def line_functions(kl):
+    """mvKeyLineFunctions: sp x ep normalised by the norm of its first two components (LineExtractor.cpp:365-377)."""
+    sx, sy = kl['startPointX'].astype(np.float64), kl['startPointY'].astype(np.float64)
+    ex, ey = kl['endPointX'].astype(np.float64), kl['endPointY'].astype(np.float64)
+    l0, l1, l2 = sy - ey, ex - sx, sx * ey - sy * ex
+    nn = np.sqrt(l0 * l0 + l1 * l1)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return np.stack([l0 / nn, l1 / nn, l2 / nn], axis=1)
+
+
+def clip_line(w, h, pt1, pt2):
+    """cv::clipLine restatement: (inside, pt1, pt2)."""
+    a = np.array([pt1[0], pt1[1], pt2[0], pt2[1]], np.int64)
+    r = lib().orc_clip_line(int(w), int(h), _p(a))
+    return bool(r), (int(a[0]), int(a[1])), (int(a[2]), int(a[3]))
+
+
+def cull_lines(keylines, linevec, w, h, dis=5.0, angle=2.5, endpoint_dis=15.0, want_groups=False):
+    """Frame::cullingLine steps 1-3 (src/Frame.cc:952-1092): merged, rebuilt, response-sorted KeyLines."""
+    kl = np.ascontiguousarray(keylines, KL_DTYPE)
+    lv = np.ascontiguousarray(linevec, np.float64).reshape(-1, 3)
+    out = np.zeros(max(len(kl), 1), KL_DTYPE)
+    grp = np.full(max(len(kl), 1), -1, np.int32)
+    f = lib().orc_cull_lines
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    m = f(_p(kl), _p(lv), len(kl), int(w), int(h), dis, angle, endpoint_dis, _p(out), _p(grp))
+    return (out[:m].copy(), grp[:len(kl)].copy()) if want_groups else out[:m].copy()
+
+
+def line_extract_culled(gray, n_features=200):
+    """Frame::ExtractLSD up to cullingLine (src/Frame.cc:895-947): LINEextractor::operator() then cullingLine(im, 5, 2.5, 15, 30)
+    with its second LBD pass and rebuilt line functions.  Returns (keylines, desc, linevec)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    kl, _, lv = line_extract(gray, n_features)
+    kl2 = cull_lines(kl, lv, w, h)
+    desc2 = lbd_compute(gray, kl2) if len(kl2) else np.empty((0, 32), np.uint8)
+    return kl2, desc2, line_functions(kl2)
+
+
 def lbd_gradients(gray):
     gray = np.ascontiguousarray(gray, np.uint8)
     dx = np.empty(gray.shape, np.int16); dy = np.empty(gray.shape, np.int16)
