@@ -80,6 +80,17 @@ ABI = {
     'hvo_lbd_sync': (C.c_int, [_vp]),
     'hvo_lbd_timer_start': (C.c_int, [_vp]),
     'hvo_lbd_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_proj_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    'hvo_proj_destroy': (None, [_vp]),
+    'hvo_proj_set_frame': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]),
+    'hvo_proj_get_grid': (C.c_int, [_vp, _vp, _vp]),
+    'hvo_proj_features_in_area': (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_proj_search': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_proj_last_rounds': (C.c_int, [_vp]),
+    'hvo_proj_last_launches': (C.c_int, [_vp]),
+    'hvo_proj_match_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    'hvo_proj_timer_start': (C.c_int, [_vp]),
+    'hvo_proj_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_line_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'hvo_line_destroy': (None, [_vp]),
     'hvo_line_max_lines': (C.c_int, [_vp]),
@@ -798,6 +809,211 @@ class LSDmatcher:
 
 # ---- Frame-level front-end ----------------------------------------------------------------------------------------
 STAGE_ORB, STAGE_LINES, STAGE_PLANES, STAGE_NORMALS, STAGE_ALL = 1, 2, 4, 8, 15
+
+
+PROJ_QUERY_DTYPE = np.dtype([('u', '<f4'), ('v', '<f4'), ('r', '<f4'), ('min_level', '<i4'), ('max_level', '<i4'), ('ur', '<f4'),
+                             ('claims', '<i4'), ('reserved', '<i4')])
+assert PROJ_QUERY_DTYPE.itemsize == 32
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+class ProjectionMatcher:
+    """Device side of the windowed matchers: the frame grid (Frame::AssignFeaturesToGrid, src/Frame.cc:832-847),
+    Frame::GetFeaturesInArea (:1502-1555) and the greedy search of ORBmatcher::SearchByProjection (src/ORBmatcher.cc:45-132,
+    1353-1497).  One frame at a time."""
+
+    def __init__(self, device=0):
+        out = _vp()
+        _check(lib().hvo_proj_create(int(device), C.byref(out)))
+        self._h = out
+        self.n = 0
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_proj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frame(self, keys_un, uright, desc, min_x, min_y, max_x, max_y):
+        keys = np.ascontiguousarray(keys_un, KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        self.n = len(keys)
+        _check(lib().hvo_proj_set_frame(self._h, _np_ptr(keys), _np_ptr(ur) if ur is not None else None, _np_ptr(desc), self.n,
+                                        float(min_x), float(min_y), float(max_x), float(max_y)))
+
+    def grid(self):
+        """(cell_start [64*48+1], cell_items): cell ix*48+iy lists mGrid[ix][iy]."""
+        cs = np.empty(GRID_COLS * GRID_ROWS + 1, np.int32)
+        items = np.empty(max(self.n, 1), np.int32)
+        _check(lib().hvo_proj_get_grid(self._h, _np_ptr(cs), _np_ptr(items)))
+        return cs, items[:cs[-1]].copy()
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = C.c_int(0)
+        _check(lib().hvo_proj_features_in_area(self._h, float(x), float(y), float(r), int(minLevel), int(maxLevel), _np_ptr(out), len(out),
+                                               C.byref(n)))
+        return out[:n.value].copy()
+
+    def search(self, queries, qdesc, claimed=None, mode=0, th_dist=100, nnratio=0.6):
+        q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        idx = np.full(max(len(q), 1), -1, np.int32)
+        dist = np.full(max(len(q), 1), 256, np.int32)
+        nm = C.c_int(0)
+        _check(lib().hvo_proj_search(self._h, _np_ptr(q), _np_ptr(qd), len(q), _np_ptr(cl) if cl is not None else None, int(mode),
+                                     int(th_dist), float(nnratio), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
+        return idx[:len(q)], dist[:len(q)], nm.value
+
+    def rounds(self):
+        return lib().hvo_proj_last_rounds(self._h)
+
+    def match_candidates(self, q, t, offsets, cand):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        cd = np.ascontiguousarray(cand, np.int32)
+        best4 = np.empty((max(len(q), 1), 4), np.int32)
+        _check(lib().hvo_proj_match_candidates(self._h, _np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(off), _np_ptr(cd), _np_ptr(best4)))
+        self.n = 0
+        return best4[:len(q)]
+
+    def timer_start(self):
+        _check(lib().hvo_proj_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_proj_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM2::ORBmatcher for the projection searches (reference include/ORBmatcher.h:38-77).  Frames and map
+    points are plain arrays (the reference's Frame / MapPoint objects stay with the caller):
+
+        F   = dict(keys_un KP_DTYPE [N], uright [N], desc [N,32], bounds (minX, minY, maxX, maxY), scale_factors [L],
+                   mappoint [N] int (index of the map point held, -1 none), claimed [N] bool (holds one with observations))
+        MPs = dict(proj_x, proj_y, proj_xr, view_cos, level, in_view, bad, has_obs, desc [M,32])
+    """
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        self._pm = ProjectionMatcher(device)
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return int(lib().hvo_hamming_distance(_np_ptr(a), _np_ptr(b)))
+
+    @staticmethod
+    def RadiusByViewingCos(viewCos):  # ORBmatcher.cc:134-140
+        return np.where(np.asarray(viewCos, np.float32) > np.float32(0.998), np.float32(2.5), np.float32(4.0))
+
+    def _set_frame(self, F):
+        b = F['bounds']
+        self._pm.set_frame(F['keys_un'], F.get('uright'), F['desc'], b[0], b[1], b[2], b[3])
+
+    def SearchByProjection(self, F, MPs, th=1.0):
+        """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:45-132).  Updates F['mappoint']
+        and F['claimed'] in place, returns (nmatches, match [M] keypoint index or -1)."""
+        M = len(MPs['proj_x'])
+        use = np.asarray(MPs['in_view'], bool) & ~np.asarray(MPs['bad'], bool)
+        sel = np.nonzero(use)[0]
+        lvl = np.asarray(MPs['level'], np.int32)[sel]
+        r = self.RadiusByViewingCos(np.asarray(MPs['view_cos'])[sel]).astype(np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        q = np.zeros(len(sel), PROJ_QUERY_DTYPE)
+        q['u'] = np.asarray(MPs['proj_x'], np.float32)[sel]; q['v'] = np.asarray(MPs['proj_y'], np.float32)[sel]
+        q['r'] = (r * np.asarray(F['scale_factors'], np.float32)[lvl]).astype(np.float32)
+        q['min_level'] = lvl - 1; q['max_level'] = lvl
+        q['ur'] = np.asarray(MPs['proj_xr'], np.float32)[sel]
+        q['claims'] = np.asarray(MPs['has_obs'], bool)[sel]
+        self._set_frame(F)
+        idx, dist, nm = self._pm.search(q, np.asarray(MPs['desc'], np.uint8)[sel], F.get('claimed'), 0, self.TH_HIGH, self.mfNNratio)
+        match = np.full(M, -1, np.int32)
+        match[sel] = idx
+        for k, i in zip(sel, idx):  # F.mvpMapPoints[bestIdx] = pMP, in query order
+            if i >= 0:
+                F['mappoint'][i] = k
+                if MPs['has_obs'][k]:
+                    F['claimed'][i] = True
+                else:
+                    F['claimed'][i] = False
+        return nm, match
+
+    @staticmethod
+    def ComputeThreeMaxima(sizes):  # ORBmatcher.cc:1630-1671
+        max1 = max2 = max3 = 0
+        ind1 = ind2 = ind3 = -1
+        for i, s in enumerate(sizes):
+            if s > max1:
+                max3, max2, max1 = max2, max1, s
+                ind3, ind2, ind1 = ind2, ind1, i
+            elif s > max2:
+                max3, max2 = max2, s
+                ind3, ind2 = ind2, i
+            elif s > max3:
+                max3, ind3 = s, i
+        if max2 < np.float32(0.1) * np.float32(max1):
+            ind2 = ind3 = -1
+        elif max3 < np.float32(0.1) * np.float32(max1):
+            ind3 = -1
+        return ind1, ind2, ind3
+
+    def SearchByProjectionLast(self, Cur, last, th, forward=False, backward=False):
+        """Matching part of SearchByProjection(CurrentFrame, LastFrame, th, mono) (ORBmatcher.cc:1353-1497).  `last` holds, for
+        every last-frame keypoint with a usable map point, its projection into the current frame: dict(u, v, ur, octave,
+        angle, has_obs, desc), in last-frame index order.  Returns (nmatches, match [len(last)])."""
+        n = len(last['u'])
+        octv = np.asarray(last['octave'], np.int32)
+        q = np.zeros(n, PROJ_QUERY_DTYPE)
+        q['u'] = last['u']; q['v'] = last['v']; q['ur'] = last['ur']
+        q['r'] = (np.float32(th) * np.asarray(Cur['scale_factors'], np.float32)[octv]).astype(np.float32)
+        if forward:
+            q['min_level'] = octv; q['max_level'] = -1
+        elif backward:
+            q['min_level'] = 0; q['max_level'] = octv
+        else:
+            q['min_level'] = octv - 1; q['max_level'] = octv + 1
+        q['claims'] = np.asarray(last['has_obs'], bool)
+        self._set_frame(Cur)
+        idx, dist, nm = self._pm.search(q, last['desc'], Cur.get('claimed'), 1, self.TH_HIGH, self.mfNNratio)
+        idx = idx.copy()
+        for k, i in enumerate(idx):
+            if i >= 0:
+                Cur['mappoint'][i] = k
+                Cur['claimed'][i] = bool(last['has_obs'][k])
+        if self.mbCheckOrientation:  # rotation consistency (:1458-1494)
+            hist = [[] for _ in range(self.HISTO_LENGTH)]
+            factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+            ang_c = np.asarray(Cur['keys_un']['angle'], np.float32)
+            for k, i in enumerate(idx):
+                if i < 0:
+                    continue
+                rot = np.float32(last['angle'][k]) - ang_c[i]
+                if rot < 0.0:
+                    rot = np.float32(rot + np.float32(360.0))
+                b = int(np.floor(float(np.float32(rot * factor)) + 0.5))  # round(): rot >= 0 here
+                if b == self.HISTO_LENGTH:
+                    b = 0
+                hist[b].append(i)
+            i1, i2, i3 = self.ComputeThreeMaxima([len(h) for h in hist])
+            for b in range(self.HISTO_LENGTH):
+                if b not in (i1, i2, i3):
+                    for i in hist[b]:
+                        Cur['mappoint'][i] = -1
+                        Cur['claimed'][i] = False
+                        nm -= 1
+        return nm, idx
 
 
 class _FrameParams(C.Structure):

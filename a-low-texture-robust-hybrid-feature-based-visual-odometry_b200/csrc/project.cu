@@ -1,0 +1,467 @@
+// Windowed (projection) matching for sm_100a: the frame grid and the greedy best / second-best search inside it.
+//
+// Replaces, for one frame at a time (tracking is sequential; SURVEY §8e "replicas only"):
+//   Frame::AssignFeaturesToGrid / PosInGrid         reference src/Frame.cc:832-847, 1680-1690
+//   Frame::GetFeaturesInArea                        src/Frame.cc:1502-1555
+//   ORBmatcher::SearchByProjection(F, MapPoints)    src/ORBmatcher.cc:45-132          (mode 0)
+//   ORBmatcher::SearchByProjection(Cur, Last / KF)  src/ORBmatcher.cc:1353-1497, 1499-1628   (mode 1, matching part)
+//
+//   k_proj_grid    one CTA: cell of every keypoint (round), histogram, exclusive scan, scatter, per-cell index sort, so a
+//                  cell lists its keypoints in index order exactly like the reference's push_back loop
+//   k_proj_round   one warp per query: the cells of the window in the reference's order (ix outer, iy inner; the iy run of
+//                  one ix is contiguous in memory), 32 candidates at a time: level / window / right-coordinate filters and
+//                  8 x __popc per lane, then the reference's sequential best / second update over the surviving lanes
+//
+// The reference assignment is greedy: a keypoint taken by an earlier query (whose map point has observations) is skipped by
+// later ones.  That order dependence is resolved exactly by iterating to the fixed point: every round all queries search in
+// parallel, treating a keypoint as claimed iff the smallest query index that chose it in the previous round is lower than
+// their own; queries 0..r are final after round r+1, and a round that changes no choice proves the fixed point, which is
+// the sequential result.  Conflicts are rare, so this takes two or three rounds.
+#include <algorithm>
+#include <climits>
+#include <new>
+
+#include "hvo_common.cuh"
+
+namespace hvo {
+
+static const int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;
+
+struct ProjKey { float x, y; int octave; float uright; };  // 16 bytes per keypoint
+struct ProjQuery { float u, v, r; int min_level, max_level; float ur; int claims; int pad; };  // hvo_proj_query
+struct GridGeom { float min_x, min_y, inv_w, inv_h; };
+
+__global__ void __launch_bounds__(1024) k_proj_grid(const hvo_keypoint* __restrict__ keys, const float* __restrict__ uright, int n,
+                                                    GridGeom g, ProjKey* __restrict__ pk, int* __restrict__ cell_start,
+                                                    int* __restrict__ cell_items, int* __restrict__ cell_of) {
+    __shared__ int s_cnt[kGridCells];
+    __shared__ int s_part[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int c = tid; c < kGridCells; c += 1024) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const hvo_keypoint k = keys[i];
+        ProjKey p;
+        p.x = k.x; p.y = k.y; p.octave = k.octave; p.uright = uright ? uright[i] : -1.f;
+        pk[i] = p;
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(k.x, g.min_x), g.inv_w)), py = (int)roundf(__fmul_rn(__fsub_rn(k.y, g.min_y), g.inv_h));
+        int c = -1;
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) { c = px * kGridRows + py; atomicAdd(&s_cnt[c], 1); }
+        cell_of[i] = c;
+    }
+    __syncthreads();
+    // exclusive scan of the 3072 counts: 3 per thread
+    int v[3], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = s_cnt[tid * 3 + k]; sum += v[k]; }
+    int pre = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+    if (lane == 31) s_part[wid] = pre;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_part[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        s_part[lane] = w;
+    }
+    __syncthreads();
+    int base = pre - sum + (wid > 0 ? s_part[wid - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { cell_start[tid * 3 + k] = base; s_cnt[tid * 3 + k] = base; base += v[k]; }
+    if (tid == 1023) cell_start[kGridCells] = base;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = cell_of[i];
+        if (c >= 0) cell_items[atomicAdd(&s_cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    // a cell lists its keypoints in index order (reference: push_back in the i loop)
+    for (int c = tid; c < kGridCells; c += 1024) {
+        const int b = cell_start[c], e = s_cnt[c];
+        for (int i = b + 1; i < e; ++i) {
+            const int x = cell_items[i];
+            int j = i - 1;
+            while (j >= b && cell_items[j] > x) { cell_items[j + 1] = cell_items[j]; --j; }
+            cell_items[j + 1] = x;
+        }
+    }
+}
+
+struct ProjWindow { int x0, x1, y0, y1; bool empty; };
+__device__ __forceinline__ ProjWindow proj_window(const GridGeom& g, float x, float y, float r) {  // Frame.cc:1507-1521
+    ProjWindow w;
+    w.empty = true;
+    w.x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.min_x), r), g.inv_w)));
+    w.x1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.min_x), r), g.inv_w)));
+    w.y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.min_y), r), g.inv_h)));
+    w.y1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.min_y), r), g.inv_h)));
+    if (w.x0 >= kGridCols || w.x1 < 0 || w.y0 >= kGridRows || w.y1 < 0) return w;
+    w.empty = false;
+    return w;
+}
+__device__ __forceinline__ bool proj_in_area(const ProjKey& p, float x, float y, float r, int minLevel, int maxLevel) {
+    if (minLevel > 0 || maxLevel >= 0) {
+        if (p.octave < minLevel) return false;
+        if (maxLevel >= 0 && p.octave > maxLevel) return false;
+    }
+    return fabsf(__fsub_rn(p.x, x)) < r && fabsf(__fsub_rn(p.y, y)) < r;
+}
+
+// Frame::GetFeaturesInArea for one window (inspection / parity of the candidate order).  One warp.
+__global__ void __launch_bounds__(32) k_proj_area(const ProjKey* __restrict__ pk, const int* __restrict__ cell_start,
+                                                  const int* __restrict__ cell_items, GridGeom g, float x, float y, float r, int minLevel,
+                                                  int maxLevel, int* __restrict__ out, int cap, int* __restrict__ n_out) {
+    const int lane = threadIdx.x;
+    const ProjWindow w = proj_window(g, x, y, r);
+    int cnt = 0;
+    if (!w.empty)
+        for (int ix = w.x0; ix <= w.x1; ++ix) {
+            const int b = cell_start[ix * kGridRows + w.y0], e = cell_start[ix * kGridRows + w.y1 + 1];
+            for (int base = b; base < e; base += 32) {
+                const int i = base + lane;
+                int id = -1;
+                bool ok = false;
+                if (i < e) { id = cell_items[i]; ok = proj_in_area(pk[id], x, y, r, minLevel, maxLevel); }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const int o = cnt + __popc(m & ((1u << lane) - 1u)); if (o < cap) out[o] = id; }
+                cnt += __popc(m);
+            }
+        }
+    if (lane == 0) *n_out = cnt;
+}
+
+__global__ void __launch_bounds__(128) k_proj_round(const ProjKey* __restrict__ pk, const uint4* __restrict__ desc,
+                                                    const int* __restrict__ cell_start, const int* __restrict__ cell_items, GridGeom g,
+                                                    const ProjQuery* __restrict__ qs, const uint4* __restrict__ qdesc, int nq,
+                                                    const int* __restrict__ claim_prev, int* __restrict__ claim_next, int mode, int th_dist,
+                                                    float nnratio, int* __restrict__ choice, int* __restrict__ choice_dist,
+                                                    int* __restrict__ changed) {
+    const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= nq) return;
+    const ProjQuery q = qs[k];
+    const uint4 qa = qdesc[2 * k], qb = qdesc[2 * k + 1];
+    const ProjWindow w = proj_window(g, q.u, q.v, q.r);
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    if (!w.empty)
+        for (int ix = w.x0; ix <= w.x1; ++ix) {
+            const int b = cell_start[ix * kGridRows + w.y0], e = cell_start[ix * kGridRows + w.y1 + 1];
+            for (int base = b; base < e; base += 32) {
+                const int i = base + lane;
+                int id = -1, dist = 256, oct = 0;
+                bool ok = false;
+                if (i < e) {
+                    id = cell_items[i];
+                    const ProjKey p = pk[id];
+                    oct = p.octave;
+                    ok = proj_in_area(p, q.u, q.v, q.r, q.min_level, q.max_level) && !(claim_prev[id] < k);
+                    if (ok && p.uright > 0) ok = !(fabsf(__fsub_rn(q.ur, p.uright)) > q.r);
+                    if (ok) {
+                        const uint4 da = desc[2 * id], db = desc[2 * id + 1];
+                        dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                               __popc(qb.x ^ db.x) + __popc(qb.y ^ db.y) + __popc(qb.z ^ db.z) + __popc(qb.w ^ db.w);
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ok);
+                while (m) {  // the reference's update, candidate by candidate (ORBmatcher.cc:104-117)
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int d = __shfl_sync(0xffffffffu, dist, j), l = __shfl_sync(0xffffffffu, oct, j), c = __shfl_sync(0xffffffffu, id, j);
+                    if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = l; bestIdx = c; }
+                    else if (d < bestDist2) { bestLevel2 = l; bestDist2 = d; }
+                }
+            }
+        }
+    int pick = -1;
+    if (bestDist <= th_dist && !(mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2))) pick = bestIdx;
+    if (lane == 0) {
+        if (choice[k] != pick) { choice[k] = pick; *changed = 1; }
+        choice_dist[k] = pick >= 0 ? bestDist : 256;
+        if (pick >= 0 && q.claims) atomicMin(&claim_next[pick], k);
+    }
+}
+
+__global__ void k_proj_claim_init(const uint8_t* __restrict__ claimed, int n, int* __restrict__ a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (claimed && claimed[i]) ? -1 : INT_MAX;
+}
+__global__ void k_proj_fill(int* __restrict__ a, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// generic candidate lists: one warp per query, candidates in the caller's order, strict '<' updates
+__global__ void __launch_bounds__(128) k_match_candidates(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
+                                                          const int* __restrict__ off, const int* __restrict__ cand, int4* __restrict__ best4) {
+    const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= nq) return;
+    const uint4 qa = q[2 * k], qb = q[2 * k + 1];
+    int d0 = 256, i0 = -1, d1 = 256, i1 = -1;
+    const int b = off[k], e = off[k + 1];
+    for (int base = b; base < e; base += 32) {
+        const int i = base + lane;
+        int id = -1, dist = 256;
+        if (i < e) {
+            id = cand[i];
+            const uint4 da = t[2 * id], db = t[2 * id + 1];
+            dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) + __popc(qb.x ^ db.x) +
+                   __popc(qb.y ^ db.y) + __popc(qb.z ^ db.z) + __popc(qb.w ^ db.w);
+        }
+        const int cnt = min(32, e - base);
+        for (int j = 0; j < cnt; ++j) {
+            const int d = __shfl_sync(0xffffffffu, dist, j), c = __shfl_sync(0xffffffffu, id, j);
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = c; }
+            else if (d < d1) { d1 = d; i1 = c; }
+        }
+    }
+    if (lane == 0) best4[k] = make_int4(i0, d0, i1, d1);
+}
+
+}  // namespace hvo
+
+using namespace hvo;
+
+struct hvo_proj {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    int n = 0, kcap = 0, qcap = 0, ccap = 0;
+    GridGeom g{0, 0, 0, 0};
+    hvo_keypoint* d_keys = nullptr;
+    float* d_uright = nullptr;
+    uint8_t* d_desc = nullptr;
+    ProjKey* d_pk = nullptr;
+    int *d_cell_start = nullptr, *d_cell_items = nullptr, *d_cell_of = nullptr;
+    uint8_t* d_claimed = nullptr;
+    int *d_claim0 = nullptr, *d_claim_a = nullptr, *d_claim_b = nullptr;
+    ProjQuery* d_q = nullptr;
+    uint8_t* d_qdesc = nullptr;
+    int *d_choice = nullptr, *d_cdist = nullptr, *d_flag = nullptr, *d_area = nullptr;
+    int* h_flag = nullptr;  // pinned [2]
+    int *d_off = nullptr, *d_cand = nullptr;
+    int4* d_best4 = nullptr;
+    int last_rounds = 0, last_launches = 0;
+};
+
+#define HVO_TRYB(call) do { if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); return HVO_ERR_CUDA; } } while (0)
+
+template <class T>
+static int grow(T*& p, size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    HVO_TRYB(cudaMalloc(&p, count * sizeof(T)));
+    return HVO_OK;
+}
+
+static int proj_reserve_keys(hvo_proj* h, int n) {
+    if (n <= h->kcap) return HVO_OK;
+    const int cap = std::max(n, 2048);
+    int st;
+    if ((st = grow(h->d_keys, cap)) || (st = grow(h->d_uright, cap)) || (st = grow(h->d_desc, (size_t)cap * 32)) || (st = grow(h->d_pk, cap)) ||
+        (st = grow(h->d_cell_items, cap)) || (st = grow(h->d_cell_of, cap)) || (st = grow(h->d_claimed, cap)) || (st = grow(h->d_claim0, cap)) ||
+        (st = grow(h->d_claim_a, cap)) || (st = grow(h->d_claim_b, cap)) || (st = grow(h->d_area, cap)))
+        return st;
+    h->kcap = cap;
+    return HVO_OK;
+}
+static int proj_reserve_queries(hvo_proj* h, int nq) {
+    if (nq <= h->qcap) return HVO_OK;
+    const int cap = std::max(nq, 2048);
+    int st;
+    if ((st = grow(h->d_q, cap)) || (st = grow(h->d_qdesc, (size_t)cap * 32)) || (st = grow(h->d_choice, cap)) || (st = grow(h->d_cdist, cap)) ||
+        (st = grow(h->d_off, (size_t)cap + 1)) || (st = grow(h->d_best4, cap)))
+        return st;
+    h->qcap = cap;
+    return HVO_OK;
+}
+
+extern "C" {
+
+int hvo_proj_create(int device, hvo_proj** out) {
+    HVO_CHECK_ARG(out, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    HVO_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { set_error("no CUDA device: libhvofront has no CPU fallback"); return HVO_ERR_CUDA; }
+    HVO_CHECK_ARG(device >= 0 && device < ndev, "device index out of range");
+    hvo_proj* h = new (std::nothrow) hvo_proj();
+    if (!h) { set_error("out of host memory"); return HVO_ERR_ARG; }
+    h->device = device;
+    int st = HVO_OK;
+    do {
+#define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
+        HVO_TRY(cudaSetDevice(device));
+        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        HVO_TRY(cudaEventCreate(&h->tev[0]));
+        HVO_TRY(cudaEventCreate(&h->tev[1]));
+        HVO_TRY(cudaMalloc(&h->d_cell_start, (kGridCells + 1) * sizeof(int)));
+        HVO_TRY(cudaMalloc(&h->d_flag, 2 * sizeof(int)));
+        HVO_TRY(cudaMallocHost(&h->h_flag, 2 * sizeof(int)));
+#undef HVO_TRY
+    } while (0);
+    if (st != HVO_OK) { hvo_proj_destroy(h); return st; }
+    *out = h;
+    return HVO_OK;
+}
+
+void hvo_proj_destroy(hvo_proj* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* bufs[] = {h->d_keys, h->d_uright, h->d_desc, h->d_pk, h->d_cell_start, h->d_cell_items, h->d_cell_of, h->d_claimed, h->d_claim0,
+                    h->d_claim_a, h->d_claim_b, h->d_q, h->d_qdesc, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_off, h->d_cand, h->d_best4};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
+    for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* uright, const uint8_t* desc, int n, float min_x, float min_y,
+                       float max_x, float max_y) {
+    HVO_CHECK_ARG(h, "null handle");
+    HVO_CHECK_ARG(n >= 0 && (n == 0 || (keys_un && desc)), "null keypoints / descriptors");
+    HVO_CHECK_ARG(max_x > min_x && max_y > min_y, "empty image bounds");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_keys(h, n);
+    if (st != HVO_OK) return st;
+    h->n = n;
+    h->g.min_x = min_x; h->g.min_y = min_y;
+    h->g.inv_w = (float)kGridCols / (max_x - min_x);   // Frame.cc:419-420
+    h->g.inv_h = (float)kGridRows / (max_y - min_y);
+    if (n > 0) {
+        HVO_CUDA(cudaMemcpyAsync(h->d_keys, keys_un, (size_t)n * sizeof(hvo_keypoint), cudaMemcpyHostToDevice, h->stream));
+        if (uright) HVO_CUDA(cudaMemcpyAsync(h->d_uright, uright, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        HVO_CUDA(cudaMemcpyAsync(h->d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_proj_grid<<<1, 1024, 0, h->stream>>>(h->d_keys, uright ? h->d_uright : nullptr, n, h->g, h->d_pk, h->d_cell_start, h->d_cell_items, h->d_cell_of);
+    HVO_CUDA(cudaGetLastError());
+    h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_proj_get_grid(hvo_proj* h, int32_t* cell_start, int32_t* cell_items) {
+    HVO_CHECK_ARG(h && cell_start && cell_items, "null argument");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaMemcpyAsync(cell_start, h->d_cell_start, (kGridCells + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    const int m = cell_start[kGridCells];
+    if (m > 0) HVO_CUDA(cudaMemcpyAsync(cell_items, h->d_cell_items, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    return HVO_OK;
+}
+
+int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_level, int max_level, int32_t* out, int capacity, int* n_out) {
+    HVO_CHECK_ARG(h && out && n_out, "null argument");
+    HVO_CHECK_ARG(capacity >= 1, "capacity < 1");
+    HVO_CUDA(cudaSetDevice(h->device));
+    *n_out = 0;
+    if (h->n == 0) return HVO_OK;
+    k_proj_area<<<1, 32, 0, h->stream>>>(h->d_pk, h->d_cell_start, h->d_cell_items, h->g, x, y, r, min_level, max_level, h->d_area, h->kcap,
+                                          h->d_flag);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    const int cnt = h->h_flag[0];
+    const int cp = std::min(cnt, capacity);
+    if (cp > 0) HVO_CUDA(cudaMemcpyAsync(out, h->d_area, (size_t)cp * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    *n_out = cnt;
+    return HVO_OK;
+}
+
+int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
+                    float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
+    HVO_CHECK_ARG(h && match_idx, "null argument");
+    HVO_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (best + second, level ratio) or 1 (best only)");
+    if (n_matches) *n_matches = 0;
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(queries && qdesc, "null queries");
+    if (h->n == 0) {
+        for (int i = 0; i < nq; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
+        return HVO_OK;
+    }
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_queries(h, nq);
+    if (st != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_q, queries, (size_t)nq * sizeof(ProjQuery), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (claimed) HVO_CUDA(cudaMemcpyAsync(h->d_claimed, claimed, (size_t)h->n, cudaMemcpyHostToDevice, s));
+    const int nb = div_up(h->n, 256);
+    k_proj_claim_init<<<nb, 256, 0, s>>>(claimed ? h->d_claimed : nullptr, h->n, h->d_claim0);
+    HVO_CUDA(cudaMemcpyAsync(h->d_claim_a, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    k_proj_fill<<<div_up(nq, 256), 256, 0, s>>>(h->d_choice, nq, -2);
+    int launches = 2, rounds = 0;
+    int *prev = h->d_claim_a, *next = h->d_claim_b;
+    while (true) {
+        HVO_CUDA(cudaMemcpyAsync(next, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        HVO_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+        k_proj_round<<<div_up(nq * 32, 128), 128, 0, s>>>(h->d_pk, reinterpret_cast<const uint4*>(h->d_desc), h->d_cell_start, h->d_cell_items,
+                                                          h->g, h->d_q, reinterpret_cast<const uint4*>(h->d_qdesc), nq, prev, next, mode, th_dist,
+                                                          nnratio, h->d_choice, h->d_cdist, h->d_flag);
+        HVO_CUDA(cudaGetLastError());
+        HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        HVO_CUDA(cudaStreamSynchronize(s));
+        ++launches; ++rounds;
+        if (!h->h_flag[0]) break;        // no choice changed: fixed point == the reference's sequential assignment
+        if (rounds > nq + 1) { set_error("projection search did not reach its fixed point"); return HVO_ERR_CUDA; }
+        std::swap(prev, next);
+    }
+    h->last_rounds = rounds; h->last_launches = launches;
+    HVO_CUDA(cudaMemcpyAsync(match_idx, h->d_choice, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, h->d_cdist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
+    return HVO_OK;
+}
+
+int hvo_proj_last_rounds(const hvo_proj* h) { return h ? h->last_rounds : 0; }
+int hvo_proj_last_launches(const hvo_proj* h) { return h ? h->last_launches : 0; }
+
+int hvo_proj_match_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
+                              int32_t* best4) {
+    HVO_CHECK_ARG(h && best4, "null argument");
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(q && offsets, "null argument");
+    const int total = offsets[nq];
+    HVO_CHECK_ARG(total >= 0 && (total == 0 || (cand && t && nt > 0)), "candidate lists without a train set");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_queries(h, nq);
+    if (st == HVO_OK) st = proj_reserve_keys(h, nt);
+    if (st != HVO_OK) return st;
+    if (total > h->ccap) {
+        if ((st = grow(h->d_cand, (size_t)std::max(total, 4096)))) return st;
+        h->ccap = std::max(total, 4096);
+    }
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt > 0) HVO_CUDA(cudaMemcpyAsync(h->d_desc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_off, offsets, ((size_t)nq + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (total > 0) HVO_CUDA(cudaMemcpyAsync(h->d_cand, cand, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s));
+    k_match_candidates<<<div_up(nq * 32, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(h->d_qdesc), nq, reinterpret_cast<const uint4*>(h->d_desc),
+                                                            h->d_off, h->d_cand, h->d_best4);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(best4, h->d_best4, (size_t)nq * sizeof(int4), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    h->n = 0;  // the frame descriptors were overwritten: hvo_proj_set_frame must be called again before the next search
+    h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_proj_timer_start(hvo_proj* h) {
+    HVO_CHECK_ARG(h, "null handle");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaEventRecord(h->tev[0], h->stream));
+    return HVO_OK;
+}
+int hvo_proj_timer_stop(hvo_proj* h, float* ms_out) {
+    HVO_CHECK_ARG(h && ms_out, "null argument");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaEventRecord(h->tev[1], h->stream));
+    HVO_CUDA(cudaEventSynchronize(h->tev[1]));
+    HVO_CUDA(cudaEventElapsedTime(ms_out, h->tev[0], h->tev[1]));
+    return HVO_OK;
+}
+
+}  // extern "C"

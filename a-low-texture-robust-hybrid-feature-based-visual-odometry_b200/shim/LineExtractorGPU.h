@@ -108,6 +108,34 @@ public:
         for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), &desc_[(size_t)i * 32], 32);
     }
 
+    // Frame::cullingLine(imGray, 5, 2.5, 15, 30) (src/Frame.cc:952-1116) in one call: the body of that function becomes
+    //   mpLSDextractorLeft->gpu().cullingLine(imGray, mvKeylinesUn, mLdesc, mvKeyLineFunctions);
+    // keylines / lineVec2d are replaced by the merged, response-sorted set, descriptors by their LBD.
+    template <class KeyLineT, class Vec3T>
+    void cullingLine(const cv::Mat& image, std::vector<KeyLineT>& keylines, cv::OutputArray descriptors, std::vector<Vec3T>& lineVec2d) {
+        static_assert(sizeof(KeyLineT) == sizeof(hvo_keyline), "KeyLine layout");
+        const int n = (int)keylines.size();
+        if (n == 0 || image.empty() || !h_ || image.cols != w_ || image.rows != hgt_ || n > hvo_line_max_lines(h_)) return;
+        const int cap = hvo_line_max_lines(h_);
+        kl_.resize(cap);
+        desc_.resize((size_t)cap * 32);
+        lv_.resize((size_t)cap * 3);
+        std::memcpy(kl_.data(), (const void*)keylines.data(), (size_t)n * sizeof(hvo_keyline));
+        for (int i = 0; i < n; ++i) { lv_[3 * i] = lineVec2d[i][0]; lv_[3 * i + 1] = lineVec2d[i][1]; lv_[3 * i + 2] = lineVec2d[i][2]; }
+        int m = 0;
+        if (hvo_line_cull(h_, image.data, (size_t)image.step, kl_.data(), lv_.data(), n, desc_.data(), &m) != HVO_OK) {
+            std::fprintf(stderr, "cullingLine: %s\n", hvo_last_error());
+            return;
+        }
+        keylines.resize(m);
+        std::memcpy((void*)keylines.data(), kl_.data(), (size_t)m * sizeof(hvo_keyline));
+        descriptors.create(m, 32, CV_8U);
+        cv::Mat d = descriptors.getMat();
+        for (int i = 0; i < m; ++i) std::memcpy(d.ptr(i), &desc_[(size_t)i * 32], 32);
+        lineVec2d.resize(m);
+        for (int i = 0; i < m; ++i) { lineVec2d[i][0] = lv_[3 * i]; lineVec2d[i][1] = lv_[3 * i + 1]; lineVec2d[i][2] = lv_[3 * i + 2]; }
+    }
+
 private:
     hvo_line* h_;
     hvo_lbd* lbd_;

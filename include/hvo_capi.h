@@ -136,6 +136,49 @@ int hvo_matcher_sync(hvo_matcher* m);
 int hvo_matcher_timer_start(hvo_matcher* m);
 int hvo_matcher_timer_stop(hvo_matcher* m, float* ms_out);
 
+/* ------------------------------------------------------------------------------------------- PROJECTION
+ * Windowed matching against one frame: the frame grid (Frame::AssignFeaturesToGrid / PosInGrid, src/Frame.cc:832-847,
+ * 1680-1690), Frame::GetFeaturesInArea (src/Frame.cc:1502-1555) and the greedy best / second-best search of
+ * ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-132, mode 0) and of
+ * SearchByProjection(CurrentFrame, LastFrame, th, mono) / (CurrentFrame, KF, found, th, ORBdist) (src/ORBmatcher.cc:1353-1497,
+ * 1499-1628, mode 1).  The caller keeps the projection (isInFrustum, pose) and the MapPoint bookkeeping: a query is the
+ * projected position, the search radius r (already multiplied by the level's scale factor), the level range handed to
+ * GetFeaturesInArea, the predicted right coordinate, and whether the map point it carries has observations (so that the
+ * keypoint it takes is skipped by later queries, ORBmatcher.cc:88-90).  match_idx[i] is the keypoint query i is assigned
+ * to, or -1; applying `F.mvpMapPoints[match_idx[i]] = pMP_i` for i ascending reproduces the reference's final state. */
+typedef struct hvo_proj_query {
+    float u, v, r;                 /* window centre and half-size */
+    int32_t min_level, max_level;  /* GetFeaturesInArea(minLevel, maxLevel); -1 = open */
+    float ur;                      /* predicted right coordinate (checked against mvuRight > 0 with tolerance r) */
+    int32_t claims;                /* != 0: the assigned keypoint counts as taken for later queries */
+    int32_t reserved;
+} hvo_proj_query;
+
+typedef struct hvo_proj hvo_proj;
+int hvo_proj_create(int device, hvo_proj** out);
+void hvo_proj_destroy(hvo_proj* h);
+/* mvKeysUn, mvuRight (or NULL), mDescriptors of the frame searched in; image bounds mnMinX.. (src/Frame.cc:1733-1760).
+ * Uploads them and builds the 64 x 48 grid on the device. */
+int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* uright, const uint8_t* desc, int n, float min_x, float min_y,
+                       float max_x, float max_y);
+/* inspection: cell_start [64*48 + 1] (cell = ix * 48 + iy), cell_items [n] = mGrid[ix][iy] concatenated */
+int hvo_proj_get_grid(hvo_proj* h, int32_t* cell_start, int32_t* cell_items);
+/* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel): indices in the reference's order; *n_out may exceed capacity */
+int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_level, int max_level, int32_t* out, int capacity, int* n_out);
+/* claimed [n] or NULL: keypoints that hold a map point with observations at call time.  mode 0: accept best <= th_dist unless
+ * (bestLevel == bestLevel2 && best > nnratio * second); mode 1: accept best <= th_dist.  match_dist may be NULL. */
+int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
+                    float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches);
+int hvo_proj_last_rounds(const hvo_proj* h);   /* fixed-point rounds of the last search (>= 1) */
+int hvo_proj_last_launches(const hvo_proj* h);
+/* Candidate lists chosen by the caller (e.g. the per-node buckets of SearchByBoW, src/ORBmatcher.cc:162-293): for query i the
+ * train rows cand[offsets[i] .. offsets[i+1]) in that order; best4[i] = {idx0, dist0, idx1, dist1} with the reference's
+ * strict '<' updates (-1 / 256 where absent).  Invalidates the frame set by hvo_proj_set_frame. */
+int hvo_proj_match_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
+                              int32_t* best4);
+int hvo_proj_timer_start(hvo_proj* h);
+int hvo_proj_timer_stop(hvo_proj* h, float* ms_out);
+
 /* ------------------------------------------------------------------------------------------------ LBD
  * Replaces cv::line_descriptor::BinaryDescriptor::compute(image, keylines, descriptors) as called at
  * src/LineExtractor.cpp:361-363 and src/Frame.cc:1094-1096 (vendored algorithm:

@@ -232,6 +232,55 @@ def frame_bf_match(q, t, nnratio, TH):
     return m
 
 
+PROJ_QUERY_DTYPE = np.dtype([('u', '<f4'), ('v', '<f4'), ('r', '<f4'), ('min_level', '<i4'), ('max_level', '<i4'), ('ur', '<f4'),
+                             ('claims', '<i4'), ('reserved', '<i4')])
+
+
+def grid_build(keys, bounds):
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    cnt = np.zeros(64 * 48, np.int32); items = np.zeros(max(len(keys), 1), np.int32)
+    f = lib().orc_grid_build
+    f.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    f(_p(keys), len(keys), *[float(b) for b in bounds], _p(cnt), _p(items))
+    return cnt, items[:cnt.sum()].copy()
+
+
+def features_in_area(keys, bounds, x, y, r, min_level=-1, max_level=-1):
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    out = np.zeros(max(len(keys), 1), np.int32)
+    f = lib().orc_features_in_area
+    f.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = f(_p(keys), len(keys), *[float(b) for b in bounds], float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
+    return out[:n].copy()
+
+
+def search_projection(keys, uright, desc, bounds, queries, qdesc, claimed=None, mode=0, th_dist=100, nnratio=0.6):
+    """ORBmatcher::SearchByProjection's sequential greedy loop (src/ORBmatcher.cc:45-132 mode 0, :1353-1497 mode 1)."""
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    idx = np.full(max(len(q), 1), -1, np.int32); dist = np.full(max(len(q), 1), 256, np.int32)
+    f = lib().orc_search_projection
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                                                                    C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    n = f(_p(keys), _p(ur) if ur is not None else None, _p(desc), len(keys), *[float(b) for b in bounds], _p(q), _p(qd), len(q),
+          _p(cl) if cl is not None else None, int(mode), int(th_dist), float(nnratio), _p(idx), _p(dist))
+    return idx[:len(q)], dist[:len(q)], int(n)
+
+
+def match_candidates(q, t, offsets, cand):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)
+    best4 = np.zeros((max(len(q), 1), 4), np.int32)
+    f = lib().orc_match_candidates
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(q), len(q), _p(t), _p(off), _p(cd), _p(best4))
+    return best4[:len(q)]
+
+
 # ---- lines: LSD wrapper fields + LBD ---------------------------------------------------------------------
 KL_DTYPE = np.dtype([('angle', '<f4'), ('class_id', '<i4'), ('octave', '<i4'), ('pt_x', '<f4'), ('pt_y', '<f4'),
                      ('response', '<f4'), ('size', '<f4'), ('startPointX', '<f4'), ('startPointY', '<f4'),

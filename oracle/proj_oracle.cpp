@@ -1,0 +1,159 @@
+// TEST INFRASTRUCTURE — CPU restatement of the windowed (projection) matchers and of the frame grid they search.
+// Not on the product path.
+//
+//   Frame::AssignFeaturesToGrid / PosInGrid        reference src/Frame.cc:832-847, 1680-1690   (64 x 48 cells)
+//   Frame::GetFeaturesInArea                       src/Frame.cc:1502-1555  (cell range by floor / ceil, ix outer, iy inner,
+//                                                  level filter, |dx| < r && |dy| < r; this order is the candidate order)
+//   ORBmatcher::SearchByProjection(F, MapPoints)   src/ORBmatcher.cc:45-132   -> mode 0: best + second with their levels, accept
+//                                                  best <= TH and not (bestLevel == bestLevel2 && best > ratio * second)
+//   ORBmatcher::SearchByProjection(Cur, Last, ...) src/ORBmatcher.cc:1353-1497 (and the reloc variant :1499-1628)
+//                                                  -> mode 1: best only, accept best <= TH
+// Both walk their queries in order and skip keypoints already holding a map point with observations (:88-90,
+// :1425-1428), i.e. claimed at call time or by an earlier query of the same call: a greedy, order-dependent assignment.
+// The projection itself (isInFrustum / pose) stays with the caller: a query is the projected position, the search radius,
+// the level range, the predicted right coordinate and whether the assigned map point counts as an observation.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace projo {
+
+struct KeyPoint { float x, y, size, angle, response; int octave, class_id; };  // cv::KeyPoint, 28 bytes
+struct Query { float u, v, r; int min_level, max_level; float ur; int claims; int pad; };  // hvo_proj_query, 32 bytes
+
+static const int kCols = 64, kRows = 48;
+
+struct Grid {
+    float min_x, min_y, inv_w, inv_h;
+    std::vector<int> cell[kCols][kRows];
+    void build(const KeyPoint* k, int n, float mnx, float mny, float mxx, float mxy) {
+        min_x = mnx; min_y = mny;
+        inv_w = (float)kCols / (mxx - mnx);
+        inv_h = (float)kRows / (mxy - mny);
+        for (int i = 0; i < n; ++i) {
+            const int px = (int)std::round((k[i].x - min_x) * inv_w), py = (int)std::round((k[i].y - min_y) * inv_h);
+            if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+    void area(const KeyPoint* k, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+        out.clear();
+        const int x0 = std::max(0, (int)std::floor((x - min_x - r) * inv_w));
+        if (x0 >= kCols) return;
+        const int x1 = std::min(kCols - 1, (int)std::ceil((x - min_x + r) * inv_w));
+        if (x1 < 0) return;
+        const int y0 = std::max(0, (int)std::floor((y - min_y - r) * inv_h));
+        if (y0 >= kRows) return;
+        const int y1 = std::min(kRows - 1, (int)std::ceil((y - min_y + r) * inv_h));
+        if (y1 < 0) return;
+        const bool check = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = x0; ix <= x1; ++ix)
+            for (int iy = y0; iy <= y1; ++iy)
+                for (int id : cell[ix][iy]) {
+                    const KeyPoint& kp = k[id];
+                    if (check) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    const float dx = kp.x - x, dy = kp.y - y;
+                    if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(id);
+                }
+    }
+};
+
+static int hamming(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 32; i += 4) {
+        uint32_t x, y;
+        std::memcpy(&x, a + i, 4);
+        std::memcpy(&y, b + i, 4);
+        d += __builtin_popcount(x ^ y);
+    }
+    return d;
+}
+
+}  // namespace projo
+
+extern "C" {
+
+// grid inspection: cell_count [64*48] (index ix * 48 + iy), cell_items in the same order (n entries at most)
+void orc_grid_build(const void* keys, int n, float min_x, float min_y, float max_x, float max_y, int32_t* cell_count, int32_t* cell_items) {
+    projo::Grid g;
+    g.build((const projo::KeyPoint*)keys, n, min_x, min_y, max_x, max_y);
+    int o = 0;
+    for (int ix = 0; ix < projo::kCols; ++ix)
+        for (int iy = 0; iy < projo::kRows; ++iy) {
+            cell_count[ix * projo::kRows + iy] = (int)g.cell[ix][iy].size();
+            for (int id : g.cell[ix][iy]) cell_items[o++] = id;
+        }
+}
+
+int orc_features_in_area(const void* keys, int n, float min_x, float min_y, float max_x, float max_y, float x, float y, float r, int minLevel,
+                         int maxLevel, int32_t* out, int cap) {
+    projo::Grid g;
+    g.build((const projo::KeyPoint*)keys, n, min_x, min_y, max_x, max_y);
+    std::vector<int> v;
+    g.area((const projo::KeyPoint*)keys, x, y, r, minLevel, maxLevel, v);
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+// mode 0: SearchByProjection(F, vpMapPoints, th)  (best / second / levels / ratio);  mode 1: best only.
+// claimed [n] (or null): keypoint holds a map point with observations at call time.  match_idx / match_dist [nq].
+int orc_search_projection(const void* keys, const float* uright, const uint8_t* desc, int n, float min_x, float min_y, float max_x,
+                          float max_y, const void* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed_in, int mode,
+                          int th_dist, float nnratio, int32_t* match_idx, int32_t* match_dist) {
+    using namespace projo;
+    const KeyPoint* K = (const KeyPoint*)keys;
+    const Query* Q = (const Query*)queries;
+    Grid g;
+    g.build(K, n, min_x, min_y, max_x, max_y);
+    std::vector<uint8_t> claimed(n > 0 ? n : 1, 0);
+    if (claimed_in) std::memcpy(claimed.data(), claimed_in, n);
+    std::vector<int> cand;
+    int nmatches = 0;
+    for (int k = 0; k < nq; ++k) {
+        match_idx[k] = -1; match_dist[k] = 256;
+        const Query& q = Q[k];
+        g.area(K, q.u, q.v, q.r, q.min_level, q.max_level, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (claimed[idx]) continue;
+            if (uright && uright[idx] > 0) {
+                const float er = std::fabs(q.ur - uright[idx]);
+                if (er > q.r) continue;
+            }
+            const int dist = hamming(qdesc + 32 * (size_t)k, desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = K[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = K[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= th_dist) {
+            if (mode == 0 && bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            match_idx[k] = bestIdx; match_dist[k] = bestDist;
+            if (q.claims) claimed[bestIdx] = 1;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// generic candidate lists (e.g. the per-vocabulary-node buckets of SearchByBoW, src/ORBmatcher.cc:162-293): for query i the
+// train indices cand[off[i] .. off[i+1]) in the caller's order; best4[i] = {idx0, dist0, idx1, dist1}, strict '<' updates.
+void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* off, const int32_t* cand, int32_t* best4) {
+    for (int i = 0; i < nq; ++i) {
+        int d0 = 256, i0 = -1, d1 = 256, i1 = -1;
+        for (int c = off[i]; c < off[i + 1]; ++c) {
+            const int d = projo::hamming(q + 32 * (size_t)i, t + 32 * (size_t)cand[c]);
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = cand[c]; }
+            else if (d < d1) { d1 = d; i1 = cand[c]; }
+        }
+        best4[4 * i] = i0; best4[4 * i + 1] = d0; best4[4 * i + 2] = i1; best4[4 * i + 3] = d1;
+    }
+}
+
+}  // extern "C"

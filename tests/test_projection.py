@@ -1,0 +1,216 @@
+"""Windowed (projection) matching: frame grid, GetFeaturesInArea, ORBmatcher::SearchByProjection (SURVEY §8 rows B4, B5, E2, E3,
+E5 and the candidate-list primitive behind E4).
+
+Oracle: oracle/proj_oracle.cpp restates src/Frame.cc:832-847, 1502-1555, 1680-1690 and src/ORBmatcher.cc:45-132, 1353-1497
+(sequential greedy loops).  No reference execution is possible here and the reference has no tests: parity unpinned by
+execution; the candidate set is cross-checked against a brute-force window test in numpy.
+GPU bar: bit-exact (indices, distances, candidate order, match counts)."""
+import numpy as np
+import pytest
+
+import oracle
+
+BOUNDS = (0.0, 0.0, 640.0, 480.0)
+
+
+def _frame_keys(synth, cfg='S1', idx=0):
+    g, _ = synth.frame(cfg, idx)
+    k, d = oracle.OrbOracle().extract(g)
+    return k, d
+
+
+def _scenario(synth, seed=0, n_extra=300, claims_all=True):
+    """Frame = ORB of S1/0; queries = ORB of S1/1 treated as projected map points (same scene, small motion) plus noise points."""
+    rng = np.random.RandomState(seed)
+    k0, d0 = _frame_keys(synth, 'S1', 0)
+    k1, d1 = _frame_keys(synth, 'S1', 1)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    n = len(k1) + n_extra
+    q = np.zeros(n, oracle.PROJ_QUERY_DTYPE)
+    lvl = np.concatenate([k1['octave'], rng.randint(0, 8, n_extra)]).astype(np.int32)
+    q['u'] = np.concatenate([k1['x'] + rng.normal(0, 1.0, len(k1)), rng.uniform(-20, 660, n_extra)]).astype(np.float32)
+    q['v'] = np.concatenate([k1['y'] + rng.normal(0, 1.0, len(k1)), rng.uniform(-20, 500, n_extra)]).astype(np.float32)
+    base_r = np.where(rng.rand(n) > 0.5, np.float32(2.5), np.float32(4.0)).astype(np.float32) * np.float32(3.0)
+    q['r'] = (base_r * sf[lvl]).astype(np.float32)
+    q['min_level'] = lvl - 1; q['max_level'] = lvl
+    q['ur'] = (q['u'] - rng.uniform(5, 40, n)).astype(np.float32)
+    q['claims'] = 1 if claims_all else (rng.rand(n) > 0.3)
+    qd = np.concatenate([d1, rng.randint(0, 256, (n_extra, 32)).astype(np.uint8)])
+    uright = np.where(rng.rand(len(k0)) > 0.4, k0['x'] - rng.uniform(5, 40, len(k0)), -1).astype(np.float32)
+    claimed = (rng.rand(len(k0)) < 0.1).astype(np.uint8)
+    return k0, d0, uright, claimed, q, qd
+
+
+def test_oracle_grid_and_area(synth):
+    k, _ = _frame_keys(synth)
+    cnt, items = oracle.grid_build(k, BOUNDS)
+    px = np.floor((k['x'] - 0) * np.float32(64 / 640.0) + 0.5).astype(int); py = np.floor((k['y'] - 0) * np.float32(48 / 480.0) + 0.5).astype(int)
+    inside = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    assert cnt.sum() == inside.sum() == len(items)
+    assert np.array_equal(np.sort(items), np.nonzero(inside)[0])
+    start = np.concatenate([[0], np.cumsum(cnt)])
+    for c in np.nonzero(cnt > 1)[0][:50]:
+        assert np.all(np.diff(items[start[c]:start[c + 1]]) > 0)          # push_back order = index order
+    rng = np.random.RandomState(1)
+    for _ in range(200):
+        x, y, r = rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(1, 60)
+        lo, hi = (-1, -1) if rng.rand() < 0.3 else (int(rng.randint(0, 5)), int(rng.randint(3, 8)))
+        got = oracle.features_in_area(k, BOUNDS, x, y, r, lo, hi)
+        ok = inside & (np.abs(k['x'] - np.float32(x)) < np.float32(r)) & (np.abs(k['y'] - np.float32(y)) < np.float32(r))
+        if lo > 0 or hi >= 0:
+            ok &= (k['octave'] >= lo)
+            if hi >= 0:
+                ok &= (k['octave'] <= hi)
+        assert np.array_equal(np.sort(got), np.nonzero(ok)[0])
+        cell = px[got] * 48 + py[got]
+        assert np.all(np.diff(cell) >= 0)                                   # ix outer, iy inner
+
+
+def test_oracle_greedy_conflict():
+    # three keypoints at one spot with descriptors at distance 0 / 8 / 16 from the query descriptor; three identical queries
+    keys = np.zeros(3, oracle.KP_DTYPE); keys['x'] = [100, 101, 102]; keys['y'] = 100; keys['octave'] = [0, 1, 0]
+    qd = np.zeros((3, 32), np.uint8)
+    d = np.zeros((3, 32), np.uint8); d[1, 0] = 0xff; d[2, 0] = 0xff; d[2, 1] = 0xff
+    q = np.zeros(3, oracle.PROJ_QUERY_DTYPE); q['u'] = 101; q['v'] = 100; q['r'] = 10; q['min_level'] = -1; q['max_level'] = -1; q['claims'] = 1
+    idx, dist, n = oracle.search_projection(keys, None, d, BOUNDS, q, qd, mode=1, th_dist=100)
+    assert idx.tolist() == [0, 1, 2] and dist.tolist() == [0, 8, 16] and n == 3
+    q['claims'] = 0                                                         # without observations nothing is ever claimed
+    idx, dist, n = oracle.search_projection(keys, None, d, BOUNDS, q, qd, mode=1, th_dist=100)
+    assert idx.tolist() == [0, 0, 0]
+    q['claims'] = 1                                                         # mode 0: best 0 / second 16 at the same level -> ratio ok
+    idx, _, _ = oracle.search_projection(keys, None, d, BOUNDS, q[:1], qd[:1], mode=0, th_dist=100, nnratio=0.6)
+    assert idx.tolist() == [0]
+    d[0, 0] = 0x0f                                                          # best 4 (level 0), second 8 (level 1): ratio not applied
+    idx, _, _ = oracle.search_projection(keys, None, d, BOUNDS, q[:1], qd[:1], mode=0, th_dist=100, nnratio=0.3)
+    assert idx.tolist() == [0]
+    keys['octave'] = 0                                                      # same level now: 4 > 0.3 * 8 -> rejected
+    idx, _, _ = oracle.search_projection(keys, None, d, BOUNDS, q[:1], qd[:1], mode=0, th_dist=100, nnratio=0.3)
+    assert idx.tolist() == [-1]
+
+
+@pytest.mark.gpu
+def test_gpu_grid_and_area(hvo, synth):
+    k, d = _frame_keys(synth)
+    pm = hvo.ProjectionMatcher()
+    pm.set_frame(k, None, d, *BOUNDS)
+    cs, items = pm.grid()
+    cnt, oitems = oracle.grid_build(k, BOUNDS)
+    assert np.array_equal(np.diff(cs), cnt) and np.array_equal(items, oitems)
+    rng = np.random.RandomState(2)
+    for _ in range(60):
+        x, y, r = rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(1, 80)
+        lo, hi = (-1, -1) if rng.rand() < 0.3 else (int(rng.randint(0, 5)), int(rng.randint(3, 8)))
+        assert np.array_equal(pm.GetFeaturesInArea(x, y, r, lo, hi), oracle.features_in_area(k, BOUNDS, x, y, r, lo, hi))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode,claims_all,seed', [(0, True, 0), (1, True, 1), (0, False, 2), (1, False, 3)])
+def test_gpu_search_projection_bit_exact(hvo, synth, mode, claims_all, seed):
+    k0, d0, ur, claimed, q, qd = _scenario(synth, seed, claims_all=claims_all)
+    pm = hvo.ProjectionMatcher()
+    pm.set_frame(k0, ur, d0, *BOUNDS)
+    idx, dist, n = pm.search(q, qd, claimed, mode, 100, 0.8)
+    oidx, odist, on = oracle.search_projection(k0, ur, d0, BOUNDS, q, qd, claimed, mode, 100, 0.8)
+    assert n == on and np.array_equal(idx, oidx) and np.array_equal(dist[idx >= 0], odist[oidx >= 0])
+    assert n > 300                                                          # the scenario really matches
+    assert not np.any(claimed[idx[idx >= 0]])
+    if claims_all:
+        m = idx[idx >= 0]
+        assert len(np.unique(m)) == len(m)                                  # every keypoint taken at most once
+
+
+@pytest.mark.gpu
+def test_gpu_search_projection_conflict_chain(hvo):
+    # 40 identical queries compete for 40 keypoints whose descriptors are at distance 0, 1, 2, ...: query i must end on keypoint i,
+    # which the fixed-point iteration reaches one query per round
+    n = 40
+    keys = np.zeros(n, oracle.KP_DTYPE); keys['x'] = 300 + 0.1 * np.arange(n); keys['y'] = 200
+    d = np.zeros((n, 32), np.uint8)
+    for i in range(n):
+        bits = np.zeros(256, np.uint8); bits[:i] = 1
+        d[i] = np.packbits(bits)
+    q = np.zeros(n, oracle.PROJ_QUERY_DTYPE); q['u'] = 302; q['v'] = 200; q['r'] = 20; q['min_level'] = -1; q['max_level'] = -1; q['claims'] = 1
+    qd = np.zeros((n, 32), np.uint8)
+    pm = hvo.ProjectionMatcher()
+    pm.set_frame(keys, None, d, *BOUNDS)
+    idx, dist, nm = pm.search(q, qd, None, 1, 100, 0.6)
+    oidx, odist, on = oracle.search_projection(keys, None, d, BOUNDS, q, qd, None, 1, 100, 0.6)
+    assert np.array_equal(idx, np.arange(n)) and np.array_equal(idx, oidx) and np.array_equal(dist, odist) and nm == on == n
+    assert pm.rounds() >= n
+
+
+@pytest.mark.gpu
+def test_gpu_search_projection_edge_cases(hvo, synth):
+    pm = hvo.ProjectionMatcher()
+    k, d = _frame_keys(synth)
+    q = np.zeros(3, oracle.PROJ_QUERY_DTYPE); q['u'] = [-500, 320, 5000]; q['v'] = [240, -900, 240]; q['r'] = 5; q['min_level'] = -1; q['max_level'] = -1
+    qd = np.zeros((3, 32), np.uint8)
+    pm.set_frame(k[:0], None, d[:0], *BOUNDS)                                # empty frame
+    idx, dist, n = pm.search(q, qd)
+    assert n == 0 and np.all(idx == -1)
+    pm.set_frame(k, None, d, *BOUNDS)
+    idx, dist, n = pm.search(q, qd)                                        # windows outside the image
+    assert n == 0 and np.all(idx == -1)
+    idx, dist, n = pm.search(q[:0], qd[:0])                                # no queries
+    assert n == 0 and len(idx) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_match_candidates(hvo, synth):
+    rng = np.random.RandomState(5)
+    q, t = synth.descriptors_S4(nq=300, nt=2000, seed=21, planted=100, ties=20)
+    lens = rng.randint(0, 70, 300); lens[:5] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.randint(0, 2000, off[-1]).astype(np.int32)
+    pm = hvo.ProjectionMatcher()
+    got = pm.match_candidates(q, t, off, cand)
+    assert np.array_equal(got, oracle.match_candidates(q, t, off, cand))
+
+
+def _mirror_inputs(synth, seed):
+    k0, d0, ur, claimed, q, qd = _scenario(synth, seed, n_extra=100, claims_all=False)
+    rng = np.random.RandomState(seed + 100)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    M = len(q)
+    lvl = q['max_level'].copy()
+    MPs = dict(proj_x=q['u'].copy(), proj_y=q['v'].copy(), proj_xr=q['ur'].copy(), view_cos=rng.uniform(0.99, 1.0, M).astype(np.float32),
+               level=lvl, in_view=rng.rand(M) > 0.1, bad=rng.rand(M) < 0.05, has_obs=q['claims'].astype(bool), desc=qd)
+    F = dict(keys_un=k0, uright=ur, desc=d0, bounds=BOUNDS, scale_factors=sf, mappoint=np.full(len(k0), -1, np.int64), claimed=claimed.astype(bool))
+    return F, MPs, sf
+
+
+@pytest.mark.gpu
+def test_orbmatcher_search_by_projection_mirror(hvo, synth):
+    F, MPs, sf = _mirror_inputs(synth, 7)
+    th = 3.0
+    # the reference loop, written out on top of the oracle primitive
+    use = MPs['in_view'] & ~MPs['bad']
+    sel = np.nonzero(use)[0]
+    r = np.where(MPs['view_cos'][sel] > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32) * np.float32(th)
+    q = np.zeros(len(sel), oracle.PROJ_QUERY_DTYPE)
+    q['u'] = MPs['proj_x'][sel]; q['v'] = MPs['proj_y'][sel]; q['r'] = (r * sf[MPs['level'][sel]]).astype(np.float32)
+    q['min_level'] = MPs['level'][sel] - 1; q['max_level'] = MPs['level'][sel]; q['ur'] = MPs['proj_xr'][sel]; q['claims'] = MPs['has_obs'][sel]
+    oidx, _, on = oracle.search_projection(F['keys_un'], F['uright'], F['desc'], BOUNDS, q, MPs['desc'][sel], F['claimed'].astype(np.uint8), 0, 100, 0.8)
+    m = hvo.ORBmatcher(0.8, True)
+    n, match = m.SearchByProjection(F, MPs, th)
+    assert n == on and np.array_equal(match[sel], oidx) and np.all(match[~use] == -1)
+    taken = match[match >= 0]
+    assert np.all(F['mappoint'][taken] >= 0)
+
+
+@pytest.mark.gpu
+def test_orbmatcher_search_by_projection_last_mirror(hvo, synth):
+    F, MPs, sf = _mirror_inputs(synth, 9)
+    rng = np.random.RandomState(11)
+    n = len(MPs['proj_x'])
+    last = dict(u=MPs['proj_x'], v=MPs['proj_y'], ur=MPs['proj_xr'], octave=np.clip(MPs['level'], 0, 7), has_obs=MPs['has_obs'], desc=MPs['desc'],
+                angle=rng.uniform(0, 360, n).astype(np.float32))
+    m = hvo.ORBmatcher(0.9, True)
+    nm, idx = m.SearchByProjectionLast(F, last, th=7.0)
+    q = np.zeros(n, oracle.PROJ_QUERY_DTYPE)
+    q['u'] = last['u']; q['v'] = last['v']; q['ur'] = last['ur']; q['r'] = (np.float32(7.0) * sf[last['octave']]).astype(np.float32)
+    q['min_level'] = last['octave'] - 1; q['max_level'] = last['octave'] + 1; q['claims'] = last['has_obs']
+    claimed0 = _mirror_inputs(synth, 9)[0]['claimed']
+    oidx, _, on = oracle.search_projection(F['keys_un'], F['uright'], F['desc'], BOUNDS, q, last['desc'], claimed0.astype(np.uint8), 1, 100, 0.9)
+    assert np.array_equal(idx, oidx)
+    assert 0 < nm <= on                                                    # the rotation histogram only removes matches
