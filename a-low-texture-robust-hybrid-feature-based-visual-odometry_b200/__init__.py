@@ -806,6 +806,32 @@ class LSDmatcher:
         out[ok] = idx[ok, 0]
         return out
 
+    def SearchDouble(self, ldesc1, ldesc2):
+        """LSDmatcher::SearchDouble(InitialFrame, CurrentFrame, LineMatches) (src/LSDmatcher.cpp:903-940): FrameBFMatch in both
+        directions (the reference runs them on two threads), kept where they agree.  Returns (nmatches, LineMatches)."""
+        if len(ldesc1) == 0 or len(ldesc2) == 0:
+            return 0, np.full(len(ldesc1), -1, np.int32)
+        m12 = self.FrameBFMatch(ldesc1, ldesc2, self.TH_LOW)
+        m21 = self.FrameBFMatch(ldesc2, ldesc1, self.TH_LOW)
+        ok = m12 >= 0
+        ok[ok] = m21[m12[ok]] == np.nonzero(ok)[0]
+        out = np.where(ok, m12, -1).astype(np.int32)
+        return int(ok.sum()), out
+
+    def SearchByDescriptor(self, ldesc_kf, ldesc_cur):
+        """Matching part of LSDmatcher::SearchByDescriptor(pKF, currentF, ...) (src/LSDmatcher.cpp:522-559): knn-2 of the key
+        frame's descriptors in the current frame, accepted when d0 / d1 < 1 / 1.5.  Returns match [len(ldesc_cur)]: key-frame
+        line index per current-frame line (later queries overwrite earlier ones, as in the reference) or -1."""
+        out = np.full(len(ldesc_cur), -1, np.int32)
+        if len(ldesc_kf) == 0 or len(ldesc_cur) < 2:
+            return out
+        idx, dist = self._bf.knnMatch2(ldesc_kf, ldesc_cur)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            ratio = (dist[:, 0].astype(np.float32) / dist[:, 1].astype(np.float32)).astype(np.float64)
+        for q in np.nonzero(ratio < np.float32(1.0) / np.float32(1.5))[0]:
+            out[idx[q, 0]] = q
+        return out
+
 
 # ---- Frame-level front-end ----------------------------------------------------------------------------------------
 STAGE_ORB, STAGE_LINES, STAGE_PLANES, STAGE_NORMALS, STAGE_ALL = 1, 2, 4, 8, 15

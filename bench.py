@@ -36,8 +36,10 @@ ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # 
 CAM = dict(fx=535.4, fy=539.2, cx=320.1, cy=247.6)                             # TUM3.yaml:8-11
 DEPTH_FACTOR, BF, NLINES = 1.0 / 5000.0, 40.0, 200                             # TUM3.yaml:34, Camera.bf, LINE.nFeatures
 ORACLE_CAM = (DEPTH_FACTOR, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'])
+ORACLE_STAGES = 15 | 16  # ORB | lines | planes | normals | cullingLine after the line extractor (what Frame::Frame runs)
 STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + rBRIEF + RGB-D depth lookup',
-          'lines: LSD (blur, 0.8 resize, gradient, ordered region growing, rectangles) + KeyLines + top-200 + LBD + line functions',
+          'lines: LSD (blur, 0.8 resize, gradient, ordered region growing, rectangles) + KeyLines + top-200 + LBD + line functions + '
+          'Frame::cullingLine (merge, rebuild, LBD again)',
           'planes: depth back-projection + 10x10 block fits + AHC merging + block erosion + ordered pixel flood fill + last merge',
           'normals: 3x subsampled cloud + integral-image normals (PCL AVERAGE_3D_GRADIENT restatement)']
 # algorithmic bytes per 640x480 frame of the HBM-bound kernels
@@ -136,11 +138,11 @@ def cpu_baseline(gray, depth, target_s=15.0):
     cores = os.cpu_count() or 1
     ns = min(len(gray), 2 * cores)
     g, d = gray[:ns], depth[:ns]
-    oracle.frontend_batch(g[:cores], d[:cores], ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)  # warm-up / page-in
+    oracle.frontend_batch(g[:cores], d[:cores], ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB)  # warm-up / page-in
     n, dt, counts = 0, 0.0, []
     t0 = time.perf_counter()
     while dt < target_s:  # bounded sample: whole passes over the same frames until ~target_s of CPU work
-        counts.append(oracle.frontend_batch(g, d, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB).mean(axis=0))
+        counts.append(oracle.frontend_batch(g, d, ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB).mean(axis=0))
         n += ns
         dt = time.perf_counter() - t0
     c = np.mean(counts, axis=0)
@@ -159,10 +161,10 @@ def run_reference(args, rank, world):
     sample = max(cores, min(args.batch, 2 * cores))
     gray, depth = make_frames(sample)
     for _ in range(args.warmup):
-        oracle.frontend_batch(gray, depth, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)
+        oracle.frontend_batch(gray, depth, ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB)
     t = time.perf_counter()
     for _ in range(args.steps):
-        oracle.frontend_batch(gray, depth, ORACLE_CAM, nthreads=cores, nlines=NLINES, **ORB)
+        oracle.frontend_batch(gray, depth, ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB)
     dt = time.perf_counter() - t
     v = sample * args.steps / dt
     print(json.dumps({
@@ -212,7 +214,7 @@ def main():
 
     B, W, H = args.batch, 640, 480
     gray, depth = make_frames(B, start=rank * B)  # every rank gets its own frames (frame-sharded, weak scaling)
-    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages,
+    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
                            max_batch=B, device=local_rank, nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'],
                            nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
     dev = torch.device('cuda', local_rank)
@@ -377,7 +379,7 @@ def main():
                d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())), ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps)
 
     # ---- single-frame latency through the host call (p50) ----
-    fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages,
+    fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
                             max_batch=1, device=local_rank)
     out1 = fe1.alloc_host(1)
     lat = []

@@ -114,7 +114,11 @@ int orc_surface_normals(const uint16_t* depth16, int W, int H, float depth_facto
                         float max_depth_change_factor, float smoothing_size, float* out8, float* dist_map_out);
 
 // LINEextractor::operator() (src/LineExtractor.cpp:329-380) on one frame; keylines: cap x 68 B, desc: cap x 32 B.
-int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keylines, uint8_t* desc, int cap) {
+int orc_cull_lines(const void* keylines_in, const double* linefunc_in, int n, int w, int h, double dis, double angle_deg,
+                   double endpoint_dis, void* keylines_out, int32_t* group_of_out);
+
+// cull != 0: followed by Frame::cullingLine(im, 5, 2.5, 15, 30) (src/Frame.cc:939), second LBD pass included
+int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keylines, uint8_t* desc, int cap, int cull) {
     std::vector<float> seg((size_t)4 * 16384);
     int n = orc_lsd_detect(gray, w, h, seg.data(), 16384, nullptr, nullptr, nullptr);
     if (n > 16384) n = 16384;
@@ -135,17 +139,31 @@ int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keyline
         kl.swap(sel);
         n = nfeat;
     }
+    std::vector<uint8_t> d((size_t)(n > 0 ? n : 1) * 32);
+    if (n > 0) orc_lbd_compute(gray, w, h, kl.data(), n, d.data(), nullptr);
+    if (cull && n > 0) {
+        std::vector<double> lv((size_t)n * 3);
+        for (int i = 0; i < n; ++i) {  // mvKeyLineFunctions (LineExtractor.cpp:365-377)
+            float e[4];
+            std::memcpy(e, &kl[(size_t)i * 68 + 28], 16);
+            const double sx = e[0], sy = e[1], ex = e[2], ey = e[3];
+            const double l0 = sy - ey, l1 = ex - sx, l2 = sx * ey - sy * ex, nn = std::sqrt(l0 * l0 + l1 * l1);
+            lv[3 * i] = l0 / nn; lv[3 * i + 1] = l1 / nn; lv[3 * i + 2] = l2 / nn;
+        }
+        std::vector<uint8_t> kl2((size_t)n * 68);
+        n = orc_cull_lines(kl.data(), lv.data(), n, w, h, 5.0, 2.5, 15.0, kl2.data(), nullptr);
+        kl.swap(kl2);
+        if (n > 0) orc_lbd_compute(gray, w, h, kl.data(), n, d.data(), nullptr);
+    }
     const int m = n < cap ? n : cap;
     if (m > 0) {
-        std::vector<uint8_t> d((size_t)n * 32);
-        orc_lbd_compute(gray, w, h, kl.data(), n, d.data(), nullptr);
         std::memcpy(keylines, kl.data(), (size_t)m * 68);
         std::memcpy(desc, d.data(), (size_t)m * 32);
     }
     return n;
 }
 
-// stages: bit 0 ORB, bit 1 lines, bit 2 planes, bit 3 normals.  counts4[f] = {keypoints, lines, planes, normals}.
+// stages: bit 0 ORB, bit 1 lines, bit 2 planes, bit 3 normals, bit 4 cullingLine after the line extractor.  counts4[f] = {keypoints, lines, planes, normals}.
 void orc_frontend_batch(const uint8_t* gray, const uint16_t* depth, int nframes, int w, int h, int nthreads, int stages,
                         int nfeatures, float scale, int nlevels, int ini_th, int min_th, int nlines, float depth_factor, float fx,
                         float fy, float cx, float cy, int32_t* counts4) {
@@ -169,7 +187,7 @@ void orc_frontend_batch(const uint8_t* gray, const uint16_t* depth, int nframes,
                 int32_t* c = counts4 + 4 * (size_t)f;
                 c[0] = c[1] = c[2] = c[3] = 0;
                 if (stages & 1) { ex.extract(g, w, h, (size_t)w, k, d); c[0] = (int32_t)k.size(); }
-                if (stages & 2) c[1] = orc_line_extract(g, w, h, nlines, kl.data(), ld.data(), nlines);
+                if (stages & 2) c[1] = orc_line_extract(g, w, h, nlines, kl.data(), ld.data(), nlines, stages & 16);
                 if (stages & 4) c[2] = orc_plane_detect(dp, w, h, depth_factor, fx, fy, cx, cy, planes.data(), 64, mem.data());
                 if (stages & 8) c[3] = orc_surface_normals(dp, w, h, depth_factor, fx, fy, cx, cy, 0.05f, 10.0f, nrm.data(), dist.data());
             }

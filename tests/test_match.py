@@ -93,3 +93,23 @@ def test_knn2_query_sharding_property(hvo, synth):
     for i in range(3):
         assert np.array_equal(parts[i][0], idx[i::3]) and np.array_equal(parts[i][1], dist[i::3])
     bf.close()
+
+
+@pytest.mark.gpu
+def test_lsdmatcher_search_double_and_by_descriptor(hvo, synth):
+    """E7 / E9: two-way FrameBFMatch with cross-check (src/LSDmatcher.cpp:903-940) and SearchByDescriptor (:522-559)."""
+    a, b = synth.descriptors_S4(nq=180, nt=200, seed=31, planted=120, ties=6)
+    m = hvo.LSDmatcher(0.95, True)
+    n, lm = m.SearchDouble(a, b)
+    m12 = oracle.frame_bf_match(a, b, 0.95, 50)
+    m21 = oracle.frame_bf_match(b, a, 0.95, 50)
+    ref = np.array([j if j >= 0 and m21[j] == i else -1 for i, j in enumerate(m12)], np.int32)
+    assert np.array_equal(lm, ref) and n == int((ref >= 0).sum()) and n > 50
+    got = m.SearchByDescriptor(a, b)
+    idx, dist = oracle.knn2(a, b)
+    exp = np.full(len(b), -1, np.int32)
+    for q in range(len(a)):
+        if np.float32(dist[q, 0]) / np.float32(dist[q, 1]) < np.float32(1.0) / np.float32(1.5):
+            exp[idx[q, 0]] = q
+    assert np.array_equal(got, exp) and (exp >= 0).sum() > 50
+    assert m.SearchDouble(a[:0], b)[0] == 0
