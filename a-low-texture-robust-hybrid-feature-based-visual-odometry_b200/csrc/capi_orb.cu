@@ -1,5 +1,6 @@
 // C ABI for the ORB extractor (include/hvo_capi.h).  No torch types, no exceptions across the boundary.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -12,6 +13,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+static thread_local int g_stream_priority = 0;
+void set_next_stream_priority(int priority) { g_stream_priority = priority; }
+cudaError_t create_stream(cudaStream_t* s) { return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, g_stream_priority); }
+int smem_carveout_percent() {
+    // HVO_CARVEOUT (percent, -1 = leave the driver default) is a tuning aid; the default is chosen in DESIGN.md section 4
+    static const int pc = [] { const char* e = getenv("HVO_CARVEOUT"); return e ? atoi(e) : -1; }();
+    return pc;
 }
 }  // namespace hvo
 

@@ -3,6 +3,7 @@
 // ExtractLSD (LINEextractor::operator(), :895-903) and ComputePlanes (PlaneDetection + surface normals, :2104-2212)
 // on the same frame.  Here the frame (gray + raw 16-bit depth) is uploaded once and the three pipelines run on three
 // CUDA streams chained by events to a master stream, so a batch of frames is one call and one device-timed region.
+#include <cstdlib>
 #include <new>
 
 #include "hvo_common.cuh"
@@ -41,23 +42,20 @@ static int frame_launch(hvo_frame* h, const uint8_t* d_gray, const uint16_t* d_d
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
     HVO_CUDA(cudaEventRecord(h->fork, h->stream));
     int launches = 0;
-    if (h->p.stages & ST_ORB) {
-        cudaStream_t s = orb_stream(h->orb);
+    // launch order = placement order: the ordered (latency-bound) pipelines first
+    if (h->p.stages & ST_PLANE) {
+        cudaStream_t s = plane_stream(h->plane);
         HVO_CUDA(cudaStreamWaitEvent(s, h->fork, 0));
-        hvo_rgbd_params rg{h->p.depth_factor, h->p.bf};
-        int st = hvo_orb_extract_batch_device(h->orb, d_gray, n, o.kps, o.desc, o.kp_counts, d_depth, &rg, o.kp_depth, o.kp_uright);
+        int st = hvo_plane_detect_batch_device(h->plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
         if (st != HVO_OK) return st;
-        launches += hvo_orb_last_launches(h->orb);
+        launches += hvo_plane_last_launches(h->plane);
         if (host) {
-            const size_t c = (size_t)h->orb_cap;
-            HVO_CUDA(cudaMemcpyAsync(host->kp_counts, o.kp_counts, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->kps, o.kps, N * c * sizeof(hvo_keypoint), cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->desc, o.desc, N * c * 32, cudaMemcpyDeviceToHost, s));
-            if (host->kp_depth) HVO_CUDA(cudaMemcpyAsync(host->kp_depth, o.kp_depth, N * c * 4, cudaMemcpyDeviceToHost, s));
-            if (host->kp_uright) HVO_CUDA(cudaMemcpyAsync(host->kp_uright, o.kp_uright, N * c * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
         }
-        HVO_CUDA(cudaEventRecord(h->join[0], s));
-        HVO_CUDA(cudaStreamWaitEvent(h->stream, h->join[0], 0));
+        HVO_CUDA(cudaEventRecord(h->join[2], s));
+        HVO_CUDA(cudaStreamWaitEvent(h->stream, h->join[2], 0));
     }
     if (h->p.stages & ST_LINE) {
         cudaStream_t s = line_stream(h->line);
@@ -75,19 +73,23 @@ static int frame_launch(hvo_frame* h, const uint8_t* d_gray, const uint16_t* d_d
         HVO_CUDA(cudaEventRecord(h->join[1], s));
         HVO_CUDA(cudaStreamWaitEvent(h->stream, h->join[1], 0));
     }
-    if (h->p.stages & ST_PLANE) {
-        cudaStream_t s = plane_stream(h->plane);
+    if (h->p.stages & ST_ORB) {
+        cudaStream_t s = orb_stream(h->orb);
         HVO_CUDA(cudaStreamWaitEvent(s, h->fork, 0));
-        int st = hvo_plane_detect_batch_device(h->plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
+        hvo_rgbd_params rg{h->p.depth_factor, h->p.bf};
+        int st = hvo_orb_extract_batch_device(h->orb, d_gray, n, o.kps, o.desc, o.kp_counts, d_depth, &rg, o.kp_depth, o.kp_uright);
         if (st != HVO_OK) return st;
-        launches += hvo_plane_last_launches(h->plane);
+        launches += hvo_orb_last_launches(h->orb);
         if (host) {
-            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
+            const size_t c = (size_t)h->orb_cap;
+            HVO_CUDA(cudaMemcpyAsync(host->kp_counts, o.kp_counts, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->kps, o.kps, N * c * sizeof(hvo_keypoint), cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->desc, o.desc, N * c * 32, cudaMemcpyDeviceToHost, s));
+            if (host->kp_depth) HVO_CUDA(cudaMemcpyAsync(host->kp_depth, o.kp_depth, N * c * 4, cudaMemcpyDeviceToHost, s));
+            if (host->kp_uright) HVO_CUDA(cudaMemcpyAsync(host->kp_uright, o.kp_uright, N * c * 4, cudaMemcpyDeviceToHost, s));
         }
-        HVO_CUDA(cudaEventRecord(h->join[2], s));
-        HVO_CUDA(cudaStreamWaitEvent(h->stream, h->join[2], 0));
+        HVO_CUDA(cudaEventRecord(h->join[0], s));
+        HVO_CUDA(cudaStreamWaitEvent(h->stream, h->join[0], 0));
     }
     if (h->p.stages & ST_NORMALS) {
         cudaStream_t s = normals_stream(h->normals);
@@ -120,17 +122,28 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
     h->p = *p; h->device = device; h->width = width; h->height = height; h->max_batch = max_batch;
     h->d_out = hvo_frame_outputs{};
     int st = HVO_OK;
+    // lines and planes are chains of long latency-bound kernels (one warp / CTA per frame): they get the high-priority
+    // streams so they are resident from the start; ORB and normals (streaming kernels with large grids) fill in around them
+    int prio_lo = 0, prio_hi = 0;
+    HVO_CUDA(cudaSetDevice(device));
+    HVO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* env_prio = getenv("HVO_FRAME_PRIORITIES");  // tuning aid: "0" = all streams at the default priority
+    if (env_prio && env_prio[0] == '0') prio_lo = prio_hi = 0;
+    set_next_stream_priority(prio_lo);
     if (st == HVO_OK && (p->stages & ST_ORB)) st = hvo_orb_create(&p->orb, width, height, max_batch, device, &h->orb);
+    set_next_stream_priority(prio_hi);
     if (st == HVO_OK && (p->stages & ST_LINE)) st = hvo_line_create(&p->line, width, height, max_batch, device, &h->line);
     if (st == HVO_OK && h->line) st = hvo_line_set_culling(h->line, p->line_cull);
     if (st == HVO_OK && (p->stages & ST_PLANE)) {
         hvo_plane_params pp{p->fx, p->fy, p->cx, p->cy, p->depth_factor};
         st = hvo_plane_create(&pp, width, height, max_batch, device, &h->plane);
     }
+    set_next_stream_priority(prio_lo);
     if (st == HVO_OK && (p->stages & ST_NORMALS)) {
         hvo_normals_params np{p->fx, p->fy, p->cx, p->cy, p->depth_factor, 0.05f, 10.0f};  // Frame.cc:2179-2180
         st = hvo_normals_create(&np, width, height, max_batch, device, &h->normals);
     }
+    set_next_stream_priority(0);
     if (st != HVO_OK) { hvo_frame_destroy(h); return st; }
     h->orb_cap = h->orb ? hvo_orb_capacity(h->orb) : 0;
     h->max_lines = h->line ? hvo_line_max_lines(h->line) : 0;

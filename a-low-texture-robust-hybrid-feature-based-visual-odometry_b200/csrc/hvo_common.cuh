@@ -31,6 +31,22 @@ void set_error(const char* fmt, ...);
         }                                                   \
     } while (0)
 
+// Kernels of different pipelines only share an SM when they ask for the same L1/shared-memory split, so every
+// long-running kernel is pinned to one carveout (percent of the 256 KB unified array given to shared memory).
+int smem_carveout_percent();
+template <class K>
+static inline void pin_carveout(K kernel) {
+    const int pc = smem_carveout_percent();
+    if (pc >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pc);
+}
+
+// Every handle owns one non-blocking stream.  hvo_frame gives the pipelines whose kernels are latency-bound (lines,
+// planes) a higher stream priority than the streaming pipelines (ORB, normals), so the long ordered kernels are placed
+// first and the streaming kernels fill the remaining warp slots: set_next_stream_priority applies to the calling
+// thread's next create_stream calls (0 = default).
+void set_next_stream_priority(int priority);
+cudaError_t create_stream(cudaStream_t* s);
+
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

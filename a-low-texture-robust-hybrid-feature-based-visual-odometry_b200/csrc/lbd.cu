@@ -244,7 +244,8 @@ int hvo_lbd_create(int width, int height, int max_batch, int max_lines, int devi
     do {
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
         HVO_TRY(cudaSetDevice(device));
-        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        pin_carveout(k_lbd_grad); pin_carveout(k_lbd_describe);
+        HVO_TRY(create_stream(&h->stream));
         HVO_TRY(cudaEventCreate(&h->tev[0]));
         HVO_TRY(cudaEventCreate(&h->tev[1]));
         const size_t B = (size_t)max_batch, px = (size_t)width * height;

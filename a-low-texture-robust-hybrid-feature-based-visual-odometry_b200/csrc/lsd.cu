@@ -938,7 +938,8 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
     do {
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
         HVO_TRY(cudaSetDevice(device));
-        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        pin_carveout(k_lsd_prep); pin_carveout(k_lsd_order); pin_carveout(k_lsd_grow); pin_carveout(k_line_keylines); pin_carveout(k_line_cull);
+        HVO_TRY(create_stream(&h->stream));
         for (auto& e : h->tev) HVO_TRY(cudaEventCreate(&e));
         if (st != HVO_OK) break;
         for (auto& e : h->sev) HVO_TRY(cudaEventCreate(&e));

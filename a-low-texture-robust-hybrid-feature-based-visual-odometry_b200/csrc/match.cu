@@ -125,7 +125,7 @@ int hvo_matcher_create(int device, hvo_matcher** out) {
     if (!m) { set_error("out of host memory"); return HVO_ERR_ARG; }
     m->device = device;
     HVO_CUDA(cudaSetDevice(device));
-    HVO_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    HVO_CUDA(create_stream(&m->stream));
     for (auto& e : m->tev) HVO_CUDA(cudaEventCreate(&e));
     HVO_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = m;

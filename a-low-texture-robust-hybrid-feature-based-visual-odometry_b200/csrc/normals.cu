@@ -217,7 +217,8 @@ int hvo_normals_create(const hvo_normals_params* p, int width, int height, int m
     h->n_out = (g.cw / 2) * (g.ch / 2);
     const size_t B = (size_t)max_batch, np = (size_t)g.cw * g.ch;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    pin_carveout(k_sn_cloud); pin_carveout(k_sn_rowscan); pin_carveout(k_sn_colscan); pin_carveout(k_sn_chamfer); pin_carveout(k_sn_normals);
+    if (e == cudaSuccess) e = create_stream(&h->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&h->tev[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&h->tev[1]);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_depth, B * width * height * 2);

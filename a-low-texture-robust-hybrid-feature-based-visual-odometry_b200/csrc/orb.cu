@@ -834,7 +834,8 @@ int hvo_orb::init() {
 
     // ---- CUDA resources ----
     HVO_CUDA(cudaSetDevice(device));
-    HVO_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    pin_carveout(k_resize); pin_carveout(k_fast_cells); pin_carveout(k_octree); pin_carveout(k_blur); pin_carveout(k_describe);
+    HVO_CUDA(create_stream(&stream));
     for (auto& e : ev) HVO_CUDA(cudaEventCreate(&e));
     for (auto& e : tev) HVO_CUDA(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch;

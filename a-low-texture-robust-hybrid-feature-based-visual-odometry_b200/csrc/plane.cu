@@ -175,7 +175,6 @@ struct AhcArgs {
     double* cand;            // [B][Nb]
     uint32_t* ulog;          // [B][Nb]  union log of the first clustering
     uint16_t* cnode;         // [B][Nb]  node of candidate i
-    float* dist;             // [B][h*w]
     uint32_t* queue;         // [B][qcap]
     int32_t* membership;     // [B][h*w]   working membershipImg, final labels on exit
     double* planes7;         // [B][planes_stride][7]
@@ -729,7 +728,25 @@ __global__ void __launch_bounds__(32, HVO_AHC_MINBLOCKS) k_plane_cluster(AhcArgs
 }
 
 // ---- kernel 2: membership image, refinement seeds and the ordered pixel flood fill.  One CTA of 256 per frame. ----
-static const int kFloodThreads = 256, kFloodBuckets = 2048;
+// A step takes up to 256 consecutive queue entries, one per thread, each with its 4 neighbour visits (1024 visits in
+// flight per step).  A visit reads only the state of the pixel it visits, so visits of one step are independent except
+// where two of them hit the same pixel: those are applied in queue order by a hash-bucket tournament (a visit goes when it
+// is the lowest pending visit of its bucket; equal pixels share a bucket, so the earlier one always went before).
+// The reference's distance map is not stored: for a pixel outside the member blocks it always equals the distance to the
+// plane the pixel is currently labelled with (FLT_MAX while unlabelled), which is recomputed when needed.
+static const int kFloodThreads = 256, kFloodBuckets = 4096;
+
+struct FloodPix { double px, py, z; };
+__device__ __forceinline__ bool flood_point(const AhcArgs& A, const uint16_t* D, int cIdx, int cx, int cy, FloodPix& P) {
+    P.z = (double)D[cIdx] * A.cam.factor;
+    if (P.z == 0) return false;
+    P.px = ((double)cx - A.cam.cx) * P.z / A.cam.fx;
+    P.py = ((double)cy - A.cam.cy) * P.z / A.cam.fy;
+    return true;
+}
+__device__ __forceinline__ float flood_dist(const double* p, const FloodPix& P) {
+    return (float)fabs(p[0] * (P.px - p[3]) + p[1] * (P.py - p[4]) + p[2] * (P.z - p[5]));
+}
 
 __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -738,29 +755,33 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
     __shared__ int s_head, s_tail, s_overflow;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Nw = A.Nw, Nh = A.Nh, Nb = Nw * Nh, W = A.w, H = A.h, npix = W * H;
-    double* pl = (double*)smem_raw;                                 // [max_ext][7]
-    int16_t* blkmap = (int16_t*)(smem_raw + (size_t)A.max_ext * 56);  // [Nb]
-    uint16_t* ext = (uint16_t*)(blkmap + Nb);                       // [max_ext]
+    double* pl = (double*)smem_raw;                                   // [max_ext][8]: normal, center, mse, 9 mse + 1e-5
+    int16_t* blkmap = (int16_t*)(smem_raw + (size_t)A.max_ext * 64);  // [Nb]
+    uint16_t* ext = (uint16_t*)(blkmap + Nb);                         // [max_ext]
     const uint16_t* D = A.depth + (size_t)f * npix;
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
-    float* dist = A.dist + (size_t)f * npix;
     uint32_t* queue = A.queue + (size_t)f * A.qcap;
     int32_t* mem = A.membership + (size_t)f * npix;
     const long long t_start = clock64();
     const int ne = A.g_ctl[8 * f + 0];
-    for (int i = tid; i < ne * 7; i += kFloodThreads) pl[i] = A.g_pl[(size_t)f * A.max_ext * 7 + i];
-    for (int i = tid; i < ne; i += kFloodThreads) ext[i] = A.g_ext[(size_t)f * A.max_ext + i];
+    for (int i = tid; i < ne; i += kFloodThreads) {
+        const double* g = A.g_pl + ((size_t)f * A.max_ext + i) * 7;
+        double* p = pl + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) p[k] = g[k];
+        p[7] = 9 * g[6] + 1e-5;
+        ext[i] = A.g_ext[(size_t)f * A.max_ext + i];
+    }
     for (int b = tid; b < Nb; b += kFloodThreads) blkmap[b] = A.g_blkmap[(size_t)f * Nb + b];
     for (int i = tid; i < kFloodBuckets; i += kFloodThreads) s_bucket[i] = 0u;
     if (tid == 0) { s_head = 0; s_tail = 0; s_overflow = 0; }
     __syncthreads();
-    // membershipImg: block label inside eroded member blocks, -1 elsewhere; distMap = FLT_MAX
+    // membershipImg: block label inside eroded member blocks, -1 elsewhere
     for (int y = wid; y < H; y += kFloodThreads / 32) {
         const int by = y / 10;
         for (int x = lane; x < W; x += 32) {
             const int bx = x / 10;
             mem[(size_t)y * W + x] = (by < Nh && bx < Nw) ? (int)blkmap[by * Nw + bx] : -1;
-            dist[(size_t)y * W + x] = 3.402823466e+38f;
         }
     }
     // refinement seeds, in block scan order (AHCPlaneFitter.hpp:545-583)
@@ -797,75 +818,103 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
     }
     __syncthreads();
     const long long t_seeds = clock64();
-    // ---- floodFill (AHCPlaneFitter.hpp:428-476): FIFO over (pixel, plane) seeds.  64 queue entries x 4 neighbours per
-    // step; visits of the same pixel inside one step are applied in queue order (hash-bucket tournament: a lane goes when
-    // it is the lowest pending lane of its bucket, so an equal pixel with a lower queue position always went before) ----
-    const int e = tid >> 2, it = tid & 3;
+    // ---- floodFill (AHCPlaneFitter.hpp:428-476): FIFO over (pixel, plane) seeds ----
+#ifdef HVO_FLOOD_PROF
+    int st_steps = 0, st_rounds = 0; long long st_t0 = 0, st_load = 0, st_tour = 0, st_comp = 0;
+#endif
     unsigned tag = 1;
     uint32_t q_next = 0;      // queue entry of the next step, fetched one step ahead when it already exists
     bool have_next = false;
     while (true) {
         const int head = s_head, tail = s_tail;
         if (head >= tail) break;
-        const int nbat = min(kFloodThreads / 4, tail - head);
-        bool valid = e < nbat;
-        int cIdx = -1, plid = 0;
-        bool ok = false;
-        float cdist = -1.f;
-        int trail0 = 0;
-        float dist0 = 0.f;
-        const uint32_t q = valid ? (have_next ? q_next : queue[head + e]) : 0u;
-        have_next = head + nbat + e < tail;
-        if (have_next) q_next = queue[head + nbat + e];
-        if (valid) {
+        const int nbat = min(kFloodThreads, tail - head);
+#ifdef HVO_FLOOD_PROF
+        ++st_steps; st_t0 = clock64();
+#endif
+        const bool have = tid < nbat;
+        const uint32_t q = have ? (have_next ? q_next : queue[head + tid]) : 0u;
+        have_next = head + nbat + tid < tail;
+        if (have_next) q_next = queue[head + nbat + tid];
+        const int plid = (int)(q >> 20);
+        int cI[4], trail0[4];
+        float cdist[4];
+        unsigned okm = 0, pend = 0, pushm = 0;  // bit d: visit d passes the plane test / is pending / pushes a new seed
+        if (have) {
             const int sIdx = (int)(q & 0xfffffu);
-            plid = (int)(q >> 20);
             const int sy = sIdx / W, sx = sIdx - sy * W;
-            int nb4[4], c = 0;
-            if (sx > 0) nb4[c++] = sIdx - 1;
-            if (sx < W - 1) nb4[c++] = sIdx + 1;
-            if (sy > 0) nb4[c++] = sIdx - W;
-            if (sy < H - 1) nb4[c++] = sIdx + W;
-            valid = it < c;
-            if (valid) {
-                cIdx = it == 0 ? nb4[0] : (it == 1 ? nb4[1] : (it == 2 ? nb4[2] : nb4[3]));
-                const int cy = cIdx / W, cx = cIdx - cy * W;
-                const int by = cy / 10, bx = cx / 10;
-                if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) valid = false;  // inside an eroded member block
-                else {
-                    trail0 = mem[cIdx];      // speculative: exact for the lanes that go in the first round
-                    dist0 = dist[cIdx];
-                    const double z = (double)D[cIdx] * A.cam.factor;
+            // valid4 order: left, right, up, down
+            cI[0] = sx > 0 ? sIdx - 1 : -1;
+            cI[1] = sx < W - 1 ? sIdx + 1 : -1;
+            cI[2] = sy > 0 ? sIdx - W : -1;
+            cI[3] = sy < H - 1 ? sIdx + W : -1;
+            int cxs[4] = {sx - 1, sx + 1, sx, sx}, cys[4] = {sy, sy, sy - 1, sy + 1};
+            uint16_t z16[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (cI[d] >= 0) {
+                    const int by = cys[d] / 10, bx = cxs[d] / 10;
+                    if (by < Nh && bx < Nw && blkmap[by * Nw + bx] >= 0) cI[d] = -1;  // inside an eroded member block
+                }
+                trail0[d] = 0; z16[d] = 0;
+                if (cI[d] >= 0) { trail0[d] = mem[cI[d]]; z16[d] = D[cI[d]]; pend |= 1u << d; }  // speculative: exact for round 1
+            }
+            const double* p = pl + 8 * plid;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                cdist[d] = -1.f;
+                if (cI[d] >= 0) {
+                    const double z = (double)z16[d] * A.cam.factor;
                     if (z != 0) {
-                        const double px = ((double)cx - A.cam.cx) * z / A.cam.fx, py = ((double)cy - A.cam.cy) * z / A.cam.fy;
-                        const double* p = pl + 7 * plid;
-                        cdist = (float)fabs(p[0] * (px - p[3]) + p[1] * (py - p[4]) + p[2] * (z - p[5]));
-                        ok = (double)cdist * (double)cdist < 9 * p[6] + 1e-5;
+                        FloodPix P;
+                        P.z = z;
+                        P.px = ((double)cxs[d] - A.cam.cx) * z / A.cam.fx;
+                        P.py = ((double)cys[d] - A.cam.cy) * z / A.cam.fy;
+                        cdist[d] = flood_dist(p, P);
+                        if ((double)cdist[d] * (double)cdist[d] < p[7]) okm |= 1u << d;
                     }
                 }
             }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { cI[d] = -1; trail0[d] = 0; cdist[d] = -1.f; }
         }
-        const unsigned hsh = ((unsigned)cIdx * 2654435761u) >> 21;  // 2048 buckets
-        bool pending = valid, push = false, first = true;
-        while (__syncthreads_or(pending)) {
-            const unsigned mykey = (tag << 8) | (unsigned)(kFloodThreads - 1 - tid);
-            if (pending) atomicMax(&s_bucket[hsh], mykey);
+#ifdef HVO_FLOOD_PROF
+        { const long long t = clock64(); st_load += t - st_t0; st_t0 = t; }
+#endif
+        bool first = true;
+        while (__syncthreads_or(pend != 0)) {
+#ifdef HVO_FLOOD_PROF
+            ++st_rounds;
+#endif
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (pend & (1u << d))
+                    atomicMax(&s_bucket[((unsigned)cI[d] * 2654435761u) >> 20], (tag << 10) | (unsigned)(1023 - (tid * 4 + d)));
             __syncthreads();
-            if (pending && s_bucket[hsh] == mykey) {
-                pending = false;
-                const int trail = first ? trail0 : mem[cIdx];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (!(pend & (1u << d))) continue;
+                if (s_bucket[((unsigned)cI[d] * 2654435761u) >> 20] != ((tag << 10) | (unsigned)(1023 - (tid * 4 + d)))) continue;
+                pend &= ~(1u << d);
+                const int cIdx = cI[d];
+                const int trail = first ? trail0[d] : mem[cIdx];
                 if (trail > -6 && !(trail >= 0 && trail == plid)) {
-                    if (ok) {
+                    if (okm & (1u << d)) {
+                        float od = 3.402823466e+38f;
                         if (trail >= 0) {
-                            const double *a = pl + 7 * plid, *b = pl + 7 * trail;
+                            const double *a = pl + 8 * plid, *b = pl + 8 * trail;
                             if (fabs(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) >= A.th_refine) {  // connect(planes)
                                 const int na = ext[trail], nbn = ext[plid];
                                 atomicOr(&adj[(size_t)na * A.nw + (nbn >> 5)], 1u << (nbn & 31));
                                 atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
                             }
+                            const int cy = cIdx / W, cx = cIdx - cy * W;
+                            FloodPix P;
+                            flood_point(A, D, cIdx, cx, cy, P);
+                            od = flood_dist(b, P);  // == distMap[cIdx]: the distance stored when the pixel took label `trail`
                         }
-                        const float od = first ? dist0 : dist[cIdx];
-                        if (cdist < od) { mem[cIdx] = plid; dist[cIdx] = cdist; push = true; }
+                        if (cdist[d] < od) { mem[cIdx] = plid; pushm |= 1u << d; }
                         else if (trail < 0) mem[cIdx] = trail - 1;
                     } else if (trail < 0) {
                         mem[cIdx] = trail - 1;
@@ -875,16 +924,24 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
             first = false;
             ++tag;
         }
+#ifdef HVO_FLOOD_PROF
+        { const long long t = clock64(); st_tour += t - st_t0; st_t0 = t; }
+#endif
         // append the new seeds in (entry, neighbour) order
-        const unsigned pm = __ballot_sync(0xffffffffu, push);
-        if (lane == 0) s_wsum[wid] = __popc(pm);
+        const int mine = __popc(pushm);
+        int pre = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        if (lane == 31) s_wsum[wid] = pre;
         __syncthreads();
         int base = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < kFloodThreads / 32; ++w) { const int v = s_wsum[w]; if (w < wid) base += v; total += v; }
-        if (push) {
-            const int pos = tail + base + __popc(pm & ((1u << lane) - 1u));
-            if (pos < A.qcap) queue[pos] = (uint32_t)cIdx | ((uint32_t)plid << 20);
+        if (mine) {
+            int pos = tail + base + pre - mine;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (pushm & (1u << d)) { if (pos < A.qcap) queue[pos] = (uint32_t)cI[d] | ((uint32_t)plid << 20); ++pos; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -893,7 +950,13 @@ __global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
             s_tail = nt; s_head = head + nbat;
         }
         __syncthreads();
+#ifdef HVO_FLOOD_PROF
+        { const long long t = clock64(); st_comp += t - st_t0; }
+#endif
     }
+#ifdef HVO_FLOOD_PROF
+    if (tid == 0 && f == 0) printf("flood: steps %d rounds %d tail %d load %lld tour %lld comp %lld\n", st_steps, st_rounds, s_tail, st_load, st_tour, st_comp);
+#endif
     if (tid == 0) {
         if (s_overflow) A.status[f] = 1;
         A.cycles[4 * (size_t)f + 1] = t_seeds - t_start;
@@ -981,7 +1044,6 @@ struct hvo_plane {
     double* d_cand = nullptr;
     uint32_t* d_ulog = nullptr;
     uint16_t* d_cnode = nullptr;
-    float* d_dist = nullptr;
     uint32_t* d_queue = nullptr;
     int32_t* d_mem = nullptr;
     double* d_planes = nullptr;  // [B][max_ext][7]
@@ -1038,9 +1100,11 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
         HVO_TRY(cudaFuncSetAttribute(k_plane_cluster<kRowW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ahc_smem));
         HVO_TRY(cudaFuncSetAttribute(k_plane_merge<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->merge_smem));
         HVO_TRY(cudaFuncSetAttribute(k_plane_merge<kRowW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->merge_smem));
-        h->flood_smem = (size_t)h->max_ext * 56 + (size_t)Nb * 2 + (size_t)h->max_ext * 2 + 16;
+        h->flood_smem = (size_t)h->max_ext * 64 + (size_t)Nb * 2 + (size_t)h->max_ext * 2 + 16;
         HVO_TRY(cudaFuncSetAttribute(k_plane_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->flood_smem));
-        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        pin_carveout(k_plane_blocks); pin_carveout(k_plane_cluster<3>); pin_carveout(k_plane_cluster<kRowW>);
+        pin_carveout(k_plane_flood); pin_carveout(k_plane_merge<3>); pin_carveout(k_plane_merge<kRowW>);
+        HVO_TRY(create_stream(&h->stream));
         HVO_TRY(cudaEventCreate(&h->tev[0]));
         HVO_TRY(cudaEventCreate(&h->tev[1]));
         const size_t B = (size_t)max_batch, px = (size_t)width * height;
@@ -1053,7 +1117,6 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
         HVO_TRY(cudaMalloc(&h->d_cand, B * Nb * sizeof(double)));
         HVO_TRY(cudaMalloc(&h->d_ulog, B * Nb * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_cnode, B * Nb * sizeof(uint16_t)));
-        HVO_TRY(cudaMalloc(&h->d_dist, B * px * sizeof(float)));
         HVO_TRY(cudaMalloc(&h->d_queue, B * (size_t)h->qcap * sizeof(uint32_t)));
         HVO_TRY(cudaMalloc(&h->d_mem, B * px * sizeof(int32_t)));
         HVO_TRY(cudaMalloc(&h->d_planes, B * (size_t)h->max_ext * 7 * sizeof(double)));
@@ -1080,7 +1143,7 @@ void hvo_plane_destroy(hvo_plane* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_ulog, h->d_cnode, h->d_dist, h->d_queue, h->d_mem, h->d_planes,
+    void* bufs[] = {h->d_depth, h->d_blocks, h->d_nodes, h->d_adj, h->d_key, h->d_cand, h->d_ulog, h->d_cnode, h->d_queue, h->d_mem, h->d_planes,
                     h->d_nplanes, h->d_status, h->d_cycles, h->d_gmse, h->d_gds, h->d_gnouse, h->d_gblkmap, h->d_gext, h->d_gisvalid,
                     h->d_gpl, h->d_gctl};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -1107,7 +1170,7 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     HVO_CUDA(cudaMemsetAsync(h->d_adj, 0, (size_t)nframes * Nb * h->nw * sizeof(uint32_t), h->stream));
     AhcArgs A;
     A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand; A.ulog = h->d_ulog; A.cnode = h->d_cnode;
-    A.dist = h->d_dist; A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
+    A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
     A.status = h->d_status; A.cycles = h->d_cycles;
     A.w = h->width; A.h = h->height; A.Nw = h->Nw; A.Nh = h->Nh; A.nw = h->nw; A.qcap = h->qcap; A.max_ext = h->max_ext;
     A.planes_stride = planes_stride; A.cam = h->cam;

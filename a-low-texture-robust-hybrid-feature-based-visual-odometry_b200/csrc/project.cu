@@ -291,7 +291,7 @@ int hvo_proj_create(int device, hvo_proj** out) {
     do {
 #define HVO_TRY(call) if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); st = HVO_ERR_CUDA; break; }
         HVO_TRY(cudaSetDevice(device));
-        HVO_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        HVO_TRY(create_stream(&h->stream));
         HVO_TRY(cudaEventCreate(&h->tev[0]));
         HVO_TRY(cudaEventCreate(&h->tev[1]));
         HVO_TRY(cudaMalloc(&h->d_cell_start, (kGridCells + 1) * sizeof(int)));
