@@ -116,6 +116,7 @@ ABI = {
     'hvo_plane_detect': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     'hvo_plane_detect_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
     'hvo_plane_detect_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'hvo_plane_detect_batch_device_u8': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     'hvo_plane_last_launches': (C.c_int, [_vp]),
     'hvo_plane_get_phase_cycles': (C.c_int, [_vp, C.c_int, _vp]),
     'hvo_plane_blocks_device': (C.c_int, [_vp, _vp, C.c_int]),
@@ -135,6 +136,7 @@ ABI = {
     'hvo_frame_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'hvo_frame_destroy': (None, [_vp]),
     'hvo_frame_capacities': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'hvo_frame_lanes': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_frame_extract_batch': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     'hvo_frame_extract_batch_device': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     'hvo_frame_last_launches': (C.c_int, [_vp]),
@@ -1044,12 +1046,13 @@ class ORBmatcher:
 
 class _FrameParams(C.Structure):
     _fields_ = [('orb', _OrbParams), ('line', _LineParams), ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
-                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int), ('line_cull', C.c_int)]
+                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int), ('line_cull', C.c_int),
+                ('lanes', C.c_int)]
 
 
 class _FrameOutputs(C.Structure):
     _fields_ = [(n, _vp) for n in ('kps', 'desc', 'kp_counts', 'kp_depth', 'kp_uright', 'keylines', 'line_desc', 'linevec3',
-                                   'line_counts', 'n_planes', 'planes7', 'membership', 'normals8')]
+                                   'line_counts', 'n_planes', 'planes7', 'membership', 'normals8', 'membership8')]
 
 
 class FrameFrontEnd:
@@ -1058,9 +1061,13 @@ class FrameFrontEnd:
     FIELDS = [f[0] for f in _FrameOutputs._fields_]
 
     def __init__(self, width, height, fx, fy, cx, cy, depth_factor, bf=40.0, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
-                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False):
+                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False, lanes=0, membership='i32'):
+        """membership: 'i32' (int32 labels, -1 = none), 'u8' (one byte per pixel, 255 = none: what a host caller needs to
+        rebuild plane_vertices_) or 'both'.  The int32 image is always the device-side working image."""
+        assert membership in ('i32', 'u8', 'both')
+        self.membership_mode = membership
         prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
-                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes, int(bool(line_cull)))
+                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes, int(bool(line_cull)), int(lanes))
         out = _vp()
         _check(lib().hvo_frame_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
         self._h = out
@@ -1068,6 +1075,8 @@ class FrameFrontEnd:
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         _check(lib().hvo_frame_capacities(out, C.byref(a), C.byref(b), C.byref(c)))
         self.orb_capacity, self.max_lines, self.normals_count = a.value, b.value, c.value
+        _check(lib().hvo_frame_lanes(out, C.byref(a), C.byref(b)))
+        self.lanes, self.chunk = a.value, b.value
 
     def close(self):
         if getattr(self, '_h', None):
@@ -1080,8 +1089,9 @@ class FrameFrontEnd:
         except Exception:
             pass
 
-    def output_shapes(self, n):
-        """name -> (shape, numpy dtype) of every output of an n-frame batch (for the selected stages)."""
+    def output_shapes(self, n, device=True):
+        """name -> (shape, numpy dtype) of every output of an n-frame batch (for the selected stages); device=False
+        leaves out the int32 membership image when the handle reports labels as bytes."""
         sh = {}
         if self.stages & STAGE_ORB:
             c = self.orb_capacity
@@ -1092,13 +1102,17 @@ class FrameFrontEnd:
             sh.update(keylines=((n, c), KL_DTYPE), line_desc=((n, c, 32), np.uint8), linevec3=((n, c, 3), np.float64),
                       line_counts=((n,), np.int32))
         if self.stages & STAGE_PLANES:
-            sh.update(n_planes=((n,), np.int32), planes7=((n, self.max_planes, 7), np.float64), membership=((n, self.h * self.w), np.int32))
+            sh.update(n_planes=((n,), np.int32), planes7=((n, self.max_planes, 7), np.float64))
+            if device or self.membership_mode != 'u8':
+                sh.update(membership=((n, self.h * self.w), np.int32))
+            if self.membership_mode != 'i32':
+                sh.update(membership8=((n, self.h * self.w), np.uint8))
         if self.stages & STAGE_NORMALS:
             sh.update(normals8=((n, self.normals_count, 8), np.float32))
         return sh
 
     def alloc_host(self, n):
-        return {k: np.empty(s, d) for k, (s, d) in self.output_shapes(n).items()}
+        return {k: np.empty(s, d) for k, (s, d) in self.output_shapes(n, device=False).items()}
 
     def _outputs(self, ptrs):
         o = _FrameOutputs()

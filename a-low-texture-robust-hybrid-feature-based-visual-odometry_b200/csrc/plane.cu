@@ -177,6 +177,7 @@ struct AhcArgs {
     uint16_t* cnode;         // [B][Nb]  node of candidate i
     uint32_t* queue;         // [B][qcap]
     int32_t* membership;     // [B][h*w]   working membershipImg, final labels on exit
+    uint8_t* membership8;    // [B][h*w]   optional compact copy of the final labels (255 = no plane)
     double* planes7;         // [B][planes_stride][7]
     int32_t* n_planes;       // [B]
     int32_t* status;         // [B]  0 ok, 1 refinement queue overflow
@@ -1020,7 +1021,9 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     __syncthreads();
     for (int i = tid; i < npix; i += kAhcThreads) {
         const int plid = mem[i];
-        mem[i] = (plid >= 0) ? (int)S.plidmap[plid] : -1;
+        const int lab = (plid >= 0) ? (int)S.plidmap[plid] : -1;
+        mem[i] = lab;
+        if (A.membership8) A.membership8[(size_t)f * npix + i] = (uint8_t)(lab < 0 || lab > 254 ? 255 : lab);
     }
     if (tid == 0) A.cycles[4 * (size_t)f + 3] = clock64() - t_start;
 }
@@ -1163,14 +1166,14 @@ static int plane_blocks_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
 
 // blocks + graph stage on device-resident depth; results into d_nplanes / d_planes7 ([n][planes_stride][7]) / d_membership
 static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframes, int32_t* d_nplanes, double* d_planes7, int planes_stride,
-                               int32_t* d_membership) {
+                               int32_t* d_membership, uint8_t* d_membership8 = nullptr) {
     int st = plane_blocks_launch(h, d_depth, nframes);
     if (st != HVO_OK) return st;
     const int Nb = h->Nw * h->Nh;
     HVO_CUDA(cudaMemsetAsync(h->d_adj, 0, (size_t)nframes * Nb * h->nw * sizeof(uint32_t), h->stream));
     AhcArgs A;
     A.depth = d_depth; A.blocks = h->d_blocks; A.nodes = h->d_nodes; A.adj = h->d_adj; A.key = h->d_key; A.cand = h->d_cand; A.ulog = h->d_ulog; A.cnode = h->d_cnode;
-    A.queue = h->d_queue; A.membership = d_membership; A.planes7 = d_planes7; A.n_planes = d_nplanes;
+    A.queue = h->d_queue; A.membership = d_membership; A.membership8 = d_membership8; A.planes7 = d_planes7; A.n_planes = d_nplanes;
     A.status = h->d_status; A.cycles = h->d_cycles;
     A.w = h->width; A.h = h->height; A.Nw = h->Nw; A.Nh = h->Nh; A.nw = h->nw; A.qcap = h->qcap; A.max_ext = h->max_ext;
     A.planes_stride = planes_stride; A.cam = h->cam;
@@ -1227,6 +1230,14 @@ int hvo_plane_detect_batch_device(hvo_plane* h, const uint16_t* d_depth16, int n
     HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch && max_planes >= 1, "nframes / max_planes out of range");
     HVO_CUDA(cudaSetDevice(h->device));
     return plane_detect_launch(h, d_depth16, nframes, d_n_planes, d_planes7, max_planes, d_membership);
+}
+
+int hvo_plane_detect_batch_device_u8(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
+                                     int max_planes, int32_t* d_membership, uint8_t* d_membership8) {
+    HVO_CHECK_ARG(h && d_depth16 && d_n_planes && d_planes7 && d_membership && d_membership8, "null argument");
+    HVO_CHECK_ARG(nframes >= 1 && nframes <= h->max_batch && max_planes >= 1, "nframes / max_planes out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    return plane_detect_launch(h, d_depth16, nframes, d_n_planes, d_planes7, max_planes, d_membership, d_membership8);
 }
 
 int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, int32_t* n_planes, double* planes7, int max_planes,

@@ -188,10 +188,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=1024, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=2048, help='frames per GPU per step')
     ap.add_argument('--stages', type=int, default=15, help='bit 0 ORB, 1 lines, 2 planes, 3 normals (profiling aid; the metric is 15)')
+    ap.add_argument('--lanes', type=int, default=0, help='pipeline lanes of the frame handle (0 = library default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--device-only', action='store_true', help='profiling aid: only the device-resident loop')
+    ap.add_argument('--e2e-only', action='store_true', help='profiling aid: skip the per-stage passes, the latency probe and the CPU baseline')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -214,7 +216,7 @@ def main():
 
     B, W, H = args.batch, 640, 480
     gray, depth = make_frames(B, start=rank * B)  # every rank gets its own frames (frame-sharded, weak scaling)
-    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
+    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True, lanes=args.lanes, membership='u8',
                            max_batch=B, device=local_rank, nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'],
                            nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
     dev = torch.device('cuda', local_rank)
@@ -267,93 +269,95 @@ def main():
 
     if args.device_only:
         print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
-                          'stages': args.stages, 'means': means}))
+                          'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means}))
         return
 
-    # ---- per-stage device times: every pipeline alone on the same batch (standalone handles, smaller batch) ----
-    Bs = min(B, 256)
-    stage_ms, kern_ms = {}, {}
-    ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'], width=W, height=H,
-                          max_batch=Bs, device=local_rank)
-    kp = d_ptrs
+    roofline = None
+    if not args.e2e_only:
+        # ---- per-stage device times: every pipeline alone on the same batch (standalone handles, smaller batch) ----
+        Bs = min(B, 256)
+        stage_ms, kern_ms = {}, {}
+        ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'], width=W, height=H,
+                              max_batch=Bs, device=local_rank)
+        kp = d_ptrs
 
-    def orb_step():
-        ex.extract_batch_device(d_gray.data_ptr(), Bs, kp['kps'], kp['desc'], kp['kp_counts'], d_depth.data_ptr(), DEPTH_FACTOR, BF,
-                                kp['kp_depth'], kp['kp_uright'])
-    for _ in range(2):
-        orb_step()
-    ex.sync()
-    ex.timer_start()
-    for _ in range(5):
-        orb_step()
-    stage_ms['orb'] = ex.timer_stop() / 5
-    ex.set_profiling(True)
-    acc = {}
-    for _ in range(5):
-        orb_step()
+        def orb_step():
+            ex.extract_batch_device(d_gray.data_ptr(), Bs, kp['kps'], kp['desc'], kp['kp_counts'], d_depth.data_ptr(), DEPTH_FACTOR, BF,
+                                    kp['kp_depth'], kp['kp_uright'])
+        for _ in range(2):
+            orb_step()
         ex.sync()
-        for k, v in ex.stage_times().items():
-            acc[k] = acc.get(k, 0.0) + v / 5
-    ex.close()
-    kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_cells': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
+        ex.timer_start()
+        for _ in range(5):
+            orb_step()
+        stage_ms['orb'] = ex.timer_stop() / 5
+        ex.set_profiling(True)
+        acc = {}
+        for _ in range(5):
+            orb_step()
+            ex.sync()
+            for k, v in ex.stage_times().items():
+                acc[k] = acc.get(k, 0.0) + v / 5
+        ex.close()
+        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_cells': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
 
-    le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
+        le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
 
-    def line_step():
-        le.extract_batch_device(d_gray.data_ptr(), Bs, kp['keylines'], kp['line_desc'], kp['linevec3'], kp['line_counts'])
-    line_step()
-    le.sync()
-    le.timer_start()
-    for _ in range(3):
+        def line_step():
+            le.extract_batch_device(d_gray.data_ptr(), Bs, kp['keylines'], kp['line_desc'], kp['linevec3'], kp['line_counts'])
         line_step()
-    stage_ms['lines'] = le.timer_stop() / 3
-    le.set_profiling(True)
-    line_step()
-    le.sync()
-    lt = le.stage_times()
-    le.close()
-    kern_ms.update({'k_lsd_prep': lt['prep'], 'k_lsd_order': lt['order'], 'k_lsd_grow': lt['grow'], 'k_line_keylines + k_lbd_*': lt['keylines_lbd']})
+        le.sync()
+        le.timer_start()
+        for _ in range(3):
+            line_step()
+        stage_ms['lines'] = le.timer_stop() / 3
+        le.set_profiling(True)
+        line_step()
+        le.sync()
+        lt = le.stage_times()
+        le.close()
+        kern_ms.update({'k_lsd_prep': lt['prep'], 'k_lsd_order': lt['order'], 'k_lsd_grow': lt['grow'], 'k_line_keylines + k_lbd_*': lt['keylines_lbd']})
 
-    pd = hvo.PlaneDetection(W, H, max_batch=Bs, device=local_rank)
-    pd.readDepthImage(depth[0], np.array([[CAM['fx'], 0, CAM['cx']], [0, CAM['fy'], CAM['cy']], [0, 0, 1]], np.float32), np.float32(DEPTH_FACTOR))
+        pd = hvo.PlaneDetection(W, H, max_batch=Bs, device=local_rank)
+        pd.readDepthImage(depth[0], np.array([[CAM['fx'], 0, CAM['cx']], [0, CAM['fy'], CAM['cy']], [0, 0, 1]], np.float32), np.float32(DEPTH_FACTOR))
 
-    def plane_step():
-        pd.detect_batch_device(d_depth.data_ptr(), Bs, kp['n_planes'], kp['planes7'], fe.max_planes, kp['membership'])
-    plane_step()
-    pd.sync()
-    pd.timer_start()
-    for _ in range(3):
+        def plane_step():
+            pd.detect_batch_device(d_depth.data_ptr(), Bs, kp['n_planes'], kp['planes7'], fe.max_planes, kp['membership'])
         plane_step()
-    stage_ms['planes'] = pd.timer_stop() / 3
-    pd.timer_start()
-    for _ in range(5):
-        pd.blocks_device(d_depth.data_ptr(), Bs)
-    kern_ms['k_plane_blocks'] = pd.timer_stop() / 5
-    kern_ms['k_plane_cluster + k_plane_flood + k_plane_merge'] = stage_ms['planes'] - kern_ms['k_plane_blocks']
-    pd.close()
+        pd.sync()
+        pd.timer_start()
+        for _ in range(3):
+            plane_step()
+        stage_ms['planes'] = pd.timer_stop() / 3
+        pd.timer_start()
+        for _ in range(5):
+            pd.blocks_device(d_depth.data_ptr(), Bs)
+        kern_ms['k_plane_blocks'] = pd.timer_stop() / 5
+        kern_ms['k_plane_cluster + k_plane_flood + k_plane_merge'] = stage_ms['planes'] - kern_ms['k_plane_blocks']
+        pd.close()
 
-    sn = hvo.SurfaceNormals(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, max_batch=Bs, device=local_rank)
-    sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
-    sn.sync()
-    sn.timer_start()
-    for _ in range(5):
+        sn = hvo.SurfaceNormals(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, max_batch=Bs, device=local_rank)
         sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
-    stage_ms['normals'] = sn.timer_stop() / 5
-    sn.close()
+        sn.sync()
+        sn.timer_start()
+        for _ in range(5):
+            sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
+        stage_ms['normals'] = sn.timer_stop() / 5
+        sn.close()
 
-    # roofline: the dominant kernel among the HBM-bound (stencil / streaming) kernels; the ordered graph kernels
-    # (k_octree, k_lsd_grow, k_plane_cluster/flood/merge) are latency-bound by construction and are listed beside it
-    peak, peak_src = measured_peak()
-    dom = max(ALG_BYTES, key=lambda k: kern_ms[k])
-    achieved = ALG_BYTES[dom] * Bs / (kern_ms[dom] * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
-                    peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
-                    kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
-                    frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
-                    stage_ms_alone={k: round(v, 3) for k, v in stage_ms.items()},
-                    serial_kernels='k_lsd_grow, k_plane_cluster, k_plane_flood, k_plane_merge and k_octree run the reference\'s ordered '
-                                   '(sequential) algorithms, one warp/CTA per frame; they are latency-bound, not HBM-bound, and dominate the step '
-                                   '(see kernel_ms); their throughput comes from the batch (frames in flight), not from bandwidth')
+        # roofline: the dominant kernel among the HBM-bound (stencil / streaming) kernels; the ordered graph kernels
+        # (k_octree, k_lsd_grow, k_plane_cluster/flood/merge) are latency-bound by construction and are listed beside it
+        peak, peak_src = measured_peak()
+        dom = max(ALG_BYTES, key=lambda k: kern_ms[k])
+        achieved = ALG_BYTES[dom] * Bs / (kern_ms[dom] * 1e-3) / 1e9
+        roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
+                        peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
+                        kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
+                        frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
+                        stage_ms_alone={k: round(v, 3) for k, v in stage_ms.items()},
+                        serial_kernels='k_lsd_grow, k_plane_cluster, k_plane_flood, k_plane_merge and k_octree run the reference\'s ordered '
+                                       '(sequential) algorithms, one warp/CTA per frame; they are latency-bound, not HBM-bound, and dominate the step '
+                                       '(see kernel_ms); their throughput comes from the batch (frames in flight), not from bandwidth')
 
     # ---- e2e: host (pinned) buffers through the C-ABI call, copies inside the timed region ----
     def pinned(shape, dtype):
@@ -364,7 +368,7 @@ def main():
     h_depth = pinned((B, H, W), np.uint16)
     h_gray[:] = gray
     h_depth[:] = depth
-    out = {k: pinned(sh, dt) for k, (sh, dt) in shapes.items()}
+    out = {k: pinned(sh, dt) for k, (sh, dt) in fe.output_shapes(B, device=False).items()}
     for _ in range(2):
         fe.extract_batch(h_gray, h_depth, out=out)
     barrier()
@@ -378,6 +382,10 @@ def main():
                h2d_bytes_per_step=int(h_gray.nbytes + h_depth.nbytes),
                d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())), ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps)
 
+    if args.e2e_only:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'lanes': fe.lanes, 'chunk': fe.chunk}))
+        return
     # ---- single-frame latency through the host call (p50) ----
     fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
                             max_batch=1, device=local_rank)

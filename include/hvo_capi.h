@@ -294,6 +294,10 @@ int hvo_plane_detect_batch(hvo_plane* h, const uint16_t* depth16, int nframes, i
  * d_membership doubles as the working membership image. */
 int hvo_plane_detect_batch_device(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
                                   int max_planes, int32_t* d_membership);
+/* Same, and also writes the final labels as one byte per pixel (plane id, 255 = no plane) into d_membership8 [n][H*W]:
+ * the compact form the frame front-end copies back to the host. */
+int hvo_plane_detect_batch_device_u8(hvo_plane* h, const uint16_t* d_depth16, int nframes, int32_t* d_n_planes, double* d_planes7,
+                                     int max_planes, int32_t* d_membership, uint8_t* d_membership8);
 int hvo_plane_last_launches(const hvo_plane* h);
 /* Profiling: SM clock cycles of the graph kernel's phases for one frame of the last call: first clustering,
  * block erosion + seeds, flood fill, last merge + relabel. */
@@ -352,6 +356,8 @@ typedef struct hvo_frame_params {
     int stages;           /* HVO_STAGE_* bits */
     int max_planes;       /* rows of planes7 per frame */
     int line_cull;        /* != 0: Frame::cullingLine after the line extractor, as Frame::ExtractLSD does (src/Frame.cc:939) */
+    int lanes;            /* 0 = default.  The handle splits a batch into chunks that go round-robin through `lanes` independent
+                             copies of the three pipelines, so uploads, kernels and downloads of different chunks overlap. */
 } hvo_frame_params;
 
 /* Output arrays of a batch of n frames.  Host pointers for hvo_frame_extract_batch, device pointers for
@@ -368,18 +374,22 @@ typedef struct hvo_frame_outputs {
     int32_t* line_counts;  /* [n]                    NL                                           */
     int32_t* n_planes;     /* [n]                    plane_num_                                   */
     double* planes7;       /* [n][max_planes][7]     normal, center, N of extractedPlanes         */
-    int32_t* membership;   /* [n][H*W]               plane id per pixel or -1 (-> plane_vertices_) */
+    int32_t* membership;   /* [n][H*W]               plane id per pixel or -1 (-> plane_vertices_); on the host
+                                                     optional when membership8 is given           */
     float* normals8;       /* [n][normals_count][8]  std::vector<SurfaceNormal>                   */
+    uint8_t* membership8;  /* [n][H*W]               the same labels in one byte (255 = none)     optional */
 } hvo_frame_outputs;
 
 typedef struct hvo_frame hvo_frame;
 int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_batch, int device, hvo_frame** out);
 void hvo_frame_destroy(hvo_frame* h);
 int hvo_frame_capacities(const hvo_frame* h, int* orb_capacity, int* max_lines, int* normals_count);
+int hvo_frame_lanes(const hvo_frame* h, int* lanes, int* chunk_frames);
 /* gray [n][H][W] uint8 and depth16 [n][H][W] uint16 in host memory (pinned memory makes the copies asynchronous);
- * returns when every output has been written. */
+ * returns when every output has been written.  n is not limited by max_batch: chunks of max_batch / lanes frames are
+ * streamed through the lanes (upload of chunk k+1 and download of chunk k-1 overlap the kernels of chunk k). */
 int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out);
-/* Everything device-resident; asynchronous.  hvo_frame_sync / hvo_frame_timer_stop wait for all three pipelines. */
+/* Everything device-resident (n <= max_batch); asynchronous.  hvo_frame_sync / hvo_frame_timer_stop wait for all pipelines. */
 int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const uint16_t* d_depth16, int nframes,
                                    const hvo_frame_outputs* d_out);
 int hvo_frame_last_launches(const hvo_frame* h);

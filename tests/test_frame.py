@@ -66,8 +66,45 @@ def test_gpu_frame_stage_subsets_and_errors(hvo, synth):
                     assert n == int(full['line_counts'][f]) and out[k][f, :n].tobytes() == full[k][f, :n].tobytes()
             else:
                 assert np.array_equal(out[k], full[k], equal_nan=True)
-        with pytest.raises(hvo.HvoError):
-            fe.extract_batch(np.concatenate([gray, gray]), np.concatenate([depth, depth]))   # more frames than max_batch
+        with pytest.raises(hvo.HvoError):   # the device-resident call is limited to max_batch frames
+            fe.extract_batch_device(1, 1, 3, {k: 1 for k in fe.output_shapes(3)})
         fe.close()
     with pytest.raises(hvo.HvoError):
         hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, stages=0)
+
+
+def _same_outputs(hvo, a, b, n):
+    for f in range(n):
+        nk, nl = int(a['kp_counts'][f]), int(a['line_counts'][f])
+        assert nk == int(b['kp_counts'][f]) and nl == int(b['line_counts'][f])
+        for k in ('kps', 'desc', 'kp_depth', 'kp_uright'):
+            assert a[k][f, :nk].tobytes() == b[k][f, :nk].tobytes(), k
+        for k in ('keylines', 'line_desc', 'linevec3'):
+            assert a[k][f, :nl].tobytes() == b[k][f, :nl].tobytes(), k
+        npl = int(a['n_planes'][f])
+        assert npl == int(b['n_planes'][f]) and np.array_equal(a['planes7'][f, :npl], b['planes7'][f, :npl])
+        assert np.array_equal(a['normals8'][f], b['normals8'][f], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gpu_frame_lanes_stream_chunks_and_byte_membership(hvo, synth):
+    """The host call streams chunks of max_batch / lanes frames round-robin through the lanes, so it takes more frames
+    than max_batch; every lane count gives the same bytes, and the one-byte labels equal the int32 membership image."""
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 7, start=11)
+    one = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=7, lanes=1, line_cull=True, membership='both')
+    assert (one.lanes, one.chunk) == (1, 7)
+    ref = one.extract_batch(gray, depth)
+    one.close()
+    lab = ref['membership']
+    assert np.array_equal(ref['membership8'], np.where(lab < 0, 255, lab).astype(np.uint8))
+    for lanes, max_batch in ((2, 4), (3, 3), (2, 7)):
+        fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=max_batch, lanes=lanes, line_cull=True, membership='u8')
+        assert fe.lanes == lanes and fe.chunk == -(-max_batch // lanes)
+        out = fe.extract_batch(gray, depth)       # 7 frames: several chunks per lane when max_batch < 7
+        assert 'membership' not in out
+        _same_outputs(hvo, ref, out, 7)
+        assert np.array_equal(out['membership8'], ref['membership8'])
+        out2 = fe.extract_batch(gray[:2], depth[:2])   # fewer frames than lanes * chunk
+        _same_outputs(hvo, ref, out2, 2)
+        fe.close()
