@@ -133,6 +133,22 @@ ABI = {
     'hvo_normals_sync': (C.c_int, [_vp]),
     'hvo_normals_timer_start': (C.c_int, [_vp]),
     'hvo_normals_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_lproj_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    'hvo_lproj_destroy': (None, [_vp]),
+    'hvo_lproj_set_frame': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]),
+    'hvo_lproj_get_grid': (C.c_int, [_vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_lproj_features_in_area': (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, C.POINTER(C.c_int)]),
+    'hvo_lproj_search': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_lproj_last_rounds': (C.c_int, [_vp]),
+    'hvo_lproj_last_launches': (C.c_int, [_vp]),
+    'hvo_lpvo_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    'hvo_lpvo_destroy': (None, [_vp]),
+    'hvo_lpvo_capacity': (C.c_int, [_vp]),
+    'hvo_lpvo_compute_batch': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'hvo_lpvo_compute_batch_device': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    'hvo_lpvo_sync': (C.c_int, [_vp]),
+    'hvo_lpvo_timer_start': (C.c_int, [_vp]),
+    'hvo_lpvo_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_frame_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'hvo_frame_destroy': (None, [_vp]),
     'hvo_frame_capacities': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -717,6 +733,56 @@ class SurfaceNormals:
         return ms.value
 
 
+class Manhattan:
+    """The normal-extraction half of ORB_SLAM2::Manhattan (reference src/Manhattan.cpp): computeNormalsLPVO on the GPU.
+    Constructed from K like the reference (Manhattan.cpp:8-19); depth is the raw 16-bit image and depth_factor."""
+
+    def __init__(self, K, width, height, depth_factor, max_batch=1, device=0):
+        K = np.asarray(K, np.float32)
+        prm = _PlaneParams(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), float(np.float32(depth_factor)))
+        out = _vp()
+        _check(lib().hvo_lpvo_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
+        self._h, self.w, self.h = out, int(width), int(height)
+        self.capacity = lib().hvo_lpvo_capacity(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_lpvo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def computeNormalsLPVO_batch(self, depth16):
+        """[n,h,w] uint16 -> list of (pt_normals [m,3] float64, depth_normals [m] float32, pixels (u, v) [m,2] int32)."""
+        d = np.ascontiguousarray(depth16, np.uint16)
+        n, c = len(d), self.capacity
+        nrm = np.empty((n, c, 3), np.float64); dep = np.empty((n, c), np.float32); pix = np.empty((n, c, 2), np.int32)
+        cnt = np.empty(n, np.int32)
+        _check(lib().hvo_lpvo_compute_batch(self._h, _np_ptr(d), n, _np_ptr(nrm), _np_ptr(dep), _np_ptr(pix), _np_ptr(cnt)))
+        return [(nrm[f, :cnt[f]], dep[f, :cnt[f]], pix[f, :cnt[f]]) for f in range(n)]
+
+    def computeNormalsLPVO(self, depth16):
+        return self.computeNormalsLPVO_batch(np.asarray(depth16)[None])[0]
+
+    def compute_device(self, d_depth, nframes, d_normals3, d_depth_out, d_pix2, d_counts):
+        _check(lib().hvo_lpvo_compute_batch_device(self._h, _vp(d_depth), nframes, _vp(d_normals3), _vp(d_depth_out), _vp(d_pix2), _vp(d_counts)))
+
+    def sync(self):
+        _check(lib().hvo_lpvo_sync(self._h))
+
+    def timer_start(self):
+        _check(lib().hvo_lpvo_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().hvo_lpvo_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+
 class BFMatcherHamming:
     """cv::BFMatcher(NORM_HAMMING, crossCheck=false).knnMatch(k=2) on the GPU (hvo_match_knn2)."""
 
@@ -760,20 +826,162 @@ class BFMatcherHamming:
         return ms.value
 
 
+LPROJ_QUERY_DTYPE = np.dtype([('x1', '<f4'), ('y1', '<f4'), ('x2', '<f4'), ('y2', '<f4'), ('r', '<f4'), ('cos_th', '<f4'), ('dir', '<f8', (3,)),
+                              ('length', '<f4'), ('claims', '<i4'), ('reserved', '<i4', (2,))])
+assert LPROJ_QUERY_DTYPE.itemsize == 64
+
+
+class LineProjectionMatcher:
+    """Device side of the windowed line matchers: the line grid (Frame::AssignFeaturesToGridForLine, src/Frame.cc:849-872),
+    Frame::GetFeaturesInAreaForLine (:1557-1631) and the greedy searches of LSDmatcher::SearchByProjection
+    (src/LSDmatcher.cpp:561-664, 709-801).  One frame at a time."""
+
+    def __init__(self, device=0):
+        out = _vp()
+        _check(lib().hvo_lproj_create(int(device), C.byref(out)))
+        self._h = out
+        self.n = 0
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_lproj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frame(self, keylines_un, line_functions, desc, lines3d, min_x, min_y, max_x, max_y):
+        kl = np.ascontiguousarray(keylines_un, KL_DTYPE)
+        fn = np.ascontiguousarray(line_functions, np.float64).reshape(-1, 3)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        l3 = None if lines3d is None else np.ascontiguousarray(lines3d, np.float64).reshape(-1, 6)
+        self.n = len(kl)
+        _check(lib().hvo_lproj_set_frame(self._h, _np_ptr(kl), _np_ptr(fn), _np_ptr(desc), _np_ptr(l3) if l3 is not None else None, self.n,
+                                         float(min_x), float(min_y), float(max_x), float(max_y)))
+
+    def grid(self):
+        """(cell_count [64*48], cell_items): cell ix*48+iy lists mGridForLine[ix][iy]."""
+        cnt = np.empty(GRID_COLS * GRID_ROWS, np.int32)
+        n = C.c_int(0)
+        _check(lib().hvo_lproj_get_grid(self._h, _np_ptr(cnt), None, 0, C.byref(n)))
+        items = np.empty(max(n.value, 1), np.int32)
+        _check(lib().hvo_lproj_get_grid(self._h, _np_ptr(cnt), _np_ptr(items), len(items), C.byref(n)))
+        return cnt, items[:n.value].copy()
+
+    def GetFeaturesInAreaForLine(self, x1, y1, x2, y2, r, minLevel=-1, maxLevel=-1, TH=0.998):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = C.c_int(0)
+        _check(lib().hvo_lproj_features_in_area(self._h, float(x1), float(y1), float(x2), float(y2), float(r), float(np.float32(TH)),
+                                                _np_ptr(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def search(self, queries, qdesc, claimed=None, mode=0, nnratio=0.95):
+        q = np.ascontiguousarray(queries, LPROJ_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        idx = np.full(max(len(q), 1), -1, np.int32)
+        dist = np.full(max(len(q), 1), 256, np.int32)
+        nm = C.c_int(0)
+        _check(lib().hvo_lproj_search(self._h, _np_ptr(q), _np_ptr(qd), len(q), _np_ptr(cl) if cl is not None else None, int(mode),
+                                      float(np.float32(nnratio)), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
+        return idx[:len(q)], dist[:len(q)], nm.value
+
+    def rounds(self):
+        return lib().hvo_lproj_last_rounds(self._h)
+
+
 class LSDmatcher:
-    """Mirror of the brute-force part of ORB_SLAM2::LSDmatcher (reference include/LSDmatcher.h:23-60):
-    match / matchNNR (src/LSDmatcher.cpp:803-863), FrameBFMatch + lineDescriptorMAD (:942-966, :1110-1135),
-    DescriptorDistance (:1137-1153).  Distances run on the GPU; the ratio / MAD filters are the reference's
-    float arithmetic on the host."""
+    """Mirror of ORB_SLAM2::LSDmatcher (reference include/LSDmatcher.h:23-60): match / matchNNR (src/LSDmatcher.cpp:803-863),
+    FrameBFMatch + lineDescriptorMAD (:942-966, :1110-1135), SearchDouble, SearchByDescriptor, the two SearchByProjection
+    (:561-664, :709-801) and DescriptorDistance (:1137-1153).  Distances and the windowed searches run on the GPU; the
+    ratio / MAD filters are the reference's float arithmetic on the host.  Frames and map lines are plain arrays:
+
+        F   = dict(keylines_un KL_DTYPE [NL], line_functions [NL,3], ldesc [NL,32], lines3d [NL,6] (mvLines3D first, second),
+                   bounds (minX, minY, maxX, maxY), mapline [NL] int (index of the map line held, -1 none),
+                   claimed [NL] bool (holds one with observations))
+        MLs = dict(proj_x1, proj_y1, proj_x2, proj_y2, view_cos, in_view, bad, has_obs, world_vector [M,3], desc [M,32])
+    """
     TH_HIGH, TH_LOW = 80, 50
 
     def __init__(self, nnratio=0.95, checkOri=True, device=0):
         self.mfNNratio = np.float32(nnratio)
         self.mbCheckOrientation = bool(checkOri)
         self._bf = BFMatcherHamming(device)
+        self._device = device
+        self._lpm = None
 
     def close(self):
         self._bf.close()
+        if self._lpm is not None:
+            self._lpm.close()
+
+    def _line_matcher(self, F, need3d):
+        if self._lpm is None:
+            self._lpm = LineProjectionMatcher(self._device)
+        b = F['bounds']
+        self._lpm.set_frame(F['keylines_un'], F['line_functions'], F['ldesc'], F.get('lines3d') if need3d else None, b[0], b[1], b[2], b[3])
+        return self._lpm
+
+    @staticmethod
+    def RadiusByViewingCos(viewCos):  # LSDmatcher.cpp:1436-1442
+        return np.where(np.asarray(viewCos, np.float32) > np.float32(0.998), np.float32(5.0), np.float32(8.0))
+
+    @staticmethod
+    def _apply(F, sel, idx, has_obs):
+        for k, i in zip(sel, idx):  # F.mvpMapLines[bestIdx] = pML, in query order
+            if i >= 0:
+                F['mapline'][i] = k
+                F['claimed'][i] = bool(has_obs[k])
+
+    def SearchByProjection(self, F, MLs, eval_orient=True, th=1.0):
+        """LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, eval_orient, th) (LSDmatcher.cpp:709-801).  Updates
+        F['mapline'] / F['claimed'] in place, returns (nmatches, match [M] frame line index or -1)."""
+        M = len(MLs['proj_x1'])
+        sel = np.nonzero(np.asarray(MLs['in_view'], bool) & ~np.asarray(MLs['bad'], bool))[0]
+        r = self.RadiusByViewingCos(np.asarray(MLs['view_cos'])[sel]).astype(np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        q = np.zeros(len(sel), LPROJ_QUERY_DTYPE)
+        for a, b in (('x1', 'proj_x1'), ('y1', 'proj_y1'), ('x2', 'proj_x2'), ('y2', 'proj_y2')):
+            q[a] = np.asarray(MLs[b], np.float32)[sel]
+        q['r'] = r
+        q['cos_th'] = np.float32(0.998)                       # default TH of GetFeaturesInAreaForLine (Frame.h:131)
+        q['dir'] = np.asarray(MLs['world_vector'], np.float64)[sel]
+        q['claims'] = np.asarray(MLs['has_obs'], bool)[sel]
+        has_obs = np.asarray(MLs['has_obs'], bool)
+        match = np.full(M, -1, np.int32)
+        if len(sel) == 0:
+            return 0, match
+        idx, _, nm = self._line_matcher(F, True).search(q, np.asarray(MLs['desc'], np.uint8)[sel], F.get('claimed'), 0, self.mfNNratio)
+        match[sel] = idx
+        self._apply(F, sel, idx, has_obs)
+        return nm, match
+
+    def SearchByProjectionLast(self, Cur, last, th):
+        """Matching part of LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th) (LSDmatcher.cpp:561-664).  `last` holds,
+        for every last-frame line with a usable map line (not an outlier, in the current frustum), its projection into the
+        current frame and its keyline: dict(proj_x1, proj_y1, proj_x2, proj_y2, keylines KL_DTYPE [M], has_obs, desc [M,32]).
+        Updates Cur['mapline'] / Cur['claimed'], returns (nmatches, match [M])."""
+        M = len(last['proj_x1'])
+        kl = np.asarray(last['keylines'], KL_DTYPE)
+        q = np.zeros(M, LPROJ_QUERY_DTYPE)
+        for a, b in (('x1', 'proj_x1'), ('y1', 'proj_y1'), ('x2', 'proj_x2'), ('y2', 'proj_y2')):
+            q[a] = np.asarray(last[b], np.float32)
+        q['r'] = np.float32(th)
+        q['cos_th'] = np.float32(0.96)
+        q['dir'][:, 0] = (kl['ePointInOctaveX'] - kl['sPointInOctaveX']).astype(np.float32)
+        q['dir'][:, 1] = (kl['ePointInOctaveY'] - kl['sPointInOctaveY']).astype(np.float32)
+        q['length'] = kl['lineLength']
+        has_obs = np.asarray(last['has_obs'], bool)
+        q['claims'] = has_obs
+        if M == 0:
+            return 0, np.full(0, -1, np.int32)
+        idx, _, nm = self._line_matcher(Cur, False).search(q, np.asarray(last['desc'], np.uint8), Cur.get('claimed'), 1, self.mfNNratio)
+        self._apply(Cur, np.arange(M), idx, has_obs)
+        return nm, idx.copy()
 
     @staticmethod
     def DescriptorDistance(a, b):

@@ -335,6 +335,63 @@ int hvo_normals_sync(hvo_normals* h);
 int hvo_normals_timer_start(hvo_normals* h);
 int hvo_normals_timer_stop(hvo_normals* h, float* ms_out);
 
+/* ---- windowed line matchers -------------------------------------------------------------------------------------
+ * Replaces, for one frame at a time, Frame::AssignFeaturesToGridForLine (src/Frame.cc:849-872, src/lineIterator.cpp),
+ * Frame::GetFeaturesInAreaForLine (src/Frame.cc:1557-1631) and the two greedy searches
+ *   mode 0: LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, eval_orient, th)  (src/LSDmatcher.cpp:709-801)
+ *   mode 1: LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th)                        (src/LSDmatcher.cpp:561-664)
+ * Projection / isInFrustum / mbTrackInView / isBad stay with the caller: a query is the projected segment, the window
+ * radius (RadiusByViewingCos * th, or th), the direction threshold of GetFeaturesInAreaForLine (0.998 default, 0.96 for
+ * mode 1) and the data of the per-candidate gate.  match_idx[i] = frame line assigned to query i or -1; applying
+ * `F.mvpMapLines[match_idx[i]] = pML_i` for i ascending reproduces the reference's final state. */
+typedef struct hvo_lproj_query {
+    float x1, y1, x2, y2;  /* mTrackProjX1, Y1, X2, Y2 */
+    float r, cos_th;       /* window half-size; TH of GetFeaturesInAreaForLine */
+    double dir[3];         /* mode 0: MapLine::GetWorldVector(); mode 1: last keyline's ePointInOctave - sPointInOctave (x, y, unused) */
+    float length;          /* mode 1: lineLength of the last frame's keyline */
+    int32_t claims;        /* != 0: the map line has observations, so the line it takes is skipped by later queries */
+    int32_t reserved[2];
+} hvo_lproj_query;
+
+typedef struct hvo_lproj hvo_lproj;
+int hvo_lproj_create(int device, hvo_lproj** out);
+void hvo_lproj_destroy(hvo_lproj* h);
+/* mvKeylinesUn, mvKeyLineFunctions [n][3], mLdesc [n][32], mvLines3D [n][6] = first.xyz, second.xyz (NULL when only mode 1 is
+ * used) of the frame searched in (n <= 1024); image bounds mnMinX.. .  Builds the 64 x 48 line grid on the device. */
+int hvo_lproj_set_frame(hvo_lproj* h, const hvo_keyline* keylines_un, const double* line_functions, const uint8_t* desc, const double* lines3d,
+                        int n, float min_x, float min_y, float max_x, float max_y);
+/* inspection: cell_count [64*48] (cell = ix * 48 + iy); cell_items (may be NULL) = mGridForLine[ix][iy] concatenated */
+int hvo_lproj_get_grid(hvo_lproj* h, int32_t* cell_count, int32_t* cell_items, int capacity, int* n_items);
+/* Frame::GetFeaturesInAreaForLine(x1, y1, x2, y2, r, -, -, TH): indices in the reference's order; *n_out may exceed capacity */
+int hvo_lproj_features_in_area(hvo_lproj* h, float x1, float y1, float x2, float y2, float r, float cos_th, int32_t* out, int capacity,
+                               int* n_out);
+/* claimed [n] or NULL: lines that hold a map line with observations at call time.  Accept best <= 95; mode 0 also applies
+ * the same-octave ratio test with nnratio (mfNNratio).  match_dist may be NULL. */
+int hvo_lproj_search(hvo_lproj* h, const hvo_lproj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, float nnratio,
+                     int32_t* match_idx, int32_t* match_dist, int* n_matches);
+int hvo_lproj_last_rounds(const hvo_lproj* h);
+int hvo_lproj_last_launches(const hvo_lproj* h);
+
+/* ---- LPVO normals -------------------------------------------------------------------------------------------
+ * Replaces Manhattan::computeNormalsLPVO (src/Manhattan.cpp:237-393, intrinsics :12-18), which Frame::ExtractMainImgPtNormals
+ * runs on every frame until the Manhattan axes are initialised (src/Frame.cc:218-228): tangent vectors by central
+ * differences where 0.2 <= z <= 7, seven cv::integral images, 10x10 box means every 15 px from (10, 10), normal = v x u,
+ * cv::normalize.  Outputs per frame, in the reference's push_back order: pt_normals (3 doubles each), depth_normals
+ * (float) and the pixel (u, v) of each sample.  Input is the raw 16-bit depth; z = (float)raw * depth_factor (the
+ * reference's live caller passes the 16-bit Mat where a float Mat is read: that bug is not reproduced). */
+typedef struct hvo_lpvo hvo_lpvo;
+int hvo_lpvo_create(const hvo_plane_params* cam, int width, int height, int max_batch, int device, hvo_lpvo** out);
+void hvo_lpvo_destroy(hvo_lpvo* h);
+int hvo_lpvo_capacity(const hvo_lpvo* h); /* lattice samples per frame = rows of every output array per frame */
+/* normals3 [n][capacity][3] double, depth [n][capacity] float, pix2 [n][capacity][2] int32, counts [n] int32 */
+int hvo_lpvo_compute_batch(hvo_lpvo* h, const uint16_t* depth16, int nframes, double* normals3, float* depth, int32_t* pix2,
+                           int32_t* counts);
+int hvo_lpvo_compute_batch_device(hvo_lpvo* h, const uint16_t* d_depth16, int nframes, double* d_normals3, float* d_depth,
+                                  int32_t* d_pix2, int32_t* d_counts);
+int hvo_lpvo_sync(hvo_lpvo* h);
+int hvo_lpvo_timer_start(hvo_lpvo* h);
+int hvo_lpvo_timer_stop(hvo_lpvo* h, float* ms_out);
+
 /* ---------------------------------------------------------------------------------------------- FRAME
  * The extraction part of Frame::Frame(imGray, imDepth, timeStamp, extractors, ...) (src/Frame.cc:188-233): the reference
  * runs three std::threads on one frame — ExtractORBNDepth (:874-884), ExtractLSD (:895-903), ComputePlanes

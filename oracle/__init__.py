@@ -435,6 +435,81 @@ def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoo
     return (out, dist) if want_dist else out
 
 
+# ---- windowed line matchers (Frame.cc:849-872, 1557-1631; LSDmatcher.cpp:561-664, 709-801) -----------------------------
+LPROJ_QUERY_DTYPE = np.dtype([('x1', '<f4'), ('y1', '<f4'), ('x2', '<f4'), ('y2', '<f4'), ('r', '<f4'), ('cos_th', '<f4'), ('dir', '<f8', (3,)),
+                              ('length', '<f4'), ('claims', '<i4'), ('reserved', '<i4', (2,))])
+assert LPROJ_QUERY_DTYPE.itemsize == 64
+
+
+def line_grid_build(keylines, bounds):
+    kl = np.ascontiguousarray(keylines, KL_DTYPE)
+    cnt = np.empty(64 * 48, np.int32)
+    f = C.c_float
+    lib().orc_line_grid_build.restype = C.c_int
+    m = lib().orc_line_grid_build(_p(kl), C.c_int(len(kl)), f(bounds[0]), f(bounds[1]), f(bounds[2]), f(bounds[3]), _p(cnt), None)
+    items = np.empty(max(m, 1), np.int32)
+    lib().orc_line_grid_build(_p(kl), C.c_int(len(kl)), f(bounds[0]), f(bounds[1]), f(bounds[2]), f(bounds[3]), _p(cnt), _p(items))
+    return cnt, items[:m]
+
+
+def line_features_in_area(keylines, func3, bounds, x1, y1, x2, y2, r, TH=0.998):
+    kl = np.ascontiguousarray(keylines, KL_DTYPE)
+    fn = np.ascontiguousarray(func3, np.float64)
+    out = np.empty(max(len(kl), 1), np.int32)
+    f = C.c_float
+    lib().orc_line_features_in_area.restype = C.c_int
+    n = lib().orc_line_features_in_area(_p(kl), _p(fn), C.c_int(len(kl)), f(bounds[0]), f(bounds[1]), f(bounds[2]), f(bounds[3]), f(x1), f(y1),
+                                        f(x2), f(y2), f(r), f(TH), _p(out), C.c_int(len(out)))
+    return out[:n].copy()
+
+
+def line_search_projection(keylines, func3, desc, lines3d, bounds, queries, qdesc, claimed=None, mode=0, nnratio=0.95):
+    kl = np.ascontiguousarray(keylines, KL_DTYPE)
+    fn = np.ascontiguousarray(func3, np.float64)
+    d = np.ascontiguousarray(desc, np.uint8)
+    l3 = np.zeros((len(kl), 6)) if lines3d is None else np.ascontiguousarray(lines3d, np.float64)
+    q = np.ascontiguousarray(queries, LPROJ_QUERY_DTYPE)
+    qd = np.ascontiguousarray(qdesc, np.uint8)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    idx = np.full(max(len(q), 1), -1, np.int32); dist = np.full(max(len(q), 1), 256, np.int32)
+    f = C.c_float
+    lib().orc_line_search_projection.restype = C.c_int
+    nm = lib().orc_line_search_projection(_p(kl), _p(fn), _p(d), _p(l3), C.c_int(len(kl)), f(bounds[0]), f(bounds[1]), f(bounds[2]), f(bounds[3]),
+                                          _p(q), _p(qd), C.c_int(len(q)), _p(cl) if cl is not None else None, C.c_int(mode), f(nnratio),
+                                          _p(idx), _p(dist))
+    return idx[:len(q)], dist[:len(q)], nm
+
+
+# ---- LPVO normals (Manhattan::computeNormalsLPVO, Manhattan.cpp:237-393) ------------------------------------------
+def integral_f32(img):
+    """cv::integral(CV_32F -> CV_64F) without the leading zero row / column."""
+    a = np.ascontiguousarray(img, np.float32)
+    out = np.empty(a.shape, np.float64)
+    lib().orc_integral_f32(_p(a), C.c_int(a.shape[1]), C.c_int(a.shape[0]), _p(out))
+    return out
+
+
+def normalize3(v):
+    """cv::normalize of a 3-vector of doubles (NORM_L2)."""
+    a = np.ascontiguousarray(v, np.float64).reshape(3)
+    out = np.empty(3, np.float64)
+    lib().orc_normalize3(_p(a), _p(out))
+    return out
+
+
+def lpvo_normals(depth16, factor, fx, fy, cx, cy):
+    """-> (normals [n,3] float64, depth [n] float32, pixel (u, v) [n,2] int32) in the reference's push_back order."""
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    cap = ((h - 1 - 10 + 14) // 15) * ((w - 1 - 10 + 14) // 15)
+    nrm = np.empty((cap, 3), np.float64); dep = np.empty(cap, np.float32); pix = np.empty((cap, 2), np.int32)
+    lib().orc_lpvo_normals.restype = C.c_int
+    n = lib().orc_lpvo_normals(_p(d), C.c_int(w), C.c_int(h), C.c_float(factor), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                               _p(nrm), _p(dep), _p(pix), C.c_int(cap))
+    assert 0 <= n <= cap
+    return nrm[:n], dep[:n], pix[:n]
+
+
 # ---- whole front-end (bench.py CPU arm) ----------------------------------------------------------------------
 def frontend_batch(gray, depth, cam, stages=15, nthreads=1, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                    nlines=200):

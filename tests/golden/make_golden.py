@@ -5,6 +5,8 @@ fixture, oracle/_ref/ref_orb = the reference's own src/ORBextractor.cc built by 
 
 prims_cv2.npz  inputs + outputs of the OpenCV primitives the reference calls (cv2 4.13.0 is the pin)
 orb_ref.npz    inputs + outputs of the reference's ORBextractor.cc on small frames
+lpvo_cv2.npz   inputs + outputs of the two cv2 primitives inside Manhattan::computeNormalsLPVO (Manhattan.cpp:312-326, :381):
+               cv2.integral (CV_32F -> CV_64F) and cv2.normalize of 3x1 double vectors
 lsd_cv2.npz    inputs + outputs of cv2.createLineSegmentDetector().detect (what LSDDetector_custom.cpp:149,158 calls) and of
                the two cv2 primitives inside it (GaussianBlur 7x7 sigma 0.75, resize 0.8 INTER_LINEAR_EXACT)
 """
@@ -113,8 +115,24 @@ def lsd():
     print('lsd_cv2.npz written')
 
 
+def lpvo():
+    assert cv2.__version__ == '4.13.0', cv2.__version__
+    r = np.random.RandomState(21)
+    img = (r.randn(48, 64) * r.choice([1e-3, 1.0, 50.0], (48, 64))).astype(np.float32)
+    img[r.rand(48, 64) < 0.3] = 0
+    vec = r.randn(256, 3) * r.choice([1e-9, 1e-3, 1.0], (256, 1))
+    vec[0] = 0
+    out = dict(img=img, integral=cv2.integral(img)[1:, 1:], vec=vec,
+               normalized=np.stack([cv2.normalize(v.reshape(3, 1), None).ravel() for v in vec]), cv2_version=np.array(cv2.__version__))
+    assert out['integral'].dtype == np.float64
+    np.savez_compressed(os.path.join(OUT, 'lpvo_cv2.npz'), **out)
+    print('lpvo_cv2.npz written')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo']
+    if 'lpvo' in which:
+        lpvo()
     if 'prims' in which:
         prims()
     if 'orb' in which:
