@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libhvofront.so')
+LIB_PATH = os.environ.get('HVO_LIB_PATH') or os.path.join(_HERE, 'libhvofront.so')  # HVO_LIB_PATH: tuning aid (a differently built library)
 
 HVO_OK, HVO_ERR_ARG, HVO_ERR_CUDA, HVO_ERR_STATE, HVO_ERR_OVERFLOW = 0, 1, 2, 3, 4
 
@@ -89,6 +89,7 @@ ABI = {
     'hvo_proj_last_rounds': (C.c_int, [_vp]),
     'hvo_proj_last_launches': (C.c_int, [_vp]),
     'hvo_proj_match_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    'hvo_proj_search_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
     'hvo_proj_timer_start': (C.c_int, [_vp]),
     'hvo_proj_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_line_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -1121,6 +1122,19 @@ class ProjectionMatcher:
         self.n = 0
         return best4[:len(q)]
 
+    def search_candidates(self, q, t, offsets, cand, th_dist=50, nnratio=0.7):
+        """greedy best / second over caller-given candidate lists (the loop of ORBmatcher::SearchByBoW)."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        cd = np.ascontiguousarray(cand, np.int32)
+        idx = np.full(max(len(q), 1), -1, np.int32); dist = np.full(max(len(q), 1), 256, np.int32)
+        nm = C.c_int(0)
+        _check(lib().hvo_proj_search_candidates(self._h, _np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(off), _np_ptr(cd), int(th_dist),
+                                                float(np.float32(nnratio)), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
+        self.n = 0
+        return idx[:len(q)], dist[:len(q)], nm.value
+
     def timer_start(self):
         _check(lib().hvo_proj_timer_start(self._h))
 
@@ -1184,6 +1198,54 @@ class ORBmatcher:
                     F['claimed'][i] = True
                 else:
                     F['claimed'][i] = False
+        return nm, match
+
+    @staticmethod
+    def bow_queries(featvec_kf, featvec_f, kf_has_mappoint):
+        """The visiting order of SearchByBoW (ORBmatcher.cc:180-266): vocabulary nodes present in both DBoW2::FeatureVectors,
+        ascending; inside a node the key frame's index list, keeping features that hold a good map point; candidates = the
+        frame's index list of that node.  featvec_* : dict node id -> list of feature indices.  Returns (query feature index
+        [nq], offsets [nq+1], cand)."""
+        qi, off, cand = [], [0], []
+        for node in sorted(set(featvec_kf) & set(featvec_f)):
+            fl = list(featvec_f[node])
+            for i in featvec_kf[node]:
+                if kf_has_mappoint[i]:
+                    qi.append(i); cand.extend(fl); off.append(len(cand))
+        return np.asarray(qi, np.int32), np.asarray(off, np.int32), np.asarray(cand, np.int32)
+
+    def SearchByBoW(self, KF, F):
+        """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:162-293).
+        KF = dict(desc [N,32], keys_un KP_DTYPE, featvec {node: [idx]}, has_mappoint [N] bool (map point present and not bad));
+        F  = dict(desc [M,32], keys KP_DTYPE, featvec).  Returns (nmatches, match [M] = key-frame feature whose map point the
+        frame feature received, or -1)."""
+        qi, off, cand = self.bow_queries(KF['featvec'], F['featvec'], np.asarray(KF['has_mappoint'], bool))
+        M = len(F['desc'])
+        match = np.full(M, -1, np.int32)
+        if len(qi) == 0:
+            return 0, match
+        idx, _, nm = self._pm.search_candidates(np.asarray(KF['desc'], np.uint8)[qi], F['desc'], off, cand, self.TH_LOW, self.mfNNratio)
+        hist = [[] for _ in range(self.HISTO_LENGTH)]
+        factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+        for k, i in zip(qi, idx):
+            if i < 0:
+                continue
+            match[i] = k
+            if self.mbCheckOrientation:
+                rot = np.float32(KF['keys_un']['angle'][k]) - np.float32(F['keys']['angle'][i])
+                if rot < 0.0:
+                    rot = np.float32(rot + np.float32(360.0))
+                b = int(np.floor(float(np.float32(rot * factor)) + 0.5))  # round(): rot >= 0 here
+                if b == self.HISTO_LENGTH:
+                    b = 0
+                hist[b].append(i)
+        if self.mbCheckOrientation:
+            keep = set(self.ComputeThreeMaxima([len(h) for h in hist]))
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for i in hist[b]:
+                        match[i] = -1
+                        nm -= 1
         return nm, match
 
     @staticmethod

@@ -28,15 +28,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: tuning aid, builds a variant (e.g. extra=['-DHVO_FAST_THREADS=64']) next to the product library."""
+    if out is None and not force and not needs_build():
         return OUT
+    out = out or OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + (['-Xptxas', '-v'] if verbose else []) + ['-o', out] + sources()
     print(' '.join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == '__main__':
-    build(force='--force' in sys.argv, verbose='-v' in sys.argv)
+    defs = [a for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    build(force='--force' in sys.argv, verbose='-v' in sys.argv, out=outs[0] if outs else None, extra=defs)

@@ -141,6 +141,10 @@ __device__ __forceinline__ int fast_strength(const int (&d)[16]) {
      : (k) == 11 ? (p)[-(st) - 3] : (k) == 12 ? (p)[-3] : (k) == 13 ? (p)[(st) - 3] : (k) == 14 ? (p)[2 * (st) - 2]    \
                                                                                                 : (p)[3 * (st) - 1])
 
+#ifndef HVO_FAST_THREADS
+#define HVO_FAST_THREADS 128
+#endif
+static const int kFastThreads = HVO_FAST_THREADS, kFastWarps = kFastThreads / 32;
 static const int kTW = 20;                 // tile row stride in 32-bit words: (60 + 6 + 3 alignment) bytes <= 72
 static const int kTileBytes = kTW * 4;     // 80
 
@@ -158,7 +162,7 @@ __device__ __forceinline__ uint32_t ring4(const uint32_t* row, int g, int dx) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbGeom g, ImgSrc src,
+__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_constant__ OrbGeom g, ImgSrc src,
                                                     const CellDesc* __restrict__ cells, uint32_t* __restrict__ cand,
                                                     int* __restrict__ ncand, int ini_th, int min_th) {
     // tile words are stored from index 1 so that group g may read word g-1 (content unused when g == 0)
@@ -184,26 +188,28 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbG
     const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
     if (aligned) {
         // all row loads of a warp are issued before the first store: <= 9 independent 128-bit-coalesced requests in flight
-        uint32_t w[9];
+        for (int rb = 0; rb < th; rb += 9 * kFastWarps) {
+            uint32_t w[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int r = warp + 8 * k;
-            if (r < th && lane < nw) w[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)(ty0 + r) * pitch + xal + 4 * lane));
-        }
+            for (int k = 0; k < 9; ++k) {
+                const int r = rb + warp + kFastWarps * k;
+                if (r < th && lane < nw) w[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)(ty0 + r) * pitch + xal + 4 * lane));
+            }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int r = warp + 8 * k;
-            if (r < th && lane < nw) tile[r * kTW + lane] = w[k];
+            for (int k = 0; k < 9; ++k) {
+                const int r = rb + warp + kFastWarps * k;
+                if (r < th && lane < nw) tile[r * kTW + lane] = w[k];
+            }
         }
     } else {
-        for (int r = warp; r < th; r += 8) {
+        for (int r = warp; r < th; r += kFastWarps) {
             if (lane < nw) {
                 const uint8_t* p = img + (long long)(ty0 + r) * pitch + xal + 4 * lane;
                 tile[r * kTW + lane] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
             }
         }
     }
-    for (int i = tid; i < zh * (kMaxCell / 4); i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    for (int i = tid; i < zh * (kMaxCell / 4); i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
     if (tid == 0) { s_ncorner = 0; s_nini = 0; s_nmin = 0; s_slot = 0; }
     __syncthreads();
 
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbG
     const uint32_t magic = (65536u + ng - 1) / ng;  // i / ng for i < 4096
     const bool use_quick = low_th <= 127;
     const uint32_t K = (uint32_t)(127 - min(low_th, 127)) * 0x01010101u;
-    for (int i = tid; i < ng * zh; i += 256) {
+    for (int i = tid; i < ng * zh; i += kFastThreads) {
         int zy = (int)(((uint32_t)i * magic) >> 16);
         if (zy * ng > i) --zy;
         const int gi = g0 + (i - zy * ng);
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbG
     // ---- pass 2: exact threshold-independent strength for the survivors; corner at t  <=>  S >= t ----
     const uint8_t* tile_b = reinterpret_cast<const uint8_t*>(tile);
     const int ncorner = s_ncorner;
-    for (int i = tid; i < ncorner; i += 256) {
+    for (int i = tid; i < ncorner; i += kFastThreads) {
         const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
         const uint8_t* p = tile_b + (zy + 3) * kTileBytes + zb0 + zx;
         const int v = *p;
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbG
 
     // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the zone counts as 0) ----
     uint32_t f_ini = 0, f_min = 0;
-    for (int i = tid, it = 0; i < ncorner; i += 256, ++it) {
+    for (int i = tid, it = 0; i < ncorner; i += kFastThreads, ++it) {
         const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
         const int s = score[pos];
         bool is_max = s > 0;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ OrbG
     while (m) {
         const int it = __ffs(m) - 1;
         m &= m - 1;
-        const int pos = clist[tid + 256 * it];
+        const int pos = clist[tid + kFastThreads * it];
         const int zy = pos / kMaxCell, zx = pos % kMaxCell;
         const int slot = atomicAdd(&s_slot, 1);
         if (s_base + slot < L.cand_cap)
@@ -934,7 +940,7 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     if (profiling) HVO_CUDA(cudaEventRecord(ev[1], stream));
     // K2: FAST cells
     if (ncells > 0) {
-        k_fast_cells<<<dim3(ncells, B), 256, 0, stream>>>(g, src, d_cells, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
+        k_fast_cells<<<dim3(ncells, B), kFastThreads, 0, stream>>>(g, src, d_cells, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
         ++launches;
     }
     if (profiling) HVO_CUDA(cudaEventRecord(ev[2], stream));

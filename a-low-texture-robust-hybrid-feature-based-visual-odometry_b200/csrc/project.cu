@@ -217,6 +217,48 @@ __global__ void __launch_bounds__(128) k_match_candidates(const uint4* __restric
     if (lane == 0) best4[k] = make_int4(i0, d0, i1, d1);
 }
 
+// Greedy search over caller-given candidate lists (ORBmatcher::SearchByBoW, src/ORBmatcher.cc:197-251): query k skips train
+// rows already assigned to an earlier query (vpMapPointMatches[realIdxF] != NULL), keeps best / second with strict '<', and
+// takes the best when best <= th_dist and (float)best < nnratio * (float)second.  One round of the fixed-point iteration.
+__global__ void __launch_bounds__(128) k_cand_round(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, const int* __restrict__ off,
+                                                    const int* __restrict__ cand, const int* __restrict__ claim_prev, int* __restrict__ claim_next,
+                                                    int th_dist, float nnratio, int* __restrict__ choice, int* __restrict__ choice_dist,
+                                                    int* __restrict__ changed) {
+    const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= nq) return;
+    const uint4 qa = q[2 * k], qb = q[2 * k + 1];
+    int d0 = 256, i0 = -1, d1 = 256;
+    const int b = off[k], e = off[k + 1];
+    for (int base = b; base < e; base += 32) {
+        const int i = base + lane;
+        int id = -1, dist = 256;
+        bool ok = false;
+        if (i < e) {
+            id = cand[i];
+            ok = !(claim_prev[id] < k);
+            if (ok) {
+                const uint4 da = t[2 * id], db = t[2 * id + 1];
+                dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) + __popc(qb.x ^ db.x) +
+                       __popc(qb.y ^ db.y) + __popc(qb.z ^ db.z) + __popc(qb.w ^ db.w);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int d = __shfl_sync(0xffffffffu, dist, j), c = __shfl_sync(0xffffffffu, id, j);
+            if (d < d0) { d1 = d0; d0 = d; i0 = c; }
+            else if (d < d1) d1 = d;
+        }
+    }
+    const int pick = (i0 >= 0 && d0 <= th_dist && (float)d0 < __fmul_rn(nnratio, (float)d1)) ? i0 : -1;
+    if (lane == 0) {
+        if (choice[k] != pick) { choice[k] = pick; *changed = 1; }
+        choice_dist[k] = pick >= 0 ? d0 : 256;
+        if (pick >= 0) atomicMin(&claim_next[pick], k);
+    }
+}
+
 }  // namespace hvo
 
 using namespace hvo;
@@ -446,6 +488,56 @@ int hvo_proj_match_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8
     HVO_CUDA(cudaStreamSynchronize(s));
     h->n = 0;  // the frame descriptors were overwritten: hvo_proj_set_frame must be called again before the next search
     h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_proj_search_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
+                               int th_dist, float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
+    HVO_CHECK_ARG(h && match_idx, "null argument");
+    if (n_matches) *n_matches = 0;
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(q && offsets, "null argument");
+    const int total = offsets[nq];
+    HVO_CHECK_ARG(total >= 0 && (total == 0 || (cand && t && nt > 0)), "candidate lists without a train set");
+    for (int i = 0; i < total; ++i) HVO_CHECK_ARG(cand[i] >= 0 && cand[i] < nt, "candidate index out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_queries(h, nq);
+    if (st == HVO_OK) st = proj_reserve_keys(h, std::max(nt, 1));
+    if (st != HVO_OK) return st;
+    if (total > h->ccap) {
+        if ((st = grow(h->d_cand, (size_t)std::max(total, 4096)))) return st;
+        h->ccap = std::max(total, 4096);
+    }
+    cudaStream_t s = h->stream;
+    h->n = 0;  // the frame descriptors are overwritten: hvo_proj_set_frame must be called again before the next windowed search
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt > 0) HVO_CUDA(cudaMemcpyAsync(h->d_desc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_off, offsets, ((size_t)nq + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (total > 0) HVO_CUDA(cudaMemcpyAsync(h->d_cand, cand, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s));
+    const int nk = std::max(nt, 1);
+    k_proj_claim_init<<<div_up(nk, 256), 256, 0, s>>>(nullptr, nk, h->d_claim0);
+    HVO_CUDA(cudaMemcpyAsync(h->d_claim_a, h->d_claim0, (size_t)nk * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    k_proj_fill<<<div_up(nq, 256), 256, 0, s>>>(h->d_choice, nq, -2);
+    int launches = 2, rounds = 0;
+    int *prev = h->d_claim_a, *next = h->d_claim_b;
+    while (true) {
+        HVO_CUDA(cudaMemcpyAsync(next, h->d_claim0, (size_t)nk * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        HVO_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+        k_cand_round<<<div_up(nq * 32, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(h->d_qdesc), nq, reinterpret_cast<const uint4*>(h->d_desc),
+                                                          h->d_off, h->d_cand, prev, next, th_dist, nnratio, h->d_choice, h->d_cdist, h->d_flag);
+        HVO_CUDA(cudaGetLastError());
+        HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        HVO_CUDA(cudaStreamSynchronize(s));
+        ++launches; ++rounds;
+        if (!h->h_flag[0]) break;
+        if (rounds > nq + 1) { set_error("candidate search did not reach its fixed point"); return HVO_ERR_CUDA; }
+        std::swap(prev, next);
+    }
+    h->last_rounds = rounds; h->last_launches = launches;
+    HVO_CUDA(cudaMemcpyAsync(match_idx, h->d_choice, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, h->d_cdist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
     return HVO_OK;
 }
 

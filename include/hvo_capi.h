@@ -176,6 +176,13 @@ int hvo_proj_last_launches(const hvo_proj* h);
  * strict '<' updates (-1 / 256 where absent).  Invalidates the frame set by hvo_proj_set_frame. */
 int hvo_proj_match_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
                               int32_t* best4);
+/* The greedy loop of ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:180-251) over the same kind of lists:
+ * queries = the key frame's features that hold a good map point, in the reference's visiting order (vocabulary node
+ * ascending, then the node's index list); cand lists = the frame's features of the same node.  Query i skips train rows
+ * taken by an earlier query of this call, and takes its best when best <= th_dist and (float)best < nnratio * (float)second.
+ * match_idx[i] = frame feature or -1.  Invalidates the frame set by hvo_proj_set_frame. */
+int hvo_proj_search_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
+                               int th_dist, float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches);
 int hvo_proj_timer_start(hvo_proj* h);
 int hvo_proj_timer_stop(hvo_proj* h, float* ms_out);
 

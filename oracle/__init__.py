@@ -281,6 +281,16 @@ def match_candidates(q, t, offsets, cand):
     return best4[:len(q)]
 
 
+def search_candidates(q, t, offsets, cand, th_dist=50, nnratio=0.7):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)
+    idx = np.full(max(len(q), 1), -1, np.int32); dist = np.full(max(len(q), 1), 256, np.int32)
+    f = lib().orc_search_candidates
+    f.restype = C.c_int
+    nm = f(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(off), _p(cd), C.c_int(th_dist), C.c_float(nnratio), _p(idx), _p(dist))
+    return idx[:len(q)], dist[:len(q)], nm
+
+
 # ---- lines: LSD wrapper fields + LBD ---------------------------------------------------------------------
 KL_DTYPE = np.dtype([('angle', '<f4'), ('class_id', '<i4'), ('octave', '<i4'), ('pt_x', '<f4'), ('pt_y', '<f4'),
                      ('response', '<f4'), ('size', '<f4'), ('startPointX', '<f4'), ('startPointY', '<f4'),

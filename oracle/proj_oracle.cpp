@@ -156,4 +156,24 @@ void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int3
     }
 }
 
+// the greedy loop of ORBmatcher::SearchByBoW (src/ORBmatcher.cc:197-251) over the same kind of candidate lists: a train row
+// assigned to an earlier query is skipped (:216-217); accept best <= th_dist && (float)best < nnratio * (float)second (:235-239)
+int orc_search_candidates(const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* off, const int32_t* cand, int th_dist, float nnratio,
+                          int32_t* match_idx, int32_t* match_dist) {
+    std::vector<char> taken(nt > 0 ? nt : 1, 0);
+    int nm = 0;
+    for (int i = 0; i < nq; ++i) {
+        int d0 = 256, i0 = -1, d1 = 256;
+        for (int c = off[i]; c < off[i + 1]; ++c) {
+            if (taken[cand[c]]) continue;
+            const int d = projo::hamming(q + 32 * (size_t)i, t + 32 * (size_t)cand[c]);
+            if (d < d0) { d1 = d0; d0 = d; i0 = cand[c]; }
+            else if (d < d1) d1 = d;
+        }
+        match_idx[i] = -1; match_dist[i] = 256;
+        if (i0 >= 0 && d0 <= th_dist && (float)d0 < nnratio * (float)d1) { match_idx[i] = i0; match_dist[i] = d0; taken[i0] = 1; ++nm; }
+    }
+    return nm;
+}
+
 }  // extern "C"

@@ -214,3 +214,71 @@ def test_orbmatcher_search_by_projection_last_mirror(hvo, synth):
     oidx, _, on = oracle.search_projection(F['keys_un'], F['uright'], F['desc'], BOUNDS, q, last['desc'], claimed0.astype(np.uint8), 1, 100, 0.9)
     assert np.array_equal(idx, oidx)
     assert 0 < nm <= on                                                    # the rotation histogram only removes matches
+
+
+def _bow_scenario(synth, seed=0):
+    """Key frame = ORB of S1/0, frame = ORB of S1/1; the vocabulary node of a feature is faked by a coarse hash of its position and
+    octave (what matters to the matcher is only which features share a node)."""
+    rng = np.random.RandomState(seed)
+    k0, d0 = _frame_keys(synth, 'S1', 0)
+    k1, d1 = _frame_keys(synth, 'S1', 1)
+    node = lambda k: (k['x'] // 80).astype(int) * 100 + (k['y'] // 80).astype(int) * 10 + (k['octave'] // 3)
+    fv0, fv1 = {}, {}
+    for i, n in enumerate(node(k0)):
+        fv0.setdefault(int(n), []).append(i)
+    for i, n in enumerate(node(k1)):
+        fv1.setdefault(int(n), []).append(i)
+    has_mp = rng.rand(len(k0)) > 0.3
+    return dict(desc=d0, keys_un=k0, featvec=fv0, has_mappoint=has_mp), dict(desc=d1, keys=k1, featvec=fv1)
+
+
+def test_oracle_search_candidates_is_greedy():
+    q = np.zeros((3, 32), np.uint8)
+    t = np.zeros((3, 32), np.uint8); t[1, 0] = 0x0f; t[2, :2] = 0xff               # distances 0, 4, 16 to every query
+    off = np.array([0, 3, 6, 9], np.int32); cand = np.tile(np.arange(3, dtype=np.int32), 3)
+    idx, dist, n = oracle.search_candidates(q, t, off, cand, th_dist=50, nnratio=0.7)
+    # query 0: best 0 < 0.7 * 4 -> takes row 0; query 1: best 4 < 0.7 * 16 -> row 1; query 2: only row 2 left, second = 256 -> row 2
+    assert idx.tolist() == [0, 1, 2] and dist.tolist() == [0, 4, 16] and n == 3
+    idx, _, n = oracle.search_candidates(q, t, off, cand, th_dist=3, nnratio=0.7)   # TH below 4: queries 1 and 2 fail
+    assert idx.tolist() == [0, -1, -1] and n == 1
+    t[1, 0] = 0                                                                     # tie 0 / 0: 0 < 0.7 * 0 is false
+    idx, _, n = oracle.search_candidates(q, t, off, cand, th_dist=50, nnratio=0.7)
+    assert idx.tolist() == [-1, -1, -1] and n == 0
+
+
+@pytest.mark.gpu
+def test_gpu_search_candidates_and_search_by_bow(hvo, synth):
+    KF, F = _bow_scenario(synth)
+    m = hvo.ORBmatcher(0.7, True)
+    qi, off, cand = m.bow_queries(KF['featvec'], F['featvec'], KF['has_mappoint'])
+    assert len(qi) > 300 and np.all(KF['has_mappoint'][qi])
+    pm = hvo.ProjectionMatcher()
+    idx, dist, nm = pm.search_candidates(KF['desc'][qi], F['desc'], off, cand, 50, 0.7)
+    ridx, rdist, rnm = oracle.search_candidates(KF['desc'][qi], F['desc'], off, cand, 50, 0.7)
+    assert rnm > 50 and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and nm == rnm
+    taken = idx[idx >= 0]
+    assert len(set(taken.tolist())) == len(taken)                                   # a frame feature is given away once
+    # heavy contention: every query sees the same short list
+    q = np.repeat(KF['desc'][qi[:1]], 30, axis=0)
+    off2 = (np.arange(31) * 12).astype(np.int32); cand2 = np.tile(cand[off[0]:off[0] + 12] if off[1] - off[0] >= 12 else np.arange(12, dtype=np.int32), 30)
+    idx, dist, nm = pm.search_candidates(q, F['desc'], off2, cand2, 255, 1.1)
+    ridx, rdist, rnm = oracle.search_candidates(q, F['desc'], off2, cand2, 255, 1.1)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and nm == rnm and pm.rounds() > 2
+    pm.close()
+    # the mirror: same assignment, then the rotation-histogram filter (ORBmatcher.cc:268-290)
+    nm, match = m.SearchByBoW(KF, F)
+    ridx, _, rnm = oracle.search_candidates(KF['desc'][qi], F['desc'], off, cand, 50, 0.7)
+    want = np.full(len(F['desc']), -1, np.int32)
+    hist = [[] for _ in range(30)]
+    for k, i in zip(qi, ridx):
+        if i >= 0:
+            want[i] = k
+            rot = np.float32(KF['keys_un']['angle'][k]) - np.float32(F['keys']['angle'][i])
+            rot = np.float32(rot + np.float32(360)) if rot < 0 else rot
+            b = int(np.floor(float(np.float32(rot * (np.float32(1) / np.float32(30)))) + 0.5)) % 30
+            hist[b].append(i)
+    keep = set(m.ComputeThreeMaxima([len(h) for h in hist]))
+    for b in range(30):
+        if b not in keep:
+            want[hist[b]] = -1
+    assert np.array_equal(match, want) and nm == int((want >= 0).sum()) > 20
