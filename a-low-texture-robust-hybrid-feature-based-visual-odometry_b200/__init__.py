@@ -150,6 +150,8 @@ ABI = {
     'hvo_lpvo_sync': (C.c_int, [_vp]),
     'hvo_lpvo_timer_start': (C.c_int, [_vp]),
     'hvo_lpvo_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_timeline_enable': (C.c_int, [C.c_int]),
+    'hvo_timeline_dump': (C.c_int, [C.c_char_p, C.c_int]),
     'hvo_frame_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'hvo_frame_destroy': (None, [_vp]),
     'hvo_frame_capacities': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -161,6 +163,18 @@ ABI = {
     'hvo_frame_timer_start': (C.c_int, [_vp]),
     'hvo_frame_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
+
+
+def timeline(on):
+    """profiling aid: start (True) or stop (False) recording one timed event per kernel launch site."""
+    _check(lib().hvo_timeline_enable(int(bool(on))))
+
+
+def timeline_dump():
+    """-> list of (ms since the first mark, stream id, name); call after the work has been synchronised."""
+    buf = C.create_string_buffer(1 << 20)
+    _check(lib().hvo_timeline_dump(buf, len(buf)))
+    return [(float(a), int(b), c) for a, b, c in (ln.split() for ln in buf.value.decode().splitlines())]
 
 
 def lib():

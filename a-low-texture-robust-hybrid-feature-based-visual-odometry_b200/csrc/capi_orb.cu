@@ -2,7 +2,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "orb.cuh"
 
@@ -17,6 +19,19 @@ void set_error(const char* fmt, ...) {
 static thread_local int g_stream_priority = 0;
 void set_next_stream_priority(int priority) { g_stream_priority = priority; }
 cudaError_t create_stream(cudaStream_t* s) { return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, g_stream_priority); }
+struct TimelineEntry { cudaEvent_t ev; const char* name; cudaStream_t stream; };
+static std::mutex g_tl_mutex;
+static std::vector<TimelineEntry> g_tl;
+static bool g_tl_on = false;
+void timeline_mark(cudaStream_t s, const char* name) {
+    if (!g_tl_on) return;
+    std::lock_guard<std::mutex> lk(g_tl_mutex);
+    if (g_tl.size() >= 4096) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_tl.push_back({e, name, s});
+}
 int smem_carveout_percent() {
     // HVO_CARVEOUT (percent, -1 = leave the driver default) is a tuning aid; the default is chosen in DESIGN.md section 4
     static const int pc = [] { const char* e = getenv("HVO_CARVEOUT"); return e ? atoi(e) : -1; }();
@@ -33,6 +48,33 @@ cudaStream_t orb_stream(hvo_orb* h) { return h->stream; }  // internal: frame.cu
 extern "C" {
 
 const char* hvo_last_error(void) { return g_err; }
+int hvo_timeline_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_tl_mutex);
+    for (auto& t : g_tl) cudaEventDestroy(t.ev);
+    g_tl.clear();
+    g_tl_on = on != 0;
+    return HVO_OK;
+}
+/* After the work has been synchronised: one line per mark, "ms-since-first-mark stream-id name". */
+int hvo_timeline_dump(char* buf, int capacity) {
+    HVO_CHECK_ARG(buf && capacity > 0, "null buffer");
+    std::lock_guard<std::mutex> lk(g_tl_mutex);
+    int off = 0;
+    buf[0] = 0;
+    std::vector<cudaStream_t> streams;
+    for (auto& t : g_tl) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.ev) != cudaSuccess || cudaEventElapsedTime(&ms, g_tl[0].ev, t.ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        int sid = -1;
+        for (size_t i = 0; i < streams.size(); ++i) if (streams[i] == t.stream) sid = (int)i;
+        if (sid < 0) { sid = (int)streams.size(); streams.push_back(t.stream); }
+        const int n = snprintf(buf + off, (size_t)(capacity - off), "%.3f %d %s\n", ms, sid, t.name);
+        if (n < 0 || off + n >= capacity) break;
+        off += n;
+    }
+    return HVO_OK;
+}
+
 const char* hvo_version(void) { return "hvofront sm_100a " __DATE__; }
 
 int hvo_device_count(int* n_out) {

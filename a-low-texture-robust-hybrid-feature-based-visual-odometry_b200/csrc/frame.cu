@@ -86,6 +86,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
             if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
             if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
         }
+        timeline_mark(s, "end_planes");
         HVO_CUDA(cudaEventRecord(L.join[2], s));
     }
     if (h->p.stages & ST_LINE) {
@@ -101,6 +102,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
             HVO_CUDA(cudaMemcpyAsync(host->line_desc, o.line_desc, N * c * 32, cudaMemcpyDeviceToHost, s));
             if (host->linevec3) HVO_CUDA(cudaMemcpyAsync(host->linevec3, o.linevec3, N * c * 24, cudaMemcpyDeviceToHost, s));
         }
+        timeline_mark(s, "end_lines");
         HVO_CUDA(cudaEventRecord(L.join[1], s));
     }
     if (h->p.stages & ST_ORB) {
@@ -118,6 +120,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
             if (host->kp_depth) HVO_CUDA(cudaMemcpyAsync(host->kp_depth, o.kp_depth, N * c * 4, cudaMemcpyDeviceToHost, s));
             if (host->kp_uright) HVO_CUDA(cudaMemcpyAsync(host->kp_uright, o.kp_uright, N * c * 4, cudaMemcpyDeviceToHost, s));
         }
+        timeline_mark(s, "end_orb");
         HVO_CUDA(cudaEventRecord(L.join[0], s));
     }
     if (h->p.stages & ST_NORMALS) {
@@ -127,6 +130,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         if (st != HVO_OK) return st;
         *launches += 5;
         if (host) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
+        timeline_mark(s, "end_normals");
         HVO_CUDA(cudaEventRecord(L.join[3], s));
     }
     return HVO_OK;

@@ -47,6 +47,10 @@ static inline void pin_carveout(K kernel) {
 void set_next_stream_priority(int priority);
 cudaError_t create_stream(cudaStream_t* s);
 
+// Profiling aid (hvo_timeline_*): when enabled, every kernel launch site records a timed event on its stream first, so the
+// start of each kernel and the overlap between the pipelines' streams can be read back as one timeline.  Off by default.
+void timeline_mark(cudaStream_t s, const char* name);
+
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

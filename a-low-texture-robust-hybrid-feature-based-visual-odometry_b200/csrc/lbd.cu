@@ -198,8 +198,10 @@ struct hvo_lbd {
 static int lbd_run_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray, int nframes, const KeyLineDev* d_kl,
                           const int32_t* d_counts, uint8_t* d_desc, float* d_fdesc) {
     const long long fpx = (long long)h->width * h->height;
+    timeline_mark(stream, "k_lbd_grad");
     k_lbd_grad<<<dim3(div_up(h->width, kGW), div_up(h->height, kGH), nframes), 256, 0, stream>>>(d_gray, h->width, h->height, fpx,
                                                                                               h->d_dx, h->d_dy);
+    timeline_mark(stream, "k_lbd_describe");
     k_lbd_describe<<<dim3(h->max_lines, nframes), 96, 0, stream>>>(h->d_dx, h->d_dy, h->width, h->height, fpx, d_kl, d_counts,
                                                                    h->max_lines, h->W, d_desc, d_fdesc);
     h->last_launches = 2;

@@ -842,12 +842,15 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
     cudaStream_t s = h->stream;
     if (h->profiling) cudaEventRecord(h->sev[0], s);
     HVO_CUDA(cudaMemsetAsync(h->d_maxsq, 0, (size_t)nframes * sizeof(int), s));
+    timeline_mark(s, "k_lsd_prep");
     k_lsd_prep<<<dim3(div_up(h->sw, kPW), div_up(h->sh, kPH), nframes), 256, 0, s>>>(
         d_gray, h->width, h->height, (long long)h->width * h->height, h->sw, h->sh, h->d_cx, h->d_cy, h->d_cstab, h->rho, h->d_pix,
         h->d_scaled, h->d_maxsq);
     if (h->profiling) cudaEventRecord(h->sev[1], s);
+    timeline_mark(s, "k_lsd_order");
     k_lsd_order<<<nframes, 1024, kOrdWarps * kBins * sizeof(uint32_t), s>>>(h->d_pix, npix, h->d_maxsq, h->d_order, h->d_norder);
     if (h->profiling) cudaEventRecord(h->sev[2], s);
+    timeline_mark(s, "k_lsd_grow");
     k_lsd_grow<<<nframes, 32, 0, s>>>(h->d_pix, h->sw, h->sh, h->d_order, h->d_norder, h->d_reg, h->min_reg_size, h->prec, 0.7, 0.8,
                                       h->d_seg, h->seg_cap, h->d_nseg, h->d_used);
     if (h->profiling) cudaEventRecord(h->sev[3], s);
@@ -860,6 +863,7 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
 static int line_cull_device(hvo_line* h, const uint8_t* d_gray, int nframes, KeyLineOut* d_kl, uint8_t* d_desc, double* d_linevec,
                             int32_t* d_counts) {
     const size_t sm = (size_t)h->nfeat * 3 + 16;
+    timeline_mark(h->stream, "k_line_cull");
     k_line_cull<<<nframes, 32, sm, h->stream>>>(d_kl, d_linevec, d_counts, h->nfeat, h->width, h->height, 5.0, std::cos(2.5 * 0.0174533),
                                                 15.0, h->d_cull, h->d_newline);
     HVO_CUDA(cudaGetLastError());
@@ -870,6 +874,7 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
                                int32_t* d_counts) {
     int st = line_detect_device(h, d_gray, nframes);
     if (st != HVO_OK) return st;
+    timeline_mark(h->stream, "k_line_keylines");
     k_line_keylines<<<nframes, 256, 0, h->stream>>>(h->d_seg, h->seg_cap, h->d_nseg, h->width, h->height, h->nfeat, h->nfeat, h->d_resp,
                                                     d_kl, d_linevec, d_counts);
     HVO_CUDA(cudaGetLastError());

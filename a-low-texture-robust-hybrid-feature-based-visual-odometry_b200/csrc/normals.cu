@@ -183,10 +183,15 @@ struct hvo_normals {
 
 static int sn_run(hvo_normals* h, const uint16_t* d_depth, int nf, float* d_out) {
     const SnGeom& g = h->g;
+    timeline_mark(h->stream, "k_sn_cloud");
     k_sn_cloud<<<dim3(div_up(g.cw, 128), g.ch, nf), 128, 0, h->stream>>>(d_depth, g, h->d_pts, h->d_dist);
+    timeline_mark(h->stream, "k_sn_rowscan");
     k_sn_rowscan<<<dim3(div_up(g.ch + 1, 64), nf), 64, 0, h->stream>>>(h->d_pts, g, h->d_sat);
+    timeline_mark(h->stream, "k_sn_colscan");
     k_sn_colscan<<<dim3(div_up((g.cw + 1) * 6, 128), nf), 128, 0, h->stream>>>(g, h->d_sat);
+    timeline_mark(h->stream, "k_sn_chamfer");
     k_sn_chamfer<<<nf, 32, 3 * g.cw * sizeof(float), h->stream>>>(g, h->d_dist);
+    timeline_mark(h->stream, "k_sn_normals");
     k_sn_normals<<<dim3(div_up(h->n_out, 128), nf), 128, 0, h->stream>>>(g, h->d_pts, h->d_dist, h->d_sat, d_out);
     HVO_CUDA(cudaGetLastError());
     return HVO_OK;

@@ -933,6 +933,7 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
         const uint8_t* sp = l == 1 ? d_gray : d_pyr + S.img_off;
         const long long sframe = l == 1 ? src.l0_frame : g.pyr_frame_bytes;
         dim3 grd(div_up(D.w, kRsW), div_up(D.h, kRsH), B);
+        timeline_mark(stream, "k_resize");
         k_resize<<<grd, 256, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
                                           d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
         ++launches;
@@ -940,19 +941,23 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     if (profiling) HVO_CUDA(cudaEventRecord(ev[1], stream));
     // K2: FAST cells
     if (ncells > 0) {
+        timeline_mark(stream, "k_fast_cells");
         k_fast_cells<<<dim3(ncells, B), kFastThreads, 0, stream>>>(g, src, d_cells, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
         ++launches;
     }
     if (profiling) HVO_CUDA(cudaEventRecord(ev[2], stream));
     // K3: quadtree
+    timeline_mark(stream, "k_octree");
     k_octree<<<dim3(n, B), 256, oct_smem, stream>>>(g, d_cand, d_ncand, d_knode, d_okp, d_on, max_quota + 8, d_err);
     ++launches;
     if (profiling) HVO_CUDA(cudaEventRecord(ev[3], stream));
     // K4: blur of every level, K5: describe
+    timeline_mark(stream, "k_blur");
     k_blur<<<dim3(nbtiles, B), 256, 0, stream>>>(g, src, d_btiles, d_blur);
     ++launches;
     if (profiling) HVO_CUDA(cudaEventRecord(ev[4], stream));
     const bool rgbd_on = d_depth16 != nullptr && rgbd != nullptr && d_kp_depth != nullptr && d_kp_uright != nullptr;
+    timeline_mark(stream, "k_describe");
     k_describe<<<dim3(div_up(g.out_cap, kDescWarps), B), kDescWarps * 32, 0, stream>>>(
         g, src, d_blur, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
         rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, d_kp_depth, d_kp_uright);

@@ -1159,6 +1159,7 @@ void hvo_plane_destroy(hvo_plane* h) {
 
 static int plane_blocks_launch(hvo_plane* h, const uint16_t* d_depth, int nframes) {
     const int nb = h->Nw * h->Nh;
+    timeline_mark(h->stream, "k_plane_blocks");
     k_plane_blocks<<<dim3(div_up(nb, 128), nframes), 128, 0, h->stream>>>(d_depth, h->width, h->height, h->cam, h->Nw, h->Nh, h->d_blocks);
     HVO_CUDA(cudaGetLastError());
     return HVO_OK;
@@ -1182,9 +1183,12 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     A.g_mse = h->d_gmse; A.g_ds = h->d_gds; A.g_nouse = h->d_gnouse; A.g_blkmap = h->d_gblkmap; A.g_ext = h->d_gext;
     A.g_isvalid = h->d_gisvalid; A.g_pl = h->d_gpl; A.g_ctl = h->d_gctl;
     const bool small = h->nw <= 3 * 32;  // row words per lane: 3 up to 3072 blocks (640x480), kRowW beyond
+    timeline_mark(h->stream, "k_plane_cluster");
     if (small) k_plane_cluster<3><<<nframes, 32, h->ahc_smem, h->stream>>>(A);
     else k_plane_cluster<kRowW><<<nframes, 32, h->ahc_smem, h->stream>>>(A);
+    timeline_mark(h->stream, "k_plane_flood");
     k_plane_flood<<<nframes, kFloodThreads, h->flood_smem, h->stream>>>(A);
+    timeline_mark(h->stream, "k_plane_merge");
     if (small) k_plane_merge<3><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
     else k_plane_merge<kRowW><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
     HVO_CUDA(cudaGetLastError());

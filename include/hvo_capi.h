@@ -35,6 +35,10 @@ const char* hvo_last_error(void);
 int hvo_device_count(int* n_out);
 /* library build info, e.g. "hvofront sm_100a <date>" */
 const char* hvo_version(void);
+/* Profiling aid: with the timeline enabled every kernel launch site first records a timed event on its stream;
+ * hvo_timeline_dump (after the work is synchronised) writes one line per mark: "ms-since-first-mark stream-id name". */
+int hvo_timeline_enable(int on);
+int hvo_timeline_dump(char* buf, int capacity);
 
 /* ------------------------------------------------------------------------------------------------ ORB
  * Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:46-110, src/ORBextractor.cc).              */
