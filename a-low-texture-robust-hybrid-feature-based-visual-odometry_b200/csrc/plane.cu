@@ -749,7 +749,9 @@ __device__ __forceinline__ float flood_dist(const double* p, const FloodPix& P) 
     return (float)fabs(p[0] * (P.px - p[3]) + p[1] * (P.py - p[4]) + p[2] * (P.z - p[5]));
 }
 
-__global__ void __launch_bounds__(kFloodThreads) k_plane_flood(AhcArgs A) {
+// 64 registers x 256 threads: four frames per SM.  More resident frames (register cap 5..8 CTAs, measured) only slow the
+// kernel down: its steps are bound by the scattered 32-byte sector traffic of the membership / depth images.
+__global__ void __launch_bounds__(kFloodThreads, 4) k_plane_flood(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_bucket[kFloodBuckets];
     __shared__ int s_wsum[kFloodThreads / 32];
