@@ -45,6 +45,9 @@ STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + r
 # algorithmic bytes per 640x480 frame of the HBM-bound kernels
 ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_cells': 950532, 'k_describe': 1922000 + 60000,
              'k_lsd_prep': 307200 + 16 * 512 * 384, 'k_plane_blocks': 614400 + 3072 * 96}
+# dram__bytes_read.sum + dram__bytes_write.sum per frame of the same kernels, from the committed ncu capture
+# profiles/r1c_launches_frontend_b1024.csv (batch 1024, summary in profiles/r1c_launch_summary.txt)
+NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_cells': 959000, 'k_describe': 2048000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
 
 
 def _gen(args):
@@ -350,7 +353,9 @@ def main():
         peak, peak_src = measured_peak()
         dom = max(ALG_BYTES, key=lambda k: kern_ms[k])
         achieved = ALG_BYTES[dom] * Bs / (kern_ms[dom] * 1e-3) / 1e9
-        roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
+        roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                        traffic=NCU_DRAM_BYTES[dom] * Bs, traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/'
+                        'r1c_launches_frontend_b1024.csv) x frames per launch',
                         peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
                         kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
                         frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
@@ -409,7 +414,9 @@ def main():
             'data': 'synthetic',
             'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames (TUM3.yaml: ORB 1000 features 8 levels x1.2, LINE 200), '
                                    f'whole front-end of Frame::Frame, {B} distinct frames per GPU per step, frame-sharded over {world} GPU(s)',
-                       'stages': STAGES, 'batch_per_gpu': B, 'mean_per_frame': means,
+                       'stages': STAGES, 'batch_per_gpu': B, 'lanes': fe.lanes, 'chunk_frames': fe.chunk, 'mean_per_frame': means,
+                       'outputs': 'keypoints + descriptors + depth/uRight, keylines + LBD + line functions, planes + one-byte membership image, '
+                                  'surface normals',
                        'l2': f'inputs larger than L2: per-step inputs {B} x 0.92 MB and working set ~{B} x 17 MB >> 126 MB'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step, 'clocks': clk, 'p50_latency_ms_single_frame': p50,

@@ -4,7 +4,9 @@
 //   in.bin : int32 magic, w, h ; gray w*h u8 ; depth w*h u16 ; float fx, fy, cx, cy, factor
 //   out.bin: int32 nl ; nl x 68 B keylines ; nl x 32 B LBD ; nl x 3 doubles ; nl x 32 B LBD (recomputed through computeLBD) ;
 //            int32 np ; np x {3 normal, 3 center doubles, int32 N, int32 n_vertices, first-vertex xyz (3 doubles)} ; w*h int32 membership ;
-//            nl int32 matchNNR(desc, desc reversed rows, 0.95)
+//            nl int32 matchNNR(desc, desc reversed rows, 0.95) ;
+//            nl int32 LineWindowMatcher::search(mode 1) of the frame's own lines against itself (radius 15, TH 0.96) ;
+//            int32 nn ; nn x 3 doubles LPVO normals ; nn floats ; nn x 2 int32 pixels
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -13,6 +15,7 @@
 #include "LineExtractorGPU.h"
 #include "MatcherGPU.h"
 #include "PlaneExtractor.h"
+#include "WindowedMatcherGPU.h"
 
 int main(int argc, char** argv) {
     if (argc != 3) { std::fprintf(stderr, "usage: shim_front in.bin out.bin\n"); return 2; }
@@ -77,6 +80,39 @@ int main(int argc, char** argv) {
         bf.matchNNR(ldesc, rev, 0.95f, m12);
         std::fwrite(m12.data(), 4, m12.size(), fo);
         if (hvo_shim::DescriptorDistance(ldesc, ldesc) != 0) return 6;
+    }
+    // ---- windowed line matcher: LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th) with the frame matched against itself ----
+    if (nl) {
+        hvo_shim::LineWindowMatcher lw;
+        std::vector<uint8_t> d((size_t)nl * 32);
+        std::vector<double> fn((size_t)nl * 3);
+        std::vector<hvo_lproj_query> q(nl);
+        for (int i = 0; i < nl; ++i) {
+            std::memcpy(&d[(size_t)i * 32], ldesc.ptr(i), 32);
+            for (int k = 0; k < 3; ++k) fn[(size_t)i * 3 + k] = lineVec2d[i].v[k];
+            const cv::line_descriptor::KeyLine& k = keylines[i];
+            hvo_lproj_query& qi = q[i];
+            std::memset(&qi, 0, sizeof(qi));
+            qi.x1 = k.startPointX; qi.y1 = k.startPointY; qi.x2 = k.endPointX; qi.y2 = k.endPointY;
+            qi.r = 15.f; qi.cos_th = 0.96f;
+            qi.dir[0] = (double)(k.ePointInOctaveX - k.sPointInOctaveX); qi.dir[1] = (double)(k.ePointInOctaveY - k.sPointInOctaveY);
+            qi.length = k.lineLength; qi.claims = 1;
+        }
+        if (!lw.setFrame(reinterpret_cast<const hvo_keyline*>(keylines.data()), fn.data(), d.data(), nullptr, nl, 0.f, 0.f, (float)w, (float)h)) return 7;
+        std::vector<int32_t> idx;
+        lw.search(q, d, nullptr, 1, 0.95f, idx);
+        std::fwrite(idx.data(), 4, idx.size(), fo);
+    }
+
+    // ---- Manhattan::computeNormalsLPVO ----
+    {
+        hvo_shim::LpvoNormals lpvo(cam[0], cam[1], cam[2], cam[3], cam[4], w, h);
+        std::vector<double> nrm; std::vector<float> dn; std::vector<int32_t> px;
+        int32_t nn = lpvo.compute(depth.data(), nrm, dn, px);
+        std::fwrite(&nn, 4, 1, fo);
+        std::fwrite(nrm.data(), 8, nrm.size(), fo);
+        std::fwrite(dn.data(), 4, dn.size(), fo);
+        std::fwrite(px.data(), 4, px.size(), fo);
     }
     std::fclose(fo);
     return 0;

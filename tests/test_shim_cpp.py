@@ -120,3 +120,25 @@ def test_front_shims_equal_python_mirror(hvo, synth):
     m12 = np.frombuffer(raw, np.int32, nl, off)
     cnt, ref = oracle.match_nnr(desc, desc[::-1].copy(), 0.95)
     assert np.array_equal(m12, ref)
+    off += 4 * nl
+    # LineWindowMatcher: the frame's own lines matched against itself, LSDmatcher::SearchByProjection(Cur, Last, 15) shape
+    lw = np.frombuffer(raw, np.int32, nl, off)
+    off += 4 * nl
+    q = np.zeros(nl, oracle.LPROJ_QUERY_DTYPE)
+    q['x1'] = kl['startPointX']; q['y1'] = kl['startPointY']; q['x2'] = kl['endPointX']; q['y2'] = kl['endPointY']
+    q['r'] = 15; q['cos_th'] = np.float32(0.96); q['claims'] = 1; q['length'] = kl['lineLength']
+    q['dir'][:, 0] = kl['ePointInOctaveX'] - kl['sPointInOctaveX']; q['dir'][:, 1] = kl['ePointInOctaveY'] - kl['sPointInOctaveY']
+    ridx, _, rnm = oracle.line_search_projection(kl, lv, desc, None, (0.0, 0.0, 640.0, 480.0), q, desc, None, 1, 0.95)
+    assert np.array_equal(lw, ridx) and rnm > nl // 2
+    # LpvoNormals: Manhattan::computeNormalsLPVO
+    nn = struct.unpack_from('<i', raw, off)[0]
+    off += 4
+    rn, rz, rpix = oracle.lpvo_normals(depth, np.float32(cam[4]), cam[0], cam[1], cam[2], cam[3])
+    assert nn == len(rn) > 500
+    assert np.array_equal(np.frombuffer(raw, np.float64, 3 * nn, off).reshape(nn, 3), rn)
+    off += 24 * nn
+    assert np.array_equal(np.frombuffer(raw, np.float32, nn, off), rz)
+    off += 4 * nn
+    assert np.array_equal(np.frombuffer(raw, np.int32, 2 * nn, off).reshape(nn, 2), rpix)
+    off += 8 * nn
+    assert off == len(raw)
