@@ -157,6 +157,7 @@ ABI = {
     'hvo_frame_capacities': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_frame_lanes': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_frame_extract_batch': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'hvo_frame_extract_batch_async': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     'hvo_frame_extract_batch_device': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     'hvo_frame_last_launches': (C.c_int, [_vp]),
     'hvo_frame_sync': (C.c_int, [_vp]),
@@ -1404,15 +1405,17 @@ class FrameFrontEnd:
             setattr(o, k, ptrs.get(k))
         return o
 
-    def extract_batch(self, gray, depth16, out=None):
-        """gray [n,h,w] uint8, depth16 [n,h,w] uint16 (host) -> dict of host arrays (see output_shapes)."""
+    def extract_batch(self, gray, depth16, out=None, wait=True):
+        """gray [n,h,w] uint8, depth16 [n,h,w] uint16 (host) -> dict of host arrays (see output_shapes).  wait=False queues the
+        call and returns (pinned buffers, untouched until sync()): the next call's uploads overlap this call's tail."""
         gray = np.ascontiguousarray(gray, np.uint8)
         depth16 = np.ascontiguousarray(depth16, np.uint16)
         n = len(gray)
         if out is None:
             out = self.alloc_host(n)
         o = self._outputs({k: v.ctypes.data for k, v in out.items()})
-        _check(lib().hvo_frame_extract_batch(self._h, _np_ptr(gray), _np_ptr(depth16), n, C.byref(o)))
+        f = lib().hvo_frame_extract_batch if wait else lib().hvo_frame_extract_batch_async
+        _check(f(self._h, _np_ptr(gray), _np_ptr(depth16), n, C.byref(o)))
         return out
 
     def extract_batch_device(self, d_gray, d_depth16, n, d_ptrs):

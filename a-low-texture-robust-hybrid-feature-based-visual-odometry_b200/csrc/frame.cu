@@ -319,7 +319,7 @@ int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const ui
     return HVO_OK;
 }
 
-int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out) {
+int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out) {
     HVO_CHECK_ARG(h && gray && depth16, "null argument");
     HVO_CHECK_ARG(nframes >= 1, "nframes < 1");
     int st = frame_check_outputs(h, out, false);
@@ -333,10 +333,8 @@ int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* d
     for (int off = 0; off < nframes; off += per, ++k) {
         FrameLane& L = h->lane[k % h->nlanes];
         const int n = std::min(per, nframes - off);
-        if (k >= h->nlanes) {  // the lane's previous chunk must be done with the staging buffers
-            st = wait_joins(h, L.up, L);
-            if (st != HVO_OK) return st;
-        }
+        st = wait_joins(h, L.up, L);  // the lane's previous chunk (of this or an earlier call) must be done with the staging buffers
+        if (st != HVO_OK) return st;
         HVO_CUDA(cudaMemcpyAsync(L.d_gray, gray + (size_t)off * px, (size_t)n * px, cudaMemcpyHostToDevice, L.up));
         HVO_CUDA(cudaMemcpyAsync(L.d_depth, depth16 + (size_t)off * px, (size_t)n * px * 2, cudaMemcpyHostToDevice, L.up));
         HVO_CUDA(cudaEventRecord(L.fork, L.up));
@@ -351,6 +349,12 @@ int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* d
         if (st != HVO_OK) return st;
     }
     h->last_launches = launches;
+    return HVO_OK;
+}
+
+int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out) {
+    const int st = hvo_frame_extract_batch_async(h, gray, depth16, nframes, out);
+    if (st != HVO_OK) return st;
     HVO_CUDA(cudaStreamSynchronize(h->stream));
     return HVO_OK;
 }

@@ -457,6 +457,9 @@ int hvo_frame_lanes(const hvo_frame* h, int* lanes, int* chunk_frames);
  * returns when every output has been written.  n is not limited by max_batch: chunks of max_batch / lanes frames are
  * streamed through the lanes (upload of chunk k+1 and download of chunk k-1 overlap the kernels of chunk k). */
 int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out);
+/* The same without the final wait: returns once everything is queued, so the uploads of the next call overlap the tail of this
+ * one (host buffers must be pinned and stay untouched; results are complete after hvo_frame_sync / hvo_frame_timer_stop). */
+int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out);
 /* Everything device-resident (n <= max_batch); asynchronous.  hvo_frame_sync / hvo_frame_timer_stop wait for all pipelines. */
 int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const uint16_t* d_depth16, int nframes,
                                    const hvo_frame_outputs* d_out);

@@ -108,3 +108,37 @@ def test_gpu_frame_lanes_stream_chunks_and_byte_membership(hvo, synth):
         out2 = fe.extract_batch(gray[:2], depth[:2])   # fewer frames than lanes * chunk
         _same_outputs(hvo, ref, out2, 2)
         fe.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frame_async_calls_overlap_and_equal_blocking(hvo, synth):
+    """hvo_frame_extract_batch_async: calls are queued back to back (the uploads of call k+1 overlap the tail of call k); after
+    sync() every output set holds what the blocking call returns."""
+    import torch
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 5, start=23)
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=4, lanes=2, line_cull=True, membership='u8')
+    ref = fe.extract_batch(gray, depth)
+
+    def pinned_like(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        return t, v
+    keep = []
+    hg, g = pinned_like(gray); hd, d = pinned_like(depth)
+    g[:] = gray; d[:] = depth
+    outs = []
+    for _ in range(3):
+        o = {}
+        for k, v in ref.items():
+            t, a = pinned_like(v)
+            a.view(np.uint8)[...] = 0xAB
+            keep.append(t); o[k] = a
+        outs.append(o)
+    for o in outs:
+        fe.extract_batch(g, d, out=o, wait=False)
+    fe.sync()
+    for o in outs:
+        _same_outputs(hvo, ref, o, 5)
+        assert np.array_equal(o['membership8'], ref['membership8'])
+    fe.close()
