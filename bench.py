@@ -30,6 +30,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':  # keeps NCCL's version banner out of stdout (one JSON line is the contract)
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 METRIC = 'front-end frames/s @640x480'
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
@@ -218,7 +220,14 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     B, W, H = args.batch, 640, 480
-    gray, depth = make_frames(B, start=rank * B)  # every rank gets its own frames (frame-sharded, weak scaling)
+    # every rank gets its own frames (frame-sharded, weak scaling): up to 1024 distinct frames per rank (8192 over 8 GPUs, the
+    # C5 sequence), repeated to fill the batch
+    n_distinct = min(B, 1024)
+    gray, depth = make_frames(n_distinct, start=rank * n_distinct)
+    if n_distinct < B:
+        reps = (B + n_distinct - 1) // n_distinct
+        gray = np.concatenate([gray] * reps)[:B]
+        depth = np.concatenate([depth] * reps)[:B]
     fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True, lanes=args.lanes, membership='u8',
                            max_batch=B, device=local_rank, nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'],
                            nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
@@ -424,7 +433,7 @@ def main():
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic',
             'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames (TUM3.yaml: ORB 1000 features 8 levels x1.2, LINE 200), '
-                                   f'whole front-end of Frame::Frame, {B} distinct frames per GPU per step, frame-sharded over {world} GPU(s)',
+                                   f'whole front-end of Frame::Frame, {B} frames per GPU per step ({n_distinct} distinct per GPU), frame-sharded over {world} GPU(s)',
                        'stages': STAGES, 'batch_per_gpu': B, 'lanes': fe.lanes, 'chunk_frames': fe.chunk, 'mean_per_frame': means,
                        'outputs': 'keypoints + descriptors + depth/uRight, keylines + LBD + line functions, planes + one-byte membership image, '
                                   'surface normals',
