@@ -33,6 +33,7 @@ struct FrameLane {
     hvo_normals* normals = nullptr;
     cudaStream_t up = nullptr;  // host API: uploads of this lane's chunks
     cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cdone[4] = {nullptr, nullptr, nullptr, nullptr};  // kernels of a pipeline done (recorded before its downloads)
     uint8_t* d_gray = nullptr;
     uint16_t* d_depth = nullptr;
     hvo_frame_outputs d_out;  // device staging of every output (host API)
@@ -45,6 +46,7 @@ struct hvo_frame {
     cudaStream_t stream = nullptr;  // master: fork/join of the device API, timing
     cudaEvent_t fork = nullptr, tev[2] = {nullptr, nullptr};
     int orb_cap = 0, max_lines = 0, normals_count = 0, last_launches = 0;
+    int last_host_lane = -1;  // lane of the most recent chunk of the host API
 };
 
 // rows [off, off + n) of every output array
@@ -70,16 +72,26 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
 
 // The pipelines of one lane on n frames: wait for `start`, run, optionally copy each stage's results back on its own
 // stream, record the lane's join events.  Launch order = placement order: the ordered (latency-bound) pipelines first.
+// `after`: lane whose kernels must have finished first (host API: chunks compute one after the other, so the ordered kernels
+// of two chunks never slow each other down, while the copies of the neighbouring chunks run beside the kernels).
 static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint8_t* d_gray, const uint16_t* d_depth, int n,
-                       const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches) {
+                       const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
+    auto wait_start = [&](cudaStream_t s) -> int {
+        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
+        if (after)
+            for (int i = 0; i < 4; ++i)
+                if (h->p.stages & (i == 0 ? ST_ORB : i == 1 ? ST_LINE : i == 2 ? ST_PLANE : ST_NORMALS)) HVO_CUDA(cudaStreamWaitEvent(s, after->cdone[i], 0));
+        return HVO_OK;
+    };
     if (h->p.stages & ST_PLANE) {
         cudaStream_t s = plane_stream(L.plane);
-        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
+        if (int ws = wait_start(s)) return ws;
         int st = o.membership8 ? hvo_plane_detect_batch_device_u8(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership, o.membership8)
                                : hvo_plane_detect_batch_device(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
         if (st != HVO_OK) return st;
         *launches += hvo_plane_last_launches(L.plane);
+        HVO_CUDA(cudaEventRecord(L.cdone[2], s));
         if (host) {
             HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
             HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
@@ -91,10 +103,11 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
     }
     if (h->p.stages & ST_LINE) {
         cudaStream_t s = line_stream(L.line);
-        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
+        if (int ws = wait_start(s)) return ws;
         int st = hvo_line_extract_batch_device(L.line, d_gray, n, o.keylines, o.line_desc, o.linevec3, o.line_counts);
         if (st != HVO_OK) return st;
         *launches += hvo_line_last_launches(L.line);
+        HVO_CUDA(cudaEventRecord(L.cdone[1], s));
         if (host) {
             const size_t c = (size_t)h->max_lines;
             HVO_CUDA(cudaMemcpyAsync(host->line_counts, o.line_counts, N * 4, cudaMemcpyDeviceToHost, s));
@@ -107,11 +120,12 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
     }
     if (h->p.stages & ST_ORB) {
         cudaStream_t s = orb_stream(L.orb);
-        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
+        if (int ws = wait_start(s)) return ws;
         hvo_rgbd_params rg{h->p.depth_factor, h->p.bf};
         int st = hvo_orb_extract_batch_device(L.orb, d_gray, n, o.kps, o.desc, o.kp_counts, d_depth, &rg, o.kp_depth, o.kp_uright);
         if (st != HVO_OK) return st;
         *launches += hvo_orb_last_launches(L.orb);
+        HVO_CUDA(cudaEventRecord(L.cdone[0], s));
         if (host) {
             const size_t c = (size_t)h->orb_cap;
             HVO_CUDA(cudaMemcpyAsync(host->kp_counts, o.kp_counts, N * 4, cudaMemcpyDeviceToHost, s));
@@ -125,10 +139,11 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
     }
     if (h->p.stages & ST_NORMALS) {
         cudaStream_t s = normals_stream(L.normals);
-        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
+        if (int ws = wait_start(s)) return ws;
         int st = hvo_normals_compute_batch_device(L.normals, d_depth, n, o.normals8);
         if (st != HVO_OK) return st;
         *launches += 5;
+        HVO_CUDA(cudaEventRecord(L.cdone[3], s));
         if (host) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
         timeline_mark(s, "end_normals");
         HVO_CUDA(cudaEventRecord(L.join[3], s));
@@ -211,6 +226,8 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
             HVO_TRY(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
             for (auto& e : L.join) HVO_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             if (st != HVO_OK) break;
+            for (auto& e : L.cdone) HVO_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            if (st != HVO_OK) break;
             HVO_TRY(cudaMalloc(&L.d_gray, B * px));
             HVO_TRY(cudaMalloc(&L.d_depth, B * px * 2));
             hvo_frame_outputs& o = L.d_out;
@@ -260,6 +277,7 @@ void hvo_frame_destroy(hvo_frame* h) {
         for (void* b : bufs) if (b) cudaFree(b);
         if (L.fork) cudaEventDestroy(L.fork);
         for (auto& e : L.join) if (e) cudaEventDestroy(e);
+        for (auto& e : L.cdone) if (e) cudaEventDestroy(e);
         if (L.up) cudaStreamDestroy(L.up);
     }
     if (h->fork) cudaEventDestroy(h->fork);
@@ -341,8 +359,9 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
         hvo_frame_outputs d = L.d_out;
         if (!out->membership8) d.membership8 = nullptr;
         const hvo_frame_outputs hostk = outputs_at(h, *out, (size_t)off);
-        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, d, &hostk, &launches);
+        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, d, &hostk, &launches, h->last_host_lane >= 0 ? &h->lane[h->last_host_lane] : nullptr);
         if (st != HVO_OK) return st;
+        h->last_host_lane = k % h->nlanes;
     }
     for (int li = 0; li < std::min(k, h->nlanes); ++li) {
         st = wait_joins(h, h->stream, h->lane[li]);
