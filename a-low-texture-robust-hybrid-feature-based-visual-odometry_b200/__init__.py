@@ -86,6 +86,7 @@ ABI = {
     'hvo_proj_get_grid': (C.c_int, [_vp, _vp, _vp]),
     'hvo_proj_features_in_area': (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
     'hvo_proj_search': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_proj_set_level_sigma': (C.c_int, [_vp, _vp, C.c_int]),
     'hvo_proj_last_rounds': (C.c_int, [_vp]),
     'hvo_proj_last_launches': (C.c_int, [_vp]),
     'hvo_proj_match_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
@@ -1124,6 +1125,10 @@ class ProjectionMatcher:
                                      int(th_dist), float(nnratio), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
         return idx[:len(q)], dist[:len(q)], nm.value
 
+    def set_level_sigma(self, inv_level_sigma2):
+        s = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        _check(lib().hvo_proj_set_level_sigma(self._h, _np_ptr(s), len(s)))
+
     def rounds(self):
         return lib().hvo_proj_last_rounds(self._h)
 
@@ -1300,12 +1305,48 @@ class ORBmatcher:
         q['claims'] = np.asarray(last['has_obs'], bool)
         self._set_frame(Cur)
         idx, dist, nm = self._pm.search(q, last['desc'], Cur.get('claimed'), 1, self.TH_HIGH, self.mfNNratio)
-        idx = idx.copy()
+        return self._apply_with_rotation_check(Cur, last, idx.copy(), nm, np.asarray(last['has_obs'], bool))
+
+    def Fuse(self, KF, MPs, th=3.0):
+        """The search of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (ORBmatcher.cc:838-990).  KF = dict(keys_un, uright,
+        desc, bounds, scale_factors, inv_level_sigma2); MPs = the map points that pass the reference's projection tests (good, not in
+        the key frame, positive depth, inside the image, distance and viewing-angle tests): dict(u, v, ur, level (PredictScale), desc).
+        Returns (nFused, bestIdx [M] key-frame keypoint or -1); Replace / AddObservation on the result stay with the caller."""
+        M = len(MPs['u'])
+        lvl = np.asarray(MPs['level'], np.int32)
+        q = np.zeros(M, PROJ_QUERY_DTYPE)
+        q['u'] = MPs['u']; q['v'] = MPs['v']; q['ur'] = MPs['ur']
+        q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
+        q['min_level'] = lvl - 1; q['max_level'] = lvl
+        self._set_frame(KF)
+        self._pm.set_level_sigma(KF['inv_level_sigma2'])
+        idx, _, nm = self._pm.search(q, MPs['desc'], None, 2, self.TH_LOW, self.mfNNratio)
+        return nm, idx.copy()
+
+    def SearchByProjectionKF(self, Cur, kf, th, ORBdist):
+        """Matching part of SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1499-1628, used by
+        relocalisation).  `kf` holds, for every key-frame map point that is good, not already found and projects inside the image
+        at a valid distance: dict(u, v, level (PredictScale), angle (of the key frame's keypoint), desc), in key-frame index order.
+        A frame keypoint that holds any map point is skipped (:1568-1569), the right coordinate is not checked, accept best <= ORBdist.
+        Cur['claimed'] must mark every keypoint with a map point.  Returns (nmatches, match [len(kf)])."""
+        n = len(kf['u'])
+        lvl = np.asarray(kf['level'], np.int32)
+        q = np.zeros(n, PROJ_QUERY_DTYPE)
+        q['u'] = kf['u']; q['v'] = kf['v']; q['ur'] = -1
+        q['r'] = (np.float32(th) * np.asarray(Cur['scale_factors'], np.float32)[lvl]).astype(np.float32)
+        q['min_level'] = lvl - 1; q['max_level'] = lvl + 1
+        q['claims'] = 1
+        b = Cur['bounds']
+        self._pm.set_frame(Cur['keys_un'], None, Cur['desc'], b[0], b[1], b[2], b[3])   # no uRight: this variant has no stereo check
+        idx, dist, nm = self._pm.search(q, kf['desc'], Cur.get('claimed'), 1, int(ORBdist), self.mfNNratio)
+        return self._apply_with_rotation_check(Cur, kf, idx.copy(), nm, np.ones(n, bool))
+
+    def _apply_with_rotation_check(self, Cur, last, idx, nm, has_obs):
         for k, i in enumerate(idx):
             if i >= 0:
                 Cur['mappoint'][i] = k
-                Cur['claimed'][i] = bool(last['has_obs'][k])
-        if self.mbCheckOrientation:  # rotation consistency (:1458-1494)
+                Cur['claimed'][i] = bool(has_obs[k])
+        if self.mbCheckOrientation:  # rotation consistency (:1458-1494, :1594-1622)
             hist = [[] for _ in range(self.HISTO_LENGTH)]
             factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
             ang_c = np.asarray(Cur['keys_un']['angle'], np.float32)

@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(128) k_proj_round(const ProjKey* __restrict__ 
                                                     const int* __restrict__ cell_start, const int* __restrict__ cell_items, GridGeom g,
                                                     const ProjQuery* __restrict__ qs, const uint4* __restrict__ qdesc, int nq,
                                                     const int* __restrict__ claim_prev, int* __restrict__ claim_next, int mode, int th_dist,
-                                                    float nnratio, int* __restrict__ choice, int* __restrict__ choice_dist,
-                                                    int* __restrict__ changed) {
+                                                    float nnratio, const float* __restrict__ inv_sigma2, int* __restrict__ choice,
+                                                    int* __restrict__ choice_dist, int* __restrict__ changed) {
     const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= nq) return;
     const ProjQuery q = qs[k];
@@ -154,8 +154,19 @@ __global__ void __launch_bounds__(128) k_proj_round(const ProjKey* __restrict__ 
                     id = cell_items[i];
                     const ProjKey p = pk[id];
                     oct = p.octave;
-                    ok = proj_in_area(p, q.u, q.v, q.r, q.min_level, q.max_level) && !(claim_prev[id] < k);
-                    if (ok && p.uright > 0) ok = !(fabsf(__fsub_rn(q.ur, p.uright)) > q.r);
+                    ok = proj_in_area(p, q.u, q.v, q.r, q.min_level, q.max_level);
+                    if (mode == 2) {  // ORBmatcher::Fuse (ORBmatcher.cc:914-944): chi-square gate on the reprojection error, nothing is claimed
+                        if (ok) {
+                            const float ex = __fsub_rn(q.u, p.x), ey = __fsub_rn(q.v, p.y);
+                            float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            double lim = 5.99;
+                            if (p.uright >= 0) { const float er = __fsub_rn(q.ur, p.uright); e2 = __fadd_rn(e2, __fmul_rn(er, er)); lim = 7.8; }
+                            ok = !((double)__fmul_rn(e2, inv_sigma2[oct]) > lim);
+                        }
+                    } else {
+                        ok = ok && !(claim_prev[id] < k);
+                        if (ok && p.uright > 0) ok = !(fabsf(__fsub_rn(q.ur, p.uright)) > q.r);
+                    }
                     if (ok) {
                         const uint4 da = desc[2 * id], db = desc[2 * id + 1];
                         dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(128) k_proj_round(const ProjKey* __restrict__ 
     if (lane == 0) {
         if (choice[k] != pick) { choice[k] = pick; *changed = 1; }
         choice_dist[k] = pick >= 0 ? bestDist : 256;
-        if (pick >= 0 && q.claims) atomicMin(&claim_next[pick], k);
+        if (pick >= 0 && q.claims && mode != 2) atomicMin(&claim_next[pick], k);
     }
 }
 
@@ -282,6 +293,8 @@ struct hvo_proj {
     int* h_flag = nullptr;  // pinned [2]
     int *d_off = nullptr, *d_cand = nullptr;
     int4* d_best4 = nullptr;
+    float* d_inv_sigma2 = nullptr;  // [64] mvInvLevelSigma2 (mode 2)
+    bool has_sigma = false;
     int last_rounds = 0, last_launches = 0;
 };
 
@@ -338,6 +351,7 @@ int hvo_proj_create(int device, hvo_proj** out) {
         HVO_TRY(cudaEventCreate(&h->tev[1]));
         HVO_TRY(cudaMalloc(&h->d_cell_start, (kGridCells + 1) * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_flag, 2 * sizeof(int)));
+        HVO_TRY(cudaMalloc(&h->d_inv_sigma2, 64 * sizeof(float)));
         HVO_TRY(cudaMallocHost(&h->h_flag, 2 * sizeof(int)));
 #undef HVO_TRY
     } while (0);
@@ -351,7 +365,8 @@ void hvo_proj_destroy(hvo_proj* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_keys, h->d_uright, h->d_desc, h->d_pk, h->d_cell_start, h->d_cell_items, h->d_cell_of, h->d_claimed, h->d_claim0,
-                    h->d_claim_a, h->d_claim_b, h->d_q, h->d_qdesc, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_off, h->d_cand, h->d_best4};
+                    h->d_claim_a, h->d_claim_b, h->d_q, h->d_qdesc, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_off, h->d_cand, h->d_best4,
+                    h->d_inv_sigma2};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->h_flag) cudaFreeHost(h->h_flag);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
@@ -415,7 +430,8 @@ int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_le
 int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
                     float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
     HVO_CHECK_ARG(h && match_idx, "null argument");
-    HVO_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (best + second, level ratio) or 1 (best only)");
+    HVO_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (best + second, level ratio), 1 (best only) or 2 (Fuse: reprojection gate)");
+    HVO_CHECK_ARG(mode != 2 || (h->has_sigma && !claimed), "mode 2 needs hvo_proj_set_level_sigma and takes no claimed array");
     if (n_matches) *n_matches = 0;
     if (nq <= 0) return HVO_OK;
     HVO_CHECK_ARG(queries && qdesc, "null queries");
@@ -441,7 +457,7 @@ int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* q
         HVO_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
         k_proj_round<<<div_up(nq * 32, 128), 128, 0, s>>>(h->d_pk, reinterpret_cast<const uint4*>(h->d_desc), h->d_cell_start, h->d_cell_items,
                                                           h->g, h->d_q, reinterpret_cast<const uint4*>(h->d_qdesc), nq, prev, next, mode, th_dist,
-                                                          nnratio, h->d_choice, h->d_cdist, h->d_flag);
+                                                          nnratio, h->d_inv_sigma2, h->d_choice, h->d_cdist, h->d_flag);
         HVO_CUDA(cudaGetLastError());
         HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
         HVO_CUDA(cudaStreamSynchronize(s));
@@ -455,6 +471,16 @@ int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* q
     if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, h->d_cdist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
     HVO_CUDA(cudaStreamSynchronize(s));
     if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
+    return HVO_OK;
+}
+
+int hvo_proj_set_level_sigma(hvo_proj* h, const float* inv_level_sigma2, int nlevels) {
+    HVO_CHECK_ARG(h && inv_level_sigma2, "null argument");
+    HVO_CHECK_ARG(nlevels >= 1 && nlevels <= 64, "nlevels out of range (1..64)");
+    HVO_CUDA(cudaSetDevice(h->device));
+    HVO_CUDA(cudaMemcpyAsync(h->d_inv_sigma2, inv_level_sigma2, (size_t)nlevels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    h->has_sigma = true;
     return HVO_OK;
 }
 

@@ -170,9 +170,14 @@ int hvo_proj_get_grid(hvo_proj* h, int32_t* cell_start, int32_t* cell_items);
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel): indices in the reference's order; *n_out may exceed capacity */
 int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_level, int max_level, int32_t* out, int capacity, int* n_out);
 /* claimed [n] or NULL: keypoints that hold a map point with observations at call time.  mode 0: accept best <= th_dist unless
- * (bestLevel == bestLevel2 && best > nnratio * second); mode 1: accept best <= th_dist.  match_dist may be NULL. */
+ * (bestLevel == bestLevel2 && best > nnratio * second); mode 1: accept best <= th_dist.  match_dist may be NULL.
+ * mode 2 = the candidate loop of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:838-990): candidates of the
+ * window at levels [min_level, max_level] whose reprojection error passes e2 * mvInvLevelSigma2[level] <= 5.99 (7.8 with a right
+ * coordinate, error then includes ur), best only, accept best <= th_dist (TH_LOW); queries are independent (nothing is claimed,
+ * claimed must be NULL); needs hvo_proj_set_level_sigma.  Replace / AddObservation stay with the caller. */
 int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
                     float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches);
+int hvo_proj_set_level_sigma(hvo_proj* h, const float* inv_level_sigma2, int nlevels); /* mvInvLevelSigma2 of the frame searched in */
 int hvo_proj_last_rounds(const hvo_proj* h);   /* fixed-point rounds of the last search (>= 1) */
 int hvo_proj_last_launches(const hvo_proj* h);
 /* Candidate lists chosen by the caller (e.g. the per-node buckets of SearchByBoW, src/ORBmatcher.cc:162-293): for query i the

@@ -271,6 +271,24 @@ def search_projection(keys, uright, desc, bounds, queries, qdesc, claimed=None, 
     return idx[:len(q)], dist[:len(q)], int(n)
 
 
+def search_fuse(keys, uright, desc, bounds, queries, qdesc, inv_sigma2, th_dist=50):
+    """the candidate loop of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:896-990)."""
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    sg = np.ascontiguousarray(inv_sigma2, np.float32)
+    idx = np.full(max(len(q), 1), -1, np.int32); dist = np.full(max(len(q), 1), 256, np.int32)
+    f = lib().orc_search_fuse
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                                                                    C.c_void_p, C.c_void_p]
+    n = f(_p(keys), _p(ur) if ur is not None else None, _p(desc), len(keys), *[float(b) for b in bounds], _p(q), _p(qd), len(q), _p(sg),
+          int(th_dist), _p(idx), _p(dist))
+    return idx[:len(q)], dist[:len(q)], int(n)
+
+
 def match_candidates(q, t, offsets, cand):
     q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
     off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)

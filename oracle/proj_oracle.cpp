@@ -142,6 +142,44 @@ int orc_search_projection(const void* keys, const float* uright, const uint8_t* 
     return nmatches;
 }
 
+// the candidate loop of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:896-990): window at levels [min, max], chi-square gate
+// on the reprojection error (5.99 mono / 7.8 with a right coordinate), best only, best <= th_dist; queries are independent
+int orc_search_fuse(const void* keys, const float* uright, const uint8_t* desc, int n, float min_x, float min_y, float max_x, float max_y,
+                    const void* queries, const uint8_t* qdesc, int nq, const float* inv_sigma2, int th_dist, int32_t* match_idx,
+                    int32_t* match_dist) {
+    using namespace projo;
+    const KeyPoint* K = (const KeyPoint*)keys;
+    const Query* Q = (const Query*)queries;
+    Grid g;
+    g.build(K, n, min_x, min_y, max_x, max_y);
+    std::vector<int> cand;
+    int nm = 0;
+    for (int k = 0; k < nq; ++k) {
+        match_idx[k] = -1; match_dist[k] = 256;
+        const Query& q = Q[k];
+        g.area(K, q.u, q.v, q.r, -1, -1, cand);   // pKF->GetFeaturesInArea(u, v, radius): every level
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const KeyPoint& kp = K[idx];
+            if (kp.octave < q.min_level || kp.octave > q.max_level) continue;
+            const float ur = uright ? uright[idx] : -1.f;
+            if (ur >= 0) {
+                const float ex = q.u - kp.x, ey = q.v - kp.y, er = q.ur - ur;
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_sigma2[kp.octave] > 7.8) continue;
+            } else {
+                const float ex = q.u - kp.x, ey = q.v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_sigma2[kp.octave] > 5.99) continue;
+            }
+            const int dist = hamming(qdesc + 32 * (size_t)k, desc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= th_dist) { match_idx[k] = bestIdx; match_dist[k] = bestDist; ++nm; }
+    }
+    return nm;
+}
+
 // generic candidate lists (e.g. the per-vocabulary-node buckets of SearchByBoW, src/ORBmatcher.cc:162-293): for query i the
 // train indices cand[off[i] .. off[i+1]) in the caller's order; best4[i] = {idx0, dist0, idx1, dist1}, strict '<' updates.
 void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* off, const int32_t* cand, int32_t* best4) {

@@ -282,3 +282,49 @@ def test_gpu_search_candidates_and_search_by_bow(hvo, synth):
         if b not in keep:
             want[hist[b]] = -1
     assert np.array_equal(match, want) and nm == int((want >= 0).sum()) > 20
+
+
+def test_oracle_fuse_gate():
+    # one keypoint at (100, 100), level 1; sigma2 = 1.44 -> inv 0.694: e2 * inv <= 5.99  <=>  e2 <= 8.63
+    keys = np.zeros(1, oracle.KP_DTYPE); keys['x'] = 100; keys['y'] = 100; keys['octave'] = 1
+    d = np.zeros((1, 32), np.uint8)
+    inv = (1.0 / (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2).astype(np.float32)
+    q = np.zeros(3, oracle.PROJ_QUERY_DTYPE); q['r'] = 10; q['v'] = 100; q['min_level'] = 0; q['max_level'] = 1
+    q['u'] = [102, 103.5, 102]                      # e2 = 4 passes, e2 = 12.25 fails
+    q['ur'] = [80, 80, 75]
+    idx, dist, n = oracle.search_fuse(keys, None, d, BOUNDS, q, np.zeros((3, 32), np.uint8), inv, 50)
+    assert idx.tolist() == [0, -1, 0] and n == 2
+    ur = np.array([78.0], np.float32)               # stereo: e2 = 4 + 4 = 8 -> 5.56 <= 7.8 passes; 4 + 9 = 13 -> 9.03 fails
+    idx, _, n = oracle.search_fuse(keys, ur, d, BOUNDS, q, np.zeros((3, 32), np.uint8), inv, 50)
+    assert idx.tolist() == [0, -1, -1] and n == 1
+    q['min_level'] = 2; q['max_level'] = 3          # level window excludes the keypoint
+    assert oracle.search_fuse(keys, None, d, BOUNDS, q, np.zeros((3, 32), np.uint8), inv, 50)[2] == 0
+
+
+@pytest.mark.gpu
+def test_gpu_fuse_and_reloc_projection_match_oracle(hvo, synth):
+    k0, d0, ur, claimed, q, qd = _scenario(synth, seed=3, n_extra=200, claims_all=True)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    inv = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    lvl = np.clip(q['max_level'], 0, 7).astype(np.int32)
+    m = hvo.ORBmatcher(0.6, True)
+    # ---- Fuse: independent queries, chi-square gate, TH_LOW ----
+    KF = dict(keys_un=k0, uright=ur, desc=d0, bounds=BOUNDS, scale_factors=sf, inv_level_sigma2=inv)
+    MPs = dict(u=q['u'], v=q['v'], ur=q['ur'], level=lvl, desc=qd)
+    nf, best = m.Fuse(KF, MPs, th=3.0)
+    qq = q.copy(); qq['r'] = (np.float32(3.0) * sf[lvl]).astype(np.float32); qq['min_level'] = lvl - 1; qq['max_level'] = lvl
+    ridx, _, rn = oracle.search_fuse(k0, ur, d0, BOUNDS, qq, qd, inv, 50)
+    assert rn > 30 and nf == rn and np.array_equal(best, ridx)
+    nf2, best2 = m.Fuse(dict(KF, uright=None), MPs, th=3.0)          # monocular key frame: 5.99 gate only
+    ridx2, _, rn2 = oracle.search_fuse(k0, None, d0, BOUNDS, qq, qd, inv, 50)
+    assert nf2 == rn2 >= rn and np.array_equal(best2, ridx2)
+    # ---- relocalisation variant: any map point blocks a keypoint, every match claims, no stereo check, ORBdist ----
+    has_mp = (np.random.RandomState(4).rand(len(k0)) < 0.15)
+    Cur = dict(keys_un=k0, desc=d0, bounds=BOUNDS, scale_factors=sf, mappoint=np.where(has_mp, 0, -1).astype(np.int32), claimed=has_mp.copy())
+    kf = dict(u=q['u'], v=q['v'], level=lvl, angle=np.zeros(len(q), np.float32), desc=qd)
+    m2 = hvo.ORBmatcher(0.6, False)                                  # rotation check off: pure assignment parity
+    nm, match = m2.SearchByProjectionKF(Cur, kf, th=10.0, ORBdist=64)
+    q3 = q.copy(); q3['r'] = (np.float32(10.0) * sf[lvl]).astype(np.float32); q3['min_level'] = lvl - 1; q3['max_level'] = lvl + 1; q3['claims'] = 1
+    ridx3, _, rn3 = oracle.search_projection(k0, None, d0, BOUNDS, q3, qd, has_mp.astype(np.uint8), 1, 64)
+    assert rn3 > 50 and nm == rn3 and np.array_equal(match, ridx3)
+    assert not np.any(has_mp[match[match >= 0]])                     # blocked keypoints never receive a match
