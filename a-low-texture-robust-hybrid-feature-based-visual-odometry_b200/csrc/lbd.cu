@@ -26,23 +26,36 @@ __constant__ int8_t c_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 2, 1, 3
 
 __global__ void __launch_bounds__(256) k_lbd_grad(const uint8_t* __restrict__ gray, int w, int h, long long frame_px,
                                                   int16_t* __restrict__ dx, int16_t* __restrict__ dy) {
-    __shared__ uint8_t raw[(kGH + 6) * (kGW + 8)];
+    __shared__ __align__(4) uint8_t raw[(kGH + 6) * (kGW + 8)];
     __shared__ uint16_t hb[(kGH + 6) * (kGW + 2)];
     __shared__ uint8_t bl[(kGH + 2) * (kGW + 4)];
     const int tx = blockIdx.x * kGW, ty = blockIdx.y * kGH, f = blockIdx.z, tid = threadIdx.x;
     const uint8_t* img = gray + (long long)f * frame_px;
     // raw tile: rows ty-3..ty+kGH+2, cols tx-3..tx+kGW+2 (reflect-101; the blurred image's own reflection equals
     // the blur of the reflected input because the kernel is symmetric)
-    for (int i = tid; i < (kGH + 6) * (kGW + 6); i += 256) {
-        const int r = i / (kGW + 6), c = i - r * (kGW + 6);
-        const int y = min(max(reflect101(ty - 3 + r, h), 0), h - 1), x = min(max(reflect101(tx - 3 + c, w), 0), w - 1);
-        raw[r * (kGW + 8) + c] = __ldg(img + (long long)y * w + x);
+    // Interior tiles (no reflection; tx is a multiple of 64, so tx - 4 is word aligned when the rows are) come in as aligned
+    // 32-bit words: raw col c then holds image col tx - 4 + c, one byte to the right of the general layout (`sh`).
+    const bool interior = tx >= 4 && ty >= 3 && tx + kGW + 4 <= w && ty + kGH + 3 <= h && (w & 3) == 0 && (frame_px & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(gray) & 3) == 0;
+    const int sh = interior ? 1 : 0;
+    if (interior) {
+        const uint8_t* base = img + (long long)(ty - 3) * w + (tx - 4);
+        for (int i = tid; i < (kGH + 6) * ((kGW + 8) / 4); i += 256) {
+            const int r = i / ((kGW + 8) / 4), c = i - r * ((kGW + 8) / 4);
+            reinterpret_cast<uint32_t*>(raw + r * (kGW + 8))[c] = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)r * w) + c);
+        }
+    } else {
+        for (int i = tid; i < (kGH + 6) * (kGW + 6); i += 256) {
+            const int r = i / (kGW + 6), c = i - r * (kGW + 6);
+            const int y = min(max(reflect101(ty - 3 + r, h), 0), h - 1), x = min(max(reflect101(tx - 3 + c, w), 0), w - 1);
+            raw[r * (kGW + 8) + c] = __ldg(img + (long long)y * w + x);
+        }
     }
     __syncthreads();
     // horizontal 5-tap (14,62,104,62,14): blurred cols tx-1..tx+kGW  <->  index 0..kGW+1
     for (int i = tid; i < (kGH + 6) * (kGW + 2); i += 256) {
         const int r = i / (kGW + 2), c = i - r * (kGW + 2);
-        const uint8_t* p = raw + r * (kGW + 8) + c;  // taps at raw cols c..c+4  (centre c+2 <-> x = tx-1+c)
+        const uint8_t* p = raw + r * (kGW + 8) + c + sh;  // taps at raw cols c..c+4  (centre c+2 <-> x = tx-1+c)
         hb[r * (kGW + 2) + c] = (uint16_t)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
     }
     __syncthreads();

@@ -44,14 +44,23 @@ struct __align__(16) LsdPix {
 struct LinCoef { int ofs; uint16_t c1; uint16_t mode; };  // INTER_LINEAR_EXACT: mode 0 interior, 1 low border, 2 high border
 
 static const int kPW = 64, kPH = 16;                 // scaled-pixel tile of k_lsd_prep
-static const int kSrcW = 88, kSrcH = 28;             // raw tile capacity (scale 0.8: 1.25 * (tile + 1) + 2 + 4 halo)
+static const int kSrcW = 96, kSrcH = 28;             // raw tile capacity (scale 0.8: 1.25 * (tile + 1) + 2 + 4 halo, + 3 bytes of word alignment)
+
+// i / d and i % d for 0 <= i < 4096, 1 <= d <= 128 without an integer division (magic = ceil(65536 / d))
+struct FastDiv { uint32_t magic; int d; };
+__device__ __forceinline__ FastDiv fastdiv_make(int d) { return FastDiv{(65536u + (uint32_t)d - 1u) / (uint32_t)d, d}; }
+__device__ __forceinline__ void fastdiv(const FastDiv& f, int i, int& q, int& r) {
+    q = (int)(((uint32_t)i * f.magic) >> 16);
+    if (q * f.d > i) --q;
+    r = i - q * f.d;
+}
 
 // --------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gray, int W, int H, long long frame_px, int sw, int sh,
                                                   const LinCoef* __restrict__ cx, const LinCoef* __restrict__ cy,
-                                                  const float2* __restrict__ cstab, double rho, LsdPix* __restrict__ pix,
+                                                  const float2* __restrict__ cstab, int sq_low_max, LsdPix* __restrict__ pix,
                                                   uint8_t* __restrict__ scaled_out, int* __restrict__ maxsq) {
-    __shared__ uint8_t raw[kSrcH][kSrcW];
+    __shared__ __align__(4) uint8_t raw[kSrcH][kSrcW];
     __shared__ uint16_t hb[kSrcH][kSrcW];
     __shared__ uint8_t bl[kSrcH][kSrcW];
     __shared__ uint16_t hr[kSrcH][kPW + 2];
@@ -66,26 +75,49 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
     const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;  // <= kSrcW - 4, kSrcH - 4
     const int rw = bw + 4, rh = bh + 4;
     if (tid == 0) s_max = 0;
-    for (int i = tid; i < rw * rh; i += 256) {
-        const int r = i / rw, c = i - r * rw;
-        const int y = reflect101(by0 - 2 + r, H), x = reflect101(bx0 - 2 + c, W);
-        raw[r][c] = __ldg(img + (long long)y * W + x);
+    // raw tile: columns bx0 - 2 .. bx1 + 2, rows by0 - 2 .. by1 + 2.  Interior tiles (no border reflection, 4-byte aligned rows)
+    // are fetched as aligned 32-bit words; `shb` = bytes between the aligned origin and the first column the tile needs.
+    const int rx0 = bx0 - 2, ry0 = by0 - 2;
+    const bool interior = rx0 >= 0 && ry0 >= 0 && rx0 + rw <= W && ry0 + rh <= H && (W & 3) == 0 && (frame_px & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(gray) & 3) == 0;
+    const int shb = interior ? (rx0 & 3) : 0;
+    if (interior) {
+        const int nwr = (shb + rw + 3) >> 2;  // words per row, <= kSrcW / 4 (the last word may reach past the tile, not past the row)
+        const FastDiv dw = fastdiv_make(nwr);
+        const uint8_t* base = img + (long long)ry0 * W + (rx0 - shb);
+        for (int i = tid; i < nwr * rh; i += 256) {
+            int r, c;
+            fastdiv(dw, i, r, c);
+            reinterpret_cast<uint32_t*>(&raw[r][0])[c] = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)r * W) + c);
+        }
+    } else {
+        const FastDiv dr = fastdiv_make(rw);
+        for (int i = tid; i < rw * rh; i += 256) {
+            int r, c;
+            fastdiv(dr, i, r, c);
+            const int y = reflect101(ry0 + r, H), x = reflect101(rx0 + c, W);
+            raw[r][c] = __ldg(img + (long long)y * W + x);
+        }
     }
     __syncthreads();
+    const FastDiv db = fastdiv_make(bw), dn = fastdiv_make(nx);
     for (int i = tid; i < bw * rh; i += 256) {  // horizontal taps 4,56,136,56,4 (the 7-tap kernel's outer taps are 0)
-        const int r = i / bw, c = i - r * bw;
-        const uint8_t* p = &raw[r][c];
+        int r, c;
+        fastdiv(db, i, r, c);
+        const uint8_t* p = &raw[r][c + shb];
         hb[r][c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
     }
     __syncthreads();
     for (int i = tid; i < bw * bh; i += 256) {
-        const int r = i / bw, c = i - r * bw;
+        int r, c;
+        fastdiv(db, i, r, c);
         const uint32_t acc = 4u * (hb[r][c] + hb[r + 4][c]) + 56u * (hb[r + 1][c] + hb[r + 3][c]) + 136u * hb[r + 2][c];
         bl[r][c] = (uint8_t)((acc + 32768u) >> 16);
     }
     __syncthreads();
     for (int i = tid; i < nx * bh; i += 256) {  // horizontal resize, 8.8 fixed point
-        const int r = i / nx, c = i - r * nx;
+        int r, c;
+        fastdiv(dn, i, r, c);
         const LinCoef k = cx[x0 + c];
         uint16_t v;
         if (k.mode == 0) v = (uint16_t)(bl[r][k.ofs - bx0] * (256 - k.c1) + bl[r][k.ofs - bx0 + 1] * k.c1);
@@ -94,7 +126,8 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
     }
     __syncthreads();
     for (int i = tid; i < nx * ny; i += 256) {  // vertical resize
-        const int r = i / nx, c = i - r * nx;
+        int r, c;
+        fastdiv(dn, i, r, c);
         const LinCoef k = cy[y0 + r];
         uint8_t v;
         if (k.mode == 0) v = (uint8_t)((hr[k.ofs - by0][c] * (256u - k.c1) + hr[k.ofs - by0 + 1][c] * (uint32_t)k.c1 + 32768u) >> 16);
@@ -114,8 +147,8 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
             const int gx = DA + BC, gy = DA - BC;
             const int sq = gx * gx + gy * gy;
             p.gxgy = (gx & 0xffff) | (gy << 16);
-            const double norm = sqrt((double)sq / 4.0);
-            if (!(norm <= rho)) {
+            // modgrad = sqrt(sq / 4.0) <= rho  <=>  sq <= sq_low_max (the largest integer for which the reference's double test holds)
+            if (sq > sq_low_max) {
                 p.ang = fast_atan2_deg((float)gx, (float)-gy);
                 const float2 cs = __ldg(&cstab[(gx + 510) * 1021 + (gy + 510)]);
                 p.c = cs.x; p.s = cs.y;
@@ -782,6 +815,7 @@ struct hvo_line {
     int device = 0, width = 0, height = 0, max_batch = 0, nfeat = 0;
     int sw = 0, sh = 0, seg_cap = 0, min_reg_size = 0;
     double rho = 0, prec = 0;
+    int sq_low_max = 0;  // gradient threshold of LSD as an integer bound on gx^2 + gy^2
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[2] = {nullptr, nullptr};
     cudaEvent_t sev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -844,7 +878,7 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
     HVO_CUDA(cudaMemsetAsync(h->d_maxsq, 0, (size_t)nframes * sizeof(int), s));
     timeline_mark(s, "k_lsd_prep");
     k_lsd_prep<<<dim3(div_up(h->sw, kPW), div_up(h->sh, kPH), nframes), 256, 0, s>>>(
-        d_gray, h->width, h->height, (long long)h->width * h->height, h->sw, h->sh, h->d_cx, h->d_cy, h->d_cstab, h->rho, h->d_pix,
+        d_gray, h->width, h->height, (long long)h->width * h->height, h->sw, h->sh, h->d_cx, h->d_cy, h->d_cstab, h->sq_low_max, h->d_pix,
         h->d_scaled, h->d_maxsq);
     if (h->profiling) cudaEventRecord(h->sev[1], s);
     timeline_mark(s, "k_lsd_order");
@@ -916,6 +950,8 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
     h->sh = (int)std::lrint((double)height * 0.8);
     h->prec = kLsdPi * 22.5 / 180;
     h->rho = 2.0 / std::sin(h->prec);
+    h->sq_low_max = -1;
+    for (int sq = 0; sq <= 2 * 510 * 510 && std::sqrt((double)sq / 4.0) <= h->rho; ++sq) h->sq_low_max = sq;
     const double log_nt = 5 * (std::log10((double)h->sw) + std::log10((double)h->sh)) / 2 + std::log10(11.0);
     h->min_reg_size = (int)(size_t)(-log_nt / std::log10(22.5 / 180));
     h->seg_cap = ((h->sw - 1) * (h->sh - 1)) / (h->min_reg_size > 0 ? h->min_reg_size : 1) + 1;  // every segment owns >= min_reg_size pixels
