@@ -972,7 +972,7 @@ template <int RW>
 __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Nb = A.Nw * A.Nh, npix = A.w * A.h;
+    const int Nb = A.Nw * A.Nh;
     AhcS S;
     ahc_merge_smem_views(smem_raw, Nb, A.max_ext, S);
     S.mse = A.g_mse + (size_t)f * Nb;
@@ -982,7 +982,6 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
     uint32_t* adj = A.adj + (size_t)f * Nb * A.nw;
     uint16_t* key = A.key + (size_t)f * Nb;
     double* cand = A.cand + (size_t)f * Nb;
-    int32_t* mem = A.membership + (size_t)f * npix;
     const long long t_start = clock64();
     const int ne = A.g_ctl[8 * f + 0];
     for (int b = tid; b < Nb; b += kAhcThreads) {
@@ -1021,13 +1020,35 @@ __global__ void __launch_bounds__(kAhcThreads) k_plane_merge(AhcArgs A) {
         if (lane == 0) A.n_planes[f] = ne2;
     }
     __syncthreads();
-    for (int i = tid; i < npix; i += kAhcThreads) {
-        const int plid = mem[i];
-        const int lab = (plid >= 0) ? (int)S.plidmap[plid] : -1;
-        mem[i] = lab;
-        if (A.membership8) A.membership8[(size_t)f * npix + i] = (uint8_t)(lab < 0 || lab > 254 ? 255 : lab);
-    }
+    // the refined-plane -> final-plane map goes to global memory (the block map's storage is free after the flood fill);
+    // k_plane_relabel applies it to the pixels with the whole machine instead of this one CTA
+    for (int i = tid; i < A.max_ext; i += kAhcThreads) A.g_blkmap[(size_t)f * Nb + i] = S.plidmap[i];
     if (tid == 0) A.cycles[4 * (size_t)f + 3] = clock64() - t_start;
+}
+
+// ---- kernel 4: final labels.  membership[i] = plidmap[membership[i]] (or -1), optionally also as one byte per pixel ----
+__device__ __forceinline__ int relabel_one(const int16_t* __restrict__ map, int plid) { return plid >= 0 ? (int)map[plid] : -1; }
+__device__ __forceinline__ uint32_t label_byte(int lab) { return (uint32_t)(lab < 0 || lab > 254 ? 255 : lab); }
+__global__ void __launch_bounds__(256) k_plane_relabel(AhcArgs A) {
+    const int f = blockIdx.y, npix = A.w * A.h, Nb = A.Nw * A.Nh;
+    const int16_t* map = A.g_blkmap + (size_t)f * Nb;
+    int32_t* mem = A.membership + (size_t)f * npix;
+    uint8_t* m8 = A.membership8 ? A.membership8 + (size_t)f * npix : nullptr;
+    const bool vec = (npix & 3) == 0 && (reinterpret_cast<uintptr_t>(A.membership) & 15) == 0 && (reinterpret_cast<uintptr_t>(A.membership8) & 3) == 0;
+    const int i4 = blockIdx.x * 256 + threadIdx.x;
+    if (vec) {
+        if (4 * i4 >= npix) return;
+        int4 v = reinterpret_cast<int4*>(mem)[i4];
+        v.x = relabel_one(map, v.x); v.y = relabel_one(map, v.y); v.z = relabel_one(map, v.z); v.w = relabel_one(map, v.w);
+        reinterpret_cast<int4*>(mem)[i4] = v;
+        if (m8) reinterpret_cast<uint32_t*>(m8)[i4] = label_byte(v.x) | (label_byte(v.y) << 8) | (label_byte(v.z) << 16) | (label_byte(v.w) << 24);
+    } else {
+        for (int i = 4 * i4; i < min(4 * i4 + 4, npix); ++i) {
+            const int lab = relabel_one(map, mem[i]);
+            mem[i] = lab;
+            if (m8) m8[i] = (uint8_t)label_byte(lab);
+        }
+    }
 }
 
 }  // namespace hvo
@@ -1193,8 +1214,10 @@ static int plane_detect_launch(hvo_plane* h, const uint16_t* d_depth, int nframe
     timeline_mark(h->stream, "k_plane_merge");
     if (small) k_plane_merge<3><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
     else k_plane_merge<kRowW><<<nframes, kAhcThreads, h->merge_smem, h->stream>>>(A);
+    timeline_mark(h->stream, "k_plane_relabel");
+    k_plane_relabel<<<dim3(div_up(div_up(h->width * h->height, 4), 256), nframes), 256, 0, h->stream>>>(A);
     HVO_CUDA(cudaGetLastError());
-    h->last_launches = 5;
+    h->last_launches = 6;
     return HVO_OK;
 }
 
