@@ -46,7 +46,7 @@ struct hvo_frame {
     cudaStream_t stream = nullptr;  // master: fork/join of the device API, timing
     cudaEvent_t fork = nullptr, tev[2] = {nullptr, nullptr};
     int orb_cap = 0, max_lines = 0, normals_count = 0, last_launches = 0;
-    int last_host_lane = -1;  // lane of the most recent chunk of the host API
+    int last_lane = -1;  // lane of the most recent chunk: the next chunk's kernels start after its kernels
 };
 
 // rows [off, off + n) of every output array
@@ -321,13 +321,16 @@ int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const ui
     const size_t px = (size_t)h->width * h->height;
     HVO_CUDA(cudaEventRecord(h->fork, h->stream));
     int launches = 0, used = 0;
-    // the batch is spread evenly over the lanes (all chunks run concurrently)
+    // the batch is spread evenly over the lanes; the chunks compute one after the other (measured: two chunks whose ordered
+    // kernels overlap are slower than the same chunks back to back)
     const int per = (nframes + h->nlanes - 1) / h->nlanes;
     for (int off = 0; off < nframes; off += per, ++used) {
         FrameLane& L = h->lane[used];
         const int n = std::min(per, nframes - off);
-        st = lane_launch(h, L, h->fork, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, outputs_at(h, *d_out, (size_t)off), nullptr, &launches);
+        st = lane_launch(h, L, h->fork, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, outputs_at(h, *d_out, (size_t)off), nullptr, &launches,
+                         h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
+        h->last_lane = used;
     }
     for (int li = 0; li < used; ++li) {
         st = wait_joins(h, h->stream, h->lane[li]);
@@ -359,9 +362,9 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
         hvo_frame_outputs d = L.d_out;
         if (!out->membership8) d.membership8 = nullptr;
         const hvo_frame_outputs hostk = outputs_at(h, *out, (size_t)off);
-        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, d, &hostk, &launches, h->last_host_lane >= 0 ? &h->lane[h->last_host_lane] : nullptr);
+        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
-        h->last_host_lane = k % h->nlanes;
+        h->last_lane = k % h->nlanes;
     }
     for (int li = 0; li < std::min(k, h->nlanes); ++li) {
         st = wait_joins(h, h->stream, h->lane[li]);

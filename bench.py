@@ -193,7 +193,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=2048, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=2368, help='frames per GPU per step (default: 2 chunks of 1184 = 8 frames per SM)')
     ap.add_argument('--stages', type=int, default=15, help='bit 0 ORB, 1 lines, 2 planes, 3 normals (profiling aid; the metric is 15)')
     ap.add_argument('--lanes', type=int, default=0, help='pipeline lanes of the frame handle (0 = library default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
