@@ -77,6 +77,7 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
 static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint8_t* d_gray, const uint16_t* d_depth, int n,
                        const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
+    if (after == &L) after = nullptr;  // one lane: every pipeline stream is already in order behind its own previous chunk
     auto wait_start = [&](cudaStream_t s) -> int {
         HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
         if (after)
@@ -84,6 +85,9 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
                 if (h->p.stages & (i == 0 ? ST_ORB : i == 1 ? ST_LINE : i == 2 ? ST_PLANE : ST_NORMALS)) HVO_CUDA(cudaStreamWaitEvent(s, after->cdone[i], 0));
         return HVO_OK;
     };
+    // ---- phase 1: the kernels of every pipeline are queued before any copy.  (A device-to-host copy into pageable memory
+    // blocks the calling thread until the stream gets there; queued behind the plane kernels it would keep the other
+    // pipelines from even starting.) ----
     if (h->p.stages & ST_PLANE) {
         cudaStream_t s = plane_stream(L.plane);
         if (int ws = wait_start(s)) return ws;
@@ -92,14 +96,6 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         if (st != HVO_OK) return st;
         *launches += hvo_plane_last_launches(L.plane);
         HVO_CUDA(cudaEventRecord(L.cdone[2], s));
-        if (host) {
-            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
-            if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
-            if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
-        }
-        timeline_mark(s, "end_planes");
-        HVO_CUDA(cudaEventRecord(L.join[2], s));
     }
     if (h->p.stages & ST_LINE) {
         cudaStream_t s = line_stream(L.line);
@@ -108,15 +104,6 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         if (st != HVO_OK) return st;
         *launches += hvo_line_last_launches(L.line);
         HVO_CUDA(cudaEventRecord(L.cdone[1], s));
-        if (host) {
-            const size_t c = (size_t)h->max_lines;
-            HVO_CUDA(cudaMemcpyAsync(host->line_counts, o.line_counts, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->keylines, o.keylines, N * c * sizeof(hvo_keyline), cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->line_desc, o.line_desc, N * c * 32, cudaMemcpyDeviceToHost, s));
-            if (host->linevec3) HVO_CUDA(cudaMemcpyAsync(host->linevec3, o.linevec3, N * c * 24, cudaMemcpyDeviceToHost, s));
-        }
-        timeline_mark(s, "end_lines");
-        HVO_CUDA(cudaEventRecord(L.join[1], s));
     }
     if (h->p.stages & ST_ORB) {
         cudaStream_t s = orb_stream(L.orb);
@@ -126,6 +113,24 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         if (st != HVO_OK) return st;
         *launches += hvo_orb_last_launches(L.orb);
         HVO_CUDA(cudaEventRecord(L.cdone[0], s));
+    }
+    if (h->p.stages & ST_NORMALS) {
+        cudaStream_t s = normals_stream(L.normals);
+        if (int ws = wait_start(s)) return ws;
+        int st = hvo_normals_compute_batch_device(L.normals, d_depth, n, o.normals8);
+        if (st != HVO_OK) return st;
+        *launches += 5;
+        HVO_CUDA(cudaEventRecord(L.cdone[3], s));
+    }
+    // ---- phase 2: results back to the host on each pipeline's own stream (shortest pipelines first), then the join events ----
+    if (h->p.stages & ST_NORMALS) {
+        cudaStream_t s = normals_stream(L.normals);
+        if (host) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
+        timeline_mark(s, "end_normals");
+        HVO_CUDA(cudaEventRecord(L.join[3], s));
+    }
+    if (h->p.stages & ST_ORB) {
+        cudaStream_t s = orb_stream(L.orb);
         if (host) {
             const size_t c = (size_t)h->orb_cap;
             HVO_CUDA(cudaMemcpyAsync(host->kp_counts, o.kp_counts, N * 4, cudaMemcpyDeviceToHost, s));
@@ -137,16 +142,28 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         timeline_mark(s, "end_orb");
         HVO_CUDA(cudaEventRecord(L.join[0], s));
     }
-    if (h->p.stages & ST_NORMALS) {
-        cudaStream_t s = normals_stream(L.normals);
-        if (int ws = wait_start(s)) return ws;
-        int st = hvo_normals_compute_batch_device(L.normals, d_depth, n, o.normals8);
-        if (st != HVO_OK) return st;
-        *launches += 5;
-        HVO_CUDA(cudaEventRecord(L.cdone[3], s));
-        if (host) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
-        timeline_mark(s, "end_normals");
-        HVO_CUDA(cudaEventRecord(L.join[3], s));
+    if (h->p.stages & ST_LINE) {
+        cudaStream_t s = line_stream(L.line);
+        if (host) {
+            const size_t c = (size_t)h->max_lines;
+            HVO_CUDA(cudaMemcpyAsync(host->line_counts, o.line_counts, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->keylines, o.keylines, N * c * sizeof(hvo_keyline), cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->line_desc, o.line_desc, N * c * 32, cudaMemcpyDeviceToHost, s));
+            if (host->linevec3) HVO_CUDA(cudaMemcpyAsync(host->linevec3, o.linevec3, N * c * 24, cudaMemcpyDeviceToHost, s));
+        }
+        timeline_mark(s, "end_lines");
+        HVO_CUDA(cudaEventRecord(L.join[1], s));
+    }
+    if (h->p.stages & ST_PLANE) {
+        cudaStream_t s = plane_stream(L.plane);
+        if (host) {
+            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
+            if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
+            if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
+        }
+        timeline_mark(s, "end_planes");
+        HVO_CUDA(cudaEventRecord(L.join[2], s));
     }
     return HVO_OK;
 }
