@@ -68,6 +68,7 @@ ABI = {
     'hvo_hamming_distance': (C.c_int, [_vp, _vp]),
     'hvo_match_knn2': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     'hvo_match_knn2_device': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    'hvo_match_distinctive': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
     'hvo_matcher_sync': (C.c_int, [_vp]),
     'hvo_matcher_timer_start': (C.c_int, [_vp]),
     'hvo_matcher_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
@@ -827,6 +828,16 @@ class BFMatcherHamming:
         dist = np.empty((len(q), 2), np.int32)
         _check(lib().hvo_match_knn2(self._h, _np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(idx), _np_ptr(dist)))
         return idx, dist
+
+    def distinctive(self, desc, offsets):
+        """MapPoint / MapLine::ComputeDistinctiveDescriptors for a batch of map elements: group g = desc[offsets[g]:offsets[g+1]]
+        (the descriptors of its observations).  Returns (best index inside each group or -1, its median distance)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        n = len(off) - 1
+        bi = np.full(max(n, 1), -1, np.int32); bm = np.full(max(n, 1), -1, np.int32)
+        _check(lib().hvo_match_distinctive(self._h, _np_ptr(d), _np_ptr(off), n, _np_ptr(bi), _np_ptr(bm)))
+        return bi[:n], bm[:n]
 
     def knn2_device(self, d_q, nq, d_t, nt, d_idx, d_dist):
         _check(lib().hvo_match_knn2_device(self._h, _vp(d_q), nq, _vp(d_t), nt, _vp(d_idx), _vp(d_dist)))

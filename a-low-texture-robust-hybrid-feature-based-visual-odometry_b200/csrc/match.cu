@@ -11,6 +11,7 @@
 //
 // Not a dense contraction in the north-star's sense: the integer pipe (POPC) is the roofline here.
 #include <algorithm>
+#include <climits>
 #include <new>
 
 #include "hvo_common.cuh"
@@ -72,6 +73,53 @@ __global__ void k_knn2_merge(const int4* __restrict__ partial, int nq, int nslic
     }
     idx2[2 * qi] = best.i0; idx2[2 * qi + 1] = best.i1;
     dist2[2 * qi] = best.i0 >= 0 ? best.d0 : -1; dist2[2 * qi + 1] = best.i1 >= 0 ? best.d1 : -1;
+}
+
+// MapPoint / MapLine::ComputeDistinctiveDescriptors (reference src/MapPoint.cc:240-300, src/MapLine.cpp:331-400): per map element
+// the descriptor with the least median Hamming distance to the other observations.  One warp per element: row i of the
+// distance matrix goes into a 257-bin histogram in shared memory (distances are integers <= 256), the median
+// sorted[int(0.5 * (n - 1))] is the first bin whose running count exceeds k; rows in order, strict '<' keeps the first minimum.
+static const int kDistWarps = 4, kDistBins = 288;  // 9 bins per lane
+
+__global__ void __launch_bounds__(kDistWarps * 32) k_distinctive(const uint4* __restrict__ desc, const int* __restrict__ off, int ngroups,
+                                                                  int* __restrict__ best_idx, int* __restrict__ best_median) {
+    __shared__ int s_hist[kDistWarps][kDistBins];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kDistWarps + w;
+    if (g >= ngroups) return;
+    const int b = off[g], n = off[g + 1] - b;
+    int* hist = s_hist[w];
+    int bestMedian = INT_MAX, bestIdx = n > 0 ? 0 : -1;
+    const int k = (n - 1) >> 1;  // int(0.5 * (N - 1))
+    for (int i = 0; i < n; ++i) {
+        for (int t = lane; t < kDistBins; t += 32) hist[t] = 0;
+        __syncwarp();
+        const uint4 a0 = desc[2 * (size_t)(b + i)], a1 = desc[2 * (size_t)(b + i) + 1];
+        for (int j = lane; j < n; j += 32) {
+            const uint4 c0 = desc[2 * (size_t)(b + j)], c1 = desc[2 * (size_t)(b + j) + 1];
+            const int d = __popc(a0.x ^ c0.x) + __popc(a0.y ^ c0.y) + __popc(a0.z ^ c0.z) + __popc(a0.w ^ c0.w) + __popc(a1.x ^ c1.x) +
+                          __popc(a1.y ^ c1.y) + __popc(a1.z ^ c1.z) + __popc(a1.w ^ c1.w);
+            atomicAdd(&hist[d], 1);
+        }
+        __syncwarp();
+        int mine = 0;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) mine += hist[lane * 9 + t];
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const unsigned reach = __ballot_sync(0xffffffffu, inc > k);
+        const int src = __ffs(reach) - 1;  // first lane whose cumulative count exceeds k
+        int median = 0;
+        if (lane == src) {
+            int c = inc - mine;
+            for (int t = 0; t < 9; ++t) { c += hist[lane * 9 + t]; if (c > k) { median = lane * 9 + t; break; } }
+        }
+        median = __shfl_sync(0xffffffffu, median, src);
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) { best_idx[g] = bestIdx; best_median[g] = n > 0 ? bestMedian : -1; }
 }
 
 }  // namespace hvo
@@ -149,6 +197,34 @@ int hvo_match_knn2_device(hvo_matcher* m, const uint8_t* d_q, int nq, const uint
     HVO_CHECK_ARG(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0, "descriptor arrays must be 16-byte aligned");
     HVO_CUDA(cudaSetDevice(m->device));
     return knn2_launch(m, d_q, nq, d_t, nt, d_idx2, d_dist2);
+}
+
+int hvo_match_distinctive(hvo_matcher* m, const uint8_t* desc, const int32_t* offsets, int ngroups, int32_t* best_idx, int32_t* best_median) {
+    HVO_CHECK_ARG(m && best_idx, "null argument");
+    if (ngroups <= 0) return HVO_OK;
+    HVO_CHECK_ARG(offsets, "null offsets");
+    const int total = offsets[ngroups];
+    HVO_CHECK_ARG(offsets[0] == 0 && total >= 0 && (total == 0 || desc), "bad offsets / null descriptors");
+    for (int g = 0; g < ngroups; ++g) HVO_CHECK_ARG(offsets[g + 1] >= offsets[g], "offsets must be non-decreasing");
+    HVO_CUDA(cudaSetDevice(m->device));
+    uint8_t* d_desc = nullptr;
+    int32_t *d_off = nullptr, *d_out = nullptr;
+    HVO_CUDA(cudaMallocAsync(&d_desc, std::max<size_t>((size_t)total * 32, 32), m->stream));
+    HVO_CUDA(cudaMallocAsync(&d_off, ((size_t)ngroups + 1) * 4, m->stream));
+    HVO_CUDA(cudaMallocAsync(&d_out, (size_t)ngroups * 8, m->stream));
+    if (total > 0) HVO_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)total * 32, cudaMemcpyHostToDevice, m->stream));
+    HVO_CUDA(cudaMemcpyAsync(d_off, offsets, ((size_t)ngroups + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+    k_distinctive<<<div_up(ngroups, kDistWarps), kDistWarps * 32, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_desc), d_off, ngroups, d_out,
+                                                                               d_out + ngroups);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(best_idx, d_out, (size_t)ngroups * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (best_median) HVO_CUDA(cudaMemcpyAsync(best_median, d_out + ngroups, (size_t)ngroups * 4, cudaMemcpyDeviceToHost, m->stream));
+    HVO_CUDA(cudaFreeAsync(d_desc, m->stream));
+    HVO_CUDA(cudaFreeAsync(d_off, m->stream));
+    HVO_CUDA(cudaFreeAsync(d_out, m->stream));
+    HVO_CUDA(cudaStreamSynchronize(m->stream));
+    m->last_launches = 1;
+    return HVO_OK;
 }
 
 int hvo_match_knn2(hvo_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2) {

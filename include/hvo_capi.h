@@ -136,6 +136,12 @@ int hvo_match_knn2(hvo_matcher* m, const uint8_t* q, int nq, const uint8_t* t, i
 /* Same with 16-byte aligned device pointers; asynchronous on the matcher's stream. */
 int hvo_match_knn2_device(hvo_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx2,
                           int32_t* d_dist2);
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:240-300) and MapLine::ComputeDistinctiveDescriptors
+ * (src/MapLine.cpp:331-400) for a batch of map elements: group g = the descriptors desc[offsets[g] .. offsets[g+1]) of its
+ * observations (in the reference's std::map iteration order); best_idx[g] = index inside the group of the descriptor with the
+ * least median distance to the others (median = sorted[int(0.5 * (N - 1))], first minimum wins), -1 for an empty group;
+ * best_median (may be NULL) = that median. */
+int hvo_match_distinctive(hvo_matcher* m, const uint8_t* desc, const int32_t* offsets, int ngroups, int32_t* best_idx, int32_t* best_median);
 int hvo_matcher_sync(hvo_matcher* m);
 int hvo_matcher_timer_start(hvo_matcher* m);
 int hvo_matcher_timer_stop(hvo_matcher* m, float* ms_out);

@@ -299,6 +299,16 @@ def match_candidates(q, t, offsets, cand):
     return best4[:len(q)]
 
 
+def distinctive(desc, offsets):
+    """MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:240-300, src/MapLine.cpp:331-400) per group."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32)
+    n = len(off) - 1
+    bi = np.full(max(n, 1), -1, np.int32); bm = np.full(max(n, 1), -1, np.int32)
+    lib().orc_distinctive(_p(d), _p(off), C.c_int(n), _p(bi), _p(bm))
+    return bi[:n], bm[:n]
+
+
 def search_candidates(q, t, offsets, cand, th_dist=50, nnratio=0.7):
     q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
     off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)

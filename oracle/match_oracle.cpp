@@ -6,6 +6,7 @@
 //   LSDmatcher::matchNNR                           src/LSDmatcher.cpp:803-826
 //   LSDmatcher::FrameBFMatch + lineDescriptorMAD   src/LSDmatcher.cpp:942-966, 1110-1135
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -77,6 +78,28 @@ void orc_frame_bf_match(const uint8_t* q, int nq, const uint8_t* t, int nt, floa
     for (int i = 0; i < nq; ++i) {
         const double d12 = (double)((float)dist[2 * i + 1] - (float)dist[2 * i]);
         if (d12 > nn12_th && (float)dist[2 * i] < TH && (float)dist[2 * i] < nnratio * (float)dist[2 * i + 1]) line_matches[i] = idx[2 * i];
+    }
+}
+
+// MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:240-300, src/MapLine.cpp:331-400) for groups of descriptors
+void orc_distinctive(const uint8_t* desc, const int32_t* off, int ngroups, int32_t* best_idx, int32_t* best_median) {
+    for (int g = 0; g < ngroups; ++g) {
+        const int b = off[g], N = off[g + 1] - b;
+        best_idx[g] = -1; best_median[g] = -1;
+        if (N <= 0) continue;
+        int BestMedian = INT_MAX, BestIdx = 0;
+        std::vector<int> v(N);
+        for (int i = 0; i < N; ++i) {
+            for (int j = 0; j < N; ++j) {
+                int d = 0;
+                for (int k = 0; k < 32; ++k) d += __builtin_popcount(desc[32 * (size_t)(b + i) + k] ^ desc[32 * (size_t)(b + j) + k]);
+                v[j] = d;
+            }
+            std::sort(v.begin(), v.end());
+            const int median = v[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_idx[g] = BestIdx; best_median[g] = BestMedian;
     }
 }
 

@@ -113,3 +113,46 @@ def test_lsdmatcher_search_double_and_by_descriptor(hvo, synth):
             exp[idx[q, 0]] = q
     assert np.array_equal(got, exp) and (exp >= 0).sum() > 50
     assert m.SearchDouble(a[:0], b)[0] == 0
+
+
+def _distinctive_groups(synth, seed=3, ngroups=400):
+    """groups of 'observations': noisy copies of a base descriptor, sizes 0..120 (most small, like real map points)"""
+    rng = np.random.RandomState(seed)
+    sizes = np.minimum(rng.geometric(0.15, ngroups), 120)
+    sizes[:6] = [0, 1, 2, 3, 33, 120]
+    base = rng.randint(0, 256, (ngroups, 32)).astype(np.uint8)
+    descs = []
+    for g, n in enumerate(sizes):
+        d = np.repeat(base[g:g + 1], n, axis=0)
+        flips = rng.rand(n, 256) < rng.uniform(0.0, 0.12)
+        d ^= np.packbits(flips, axis=1)
+        if n > 3 and g % 5 == 0:
+            d[1] = d[0]                                  # exact duplicates: equal medians, the first row must win
+        descs.append(d)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    return np.concatenate(descs) if off[-1] else np.zeros((0, 32), np.uint8), off
+
+
+def test_oracle_distinctive_matches_a_numpy_statement(synth):
+    desc, off = _distinctive_groups(synth, ngroups=60)
+    bi, bm = oracle.distinctive(desc, off)
+    for g in range(len(off) - 1):
+        d = desc[off[g]:off[g + 1]]
+        if len(d) == 0:
+            assert bi[g] == -1
+            continue
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (len(d) - 1))]
+        assert bi[g] == int(np.argmin(med)) and bm[g] == med.min()
+
+
+@pytest.mark.gpu
+def test_gpu_distinctive_descriptors_bit_exact(hvo, synth):
+    desc, off = _distinctive_groups(synth)
+    bf = hvo.BFMatcherHamming()
+    bi, bm = bf.distinctive(desc, off)
+    ri, rm = oracle.distinctive(desc, off)
+    assert np.array_equal(bi, ri) and np.array_equal(bm, rm)
+    bi0, _ = bf.distinctive(np.zeros((0, 32), np.uint8), np.zeros(3, np.int32))   # only empty groups
+    assert bi0.tolist() == [-1, -1]
+    bf.close()
