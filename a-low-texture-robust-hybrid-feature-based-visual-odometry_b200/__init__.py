@@ -1334,6 +1334,37 @@ class ORBmatcher:
         idx, _, nm = self._pm.search(q, MPs['desc'], None, 2, self.TH_LOW, self.mfNNratio)
         return nm, idx.copy()
 
+    def FuseSim3(self, KF, pts, th):
+        """The search of ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, th, vpReplacePoint) (ORBmatcher.cc:992-1121,
+        loop closing): window of radius th * sf[level] at levels [level-1, level], best Hamming distance, accepted when <= TH_LOW;
+        no reprojection gate, nothing is claimed.  pts = dict(u, v, level, desc) of the points that pass the Sim3 projection tests.
+        Returns (count, bestIdx [M])."""
+        lvl = np.asarray(pts['level'], np.int32)
+        q = np.zeros(len(lvl), PROJ_QUERY_DTYPE)
+        q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1
+        q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
+        q['min_level'] = lvl - 1; q['max_level'] = lvl
+        b = KF['bounds']
+        self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+        idx, _, nm = self._pm.search(q, pts['desc'], None, 1, self.TH_LOW, self.mfNNratio)
+        return nm, idx.copy()
+
+    def SearchByProjectionSim3(self, KF, pts, matched, th):
+        """The search of ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:295-410, loop
+        detection): like FuseSim3, but key-frame features already in vpMatched are skipped and every match is entered into it.
+        `matched` [N] bool is updated in place.  Returns (nmatches, bestIdx [M])."""
+        lvl = np.asarray(pts['level'], np.int32)
+        q = np.zeros(len(lvl), PROJ_QUERY_DTYPE)
+        q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1
+        q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
+        q['min_level'] = lvl - 1; q['max_level'] = lvl
+        q['claims'] = 1
+        b = KF['bounds']
+        self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+        idx, _, nm = self._pm.search(q, pts['desc'], np.asarray(matched, np.uint8), 1, self.TH_LOW, self.mfNNratio)
+        matched[idx[idx >= 0]] = True
+        return nm, idx.copy()
+
     def SearchByProjectionKF(self, Cur, kf, th, ORBdist):
         """Matching part of SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1499-1628, used by
         relocalisation).  `kf` holds, for every key-frame map point that is good, not already found and projects inside the image

@@ -328,3 +328,28 @@ def test_gpu_fuse_and_reloc_projection_match_oracle(hvo, synth):
     ridx3, _, rn3 = oracle.search_projection(k0, None, d0, BOUNDS, q3, qd, has_mp.astype(np.uint8), 1, 64)
     assert rn3 > 50 and nm == rn3 and np.array_equal(match, ridx3)
     assert not np.any(has_mp[match[match >= 0]])                     # blocked keypoints never receive a match
+
+
+@pytest.mark.gpu
+def test_gpu_loop_closing_searches_match_oracle(hvo, synth):
+    """ORBmatcher::Fuse(KF, Scw, ...) and SearchByProjection(KF, Scw, ...) (ORBmatcher.cc:992-1121, 295-410): window + level range,
+    best <= TH_LOW; the first claims nothing, the second skips and fills vpMatched."""
+    k0, d0, ur, claimed, q, qd = _scenario(synth, seed=8, n_extra=150, claims_all=True)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    lvl = np.clip(q['max_level'], 0, 7).astype(np.int32)
+    KF = dict(keys_un=k0, desc=d0, bounds=BOUNDS, scale_factors=sf)
+    pts = dict(u=q['u'], v=q['v'], level=lvl, desc=qd)
+    m = hvo.ORBmatcher(0.75, True)
+    qq = q.copy(); qq['r'] = (np.float32(4.0) * sf[lvl]).astype(np.float32); qq['min_level'] = lvl - 1; qq['max_level'] = lvl; qq['ur'] = -1
+    qq['claims'] = 0
+    n1, b1 = m.FuseSim3(KF, pts, 4.0)
+    r1, _, rn1 = oracle.search_projection(k0, None, d0, BOUNDS, qq, qd, None, 1, 50)
+    assert rn1 > 30 and n1 == rn1 and np.array_equal(b1, r1)
+    assert len(set(b1[b1 >= 0].tolist())) < (b1 >= 0).sum() or True          # without claims several points may pick one keypoint
+    matched = claimed.astype(bool).copy()
+    qq['claims'] = 1
+    n2, b2 = m.SearchByProjectionSim3(KF, pts, matched, 4.0)
+    r2, _, rn2 = oracle.search_projection(k0, None, d0, BOUNDS, qq, qd, claimed, 1, 50)
+    assert rn2 > 30 and n2 == rn2 and np.array_equal(b2, r2)
+    got = b2[b2 >= 0]
+    assert len(set(got.tolist())) == len(got) and not np.any(claimed.astype(bool)[got]) and np.all(matched[got])
