@@ -30,7 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':  # keeps NCCL's version banner out of stdout (one JSON line is the contract)
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':  # keeps NCCL's version banner (env or nccl.conf) out of stdout: one JSON line is the contract
     os.environ['NCCL_DEBUG'] = 'WARN'
 
 METRIC = 'front-end frames/s @640x480'
