@@ -30,8 +30,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':  # keeps NCCL's version banner (env or nccl.conf) out of stdout: one JSON line is the contract
-    os.environ['NCCL_DEBUG'] = 'WARN'
+
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner at the WARN / VERSION debug levels) write to
+# file descriptor 1 directly, so descriptor 1 is pointed at stderr for the whole run and the result line goes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + '\n').encode())
+
 
 METRIC = 'front-end frames/s @640x480'
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
@@ -172,7 +180,7 @@ def run_reference(args, rank, world):
         oracle.frontend_batch(gray, depth, ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB)
     dt = time.perf_counter() - t
     v = sample * args.steps / dt
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
@@ -184,7 +192,7 @@ def run_reference(args, rank, world):
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': f'{sample} frames x {args.steps} steps'},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    })
 
 
 def main():
@@ -280,8 +288,8 @@ def main():
     means = dict(keypoints=d_counts('kp_counts'), lines=d_counts('line_counts'), planes=d_counts('n_planes'))
 
     if args.device_only:
-        print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
-                          'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means}))
+        emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
+              'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means})
         return
 
     roofline = None
@@ -409,7 +417,7 @@ def main():
 
     if args.e2e_only:
         if rank == 0:
-            print(json.dumps({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'lanes': fe.lanes, 'chunk': fe.chunk}))
+            emit({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'lanes': fe.lanes, 'chunk': fe.chunk})
         return
     # ---- single-frame latency through the host call (p50) ----
     fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
@@ -428,7 +436,7 @@ def main():
         cpu = cpu_baseline(gray, depth)
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic',
@@ -440,7 +448,7 @@ def main():
                        'l2': f'inputs larger than L2: per-step inputs {B} x 0.92 MB and working set ~{B} x 17 MB >> 126 MB'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step, 'clocks': clk, 'p50_latency_ms_single_frame': p50,
-        }))
+        })
     if world > 1:
         dist.destroy_process_group()
 
