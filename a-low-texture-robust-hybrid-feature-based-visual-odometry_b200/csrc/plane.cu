@@ -748,6 +748,8 @@ __global__ void __launch_bounds__(32, HVO_AHC_MINBLOCKS) k_plane_cluster(AhcArgs
 static const int kFloodThreads = 256, kFloodBuckets = 4096;
 
 struct FloodPix { double px, py, z; };
+// (double)v for a 16-bit value without the conversion pipe: 2^52 + v is exact, subtracting 2^52 gives v
+__device__ __forceinline__ double u16_to_double(uint16_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 __device__ __forceinline__ bool flood_point(const AhcArgs& A, const uint16_t* D, int cIdx, int cx, int cy, FloodPix& P) {
     P.z = (double)D[cIdx] * A.cam.factor;
     if (P.z == 0) return false;
@@ -851,6 +853,8 @@ __global__ void __launch_bounds__(kFloodThreads, 4) k_plane_flood(AhcArgs A) {
         if (have_next) q_next = queue[head + nbat + tid];
         const int plid = (int)(q >> 20);
         int cI[4], trail0[4];
+        int cxs[4] = {0, 0, 0, 0}, cys[4] = {0, 0, 0, 0};
+        uint16_t z16[4] = {0, 0, 0, 0};
         float cdist[4];
         unsigned okm = 0, pend = 0, pushm = 0;  // bit d: visit d passes the plane test / is pending / pushes a new seed
         if (have) {
@@ -861,8 +865,8 @@ __global__ void __launch_bounds__(kFloodThreads, 4) k_plane_flood(AhcArgs A) {
             cI[1] = sx < W - 1 ? sIdx + 1 : -1;
             cI[2] = sy > 0 ? sIdx - W : -1;
             cI[3] = sy < H - 1 ? sIdx + W : -1;
-            int cxs[4] = {sx - 1, sx + 1, sx, sx}, cys[4] = {sy, sy, sy - 1, sy + 1};
-            uint16_t z16[4];
+            cxs[0] = sx - 1; cxs[1] = sx + 1; cxs[2] = sx; cxs[3] = sx;
+            cys[0] = sy; cys[1] = sy; cys[2] = sy - 1; cys[3] = sy + 1;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 if (cI[d] >= 0) {
@@ -877,7 +881,7 @@ __global__ void __launch_bounds__(kFloodThreads, 4) k_plane_flood(AhcArgs A) {
             for (int d = 0; d < 4; ++d) {
                 cdist[d] = -1.f;
                 if (cI[d] >= 0) {
-                    const double z = (double)z16[d] * A.cam.factor;
+                    const double z = u16_to_double(z16[d]) * A.cam.factor;
                     if (z != 0) {
                         FloodPix P;
                         P.z = z;
@@ -922,9 +926,10 @@ __global__ void __launch_bounds__(kFloodThreads, 4) k_plane_flood(AhcArgs A) {
                                 atomicOr(&adj[(size_t)na * A.nw + (nbn >> 5)], 1u << (nbn & 31));
                                 atomicOr(&adj[(size_t)nbn * A.nw + (na >> 5)], 1u << (na & 31));
                             }
-                            const int cy = cIdx / W, cx = cIdx - cy * W;
-                            FloodPix P;
-                            flood_point(A, D, cIdx, cx, cy, P);
+                            FloodPix P;   // okm implies a valid depth; the pixel's depth is still in a register
+                            P.z = u16_to_double(z16[d]) * A.cam.factor;
+                            P.px = div_by_const(((double)cxs[d] - A.cam.cx) * P.z, A.cam.fx, A.cam.rfx);
+                            P.py = div_by_const(((double)cys[d] - A.cam.cy) * P.z, A.cam.fy, A.cam.rfy);
                             od = flood_dist(b, P);  // == distMap[cIdx]: the distance stored when the pixel took label `trail`
                         }
                         if (cdist[d] < od) { mem[cIdx] = plid; pushm |= 1u << d; }
