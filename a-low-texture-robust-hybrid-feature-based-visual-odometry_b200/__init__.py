@@ -92,6 +92,8 @@ ABI = {
     'hvo_proj_last_launches': (C.c_int, [_vp]),
     'hvo_proj_match_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     'hvo_proj_search_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_proj_search_triangulation': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp,
+                                               C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(C.c_int)]),
     'hvo_proj_timer_start': (C.c_int, [_vp]),
     'hvo_proj_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_line_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -1153,6 +1155,25 @@ class ProjectionMatcher:
         self.n = 0
         return best4[:len(q)]
 
+    def search_triangulation(self, qdesc, qkeys, qstereo, tdesc, tkeys, tflags, offsets, cand, F12, ex, ey, scale_factors, level_sigma2,
+                             only_stereo=False, th_low=50):
+        """the candidate loop of ORBmatcher::SearchForTriangulation (hvo_proj_search_triangulation)."""
+        qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32); qk = np.ascontiguousarray(qkeys, KP_DTYPE)
+        qs = np.ascontiguousarray(qstereo, np.uint8)
+        td = np.ascontiguousarray(tdesc, np.uint8).reshape(-1, 32); tk = np.ascontiguousarray(tkeys, KP_DTYPE)
+        tf = np.ascontiguousarray(tflags, np.uint8)
+        off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sf = np.ascontiguousarray(scale_factors, np.float32); sg = np.ascontiguousarray(level_sigma2, np.float32)
+        idx = np.full(max(len(qd), 1), -1, np.int32); dist = np.full(max(len(qd), 1), 256, np.int32)
+        nm = C.c_int(0)
+        _check(lib().hvo_proj_search_triangulation(self._h, _np_ptr(qd), _np_ptr(qk), _np_ptr(qs), len(qd), _np_ptr(td), _np_ptr(tk), _np_ptr(tf),
+                                                   len(td), _np_ptr(off), _np_ptr(cd), _np_ptr(F), float(np.float32(ex)), float(np.float32(ey)),
+                                                   _np_ptr(sf), _np_ptr(sg), len(sf), int(bool(only_stereo)), int(th_low), _np_ptr(idx),
+                                                   _np_ptr(dist), C.byref(nm)))
+        self.n = 0
+        return idx[:len(qd)], dist[:len(qd)], nm.value
+
     def search_candidates(self, q, t, offsets, cand, th_dist=50, nnratio=0.7):
         """greedy best / second over caller-given candidate lists (the loop of ORBmatcher::SearchByBoW)."""
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
@@ -1244,6 +1265,44 @@ class ORBmatcher:
                 if kf_has_mappoint[i]:
                     qi.append(i); cand.extend(fl); off.append(len(cand))
         return np.asarray(qi, np.int32), np.asarray(off, np.int32), np.asarray(cand, np.int32)
+
+    def SearchForTriangulation(self, KF1, KF2, F12, epipole, bOnlyStereo=False):
+        """ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:668-836).
+        KFi = dict(desc, keys_un, uright, featvec, has_mappoint [N] bool, scale_factors, level_sigma2); epipole = (ex, ey) of pKF1's
+        camera centre in pKF2 (:676-683, host pose algebra).  Returns (nmatches, vMatchedPairs [[idx1, idx2]])."""
+        free1 = ~np.asarray(KF1['has_mappoint'], bool)
+        qi, off, cand = self.bow_queries(KF1['featvec'], KF2['featvec'], free1)
+        if len(qi) == 0:
+            return 0, np.zeros((0, 2), np.int32)
+        ur1 = np.asarray(KF1['uright'], np.float32); ur2 = np.asarray(KF2['uright'], np.float32)
+        tflags = (np.asarray(KF2['has_mappoint'], bool).astype(np.uint8) | ((ur2 >= 0).astype(np.uint8) << 1)).astype(np.uint8)
+        idx, _, nm = self._pm.search_triangulation(np.asarray(KF1['desc'], np.uint8)[qi], np.asarray(KF1['keys_un'], KP_DTYPE)[qi],
+                                                   (ur1[qi] >= 0), KF2['desc'], KF2['keys_un'], tflags, off, cand, F12, epipole[0], epipole[1],
+                                                   KF2['scale_factors'], KF2['level_sigma2'], bOnlyStereo, self.TH_LOW)
+        m12 = np.full(len(KF1['desc']), -1, np.int32)
+        hist = [[] for _ in range(self.HISTO_LENGTH)]
+        factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+        for k, i in zip(qi, idx):
+            if i < 0:
+                continue
+            m12[k] = i
+            if self.mbCheckOrientation:
+                rot = np.float32(KF1['keys_un']['angle'][k]) - np.float32(KF2['keys_un']['angle'][i])
+                if rot < 0.0:
+                    rot = np.float32(rot + np.float32(360.0))
+                b = int(np.floor(float(np.float32(rot * factor)) + 0.5))  # round(): rot >= 0 here
+                if b == self.HISTO_LENGTH:
+                    b = 0
+                hist[b].append(k)
+        if self.mbCheckOrientation:
+            keep = set(self.ComputeThreeMaxima([len(h) for h in hist]))
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for k in hist[b]:
+                        m12[k] = -1
+                        nm -= 1
+        i1 = np.nonzero(m12 >= 0)[0]
+        return nm, np.stack([i1, m12[i1]], axis=1).astype(np.int32)
 
     def SearchByBoW(self, KF, F):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:162-293).

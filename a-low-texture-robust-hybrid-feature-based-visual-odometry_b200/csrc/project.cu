@@ -270,6 +270,74 @@ __global__ void __launch_bounds__(128) k_cand_round(const uint4* __restrict__ q,
     }
 }
 
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:668-836): candidates of a query = the second key frame's features of the
+// same vocabulary node, in list order; a candidate passes when it holds no map point, satisfies the stereo-only rule, has
+// dist <= TH_LOW, lies away from the epipole (monocular pair) and close to the epipolar line (CheckDistEpipolarLine, :143-160);
+// among the passing candidates `dist <= bestDist` keeps the LAST one of the minimum distance.  Queries are independent
+// (this reference never sets vbMatched2).
+struct TriParams { float F[9]; float ex, ey; int only_stereo, th_low; };
+
+__global__ void __launch_bounds__(128) k_tri_search(const uint4* __restrict__ qdesc, const hvo_keypoint* __restrict__ qkeys,
+                                                    const uint8_t* __restrict__ qstereo, int nq, const uint4* __restrict__ tdesc,
+                                                    const hvo_keypoint* __restrict__ tkeys, const uint8_t* __restrict__ tflags,
+                                                    const int* __restrict__ off, const int* __restrict__ cand, TriParams P,
+                                                    const float* __restrict__ scale_factors, const float* __restrict__ level_sigma2,
+                                                    int* __restrict__ match_idx, int* __restrict__ match_dist) {
+    const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= nq) return;
+    const uint4 qa = qdesc[2 * k], qb = qdesc[2 * k + 1];
+    const hvo_keypoint kp1 = qkeys[k];
+    const bool stereo1 = qstereo[k] != 0;
+    // epipolar line l = x1' F12
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[0]), __fmul_rn(kp1.y, P.F[3])), P.F[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[1]), __fmul_rn(kp1.y, P.F[4])), P.F[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[2]), __fmul_rn(kp1.y, P.F[5])), P.F[8]);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    int bestDist = P.th_low, bestIdx = -1;
+    const bool skip_query = P.only_stereo && !stereo1;
+    const int beg = off[k], end = skip_query ? beg : off[k + 1];
+    for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        int id = -1, dist = 256;
+        bool ok = false;
+        if (i < end) {
+            id = cand[i];
+            const uint8_t fl = tflags[id];  // bit 0: holds a map point, bit 1: has a right coordinate
+            const bool stereo2 = (fl & 2) != 0;
+            ok = !(fl & 1) && !(P.only_stereo && !stereo2);
+            if (ok) {
+                const uint4 da = tdesc[2 * id], db = tdesc[2 * id + 1];
+                dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) + __popc(qb.x ^ db.x) +
+                       __popc(qb.y ^ db.y) + __popc(qb.z ^ db.z) + __popc(qb.w ^ db.w);
+                ok = dist <= P.th_low;
+            }
+            if (ok) {
+                const hvo_keypoint kp2 = tkeys[id];
+                if (!stereo1 && !stereo2) {
+                    const float dx = __fsub_rn(P.ex, kp2.x), dy = __fsub_rn(P.ey, kp2.y);
+                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, scale_factors[kp2.octave])) ok = false;
+                }
+                if (ok) {
+                    if (den == 0) ok = false;
+                    else {
+                        const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), c);
+                        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                        ok = (double)dsqr < 3.84 * (double)level_sigma2[kp2.octave];
+                    }
+                }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int d = __shfl_sync(0xffffffffu, dist, j), cidx = __shfl_sync(0xffffffffu, id, j);
+            if (!(d > bestDist)) { bestDist = d; bestIdx = cidx; }
+        }
+    }
+    if (lane == 0) { match_idx[k] = bestIdx; match_dist[k] = bestIdx >= 0 ? bestDist : 256; }
+}
+
 }  // namespace hvo
 
 using namespace hvo;
@@ -564,6 +632,60 @@ int hvo_proj_search_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint
     if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, h->d_cdist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
     HVO_CUDA(cudaStreamSynchronize(s));
     if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
+    return HVO_OK;
+}
+
+int hvo_proj_search_triangulation(hvo_proj* h, const uint8_t* qdesc, const hvo_keypoint* qkeys, const uint8_t* qstereo, int nq, const uint8_t* tdesc,
+                                  const hvo_keypoint* tkeys, const uint8_t* tflags, int nt, const int32_t* offsets, const int32_t* cand,
+                                  const float* F12, float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                  int only_stereo, int th_low, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
+    HVO_CHECK_ARG(h && match_idx, "null argument");
+    if (n_matches) *n_matches = 0;
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(qdesc && qkeys && qstereo && offsets && F12 && scale_factors && level_sigma2, "null argument");
+    HVO_CHECK_ARG(nlevels >= 1 && nlevels <= 64, "nlevels out of range (1..64)");
+    const int total = offsets[nq];
+    HVO_CHECK_ARG(total >= 0 && (total == 0 || (cand && tdesc && tkeys && tflags && nt > 0)), "candidate lists without a train set");
+    for (int i = 0; i < total; ++i) HVO_CHECK_ARG(cand[i] >= 0 && cand[i] < nt, "candidate index out of range");
+    for (int i = 0; i < nt; ++i) HVO_CHECK_ARG(tkeys[i].octave >= 0 && tkeys[i].octave < nlevels, "train keypoint octave out of range");
+    HVO_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->n = 0;  // scratch of the windowed search is not touched, but the call owns the stream: keep the contract simple
+    uint8_t *d_qd = nullptr, *d_qs = nullptr, *d_td = nullptr, *d_tf = nullptr;
+    hvo_keypoint *d_qk = nullptr, *d_tk = nullptr;
+    int *d_off = nullptr, *d_cand = nullptr, *d_out = nullptr;
+    float* d_tab = nullptr;
+    const size_t ntt = (size_t)std::max(nt, 1), tot = (size_t)std::max(total, 1);
+    HVO_CUDA(cudaMallocAsync(&d_qd, (size_t)nq * 32, s)); HVO_CUDA(cudaMallocAsync(&d_qk, (size_t)nq * sizeof(hvo_keypoint), s));
+    HVO_CUDA(cudaMallocAsync(&d_qs, (size_t)nq, s)); HVO_CUDA(cudaMallocAsync(&d_td, ntt * 32, s));
+    HVO_CUDA(cudaMallocAsync(&d_tk, ntt * sizeof(hvo_keypoint), s)); HVO_CUDA(cudaMallocAsync(&d_tf, ntt, s));
+    HVO_CUDA(cudaMallocAsync(&d_off, ((size_t)nq + 1) * 4, s)); HVO_CUDA(cudaMallocAsync(&d_cand, tot * 4, s));
+    HVO_CUDA(cudaMallocAsync(&d_out, (size_t)nq * 8, s)); HVO_CUDA(cudaMallocAsync(&d_tab, 128 * sizeof(float), s));
+    HVO_CUDA(cudaMemcpyAsync(d_qd, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_qk, qkeys, (size_t)nq * sizeof(hvo_keypoint), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_qs, qstereo, (size_t)nq, cudaMemcpyHostToDevice, s));
+    if (nt > 0) {
+        HVO_CUDA(cudaMemcpyAsync(d_td, tdesc, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+        HVO_CUDA(cudaMemcpyAsync(d_tk, tkeys, (size_t)nt * sizeof(hvo_keypoint), cudaMemcpyHostToDevice, s));
+        HVO_CUDA(cudaMemcpyAsync(d_tf, tflags, (size_t)nt, cudaMemcpyHostToDevice, s));
+    }
+    HVO_CUDA(cudaMemcpyAsync(d_off, offsets, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (total > 0) HVO_CUDA(cudaMemcpyAsync(d_cand, cand, (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_tab, scale_factors, (size_t)nlevels * sizeof(float), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_tab + 64, level_sigma2, (size_t)nlevels * sizeof(float), cudaMemcpyHostToDevice, s));
+    TriParams P;
+    for (int i = 0; i < 9; ++i) P.F[i] = F12[i];
+    P.ex = ex; P.ey = ey; P.only_stereo = only_stereo != 0; P.th_low = th_low;
+    k_tri_search<<<div_up(nq * 32, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(d_qd), d_qk, d_qs, nq, reinterpret_cast<const uint4*>(d_td), d_tk,
+                                                      d_tf, d_off, d_cand, P, d_tab, d_tab + 64, d_out, d_out + nq);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(match_idx, d_out, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, d_out + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    void* bufs[] = {d_qd, d_qk, d_qs, d_td, d_tk, d_tf, d_off, d_cand, d_out, d_tab};
+    for (void* b : bufs) HVO_CUDA(cudaFreeAsync(b, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
+    h->last_launches = 1; h->last_rounds = 1;
     return HVO_OK;
 }
 

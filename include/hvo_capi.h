@@ -198,6 +198,16 @@ int hvo_proj_match_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8
  * match_idx[i] = frame feature or -1.  Invalidates the frame set by hvo_proj_set_frame. */
 int hvo_proj_search_candidates(hvo_proj* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets, const int32_t* cand,
                                int th_dist, float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches);
+/* The candidate loop of ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:668-836)
+ * with CheckDistEpipolarLine (:143-160).  Queries = features of pKF1 without a map point, in (vocabulary node, index list) order, with
+ * their undistorted keypoints and stereo flags; cand lists = features of pKF2 in the same node.  tflags[i]: bit 0 = pKF2 feature i
+ * holds a map point, bit 1 = it has a right coordinate.  F12 row-major 3x3, (ex, ey) = epipole in pKF2, scale_factors / level_sigma2 of
+ * pKF2.  match_idx[i] = pKF2 feature or -1 (the last candidate of minimum distance <= th_low that passes the gates).  The rotation
+ * histogram and vMatchedPairs stay with the caller.  Invalidates the frame set by hvo_proj_set_frame. */
+int hvo_proj_search_triangulation(hvo_proj* h, const uint8_t* qdesc, const hvo_keypoint* qkeys, const uint8_t* qstereo, int nq, const uint8_t* tdesc,
+                                  const hvo_keypoint* tkeys, const uint8_t* tflags, int nt, const int32_t* offsets, const int32_t* cand,
+                                  const float* F12, float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                  int only_stereo, int th_low, int32_t* match_idx, int32_t* match_dist, int* n_matches);
 int hvo_proj_timer_start(hvo_proj* h);
 int hvo_proj_timer_stop(hvo_proj* h, float* ms_out);
 

@@ -289,6 +289,26 @@ def search_fuse(keys, uright, desc, bounds, queries, qdesc, inv_sigma2, th_dist=
     return idx[:len(q)], dist[:len(q)], int(n)
 
 
+def search_triangulation(qdesc, qkeys, qstereo, tdesc, tkeys, tflags, offsets, cand, F12, ex, ey, scale_factors, level_sigma2,
+                         only_stereo=False, th_low=50):
+    """the candidate loop of ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:668-836, CheckDistEpipolarLine :143-160)."""
+    qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32); qk = np.ascontiguousarray(qkeys, KP_DTYPE)
+    qs = np.ascontiguousarray(qstereo, np.uint8)
+    td = np.ascontiguousarray(tdesc, np.uint8).reshape(-1, 32); tk = np.ascontiguousarray(tkeys, KP_DTYPE)
+    tf = np.ascontiguousarray(tflags, np.uint8)
+    off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf = np.ascontiguousarray(scale_factors, np.float32); sg = np.ascontiguousarray(level_sigma2, np.float32)
+    idx = np.full(max(len(qd), 1), -1, np.int32); dist = np.full(max(len(qd), 1), 256, np.int32)
+    f = lib().orc_search_triangulation
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                  C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = f(_p(qd), _p(qk), _p(qs), len(qd), _p(td), _p(tk), _p(tf), _p(off), _p(cd), _p(F), float(np.float32(ex)), float(np.float32(ey)), _p(sf),
+          _p(sg), int(bool(only_stereo)), int(th_low), _p(idx), _p(dist))
+    return idx[:len(qd)], dist[:len(qd)], int(n)
+
+
 def match_candidates(q, t, offsets, cand):
     q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
     off = np.ascontiguousarray(offsets, np.int32); cd = np.ascontiguousarray(cand, np.int32)

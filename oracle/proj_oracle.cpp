@@ -180,6 +180,47 @@ int orc_search_fuse(const void* keys, const float* uright, const uint8_t* desc, 
     return nm;
 }
 
+// the candidate loop of ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:668-836) with CheckDistEpipolarLine (:143-160)
+int orc_search_triangulation(const uint8_t* qdesc, const void* qkeys, const uint8_t* qstereo, int nq, const uint8_t* tdesc, const void* tkeys,
+                             const uint8_t* tflags, const int32_t* off, const int32_t* cand, const float* F12, float ex, float ey,
+                             const float* scale_factors, const float* level_sigma2, int only_stereo, int th_low, int32_t* match_idx,
+                             int32_t* match_dist) {
+    using namespace projo;
+    const KeyPoint* K1 = (const KeyPoint*)qkeys;
+    const KeyPoint* K2 = (const KeyPoint*)tkeys;
+    int nm = 0;
+    for (int k = 0; k < nq; ++k) {
+        match_idx[k] = -1; match_dist[k] = 256;
+        const bool bStereo1 = qstereo[k] != 0;
+        if (only_stereo && !bStereo1) continue;
+        const KeyPoint& kp1 = K1[k];
+        int bestDist = th_low, bestIdx2 = -1;
+        for (int c = off[k]; c < off[k + 1]; ++c) {
+            const int idx2 = cand[c];
+            if (tflags[idx2] & 1) continue;
+            const bool bStereo2 = (tflags[idx2] & 2) != 0;
+            if (only_stereo && !bStereo2) continue;
+            const int dist = hamming(qdesc + 32 * (size_t)k, tdesc + 32 * (size_t)idx2);
+            if (dist > th_low || dist > bestDist) continue;
+            const KeyPoint& kp2 = K2[idx2];
+            if (!bStereo1 && !bStereo2) {
+                const float distex = ex - kp2.x, distey = ey - kp2.y;
+                if (distex * distex + distey * distey < 100 * scale_factors[kp2.octave]) continue;
+            }
+            const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+            const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+            const float cc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+            const float num = a * kp2.x + b * kp2.y + cc;
+            const float den = a * a + b * b;
+            if (den == 0) continue;
+            const float dsqr = num * num / den;
+            if (dsqr < 3.84 * level_sigma2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) { match_idx[k] = bestIdx2; match_dist[k] = bestDist; ++nm; }
+    }
+    return nm;
+}
+
 // generic candidate lists (e.g. the per-vocabulary-node buckets of SearchByBoW, src/ORBmatcher.cc:162-293): for query i the
 // train indices cand[off[i] .. off[i+1]) in the caller's order; best4[i] = {idx0, dist0, idx1, dist1}, strict '<' updates.
 void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* off, const int32_t* cand, int32_t* best4) {

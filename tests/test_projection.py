@@ -353,3 +353,61 @@ def test_gpu_loop_closing_searches_match_oracle(hvo, synth):
     assert rn2 > 30 and n2 == rn2 and np.array_equal(b2, r2)
     got = b2[b2 >= 0]
     assert len(set(got.tolist())) == len(got) and not np.any(claimed.astype(bool)[got]) and np.all(matched[got])
+
+
+def _fundamental(tx=0.05, ty=0.01, tz=0.0, fx=535.4, fy=539.2, cx=320.1, cy=247.6):
+    """F12 of two cameras that differ by a small translation (x1' F12 x2 = 0), float32 like the reference's cv::Mat."""
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    t = np.array([tx, ty, tz])
+    tx_ = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    F = np.linalg.inv(K).T @ tx_ @ np.linalg.inv(K)
+    return (F / np.abs(F).max()).astype(np.float32)
+
+
+def test_oracle_triangulation_gates():
+    k1 = np.zeros(1, oracle.KP_DTYPE); k1['x'] = 300; k1['y'] = 200
+    k2 = np.zeros(4, oracle.KP_DTYPE); k2['x'] = [310, 310, 310, 400]; k2['y'] = [200, 200, 230, 200]
+    F = _fundamental(ty=0.0)                                  # pure x translation: epipolar lines are horizontal (y2 = y1)
+    d1 = np.zeros((1, 32), np.uint8); d2 = np.zeros((4, 32), np.uint8); d2[3, 0] = 0x01
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32); sg = (sf * sf).astype(np.float32)
+    off = np.array([0, 4], np.int32); cand = np.arange(4, dtype=np.int32)
+    args = (d1, k1, [0], d2, k2, None, off, cand, F, -1e6, -1e6, sf, sg)
+    run = lambda fl, **kw: oracle.search_triangulation(*args[:5], fl, *args[6:], **kw)
+    idx, dist, n = run([0, 0, 0, 0])
+    assert idx.tolist() == [1] and dist.tolist() == [0] and n == 1       # equal distances: the LAST passing candidate; row 2 is off the line
+    assert run([0, 1, 0, 0])[0].tolist() == [0]                         # a candidate with a map point is skipped
+    assert run([1, 1, 0, 0])[0].tolist() == [3]                         # only the worse one on the line remains (distance 1)
+    assert run([0, 0, 0, 0], only_stereo=True)[2] == 0                  # monocular query under bOnlyStereo
+    idx, _, _ = oracle.search_triangulation(d1, k1, [0], d2, k2, [0, 0, 0, 0], off, cand, F, 310.0, 200.0, sf, sg)
+    assert idx.tolist() == [3]                                          # candidates within 10 px of the epipole are dropped (mono pair)
+
+
+@pytest.mark.gpu
+def test_gpu_search_for_triangulation_matches_oracle(hvo, synth):
+    KFa, Fb = _bow_scenario(synth, seed=2)
+    rng = np.random.RandomState(12)
+    k1, k2 = KFa['keys_un'], Fb['keys']
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32); sg = (sf * sf).astype(np.float32)
+    ur1 = np.where(rng.rand(len(k1)) < 0.6, k1['x'] - 20, -1).astype(np.float32)
+    ur2 = np.where(rng.rand(len(k2)) < 0.6, k2['x'] - 20, -1).astype(np.float32)
+    KF1 = dict(desc=KFa['desc'], keys_un=k1, uright=ur1, featvec=KFa['featvec'], has_mappoint=rng.rand(len(k1)) < 0.4, scale_factors=sf, level_sigma2=sg)
+    KF2 = dict(desc=Fb['desc'], keys_un=k2, uright=ur2, featvec=Fb['featvec'], has_mappoint=rng.rand(len(k2)) < 0.3, scale_factors=sf, level_sigma2=sg)
+    F12 = _fundamental(0.004, 0.0005)                        # S1/0 -> S1/1 is a small motion: matches lie near these epipolar lines
+    m = hvo.ORBmatcher(0.6, False)
+    qi, off, cand = m.bow_queries(KF1['featvec'], KF2['featvec'], ~KF1['has_mappoint'])
+    tflags = (KF2['has_mappoint'].astype(np.uint8) | ((ur2 >= 0).astype(np.uint8) << 1)).astype(np.uint8)
+    pm = hvo.ProjectionMatcher()
+    total = 0
+    for only_stereo in (False, True):
+        for ex, ey in ((-1e5, 240.0), (330.0, 240.0)):
+            got = pm.search_triangulation(KF1['desc'][qi], k1[qi], ur1[qi] >= 0, KF2['desc'], k2, tflags, off, cand, F12, ex, ey, sf, sg, only_stereo, 50)
+            ref = oracle.search_triangulation(KF1['desc'][qi], k1[qi], ur1[qi] >= 0, KF2['desc'], k2, tflags, off, cand, F12, ex, ey, sf, sg, only_stereo, 50)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+            total += ref[2]
+    assert total > 40
+    pm.close()
+    nm, pairs = m.SearchForTriangulation(KF1, KF2, F12, (-1e5, 240.0), False)
+    ref = oracle.search_triangulation(KF1['desc'][qi], k1[qi], ur1[qi] >= 0, KF2['desc'], k2, tflags, off, cand, F12, -1e5, 240.0, sf, sg, False, 50)
+    want = {(int(a), int(b)) for a, b in zip(qi, ref[0]) if b >= 0}
+    assert nm == len(want) > 10 and {(int(a), int(b)) for a, b in pairs} == want
+    assert not np.any(KF1['has_mappoint'][pairs[:, 0]]) and not np.any(KF2['has_mappoint'][pairs[:, 1]])
