@@ -1408,6 +1408,31 @@ class ORBmatcher:
         idx, _, nm = self._pm.search(q, pts['desc'], None, 1, self.TH_LOW, self.mfNNratio)
         return nm, idx.copy()
 
+    def SearchBySim3(self, KF1, KF2, pts1in2, pts2in1, th):
+        """The searches of ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (ORBmatcher.cc:1123-1351): the map
+        points of KF1 projected into KF2 and those of KF2 projected into KF1 (Sim3 algebra, PredictScale and the already-matched /
+        bad / out-of-range filters stay with the caller), each matched to the best descriptor in its window at levels
+        [level-1, level] when <= TH_HIGH, kept where both directions agree (:1213-1228).  ptsAinB = dict(index (feature of A),
+        u, v, level, desc).  Returns (nFound, pairs [[idx1, idx2]])."""
+        def one(KF, pts):
+            lvl = np.asarray(pts['level'], np.int32)
+            q = np.zeros(len(lvl), PROJ_QUERY_DTYPE)
+            q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1
+            q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
+            q['min_level'] = lvl - 1; q['max_level'] = lvl
+            b = KF['bounds']
+            self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+            return self._pm.search(q, pts['desc'], None, 1, self.TH_HIGH, self.mfNNratio)[0]
+        m1 = np.full(len(KF1['desc']), -1, np.int32); m2 = np.full(len(KF2['desc']), -1, np.int32)
+        if len(pts1in2['u']):
+            m1[np.asarray(pts1in2['index'], np.int64)] = one(KF2, pts1in2)
+        if len(pts2in1['u']):
+            m2[np.asarray(pts2in1['index'], np.int64)] = one(KF1, pts2in1)
+        i1 = np.nonzero(m1 >= 0)[0]
+        ok = m2[m1[i1]] == i1
+        pairs = np.stack([i1[ok], m1[i1[ok]]], axis=1).astype(np.int32)
+        return len(pairs), pairs
+
     def SearchByProjectionSim3(self, KF, pts, matched, th):
         """The search of ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:295-410, loop
         detection): like FuseSim3, but key-frame features already in vpMatched are skipped and every match is entered into it.

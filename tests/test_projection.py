@@ -411,3 +411,33 @@ def test_gpu_search_for_triangulation_matches_oracle(hvo, synth):
     want = {(int(a), int(b)) for a, b in zip(qi, ref[0]) if b >= 0}
     assert nm == len(want) > 10 and {(int(a), int(b)) for a, b in pairs} == want
     assert not np.any(KF1['has_mappoint'][pairs[:, 0]]) and not np.any(KF2['has_mappoint'][pairs[:, 1]])
+
+
+@pytest.mark.gpu
+def test_gpu_search_by_sim3_cross_check(hvo, synth):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1123-1351): two windowed searches (TH_HIGH, levels [l-1, l], nothing claimed) and
+    the agreement test, against the oracle's sequential loop run in both directions."""
+    ka, da = _frame_keys(synth, 'S1', 0)
+    kb, db = _frame_keys(synth, 'S1', 1)
+    rng = np.random.RandomState(21)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    KF1 = dict(keys_un=ka, desc=da, bounds=BOUNDS, scale_factors=sf)
+    KF2 = dict(keys_un=kb, desc=db, bounds=BOUNDS, scale_factors=sf)
+
+    def proj(k, d, n):                                   # "map points" of one key frame seen in the other: same scene, small motion
+        sel = np.sort(rng.choice(len(k), n, replace=False))
+        return dict(index=sel, u=(k['x'][sel] + rng.normal(0, 1.5, n)).astype(np.float32), v=(k['y'][sel] + rng.normal(0, 1.5, n)).astype(np.float32),
+                    level=k['octave'][sel].astype(np.int32), desc=d[sel])
+    p12, p21 = proj(ka, da, 600), proj(kb, db, 600)
+    m = hvo.ORBmatcher(0.75, True)
+    n, pairs = m.SearchBySim3(KF1, KF2, p12, p21, 7.5)
+
+    def ref(K, D, pts):
+        q = np.zeros(len(pts['u']), oracle.PROJ_QUERY_DTYPE)
+        q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1; q['r'] = (np.float32(7.5) * sf[pts['level']]).astype(np.float32)
+        q['min_level'] = pts['level'] - 1; q['max_level'] = pts['level']
+        return oracle.search_projection(K, None, D, BOUNDS, q, pts['desc'], None, 1, 100)[0]
+    m1 = np.full(len(ka), -1, np.int32); m1[p12['index']] = ref(kb, db, p12)
+    m2 = np.full(len(kb), -1, np.int32); m2[p21['index']] = ref(ka, da, p21)
+    want = [(i, m1[i]) for i in range(len(ka)) if m1[i] >= 0 and m2[m1[i]] == i]
+    assert n == len(want) > 30 and [tuple(p) for p in pairs.tolist()] == want
