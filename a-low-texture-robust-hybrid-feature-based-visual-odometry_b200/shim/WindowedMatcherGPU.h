@@ -5,6 +5,8 @@
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)        src/ORBmatcher.cc:45-132     PointWindowMatcher::search(mode 0)
 //   ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, mono)           src/ORBmatcher.cc:1353-1497  PointWindowMatcher::search(mode 1)
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)               src/ORBmatcher.cc:162-293    PointWindowMatcher::searchCandidates
+//   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)                   src/ORBmatcher.cc:838-990    PointWindowMatcher::setLevelSigma + search(mode 2)
+//   ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, pairs, bOnlyStereo)     src/ORBmatcher.cc:668-836    PointWindowMatcher::searchTriangulation
 //   LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, bool, th)   src/LSDmatcher.cpp:709-801   LineWindowMatcher::search(mode 0)
 //   LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th)                 src/LSDmatcher.cpp:561-664   LineWindowMatcher::search(mode 1)
 //   Manhattan::computeNormalsLPVO(depth, K, pt_normals, depth_normals)          src/Manhattan.cpp:237-393    LpvoNormals::compute
@@ -51,6 +53,25 @@ public:
         int n = 0;
         if (nq > 0 && !ok(hvo_proj_search_candidates(h_, qdesc.data(), nq, tdesc.data(), (int)(tdesc.size() / 32), offsets.data(), cand.data(), th,
                                                      nnratio, idx.data(), nullptr, &n))) return 0;
+        return n;
+    }
+
+    // Fuse: mvInvLevelSigma2 of the key frame searched in, then search(mode 2, TH_LOW)
+    bool setLevelSigma(const std::vector<float>& invLevelSigma2) { return ok(hvo_proj_set_level_sigma(h_, invLevelSigma2.data(), (int)invLevelSigma2.size())); }
+    // SearchForTriangulation: queries = pKF1 features without a map point in (node, list) order; tflags bit 0 = pKF2 feature holds a
+    // map point, bit 1 = it has a right coordinate; F12 row-major; (ex, ey) epipole in pKF2
+    int searchTriangulation(const std::vector<uint8_t>& qdesc, const std::vector<hvo_keypoint>& qkeys, const std::vector<uint8_t>& qstereo,
+                            const std::vector<uint8_t>& tdesc, const std::vector<hvo_keypoint>& tkeys, const std::vector<uint8_t>& tflags,
+                            const std::vector<int32_t>& offsets, const std::vector<int32_t>& cand, const float F12[9], float ex, float ey,
+                            const std::vector<float>& scaleFactors, const std::vector<float>& levelSigma2, bool onlyStereo, int thLow,
+                            std::vector<int32_t>& idx) {
+        const int nq = (int)qkeys.size();
+        idx.assign(nq, -1);
+        int n = 0;
+        if (nq > 0 && !ok(hvo_proj_search_triangulation(h_, qdesc.data(), qkeys.data(), qstereo.data(), nq, tdesc.data(), tkeys.data(), tflags.data(),
+                                                        (int)tkeys.size(), offsets.data(), cand.data(), F12, ex, ey, scaleFactors.data(),
+                                                        levelSigma2.data(), (int)scaleFactors.size(), onlyStereo ? 1 : 0, thLow, idx.data(), nullptr,
+                                                        &n))) return 0;
         return n;
     }
 
