@@ -298,8 +298,8 @@ __device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t
     const int ddy = k / 3 - 1, ddx = k - (k / 3) * 3 - 1;
     while (i < n) {
         const int nb = min(3, n - i);
-        bool def = false;
-        int xx = 0, yy = 0, ni = 0;
+        bool def = false, isused = true;
+        int xx = 0, yy = 0, ni = -1;
         LsdPix p;
         p.ang = LSD_NOTDEF; p.c = 0.f; p.s = 0.f;
         if (cidx < nb && k != 4) {
@@ -308,13 +308,16 @@ __device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t
             xx = (int)(c & 0xffff) + ddx; yy = (int)(c >> 16) + ddy;
             if (xx >= 0 && yy >= 0 && xx < w && yy < h) {
                 ni = yy * w + xx;
+                // record and `used` bit are requested together; pixels accepted later in this step are tracked in `isused` below,
+                // so the bitmap is not read again after the record has arrived
+                isused = used_get(used, ni);
                 p = pix[ni];
                 def = p.ang != LSD_NOTDEF;
             }
         }
         const double a = (double)p.ang * LSD_DEG2RAD;
         for (int c = 0; c < nb; ++c) {
-            const bool cand = def && cidx == c && !used_get(used, ni);
+            const bool cand = def && cidx == c && !isused;
             unsigned pending = __ballot_sync(kFull, cand);
             while (pending) {
                 const bool al = cand && lsd_aligned(reg_angle, a, prec);
@@ -328,6 +331,7 @@ __device__ int lsd_region_grow(const LsdPix* __restrict__ pix, volatile uint32_t
                     ring[n & (kRing - 1)] = packed;
                     lsd_prefetch_nbhd(pix, w, h, xx, yy);
                 }
+                if (ni == __shfl_sync(kFull, ni, j)) isused = true;  // the same pixel seen from a later centre of this step
                 const float cs = __shfl_sync(kFull, p.c, j), sn = __shfl_sync(kFull, p.s, j);
                 sumdx = __fadd_rn(sumdx, cs);
                 sumdy = __fadd_rn(sumdy, sn);
