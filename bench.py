@@ -111,6 +111,11 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            self.proc.wait()
         sm, smax, reasons = [], None, set()
         for ts, line in self.lines:
             p = [x.strip() for x in line.split(',')]
@@ -222,16 +227,15 @@ def main():
     import hvo_b200 as hvo
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    B, W, H = args.batch, 640, 480
+    # every rank gets its own frames (frame-sharded, weak scaling): up to 1024 distinct frames per rank (8192 over 8 GPUs, the
+    # C5 sequence), repeated to fill the batch.  Generated (forked worker pool) before this process touches CUDA or NCCL.
+    n_distinct = min(B, 1024)
+    gray, depth = make_frames(n_distinct, start=rank * n_distinct)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    B, W, H = args.batch, 640, 480
-    # every rank gets its own frames (frame-sharded, weak scaling): up to 1024 distinct frames per rank (8192 over 8 GPUs, the
-    # C5 sequence), repeated to fill the batch
-    n_distinct = min(B, 1024)
-    gray, depth = make_frames(n_distinct, start=rank * n_distinct)
     if n_distinct < B:
         reps = (B + n_distinct - 1) // n_distinct
         gray = np.concatenate([gray] * reps)[:B]
@@ -246,6 +250,15 @@ def main():
     d_out = {k: torch.empty(int(np.prod(sh)) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, (sh, dt) in shapes.items()}
     d_ptrs = {k: v.data_ptr() for k, v in d_out.items()}
     torch.cuda.synchronize()
+
+    def teardown():
+        # leave the device idle and release everything in a fixed order (handles before the process group)
+        torch.cuda.synchronize()
+        fe.close()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
 
     def step_device():
         fe.extract_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), B, d_ptrs)
@@ -290,6 +303,7 @@ def main():
     if args.device_only:
         emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
               'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means})
+        teardown()
         return
 
     roofline = None
@@ -418,6 +432,7 @@ def main():
     if args.e2e_only:
         if rank == 0:
             emit({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'lanes': fe.lanes, 'chunk': fe.chunk})
+        teardown()
         return
     # ---- single-frame latency through the host call (p50) ----
     fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
@@ -449,8 +464,7 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step, 'clocks': clk, 'p50_latency_ms_single_frame': p50,
         })
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == '__main__':
