@@ -284,7 +284,8 @@ def main():
         step_device()
     fe.sync()
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:  # one sampler per job (rank 0's GPU): N concurrent nvidia-smi loops would only load the driver
+        clocks.start()
     time.sleep(0.25)
     barrier()
     t0 = time.time()
