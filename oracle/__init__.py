@@ -480,6 +480,44 @@ def eig33sym(K):
     return s, V
 
 
+def ref_bin(name):
+    """Path of a binary built from the reference's own sources (oracle/_ref/<name>), or None."""
+    p = os.path.join(_HERE, '_ref', name)
+    return p if os.path.exists(p) else None
+
+
+def ref_peac(depth_frames, factor, fx, fy, cx, cy, perturb=None):
+    """Run the reference's own PlaneExtractor.cpp + include/peac/*.hpp (oracle/_ref/ref_peac) on [n,h,w] uint16 frames.
+    Returns a list of dicts: blocks [nb,10] (N, nouse, center, normal, mse, curvature), planes [np,9] (N, nvertices, normal,
+    center, mse), membership [h*w] int32.  None when the binary is not available.  perturb: eigen-solver perturbation
+    (ref_peac_perturb build)."""
+    exe = ref_bin('ref_peac_perturb' if perturb is not None else 'ref_peac')
+    if exe is None:
+        return None
+    d = np.ascontiguousarray(depth_frames, np.uint16)
+    n, h, w = d.shape
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('<4i', 0x50454143, w, h, n))
+            f.write(np.array([fx, fy, cx, cy, factor], np.float32).tobytes())
+            f.write(d.tobytes())
+        subprocess.check_call([exe, fi, fo] + ([repr(float(perturb))] if perturb is not None else []))
+        raw = open(fo, 'rb').read()
+    out, off = [], 0
+    bdt = np.dtype([('N', '<i4'), ('nouse', '<i4'), ('center', '<f8', (3,)), ('normal', '<f8', (3,)), ('mse', '<f8'), ('curvature', '<f8')])
+    pdt = np.dtype([('N', '<i4'), ('nvertices', '<i4'), ('normal', '<f8', (3,)), ('center', '<f8', (3,)), ('mse', '<f8')])
+    for _ in range(n):
+        (nb,) = struct.unpack_from('<i', raw, off); off += 4
+        blocks = np.frombuffer(raw, bdt, nb, off).copy(); off += bdt.itemsize * nb
+        (npl,) = struct.unpack_from('<i', raw, off); off += 4
+        planes = np.frombuffer(raw, pdt, npl, off).copy(); off += pdt.itemsize * npl
+        mem = np.frombuffer(raw, np.int32, h * w, off).copy(); off += 4 * h * w
+        out.append(dict(blocks=blocks, planes=planes, membership=mem))
+    assert off == len(raw)
+    return out
+
+
 # ---- surface normals (PCL integral-image style, Frame.cc:2155-2212) -------------------------------------------
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)

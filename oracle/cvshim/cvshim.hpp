@@ -15,15 +15,26 @@
 
 typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
+// OpenCV's type code: depth in the low 3 bits, (channels - 1) << 3 above
 #define CV_8U 0
-#define CV_8UC1 0
+#define CV_8S 1
 #define CV_16U 2
-#define CV_16UC1 2
+#define CV_16S 3
+#define CV_32S 4
 #define CV_32F 5
-#define CV_32FC1 5
 #define CV_64F 6
-#define CV_64FC1 6
-static inline size_t cvshim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_32F ? 4 : 8)); }
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
+#define CV_16SC1 CV_MAKETYPE(CV_16S, 1)
+#define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+static inline size_t cvshim_elem_size(int type) {
+    static const size_t depth_bytes[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+    return depth_bytes[type & 7] * (size_t)((type >> 3) + 1);
+}
 
 static inline int cvRound(double v) { return cvp::cv_round(v); }
 static inline int cvRound(float v) { return cvp::cv_round(v); }
@@ -64,6 +75,30 @@ struct Rect {
     Rect(int _x, int _y, int w, int h) : x(_x), y(_y), width(w), height(h) {}
 };
 
+struct Range {
+    int start, end;
+    Range(int s, int e) : start(s), end(e) {}
+};
+template <typename T, int N>
+struct Vec {
+    T val[N];
+    Vec() { for (int i = 0; i < N; ++i) val[i] = T(0); }
+    explicit Vec(const T* p) { for (int i = 0; i < N; ++i) val[i] = p[i]; }
+    Vec(T a, T b) { static_assert(N == 2, "Vec2"); val[0] = a; val[1] = b; }
+    Vec(T a, T b, T c) { static_assert(N == 3, "Vec3"); val[0] = a; val[1] = b; val[2] = c; }
+    T& operator[](int i) { return val[i]; }
+    const T& operator[](int i) const { return val[i]; }
+};
+typedef Vec<uchar, 3> Vec3b;
+typedef Vec<double, 2> Vec2d;
+typedef Vec<float, 4> Vec4f;
+struct Scalar {
+    double val[4];
+    Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+};
+static inline long long getTickCount() { return 0; }
+static inline double getTickFrequency() { return 1.0; }
+
 struct KeyPoint {
     Point2f pt;
     float size, angle, response;
@@ -82,6 +117,7 @@ struct MatStep {
 };
 
 struct MatZerosExpr { int rows, cols, type; };
+struct MatOnesExpr { int rows, cols, type; };
 
 class Mat {
 public:
@@ -111,6 +147,35 @@ public:
         return *this;
     }
     static MatZerosExpr zeros(int r, int c, int type) { return MatZerosExpr{r, c, type}; }
+    static MatOnesExpr ones(int r, int c, int type) { return MatOnesExpr{r, c, type}; }
+    Mat& operator=(const MatOnesExpr& z) {  // 8U only (the one use: ahc::PlaneFitter::getGraph)
+        assert(z.type == CV_8UC1);
+        create(z.rows, z.cols, z.type);
+        for (int y = 0; y < rows; ++y) std::memset(data + (size_t)y * step.v, 1, (size_t)cols);
+        return *this;
+    }
+    Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
+    int depth() const { return type_ & 7; }
+    int channels() const { return (type_ >> 3) + 1; }
+    // setTo for the element types the reference writes: int labels / 8U masks, and Vec3b colours
+    Mat& setTo(int v) {
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                if (type_ == CV_32SC1) at<int>(y, x) = v;
+                else if (type_ == CV_8UC1) at<uchar>(y, x) = (uchar)v;
+                else { assert(!"cvshim: setTo(int) on an unsupported type"); }
+            }
+        return *this;
+    }
+    Mat& setTo(const Vec3b& v) {
+        assert(type_ == CV_8UC3);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) at<Vec3b>(y, x) = v;
+        return *this;
+    }
+    // linear element index of a continuous matrix (cv::Mat::at<T>(int i0))
+    template <typename T> T& at(int i) { return *(T*)(data + (size_t)(i / cols) * step.v + (size_t)(i % cols) * sizeof(T)); }
+    template <typename T> const T& at(int i) const { return *(const T*)(data + (size_t)(i / cols) * step.v + (size_t)(i % cols) * sizeof(T)); }
     Mat operator()(const Rect& r) const {
         Mat m(*this);
         m.data = data + (size_t)r.y * step.v + r.x * cvshim_elem_size(type_);

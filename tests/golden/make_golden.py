@@ -9,8 +9,12 @@ lpvo_cv2.npz   inputs + outputs of the two cv2 primitives inside Manhattan::comp
                cv2.integral (CV_32F -> CV_64F) and cv2.normalize of 3x1 double vectors
 lsd_cv2.npz    inputs + outputs of cv2.createLineSegmentDetector().detect (what LSDDetector_custom.cpp:149,158 calls) and of
                the two cv2 primitives inside it (GaussianBlur 7x7 sigma 0.75, resize 0.8 INTER_LINEAR_EXACT)
+peac_ref.npz   outputs of the reference's own plane extractor (src/PlaneExtractor.cpp + include/peac/*.hpp compiled unmodified
+               into oracle/_ref/ref_peac) on synthetic depth frames: initial 10x10 blocks, extracted planes, membership image.
+               Inputs are the seeded synth frames (cfg, index); a CRC of every input depth image is stored with them.
 """
 import os
+import zlib
 import sys
 
 import cv2
@@ -129,8 +133,37 @@ def lpvo():
     print('lpvo_cv2.npz written')
 
 
+PEAC_CASES = [('S1', 0), ('S1', 9), ('S2', 3), ('S3', 1)]
+
+
+def peac():
+    if oracle.ref_bin('ref_peac') is None:
+        print('oracle/_ref/ref_peac missing: run make -C oracle first')
+        return
+    out = dict(cases=np.array([f'{c}:{i}' for c, i in PEAC_CASES]))
+    for cfg, idx in PEAC_CASES:
+        c = synth.CONFIGS[cfg]
+        _, d = synth.frame(cfg, idx)
+        (r,) = oracle.ref_peac(d[None], np.float32(1.0 / c['factor']), c['fx'], c['fy'], c['cx'], c['cy'])
+        k = f'{cfg}_{idx}_'
+        out[k + 'depth_crc'] = np.uint32(zlib.crc32(d.tobytes()))
+        # block statistics: validity / N for every block, the double-precision fit for every 4th one (fixture size)
+        out[k + 'block_N'] = r['blocks']['N'].astype(np.int16)
+        out[k + 'block_nouse'] = r['blocks']['nouse'].astype(np.int8)
+        out[k + 'blocks_every4'] = r['blocks'][::4]
+        out[k + 'planes'] = r['planes']
+        # the reference leaves its visit counters (-2 .. -6) in unassigned pixels (AHCPlaneFitter.hpp:445, 468-472): consumers only
+        # read labels >= 0 (refineDetails :362-368), so the fixture keeps max(label, -1)
+        out[k + 'membership'] = np.maximum(r['membership'], -1).astype(np.int8).reshape(d.shape)
+        print(cfg, idx, len(r['planes']), r['planes']['N'])
+    np.savez_compressed(os.path.join(OUT, 'peac_ref.npz'), **out)
+    print('peac_ref.npz written')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac']
+    if 'peac' in which:
+        peac()
     if 'lpvo' in which:
         lpvo()
     if 'prims' in which:
