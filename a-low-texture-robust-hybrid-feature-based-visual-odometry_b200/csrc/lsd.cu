@@ -13,13 +13,14 @@
 //                   points; the `used` map is a bitmap in global memory (no shared memory: 32 frames per SM, and the
 //                   kernel co-resides with the other pipelines); sums over a region are warp reductions.
 //                   Frames are independent, so a batch fills the machine with one warp per frame.
-//   k_line_keylines one CTA per frame: KeyLine fields, rank by response (ties: detection order), keep nLSDFeature,
+//   k_line_keylines one CTA per frame: KeyLine fields, rank by response (ties: libstdc++'s std::sort order), keep nLSDFeature,
 //                   2-D line functions
 #include <algorithm>
 #include <cmath>
 #include <new>
 #include <vector>
 
+#include "std_sort.cuh"
 #include "hvo_common.cuh"
 
 struct hvo_lbd;
@@ -548,12 +549,31 @@ __global__ void __launch_bounds__(256) k_line_keylines(const float* __restrict__
     }
     const int nout = select ? nfeat : n;
     if (tid == 0) counts[f] = min(nout, max_lines);
+    // sort_lines_by_response (LineExtractor.cpp:351-360) is an unstable std::sort.  Without equal responses the result is the
+    // plain descending rank (computed in parallel); with ties the order is libstdc++'s, replayed by one thread (std_sort.cuh).
+    extern __shared__ uint16_t kl_sm[];   // [seg_cap] sorted index list, then [seg_cap] rank of every input line
+    uint16_t* sidx = kl_sm;
+    uint16_t* srank = kl_sm + seg_cap;
+    if (select) {
+        int tie = 0;
+        for (int i = tid; i < n; i += 256) {
+            const float r = R[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) { const float q = R[j]; rank += (q > r || (q == r && j < i)) ? 1 : 0; tie |= (q == r && j != i) ? 1 : 0; }
+            srank[i] = (uint16_t)rank;
+            sidx[i] = (uint16_t)i;
+        }
+        if (__syncthreads_or(tie)) {
+            if (tid == 0) stdsort::sort(sidx, n, [R](uint16_t a, uint16_t b) { return R[a] > R[b]; });
+            __syncthreads();
+            for (int k = tid; k < n; k += 256) srank[sidx[k]] = (uint16_t)k;
+            __syncthreads();
+        }
+    }
     for (int i = tid; i < n; i += 256) {
         int rank = i;
-        if (select) {  // sort_lines_by_response (LineExtractor.cpp:351-360): response descending; ties keep detection order
-            const float r = R[i];
-            rank = 0;
-            for (int j = 0; j < n; ++j) { const float q = R[j]; rank += (q > r || (q == r && j < i)) ? 1 : 0; }
+        if (select) {
+            rank = srank[i];
             if (rank >= nfeat) continue;
         }
         if (rank >= max_lines) continue;
@@ -606,9 +626,11 @@ __device__ __forceinline__ void cull_merge_two(const float l1[4], const float l2
     const double kPi = 3.1415926535897932384626433832795;
     double thi, thj, thr;
     if (dlix == 0.0f) thi = kPi / 2.0;
-    else thi = atan((double)__fdiv_rn(dliy, dlix));
+    // the reference's atan(float) binds to the float overload (Frame.cc:33 'using namespace std'): a float-precision angle.
+    // Here: the correctly rounded float (libm's atanf is within 1 ulp of it, not pinned by the reference).
+    else thi = (double)(float)atan((double)__fdiv_rn(dliy, dlix));
     if (dljx == 0.0f) thj = kPi / 2.0;
-    else thj = atan((double)__fdiv_rn(dljy, dljx));
+    else thj = (double)(float)atan((double)__fdiv_rn(dljy, dljx));
     if (fabs(thi - thj) <= kPi / 2.0) {
         thr = (li * thi + lj * thj) / (li + lj);
     } else {
@@ -680,7 +702,7 @@ __global__ void __launch_bounds__(32) k_line_cull(KeyLineOut* __restrict__ kls, 
                                                  CullLine* __restrict__ scratch, float* __restrict__ newline) {
     extern __shared__ int16_t cull_sm[];  // grp[max_lines] (leader of a merged line, -1 none), then tag bytes
     int16_t* grp = cull_sm;
-    uint8_t* tag = (uint8_t*)(cull_sm + max_lines);
+    uint8_t* tag = (uint8_t*)(cull_sm + 2 * max_lines);
     const int f = blockIdx.x, lane = threadIdx.x;
     const int n = min(counts[f], max_lines);
     KeyLineOut* K = kls + (long long)f * max_lines;
@@ -779,12 +801,31 @@ __global__ void __launch_bounds__(32) k_line_cull(KeyLineOut* __restrict__ kls, 
         nout += __popc(km);
     }
     __syncwarp();
-    // ---- step 3: KeyLines of the new segments at their response rank (descending, ties keep creation order) ----
+    // ---- step 3: KeyLines of the new segments at their response rank.  std::sort (Frame.cc:1087) is unstable: without equal
+    //      responses the order is the plain descending rank; with ties it is libstdc++'s, replayed by one lane (std_sort.cuh) ----
+    uint16_t* sidx = (uint16_t*)grp;                       // the group leaders are dead here: [max_lines] sorted index list
+    uint16_t* srank = sidx + max_lines;                    // [max_lines] rank of every new line
+    {
+        int tie = 0;
+        for (int i = lane; i < nout; i += 32) {
+            const float r = NL[5 * i + 4];
+            int rank = 0;
+            for (int j = 0; j < nout; ++j) { const float q = NL[5 * j + 4]; rank += (q > r || (q == r && j < i)) ? 1 : 0; tie |= (q == r && j != i) ? 1 : 0; }
+            srank[i] = (uint16_t)rank;
+            sidx[i] = (uint16_t)i;
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, tie)) {
+            if (lane == 0) stdsort::sort(sidx, nout, [NL](uint16_t a, uint16_t b) { return NL[5 * a + 4] > NL[5 * b + 4]; });
+            __syncwarp();
+            for (int k = lane; k < nout; k += 32) srank[sidx[k]] = (uint16_t)k;
+            __syncwarp();
+        }
+    }
     for (int i = lane; i < nout; i += 32) {
         const float e[4] = {NL[5 * i], NL[5 * i + 1], NL[5 * i + 2], NL[5 * i + 3]};
         const float r = NL[5 * i + 4];
-        int rank = 0;
-        for (int j = 0; j < nout; ++j) { const float q = NL[5 * j + 4]; rank += (q > r || (q == r && j < i)) ? 1 : 0; }
+        const int rank = srank[i];
         KeyLineOut kl;
         kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];
         kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
@@ -900,7 +941,7 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
 // Frame::cullingLine(im, 5, 2.5, 15, 30) (src/Frame.cc:939) on device-resident KeyLines, in place, then LBD on the result
 static int line_cull_device(hvo_line* h, const uint8_t* d_gray, int nframes, KeyLineOut* d_kl, uint8_t* d_desc, double* d_linevec,
                             int32_t* d_counts) {
-    const size_t sm = (size_t)h->nfeat * 3 + 16;
+    const size_t sm = (size_t)h->nfeat * 5 + 16;   // grp int16 (reused as the sorted index list), rank u16, tag bytes
     timeline_mark(h->stream, "k_line_cull");
     k_line_cull<<<nframes, 32, sm, h->stream>>>(d_kl, d_linevec, d_counts, h->nfeat, h->width, h->height, 5.0, std::cos(2.5 * 0.0174533),
                                                 15.0, h->d_cull, h->d_newline);
@@ -913,7 +954,7 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
     int st = line_detect_device(h, d_gray, nframes);
     if (st != HVO_OK) return st;
     timeline_mark(h->stream, "k_line_keylines");
-    k_line_keylines<<<nframes, 256, 0, h->stream>>>(h->d_seg, h->seg_cap, h->d_nseg, h->width, h->height, h->nfeat, h->nfeat, h->d_resp,
+    k_line_keylines<<<nframes, 256, (size_t)h->seg_cap * 4, h->stream>>>(h->d_seg, h->seg_cap, h->d_nseg, h->width, h->height, h->nfeat, h->nfeat, h->d_resp,
                                                     d_kl, d_linevec, d_counts);
     HVO_CUDA(cudaGetLastError());
     if (h->cull) {
@@ -1014,6 +1055,15 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
         HVO_TRY(cudaMemcpy(h->d_cy, cy.data(), cy.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
         HVO_TRY(cudaMemcpy(h->d_cstab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
         HVO_TRY(cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrdWarps * kBins * (int)sizeof(uint32_t)));
+        {   // k_line_keylines keeps two u16 per possible segment; the attribute is per function: only ever raise it
+            static size_t s_kl_smem_max[64] = {0};
+            const size_t want = std::max<size_t>((size_t)h->seg_cap * 4, 48 * 1024);
+            if (want > 200 * 1024 || h->seg_cap > 65535) { set_error("image too large for the KeyLine kernel"); st = HVO_ERR_ARG; break; }
+            if (device < 64 && want > s_kl_smem_max[device]) {
+                HVO_TRY(cudaFuncSetAttribute(k_line_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+                s_kl_smem_max[device] = want;
+            }
+        }
 #undef HVO_TRY
     } while (0);
     if (st == HVO_OK) st = hvo_lbd_create(width, height, max_batch, h->nfeat, device, &h->lbd);

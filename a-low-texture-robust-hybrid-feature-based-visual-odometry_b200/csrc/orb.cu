@@ -2,7 +2,7 @@
 //
 //   k_resize      x(nlevels-1)  fixed-point bilinear pyramid, bit-exact with cv::resize INTER_LINEAR 8U
 //                               (reference ORBextractor.cc:1105-1130)
-//   k_fast_cells  x1            one CTA per reference FAST cell: FAST-9/16 strength, cell-local NMS,
+//   k_fast_strips x1            one CTA per row of reference FAST cells: FAST-9/16 strength, cell-local NMS,
 //                               per-cell threshold fallback (ORBextractor.cc:763-826) - no score map in HBM
 //   k_octree      x1            one CTA per (frame, level): DistributeOctTree (ORBextractor.cc:537-761)
 //                               with parallel key partitioning and the std::list order emulated exactly
@@ -32,7 +32,8 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 static const int h_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 static const int kEdge = 19;
-static const int kMaxCell = 64;  // wCell = ceil(width / floor(width/30)) <= 60
+static const int kFastMaxZh = 64;    // hCell = ceil(height / floor(height/30)) <= 60
+static const int kFastMaxZone = 672; // widest run of cells one strip CTA takes (px)
 
 __device__ __forceinline__ const uint8_t* level_ptr(const OrbGeom& g, const ImgSrc& s, int l, int f, int& pitch) {
     if (l == 0) {
@@ -141,15 +142,23 @@ __device__ __forceinline__ int fast_strength(const int (&d)[16]) {
      : (k) == 11 ? (p)[-(st) - 3] : (k) == 12 ? (p)[-3] : (k) == 13 ? (p)[(st) - 3] : (k) == 14 ? (p)[2 * (st) - 2]    \
                                                                                                 : (p)[3 * (st) - 1])
 
-#ifndef HVO_FAST_THREADS
-#define HVO_FAST_THREADS 128
-#endif
-static const int kFastThreads = HVO_FAST_THREADS, kFastWarps = kFastThreads / 32;
-static const int kTW = 20;                 // tile row stride in 32-bit words: (60 + 6 + 3 alignment) bytes <= 72
-static const int kTileBytes = kTW * 4;     // 80
+// One CTA per STRIP = one row of reference FAST cells of one level of one frame (the zones of a cell row tile the level
+// without gaps: cell ROI = zone + 3-px ring, ORBextractor.cc:787-803).  The FAST strength of a pixel depends on the image
+// only; what is cell-local is (a) non-max suppression (neighbours outside the cell's zone count as 0) and (b) the
+// threshold fallback (ORBextractor.cc:807-814).  So the strip is processed as one image band:
+//   fill     the band (zone rows + 3-px ring) goes to shared memory as one bulk copy per row (cp.async.bulk + mbarrier:
+//            the copy engine moves the bytes, no LDG/STS issue slots), while the threads clear the score map
+//   pass 1   quick reject, 4 pixels per thread on packed bytes; survivors go to a warp-private queue
+//   pass 2   exact threshold-independent strength for queued survivors, 32 at a time (dense warps), no CTA barrier
+//   pass 3   NMS over the score map (word-wise skip of empty groups), cell-aware; maxima -> list (reuses the band's memory)
+//   emit     per-cell ini/min decision, one global atomic per strip
+static const int kFastThreads = 256, kFastWarps = kFastThreads / 32;
+static const int kFastQueue = 256;   // per-warp survivor queue (entries; >= 31 + 128)
+static const int kFastMaxCellsPerStrip = 64;
 
-// Packed 4-pixel FAST ring compare.  `lo`/`hi` are two consecutive tile words of one row; returns the 4 ring
-// bytes seen by the 4 pixels of the group at horizontal offset dx (-3..3).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Packed 4-pixel FAST ring compare: the 4 ring bytes seen by the 4 pixels of word g at horizontal offset dx (-3..3).
 __device__ __forceinline__ uint32_t ring4(const uint32_t* row, int g, int dx) {
     switch (dx) {
         case 0: return row[g];
@@ -162,144 +171,211 @@ __device__ __forceinline__ uint32_t ring4(const uint32_t* row, int g, int dx) {
     }
 }
 
-__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_constant__ OrbGeom g, ImgSrc src,
-                                                    const CellDesc* __restrict__ cells, uint32_t* __restrict__ cand,
-                                                    int* __restrict__ ncand, int ini_th, int min_th) {
-    // tile words are stored from index 1 so that group g may read word g-1 (content unused when g == 0)
-    __shared__ uint32_t tile_w[1 + (kMaxCell + 6) * kTW + 2];
-    __shared__ uint8_t score[kMaxCell * kMaxCell];
-    __shared__ uint16_t clist[kMaxCell * kMaxCell];
-    __shared__ int s_ncorner, s_nini, s_nmin, s_base, s_slot;
+__global__ void __launch_bounds__(kFastThreads) k_fast_strips(const __grid_constant__ OrbGeom g, ImgSrc src,
+                                                              const StripDesc* __restrict__ strips, uint32_t* __restrict__ cand,
+                                                              int* __restrict__ ncand, int ini_th, int min_th) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_queue[kFastWarps][kFastQueue];
+    __shared__ int s_nini[kFastMaxCellsPerStrip], s_nmin[kFastMaxCellsPerStrip];
+    __shared__ int s_nlist, s_base, s_slot, s_total;
 
-    const CellDesc c = cells[blockIdx.x];
+    const StripDesc c = strips[blockIdx.x];
     const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const LevelGeom& L = g.lv[c.level];
     int pitch;
     const uint8_t* img = level_ptr(g, src, c.level, f, pitch);
-    const int zw = c.zw, zh = c.zh, tw = zw + 6, th = zh + 6;
+    const int zh = c.zh, zw = c.zw, th = zh + 6;
     const int low_th = min(ini_th, min_th);
-    uint32_t* tile = tile_w + 1;
 
-    // ---- tile (zone + 3-px ring) -> shared memory, as aligned 32-bit words ----
-    const int tx0 = c.x0 - 3, ty0 = c.y0 - 3;
-    const int xal = tx0 & ~3;              // word-aligned tile origin (>= 12: the search window starts at x = 16)
-    const int sh = tx0 - xal;              // 0..3
-    const int nw = (sh + tw + 3) >> 2;     // words per tile row (all inside the image row: x < w - 13)
-    const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
-    if (aligned) {
-        // all row loads of a warp are issued before the first store: <= 9 independent 128-bit-coalesced requests in flight
-        for (int rb = 0; rb < th; rb += 9 * kFastWarps) {
-            uint32_t w[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int r = rb + warp + kFastWarps * k;
-                if (r < th && lane < nw) w[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)(ty0 + r) * pitch + xal + 4 * lane));
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int r = rb + warp + kFastWarps * k;
-                if (r < th && lane < nw) tile[r * kTW + lane] = w[k];
+    // band geometry: tile column 0 = image column xal (16-byte aligned), zone starts at tile byte zb0
+    const int xal = (c.x0 - 3) & ~15;
+    const int zb0 = c.x0 - xal;                       // >= 3
+    const int ts = c.tstride;                         // bytes per band row, multiple of 16
+    const int tsw = ts >> 2;
+    unsigned char* tile_b = fs_smem + 16;             // word -1 of row 0 must be addressable (content unused)
+    uint32_t* tile = reinterpret_cast<uint32_t*>(tile_b);
+    unsigned char* score = tile_b + c.score_off;      // (zh + 2) rows of ts bytes; row 0 and row zh+1 stay 0
+    uint32_t* list = tile;                            // NMS maxima, written after the band is dead
+
+    // ---- fill ----
+    const bool bulk = ((pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    if (tid == 0) {
+        s_nlist = 0; s_slot = 0;
+        if (bulk) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (tid < kFastMaxCellsPerStrip) { s_nini[tid] = 0; s_nmin[tid] = 0; }
+    __syncthreads();
+    if (bulk) {
+        if (warp == 0) {
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_bar)), "r"(th * ts) : "memory");
+            __syncwarp();
+            for (int r = lane; r < th; r += 32) {
+                const uint8_t* gp = img + (long long)(c.y0 - 3 + r) * pitch + xal;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_addr(tile_b + r * ts)),
+                             "l"(gp), "r"(ts), "r"(smem_addr(&s_bar))
+                             : "memory");
             }
         }
     } else {
-        for (int r = warp; r < th; r += kFastWarps) {
-            if (lane < nw) {
-                const uint8_t* p = img + (long long)(ty0 + r) * pitch + xal + 4 * lane;
-                tile[r * kTW + lane] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
-            }
+        const int lim = L.w - 1 - xal;
+        for (int i = tid; i < th * tsw; i += kFastThreads) {
+            const int r = i / tsw, wi = i - r * tsw;
+            const uint8_t* p = img + (long long)(c.y0 - 3 + r) * pitch + xal;
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w |= (uint32_t)__ldg(p + min(4 * wi + j, lim)) << (8 * j);
+            tile[r * tsw + wi] = w;
         }
     }
-    for (int i = tid; i < zh * (kMaxCell / 4); i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
-    if (tid == 0) { s_ncorner = 0; s_nini = 0; s_nmin = 0; s_slot = 0; }
+    {   // clear the score map while the copy engine works
+        uint4* sc4 = reinterpret_cast<uint4*>(score);
+        const int n16 = ((zh + 2) * ts) >> 4;
+        for (int i = tid; i < n16; i += kFastThreads) sc4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (bulk) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_addr(&s_bar)) : "memory");
+    }
     __syncthreads();
 
-    // ---- pass 1: quick reject, 4 pixels per thread.  A 9-arc always contains ring point 0 or 8 and ring point
-    //      4 or 12, so a corner needs |v - ring| > t on one point of each pair.  VABSDIFF4 is a native
-    //      instruction; "byte > t" is the carry trick ((x & 0x7f) + (127 - t)) | x.  Survivors (~5 % of the pixels)
-    //      are compacted into a list so that the expensive part below runs on dense warps. ----
-    const int zb0 = sh + 3;                          // tile byte column of the first zone pixel
+    // ---- pass 1 + 2 ----
+    // A 9-arc always contains ring point 0 or 8 and ring point 4 or 12, so a corner needs |v - ring| > t on one point of each
+    // pair.  VABSDIFF4 is native; "byte > t" is the carry trick ((x & 0x7f) + (127 - t)) | x.
     const int g0 = zb0 >> 2, g1 = (zb0 + zw - 1) >> 2, ng = g1 - g0 + 1;
-    const uint32_t magic = (65536u + ng - 1) / ng;  // i / ng for i < 4096
+    const uint32_t magic = (1u << 20) / (uint32_t)ng + 1;  // i / ng for i < 2^15 (ng <= 1024)
     const bool use_quick = low_th <= 127;
     const uint32_t K = (uint32_t)(127 - min(low_th, 127)) * 0x01010101u;
-    for (int i = tid; i < ng * zh; i += kFastThreads) {
-        int zy = (int)(((uint32_t)i * magic) >> 16);
-        if (zy * ng > i) --zy;
-        const int gi = g0 + (i - zy * ng);
-        const uint32_t* r0 = tile + (zy + 3) * kTW;
-        const uint32_t v4 = r0[gi];
-        uint32_t zmask = 0x80808080u;
-        const int b0 = 4 * gi;
-        if (b0 < zb0) zmask &= 0xffffffffu << (8 * (zb0 - b0));
-        if (b0 + 3 > zb0 + zw - 1) zmask &= 0xffffffffu >> (8 * (b0 + 3 - (zb0 + zw - 1)));
-        uint32_t maybe = zmask;
-        if (use_quick) {
-            const uint32_t a0 = __vabsdiffu4(v4, (tile + (zy + 6) * kTW)[gi]), a8 = __vabsdiffu4(v4, (tile + zy * kTW)[gi]);
-            const uint32_t a4 = __vabsdiffu4(v4, ring4(r0, gi, 3)), a12 = __vabsdiffu4(v4, ring4(r0, gi, -3));
-            const uint32_t m08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
-            const uint32_t m412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
-            maybe &= m08 & m412;
+    uint32_t* q = s_queue[warp];
+    int qh = 0, qn = 0;                                  // warp-uniform queue head / tail (monotonic)
+    const int ntot = ng * zh;
+    for (int ib = warp * 32; ib < ntot; ib += kFastThreads) {
+        const int i = ib + lane;
+        uint32_t maybe = 0;
+        int zy = 0, b0 = 0;
+        if (i < ntot) {
+            zy = (int)(((unsigned long long)(uint32_t)i * magic) >> 20);
+            if (zy * ng > i) --zy;
+            const int gi = g0 + (i - zy * ng);
+            const uint32_t* r0 = tile + (zy + 3) * tsw;
+            const uint32_t v4 = r0[gi];
+            b0 = 4 * gi;
+            maybe = 0x80808080u;
+            if (b0 < zb0) maybe &= 0xffffffffu << (8 * (zb0 - b0));
+            if (b0 + 3 > zb0 + zw - 1) maybe &= 0xffffffffu >> (8 * (b0 + 3 - (zb0 + zw - 1)));
+            if (use_quick) {
+                const uint32_t a0 = __vabsdiffu4(v4, (r0 + 3 * tsw)[gi]), a8 = __vabsdiffu4(v4, (r0 - 3 * tsw)[gi]);
+                const uint32_t a4 = __vabsdiffu4(v4, ring4(r0, gi, 3)), a12 = __vabsdiffu4(v4, ring4(r0, gi, -3));
+                const uint32_t m08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
+                const uint32_t m412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
+                maybe &= m08 & m412;
+            }
         }
+        // warp-private compaction of the survivors
+        const int cnt = __popc(maybe);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int slot = qn + incl - cnt;
         while (maybe) {
             const int j = (__ffs(maybe) - 1) >> 3;
             maybe &= maybe - 1;
-            clist[atomicAdd(&s_ncorner, 1)] = (uint16_t)(zy * kMaxCell + (b0 + j - zb0));
+            q[slot & (kFastQueue - 1)] = ((uint32_t)zy << 16) | (uint32_t)(b0 + j);
+            ++slot;
         }
+        qn += total;
+        __syncwarp();
+        while (qn - qh >= 32) {
+            const uint32_t pos = q[(qh + lane) & (kFastQueue - 1)];
+            const int py = pos >> 16, px = pos & 0xffff;
+            const uint8_t* p = tile_b + (py + 3) * ts + px;
+            const int v = *p;
+            int d[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, ts, k);
+            const int sc = fast_strength(d);
+            if (sc >= low_th) score[(py + 1) * ts + px] = (uint8_t)sc;   // in [low_th, 254]; non-corners stay 0
+            qh += 32;
+        }
+        __syncwarp();
     }
-    __syncthreads();
-
-    // ---- pass 2: exact threshold-independent strength for the survivors; corner at t  <=>  S >= t ----
-    const uint8_t* tile_b = reinterpret_cast<const uint8_t*>(tile);
-    const int ncorner = s_ncorner;
-    for (int i = tid; i < ncorner; i += kFastThreads) {
-        const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
-        const uint8_t* p = tile_b + (zy + 3) * kTileBytes + zb0 + zx;
+    if (lane < qn - qh) {
+        const uint32_t pos = q[(qh + lane) & (kFastQueue - 1)];
+        const int py = pos >> 16, px = pos & 0xffff;
+        const uint8_t* p = tile_b + (py + 3) * ts + px;
         const int v = *p;
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, kTileBytes, k);
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, ts, k);
         const int sc = fast_strength(d);
-        if (sc >= low_th) score[pos] = (uint8_t)sc;  // in [low_th, 254]; non-corners stay 0
+        if (sc >= low_th) score[(py + 1) * ts + px] = (uint8_t)sc;
     }
     __syncthreads();
 
-    // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the zone counts as 0) ----
-    uint32_t f_ini = 0, f_min = 0;
-    for (int i = tid, it = 0; i < ncorner; i += kFastThreads, ++it) {
-        const int pos = clist[i], zy = pos / kMaxCell, zx = pos % kMaxCell;
-        const int s = score[pos];
-        bool is_max = s > 0;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0) continue;
-                const int yy = zy + dy, xx = zx + dx;
-                if (yy >= 0 && yy < zh && xx >= 0 && xx < zw) is_max = is_max && (s > (int)score[yy * kMaxCell + xx]);
+    // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the cell's zone counts as 0) ----
+    const int wcell = c.wcell;
+    const uint32_t cmagic = (1u << 20) / (uint32_t)wcell + 1;   // zx / wcell for zx < 2^12
+    const uint32_t* score_w = reinterpret_cast<const uint32_t*>(score);
+    for (int i = tid; i < ntot; i += kFastThreads) {
+        int zy = (int)(((unsigned long long)(uint32_t)i * magic) >> 20);
+        if (zy * ng > i) --zy;
+        const int gi = g0 + (i - zy * ng);
+        uint32_t w = score_w[(zy + 1) * tsw + gi];
+        while (w) {
+            const int j = (__ffs(w) - 1) >> 3;
+            const int s = (w >> (8 * j)) & 0xff;
+            w &= ~(0xffu << (8 * j));
+            const int px = 4 * gi + j, zx = px - zb0;
+            int cj = (int)(((uint32_t)zx * cmagic) >> 20);
+            if (cj * wcell > zx) --cj;
+            const int cx = zx - cj * wcell;
+            const bool has_l = cx > 0, has_r = cx < wcell - 1 && zx < zw - 1;
+            const uint8_t* sp = score + (zy + 1) * ts + px;
+            bool is_max = s > (int)sp[-ts] && s > (int)sp[ts];
+            if (has_l) is_max = is_max && s > (int)sp[-ts - 1] && s > (int)sp[-1] && s > (int)sp[ts - 1];
+            if (has_r) is_max = is_max && s > (int)sp[-ts + 1] && s > (int)sp[1] && s > (int)sp[ts + 1];
+            if (is_max) {
+                if (s >= ini_th) atomicAdd(&s_nini[cj], 1);
+                if (s >= min_th) atomicAdd(&s_nmin[cj], 1);
+                list[atomicAdd(&s_nlist, 1)] = (uint32_t)(c.x0 + zx) | ((uint32_t)(c.y0 + zy) << 12) | ((uint32_t)s << 24);
             }
-        if (is_max) {
-            if (s >= ini_th) f_ini |= 1u << it;
-            if (s >= min_th) f_min |= 1u << it;
         }
     }
-    if (f_ini) atomicAdd(&s_nini, __popc(f_ini));
-    if (f_min) atomicAdd(&s_nmin, __popc(f_min));
     __syncthreads();
-    const bool use_ini = s_nini > 0;
-    const int n = use_ini ? s_nini : s_nmin;
-    if (n == 0) return;
-    if (tid == 0) s_base = atomicAdd(&ncand[f * g.nlevels + c.level], n);
+
+    // ---- emit: a cell that has a corner at ini_th keeps those, else the ones at min_th ----
+    if (tid == 0) {
+        int n = 0;
+        for (int j = 0; j < c.ncells; ++j) n += s_nini[j] > 0 ? s_nini[j] : s_nmin[j];
+        s_total = n;
+        s_base = n > 0 ? atomicAdd(&ncand[f * g.nlevels + c.level], n) : 0;
+    }
     __syncthreads();
-    uint32_t m = use_ini ? f_ini : f_min;
+    if (s_total == 0) return;
     uint32_t* out = cand + (long long)f * g.cand_total + L.cand_off + s_base;
-    while (m) {
-        const int it = __ffs(m) - 1;
-        m &= m - 1;
-        const int pos = clist[tid + kFastThreads * it];
-        const int zy = pos / kMaxCell, zx = pos % kMaxCell;
-        const int slot = atomicAdd(&s_slot, 1);
-        if (s_base + slot < L.cand_cap)
-            out[slot] = (uint32_t)(c.x0 + zx) | ((uint32_t)(c.y0 + zy) << 12) | ((uint32_t)score[pos] << 24);
+    const int nlist = s_nlist;
+    for (int i = tid; i < nlist; i += kFastThreads) {
+        const uint32_t e = list[i];
+        const int zx = (int)(e & 0xfff) - c.x0, s = (int)(e >> 24);
+        int cj = (int)(((uint32_t)zx * cmagic) >> 20);
+        if (cj * wcell > zx) --cj;
+        const bool keep = s_nini[cj] > 0 ? s >= ini_th : s >= min_th;
+        if (keep) {
+            const int slot = atomicAdd(&s_slot, 1);
+            if (s_base + slot < L.cand_cap) out[slot] = e;
+        }
     }
 }
 
@@ -777,8 +853,9 @@ int hvo_orb::init() {
     long long off = 0, boff = 0;
     int cand_off = 0, kp_off = 0;
     std::vector<TileDesc> btiles;
-    std::vector<CellDesc> cells;
-    max_zw = max_zh = max_quota = 0;
+    std::vector<StripDesc> strips;
+    fast_smem = 0;
+    max_quota = 0;
     for (int l = 0; l < n; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)width * isf[l]);
@@ -807,25 +884,45 @@ int hvo_orb::init() {
         L.wCell = (int)std::ceil(fw / L.nCols); L.hCell = (int)std::ceil(fh / L.nRows);
         L.nIni = (int)std::round((float)(L.maxBX - L.minBX) / (L.maxBY - L.minBY));
         L.hX = L.nIni > 0 ? (float)(L.maxBX - L.minBX) / L.nIni : 1.f;
+        const int max_seg_cells = std::max(1, kFastMaxZone / L.wCell);   // a strip = a run of cells of one cell row
         for (int i = 0; i < L.nRows; ++i) {
             const float iniY = (float)(L.minBY + i * L.hCell);
             float maxY = iniY + L.hCell + 6;
             if (iniY >= L.maxBY - 3) continue;
             if (maxY > L.maxBY) maxY = (float)L.maxBY;
+            const int zh = (int)maxY - (int)iniY - 6;
+            if (zh <= 0) continue;
+            if (zh > kFastMaxZh) { set_error("internal: FAST cell higher than %d", kFastMaxZh); return HVO_ERR_ARG; }
+            StripDesc st;
+            std::memset(&st, 0, sizeof(st));
+            int listcap = 0;
+            auto flush = [&]() {
+                if (st.ncells == 0) return;
+                const int xal = (st.x0 - 3) & ~15, zb0 = st.x0 - xal;
+                st.tstride = (short)align_up((size_t)(zb0 + st.zw + 8), 16);
+                st.score_off = (int)align_up(std::max<size_t>((size_t)(zh + 6) * st.tstride, (size_t)listcap * 4), 16);
+                fast_smem = std::max(fast_smem, (size_t)16 + st.score_off + (size_t)(zh + 2) * st.tstride);
+                strips.push_back(st);
+                std::memset(&st, 0, sizeof(st));
+                listcap = 0;
+            };
             for (int j = 0; j < L.nCols; ++j) {
                 const float iniX = (float)(L.minBX + j * L.wCell);
                 float maxX = iniX + L.wCell + 6;
                 if (iniX >= L.maxBX - 6) continue;
                 if (maxX > L.maxBX) maxX = (float)L.maxBX;
-                CellDesc c;
-                c.level = (short)l; c.x0 = (short)((int)iniX + 3); c.y0 = (short)((int)iniY + 3);
-                c.zw = (short)((int)maxX - (int)iniX - 6); c.zh = (short)((int)maxY - (int)iniY - 6); c.pad = 0;
-                if (c.zw <= 0 || c.zh <= 0) continue;
-                if (c.zw > kMaxCell || c.zh > kMaxCell) { set_error("internal: FAST cell larger than %d", kMaxCell); return HVO_ERR_ARG; }
-                max_zw = std::max(max_zw, (int)c.zw); max_zh = std::max(max_zh, (int)c.zh);
-                L.cand_cap += ((c.zw + 1) / 2) * ((c.zh + 1) / 2);  // NMS survivors are never 8-adjacent
-                cells.push_back(c);
+                const int zw = (int)maxX - (int)iniX - 6;
+                if (zw <= 0) continue;
+                if (st.ncells == 0) {
+                    st.level = (short)l; st.x0 = (short)((int)iniX + 3); st.y0 = (short)((int)iniY + 3); st.zh = (short)zh;
+                    st.wcell = (short)L.wCell;
+                }
+                st.zw += (short)zw; st.ncells += 1;
+                const int nms_cap = ((zw + 1) / 2) * ((zh + 1) / 2);  // NMS survivors are never 8-adjacent
+                L.cand_cap += nms_cap; listcap += nms_cap;
+                if (st.ncells == max_seg_cells) flush();
             }
+            flush();
         }
         cand_off += L.cand_cap;
     }
@@ -836,11 +933,11 @@ int hvo_orb::init() {
     g.cand_total = std::max(cand_off, 1);
     g.kp_total = kp_off;
     g.out_cap = kp_off;
-    ncells = (int)cells.size();
+    nstrips = (int)strips.size();
 
     // ---- CUDA resources ----
     HVO_CUDA(cudaSetDevice(device));
-    pin_carveout(k_resize); pin_carveout(k_fast_cells); pin_carveout(k_octree); pin_carveout(k_blur); pin_carveout(k_describe);
+    pin_carveout(k_resize); pin_carveout(k_fast_strips); pin_carveout(k_octree); pin_carveout(k_blur); pin_carveout(k_describe);
     HVO_CUDA(create_stream(&stream));
     for (auto& e : ev) HVO_CUDA(cudaEventCreate(&e));
     for (auto& e : tev) HVO_CUDA(cudaEventCreate(&e));
@@ -856,8 +953,16 @@ int hvo_orb::init() {
     HVO_CUDA(cudaMalloc(&d_on, B * n * sizeof(int)));
     HVO_CUDA(cudaMalloc(&d_err, sizeof(int)));
     HVO_CUDA(cudaMemset(d_err, 0, sizeof(int)));
-    HVO_CUDA(cudaMalloc(&d_cells, std::max<size_t>(cells.size(), 1) * sizeof(CellDesc)));
-    if (!cells.empty()) HVO_CUDA(cudaMemcpy(d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    HVO_CUDA(cudaMalloc(&d_strips, std::max<size_t>(strips.size(), 1) * sizeof(StripDesc)));
+    if (!strips.empty()) HVO_CUDA(cudaMemcpy(d_strips, strips.data(), strips.size() * sizeof(StripDesc), cudaMemcpyHostToDevice));
+    if (fast_smem > 200 * 1024) { set_error("internal: FAST strip needs %zu bytes of shared memory", fast_smem); return HVO_ERR_ARG; }
+    {   // the attribute is per function (shared by all handles on the device): only ever raise it
+        static size_t s_fast_smem_max[64] = {0};
+        if (device < 64 && fast_smem > s_fast_smem_max[device]) {
+            HVO_CUDA(cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+            s_fast_smem_max[device] = fast_smem;
+        }
+    }
 
     // ---- resize tables (cv::resize INTER_LINEAR 8U coefficient generation, oracle/cvprims.hpp) ----
     std::vector<int2> xt;
@@ -908,7 +1013,7 @@ int hvo_orb::init() {
 void hvo_orb::release() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    void* bufs[] = {d_blur, d_btiles, d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_cells, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
+    void* bufs[] = {d_blur, d_btiles, d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_strips, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
                     d_kps, d_desc, d_counts, d_kpdepth, d_kpuright};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -940,9 +1045,9 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     }
     if (profiling) HVO_CUDA(cudaEventRecord(ev[1], stream));
     // K2: FAST cells
-    if (ncells > 0) {
-        timeline_mark(stream, "k_fast_cells");
-        k_fast_cells<<<dim3(ncells, B), kFastThreads, 0, stream>>>(g, src, d_cells, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
+    if (nstrips > 0) {
+        timeline_mark(stream, "k_fast_strips");
+        k_fast_strips<<<dim3(nstrips, B), kFastThreads, fast_smem, stream>>>(g, src, d_strips, d_cand, d_ncand, p.ini_th_fast, p.min_th_fast);
         ++launches;
     }
     if (profiling) HVO_CUDA(cudaEventRecord(ev[2], stream));

@@ -43,8 +43,11 @@ struct TileDesc {  // one 128x32 tile of a level (blur kernel)
     short level, tx, ty, pad;
 };
 
-struct CellDesc {  // one FAST cell = detection zone of one reference cell ROI (zone = ROI minus the 3-px ring)
-    short level, x0, y0, zw, zh, pad;
+struct StripDesc {  // one FAST strip = the detection zones of a run of cells of one reference cell row (zone = ROI minus the 3-px ring)
+    short level, x0, y0, zw, zh;  // zone origin (level coords) and size: zw = sum of the cells' zone widths
+    short wcell, ncells;          // cell pitch in x (the last cell of a row may be narrower), cells in the run
+    short tstride;                // bytes per row of the band in shared memory (multiple of 16)
+    int score_off;                // byte offset of the score map behind the band
 };
 
 }  // namespace hvo
@@ -60,8 +63,8 @@ struct hvo_orb {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     bool profiling = false, have_stage_times = false;
     int last_launches = 0, last_nframes = 0;
-    int ncells = 0, max_zw = 0, max_zh = 0, max_quota = 0;
-    size_t oct_smem = 0;
+    int nstrips = 0, max_quota = 0;
+    size_t oct_smem = 0, fast_smem = 0;
     // device buffers
     uint8_t* d_l0 = nullptr;        // staging for host frames [B][h][w]
     uint16_t* d_depth = nullptr;    // staging for host depth [B][h][w]
@@ -72,7 +75,7 @@ struct hvo_orb {
     int2* d_xtab = nullptr;         // per level: {sx, w0 | w1 << 16}
     int4* d_ytab = nullptr;         // per level: {sy0, sy1, b0, b1}
     std::vector<int> xtab_off, ytab_off;
-    hvo::CellDesc* d_cells = nullptr;
+    hvo::StripDesc* d_strips = nullptr;
     uint32_t* d_cand = nullptr;     // [B][cand_total] packed x | y << 12 | score << 24
     int* d_ncand = nullptr;         // [B][nlevels]
     uint16_t* d_knode = nullptr;    // [B][cand_total] quadtree scratch

@@ -53,11 +53,11 @@ STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + r
           'planes: depth back-projection + 10x10 block fits + AHC merging + block erosion + ordered pixel flood fill + last merge',
           'normals: 3x subsampled cloud + integral-image normals (PCL AVERAGE_3D_GRADIENT restatement)']
 # algorithmic bytes per 640x480 frame of the HBM-bound kernels
-ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_cells': 950532, 'k_describe': 1922000 + 60000,
+ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_strips': 950532, 'k_describe': 1922000 + 60000,
              'k_lsd_prep': 307200 + 16 * 512 * 384, 'k_plane_blocks': 614400 + 3072 * 96}
 # dram__bytes_read.sum + dram__bytes_write.sum per frame of the same kernels, from the committed ncu capture
 # profiles/r1c_launches_frontend_b1024.csv (batch 1024, summary in profiles/r1c_launch_summary.txt)
-NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_cells': 959000, 'k_describe': 2048000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
+NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_strips': 959000, 'k_describe': 2048000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
 
 
 def _gen(args):
@@ -334,7 +334,7 @@ def main():
             for k, v in ex.stage_times().items():
                 acc[k] = acc.get(k, 0.0) + v / 5
         ex.close()
-        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_cells': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
+        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_strips': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
 
         le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
 

@@ -370,14 +370,22 @@ def lsd_detect(gray, want_scaled=False):
     return seg[:n].copy()
 
 
+def sort_by_response(resp):
+    """Permutation std::sort(.., sort_lines_by_response()) (include/auxiliar.h:47-52) leaves: descending, ties in libstdc++'s order."""
+    r = np.ascontiguousarray(resp, np.float32)
+    idx = np.empty(len(r), np.int32)
+    lib().orc_sort_by_response(_p(r), len(r), _p(idx))
+    return idx
+
+
 def line_extract(gray, n_features=200):
     """LINEextractor::operator() restated: LSD -> keylines -> (if > n_features) response sort, truncate, renumber ->
     LBD -> line functions.  Returns (keylines, desc, linevec [n,3] float64)."""
     gray = np.ascontiguousarray(gray, np.uint8)
     h, w = gray.shape
     kl = keylines_from_segments(lsd_detect(gray), w, h)
-    if len(kl) > n_features:  # sort_lines_by_response; ties keep detection order (std::sort leaves them unspecified)
-        order = np.argsort(-kl['response'], kind='stable')[:n_features]
+    if len(kl) > n_features:  # std::sort with sort_lines_by_response: ties in libstdc++'s (unstable) order
+        order = sort_by_response(kl['response'])[:n_features]
         kl = kl[order].copy()
         kl['class_id'] = np.arange(n_features, dtype=np.int32)
     desc = lbd_compute(gray, kl) if len(kl) else np.empty((0, 32), np.uint8)
@@ -514,6 +522,46 @@ def ref_peac(depth_frames, factor, fx, fy, cx, cy, perturb=None):
         planes = np.frombuffer(raw, pdt, npl, off).copy(); off += pdt.itemsize * npl
         mem = np.frombuffer(raw, np.int32, h * w, off).copy(); off += 4 * h * w
         out.append(dict(blocks=blocks, planes=planes, membership=mem))
+    assert off == len(raw)
+    return out
+
+
+def ref_lines(frames, n_features=200, cull=True):
+    """Run the reference's own line front-end (oracle/_ref/ref_lines: LSDDetector_custom.cpp whole, the LBD functions of
+    binary_descriptor_custom.cpp, LINEextractor::operator() and Frame::cullingLine extracted at build time) on [n,h,w] uint8
+    frames.  Returns a list of dicts: keylines/desc/fdesc/linevec (after LINEextractor::operator()) and, with cull,
+    keylines2/desc2/linevec2 (after Frame::cullingLine).  None when the binary is not available."""
+    exe = ref_bin('ref_lines')
+    if exe is None:
+        return None
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('<6i', 0x4c494e45, w, h, n, n_features, 1 if cull else 0))
+            f.write(frames.tobytes())
+        subprocess.check_call([exe, fi, fo], stdout=subprocess.DEVNULL)
+        raw = open(fo, 'rb').read()
+    out, off = [], 0
+
+    def take(with_float):
+        nonlocal off
+        (k,) = struct.unpack_from('<i', raw, off); off += 4
+        kl = np.frombuffer(raw, KL_DTYPE, k, off).copy(); off += 68 * k
+        d = np.frombuffer(raw, np.uint8, 32 * k, off).reshape(k, 32).copy(); off += 32 * k
+        fd = None
+        if with_float:
+            fd = np.frombuffer(raw, np.float32, 72 * k, off).reshape(k, 72).copy(); off += 288 * k
+        lv = np.frombuffer(raw, np.float64, 3 * k, off).reshape(k, 3).copy(); off += 24 * k
+        return kl, d, fd, lv
+    for _ in range(n):
+        kl, d, fd, lv = take(True)
+        r = dict(keylines=kl, desc=d, fdesc=fd, linevec=lv)
+        if cull:
+            kl2, d2, _, lv2 = take(False)
+            r.update(keylines2=kl2, desc2=d2, linevec2=lv2)
+        out.append(r)
     assert off == len(raw)
     return out
 

@@ -10,7 +10,7 @@
 //   2. every group is folded into one segment with MergeTwoLines (float endpoints, double arithmetic, atan/sin/cos),
 //      ungrouped untagged lines are kept, in index order.
 //   3. KeyLines are rebuilt from the new segments (:1061-1086; numOfPixels = cv::LineIterator(...).count on the
-//      cvRound'ed endpoints, after cv::clipLine), sorted by response (descending; std::sort leaves ties unspecified, the
+//      cvRound'ed endpoints, after cv::clipLine), sorted by response (descending, std::sort: ties in libstdc++'s order; the
 //      oracle keeps creation order, like LineExtractor.cpp:353), class_id renumbered.
 //   4. LBD descriptors are computed again on the new KeyLines (:1094-1096) and the line functions rebuilt (:1097-1108).
 // cv::clipLine is un-vendored OpenCV (imgproc/src/drawing.cpp); its restatement below is pinned to cv2.clipLine in
@@ -67,9 +67,12 @@ static void merge_two_lines(const float l1[4], const float l2[4], float out[4]) 
     const double kPi = 3.1415926535897932384626433832795;
     double thi, thj, thr;
     if (dlix == 0.0f) thi = kPi / 2.0;
-    else thi = std::atan((double)(dliy / dlix));
+    // atan(float) binds to the float overload in the reference (Frame.cc:33 'using namespace std', :1170): a float-precision
+    // angle.  The oracle fixes the correctly rounded float; the host libm's atanf is within 1 ulp of it (checked against the
+    // executed reference in tests/test_ref_lines.py).
+    else thi = (double)(float)std::atan((double)(dliy / dlix));
     if (dljx == 0.0f) thj = kPi / 2.0;
-    else thj = std::atan((double)(dljy / dljx));
+    else thj = (double)(float)std::atan((double)(dljy / dljx));
     if (std::fabs(thi - thj) <= kPi / 2.0) {
         thr = (li * thi + lj * thj) / (li + lj);
     } else {
@@ -231,7 +234,9 @@ int orc_cull_lines(const void* keylines_in, const double* linefunc_in, int n, in
     }
     std::vector<int> idx(m);
     std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return kl[a].response > kl[b].response; });
+    // std::sort with sort_lines_by_response (Frame.cc:1087): unstable; the order of equal responses is libstdc++'s (pinned by
+    // executing the reference: tests/test_ref_lines.py).  Sorting indices gives the same permutation as sorting the structs.
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return kl[a].response > kl[b].response; });
     KeyLine* out = (KeyLine*)keylines_out;
     for (int i = 0; i < m; ++i) { out[i] = kl[idx[i]]; out[i].class_id = i; }
     return m;

@@ -1,14 +1,20 @@
-// TEST INFRASTRUCTURE — minimal stand-in for the slice of the OpenCV C++ API that the reference's
-// src/ORBextractor.cc uses, so that file can be compiled UNMODIFIED from /root/reference into
-// oracle/_ref/ (OpenCV's C++ headers/libs are absent from this image).  The image primitives forward to
-// oracle/cvprims.hpp, which is pinned bit-exactly against cv2 4.13.0.  Not a general OpenCV replacement.
+// TEST INFRASTRUCTURE — minimal stand-in for the slice of the OpenCV C++ API that the reference sources compiled into
+// oracle/_ref/ use (src/ORBextractor.cc, src/PlaneExtractor.cpp + include/peac, Thirdparty/line_descriptor, and the
+// functions of src/Frame.cc / src/LineExtractor.cpp / src/*matcher* that oracle/extract_ref.py pulls out at build time), so
+// those sources can be compiled UNMODIFIED from /root/reference (OpenCV's C++ headers/libs are absent from this image).
+// The image primitives forward to oracle/cvprims.hpp and to the oracle's LSD / clipLine restatements, each of which is pinned
+// bit-exactly against cv2 4.13.0 (tests/test_oracle_prims.py, tests/test_lsd.py, tests/test_cull.py).  Not a general OpenCV
+// replacement.
 #pragma once
 #include <cassert>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <memory>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../cvprims.hpp"
@@ -44,9 +50,32 @@ static inline int cvFloor(float v) { return cvp::cv_floor(v); }
 static inline int cvCeil(double v) { return cvp::cv_ceil(v); }
 static inline int cvCeil(float v) { return cvp::cv_ceil(v); }
 
+#define CV_EXPORTS
+#define CV_EXPORTS_W
+#define CV_OUT
+#define CV_IN_OUT
+#define CV_WRAP
+#define CV_GRAY2BGR 8
+#define CV_BGR2GRAY 6
+
+// restatements living in oracle/_build/liboracle.so (pinned to cv2 4.13.0)
+extern "C" int orc_lsd_detect(const uint8_t* gray, int w, int h, float* segments4, int cap, uint8_t* scaled_out, int* sw, int* sh);
+extern "C" int orc_clip_line(int w, int h, long long* pts4);
+
 namespace cv {
 
-enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+using std::max;
+using std::min;
+using std::abs;
+using std::sqrt;
+using std::pow;
+using std::exp;
+using std::log;
+using std::swap;
+
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, BORDER_DEFAULT = 4 };
+enum { COLOR_BGR2GRAY = 6, COLOR_GRAY2BGR = 8 };
+enum { NORM_HAMMING = 6 };
 enum { INTER_LINEAR = 1 };
 
 template <typename T>
@@ -61,15 +90,26 @@ static inline Point_<T>& operator*=(Point_<T>& a, float b) {
     a.y = (T)(a.y * b);
     return a;
 }
+template <typename T> static inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
+template <typename T> static inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <typename T> static inline Point_<T>& operator+=(Point_<T>& a, const Point_<T>& b) { a.x += b.x; a.y += b.y; return a; }
+// cv::Point_<T> * double: saturate_cast<T>(a.x * b), computed in double
+template <typename T> static inline Point_<T> operator*(const Point_<T>& a, double b) { return Point_<T>((T)(a.x * b), (T)(a.y * b)); }
 typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
+template <typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
 
 struct Size {
     int width, height;
     Size() : width(0), height(0) {}
     Size(int w, int h) : width(w), height(h) {}
 };
+static inline bool operator==(const Size& a, const Size& b) { return a.width == b.width && a.height == b.height; }
+static inline bool operator!=(const Size& a, const Size& b) { return !(a == b); }
 struct Rect {
     int x, y, width, height;
     Rect(int _x, int _y, int w, int h) : x(_x), y(_y), width(w), height(h) {}
@@ -95,7 +135,35 @@ typedef Vec<float, 4> Vec4f;
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+    static Scalar all(double v) { return Scalar(v, v, v, v); }
 };
+struct DMatch {
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.4028235e38f) {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    bool operator<(const DMatch& m) const { return distance < m.distance; }
+};
+struct FileNode {};
+struct FileStorage {};
+class Algorithm {
+public:
+    virtual ~Algorithm() {}
+    virtual void read(const FileNode&) {}
+    virtual void write(FileStorage&) const {}
+};
+template <typename T>
+struct Ptr : public std::shared_ptr<T> {
+    Ptr() {}
+    Ptr(T* p) : std::shared_ptr<T>(p) {}
+    template <typename U> Ptr(const Ptr<U>& o) : std::shared_ptr<T>(o) {}
+    operator T*() const { return this->get(); }
+};
+template <typename T> struct cvshim_type;
+template <> struct cvshim_type<uchar> { enum { value = CV_8UC1 }; };
+template <> struct cvshim_type<int> { enum { value = CV_32SC1 }; };
+template <> struct cvshim_type<float> { enum { value = CV_32FC1 }; };
+template <> struct cvshim_type<double> { enum { value = CV_64FC1 }; };
 static inline long long getTickCount() { return 0; }
 static inline double getTickFrequency() { return 1.0; }
 
@@ -155,6 +223,17 @@ public:
         return *this;
     }
     Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
+    Size size() const { return Size(cols, rows); }
+    Mat row(int y) const { return (*this)(Rect(0, y, cols, 1)); }
+    void copyTo(Mat& dst) const { dst = clone(); }
+    void copyTo(const class _OutputArray& dst) const;
+    bool isContinuous() const { return step.v == (size_t)cols * cvshim_elem_size(type_); }
+    double dot(const Mat& o) const {  // CV_64F vectors only (Frame::TwoLineAngle); cv::Mat::dot accumulates in order
+        assert(type_ == CV_64FC1 && o.type_ == CV_64FC1 && rows * cols == o.rows * o.cols);
+        double r = 0;
+        for (int i = 0; i < rows * cols; ++i) r += at<double>(i) * o.at<double>(i);
+        return r;
+    }
     int depth() const { return type_ & 7; }
     int channels() const { return (type_ >> 3) + 1; }
     // setTo for the element types the reference writes: int labels / 8U masks, and Vec3b colours
@@ -191,8 +270,8 @@ public:
         return m;
     }
     int type() const { return type_; }
-    template <typename T> T* ptr(int y) { return (T*)(data + (size_t)y * step.v); }
-    template <typename T> const T* ptr(int y) const { return (const T*)(data + (size_t)y * step.v); }
+    template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step.v); }
+    template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step.v); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     size_t step1() const { return step.v; }
     template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step.v + x * sizeof(T)); }
@@ -203,6 +282,24 @@ public:
 private:
     int type_ = CV_8UC1;
     std::shared_ptr<std::vector<uchar>> buf_;
+};
+
+// cv::Mat_<T>(r, c) << a, b, ... (comma initialiser)
+template <typename T>
+class Mat_ : public Mat {
+public:
+    Mat_() {}
+    Mat_(int r, int c) : Mat(r, c, cvshim_type<T>::value) {}
+    struct Init {
+        Mat_ m;
+        int i;
+        Init& operator,(T v) { m.template at<T>(i++) = v; return *this; }
+        operator Mat() const { return m; }
+        operator Mat_() const { return m; }
+    };
+    Init operator<<(T v) { Init it{*this, 0}; it.m.template at<T>(it.i++) = v; return it; }
+    T& operator()(int y, int x) { return this->template at<T>(y, x); }
+    const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
 };
 
 class _InputArray {
@@ -222,6 +319,12 @@ public:
 private:
     Mat* m_;
 };
+inline void Mat::copyTo(const _OutputArray& dst) const {
+    Mat c = clone();
+    dst.create(rows, cols, type_);
+    Mat d = dst.getMat();
+    for (int y = 0; y < rows; ++y) std::memcpy(d.data + (size_t)y * d.step.v, c.data + (size_t)y * c.step.v, (size_t)cols * cvshim_elem_size(type_));
+}
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 
@@ -258,14 +361,76 @@ static inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom,
     }
 }
 
-static inline void GaussianBlur(const Mat& src, Mat& dst, Size k, double sx, double sy, int border) {
-    assert(k.width == 7 && k.height == 7 && sx == 2 && sy == 2 && border == BORDER_REFLECT_101);
-    (void)k; (void)sx; (void)sy; (void)border;
+static inline void GaussianBlur(const Mat& src, Mat& dst, Size k, double sx, double sy = 0, int border = BORDER_DEFAULT) {
+    // the two calls the reference makes: 7x7 sigma 2 (ORBextractor.cc:1084) and 5x5 sigma 1 (binary_descriptor_custom.cpp:358)
+    const bool is7 = k.width == 7 && k.height == 7 && sx == 2 && (sy == 2 || sy == 0);
+    const bool is5 = k.width == 5 && k.height == 5 && sx == 1 && (sy == 1 || sy == 0);
+    assert((is7 || is5) && border == BORDER_REFLECT_101 && src.type() == CV_8UC1);
+    (void)border; (void)is5;
     Mat tmp(src.rows, src.cols, CV_8UC1);
-    cvp::gaussian_blur7_s2(src.data, src.cols, src.rows, src.step.v, tmp.data, tmp.step.v);
+    if (is7) cvp::gaussian_blur7_s2(src.data, src.cols, src.rows, src.step.v, tmp.data, tmp.step.v);
+    else cvp::gaussian_blur5_s1(src.data, src.cols, src.rows, src.step.v, tmp.data, tmp.step.v);
     dst.create(src.rows, src.cols, CV_8UC1);
     for (int y = 0; y < tmp.rows; ++y) std::memcpy(dst.data + (size_t)y * dst.step.v, tmp.data + (size_t)y * tmp.step.v, (size_t)tmp.cols);
 }
+
+// cv::Sobel(src 8U, dst, CV_16S, dx, dy, 3): exactly one of (1,0) / (0,1)
+static inline void Sobel(const Mat& src, Mat& dst, int ddepth, int dx, int dy, int ksize) {
+    assert(src.type() == CV_8UC1 && ddepth == CV_16SC1 && ksize == 3 && dx + dy == 1 && src.isContinuous());
+    (void)ddepth; (void)ksize;
+    std::vector<int16_t> gx((size_t)src.rows * src.cols), gy(gx.size());
+    cvp::sobel3_s16(src.data, src.cols, src.rows, src.step.v, gx.data(), gy.data());
+    dst.create(src.rows, src.cols, CV_16SC1);
+    const std::vector<int16_t>& g = dx ? gx : gy;
+    for (int y = 0; y < src.rows; ++y) std::memcpy(dst.data + (size_t)y * dst.step.v, g.data() + (size_t)y * src.cols, (size_t)src.cols * 2);
+}
+
+// never reached on the reference's path (single octave, grey input); they only have to compile
+static inline void pyrDown(const Mat&, Mat&, Size) { std::fprintf(stderr, "cvshim: pyrDown is not on the path (numOctaves == 1)\n"); std::abort(); }
+static inline void cvtColor(const Mat& src, Mat& dst, int code) {
+    if (code == COLOR_GRAY2BGR) { (void)src; dst = Mat(src.rows, src.cols, CV_8UC3); return; }   // debug drawing target only
+    std::fprintf(stderr, "cvshim: cvtColor(BGR2GRAY) is not on the path (grey input)\n"); std::abort();
+}
+template <typename P> static inline void line(Mat&, P, P, const Scalar&, double = 1, int = 8, int = 0) {}  // debug drawing: no-op
+
+// cv::LineSegmentDetector with the default parameters (what LSDDetector_custom.cpp:149 constructs): forwards to the oracle's
+// restatement, which is bit-identical to cv2.createLineSegmentDetector().detect (tests/test_lsd.py, golden + live)
+class LineSegmentDetector : public Algorithm {
+public:
+    void detect(const Mat& img, std::vector<Vec4f>& lines) {
+        assert(img.type() == CV_8UC1 && img.isContinuous());
+        std::vector<float> seg((size_t)4 * 65536);
+        const int n = orc_lsd_detect(img.data, img.cols, img.rows, seg.data(), 65536, nullptr, nullptr, nullptr);
+        assert(n <= 65536);
+        lines.clear();
+        for (int i = 0; i < n; ++i) lines.push_back(Vec4f(&seg[4 * i]));
+    }
+};
+static inline Ptr<LineSegmentDetector> createLineSegmentDetector() { return Ptr<LineSegmentDetector>(new LineSegmentDetector()); }
+static inline Ptr<LineSegmentDetector> createLineSegmentDetector(int, double, double, double, double, double, double, int) {
+    std::fprintf(stderr, "cvshim: only the default LineSegmentDetector is on the path\n"); std::abort();
+}
+
+// cv::LineIterator(img, pt1, pt2): only .count is read (8-connected, after cv::clipLine; Point2f -> Point is cvRound).
+// clipLine restatement pinned to cv2.clipLine (tests/test_cull.py).
+class LineIterator {
+public:
+    int count;
+    LineIterator(const Mat& img, Point2f p1, Point2f p2) { init(img, cvRound(p1.x), cvRound(p1.y), cvRound(p2.x), cvRound(p2.y)); }
+    LineIterator(const Mat& img, Point p1, Point p2) { init(img, p1.x, p1.y, p2.x, p2.y); }
+private:
+    void init(const Mat& img, long long x1, long long y1, long long x2, long long y2) {
+        const long long w = img.cols, h = img.rows;
+        if ((unsigned long long)x1 >= (unsigned long long)w || (unsigned long long)x2 >= (unsigned long long)w ||
+            (unsigned long long)y1 >= (unsigned long long)h || (unsigned long long)y2 >= (unsigned long long)h) {
+            long long pts[4] = {x1, y1, x2, y2};
+            if (!orc_clip_line((int)w, (int)h, pts)) { count = 0; return; }
+            x1 = pts[0]; y1 = pts[1]; x2 = pts[2]; y2 = pts[3];
+        }
+        const long long dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
+        count = (int)std::max(dx, dy) + 1;
+    }
+};
 
 struct KeyPointsFilter {
     static void retainBest(std::vector<KeyPoint>&, int) {

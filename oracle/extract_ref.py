@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — pulls line ranges out of the reference's own sources, at BUILD time, into oracle/_ref/gen/*.inc so
+that they can be compiled (unmodified, where they lie being impossible: the files as a whole need the full OpenCV / PCL / g2o
+APIs) into the oracle/_ref harnesses.  Nothing extracted is committed: oracle/_ref/ is git-ignored.
+
+    python oracle/extract_ref.py [/root/reference] [oracle/_ref/gen]
+
+Every range carries an anchor: a substring its first line must contain, so that a drifted reference fails loudly instead of
+compiling something else."""
+import os
+import sys
+
+# name -> list of (file, first line, last line, anchor in the first line); 1-based inclusive, concatenated in order
+RANGES = {
+    # LBD of the vendored line_descriptor: includes/defines/namespace + combinations table + Params ctor; create + ctor; dtor ..
+    # binaryConversion; compute + computeImpl; computeLBD.  (The rest of the file is the EDLines detector, never called.)
+    'lbd': [
+        ('Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp', 42, 116, '#include "precomp_custom.hpp"'),
+        ('Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp', 206, 259, 'BinaryDescriptor::createBinaryDescriptor()'),
+        ('Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp', 302, 412, 'BinaryDescriptor::~BinaryDescriptor()'),
+        ('Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp', 523, 687, '/* requires descriptors computation (only one image) */'),
+        ('Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp', 1026, 1372, 'int BinaryDescriptor::computeLBD('),
+    ],
+    # sort_lines_by_response
+    'auxiliar': [('include/auxiliar.h', 47, 52, 'struct sort_lines_by_response')],
+    # LINEextractor::operator()
+    'line_extractor': [('src/LineExtractor.cpp', 329, 380, 'void LINEextractor::operator()')],
+    # Frame::cullingLine, PointLineDistance, TwoLineAngle, MergeTwoLines
+    'frame_cull': [('src/Frame.cc', 952, 1203, 'void Frame::cullingLine(')],
+}
+
+
+def extract(ref, out):
+    os.makedirs(out, exist_ok=True)
+    for name, parts in RANGES.items():
+        chunks = []
+        for path, a, b, anchor in parts:
+            lines = open(os.path.join(ref, path), encoding='utf-8', errors='replace').read().split('\n')
+            if anchor and anchor not in lines[a - 1]:
+                raise SystemExit(f'extract_ref: {path}:{a} does not contain {anchor!r} (reference drifted?): {lines[a - 1]!r}')
+            chunks.append(f'// ---- {path}:{a}-{b} (extracted at build time, not committed) ----')
+            chunks.append(f'#line {a} "{os.path.join(ref, path)}"')
+            chunks += lines[a - 1:b]
+        with open(os.path.join(out, name + '.inc'), 'w') as f:
+            f.write('\n'.join(chunks) + '\n')
+    print(f'extract_ref: wrote {len(RANGES)} files to {out}')
+
+
+if __name__ == '__main__':
+    ref = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'gen')
+    extract(ref, out)

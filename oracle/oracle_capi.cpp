@@ -117,6 +117,12 @@ int orc_surface_normals(const uint16_t* depth16, int W, int H, float depth_facto
 int orc_cull_lines(const void* keylines_in, const double* linefunc_in, int n, int w, int h, double dis, double angle_deg,
                    double endpoint_dis, void* keylines_out, int32_t* group_of_out);
 
+// std::sort(first, last, sort_lines_by_response()) on indices: idx_out[k] = input position of the k-th line after the sort
+void orc_sort_by_response(const float* resp, int n, int32_t* idx_out) {
+    std::iota(idx_out, idx_out + n, 0);
+    std::sort(idx_out, idx_out + n, [&](int a, int b) { return resp[a] > resp[b]; });
+}
+
 // cull != 0: followed by Frame::cullingLine(im, 5, 2.5, 15, 30) (src/Frame.cc:939), second LBD pass included
 int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keylines, uint8_t* desc, int cap, int cull) {
     std::vector<float> seg((size_t)4 * 16384);
@@ -125,11 +131,11 @@ int orc_line_extract(const uint8_t* gray, int w, int h, int nfeat, void* keyline
     std::vector<uint8_t> kl((size_t)n * 68);
     orc_keylines_from_segments(seg.data(), n, w, h, kl.data());
     std::vector<uint8_t> sel;
-    if (n > nfeat) {  // sort_lines_by_response, truncate, renumber class_id (:351-360); ties keep detection order
+    if (n > nfeat) {  // sort_lines_by_response, truncate, renumber class_id (:351-360); std::sort: ties in libstdc++'s order
         std::vector<int> idx(n);
         std::iota(idx.begin(), idx.end(), 0);
         auto resp = [&](int i) { float r; std::memcpy(&r, &kl[(size_t)i * 68 + 20], 4); return r; };
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return resp(a) > resp(b); });
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return resp(a) > resp(b); });
         sel.resize((size_t)nfeat * 68);
         for (int i = 0; i < nfeat; ++i) {
             std::memcpy(&sel[(size_t)i * 68], &kl[(size_t)idx[i] * 68], 68);

@@ -12,6 +12,9 @@ lsd_cv2.npz    inputs + outputs of cv2.createLineSegmentDetector().detect (what 
 peac_ref.npz   outputs of the reference's own plane extractor (src/PlaneExtractor.cpp + include/peac/*.hpp compiled unmodified
                into oracle/_ref/ref_peac) on synthetic depth frames: initial 10x10 blocks, extracted planes, membership image.
                Inputs are the seeded synth frames (cfg, index); a CRC of every input depth image is stored with them.
+lines_ref.npz  outputs of the reference's own line front-end (oracle/_ref/ref_lines: vendored LSDDetector_custom.cpp whole, the
+               LBD functions of binary_descriptor_custom.cpp, LINEextractor::operator() and Frame::cullingLine extracted at build
+               time) on synthetic frames: KeyLines + LBD + line functions before and after cullingLine.
 """
 import os
 import zlib
@@ -160,8 +163,30 @@ def peac():
     print('peac_ref.npz written')
 
 
+LINE_CASES = [('S1', 3), ('S1', 4), ('S2', 2), ('S3', 0)]     # S1:3 and S1:4 hold equal responses at the sort (std::sort tie order)
+
+
+def lines():
+    if oracle.ref_bin('ref_lines') is None:
+        print('oracle/_ref/ref_lines missing: run make -C oracle first')
+        return
+    out = dict(cases=np.array([f'{c}:{i}' for c, i in LINE_CASES]))
+    for cfg, idx in LINE_CASES:
+        g, _ = synth.frame(cfg, idx)
+        (r,) = oracle.ref_lines(g[None], n_features=200, cull=True)
+        k = f'{cfg}_{idx}_'
+        out[k + 'gray_crc'] = np.uint32(zlib.crc32(g.tobytes()))
+        for name in ('keylines', 'desc', 'linevec', 'keylines2', 'desc2', 'linevec2'):
+            out[k + name] = r[name]
+        print(cfg, idx, len(r['keylines']), len(r['keylines2']))
+    np.savez_compressed(os.path.join(OUT, 'lines_ref.npz'), **out)
+    print('lines_ref.npz written')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines']
+    if 'lines' in which:
+        lines()
     if 'peac' in which:
         peac()
     if 'lpvo' in which:
