@@ -566,6 +566,134 @@ def ref_lines(frames, n_features=200, cull=True):
     return out
 
 
+# ---- the reference's own windowed matchers, executed (oracle/_ref/ref_match; oracle/ref_match_main.cpp) ----------------
+def _run_ref_match(payload):
+    exe = ref_bin('ref_match')
+    if exe is None:
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(payload)
+        subprocess.check_call([exe, fi, fo], stdout=subprocess.DEVNULL)
+        return open(fo, 'rb').read()
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32).tobytes()
+
+
+def _point_frame_bytes(F):
+    k = np.ascontiguousarray(F['keys_un'], KP_DTYPE)
+    n = len(k)
+    ur = np.full(n, -1, np.float32) if F.get('uright') is None else F['uright']
+    cl = np.zeros(n, np.uint8) if F.get('claimed') is None else np.asarray(F['claimed'], np.uint8)
+    sf = np.zeros(8, np.float32); sf[:len(F['scale_factors'])] = F['scale_factors']
+    return struct.pack('<i', n) + k.tobytes() + _f32(ur) + np.ascontiguousarray(F['desc'], np.uint8).tobytes() + cl.tobytes() + sf.tobytes()
+
+
+def _line_frame_bytes(F):
+    kl = np.ascontiguousarray(F['keylines_un'], KL_DTYPE)
+    n = len(kl)
+    l3 = np.zeros((n, 6)) if F.get('lines3d') is None else F['lines3d']
+    cl = np.zeros(n, np.uint8) if F.get('claimed') is None else np.asarray(F['claimed'], np.uint8)
+    return (struct.pack('<i', n) + kl.tobytes() + np.ascontiguousarray(F['line_functions'], np.float64).tobytes()
+            + np.ascontiguousarray(F['ldesc'], np.uint8).tobytes() + np.ascontiguousarray(l3, np.float64).tobytes() + cl.tobytes())
+
+
+def _read_grid(raw, off):
+    cnt = np.empty(64 * 48, np.int32); items = []
+    for c in range(64 * 48):
+        (k,) = struct.unpack_from('<i', raw, off); off += 4
+        cnt[c] = k
+        items.append(np.frombuffer(raw, np.int32, k, off)); off += 4 * k
+    return cnt, (np.concatenate(items) if items else np.zeros(0, np.int32)), off
+
+
+def _read_lists(raw, off, n):
+    out = []
+    for _ in range(n):
+        (k,) = struct.unpack_from('<i', raw, off); off += 4
+        out.append(np.frombuffer(raw, np.int32, k, off).copy()); off += 4 * k
+    return out, off
+
+
+def ref_search_by_projection(F, MPs, th, nnratio, windows=()):
+    """The reference's ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) executed on the mirror's dict layout
+    (hvo.ORBmatcher docstring).  windows: [(x, y, r, minLevel, maxLevel)] answered by its Frame::GetFeaturesInArea.
+    Returns dict(nmatches, assign [N] map point index / -1 / -2 = held before the call, grid (cnt, items), areas)."""
+    M = len(MPs['proj_x'])
+    b = struct.pack('<2i', 0x4d544348, 0) + _f32(F['bounds']) + _point_frame_bytes(F) + struct.pack('<iff', M, th, nnratio)
+    for i in range(M):
+        b += struct.pack('<3fif4B', MPs['proj_x'][i], MPs['proj_y'][i], MPs['proj_xr'][i], int(MPs['level'][i]), MPs['view_cos'][i],
+                         int(MPs['in_view'][i]), int(MPs['bad'][i]), int(MPs['has_obs'][i]), 0) + np.asarray(MPs['desc'][i], np.uint8).tobytes()
+    w = np.asarray(windows, np.float32).reshape(-1, 5)
+    b += struct.pack('<i', len(w)) + w.tobytes()
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    cnt, items, off = _read_grid(raw, 0)
+    areas, off = _read_lists(raw, off, len(w))
+    (nm,) = struct.unpack_from('<i', raw, off); off += 4
+    n = len(F['keys_un'])
+    return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, n, off).copy(), grid=(cnt, items), areas=areas)
+
+
+def ref_search_by_projection_last(Cur, Last, cam, Tcw_cur, Tcw_last, th, mono=False, check_ori=True):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) executed.  cam = (fx, fy, cx, cy, mb, mbf);
+    Last = dict(keys KP_DTYPE [N], has_mp, outlier, has_obs, world_pos [N,3] float32, desc [N,32]).
+    Returns dict(nmatches, assign [Ncur] last-frame feature index / -1 / -2)."""
+    n = len(Last['keys'])
+    b = struct.pack('<2i', 0x4d544348, 1) + _f32(Cur['bounds']) + _point_frame_bytes(Cur) + _f32(cam) + _f32(Tcw_cur) + _f32(Tcw_last)
+    b += struct.pack('<f3i', th, int(mono), int(check_ori), n) + np.ascontiguousarray(Last['keys'], KP_DTYPE).tobytes()
+    for i in range(n):
+        b += struct.pack('<4B', int(Last['has_mp'][i]), int(Last['outlier'][i]), int(Last['has_obs'][i]), 0) + _f32(Last['world_pos'][i]) \
+            + np.asarray(Last['desc'][i], np.uint8).tobytes()
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, len(Cur['keys_un']), 4).copy())
+
+
+def ref_line_search_by_projection(F, MLs, th, nnratio, windows=()):
+    """The reference's LSDmatcher::SearchByProjection(Frame&, vector<MapLine*>&, eval_orient, th) executed on the mirror's dict layout
+    (hvo.LSDmatcher docstring; MLs also carries level).  windows: [(x1, y1, x2, y2, r, TH)] for Frame::GetFeaturesInAreaForLine."""
+    M = len(MLs['proj_x1'])
+    b = struct.pack('<2i', 0x4d544348, 2) + _f32(F['bounds']) + _line_frame_bytes(F) + struct.pack('<iff', M, th, nnratio)
+    for i in range(M):
+        b += struct.pack('<4fif4B', MLs['proj_x1'][i], MLs['proj_y1'][i], MLs['proj_x2'][i], MLs['proj_y2'][i], int(MLs['level'][i]), MLs['view_cos'][i],
+                         int(MLs['in_view'][i]), int(MLs['bad'][i]), int(MLs['has_obs'][i]), 0) \
+            + np.asarray(MLs['world_vector'][i], np.float64).tobytes() + np.asarray(MLs['desc'][i], np.uint8).tobytes()
+    w = np.asarray(windows, np.float32).reshape(-1, 6)
+    b += struct.pack('<i', len(w)) + w.tobytes()
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    cnt, items, off = _read_grid(raw, 0)
+    areas, off = _read_lists(raw, off, len(w))
+    (nm,) = struct.unpack_from('<i', raw, off); off += 4
+    return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, len(F['keylines_un']), off).copy(), grid=(cnt, items), areas=areas)
+
+
+def ref_line_search_by_projection_last(Cur, Last, th):
+    """The reference's LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th) executed.  Last = dict(keylines KL_DTYPE [N], has_ml,
+    outlier, has_obs, in_frustum, proj_x1, proj_y1, proj_x2, proj_y2, level, desc [N,32]) (isInFrustum is the harness's one stand-in)."""
+    n = len(Last['keylines'])
+    eye = np.eye(4, dtype=np.float32)
+    b = struct.pack('<2i', 0x4d544348, 3) + _f32(Cur['bounds']) + _line_frame_bytes(Cur) + _f32(eye) + _f32(eye) + struct.pack('<fi', th, n)
+    b += np.ascontiguousarray(Last['keylines'], KL_DTYPE).tobytes()
+    for i in range(n):
+        b += struct.pack('<4B4fi', int(Last['has_ml'][i]), int(Last['outlier'][i]), int(Last['has_obs'][i]), int(Last['in_frustum'][i]),
+                         Last['proj_x1'][i], Last['proj_y1'][i], Last['proj_x2'][i], Last['proj_y2'][i], int(Last['level'][i])) \
+            + np.asarray(Last['desc'][i], np.uint8).tobytes()
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, len(Cur['keylines_un']), 4).copy())
+
+
 # ---- surface normals (PCL integral-image style, Frame.cc:2155-2212) -------------------------------------------
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)

@@ -224,6 +224,13 @@ public:
     }
     Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
     Size size() const { return Size(cols, rows); }
+    Mat col(int x) const { return (*this)(Rect(x, 0, 1, rows)); }
+    Mat t() const {  // CV_32F only (pose blocks)
+        assert(type_ == CV_32FC1);
+        Mat r(cols, rows, CV_32FC1);
+        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) r.at<float>(x, y) = at<float>(y, x);
+        return r;
+    }
     Mat row(int y) const { return (*this)(Rect(0, y, cols, 1)); }
     void copyTo(Mat& dst) const { dst = clone(); }
     void copyTo(const class _OutputArray& dst) const;
@@ -301,6 +308,32 @@ public:
     T& operator()(int y, int x) { return this->template at<T>(y, x); }
     const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
 };
+
+// The three cv::MatExpr forms the reference's matchers use on small CV_32F pose blocks: A * B, A + B, -A.
+// cv::gemm on CV_32F accumulates in float, in k order (checked against cv2.gemm 4.13.0: 0 mismatches in 2000 random 3x3 * 3x1).
+static inline Mat operator*(const Mat& a, const Mat& b) {
+    assert(a.type() == CV_32FC1 && b.type() == CV_32FC1 && a.cols == b.rows);
+    Mat r(a.rows, b.cols, CV_32FC1);
+    for (int i = 0; i < a.rows; ++i)
+        for (int j = 0; j < b.cols; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < a.cols; ++k) s += a.at<float>(i, k) * b.at<float>(k, j);
+            r.at<float>(i, j) = s;
+        }
+    return r;
+}
+static inline Mat operator+(const Mat& a, const Mat& b) {
+    assert(a.type() == CV_32FC1 && b.type() == CV_32FC1 && a.rows == b.rows && a.cols == b.cols);
+    Mat r(a.rows, a.cols, CV_32FC1);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) r.at<float>(i, j) = a.at<float>(i, j) + b.at<float>(i, j);
+    return r;
+}
+static inline Mat operator-(const Mat& a) {
+    assert(a.type() == CV_32FC1);
+    Mat r(a.rows, a.cols, CV_32FC1);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) r.at<float>(i, j) = -a.at<float>(i, j);
+    return r;
+}
 
 class _InputArray {
 public:

@@ -27,6 +27,25 @@ RANGES = {
     'line_extractor': [('src/LineExtractor.cpp', 329, 380, 'void LINEextractor::operator()')],
     # Frame::cullingLine, PointLineDistance, TwoLineAngle, MergeTwoLines
     'frame_cull': [('src/Frame.cc', 952, 1203, 'void Frame::cullingLine(')],
+    # Frame grids: AssignFeaturesToGrid, AssignFeaturesToGridForLine; GetFeaturesInArea (the two '#pragma GCC' lines around it
+    # are left out), GetFeaturesInAreaForLine; PosInGrid
+    'frame_grid': [('src/Frame.cc', 832, 872, 'void Frame::AssignFeaturesToGrid()'),
+                   ('src/Frame.cc', 1502, 1555, 'vector<size_t> Frame::GetFeaturesInArea('),
+                   ('src/Frame.cc', 1557, 1631, 'vector<size_t> Frame::GetFeaturesInAreaForLine('),
+                   ('src/Frame.cc', 1680, 1690, 'bool Frame::PosInGrid(')],
+    # ORBmatcher: constants + ctor, SearchByProjection(F, MapPoints, th) + RadiusByViewingCos, SearchByProjection(Cur, Last, th,
+    # mono), ComputeThreeMaxima + DescriptorDistance
+    'orbmatcher': [('src/ORBmatcher.cc', 37, 43, 'const int ORBmatcher::TH_HIGH'),
+                   ('src/ORBmatcher.cc', 45, 140, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints'),
+                   ('src/ORBmatcher.cc', 1353, 1497, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
+                   ('src/ORBmatcher.cc', 1630, 1692, 'void ORBmatcher::ComputeThreeMaxima(')],
+    # LSDmatcher: constants + ctor + computeAngle2D, SearchByProjection(Cur, Last, th), SearchByProjection(F, MapLines, ...),
+    # DescriptorDistance, RadiusByViewingCos
+    'lsdmatcher': [('src/LSDmatcher.cpp', 12, 34, 'const int LSDmatcher::TH_HIGH'),
+                   ('src/LSDmatcher.cpp', 561, 664, 'int LSDmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
+                   ('src/LSDmatcher.cpp', 709, 801, 'int LSDmatcher::SearchByProjection(Frame &F, const std::vector<MapLine *> &vpMapLines'),
+                   ('src/LSDmatcher.cpp', 1137, 1153, 'int LSDmatcher::DescriptorDistance('),
+                   ('src/LSDmatcher.cpp', 1436, 1442, 'float LSDmatcher::RadiusByViewingCos(')],
 }
 
 

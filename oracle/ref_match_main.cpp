@@ -1,0 +1,305 @@
+// TEST INFRASTRUCTURE — driver for the reference's own windowed matchers, compiled from the sources where they lie.  The
+// functions are pulled out at build time by oracle/extract_ref.py (oracle/_ref/gen/*.inc, never committed):
+//   src/Frame.cc:832-872, 1502-1555, 1557-1631, 1680-1690   AssignFeaturesToGrid(+ForLine), GetFeaturesInArea(+ForLine), PosInGrid
+//   src/ORBmatcher.cc:37-43, 45-140, 1353-1497, 1630-1692   SearchByProjection(F, MapPoints, th), RadiusByViewingCos,
+//                                                            SearchByProjection(Cur, Last, th, mono), ComputeThreeMaxima, DescriptorDistance
+//   src/LSDmatcher.cpp:12-34, 561-664, 709-801, 1137-1153, 1436-1442   the two line SearchByProjection + helpers
+//   src/lineIterator.cpp                                     whole file, unmodified
+// and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
+// (declared below with the reference header line each one mirrors) plus the OpenCV / Eigen stand-ins.
+// One substitution: Frame::isInFrustum(MapLine*, float) (Frame.cc:1438-1499, not on the pinned path) returns the map line's
+// precomputed mbTrackInView; the projection fields it would fill are given as input.
+//
+//   ref_match <in.bin> <out.bin>      (formats: see oracle/__init__.py ref_match_*)
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <list>
+#include <set>
+#include <unordered_set>
+#include <vector>
+
+#include "precomp_custom.hpp"   // vendored line_descriptor umbrella (KeyLine)
+#include <Eigen/Core>
+#include "lineIterator.h"
+
+using namespace std;
+using namespace cv;
+using namespace cv::line_descriptor;
+using namespace Eigen;
+typedef Matrix<double, 6, 1> Vector6d;   // include/auxiliar.h:23
+
+#define FRAME_GRID_ROWS 48               // include/Frame.h:59-60
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM2 {
+class KeyFrame;
+class MapPoint {                          // include/MapPoint.h:49-102
+public:
+    cv::Mat GetWorldPos() { return pos.clone(); }
+    int Observations() { return nobs; }
+    bool isBad() { return bad; }
+    cv::Mat GetDescriptor() { return desc.clone(); }
+    float mTrackProjX, mTrackProjY, mTrackProjXR;
+    bool mbTrackInView;
+    int mnTrackScaleLevel;
+    float mTrackViewCos;
+    cv::Mat pos, desc;
+    int nobs = 0;
+    bool bad = false;
+    int id = -1;
+};
+class MapLine {                           // include/MapLine.h:40-110
+public:
+    Vector6d GetWorldPos() { return wpos; }
+    Vector3d GetWorldVector() { return wvec; }
+    int Observations() { return nobs; }
+    bool isBad() { return bad; }
+    Mat GetDescriptor() { return desc.clone(); }
+    float mTrackProjX1, mTrackProjY1, mTrackProjX2, mTrackProjY2;
+    int mnTrackScaleLevel;
+    float mTrackViewCos;
+    bool mbTrackInView;
+    Vector6d wpos;
+    Vector3d wvec;
+    Mat desc;
+    int nobs = 0;
+    bool bad = false;
+    int id = -1;
+};
+class Frame {                             // include/Frame.h:129-131, 224-353
+public:
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
+    vector<size_t> GetFeaturesInAreaForLine(const float& x1, const float& y1, const float& x2, const float& y2, const float& r, const int minLevel = -1,
+                                            const int maxLevel = -1, const float TH = 0.998) const;
+    void AssignFeaturesToGrid();
+    void AssignFeaturesToGridForLine();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    bool isInFrustum(MapLine* pML, float) { return pML->mbTrackInView; }
+    static float fx, fy, cx, cy;
+    float mb = 0.f, mbf = 0.f;
+    int N = 0, NL = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors, mLdesc;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    vector<KeyLine> mvKeylinesUn;
+    std::vector<std::pair<Eigen::Vector3d, Eigen::Vector3d>> mvLines3D;
+    vector<Vector3d> mvKeyLineFunctions;
+    vector<bool> mvbLineOutlier;
+    std::vector<MapLine*> mvpMapLines;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<std::size_t> mGridForLine[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    cv::Mat mTcw;
+    vector<float> mvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+class ORBmatcher {                        // include/ORBmatcher.h:38-104
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+protected:
+    float RadiusByViewingCos(const float& viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+class LSDmatcher {                        // include/LSDmatcher.h:20-70
+public:
+    LSDmatcher(float nnratio = 0.6, bool checkOri = true);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th);
+    int SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, const bool eval_orient, const float th = 3);
+    static int DescriptorDistance(const Mat& a, const Mat& b);
+    static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+protected:
+    double computeAngle2D(const cv::Mat& vector1, const cv::Mat& vector2);
+    float RadiusByViewingCos(const float& viewCos);
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+#include "gen/frame_grid.inc"
+#include "gen/orbmatcher.inc"
+}  // namespace ORB_SLAM2
+namespace ORB_SLAM2 {
+#include "gen/lsdmatcher.inc"
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+// ---- binary I/O ----
+static FILE *g_in, *g_out;
+template <class T> static T get() { T v; if (std::fread(&v, sizeof(T), 1, g_in) != 1) { std::fprintf(stderr, "ref_match: short input\n"); std::exit(4); } return v; }
+template <class T> static void get_n(T* p, size_t n) { if (n && std::fread(p, sizeof(T), n, g_in) != n) { std::fprintf(stderr, "ref_match: short input\n"); std::exit(4); } }
+template <class T> static void put(const T& v) { std::fwrite(&v, sizeof(T), 1, g_out); }
+static cv::Mat get_desc_rows(int n) {
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1);
+    get_n(m.data, (size_t)n * 32);
+    return m;
+}
+static void set_bounds() {
+    float b[4]; get_n(b, 4);
+    Frame::mnMinX = b[0]; Frame::mnMinY = b[1]; Frame::mnMaxX = b[2]; Frame::mnMaxY = b[3];
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);    // Frame.cc:198-199
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+}
+static cv::Mat get_pose() { cv::Mat T(4, 4, CV_32FC1); get_n((float*)T.data, 16); return T; }
+
+// point frame: N, keysUn[N], uright[N], desc[N][32], claimed[N] (holds a map point with observations)
+static void read_point_frame(Frame& F, std::vector<MapPoint>& claimed_pool) {
+    F.N = get<int32_t>();
+    F.mvKeysUn.resize(F.N); get_n(F.mvKeysUn.data(), F.N);
+    F.mvKeys = F.mvKeysUn;
+    F.mvuRight.resize(F.N); get_n(F.mvuRight.data(), F.N);
+    F.mDescriptors = get_desc_rows(F.N);
+    std::vector<uint8_t> cl(F.N); get_n(cl.data(), F.N);
+    claimed_pool.resize(F.N);
+    F.mvpMapPoints.assign(F.N, nullptr);
+    for (int i = 0; i < F.N; ++i) if (cl[i]) { claimed_pool[i].nobs = 1; claimed_pool[i].id = -2; F.mvpMapPoints[i] = &claimed_pool[i]; }
+    F.mvScaleFactors.resize(8); get_n(F.mvScaleFactors.data(), 8);
+    F.AssignFeaturesToGrid();
+}
+// line frame: NL, keylinesUn[NL], line functions [NL][3], desc, lines3D [NL][6], claimed[NL]
+static void read_line_frame(Frame& F, std::vector<MapLine>& claimed_pool) {
+    F.NL = get<int32_t>();
+    F.mvKeylinesUn.resize(F.NL); get_n(F.mvKeylinesUn.data(), F.NL);
+    F.mvKeyLineFunctions.resize(F.NL);
+    for (int i = 0; i < F.NL; ++i) get_n(F.mvKeyLineFunctions[i].data(), 3);
+    F.mLdesc = get_desc_rows(F.NL);
+    F.mvLines3D.resize(F.NL);
+    for (int i = 0; i < F.NL; ++i) { get_n(F.mvLines3D[i].first.data(), 3); get_n(F.mvLines3D[i].second.data(), 3); }
+    std::vector<uint8_t> cl(F.NL); get_n(cl.data(), F.NL);
+    claimed_pool.resize(F.NL);
+    F.mvpMapLines.assign(F.NL, nullptr);
+    for (int i = 0; i < F.NL; ++i) if (cl[i]) { claimed_pool[i].nobs = 1; claimed_pool[i].id = -2; F.mvpMapLines[i] = &claimed_pool[i]; }
+    F.AssignFeaturesToGridForLine();
+}
+static void put_grid(const std::vector<std::size_t> (*grid)[FRAME_GRID_ROWS]) {
+    for (int ix = 0; ix < FRAME_GRID_COLS; ++ix)
+        for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) {
+            put<int32_t>((int32_t)grid[ix][iy].size());
+            for (size_t v : grid[ix][iy]) put<int32_t>((int32_t)v);
+        }
+}
+
+int main(int argc, char** argv) {
+    if (argc != 3) { std::fprintf(stderr, "usage: ref_match in.bin out.bin\n"); return 2; }
+    g_in = std::fopen(argv[1], "rb");
+    g_out = std::fopen(argv[2], "wb");
+    if (!g_in || !g_out) return 2;
+    if (get<int32_t>() != 0x4d544348) return 3;
+    const int op = get<int32_t>();
+    set_bounds();
+    if (op == 0) {          // ORBmatcher::SearchByProjection(F, vpMapPoints, th)
+        Frame F; std::vector<MapPoint> pool;
+        read_point_frame(F, pool);
+        const int M = get<int32_t>();
+        const float th = get<float>(), nnratio = get<float>();
+        std::vector<MapPoint> mps(M);
+        std::vector<MapPoint*> vp(M);
+        for (int i = 0; i < M; ++i) {
+            MapPoint& m = mps[i];
+            m.mTrackProjX = get<float>(); m.mTrackProjY = get<float>(); m.mTrackProjXR = get<float>();
+            m.mnTrackScaleLevel = get<int32_t>(); m.mTrackViewCos = get<float>();
+            m.mbTrackInView = get<uint8_t>() != 0; m.bad = get<uint8_t>() != 0; m.nobs = get<uint8_t>(); (void)get<uint8_t>();
+            m.desc = get_desc_rows(1); m.id = i; vp[i] = &m;
+        }
+        // window queries answered by the reference's GetFeaturesInArea, for the grid / candidate-order pin
+        const int nq = get<int32_t>();
+        std::vector<float> wq((size_t)nq * 5); get_n(wq.data(), wq.size());
+        put_grid(F.mGrid);
+        for (int i = 0; i < nq; ++i) {
+            const vector<size_t> v = F.GetFeaturesInArea(wq[5 * i], wq[5 * i + 1], wq[5 * i + 2], (int)wq[5 * i + 3], (int)wq[5 * i + 4]);
+            put<int32_t>((int32_t)v.size());
+            for (size_t x : v) put<int32_t>((int32_t)x);
+        }
+        ORBmatcher matcher(nnratio, true);
+        const int nm = matcher.SearchByProjection(F, vp, th);
+        put<int32_t>(nm);
+        for (int i = 0; i < F.N; ++i) put<int32_t>(F.mvpMapPoints[i] ? F.mvpMapPoints[i]->id : -1);
+    } else if (op == 1) {   // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)
+        Frame C, L; std::vector<MapPoint> pool;
+        read_point_frame(C, pool);
+        float cam[6]; get_n(cam, 6);
+        Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3]; C.mb = cam[4]; C.mbf = cam[5];
+        C.mTcw = get_pose(); L.mTcw = get_pose();
+        const float th = get<float>();
+        const int mono = get<int32_t>(), check_ori = get<int32_t>();
+        L.N = get<int32_t>();
+        L.mvKeys.resize(L.N); get_n(L.mvKeys.data(), L.N);
+        L.mvKeysUn = L.mvKeys;
+        std::vector<MapPoint> mps(L.N);
+        L.mvpMapPoints.assign(L.N, nullptr); L.mvbOutlier.assign(L.N, false);
+        for (int i = 0; i < L.N; ++i) {
+            const int has = get<uint8_t>(); L.mvbOutlier[i] = get<uint8_t>() != 0; mps[i].nobs = get<uint8_t>(); (void)get<uint8_t>();
+            mps[i].pos = cv::Mat(3, 1, CV_32FC1); get_n((float*)mps[i].pos.data, 3);
+            mps[i].desc = get_desc_rows(1); mps[i].id = i;
+            if (has) L.mvpMapPoints[i] = &mps[i];
+        }
+        ORBmatcher matcher(0.9f, check_ori != 0);
+        const int nm = matcher.SearchByProjection(C, L, th, mono != 0);
+        put<int32_t>(nm);
+        for (int i = 0; i < C.N; ++i) put<int32_t>(C.mvpMapPoints[i] ? C.mvpMapPoints[i]->id : -1);
+    } else if (op == 2) {   // LSDmatcher::SearchByProjection(F, vpMapLines, eval_orient, th)
+        Frame F; std::vector<MapLine> pool;
+        read_line_frame(F, pool);
+        const int M = get<int32_t>();
+        const float th = get<float>(), nnratio = get<float>();
+        std::vector<MapLine> mls(M);
+        std::vector<MapLine*> vp(M);
+        for (int i = 0; i < M; ++i) {
+            MapLine& m = mls[i];
+            m.mTrackProjX1 = get<float>(); m.mTrackProjY1 = get<float>(); m.mTrackProjX2 = get<float>(); m.mTrackProjY2 = get<float>();
+            m.mnTrackScaleLevel = get<int32_t>(); m.mTrackViewCos = get<float>();
+            m.mbTrackInView = get<uint8_t>() != 0; m.bad = get<uint8_t>() != 0; m.nobs = get<uint8_t>(); (void)get<uint8_t>();
+            get_n(m.wvec.data(), 3);
+            m.desc = get_desc_rows(1); m.id = i; vp[i] = &m;
+        }
+        const int nq = get<int32_t>();
+        std::vector<float> wq((size_t)nq * 6); get_n(wq.data(), wq.size());
+        put_grid(F.mGridForLine);
+        for (int i = 0; i < nq; ++i) {
+            const vector<size_t> v = F.GetFeaturesInAreaForLine(wq[6 * i], wq[6 * i + 1], wq[6 * i + 2], wq[6 * i + 3], wq[6 * i + 4], -1, -1, wq[6 * i + 5]);
+            put<int32_t>((int32_t)v.size());
+            for (size_t x : v) put<int32_t>((int32_t)x);
+        }
+        LSDmatcher matcher(nnratio, true);
+        const int nm = matcher.SearchByProjection(F, vp, true, th);
+        put<int32_t>(nm);
+        for (int i = 0; i < F.NL; ++i) put<int32_t>(F.mvpMapLines[i] ? F.mvpMapLines[i]->id : -1);
+    } else if (op == 3) {   // LSDmatcher::SearchByProjection(CurrentFrame, LastFrame, th)
+        Frame C, L; std::vector<MapLine> pool;
+        read_line_frame(C, pool);
+        C.mTcw = get_pose(); L.mTcw = get_pose();
+        const float th = get<float>();
+        L.NL = get<int32_t>();
+        L.mvKeylinesUn.resize(L.NL); get_n(L.mvKeylinesUn.data(), L.NL);
+        std::vector<MapLine> mls(L.NL);
+        L.mvpMapLines.assign(L.NL, nullptr); L.mvbLineOutlier.assign(L.NL, false);
+        for (int i = 0; i < L.NL; ++i) {
+            MapLine& m = mls[i];
+            const int has = get<uint8_t>(); L.mvbLineOutlier[i] = get<uint8_t>() != 0; m.nobs = get<uint8_t>(); m.mbTrackInView = get<uint8_t>() != 0;
+            m.mTrackProjX1 = get<float>(); m.mTrackProjY1 = get<float>(); m.mTrackProjX2 = get<float>(); m.mTrackProjY2 = get<float>();
+            m.mnTrackScaleLevel = get<int32_t>();
+            m.desc = get_desc_rows(1); m.id = i;
+            if (has) L.mvpMapLines[i] = &m;
+        }
+        LSDmatcher matcher(0.95f, true);
+        const int nm = matcher.SearchByProjection(C, L, th);
+        put<int32_t>(nm);
+        for (int i = 0; i < C.NL; ++i) put<int32_t>(C.mvpMapLines[i] ? C.mvpMapLines[i]->id : -1);
+    } else {
+        return 5;
+    }
+    std::fclose(g_in);
+    std::fclose(g_out);
+    return 0;
+}

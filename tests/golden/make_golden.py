@@ -15,6 +15,9 @@ peac_ref.npz   outputs of the reference's own plane extractor (src/PlaneExtracto
 lines_ref.npz  outputs of the reference's own line front-end (oracle/_ref/ref_lines: vendored LSDDetector_custom.cpp whole, the
                LBD functions of binary_descriptor_custom.cpp, LINEextractor::operator() and Frame::cullingLine extracted at build
                time) on synthetic frames: KeyLines + LBD + line functions before and after cullingLine.
+match_ref.npz  outputs of the reference's own windowed matchers (oracle/_ref/ref_match: Frame grids + GetFeaturesInArea*, the two
+               ORBmatcher::SearchByProjection and the two LSDmatcher::SearchByProjection, extracted at build time) on the scenes of
+               tests/test_ref_match.py: grids, candidate lists, final assignments, match counts.
 """
 import os
 import zlib
@@ -183,8 +186,23 @@ def lines():
     print('lines_ref.npz written')
 
 
+def match():
+    if oracle.ref_bin('ref_match') is None:
+        print('oracle/_ref/ref_match missing: run make -C oracle first')
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_ref_match as t
+    t._golden = None
+    for check in (t._check_search_by_projection, t._check_search_last, t._check_line_search, t._check_line_search_last):
+        check(hvo_b200, synth, gpu=False)          # CPU leg: the mirrors on the oracle must already equal the live reference
+    np.savez_compressed(os.path.join(OUT, 'match_ref.npz'), **t.RECORD)
+    print('match_ref.npz written:', len(t.RECORD), 'arrays')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match']
+    if 'match' in which:
+        match()
     if 'lines' in which:
         lines()
     if 'peac' in which:

@@ -1,0 +1,311 @@
+"""Windowed matchers pinned BY EXECUTION of the reference's own functions (oracle/_ref/ref_match, built by oracle/Makefile):
+Frame::AssignFeaturesToGrid(+ForLine), PosInGrid, GetFeaturesInArea(+ForLine) (src/Frame.cc:832-872, 1502-1631, 1680-1690),
+ORBmatcher::SearchByProjection(F, MapPoints, th) and (Cur, Last, th, mono) with the rotation histogram (src/ORBmatcher.cc:45-140,
+1353-1497, 1630-1692), LSDmatcher::SearchByProjection x2 (src/LSDmatcher.cpp:561-664, 709-801) and src/lineIterator.cpp, pulled out
+of the reference at build time (oracle/extract_ref.py) and compiled against stand-in Frame / MapPoint / MapLine classes.
+
+The host-side mirrors (hvo.ORBmatcher / hvo.LSDmatcher: query building, application of the result, rotation histogram) are run
+  CPU: on top of the CPU oracle's search (an adapter with the ProjectionMatcher interface),
+  GPU: on top of the CUDA search (hvo_proj_* / hvo_lproj_*),
+and must reproduce the reference's final Frame::mvpMapPoints / mvpMapLines and match count exactly; grids and candidate lists
+(order included) are compared directly.  Everything here is integer / index work: the bar is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+BOUNDS = (0.0, 0.0, 640.0, 480.0)
+SF = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'match_ref.npz')
+_golden = np.load(GOLDEN) if os.path.exists(GOLDEN) else None
+RECORD = {}     # filled when tests/golden/make_golden.py runs these checks to (re)write the fixture
+
+
+def _need_ref():
+    if oracle.ref_bin('ref_match') is None and _golden is None:
+        pytest.skip('neither oracle/_ref/ref_match nor tests/golden/match_ref.npz is available')
+
+
+def _ref(key, run):
+    """The executed reference's result for scene `key`: run live when the binary is there (and checked against the committed
+    fixture), else taken from the fixture tests/golden/match_ref.npz."""
+    live = run() if oracle.ref_bin('ref_match') is not None else None
+    if live is not None:
+        flat = dict(nmatches=np.int32(live['nmatches']), assign=live['assign'])
+        if 'grid' in live:
+            flat.update(grid_cnt=live['grid'][0], grid_items=live['grid'][1], area_len=np.array([len(a) for a in live['areas']], np.int32),
+                        area_items=np.concatenate(live['areas'] + [np.zeros(0, np.int32)]))
+        for k, v in flat.items():
+            RECORD[f'{key}_{k}'] = v
+            if _golden is not None and f'{key}_{k}' in _golden:
+                assert np.array_equal(_golden[f'{key}_{k}'], v), f'fixture differs from the live reference: {key}_{k}'
+        return live
+    g = _golden
+    out = dict(nmatches=int(g[f'{key}_nmatches']), assign=g[f'{key}_assign'])
+    if f'{key}_grid_cnt' in g:
+        ends = np.cumsum(g[f'{key}_area_len'])
+        out['grid'] = (g[f'{key}_grid_cnt'], g[f'{key}_grid_items'])
+        out['areas'] = [g[f'{key}_area_items'][e - n:e] for e, n in zip(ends, g[f'{key}_area_len'])]
+    return out
+
+
+class OraclePM:
+    """hvo.ProjectionMatcher's interface served by the CPU oracle (for the CPU leg of these tests)."""
+
+    def set_frame(self, keys, uright, desc, a, b, c, d):
+        self.k, self.ur, self.d, self.b = keys, uright, desc, (a, b, c, d)
+
+    def search(self, q, qd, claimed, mode, th, ratio):
+        return oracle.search_projection(self.k, self.ur, self.d, self.b, q, qd, claimed, mode, th, ratio)
+
+
+class OracleLPM:
+    def set_frame(self, kl, fn, desc, l3, a, b, c, d):
+        self.kl, self.fn, self.d, self.l3, self.b = kl, fn, desc, l3, (a, b, c, d)
+
+    def search(self, q, qd, claimed, mode, ratio):
+        return oracle.line_search_projection(self.kl, self.fn, self.d, self.l3, self.b, q, qd, claimed, mode, ratio)
+
+
+def _orb_matcher(hvo, gpu, nnratio, check_ori=True):
+    if gpu:
+        return hvo.ORBmatcher(nnratio, check_ori)
+    m = hvo.ORBmatcher.__new__(hvo.ORBmatcher)
+    m.mfNNratio, m.mbCheckOrientation, m._pm = float(nnratio), bool(check_ori), OraclePM()
+    return m
+
+
+def _lsd_matcher(hvo, gpu, nnratio):
+    if gpu:
+        return hvo.LSDmatcher(nnratio, True)
+    m = hvo.LSDmatcher.__new__(hvo.LSDmatcher)
+    m.mfNNratio, m.mbCheckOrientation, m._lpm, m._bf = np.float32(nnratio), True, OracleLPM(), None
+    m._line_matcher = lambda F, need3d: (m._lpm.set_frame(F['keylines_un'], F['line_functions'], F['ldesc'], F.get('lines3d') if need3d else None,
+                                                           *F['bounds']), m._lpm)[1]
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# points
+# ---------------------------------------------------------------------------------------------------------------------------
+def _point_scene(synth, seed):
+    rng = np.random.RandomState(seed)
+    k0, d0 = oracle.OrbOracle().extract(synth.frame('S1', 0)[0])
+    k1, d1 = oracle.OrbOracle().extract(synth.frame('S1', 1)[0])
+    n0 = len(k0)
+    F = dict(keys_un=k0, desc=d0, bounds=BOUNDS, scale_factors=SF,
+             uright=np.where(rng.rand(n0) > 0.4, k0['x'] - rng.uniform(5, 40, n0), -1).astype(np.float32),
+             claimed=(rng.rand(n0) < 0.1), mappoint=np.full(n0, -1, np.int32))
+    F['mappoint'][F['claimed']] = -2
+    n_extra = 250
+    M = len(k1) + n_extra
+    MPs = dict(proj_x=np.concatenate([k1['x'] + rng.normal(0, 1.0, len(k1)), rng.uniform(-20, 660, n_extra)]).astype(np.float32),
+               proj_y=np.concatenate([k1['y'] + rng.normal(0, 1.0, len(k1)), rng.uniform(-20, 500, n_extra)]).astype(np.float32),
+               level=np.concatenate([k1['octave'], rng.randint(0, 8, n_extra)]).astype(np.int32),
+               view_cos=rng.uniform(0.99, 1.0, M).astype(np.float32), in_view=rng.rand(M) > 0.1, bad=rng.rand(M) < 0.05,
+               has_obs=rng.rand(M) > 0.3, desc=np.concatenate([d1, rng.randint(0, 256, (n_extra, 32)).astype(np.uint8)]))
+    MPs['proj_xr'] = (MPs['proj_x'] - rng.uniform(5, 40, M)).astype(np.float32)
+    return F, MPs, k1, d1
+
+
+def _check_search_by_projection(hvo, synth, gpu):
+    _need_ref()
+    for seed, th in ((0, 1.0), (1, 3.0), (2, 5.0)):
+        F, MPs, _, _ = _point_scene(synth, seed)
+        rng = np.random.RandomState(100 + seed)
+        windows = [(rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(1, 60), *((-1, -1) if rng.rand() < 0.3 else (rng.randint(0, 5), rng.randint(3, 8))))
+                   for _ in range(40)]
+        ref = _ref(f'pts_map_{seed}', lambda: oracle.ref_search_by_projection(F, MPs, th, 0.8, windows))
+        # grid and candidate lists (order included)
+        if gpu:
+            pm = hvo.ProjectionMatcher()
+            pm.set_frame(F['keys_un'], F['uright'], F['desc'], *BOUNDS)
+            cs, items = pm.grid()
+            cnt = np.diff(cs)
+            areas = [pm.GetFeaturesInArea(np.float32(w[0]), np.float32(w[1]), np.float32(w[2]), int(w[3]), int(w[4])) for w in windows]
+            pm.close()
+        else:
+            cnt, items = oracle.grid_build(F['keys_un'], BOUNDS)
+            areas = [oracle.features_in_area(F['keys_un'], BOUNDS, np.float32(w[0]), np.float32(w[1]), np.float32(w[2]), int(w[3]), int(w[4])) for w in windows]
+        assert np.array_equal(cnt, ref['grid'][0]) and np.array_equal(items, ref['grid'][1])
+        assert sum(len(a) for a in ref['areas']) > 100
+        for a, b in zip(areas, ref['areas']):
+            assert np.array_equal(a, b)
+        # the greedy assignment
+        m = _orb_matcher(hvo, gpu, 0.8)
+        nm, match = m.SearchByProjection(F, MPs, th)
+        assert nm == ref['nmatches'] and nm > 300
+        assert np.array_equal(F['mappoint'], ref['assign'])
+
+
+def test_cpu_search_by_projection_equals_reference(hvo, synth):
+    _check_search_by_projection(hvo, synth, gpu=False)
+
+
+@pytest.mark.gpu
+def test_gpu_search_by_projection_equals_reference(hvo, synth):
+    _check_search_by_projection(hvo, synth, gpu=True)
+
+
+def _f32(x):
+    return np.asarray(x, np.float32)
+
+
+def _project_last(Last, cam, Tcw, th_unused=None):
+    """The projection of SearchByProjection(Cur, Last) (ORBmatcher.cc:1387-1404) with the reference's float arithmetic:
+    cv::gemm on CV_32F accumulates in float in k order, invzc = 1.0 / z is a double division narrowed to float."""
+    fx, fy, cx, cy, mb, mbf = (np.float32(v) for v in cam)
+    R, t = _f32(Tcw[:3, :3]), _f32(Tcw[:3, 3])
+    P = _f32(Last['world_pos'])
+    xc = np.zeros((len(P), 3), np.float32)
+    for i in range(3):
+        s = np.zeros(len(P), np.float32)
+        for k in range(3):
+            s = (s + (R[i, k] * P[:, k]).astype(np.float32)).astype(np.float32)
+        xc[:, i] = (s + t[i]).astype(np.float32)
+    with np.errstate(divide='ignore'):
+        invz = (1.0 / xc[:, 2].astype(np.float64)).astype(np.float32)
+    u = ((fx * xc[:, 0]).astype(np.float32) * invz).astype(np.float32) + cx
+    v = ((fy * xc[:, 1]).astype(np.float32) * invz).astype(np.float32) + cy
+    ur = (u - (mbf * invz).astype(np.float32)).astype(np.float32)
+    return u.astype(np.float32), v.astype(np.float32), ur, invz
+
+
+def _check_search_last(hvo, synth, gpu):
+    _need_ref()
+    cam = (535.4, 539.2, 320.1, 247.6, 0.0747, 40.0)
+    for seed, dz, check_ori in ((0, 0.0, True), (1, 0.2, True), (2, -0.2, False)):
+        rng = np.random.RandomState(seed)
+        F, _, k1, d1 = _point_scene(synth, seed + 10)
+        n1 = len(k1)
+        # last-frame map points: back-project the last frame's keypoints at random depths, then move the camera a little
+        z = rng.uniform(1.0, 4.0, n1).astype(np.float32)
+        P = np.stack([(k1['x'] - cam[2]) * z / cam[0], (k1['y'] - cam[3]) * z / cam[1], z], 1).astype(np.float32)
+        ang = 0.004
+        Tc = np.eye(4, dtype=np.float32)
+        Tc[:3, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], np.float32)
+        Tc[:3, 3] = np.array([0.01, -0.005, dz], np.float32)             # |dz| > mb: forward / backward window
+        Tl = np.eye(4, dtype=np.float32)
+        Last = dict(keys=k1, has_mp=rng.rand(n1) > 0.2, outlier=rng.rand(n1) < 0.1, has_obs=rng.rand(n1) > 0.2, world_pos=P, desc=d1)
+        ref = _ref(f'pts_last_{seed}', lambda: oracle.ref_search_by_projection_last(F, Last, cam, Tc, Tl, 7.0, mono=False, check_ori=check_ori))
+        # the mirror takes the usable last-frame features with their projections (host side of the reference loop)
+        u, v, ur, invz = _project_last(Last, cam, Tc)
+        use = Last['has_mp'] & ~Last['outlier'] & ~(invz < 0) & ~(u < BOUNDS[0]) & ~(u > BOUNDS[2]) & ~(v < BOUNDS[1]) & ~(v > BOUNDS[3])
+        sel = np.nonzero(use)[0]
+        last = dict(u=u[sel], v=v[sel], ur=ur[sel], octave=k1['octave'][sel], angle=k1['angle'][sel], has_obs=Last['has_obs'][sel], desc=d1[sel])
+        tlc_z = -dz                                                       # tlc = Rlw * twc + tlw with Rlw = I: -Rcw^T tcw, z component
+        m = _orb_matcher(hvo, gpu, 0.9, check_ori)
+        nm, match = m.SearchByProjectionLast(F, last, 7.0, forward=tlc_z > cam[4], backward=-tlc_z > cam[4])
+        got = F['mappoint'].copy()
+        got[got >= 0] = sel[got[got >= 0]]                                # back to last-frame feature indices
+        assert nm == ref['nmatches'] and nm > 150
+        assert np.array_equal(got, ref['assign'])
+
+
+def test_cpu_search_last_frame_equals_reference(hvo, synth):
+    _check_search_last(hvo, synth, gpu=False)
+
+
+@pytest.mark.gpu
+def test_gpu_search_last_frame_equals_reference(hvo, synth):
+    _check_search_last(hvo, synth, gpu=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# lines
+# ---------------------------------------------------------------------------------------------------------------------------
+def _line_scene(synth, seed):
+    rng = np.random.RandomState(seed)
+    kl0, d0, lv0 = oracle.line_extract(synth.frame('S1', 0)[0], 200)
+    kl1, d1, _ = oracle.line_extract(synth.frame('S1', 1)[0], 200)
+    n0, n1 = len(kl0), len(kl1)
+    dirs0 = rng.normal(size=(n0, 3)); p0 = rng.uniform(-2, 2, (n0, 3))
+    F = dict(keylines_un=kl0, line_functions=lv0, ldesc=d0, lines3d=np.concatenate([p0 + dirs0, p0], 1), bounds=BOUNDS,
+             claimed=(rng.rand(n0) < 0.1), mapline=np.full(n0, -1, np.int32))
+    F['mapline'][F['claimed']] = -2
+    n_extra = 120
+    M = n1 + n_extra
+    jit = lambda a: (a + rng.normal(0, 1.0, len(a))).astype(np.float32)
+    ex = rng.uniform(-20, 660, (n_extra, 2)); ey = rng.uniform(-20, 500, (n_extra, 2))
+    MLs = dict(proj_x1=np.concatenate([jit(kl1['startPointX']), ex[:, 0]]).astype(np.float32), proj_y1=np.concatenate([jit(kl1['startPointY']), ey[:, 0]]).astype(np.float32),
+               proj_x2=np.concatenate([jit(kl1['endPointX']), ex[:, 1]]).astype(np.float32), proj_y2=np.concatenate([jit(kl1['endPointY']), ey[:, 1]]).astype(np.float32),
+               level=np.zeros(M, np.int32), view_cos=rng.uniform(0.99, 1.0, M).astype(np.float32), in_view=rng.rand(M) > 0.1, bad=rng.rand(M) < 0.05,
+               has_obs=rng.rand(M) > 0.25, desc=np.concatenate([d1, rng.randint(0, 256, (n_extra, 32)).astype(np.uint8)]))
+    mid0 = np.stack([(kl0['startPointX'] + kl0['endPointX']) / 2, (kl0['startPointY'] + kl0['endPointY']) / 2], 1)
+    midq = np.stack([(MLs['proj_x1'] + MLs['proj_x2']) / 2, (MLs['proj_y1'] + MLs['proj_y2']) / 2], 1)
+    near = np.argmin(((midq[:, None, :] - mid0[None, :, :]) ** 2).sum(-1), axis=1)
+    wv = dirs0[near] * rng.choice([-1.0, 1.0], (M, 1)) * rng.uniform(0.5, 2.0, (M, 1)) + rng.normal(0, 0.05, (M, 3))
+    rnd = rng.rand(M) < 0.2
+    wv[rnd] = rng.normal(size=(int(rnd.sum()), 3))
+    MLs['world_vector'] = wv
+    return F, MLs, kl1, d1
+
+
+def _check_line_search(hvo, synth, gpu):
+    _need_ref()
+    for seed, th in ((0, 1.0), (1, 3.0)):
+        F, MLs, _, _ = _line_scene(synth, seed)
+        rng = np.random.RandomState(200 + seed)
+        windows = [(rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(3, 40),
+                    rng.choice([0.998, 0.96, 0.5, 0.0])) for _ in range(40)]
+        ref = _ref(f'lines_map_{seed}', lambda: oracle.ref_line_search_by_projection(F, MLs, th, 0.95, windows))
+        if gpu:
+            lpm = hvo.LineProjectionMatcher()
+            lpm.set_frame(F['keylines_un'], F['line_functions'], F['ldesc'], F['lines3d'], *BOUNDS)
+            cnt, items = lpm.grid()
+            areas = [lpm.GetFeaturesInAreaForLine(*(np.float32(x) for x in w[:5]), TH=np.float32(w[5])) for w in windows]
+            lpm.close()
+        else:
+            cnt, items = oracle.line_grid_build(F['keylines_un'], BOUNDS)
+            areas = [oracle.line_features_in_area(F['keylines_un'], F['line_functions'], BOUNDS, *(np.float32(x) for x in w[:5]), TH=np.float32(w[5])) for w in windows]
+        assert np.array_equal(cnt, ref['grid'][0]) and np.array_equal(items, ref['grid'][1])
+        assert sum(len(a) for a in ref['areas']) > 50
+        for a, b in zip(areas, ref['areas']):
+            assert np.array_equal(a, b)
+        m = _lsd_matcher(hvo, gpu, 0.95)
+        nm, match = m.SearchByProjection(F, MLs, True, th)
+        assert nm == ref['nmatches'] and nm > 40
+        assert np.array_equal(F['mapline'], ref['assign'])
+
+
+def test_cpu_line_search_by_projection_equals_reference(hvo, synth):
+    _check_line_search(hvo, synth, gpu=False)
+
+
+@pytest.mark.gpu
+def test_gpu_line_search_by_projection_equals_reference(hvo, synth):
+    _check_line_search(hvo, synth, gpu=True)
+
+
+def _check_line_search_last(hvo, synth, gpu):
+    _need_ref()
+    for seed in (0, 1):
+        rng = np.random.RandomState(300 + seed)
+        F, MLs, kl1, d1 = _line_scene(synth, seed + 5)
+        n1 = len(kl1)
+        Last = dict(keylines=kl1, has_ml=rng.rand(n1) > 0.15, outlier=rng.rand(n1) < 0.1, has_obs=rng.rand(n1) > 0.25, in_frustum=rng.rand(n1) > 0.1,
+                    proj_x1=MLs['proj_x1'][:n1], proj_y1=MLs['proj_y1'][:n1], proj_x2=MLs['proj_x2'][:n1], proj_y2=MLs['proj_y2'][:n1],
+                    level=np.zeros(n1, np.int32), desc=d1)
+        ref = _ref(f'lines_last_{seed}', lambda: oracle.ref_line_search_by_projection_last(F, Last, 15.0))
+        sel = np.nonzero(Last['has_ml'] & ~Last['outlier'] & Last['in_frustum'])[0]
+        last = dict(proj_x1=Last['proj_x1'][sel], proj_y1=Last['proj_y1'][sel], proj_x2=Last['proj_x2'][sel], proj_y2=Last['proj_y2'][sel],
+                    keylines=kl1[sel], has_obs=Last['has_obs'][sel], desc=d1[sel])
+        m = _lsd_matcher(hvo, gpu, 0.95)
+        nm, match = m.SearchByProjectionLast(F, last, 15.0)
+        got = F['mapline'].copy()
+        got[got >= 0] = sel[got[got >= 0]]
+        assert nm == ref['nmatches'] and nm > 40
+        assert np.array_equal(got, ref['assign'])
+
+
+def test_cpu_line_search_last_frame_equals_reference(hvo, synth):
+    _check_line_search_last(hvo, synth, gpu=False)
+
+
+@pytest.mark.gpu
+def test_gpu_line_search_last_frame_equals_reference(hvo, synth):
+    _check_line_search_last(hvo, synth, gpu=True)
