@@ -36,7 +36,7 @@ class _OrbParams(C.Structure):
 
 
 class _RgbdParams(C.Structure):
-    _fields_ = [('depth_factor', C.c_float), ('bf', C.c_float)]
+    _fields_ = [('depth_factor', C.c_float), ('bf', C.c_float), ('distorted', C.c_int)]
 
 
 _lib = None
@@ -60,6 +60,7 @@ ABI = {
     'hvo_orb_set_profiling': (C.c_int, [_vp, C.c_int]),
     'hvo_orb_stage_times': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_orb_last_launches': (C.c_int, [_vp]),
+    'hvo_stereo_uright_from_depth': (C.c_int, [_vp, _vp, C.c_int, C.c_float, _vp]),
     'hvo_orb_level_size': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_orb_get_pyramid_level': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t]),
     'hvo_orb_get_candidates': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
@@ -303,9 +304,10 @@ class ORBextractor:
         return kps[:n.value].copy(), desc[:n.value].copy()
 
     # -- batched host path ----------------------------------------------------------------------------
-    def extract_batch(self, frames, depth16=None, depth_factor=None, bf=None, out=None):
+    def extract_batch(self, frames, depth16=None, depth_factor=None, bf=None, out=None, distorted=False):
         """frames [n,h,w] uint8 (host; pinned memory makes the copies asynchronous).  Returns
-        dict(counts, kps [n,cap], desc [n,cap,32], depth, uright)."""
+        dict(counts, kps [n,cap], desc [n,cap,32], depth, uright).  distorted: the camera has k1 != 0, so mvuRight needs the
+        undistorted keypoints (Frame.cc:1944): uright comes back as -1, form it with stereo_uright_from_depth()."""
         assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
         n, h, w = frames.shape
         self._ensure(w, h)
@@ -318,17 +320,27 @@ class ORBextractor:
         rg = None
         if depth16 is not None:
             assert depth16.dtype == np.uint16 and depth16.shape == frames.shape and depth16.flags.c_contiguous
-            rg = C.byref(_RgbdParams(float(depth_factor), float(bf)))
+            rg = C.byref(_RgbdParams(float(depth_factor), float(bf), int(bool(distorted))))
         _check(lib().hvo_orb_extract_batch(self._h, _np_ptr(frames), n, _np_ptr(out['kps']), _np_ptr(out['desc']),
                                            _np_ptr(out['counts']), _np_ptr(depth16) if depth16 is not None else None, rg,
                                            _np_ptr(out['depth']) if depth16 is not None else None,
                                            _np_ptr(out['uright']) if depth16 is not None else None))
         return out
 
+    @staticmethod
+    def stereo_uright_from_depth(keys_un, kp_depth, bf):
+        """mvuRight of a distorted camera (second half of Frame::ComputeStereoFromRGBD, Frame.cc:1953-1958): keys_un = the keypoints
+        after Frame::UndistortKeyPoints, kp_depth = the device's mvDepth."""
+        k = np.ascontiguousarray(keys_un, KP_DTYPE)
+        d = np.ascontiguousarray(kp_depth, np.float32)
+        out = np.empty(len(k), np.float32)
+        _check(lib().hvo_stereo_uright_from_depth(_np_ptr(k), _np_ptr(d), len(k), float(bf), _np_ptr(out)))
+        return out
+
     # -- device-resident path (raw device pointers, e.g. torch tensor .data_ptr()) ---------------------
     def extract_batch_device(self, d_gray, nframes, d_kps, d_desc, d_counts, d_depth16=None, depth_factor=0.0, bf=0.0,
-                             d_kp_depth=None, d_kp_uright=None):
-        rg = C.byref(_RgbdParams(float(depth_factor), float(bf))) if d_depth16 else None
+                             d_kp_depth=None, d_kp_uright=None, distorted=False):
+        rg = C.byref(_RgbdParams(float(depth_factor), float(bf), int(bool(distorted)))) if d_depth16 else None
         _check(lib().hvo_orb_extract_batch_device(self._h, _vp(d_gray), nframes, _vp(d_kps), _vp(d_desc), _vp(d_counts),
                                                   _vp(d_depth16) if d_depth16 else None, rg,
                                                   _vp(d_kp_depth) if d_kp_depth else None,
@@ -1058,19 +1070,25 @@ class LSDmatcher:
         out = np.where(ok, m12, -1).astype(np.int32)
         return int(ok.sum()), out
 
-    def SearchByDescriptor(self, ldesc_kf, ldesc_cur):
-        """Matching part of LSDmatcher::SearchByDescriptor(pKF, currentF, ...) (src/LSDmatcher.cpp:522-559): knn-2 of the key
-        frame's descriptors in the current frame, accepted when d0 / d1 < 1 / 1.5.  Returns match [len(ldesc_cur)]: key-frame
-        line index per current-frame line (later queries overwrite earlier ones, as in the reference) or -1."""
+    def SearchByDescriptor(self, ldesc_kf, ldesc_cur, has_mapline=None):
+        """Matching part of LSDmatcher::SearchByDescriptor(pKF, currentF, vpMapLineMatches) (src/LSDmatcher.cpp:522-559): knn-2 of
+        the key frame's descriptors in the current frame, accepted when d0 / d1 < 1 / 1.5 AND the key-frame line holds a MapLine
+        (`if(mapLine)`, :549-553; has_mapline [len(ldesc_kf)] bool, default: all do).  Returns (nmatches, match [len(ldesc_cur)]):
+        key-frame line index per current-frame line or -1; a later accepted query overwrites an earlier one on the same
+        current-frame line, a query without a MapLine never does, and nmatches counts every accepted query, as in the reference."""
         out = np.full(len(ldesc_cur), -1, np.int32)
         if len(ldesc_kf) == 0 or len(ldesc_cur) < 2:
-            return out
+            return 0, out
+        has = np.ones(len(ldesc_kf), bool) if has_mapline is None else np.asarray(has_mapline, bool)
         idx, dist = self._bf.knnMatch2(ldesc_kf, ldesc_cur)
         with np.errstate(divide='ignore', invalid='ignore'):
             ratio = (dist[:, 0].astype(np.float32) / dist[:, 1].astype(np.float32)).astype(np.float64)
+        nmatches = 0
         for q in np.nonzero(ratio < np.float32(1.0) / np.float32(1.5))[0]:
-            out[idx[q, 0]] = q
-        return out
+            if has[q]:
+                out[idx[q, 0]] = q
+                nmatches += 1
+        return nmatches, out
 
 
 # ---- Frame-level front-end ----------------------------------------------------------------------------------------
@@ -1498,7 +1516,7 @@ class ORBmatcher:
 
 class _FrameParams(C.Structure):
     _fields_ = [('orb', _OrbParams), ('line', _LineParams), ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
-                ('depth_factor', C.c_float), ('bf', C.c_float), ('stages', C.c_int), ('max_planes', C.c_int), ('line_cull', C.c_int),
+                ('depth_factor', C.c_float), ('bf', C.c_float), ('distorted', C.c_int), ('stages', C.c_int), ('max_planes', C.c_int), ('line_cull', C.c_int),
                 ('lanes', C.c_int)]
 
 
@@ -1513,13 +1531,14 @@ class FrameFrontEnd:
     FIELDS = [f[0] for f in _FrameOutputs._fields_]
 
     def __init__(self, width, height, fx, fy, cx, cy, depth_factor, bf=40.0, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
-                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False, lanes=0, membership='i32'):
+                 min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False, lanes=0, membership='i32',
+                 distorted=False):
         """membership: 'i32' (int32 labels, -1 = none), 'u8' (one byte per pixel, 255 = none: what a host caller needs to
         rebuild plane_vertices_) or 'both'.  The int32 image is always the device-side working image."""
         assert membership in ('i32', 'u8', 'both')
         self.membership_mode = membership
         prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
-                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, stages, max_planes, int(bool(line_cull)), int(lanes))
+                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, int(bool(distorted)), stages, max_planes, int(bool(line_cull)), int(lanes))
         out = _vp()
         _check(lib().hvo_frame_create(C.byref(prm), int(width), int(height), int(max_batch), int(device), C.byref(out)))
         self._h = out
@@ -1578,8 +1597,15 @@ class FrameFrontEnd:
         gray = np.ascontiguousarray(gray, np.uint8)
         depth16 = np.ascontiguousarray(depth16, np.uint16)
         n = len(gray)
+        if gray.ndim != 3 or gray.shape[1:] != (self.h, self.w) or depth16.shape != gray.shape:
+            raise HvoError(HVO_ERR_ARG, f'gray / depth16 must be [n, {self.h}, {self.w}] (got {gray.shape}, {depth16.shape})')
         if out is None:
             out = self.alloc_host(n)
+        else:   # the C side writes through raw pointers: every caller-supplied array must have the exact layout
+            for k, (shape, dt) in self.output_shapes(n, device=False).items():
+                a = out.get(k)
+                if a is None or a.shape != tuple(shape) or a.dtype != np.dtype(dt) or not a.flags.c_contiguous:
+                    raise HvoError(HVO_ERR_ARG, f'out[{k!r}] must be a C-contiguous {np.dtype(dt)} array of shape {tuple(shape)}')
         o = self._outputs({k: v.ctypes.data for k, v in out.items()})
         f = lib().hvo_frame_extract_batch if wait else lib().hvo_frame_extract_batch_async
         _check(f(self._h, _np_ptr(gray), _np_ptr(depth16), n, C.byref(o)))

@@ -43,6 +43,7 @@ using namespace hvo;
 
 namespace hvo {
 cudaStream_t orb_stream(hvo_orb* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+int* orb_error_flag(hvo_orb* h) { return h->d_err; }         // internal: frame.cu folds the device error flags into its own status
 }
 
 extern "C" {
@@ -255,6 +256,15 @@ int hvo_orb_stage_times(hvo_orb* h, float* ms5) {
     for (int i = 0; i < 5; ++i) HVO_CUDA(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
     return HVO_OK;
 }
+int hvo_stereo_uright_from_depth(const hvo_keypoint* keys_un, const float* kp_depth, int n, float bf, float* uright) {
+    HVO_CHECK_ARG(n >= 0 && (n == 0 || (keys_un && kp_depth && uright)), "null argument");
+    for (int i = 0; i < n; ++i) {
+        const float d = kp_depth[i];
+        uright[i] = d > 0.f ? keys_un[i].x - bf / d : -1.f;   // host code is built with -ffp-contract=off
+    }
+    return HVO_OK;
+}
+
 int hvo_orb_last_launches(const hvo_orb* h) { return h ? h->last_launches : 0; }
 
 int hvo_orb_level_size(const hvo_orb* h, int level, int* w, int* h_out) {

@@ -18,11 +18,29 @@ cudaStream_t orb_stream(hvo_orb* h);
 cudaStream_t line_stream(hvo_line* h);
 cudaStream_t plane_stream(hvo_plane* h);
 cudaStream_t normals_stream(hvo_normals* h);
+int* orb_error_flag(hvo_orb* h);
+const int* line_segment_counts(hvo_line* h);
+int line_segment_cap(hvo_line* h);
+const int32_t* plane_status(hvo_plane* h);
 }  // namespace hvo
 using namespace hvo;
 
 enum { ST_ORB = 1, ST_LINE = 2, ST_PLANE = 4, ST_NORMALS = 8 };
 static const int kMaxLanes = 8;
+
+// Device-side capacity faults of the pipelines (ORB quadtree arena, LSD segment buffer, plane refinement queue) are folded,
+// on the pipeline's own stream right after its kernels, into one sticky record per frame handle: fault[0] = lowest frame index
+// (within its call) that overflowed, fault[1] = OR of the pipeline codes.  hvo_frame_sync / hvo_frame_timer_stop /
+// hvo_frame_extract_batch read it back and return HVO_ERR_OVERFLOW ("reported, never silent", hvo_capi.h).
+enum { FAULT_ORB = 1, FAULT_LINE = 2, FAULT_PLANE = 4 };
+__global__ void k_frame_fold_status(const int* __restrict__ flags, int n, int stride_is_zero, int threshold, int base, int code, int* __restrict__ fault) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        if (flags[stride_is_zero ? 0 : f] > threshold) {
+            atomicMin(&fault[0], base + f);
+            atomicOr(&fault[1], code);
+        }
+    }
+}
 
 // One lane = an independent copy of the three pipelines (own handles, streams, scratch) for chunks of `cap` frames.
 struct FrameLane {
@@ -47,7 +65,11 @@ struct hvo_frame {
     cudaEvent_t fork = nullptr, tev[2] = {nullptr, nullptr};
     int orb_cap = 0, max_lines = 0, normals_count = 0, last_launches = 0;
     int last_lane = -1;  // lane of the most recent chunk: the next chunk's kernels start after its kernels
+    int* d_fault = nullptr;   // {first faulty frame, pipeline codes}, sticky until read
+    int* h_fault = nullptr;   // pinned copy
 };
+
+static const int kNoFault = 0x7fffffff;
 
 // rows [off, off + n) of every output array
 static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs& o, size_t off) {
@@ -74,7 +96,7 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
 // stream, record the lane's join events.  Launch order = placement order: the ordered (latency-bound) pipelines first.
 // `after`: lane whose kernels must have finished first (host API: chunks compute one after the other, so the ordered kernels
 // of two chunks never slow each other down, while the copies of the neighbouring chunks run beside the kernels).
-static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint8_t* d_gray, const uint16_t* d_depth, int n,
+static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint8_t* d_gray, const uint16_t* d_depth, int n, int base,
                        const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
     if (after == &L) after = nullptr;  // one lane: every pipeline stream is already in order behind its own previous chunk
@@ -94,7 +116,8 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         int st = o.membership8 ? hvo_plane_detect_batch_device_u8(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership, o.membership8)
                                : hvo_plane_detect_batch_device(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
         if (st != HVO_OK) return st;
-        *launches += hvo_plane_last_launches(L.plane);
+        *launches += hvo_plane_last_launches(L.plane) + 1;
+        k_frame_fold_status<<<(n + 255) / 256, 256, 0, s>>>(plane_status(L.plane), n, 0, 0, base, FAULT_PLANE, h->d_fault);
         HVO_CUDA(cudaEventRecord(L.cdone[2], s));
     }
     if (h->p.stages & ST_LINE) {
@@ -102,16 +125,19 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         if (int ws = wait_start(s)) return ws;
         int st = hvo_line_extract_batch_device(L.line, d_gray, n, o.keylines, o.line_desc, o.linevec3, o.line_counts);
         if (st != HVO_OK) return st;
-        *launches += hvo_line_last_launches(L.line);
+        *launches += hvo_line_last_launches(L.line) + 1;
+        k_frame_fold_status<<<(n + 255) / 256, 256, 0, s>>>(line_segment_counts(L.line), n, 0, line_segment_cap(L.line), base, FAULT_LINE, h->d_fault);
         HVO_CUDA(cudaEventRecord(L.cdone[1], s));
     }
     if (h->p.stages & ST_ORB) {
         cudaStream_t s = orb_stream(L.orb);
         if (int ws = wait_start(s)) return ws;
-        hvo_rgbd_params rg{h->p.depth_factor, h->p.bf};
+        hvo_rgbd_params rg{h->p.depth_factor, h->p.bf, h->p.distorted};
         int st = hvo_orb_extract_batch_device(L.orb, d_gray, n, o.kps, o.desc, o.kp_counts, d_depth, &rg, o.kp_depth, o.kp_uright);
         if (st != HVO_OK) return st;
-        *launches += hvo_orb_last_launches(L.orb);
+        *launches += hvo_orb_last_launches(L.orb) + 1;
+        k_frame_fold_status<<<1, 32, 0, s>>>(orb_error_flag(L.orb), 1, 1, 0, base, FAULT_ORB, h->d_fault);   // one flag per chunk
+        HVO_CUDA(cudaMemsetAsync(orb_error_flag(L.orb), 0, sizeof(int), s));
         HVO_CUDA(cudaEventRecord(L.cdone[0], s));
     }
     if (h->p.stages & ST_NORMALS) {
@@ -172,6 +198,21 @@ static int wait_joins(hvo_frame* h, cudaStream_t s, FrameLane& L) {
     for (int i = 0; i < 4; ++i)
         if (h->p.stages & (i == 0 ? ST_ORB : i == 1 ? ST_LINE : i == 2 ? ST_PLANE : ST_NORMALS)) HVO_CUDA(cudaStreamWaitEvent(s, L.join[i], 0));
     return HVO_OK;
+}
+
+// After the master stream has been synchronised: read the sticky fault record, reset it, report.
+static int frame_check_fault(hvo_frame* h) {
+    HVO_CUDA(cudaMemcpyAsync(h->h_fault, h->d_fault, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_fault[1] == 0) return HVO_OK;
+    const int frame = h->h_fault[0], code = h->h_fault[1];
+    h->h_fault[0] = kNoFault; h->h_fault[1] = 0;
+    HVO_CUDA(cudaMemcpyAsync(h->d_fault, h->h_fault, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));
+    set_error("device-side capacity overflow in frame %d of its call:%s%s%s (the outputs of that frame are truncated)", frame,
+              (code & FAULT_ORB) ? " ORB quadtree arena" : "", (code & FAULT_LINE) ? " LSD segment buffer" : "",
+              (code & FAULT_PLANE) ? " plane refinement queue" : "");
+    return HVO_ERR_OVERFLOW;
 }
 
 extern "C" {
@@ -236,6 +277,10 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
         HVO_TRY(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
         for (auto& e : h->tev) HVO_TRY(cudaEventCreate(&e));
         if (st != HVO_OK) break;
+        HVO_TRY(cudaMalloc(&h->d_fault, 2 * sizeof(int)));
+        HVO_TRY(cudaHostAlloc(&h->h_fault, 2 * sizeof(int), cudaHostAllocDefault));
+        h->h_fault[0] = kNoFault; h->h_fault[1] = 0;
+        HVO_TRY(cudaMemcpy(h->d_fault, h->h_fault, 2 * sizeof(int), cudaMemcpyHostToDevice));
         const size_t B = (size_t)cap, px = (size_t)width * height;
         for (int li = 0; li < nl && st == HVO_OK; ++li) {
             FrameLane& L = h->lane[li];
@@ -297,6 +342,8 @@ void hvo_frame_destroy(hvo_frame* h) {
         for (auto& e : L.cdone) if (e) cudaEventDestroy(e);
         if (L.up) cudaStreamDestroy(L.up);
     }
+    if (h->d_fault) cudaFree(h->d_fault);
+    if (h->h_fault) cudaFreeHost(h->h_fault);
     if (h->fork) cudaEventDestroy(h->fork);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -344,7 +391,7 @@ int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const ui
     for (int off = 0; off < nframes; off += per, ++used) {
         FrameLane& L = h->lane[used];
         const int n = std::min(per, nframes - off);
-        st = lane_launch(h, L, h->fork, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, outputs_at(h, *d_out, (size_t)off), nullptr, &launches,
+        st = lane_launch(h, L, h->fork, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, off, outputs_at(h, *d_out, (size_t)off), nullptr, &launches,
                          h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
         h->last_lane = used;
@@ -379,7 +426,7 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
         hvo_frame_outputs d = L.d_out;
         if (!out->membership8) d.membership8 = nullptr;
         const hvo_frame_outputs hostk = outputs_at(h, *out, (size_t)off);
-        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
+        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, off, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
         h->last_lane = k % h->nlanes;
     }
@@ -395,7 +442,7 @@ int hvo_frame_extract_batch(hvo_frame* h, const uint8_t* gray, const uint16_t* d
     const int st = hvo_frame_extract_batch_async(h, gray, depth16, nframes, out);
     if (st != HVO_OK) return st;
     HVO_CUDA(cudaStreamSynchronize(h->stream));
-    return HVO_OK;
+    return frame_check_fault(h);
 }
 
 int hvo_frame_last_launches(const hvo_frame* h) { return h ? h->last_launches : 0; }
@@ -403,7 +450,7 @@ int hvo_frame_sync(hvo_frame* h) {
     HVO_CHECK_ARG(h, "null handle");
     HVO_CUDA(cudaSetDevice(h->device));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
-    return HVO_OK;
+    return frame_check_fault(h);
 }
 int hvo_frame_timer_start(hvo_frame* h) {
     HVO_CHECK_ARG(h, "null handle");
@@ -417,7 +464,7 @@ int hvo_frame_timer_stop(hvo_frame* h, float* ms_out) {
     HVO_CUDA(cudaEventRecord(h->tev[1], h->stream));
     HVO_CUDA(cudaEventSynchronize(h->tev[1]));
     HVO_CUDA(cudaEventElapsedTime(ms_out, h->tev[0], h->tev[1]));
-    return HVO_OK;
+    return frame_check_fault(h);
 }
 
 }  // extern "C"

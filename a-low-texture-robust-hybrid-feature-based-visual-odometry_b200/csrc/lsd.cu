@@ -17,6 +17,7 @@
 //                   2-D line functions
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -972,6 +973,8 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
 
 namespace hvo {
 cudaStream_t line_stream(hvo_line* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+const int* line_segment_counts(hvo_line* h) { return h->d_nseg; }  // internal: > line_segment_cap means the segment buffer overflowed
+int line_segment_cap(hvo_line* h) { return h->seg_cap; }
 }
 
 extern "C" {
@@ -1000,6 +1003,8 @@ int hvo_line_create(const hvo_line_params* p, int width, int height, int max_bat
     const double log_nt = 5 * (std::log10((double)h->sw) + std::log10((double)h->sh)) / 2 + std::log10(11.0);
     h->min_reg_size = (int)(size_t)(-log_nt / std::log10(22.5 / 180));
     h->seg_cap = ((h->sw - 1) * (h->sh - 1)) / (h->min_reg_size > 0 ? h->min_reg_size : 1) + 1;  // every segment owns >= min_reg_size pixels
+    // test aid: a smaller segment buffer, to provoke HVO_ERR_OVERFLOW (the bound above cannot be exceeded by construction)
+    if (const char* e = getenv("HVO_DEBUG_LINE_SEGCAP")) h->seg_cap = std::max(1, std::min(h->seg_cap, atoi(e)));
     std::vector<LinCoef> cx, cy;
     lsd_exact_coeffs(width, h->sw, 0.8, cx);
     lsd_exact_coeffs(height, h->sh, 0.8, cy);
@@ -1116,9 +1121,11 @@ int hvo_line_cull(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keyline* 
     HVO_CUDA(cudaMemcpyAsync(h->d_counts, &cnt_in, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     int st = line_cull_device(h, h->d_gray, 1, h->d_kl, h->d_desc, h->d_linevec, h->d_counts);
     if (st != HVO_OK) return st;
-    int32_t cnt = 0;
+    int32_t cnt = 0, nseg = 0;
     HVO_CUDA(cudaMemcpyAsync(&cnt, h->d_counts, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(&nseg, h->d_nseg, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
+    if (nseg > h->seg_cap) { set_error("LSD segment buffer overflow (%d segments, capacity %d)", nseg, h->seg_cap); return HVO_ERR_OVERFLOW; }
     if (cnt > 0) {
         HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, (size_t)cnt * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
         HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, h->stream));
@@ -1167,7 +1174,11 @@ int hvo_line_extract_batch(hvo_line* h, const uint8_t* gray, int nframes, hvo_ke
     HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, n * ml * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, n * ml * 32, cudaMemcpyDeviceToHost, h->stream));
     if (linevec3) HVO_CUDA(cudaMemcpyAsync(linevec3, h->d_linevec, n * ml * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> nseg(n);
+    HVO_CUDA(cudaMemcpyAsync(nseg.data(), h->d_nseg, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < nframes; ++f)
+        if (nseg[f] > h->seg_cap) { set_error("LSD segment buffer overflow in frame %d (%d segments, capacity %d)", f, nseg[f], h->seg_cap); return HVO_ERR_OVERFLOW; }
     return HVO_OK;
 }
 
@@ -1183,9 +1194,11 @@ int hvo_line_extract(hvo_line* h, const uint8_t* gray, size_t stride, hvo_keylin
     HVO_CUDA(cudaMemcpy2DAsync(h->d_gray, h->width, gray, stride, h->width, h->height, cudaMemcpyHostToDevice, h->stream));
     int st = line_extract_device(h, h->d_gray, 1, h->d_kl, h->d_desc, h->d_linevec, h->d_counts);
     if (st != HVO_OK) return st;
-    int32_t cnt = 0;
+    int32_t cnt = 0, nseg = 0;
     HVO_CUDA(cudaMemcpyAsync(&cnt, h->d_counts, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpyAsync(&nseg, h->d_nseg, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
+    if (nseg > h->seg_cap) { set_error("LSD segment buffer overflow (%d segments, capacity %d)", nseg, h->seg_cap); return HVO_ERR_OVERFLOW; }
     if (cnt > 0) {
         HVO_CUDA(cudaMemcpyAsync(keylines, h->d_kl, (size_t)cnt * sizeof(KeyLineOut), cudaMemcpyDeviceToHost, h->stream));
         HVO_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, h->stream));

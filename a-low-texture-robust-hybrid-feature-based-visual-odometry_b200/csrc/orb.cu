@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
                                                               const int* __restrict__ on, hvo_keypoint* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int32_t* __restrict__ counts,
                                                               const uint16_t* __restrict__ depth16, float depth_factor,
-                                                              float bf, float* __restrict__ kp_depth,
+                                                              float bf, int distorted, float* __restrict__ kp_depth,
                                                               float* __restrict__ kp_uright) {
     __shared__ int8_t s_pat[1024];
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -804,7 +804,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
             const float d = __fmul_rn((float)depth16[((long long)f * g.height + v) * g.width + u], depth_factor);
             const bool ok = d > 0.f && d < 7.0f;
             kp_depth[o] = ok ? d : -1.f;
-            kp_uright[o] = ok ? __fsub_rn(x, __fdiv_rn(bf, d)) : -1.f;
+            // mvuRight = kpU.pt.x - bf / d needs the UNDISTORTED x (Frame.cc:1944, 1957): only formed here when mvKeysUn == mvKeys
+            kp_uright[o] = (ok && !distorted) ? __fsub_rn(x, __fdiv_rn(bf, d)) : -1.f;
         }
     }
 }
@@ -1065,7 +1066,7 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     timeline_mark(stream, "k_describe");
     k_describe<<<dim3(div_up(g.out_cap, kDescWarps), B), kDescWarps * 32, 0, stream>>>(
         g, src, d_blur, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
-        rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, d_kp_depth, d_kp_uright);
+        rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, rgbd_on ? rgbd->distorted : 0, d_kp_depth, d_kp_uright);
     ++launches;
     if (profiling) { HVO_CUDA(cudaEventRecord(ev[5], stream)); have_stage_times = true; }
     HVO_CUDA(cudaGetLastError());

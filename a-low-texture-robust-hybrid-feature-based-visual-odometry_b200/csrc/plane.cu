@@ -13,6 +13,7 @@
 //                    hits applied in queue order), the last merge and the final relabelling.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -1103,6 +1104,7 @@ struct hvo_plane {
 
 namespace hvo {
 cudaStream_t plane_stream(hvo_plane* h) { return h->stream; }  // internal: frame.cu chains the stages on events
+const int32_t* plane_status(hvo_plane* h) { return h->d_status; }    // internal: per frame, != 0 = refinement queue overflow
 }
 
 extern "C" {
@@ -1127,6 +1129,8 @@ int hvo_plane_create(const hvo_plane_params* p, int width, int height, int max_b
     HVO_CHECK_ARG(Nb <= kRowW * 1024, "too many 10x10 blocks (max 9216, i.e. 1280x720)");
     h->nw = (Nb + 31) / 32;
     h->qcap = 2 * width * height;
+    // test aid: a smaller refinement queue, to provoke HVO_ERR_OVERFLOW
+    if (const char* e = getenv("HVO_DEBUG_PLANE_QCAP")) h->qcap = std::max(64, std::min(h->qcap, atoi(e)));
     h->max_ext = Nb * 100 / kMinSupport + 2;
     h->cam.factor = (double)p->depth_factor; h->cam.fx = (double)p->fx; h->cam.fy = (double)p->fy;
     h->cam.rfx = 1.0 / h->cam.fx; h->cam.rfy = 1.0 / h->cam.fy;

@@ -61,11 +61,22 @@ typedef struct hvo_keypoint {
 } hvo_keypoint;
 
 /* Optional RGB-D epilogue = Frame::ComputeStereoFromRGBD (src/Frame.cc:1940-1961) fused after extraction.
- * depth is raw 16-bit (TUM: metres*5000); depth_factor = 1/DepthMapFactor (src/Tracking.cc:156-160). */
+ * depth is raw 16-bit (TUM: metres*5000); depth_factor = 1/DepthMapFactor (src/Tracking.cc:156-160).
+ * kp_depth (mvDepth) is sampled at the DISTORTED keypoint, as the reference does (Frame.cc:1948-1951), and is always valid.
+ * kp_uright (mvuRight) is kpU.pt.x - bf / d with kpU the UNDISTORTED keypoint (Frame.cc:1944, 1957).  Undistortion
+ * (Frame::UndistortKeyPoints, Frame.cc:1701-1731, cv::undistortPoints) stays on the host, so the device can form mvuRight only
+ * for a camera without distortion (mvKeysUn == mvKeys, Frame.cc:1703-1707): set `distorted` for any other camera (TUM1.yaml,
+ * TUM2.yaml, ICSL_LPVO.yaml have k1 != 0); kp_uright is then filled with -1 and the caller forms it after UndistortKeyPoints with
+ * hvo_stereo_uright_from_depth(). */
 typedef struct hvo_rgbd_params {
     float depth_factor; /* metres per raw unit, e.g. 1/5000 */
     float bf;           /* stereo baseline * fx (Camera.bf) */
+    int distorted;      /* != 0: Camera.k1 != 0, kp_uright is not formed on the device */
 } hvo_rgbd_params;
+
+/* mvuRight of a distorted camera, host side: uright[i] = keys_un[i].x - bf / kp_depth[i] where kp_depth[i] > 0, else -1
+ * (the second half of Frame::ComputeStereoFromRGBD, Frame.cc:1953-1958, on the undistorted keypoints). */
+int hvo_stereo_uright_from_depth(const hvo_keypoint* keys_un, const float* kp_depth, int n, float bf, float* uright);
 
 /* Create an extractor for frames of width x height, up to max_batch frames per call, on CUDA `device`. */
 int hvo_orb_create(const hvo_orb_params* params, int width, int height, int max_batch, int device, hvo_orb** out);
@@ -442,6 +453,7 @@ typedef struct hvo_frame_params {
     float fx, fy, cx, cy; /* Camera.* */
     float depth_factor;   /* 1 / DepthMapFactor */
     float bf;             /* Camera.bf */
+    int distorted;        /* != 0: Camera.k1 != 0 (see hvo_rgbd_params): kp_uright is filled with -1 */
     int stages;           /* HVO_STAGE_* bits */
     int max_planes;       /* rows of planes7 per frame */
     int line_cull;        /* != 0: Frame::cullingLine after the line extractor, as Frame::ExtractLSD does (src/Frame.cc:939) */

@@ -142,3 +142,77 @@ def test_gpu_frame_async_calls_overlap_and_equal_blocking(hvo, synth):
         _same_outputs(hvo, ref, o, 5)
         assert np.array_equal(o['membership8'], ref['membership8'])
     fe.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frame_reports_device_side_overflow(hvo, synth, monkeypatch):
+    """The pipelines' fixed-capacity buffers cannot overflow by construction; HVO_DEBUG_* shrinks two of them so that the
+    device-side fault flags fire.  hvo_frame_* must return HVO_ERR_OVERFLOW naming the frame and the pipeline, through
+    extract_batch, through a queued call + sync, and recover on the next call (the record is reset when read)."""
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 3, start=11)
+    flat = np.full((480, 640), 90, np.uint8)
+    gray[0] = flat                                            # frame 0 has no line segments: the first faulty frame is 1
+    # LSD segment buffer
+    monkeypatch.setenv('HVO_DEBUG_LINE_SEGCAP', '20')
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=3, stages=hvo.STAGE_LINES | hvo.STAGE_ORB)
+    monkeypatch.delenv('HVO_DEBUG_LINE_SEGCAP')
+    with pytest.raises(hvo.HvoError) as e:
+        fe.extract_batch(gray, depth)
+    assert e.value.status == hvo.HVO_ERR_OVERFLOW and 'frame 1' in str(e.value) and 'LSD segment buffer' in str(e.value)
+    out = fe.extract_batch(np.stack([flat] * 3), depth)      # no segments at all: no fault, and the old one does not linger
+    assert (out['line_counts'] == 0).all()
+    fe.extract_batch(gray, depth, wait=False)                 # queued call: the fault is reported by the sync
+    with pytest.raises(hvo.HvoError) as e:
+        fe.sync()
+    assert e.value.status == hvo.HVO_ERR_OVERFLOW
+    fe.close()
+    # the standalone line extractor reports it too
+    monkeypatch.setenv('HVO_DEBUG_LINE_SEGCAP', '20')
+    ex = hvo.LINEextractor(1, 1.2, 200, 0.125, width=640, height=480)
+    monkeypatch.delenv('HVO_DEBUG_LINE_SEGCAP')
+    with pytest.raises(hvo.HvoError) as e:
+        ex(gray[1])
+    assert e.value.status == hvo.HVO_ERR_OVERFLOW
+    ex.close()
+    # plane refinement queue
+    monkeypatch.setenv('HVO_DEBUG_PLANE_QCAP', '256')
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=3, stages=hvo.STAGE_PLANES)
+    monkeypatch.delenv('HVO_DEBUG_PLANE_QCAP')
+    with pytest.raises(hvo.HvoError) as e:
+        fe.extract_batch(gray, depth)
+    assert e.value.status == hvo.HVO_ERR_OVERFLOW and 'frame 0' in str(e.value) and 'plane refinement queue' in str(e.value)
+    fe.close()
+    # and with the real capacities the same frames are fine
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=3)
+    fe.extract_batch(gray, depth)
+    fe.close()
+
+
+@pytest.mark.gpu
+def test_gpu_rgbd_epilogue_of_a_distorted_camera(hvo, synth):
+    """TUM1.yaml has k1 != 0: mvuRight is kpU.pt.x - bf / d on the UNDISTORTED keypoint (Frame.cc:1944, 1957).  With `distorted`
+    the device leaves kp_uright at -1 and hvo_stereo_uright_from_depth forms it from cv::undistortPoints' output."""
+    cv2 = pytest.importorskip('cv2')
+    K = np.array([[517.306408, 0, 318.643040], [0, 516.469215, 255.313989], [0, 0, 1]], np.float32)      # Examples/RGB-D/TUM1.yaml
+    dist = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+    gray, depth = synth.sequence('S1', 2, start=3)
+    ex = hvo.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=2)
+    plain = ex.extract_batch(gray, depth16=depth, depth_factor=1.0 / 5000.0, bf=40.0)
+    out = ex.extract_batch(gray, depth16=depth, depth_factor=1.0 / 5000.0, bf=40.0, distorted=True)
+    assert np.array_equal(out['depth'], plain['depth'])                      # mvDepth is sampled at the distorted keypoint either way
+    for f in range(2):
+        n = int(out['counts'][f])
+        assert (out['uright'][f, :n] == -1).all()
+        kps = out['kps'][f, :n].copy()
+        pts = np.stack([kps['x'], kps['y']], 1).reshape(-1, 1, 2).astype(np.float32)
+        un = cv2.undistortPoints(pts, K, dist, None, K).reshape(-1, 2)    # Frame::UndistortKeyPoints (Frame.cc:1701-1731)
+        kun = kps.copy(); kun['x'] = un[:, 0]; kun['y'] = un[:, 1]
+        ur = hvo.ORBextractor.stereo_uright_from_depth(kun, out['depth'][f, :n], 40.0)
+        d = out['depth'][f, :n]
+        with np.errstate(divide='ignore'):
+            exp = np.where(d > 0, kun['x'] - np.float32(40.0) / d, np.float32(-1)).astype(np.float32)
+        assert np.array_equal(ur, exp)
+        moved = np.abs(kun['x'] - kps['x']) > 0.5
+        assert moved.any() and np.any(ur[moved & (d > 0)] != plain['uright'][f, :n][moved & (d > 0)])   # the distortion matters
+    ex.close()

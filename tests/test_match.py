@@ -105,13 +105,19 @@ def test_lsdmatcher_search_double_and_by_descriptor(hvo, synth):
     m21 = oracle.frame_bf_match(b, a, 0.95, 50)
     ref = np.array([j if j >= 0 and m21[j] == i else -1 for i, j in enumerate(m12)], np.int32)
     assert np.array_equal(lm, ref) and n == int((ref >= 0).sum()) and n > 50
-    got = m.SearchByDescriptor(a, b)
+    # two key-frame lines land on the same current-frame line; the second one holds no MapLine and must not overwrite the first
+    a = a.copy(); a[101] = a[100]
+    has = np.ones(len(a), bool); has[101] = False; has[::7] = False
+    nm, got = m.SearchByDescriptor(a, b, has)
     idx, dist = oracle.knn2(a, b)
     exp = np.full(len(b), -1, np.int32)
-    for q in range(len(a)):
-        if np.float32(dist[q, 0]) / np.float32(dist[q, 1]) < np.float32(1.0) / np.float32(1.5):
+    en = 0
+    for q in range(len(a)):   # src/LSDmatcher.cpp:541-556
+        if np.float32(dist[q, 0]) / np.float32(dist[q, 1]) < np.float32(1.0) / np.float32(1.5) and has[q]:
             exp[idx[q, 0]] = q
-    assert np.array_equal(got, exp) and (exp >= 0).sum() > 50
+            en += 1
+    assert np.array_equal(got, exp) and nm == en and (exp >= 0).sum() > 40
+    assert idx[100, 0] == idx[101, 0] and got[idx[100, 0]] in (100, -1) and got[idx[100, 0]] != 101
     assert m.SearchDouble(a[:0], b)[0] == 0
 
 
