@@ -61,6 +61,15 @@ ABI = {
     'hvo_orb_stage_times': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_orb_last_launches': (C.c_int, [_vp]),
     'hvo_stereo_uright_from_depth': (C.c_int, [_vp, _vp, C.c_int, C.c_float, _vp]),
+    'hvo_membership4_expand': (C.c_int, [_vp, C.c_int, _vp]),
+    'hvo_seq_create': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    'hvo_seq_destroy': (None, [_vp]),
+    'hvo_seq_devices': (C.c_int, [_vp]),
+    'hvo_seq_capacities': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'hvo_seq_shard': (None, [C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    'hvo_seq_extract': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'hvo_seq_last_ms': (C.c_float, [_vp]),
+    'hvo_normals3_expand': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     'hvo_orb_level_size': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_orb_get_pyramid_level': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t]),
     'hvo_orb_get_candidates': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
@@ -1522,7 +1531,7 @@ class _FrameParams(C.Structure):
 
 class _FrameOutputs(C.Structure):
     _fields_ = [(n, _vp) for n in ('kps', 'desc', 'kp_counts', 'kp_depth', 'kp_uright', 'keylines', 'line_desc', 'linevec3',
-                                   'line_counts', 'n_planes', 'planes7', 'membership', 'normals8', 'membership8')]
+                                   'line_counts', 'n_planes', 'planes7', 'membership', 'normals8', 'membership8', 'membership4', 'normals3')]
 
 
 class FrameFrontEnd:
@@ -1532,11 +1541,15 @@ class FrameFrontEnd:
 
     def __init__(self, width, height, fx, fy, cx, cy, depth_factor, bf=40.0, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
                  min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=16, max_batch=1, device=0, line_cull=False, lanes=0, membership='i32',
-                 distorted=False):
+                 distorted=False, normals='n8'):
         """membership: 'i32' (int32 labels, -1 = none), 'u8' (one byte per pixel, 255 = none: what a host caller needs to
-        rebuild plane_vertices_) or 'both'.  The int32 image is always the device-side working image."""
-        assert membership in ('i32', 'u8', 'both')
-        self.membership_mode = membership
+        rebuild plane_vertices_), 'both', or 'u4' (host calls only: two pixels per byte, 15 = none, max_planes <= 15; expand with
+        membership4_expand).  The int32 image is always the device-side working image.
+        normals: 'n8' (SurfaceNormal rows: normal, position, pixel) or 'n3' (host calls only: the normal alone; normals3_expand
+        rebuilds the rows from the depth image)."""
+        assert membership in ('i32', 'u8', 'both', 'u4') and normals in ('n8', 'n3')
+        self.membership_mode, self.normals_mode = membership, normals
+        self.cam = (float(fx), float(fy), float(cx), float(cy), float(np.float32(depth_factor)))
         prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
                            fx, fy, cx, cy, float(np.float32(depth_factor)), bf, int(bool(distorted)), stages, max_planes, int(bool(line_cull)), int(lanes))
         out = _vp()
@@ -1574,13 +1587,37 @@ class FrameFrontEnd:
                       line_counts=((n,), np.int32))
         if self.stages & STAGE_PLANES:
             sh.update(n_planes=((n,), np.int32), planes7=((n, self.max_planes, 7), np.float64))
-            if device or self.membership_mode != 'u8':
+            if device or self.membership_mode in ('i32', 'both'):
                 sh.update(membership=((n, self.h * self.w), np.int32))
-            if self.membership_mode != 'i32':
+            if self.membership_mode in ('u8', 'both') or (device and self.membership_mode == 'u4'):
                 sh.update(membership8=((n, self.h * self.w), np.uint8))
+            if self.membership_mode == 'u4' and not device:
+                sh.update(membership4=((n, self.h * self.w // 2), np.uint8))
         if self.stages & STAGE_NORMALS:
-            sh.update(normals8=((n, self.normals_count, 8), np.float32))
+            if device or self.normals_mode == 'n8':
+                sh.update(normals8=((n, self.normals_count, 8), np.float32))
+            else:
+                sh.update(normals3=((n, self.normals_count, 3), np.float32))
         return sh
+
+    @staticmethod
+    def membership4_expand(labels4):
+        """[.., H*W/2] uint8 -> [.., H*W] int32 labels (-1 = none): hvo_membership4_expand."""
+        a = np.ascontiguousarray(labels4, np.uint8)
+        out = np.empty(a.shape[:-1] + (a.shape[-1] * 2,), np.int32)
+        for i in range(int(np.prod(a.shape[:-1], dtype=np.int64))):
+            _check(lib().hvo_membership4_expand(_vp(a.reshape(-1, a.shape[-1])[i].ctypes.data), a.shape[-1] * 2,
+                                                _vp(out.reshape(-1, out.shape[-1])[i].ctypes.data)))
+        return out
+
+    def normals3_expand(self, normals3, depth16):
+        """normals3 [count,3] of one frame + its raw depth -> normals8 [count,8] (hvo_normals3_expand)."""
+        n3 = np.ascontiguousarray(normals3, np.float32)
+        d = np.ascontiguousarray(depth16, np.uint16)
+        out = np.empty((len(n3), 8), np.float32)
+        fx, fy, cx, cy, df = self.cam
+        _check(lib().hvo_normals3_expand(_np_ptr(n3), _np_ptr(d), self.w, self.h, fx, fy, cx, cy, df, _np_ptr(out)))
+        return out
 
     def alloc_host(self, n):
         return {k: np.empty(s, d) for k, (s, d) in self.output_shapes(n, device=False).items()}
@@ -1629,3 +1666,55 @@ class FrameFrontEnd:
         ms = C.c_float(0)
         _check(lib().hvo_frame_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+
+class FrameSequence(FrameFrontEnd):
+    """Offline sequences on several GPUs of one box from one process (hvo_seq_*): the frames of a call are partitioned across
+    `devices` in contiguous ranges, one host thread + one frame handle per device, every device writes its rows of the caller's host
+    arrays.  No NCCL.  The Python mirror of a loop of Frame constructions over a recorded sequence."""
+
+    def __init__(self, width, height, fx, fy, cx, cy, depth_factor, devices, frames_per_call=2368, bf=40.0, nfeatures=1000, scale_factor=1.2,
+                 nlevels=8, ini_th=20, min_th=7, n_lines=200, stages=STAGE_ALL, max_planes=15, line_cull=True, lanes=0, membership='u4',
+                 normals='n3', distorted=False):
+        assert membership in ('i32', 'u8', 'both', 'u4') and normals in ('n8', 'n3')
+        self.membership_mode, self.normals_mode = membership, normals
+        self.cam = (float(fx), float(fy), float(cx), float(cy), float(np.float32(depth_factor)))
+        prm = _FrameParams(_OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th), _LineParams(1, 1.2, n_lines, 0.125),
+                           fx, fy, cx, cy, float(np.float32(depth_factor)), bf, int(bool(distorted)), stages, max_planes, int(bool(line_cull)), int(lanes))
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        out = _vp()
+        _check(lib().hvo_seq_create(C.byref(prm), int(width), int(height), dev, len(devices), int(frames_per_call), C.byref(out)))
+        self._h = None          # not a frame handle: FrameFrontEnd.close() must not touch it
+        self._seq = out
+        self.devices = list(devices)
+        self.w, self.h, self.max_batch, self.stages, self.max_planes = int(width), int(height), int(frames_per_call), stages, max_planes
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().hvo_seq_capacities(out, C.byref(a), C.byref(b), C.byref(c)))
+        self.orb_capacity, self.max_lines, self.normals_count = a.value, b.value, c.value
+
+    def close(self):
+        if getattr(self, '_seq', None):
+            lib().hvo_seq_destroy(self._seq)
+            self._seq = None
+
+    @staticmethod
+    def shard(nframes, ndevices, d):
+        a, b = C.c_int(0), C.c_int(0)
+        lib().hvo_seq_shard(int(nframes), int(ndevices), int(d), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def extract(self, gray, depth16, out=None):
+        """gray [n,h,w] uint8, depth16 [n,h,w] uint16 (host, ideally pinned) -> dict of host arrays in frame order."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth16 = np.ascontiguousarray(depth16, np.uint16)
+        n = len(gray)
+        if gray.ndim != 3 or gray.shape[1:] != (self.h, self.w) or depth16.shape != gray.shape:
+            raise HvoError(HVO_ERR_ARG, f'gray / depth16 must be [n, {self.h}, {self.w}]')
+        if out is None:
+            out = self.alloc_host(n)
+        o = self._outputs({k: v.ctypes.data for k, v in out.items()})
+        _check(lib().hvo_seq_extract(self._seq, _np_ptr(gray), _np_ptr(depth16), n, C.byref(o)))
+        return out
+
+    def last_ms(self):
+        return float(lib().hvo_seq_last_ms(self._seq))

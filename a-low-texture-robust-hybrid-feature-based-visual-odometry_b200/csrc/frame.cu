@@ -42,6 +42,30 @@ __global__ void k_frame_fold_status(const int* __restrict__ flags, int n, int st
     }
 }
 
+// Compact host outputs: 4-bit plane labels and normal-only surface normals, packed on the device before the download.
+__global__ void k_pack_membership4(const uint8_t* __restrict__ m8, uint8_t* __restrict__ m4, long long npairs8) {
+    // 16 labels in, 8 bytes out per thread
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4*>(m8)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // bytes b0 b1 b2 b3 (255 -> 15) -> two output bytes (b0 | b1 << 4), (b2 | b3 << 4)
+            const uint32_t n = w[k] & 0x0f0f0f0fu;                      // 255 & 15 = 15 = none; labels are < 15
+            const uint32_t packed = (n & 0xfu) | ((n >> 4) & 0xf0u) | ((n >> 8) & 0xf00u) | ((n >> 12) & 0xf000u);
+            o[k >> 1] |= packed << (16 * (k & 1));
+        }
+        reinterpret_cast<uint2*>(m4)[i] = make_uint2(o[0], o[1]);
+    }
+}
+__global__ void k_pack_normals3(const float* __restrict__ n8, float* __restrict__ n3, long long rows) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(n8)[2 * i];
+        n3[3 * i] = v.x; n3[3 * i + 1] = v.y; n3[3 * i + 2] = v.z;
+    }
+}
+
 // One lane = an independent copy of the three pipelines (own handles, streams, scratch) for chunks of `cap` frames.
 struct FrameLane {
     int cap = 0;
@@ -65,6 +89,7 @@ struct hvo_frame {
     cudaEvent_t fork = nullptr, tev[2] = {nullptr, nullptr};
     int orb_cap = 0, max_lines = 0, normals_count = 0, last_launches = 0;
     int last_lane = -1;  // lane of the most recent chunk: the next chunk's kernels start after its kernels
+    int next_lane = 0;   // host API: lane of the next chunk (round-robin across calls)
     int* d_fault = nullptr;   // {first faulty frame, pipeline codes}, sticky until read
     int* h_fault = nullptr;   // pinned copy
 };
@@ -88,7 +113,9 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
     if (o.planes7) r.planes7 = o.planes7 + off * (size_t)h->p.max_planes * 7;
     if (o.membership) r.membership = o.membership + off * px;
     if (o.membership8) r.membership8 = o.membership8 + off * px;
+    if (o.membership4) r.membership4 = o.membership4 + off * (px / 2);
     if (o.normals8) r.normals8 = o.normals8 + off * (size_t)h->normals_count * 8;
+    if (o.normals3) r.normals3 = o.normals3 + off * (size_t)h->normals_count * 3;
     return r;
 }
 
@@ -117,6 +144,11 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
                                : hvo_plane_detect_batch_device(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
         if (st != HVO_OK) return st;
         *launches += hvo_plane_last_launches(L.plane) + 1;
+        if (o.membership4 && o.membership8) {
+            const long long n16 = (long long)(N * px / 16);
+            k_pack_membership4<<<(int)std::min<long long>((n16 + 255) / 256, 148 * 16), 256, 0, s>>>(o.membership8, o.membership4, n16);
+            ++*launches;
+        }
         k_frame_fold_status<<<(n + 255) / 256, 256, 0, s>>>(plane_status(L.plane), n, 0, 0, base, FAULT_PLANE, h->d_fault);
         HVO_CUDA(cudaEventRecord(L.cdone[2], s));
     }
@@ -146,12 +178,18 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         int st = hvo_normals_compute_batch_device(L.normals, d_depth, n, o.normals8);
         if (st != HVO_OK) return st;
         *launches += 5;
+        if (o.normals3) {
+            const long long rows = (long long)(N * (size_t)h->normals_count);
+            k_pack_normals3<<<(int)std::min<long long>((rows + 255) / 256, 148 * 16), 256, 0, s>>>(o.normals8, o.normals3, rows);
+            ++*launches;
+        }
         HVO_CUDA(cudaEventRecord(L.cdone[3], s));
     }
     // ---- phase 2: results back to the host on each pipeline's own stream (shortest pipelines first), then the join events ----
     if (h->p.stages & ST_NORMALS) {
         cudaStream_t s = normals_stream(L.normals);
-        if (host) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
+        if (host && host->normals8) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
+        if (host && host->normals3) HVO_CUDA(cudaMemcpyAsync(host->normals3, o.normals3, N * (size_t)h->normals_count * 12, cudaMemcpyDeviceToHost, s));
         timeline_mark(s, "end_normals");
         HVO_CUDA(cudaEventRecord(L.join[3], s));
     }
@@ -187,6 +225,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
             HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
             if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
             if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
+            if (host->membership4) HVO_CUDA(cudaMemcpyAsync(host->membership4, o.membership4, N * (px / 2), cudaMemcpyDeviceToHost, s));
         }
         timeline_mark(s, "end_planes");
         HVO_CUDA(cudaEventRecord(L.join[2], s));
@@ -216,6 +255,34 @@ static int frame_check_fault(hvo_frame* h) {
 }
 
 extern "C" {
+
+int hvo_membership4_expand(const uint8_t* labels4, int npixels, int32_t* labels) {
+    HVO_CHECK_ARG(labels4 && labels && npixels >= 0 && (npixels & 1) == 0, "bad argument");
+    for (int i = 0; i < npixels / 2; ++i) {
+        const int a = labels4[i] & 15, b = labels4[i] >> 4;
+        labels[2 * i] = a == 15 ? -1 : a;
+        labels[2 * i + 1] = b == 15 ? -1 : b;
+    }
+    return HVO_OK;
+}
+
+int hvo_normals3_expand(const float* normals3, const uint16_t* depth16, int width, int height, float fx, float fy, float cx, float cy,
+                        float depth_factor, float* normals8) {
+    HVO_CHECK_ARG(normals3 && depth16 && normals8 && width > 0 && height > 0, "bad argument");
+    const int cw = (width + 2) / 3, ch = (height + 2) / 3, ow = cw / 2, oh = ch / 2;
+    for (int i = 0; i < ow * oh; ++i) {
+        const int m = 2 * (i / ow) + 1, n = 2 * (i % ow) + 1;
+        // the subsampled cloud of Frame::ComputePlanes (Frame.cc:2158-2171), float arithmetic as on the device (no FMA)
+        const float z = (float)depth16[(size_t)(3 * m) * width + 3 * n] * depth_factor;
+        float* o = normals8 + (size_t)i * 8;
+        o[0] = normals3[3 * i]; o[1] = normals3[3 * i + 1]; o[2] = normals3[3 * i + 2];
+        o[3] = ((float)(3 * n) - cx) * z / fx;
+        o[4] = ((float)(3 * m) - cy) * z / fy;
+        o[5] = z;
+        o[6] = (float)(n * 3); o[7] = (float)(m * 3);
+    }
+    return HVO_OK;
+}
 
 int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_batch, int device, hvo_frame** out) {
     HVO_CHECK_ARG(out, "null out");
@@ -313,8 +380,12 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
                 HVO_TRY(cudaMalloc(&o.planes7, B * (size_t)p->max_planes * 56));
                 HVO_TRY(cudaMalloc(&o.membership, B * px * 4));
                 HVO_TRY(cudaMalloc(&o.membership8, B * px));
+                HVO_TRY(cudaMalloc(&o.membership4, B * (px / 2) + 16));
             }
-            if (L.normals) HVO_TRY(cudaMalloc(&o.normals8, B * (size_t)h->normals_count * 32));
+            if (L.normals) {
+                HVO_TRY(cudaMalloc(&o.normals8, B * (size_t)h->normals_count * 32));
+                HVO_TRY(cudaMalloc(&o.normals3, B * (size_t)h->normals_count * 12));
+            }
         }
 #undef HVO_TRY
     } while (0);
@@ -335,7 +406,7 @@ void hvo_frame_destroy(hvo_frame* h) {
         if (L.normals) hvo_normals_destroy(L.normals);
         hvo_frame_outputs& o = L.d_out;
         void* bufs[] = {L.d_gray, L.d_depth, o.kps, o.desc, o.kp_counts, o.kp_depth, o.kp_uright, o.keylines, o.line_desc, o.linevec3,
-                        o.line_counts, o.n_planes, o.planes7, o.membership, o.membership8, o.normals8};
+                        o.line_counts, o.n_planes, o.planes7, o.membership, o.membership8, o.normals8, o.membership4, o.normals3};
         for (void* b : bufs) if (b) cudaFree(b);
         if (L.fork) cudaEventDestroy(L.fork);
         for (auto& e : L.join) if (e) cudaEventDestroy(e);
@@ -369,8 +440,13 @@ static int frame_check_outputs(const hvo_frame* h, const hvo_frame_outputs* o, b
     HVO_CHECK_ARG(o, "null outputs");
     if (h->p.stages & ST_ORB) HVO_CHECK_ARG(o->kps && o->desc && o->kp_counts, "ORB outputs missing");
     if (h->p.stages & ST_LINE) HVO_CHECK_ARG(o->keylines && o->line_desc && o->line_counts, "line outputs missing");
-    if (h->p.stages & ST_PLANE) HVO_CHECK_ARG(o->n_planes && o->planes7 && (o->membership || (!device && o->membership8)), "plane outputs missing");
-    if (h->p.stages & ST_NORMALS) HVO_CHECK_ARG(o->normals8, "normals output missing");
+    if (h->p.stages & ST_PLANE) HVO_CHECK_ARG(o->n_planes && o->planes7 && (o->membership || (!device && (o->membership8 || o->membership4))), "plane outputs missing");
+    if (h->p.stages & ST_NORMALS) HVO_CHECK_ARG(o->normals8 || (!device && o->normals3), "normals output missing");
+    if (o->membership4) {
+        HVO_CHECK_ARG(h->p.max_planes <= 15, "membership4 needs max_planes <= 15");
+        HVO_CHECK_ARG(((size_t)h->width * h->height) % 16 == 0, "membership4 needs width * height divisible by 16");
+        if (device) HVO_CHECK_ARG(o->membership8, "membership4 on the device needs membership8 as well");
+    }
     return HVO_OK;
 }
 
@@ -387,7 +463,10 @@ int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const ui
     int launches = 0, used = 0;
     // the batch is spread evenly over the lanes; the chunks compute one after the other (measured: two chunks whose ordered
     // kernels overlap are slower than the same chunks back to back)
-    const int per = (nframes + h->nlanes - 1) / h->nlanes;
+    // as few chunks as the lane capacity allows, of equal size (the ordered kernels are latency-bound: one warp / CTA per frame, so
+    // a chunk of 1024 is faster than two of 512)
+    const int nchunks = (nframes + h->lane[0].cap - 1) / h->lane[0].cap;
+    const int per = (nframes + nchunks - 1) / nchunks;
     for (int off = 0; off < nframes; off += per, ++used) {
         FrameLane& L = h->lane[used];
         const int n = std::min(per, nframes - off);
@@ -411,12 +490,18 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
     if (st != HVO_OK) return st;
     HVO_CUDA(cudaSetDevice(h->device));
     const size_t px = (size_t)h->width * h->height;
-    // chunk size: the lane capacity, or less when the batch is small so every lane gets work
+    // chunks: as few as the lane capacity allows, of equal size.  Chunks go round-robin through the lanes ACROSS calls
+    // (next_lane), so that the upload of a one-chunk call overlaps the kernels of the previous call on the other lane.
     const int cap = h->lane[0].cap;
-    const int per = std::min(cap, (nframes + h->nlanes - 1) / h->nlanes);
+    const int nchunks = (nframes + cap - 1) / cap;
+    const int per = (nframes + nchunks - 1) / nchunks;
     int launches = 0, k = 0;
+    bool lane_used[kMaxLanes] = {false};
     for (int off = 0; off < nframes; off += per, ++k) {
-        FrameLane& L = h->lane[k % h->nlanes];
+        const int li = h->next_lane;
+        h->next_lane = (h->next_lane + 1) % h->nlanes;
+        lane_used[li] = true;
+        FrameLane& L = h->lane[li];
         const int n = std::min(per, nframes - off);
         st = wait_joins(h, L.up, L);  // the lane's previous chunk (of this or an earlier call) must be done with the staging buffers
         if (st != HVO_OK) return st;
@@ -424,13 +509,16 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
         HVO_CUDA(cudaMemcpyAsync(L.d_depth, depth16 + (size_t)off * px, (size_t)n * px * 2, cudaMemcpyHostToDevice, L.up));
         HVO_CUDA(cudaEventRecord(L.fork, L.up));
         hvo_frame_outputs d = L.d_out;
-        if (!out->membership8) d.membership8 = nullptr;
+        if (!out->membership8 && !out->membership4) d.membership8 = nullptr;
+        if (!out->membership4) d.membership4 = nullptr;
+        if (!out->normals3) d.normals3 = nullptr;
         const hvo_frame_outputs hostk = outputs_at(h, *out, (size_t)off);
         st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, off, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
-        h->last_lane = k % h->nlanes;
+        h->last_lane = li;
     }
-    for (int li = 0; li < std::min(k, h->nlanes); ++li) {
+    for (int li = 0; li < h->nlanes; ++li) {
+        if (!lane_used[li]) continue;
         st = wait_joins(h, h->stream, h->lane[li]);
         if (st != HVO_OK) return st;
     }

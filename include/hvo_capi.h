@@ -479,7 +479,20 @@ typedef struct hvo_frame_outputs {
                                                      optional when membership8 is given           */
     float* normals8;       /* [n][normals_count][8]  std::vector<SurfaceNormal>                   */
     uint8_t* membership8;  /* [n][H*W]               the same labels in one byte (255 = none)     optional */
+    /* Compact forms for host callers (what goes over PCIe: 256 KB instead of 581 KB per 640x480 frame).  Optional.         */
+    uint8_t* membership4;  /* [n][H*W/2]             two pixels per byte (low nibble = even pixel), 15 = none; needs
+                                                     max_planes <= 15 and an even H*W.  hvo_membership4_expand() restores labels */
+    float* normals3;       /* [n][normals_count][3]  the normal only (NaN = none); position and pixel of a SurfaceNormal are
+                                                     functions of (m, n) and the depth: hvo_normals3_expand() restores normals8 */
 } hvo_frame_outputs;
+
+/* Host-side expanders of the compact outputs (plain C loops, no CUDA). */
+/* labels4 [H*W/2] -> labels [H*W] int32 (-1 = none) */
+int hvo_membership4_expand(const uint8_t* labels4, int npixels, int32_t* labels);
+/* normals3 [count][3] + the frame's raw depth -> normals8 [count][8] = normal, cameraPosition, FramePosition exactly as the device
+ * writes them (src/Frame.cc:2158-2171, 2191-2196): row i <-> cloud cell m = 2 (i / (cw/2)) + 1, n = 2 (i % (cw/2)) + 1, cw = ceil(W/3) */
+int hvo_normals3_expand(const float* normals3, const uint16_t* depth16, int width, int height, float fx, float fy, float cx, float cy,
+                        float depth_factor, float* normals8);
 
 typedef struct hvo_frame hvo_frame;
 int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_batch, int device, hvo_frame** out);
@@ -500,6 +513,26 @@ int hvo_frame_last_launches(const hvo_frame* h);
 int hvo_frame_sync(hvo_frame* h);
 int hvo_frame_timer_start(hvo_frame* h);
 int hvo_frame_timer_stop(hvo_frame* h, float* ms_out);
+
+/* ---------------------------------------------------------------------------------------------- SEQUENCE (several GPUs)
+ * Offline sequences (BASELINE config 5) on several GPUs of one box from ONE process: Frame construction has no cross-frame state
+ * (the extractors' members are scratch: mvImagePyramid, the LBD gradient images), so the frames [0, n) of a call are partitioned
+ * across the devices in contiguous ranges (hvo_seq_shard), each device gets one host thread driving one hvo_frame handle with its
+ * own streams, and every device writes its own rows of the caller's output arrays: the gather is the layout.  No NCCL, no
+ * collective.  gray / depth16 / outputs are HOST arrays of n frames (pinned memory makes the copies asynchronous); a device
+ * processes its range as queued calls of at most frames_per_call frames.  Replaces a loop of Frame::Frame(...) extractions over a
+ * recorded sequence (Examples/RGB-D/rgbd_tum.cc:86-152 without the tracking step).                                                  */
+typedef struct hvo_seq hvo_seq;
+int hvo_seq_create(const hvo_frame_params* p, int width, int height, const int* devices, int ndevices, int frames_per_call, hvo_seq** out);
+void hvo_seq_destroy(hvo_seq* s);
+int hvo_seq_devices(const hvo_seq* s);
+int hvo_seq_capacities(const hvo_seq* s, int* orb_capacity, int* max_lines, int* normals_count);
+/* the contiguous range of device d (of ndevices) in a call of nframes frames; sizes differ by at most one frame */
+void hvo_seq_shard(int nframes, int ndevices, int d, int* first, int* count);
+/* blocks until every output row has been written; a device-side fault or CUDA error of any device is returned with its device id */
+int hvo_seq_extract(hvo_seq* s, const uint8_t* gray, const uint16_t* depth16, int nframes, const hvo_frame_outputs* out);
+/* device time of the last hvo_seq_extract: CUDA events around each device's share (uploads, kernels, downloads), max over devices */
+float hvo_seq_last_ms(const hvo_seq* s);
 
 #ifdef __cplusplus
 }

@@ -216,3 +216,29 @@ def test_gpu_rgbd_epilogue_of_a_distorted_camera(hvo, synth):
         moved = np.abs(kun['x'] - kps['x']) > 0.5
         assert moved.any() and np.any(ur[moved & (d > 0)] != plain['uright'][f, :n][moved & (d > 0)])   # the distortion matters
     ex.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frame_compact_host_outputs(hvo, synth):
+    """membership4 (two pixels per byte) and normals3 (normal only) are the same results in 256 KB instead of 581 KB per frame:
+    expanded on the host they equal the full outputs bit for bit."""
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 3, start=60)
+    full = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=3, max_planes=15, membership='both')
+    a = full.extract_batch(gray, depth)
+    full.close()
+    fe = hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=3, max_planes=15, membership='u4', normals='n3')
+    b = fe.extract_batch(gray, depth)
+    assert 'membership' not in b and 'normals8' not in b and b['membership4'].shape == (3, 640 * 480 // 2)
+    assert np.array_equal(fe.membership4_expand(b['membership4']), a['membership'])
+    for f in range(3):
+        n8 = fe.normals3_expand(b['normals3'][f], depth[f])
+        assert n8.tobytes() == a['normals8'][f].tobytes()              # NaN rows included
+    assert np.array_equal(a['n_planes'], b['n_planes']) and np.array_equal(a['kp_counts'], b['kp_counts'])
+    for f in range(3):
+        n, nl, npl = int(a['kp_counts'][f]), int(a['line_counts'][f]), int(a['n_planes'][f])
+        assert a['kps'][f, :n].tobytes() == b['kps'][f, :n].tobytes() and np.array_equal(a['desc'][f, :n], b['desc'][f, :n])
+        assert a['keylines'][f, :nl].tobytes() == b['keylines'][f, :nl].tobytes() and np.array_equal(a['planes7'][f, :npl], b['planes7'][f, :npl])
+    fe.close()
+    with pytest.raises(hvo.HvoError):                                     # 16 planes do not fit 4 bits
+        hvo.FrameFrontEnd(640, 480, fx, fy, cx, cy, df, max_batch=1, max_planes=16, membership='u4').extract_batch(gray[:1], depth[:1])
