@@ -249,70 +249,28 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_strips(const __grid_const
     // ---- pass 1 + 2 ----
     // A 9-arc always contains ring point 0 or 8 and ring point 4 or 12, so a corner needs |v - ring| > t on one point of each
     // pair.  VABSDIFF4 is native; "byte > t" is the carry trick ((x & 0x7f) + (127 - t)) | x.
-    const int g0 = zb0 >> 2, g1 = (zb0 + zw - 1) >> 2, ng = g1 - g0 + 1;
-    const uint32_t magic = (1u << 20) / (uint32_t)ng + 1;  // i / ng for i < 2^15 (ng <= 1024)
+    // Survivors (byte flags in bit 7 of `flags`) are compacted into a warp-private queue with four ballots (no shuffles, no loop
+    // over the flags) and processed 32 at a time, so the expensive part runs on full warps without a CTA barrier in between.
+    const int g0 = zb0 >> 2, g1 = (zb0 + zw - 1) >> 2;
     const bool use_quick = low_th <= 127;
     const uint32_t K = (uint32_t)(127 - min(low_th, 127)) * 0x01010101u;
     uint32_t* q = s_queue[warp];
     int qh = 0, qn = 0;                                  // warp-uniform queue head / tail (monotonic)
-    const int ntot = ng * zh;
-    for (int ib = warp * 32; ib < ntot; ib += kFastThreads) {
-        const int i = ib + lane;
-        uint32_t maybe = 0;
-        int zy = 0, b0 = 0;
-        if (i < ntot) {
-            zy = (int)(((unsigned long long)(uint32_t)i * magic) >> 20);
-            if (zy * ng > i) --zy;
-            const int gi = g0 + (i - zy * ng);
-            const uint32_t* r0 = tile + (zy + 3) * tsw;
-            const uint32_t v4 = r0[gi];
-            b0 = 4 * gi;
-            maybe = 0x80808080u;
-            if (b0 < zb0) maybe &= 0xffffffffu << (8 * (zb0 - b0));
-            if (b0 + 3 > zb0 + zw - 1) maybe &= 0xffffffffu >> (8 * (b0 + 3 - (zb0 + zw - 1)));
-            if (use_quick) {
-                const uint32_t a0 = __vabsdiffu4(v4, (r0 + 3 * tsw)[gi]), a8 = __vabsdiffu4(v4, (r0 - 3 * tsw)[gi]);
-                const uint32_t a4 = __vabsdiffu4(v4, ring4(r0, gi, 3)), a12 = __vabsdiffu4(v4, ring4(r0, gi, -3));
-                const uint32_t m08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
-                const uint32_t m412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
-                maybe &= m08 & m412;
-            }
-        }
-        // warp-private compaction of the survivors
-        const int cnt = __popc(maybe);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        int slot = qn + incl - cnt;
-        while (maybe) {
-            const int j = (__ffs(maybe) - 1) >> 3;
-            maybe &= maybe - 1;
-            q[slot & (kFastQueue - 1)] = ((uint32_t)zy << 16) | (uint32_t)(b0 + j);
-            ++slot;
-        }
+    const unsigned lt = (1u << lane) - 1u;
+    auto enqueue = [&](uint32_t flags, uint32_t base_pos) -> bool {   // base_pos = zy << 16 | band column of byte 0
+        const unsigned m0 = __ballot_sync(0xffffffffu, flags & 0x80u), m1 = __ballot_sync(0xffffffffu, flags & 0x8000u);
+        const unsigned m2 = __ballot_sync(0xffffffffu, flags & 0x800000u), m3 = __ballot_sync(0xffffffffu, flags & 0x80000000u);
+        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), total = c0 + c1 + c2 + __popc(m3);
+        if (total == 0) return false;
+        if (flags & 0x80u) q[(qn + __popc(m0 & lt)) & (kFastQueue - 1)] = base_pos;
+        if (flags & 0x8000u) q[(qn + c0 + __popc(m1 & lt)) & (kFastQueue - 1)] = base_pos + 1;
+        if (flags & 0x800000u) q[(qn + c0 + c1 + __popc(m2 & lt)) & (kFastQueue - 1)] = base_pos + 2;
+        if (flags & 0x80000000u) q[(qn + c0 + c1 + c2 + __popc(m3 & lt)) & (kFastQueue - 1)] = base_pos + 3;
         qn += total;
         __syncwarp();
-        while (qn - qh >= 32) {
-            const uint32_t pos = q[(qh + lane) & (kFastQueue - 1)];
-            const int py = pos >> 16, px = pos & 0xffff;
-            const uint8_t* p = tile_b + (py + 3) * ts + px;
-            const int v = *p;
-            int d[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, ts, k);
-            const int sc = fast_strength(d);
-            if (sc >= low_th) score[(py + 1) * ts + px] = (uint8_t)sc;   // in [low_th, 254]; non-corners stay 0
-            qh += 32;
-        }
-        __syncwarp();
-    }
-    if (lane < qn - qh) {
-        const uint32_t pos = q[(qh + lane) & (kFastQueue - 1)];
+        return true;
+    };
+    auto strength_at = [&](uint32_t pos) {
         const int py = pos >> 16, px = pos & 0xffff;
         const uint8_t* p = tile_b + (py + 3) * ts + px;
         const int v = *p;
@@ -320,39 +278,80 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_strips(const __grid_const
 #pragma unroll
         for (int k = 0; k < 16; ++k) d[k] = v - (int)HVO_RING(p, ts, k);
         const int sc = fast_strength(d);
-        if (sc >= low_th) score[(py + 1) * ts + px] = (uint8_t)sc;
+        if (sc >= low_th) score[(py + 1) * ts + px] = (uint8_t)sc;   // in [low_th, 254]; non-corners stay 0
+    };
+    for (int zy = warp; zy < zh; zy += kFastWarps) {
+        const uint32_t* r0 = tile + (zy + 3) * tsw;
+        for (int gb = g0; gb <= g1; gb += 32) {
+            const int gi = gb + lane;
+            uint32_t maybe = 0;
+            if (gi <= g1) {
+                const uint32_t v4 = r0[gi];
+                const int b0 = 4 * gi;
+                maybe = 0x80808080u;
+                if (b0 < zb0) maybe &= 0xffffffffu << (8 * (zb0 - b0));
+                if (b0 + 3 > zb0 + zw - 1) maybe &= 0xffffffffu >> (8 * (b0 + 3 - (zb0 + zw - 1)));
+                if (use_quick) {
+                    const uint32_t a0 = __vabsdiffu4(v4, (r0 + 3 * tsw)[gi]), a8 = __vabsdiffu4(v4, (r0 - 3 * tsw)[gi]);
+                    const uint32_t a4 = __vabsdiffu4(v4, ring4(r0, gi, 3)), a12 = __vabsdiffu4(v4, ring4(r0, gi, -3));
+                    const uint32_t m08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
+                    const uint32_t m412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
+                    maybe &= m08 & m412;
+                }
+            }
+            if (!enqueue(maybe, ((uint32_t)zy << 16) | (uint32_t)(4 * gi))) continue;
+            while (qn - qh >= 32) {
+                strength_at(q[(qh + lane) & (kFastQueue - 1)]);
+                qh += 32;
+            }
+            __syncwarp();
+        }
     }
+    if (lane < qn - qh) strength_at(q[(qh + lane) & (kFastQueue - 1)]);
     __syncthreads();
 
-    // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the cell's zone counts as 0) ----
+    // ---- pass 3: cell-local non-max suppression (strict '>' on the 8 neighbours, outside the cell's zone counts as 0).  Same
+    //      skeleton: pixels with a score are compacted per warp and tested 32 at a time, branch-free (the guard rows / columns of
+    //      the score map are zero, so all 8 neighbours can always be read) ----
     const int wcell = c.wcell;
     const uint32_t cmagic = (1u << 20) / (uint32_t)wcell + 1;   // zx / wcell for zx < 2^12
     const uint32_t* score_w = reinterpret_cast<const uint32_t*>(score);
-    for (int i = tid; i < ntot; i += kFastThreads) {
-        int zy = (int)(((unsigned long long)(uint32_t)i * magic) >> 20);
-        if (zy * ng > i) --zy;
-        const int gi = g0 + (i - zy * ng);
-        uint32_t w = score_w[(zy + 1) * tsw + gi];
-        while (w) {
-            const int j = (__ffs(w) - 1) >> 3;
-            const int s = (w >> (8 * j)) & 0xff;
-            w &= ~(0xffu << (8 * j));
-            const int px = 4 * gi + j, zx = px - zb0;
-            int cj = (int)(((uint32_t)zx * cmagic) >> 20);
-            if (cj * wcell > zx) --cj;
-            const int cx = zx - cj * wcell;
-            const bool has_l = cx > 0, has_r = cx < wcell - 1 && zx < zw - 1;
-            const uint8_t* sp = score + (zy + 1) * ts + px;
-            bool is_max = s > (int)sp[-ts] && s > (int)sp[ts];
-            if (has_l) is_max = is_max && s > (int)sp[-ts - 1] && s > (int)sp[-1] && s > (int)sp[ts - 1];
-            if (has_r) is_max = is_max && s > (int)sp[-ts + 1] && s > (int)sp[1] && s > (int)sp[ts + 1];
-            if (is_max) {
-                if (s >= ini_th) atomicAdd(&s_nini[cj], 1);
-                if (s >= min_th) atomicAdd(&s_nmin[cj], 1);
-                list[atomicAdd(&s_nlist, 1)] = (uint32_t)(c.x0 + zx) | ((uint32_t)(c.y0 + zy) << 12) | ((uint32_t)s << 24);
+    qh = qn = 0;
+    auto nms_at = [&](uint32_t pos) {
+        const int zy = pos >> 16, px = pos & 0xffff, zx = px - zb0;
+        int cj = (int)(((uint32_t)zx * cmagic) >> 20);
+        if (cj * wcell > zx) --cj;
+        const int cx = zx - cj * wcell;
+        const uint8_t* sp = score + (zy + 1) * ts + px;
+        const int s = sp[0];
+        const int up = sp[-ts], dn = sp[ts];
+        const int l = max(max((int)sp[-ts - 1], (int)sp[-1]), (int)sp[ts - 1]);
+        const int r = max(max((int)sp[-ts + 1], (int)sp[1]), (int)sp[ts + 1]);
+        int m = max(up, dn);
+        m = max(m, cx > 0 ? l : 0);
+        m = max(m, (cx < wcell - 1 && zx < zw - 1) ? r : 0);
+        if (s > m) {
+            if (s >= ini_th) atomicAdd(&s_nini[cj], 1);
+            if (s >= min_th) atomicAdd(&s_nmin[cj], 1);
+            list[atomicAdd(&s_nlist, 1)] = (uint32_t)(c.x0 + zx) | ((uint32_t)(c.y0 + zy) << 12) | ((uint32_t)s << 24);
+        }
+    };
+    for (int zy = warp; zy < zh; zy += kFastWarps) {
+        const uint32_t* srow = score_w + (zy + 1) * tsw;
+        for (int gb = g0; gb <= g1; gb += 32) {
+            const int gi = gb + lane;
+            uint32_t w = gi <= g1 ? srow[gi] : 0u;
+            // byte != 0 -> bit 7 of that byte
+            w = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+            if (!enqueue(w, ((uint32_t)zy << 16) | (uint32_t)(4 * gi))) continue;
+            while (qn - qh >= 32) {
+                nms_at(q[(qh + lane) & (kFastQueue - 1)]);
+                qh += 32;
             }
+            __syncwarp();
         }
     }
+    if (lane < qn - qh) nms_at(q[(qh + lane) & (kFastQueue - 1)]);
     __syncthreads();
 
     // ---- emit: a cell that has a corner at ini_th keeps those, else the ones at min_th ----

@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py — front-end frames/s at 640x480 (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one batch of B synthetic TUM-fr3-shaped 640x480 RGB-D frames per
-GPU (config C1 of BASELINE.json).  Frames are independent, so ranks shard them with no data-path collective
-("scaling": "weak"); torch.distributed is used only for the barrier and the max-over-ranks of the time.
+A "step" is one pass of the hot path over the C5 sequence of BASELINE.json: 8192 synthetic TUM-fr3-shaped 640x480 RGB-D frames,
+frame-sharded across the N GPUs in contiguous ranges (8192 / N frames per GPU per step: "scaling": "strong").  Frames are
+independent, so there is no data-path collective; torch.distributed carries only the barrier and the max-over-ranks of the time.
+A GPU processes its share as calls of at most 2368 frames (2 chunks of 1184 = 8 frames per SM).
 
-  value  whole-job frames/s with the inputs already resident in HBM (CUDA events on the library's stream)
-  e2e    the same metric through the reference-facing C-ABI call with HOST (pinned) buffers: host->device
-         copy of gray+depth and device->host read of keypoints/descriptors inside the timed region
-  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section "Measurement"
+  value     whole-job frames/s with the inputs already resident in HBM (CUDA events on the library's master stream, max over ranks)
+  e2e       the same through the reference-facing C-ABI call with HOST (pinned) buffers: host->device copy of gray + depth and
+            device->host read of every output inside the timed region (compact outputs: 4-bit plane labels, normal-only normals)
+  weak      the round-1 line for comparison: every GPU processes 2368 frames per step, whatever N is
+  configs   sub-records for the other BASELINE.json configs: C2 (ICL-shaped low texture), C3 (1280x720, 2000 ORB), C4 (matching
+            stress 2000 x 50 000 ORB + 200 x 5 000 LBD with cv2.BFMatcher beside it)
+  roofline / cpu_baseline (throughput AND per-frame latency in the reference's 3-thread shape) / clocks / gpu_launches /
+  p50_latency_ms_single_frame: see DESIGN.md section "Measurement"
 
---impl reference times the reference's CPU implementation of the same path on the host cores: the oracle port
-(oracle/, a restatement that is bit-identical to the reference's own ORBextractor.cc compiled in oracle/_ref;
-the reference binary itself cannot be built: OpenCV/PCL/Eigen/Pangolin are absent from this image).
+--impl reference times the reference's CPU implementation of the same path on the host cores: the oracle port (oracle/), which is
+pinned by execution to the reference's own sources compiled in oracle/_ref (ORBextractor.cc, PlaneExtractor.cpp + peac, the vendored
+line_descriptor, Frame::cullingLine); the reference binary itself cannot be built (OpenCV / PCL / Eigen / Pangolin are absent).
 """
 import argparse
 import json
@@ -42,9 +47,13 @@ def emit(obj):
 
 
 METRIC = 'front-end frames/s @640x480'
+C5_FRAMES = 8192                                                               # BASELINE.json configs[4]
+CALL_FRAMES = 2368                                                             # frames per library call: 2 chunks of 1184 = 8 frames per SM
+CHUNK = 1184
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
 CAM = dict(fx=535.4, fy=539.2, cx=320.1, cy=247.6)                             # TUM3.yaml:8-11
 DEPTH_FACTOR, BF, NLINES = 1.0 / 5000.0, 40.0, 200                             # TUM3.yaml:34, Camera.bf, LINE.nFeatures
+MAX_PLANES = 15                                                                # rows of planes7 (4-bit labels on the wire)
 ORACLE_CAM = (DEPTH_FACTOR, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'])
 ORACLE_STAGES = 15 | 16  # ORB | lines | planes | normals | cullingLine after the line extractor (what Frame::Frame runs)
 STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + rBRIEF + RGB-D depth lookup',
@@ -53,11 +62,14 @@ STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + r
           'planes: depth back-projection + 10x10 block fits + AHC merging + block erosion + ordered pixel flood fill + last merge',
           'normals: 3x subsampled cloud + integral-image normals (PCL AVERAGE_3D_GRADIENT restatement)']
 # algorithmic bytes per 640x480 frame of the HBM-bound kernels
-ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_strips': 950532, 'k_describe': 1922000 + 60000,
+ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_strips': 950532, 'k_blur': 1901064, 'k_describe': 1922000 + 60000,
              'k_lsd_prep': 307200 + 16 * 512 * 384, 'k_plane_blocks': 614400 + 3072 * 96}
-# dram__bytes_read.sum + dram__bytes_write.sum per frame of the same kernels, from the committed ncu capture
-# profiles/r1c_launches_frontend_b1024.csv (batch 1024, summary in profiles/r1c_launch_summary.txt)
-NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_strips': 959000, 'k_describe': 2048000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
+# whole front-end: ORB 6 403 474 + LBD pre 2 150 400 + LBD gather 2 x 3 024 000 + LSD 3 452 928 + seed order / regions 2 359 296 +
+# planes 909 312 + membership 1 536 000 + normals 2 054 400
+ALG_BYTES_FRAME = 6403474 + 2150400 + 2 * 3024000 + 3452928 + 2359296 + 909312 + 1536000 + 2054400
+# dram__bytes_read.sum + dram__bytes_write.sum per frame of the same kernels, from this round's committed ncu capture
+# (profiles/r2_ncu_full_orb_kernels_b296.csv for the ORB kernels; profiles/r1d_* for the others, unchanged kernels)
+NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_strips': 968000, 'k_blur': 1997000, 'k_describe': 1965000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
 
 
 def _gen(args):
@@ -176,7 +188,7 @@ def run_reference(args, rank, world):
         return
     import oracle
     cores = os.cpu_count() or 1
-    sample = max(cores, min(args.batch, 2 * cores))
+    sample = max(cores, min(2368, 2 * cores))
     gray, depth = make_frames(sample)
     for _ in range(args.warmup):
         oracle.frontend_batch(gray, depth, ORACLE_CAM, stages=ORACLE_STAGES, nthreads=cores, nlines=NLINES, **ORB)
@@ -187,17 +199,43 @@ def run_reference(args, rank, world):
     v = sample * args.steps / dt
     emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D, whole front-end (ORB 1000 features 8 levels x1.2, <=200 LSD/LBD '
-                               f'lines, PEAC planes, surface normals); bounded sample of {sample} frames/step',
-                   'stages': STAGES, 'note': 'reference CPU path = oracle port (ORB bit-identical to the reference ORBextractor.cc built in '
-                                             'oracle/_ref; LSD bit-identical to cv2 4.13.0); the reference binary needs OpenCV/PCL/Eigen/'
-                                             'Pangolin, absent here'},
+        'config': {'workload': f'C5/C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames (TUM3.yaml: ORB 1000 features 8 levels x1.2, LINE 200), whole '
+                               f'front-end of Frame::Frame; bounded sample of {sample} frames/step of the 8192-frame sequence',
+                   'stages': STAGES, 'note': 'reference CPU path = oracle port, pinned by execution to the reference sources compiled in oracle/_ref '
+                                             '(ORBextractor.cc, PlaneExtractor.cpp + peac, vendored line_descriptor, Frame::cullingLine; LSD to cv2 4.13.0); '
+                                             'the reference binary needs OpenCV/PCL/Eigen/Pangolin, absent here'},
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': f'{sample} frames x {args.steps} steps'},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     })
+
+
+def cpu_latency(gray, depth, nframes=60, warm=5):
+    """Per-frame latency of the CPU front-end in the reference's own shape (src/Frame.cc:208-233): three concurrent threads per frame,
+    ORB || LSD + cullingLine + LBD || PEAC + normals, joined; time around the join as MTimeFeatExtract does."""
+    import oracle
+    groups = (1, 2 | 16, 4 | 8)
+    lat = []
+    for i in range(warm + nframes):
+        g, d = gray[i % len(gray)][None], depth[i % len(depth)][None]
+        th = [threading.Thread(target=oracle.frontend_batch, args=(g, d, ORACLE_CAM), kwargs=dict(stages=s, nthreads=1, nlines=NLINES, **ORB)) for s in groups]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if i >= warm:
+            lat.append(1e3 * (time.perf_counter() - t0))
+    lat = np.array(lat)
+    return dict(mean=float(lat.mean()), p50=float(np.median(lat)), p95=float(np.percentile(lat, 95)), frames=nframes, threads_per_frame=3,
+                shape='ORB || LSD + cullingLine + LBD x2 || PEAC + normals, joined (Frame.cc:208-233)')
+
+
+def shard(n, world, rank):
+    base, rem = divmod(n, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
 
 
 def main():
@@ -206,10 +244,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=2368, help='frames per GPU per step (default: 2 chunks of 1184 = 8 frames per SM)')
+    ap.add_argument('--frames', type=int, default=C5_FRAMES, help='frames per step over all GPUs (default: the C5 sequence, 8192)')
+    ap.add_argument('--batch', type=int, default=CALL_FRAMES, help='frames per library call (default 2368 = 2 chunks of 1184)')
     ap.add_argument('--stages', type=int, default=15, help='bit 0 ORB, 1 lines, 2 planes, 3 normals (profiling aid; the metric is 15)')
     ap.add_argument('--lanes', type=int, default=0, help='pipeline lanes of the frame handle (0 = library default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the C2 / C3 / C4 sub-records')
     ap.add_argument('--device-only', action='store_true', help='profiling aid: only the device-resident loop')
     ap.add_argument('--e2e-only', action='store_true', help='profiling aid: skip the per-stage passes, the latency probe and the CPU baseline')
     args = ap.parse_args()
@@ -225,28 +265,30 @@ def main():
     import torch
     import torch.distributed as dist
     import hvo_b200 as hvo
+    from hvo_b200 import synth
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
-    B, W, H = args.batch, 640, 480
-    # every rank gets its own frames (frame-sharded, weak scaling): up to 1024 distinct frames per rank (8192 over 8 GPUs, the
-    # C5 sequence), repeated to fill the batch.  Generated (forked worker pool) before this process touches CUDA or NCCL.
-    n_distinct = min(B, 1024)
-    gray, depth = make_frames(n_distinct, start=rank * n_distinct)
+    W, H = 640, 480
+    px = W * H
+    first, count = shard(args.frames, world, rank)            # this rank's contiguous range of the sequence
+    call = min(args.batch, count)
+    # distinct synthetic frames of this rank's range (seeds 1000 + first ...): up to 1024, repeated to fill the range.  Generated
+    # (forked worker pool) before this process touches CUDA or NCCL.
+    n_distinct = min(count, 1024)
+    gray, depth = make_frames(n_distinct, start=first)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    if n_distinct < B:
-        reps = (B + n_distinct - 1) // n_distinct
-        gray = np.concatenate([gray] * reps)[:B]
-        depth = np.concatenate([depth] * reps)[:B]
-    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True, lanes=args.lanes, membership='u8',
-                           max_batch=B, device=local_rank, nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'],
-                           nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
+    reps = (count + n_distinct - 1) // n_distinct
     dev = torch.device('cuda', local_rank)
-    d_gray = torch.from_numpy(gray).to(dev)
-    d_depth = torch.from_numpy(depth.view(np.int16)).to(dev)
-    shapes = fe.output_shapes(B)
+    d_gray = torch.from_numpy(gray).to(dev).repeat(reps, 1, 1)[:count].contiguous()
+    d_depth = torch.from_numpy(depth.view(np.int16)).to(dev).repeat(reps, 1, 1)[:count].contiguous()
+    fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
+                           lanes=args.lanes, membership='u4', normals='n3', max_planes=MAX_PLANES, max_batch=call, device=local_rank,
+                           nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'], nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
+    # one set of device outputs for a call, reused by every call of a step (the bench keeps no results)
+    shapes = fe.output_shapes(call)
     d_out = {k: torch.empty(int(np.prod(sh)) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, (sh, dt) in shapes.items()}
     d_ptrs = {k: v.data_ptr() for k, v in d_out.items()}
     torch.cuda.synchronize()
@@ -260,8 +302,9 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
 
-    def step_device():
-        fe.extract_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), B, d_ptrs)
+    def step_device(nfr=count):
+        for off in range(0, nfr, call):
+            fe.extract_batch_device(d_gray.data_ptr() + off * px, d_depth.data_ptr() + off * px * 2, min(call, nfr - off), d_ptrs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,7 +322,7 @@ def main():
     def d_counts(name):
         return d_out[name].view(torch.int32).float().mean().item() if name in d_out else None
 
-    # ---- value: inputs resident in HBM ----
+    # ---- value: strong scaling on the C5 sequence, inputs resident in HBM ----
     for _ in range(args.warmup):
         step_device()
     fe.sync()
@@ -297,20 +340,33 @@ def main():
     barrier()
     clk = clocks.stop(t0, t1)
     ms = max_over_ranks(ms)
-    launches_per_step = fe.last_launches()
-    value = world * B * args.steps / (ms * 1e-3)
+    calls_per_step = (count + call - 1) // call
+    launches_per_step = fe.last_launches() * calls_per_step
+    value = args.frames * args.steps / (ms * 1e-3)
     means = dict(keypoints=d_counts('kp_counts'), lines=d_counts('line_counts'), planes=d_counts('n_planes'))
 
     if args.device_only:
-        emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True,
+        emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True, 'frames_per_step': args.frames,
               'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means})
         teardown()
         return
 
+    # ---- weak scaling (the round-1 line): every GPU processes one call of 2368 frames per step ----
+    wn = min(call, count)
+    for _ in range(2):
+        step_device(wn)
+    barrier()
+    fe.timer_start()
+    for _ in range(5):
+        step_device(wn)
+    weak_ms = max_over_ranks(fe.timer_stop())
+    barrier()
+    weak = dict(value=world * wn * 5 / (weak_ms * 1e-3), unit='frames/s', frames_per_gpu_per_step=wn, steps=5, ms_per_step=weak_ms / 5, scaling='weak')
+
     roofline = None
     if not args.e2e_only:
-        # ---- per-stage device times: every pipeline alone on the same batch (standalone handles, smaller batch) ----
-        Bs = min(B, 256)
+        # ---- per-stage device times: every pipeline alone at the chunk size the frame handle runs (standalone handles) ----
+        Bs = min(count, CHUNK)
         stage_ms, kern_ms = {}, {}
         ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'], width=W, height=H,
                               max_batch=Bs, device=local_rank)
@@ -334,9 +390,10 @@ def main():
             for k, v in ex.stage_times().items():
                 acc[k] = acc.get(k, 0.0) + v / 5
         ex.close()
-        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_strips': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
+        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_strips': acc['fast'], 'k_octree': acc['octree'], 'k_blur': acc['blur'], 'k_describe': acc['describe']})
 
         le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
+        le.set_culling(True)
 
         def line_step():
             le.extract_batch_device(d_gray.data_ptr(), Bs, kp['keylines'], kp['line_desc'], kp['linevec3'], kp['line_counts'])
@@ -351,7 +408,7 @@ def main():
         le.sync()
         lt = le.stage_times()
         le.close()
-        kern_ms.update({'k_lsd_prep': lt['prep'], 'k_lsd_order': lt['order'], 'k_lsd_grow': lt['grow'], 'k_line_keylines + k_lbd_*': lt['keylines_lbd']})
+        kern_ms.update({'k_lsd_prep': lt['prep'], 'k_lsd_order': lt['order'], 'k_lsd_grow': lt['grow'], 'k_line_keylines + k_line_cull + k_lbd_*': lt['keylines_lbd']})
 
         pd = hvo.PlaneDetection(W, H, max_batch=Bs, device=local_rank)
         pd.readDepthImage(depth[0], np.array([[CAM['fx'], 0, CAM['cx']], [0, CAM['fy'], CAM['cy']], [0, 0, 1]], np.float32), np.float32(DEPTH_FACTOR))
@@ -368,7 +425,12 @@ def main():
         for _ in range(5):
             pd.blocks_device(d_depth.data_ptr(), Bs)
         kern_ms['k_plane_blocks'] = pd.timer_stop() / 5
-        kern_ms['k_plane_cluster + k_plane_flood + k_plane_merge'] = stage_ms['planes'] - kern_ms['k_plane_blocks']
+        cyc = pd.phase_cycles(0)
+        rest = stage_ms['planes'] - kern_ms['k_plane_blocks']
+        tot_c = float(sum(cyc.values())) or 1.0
+        kern_ms['k_plane_cluster'] = rest * cyc.get('cluster', 0) / tot_c       # split of the ordered chain by its own cycle counters (frame 0)
+        kern_ms['k_plane_flood'] = rest * (cyc.get('seeds', 0) + cyc.get('flood', 0)) / tot_c
+        kern_ms['k_plane_merge + k_plane_relabel'] = rest * cyc.get('merge_relabel', 0) / tot_c
         pd.close()
 
         sn = hvo.SurfaceNormals(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, max_batch=Bs, device=local_rank)
@@ -378,91 +440,168 @@ def main():
         for _ in range(5):
             sn.compute_device(d_depth.data_ptr(), Bs, kp['normals8'])
         stage_ms['normals'] = sn.timer_stop() / 5
+        kern_ms['k_sn_* x5'] = stage_ms['normals']
         sn.close()
 
-        # roofline: the dominant kernel among the HBM-bound (stencil / streaming) kernels; the ordered graph kernels
-        # (k_octree, k_lsd_grow, k_plane_cluster/flood/merge) are latency-bound by construction and are listed beside it
+        # roofline: the HBM-bound (stencil / streaming) kernels against the measured copy bandwidth; beside it the step as a whole and the
+        # kernel that really dominates it (an ordered graph kernel: latency-bound by construction, no bandwidth roofline applies)
         peak, peak_src = measured_peak()
         dom = max(ALG_BYTES, key=lambda k: kern_ms[k])
         achieved = ALG_BYTES[dom] * Bs / (kern_ms[dom] * 1e-3) / 1e9
+        serial_sum = sum(kern_ms.values())
+        top = max(kern_ms, key=lambda k: kern_ms[k])
+        step_gbs = ALG_BYTES_FRAME * count / ((ms / args.steps) * 1e-3) / 1e9
         roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                         traffic=NCU_DRAM_BYTES[dom] * Bs, traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/'
-                        'r1c_launches_frontend_b1024.csv) x frames per launch',
+                        'r2_ncu_full_orb_kernels_b296.csv) x frames per launch',
                         peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
                         kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
                         frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
                         stage_ms_alone={k: round(v, 3) for k, v in stage_ms.items()},
-                        serial_kernels='k_lsd_grow, k_plane_cluster, k_plane_flood, k_plane_merge and k_octree run the reference\'s ordered '
-                                       '(sequential) algorithms, one warp/CTA per frame; they are latency-bound, not HBM-bound, and dominate the step '
-                                       '(see kernel_ms); their throughput comes from the batch (frames in flight), not from bandwidth')
+                        step_frac=step_gbs / peak, step_achieved_gbs=step_gbs, step_algorithmic_bytes_per_frame=ALG_BYTES_FRAME,
+                        dominant_kernel=dict(name=top, ms=round(kern_ms[top], 3), share_of_serialised_kernels=round(kern_ms[top] / serial_sum, 3),
+                                             note='the step is dominated by the ordered graph kernels (k_lsd_grow, k_plane_cluster, k_plane_flood): the '
+                                                  'reference sequential algorithms, one warp / CTA per frame, latency-bound; their throughput comes from the '
+                                                  'frames in flight, not from bandwidth'),
+                        serialised_kernel_ms_per_chunk=round(serial_sum, 2))
 
     # ---- e2e: host (pinned) buffers through the C-ABI call, copies inside the timed region ----
     def pinned(shape, dtype):
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         return t.numpy().view(dtype).reshape(shape)
-    h_gray = pinned((B, H, W), np.uint8)
-    h_depth = pinned((B, H, W), np.uint16)
-    h_gray[:] = gray
-    h_depth[:] = depth
-    # two sets of pinned output buffers, used alternately: step k+1 is queued (hvo_frame_extract_batch_async) while step k still
-    # runs, so its uploads overlap the tail of step k; the timer stops after every download has landed
-    outs = [{k: pinned(sh, dt) for k, (sh, dt) in fe.output_shapes(B, device=False).items()} for _ in range(2)]
-    out = outs[0]
-    for i in range(2):
-        fe.extract_batch(h_gray, h_depth, out=outs[i])
+    h_gray = pinned((call, H, W), np.uint8)
+    h_depth = pinned((call, H, W), np.uint16)
+    rep = (call + n_distinct - 1) // n_distinct
+    h_gray[:] = np.concatenate([gray] * rep)[:call]
+    h_depth[:] = np.concatenate([depth] * rep)[:call]
+    # two sets of pinned output buffers, used alternately: call k+1 is queued (hvo_frame_extract_batch_async) while call k still
+    # runs, so its uploads overlap the tail of call k; the timer stops after every download has landed
+    outs = [{k: pinned(sh, dt) for k, (sh, dt) in fe.output_shapes(call, device=False).items()} for _ in range(2)]
+
+    def step_host(wait):
+        for i, off in enumerate(range(0, count, call)):
+            n = min(call, count - off)
+            o = outs[i % 2] if n == call else {k: v[:n] for k, v in outs[i % 2].items()}
+            fe.extract_batch(h_gray[:n], h_depth[:n], out=o, wait=wait)
+    step_host(True)
     barrier()
-    e2e_steps = max(4, args.steps // 2)
+    e2e_steps = max(3, args.steps // 2)
     fe.timer_start()
     for i in range(e2e_steps):
-        fe.extract_batch(h_gray, h_depth, out=outs[i % 2], wait=False)
+        step_host(False)
     e2e_ms = max_over_ranks(fe.timer_stop())
     barrier()
-    # the same with one blocking call per step (what a caller without double buffering sees)
+    # the same with blocking calls (what a caller without double buffering sees)
     fe.timer_start()
-    for i in range(e2e_steps):
-        fe.extract_batch(h_gray, h_depth, out=outs[i % 2])
+    for i in range(2):
+        step_host(True)
     e2e_blocking_ms = max_over_ranks(fe.timer_stop())
     barrier()
-    e2e = dict(value=world * B * e2e_steps / (e2e_ms * 1e-3), unit='frames/s',
-               h2d_bytes_per_step=int(h_gray.nbytes + h_depth.nbytes),
-               d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())), ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
-               call='hvo_frame_extract_batch_async x steps + hvo_frame_timer_stop (pinned host buffers, two output sets alternating)',
-               blocking_calls_value=world * B * e2e_steps / (e2e_blocking_ms * 1e-3))
+    out_bytes_frame = sum(v.nbytes for v in outs[0].values()) // call
+    e2e = dict(value=args.frames * e2e_steps / (e2e_ms * 1e-3), unit='frames/s',
+               h2d_bytes_per_step=int(count * px * 3), d2h_bytes_per_step=int(count * out_bytes_frame), d2h_bytes_per_frame=int(out_bytes_frame),
+               bytes_are='per GPU', ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
+               call='hvo_frame_extract_batch_async per 2368 frames + hvo_frame_timer_stop (pinned host buffers, two output sets alternating; outputs: '
+                    'keypoints, descriptors, depth / uRight, keylines, LBD, line functions, planes, 4-bit plane labels, surface normals)',
+               blocking_calls_value=args.frames * 2 / (e2e_blocking_ms * 1e-3))
 
     if args.e2e_only:
         if rank == 0:
-            emit({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'lanes': fe.lanes, 'chunk': fe.chunk})
+            emit({'metric': METRIC, 'value': value, 'ms_per_step': ms / args.steps, 'e2e': e2e, 'weak': weak, 'lanes': fe.lanes, 'chunk': fe.chunk})
         teardown()
         return
+
     # ---- single-frame latency through the host call (p50) ----
     fe1 = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
-                            max_batch=1, device=local_rank)
+                            max_batch=1, device=local_rank, max_planes=MAX_PLANES, membership='u4', normals='n3')
     out1 = fe1.alloc_host(1)
     lat = []
     for i in range(24):
         t = time.perf_counter()
-        fe1.extract_batch(gray[i % B][None], depth[i % B][None], out=out1)
+        fe1.extract_batch(gray[i % n_distinct][None], depth[i % n_distinct][None], out=out1)
         lat.append(1e3 * (time.perf_counter() - t))
     p50 = float(np.median(lat[4:]))
     fe1.close()
 
+    # ---- the other BASELINE.json configs (rank 0): device-resident throughput of C2 / C3, matching stress C4 ----
+    configs = None
+    if rank == 0 and not args.no_configs:
+        configs = {}
+        for name, cfg, w2, h2, nfeat, nb in (('C2', 'S2', 640, 480, 1000, 1184), ('C3', 'S3', 1280, 720, 2000, 592)):
+            c = synth.CONFIGS[cfg]
+            g2, dp2 = make_frames(64, cfg=cfg)
+            fe2 = hvo.FrameFrontEnd(w2, h2, c['fx'], c['fy'], c['cx'], c['cy'], 1.0 / c['factor'], bf=BF, n_lines=NLINES, line_cull=True, lanes=1,
+                                    membership='u4', normals='n3', max_planes=MAX_PLANES, max_batch=nb, device=local_rank, nfeatures=nfeat)
+            r2 = (nb + 63) // 64
+            dg = torch.from_numpy(g2).to(dev).repeat(r2, 1, 1)[:nb].contiguous()
+            dd = torch.from_numpy(dp2.view(np.int16)).to(dev).repeat(r2, 1, 1)[:nb].contiguous()
+            sh2 = fe2.output_shapes(nb)
+            do = {k: torch.empty(int(np.prod(s_)) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, (s_, dt) in sh2.items()}
+            dp = {k: v.data_ptr() for k, v in do.items()}
+            for _ in range(2):
+                fe2.extract_batch_device(dg.data_ptr(), dd.data_ptr(), nb, dp)
+            fe2.sync()
+            fe2.timer_start()
+            for _ in range(3):
+                fe2.extract_batch_device(dg.data_ptr(), dd.data_ptr(), nb, dp)
+            m2 = fe2.timer_stop() / 3
+            configs[name] = dict(workload=f'{cfg}: {w2}x{h2}, {nfeat} ORB features, whole front-end, {nb} frames per step (64 distinct), device-resident',
+                                 value=nb / m2 * 1e3, unit='frames/s', ms_per_step=m2,
+                                 mean_per_frame=dict(keypoints=do['kp_counts'].view(torch.int32).float().mean().item(),
+                                                     lines=do['line_counts'].view(torch.int32).float().mean().item(),
+                                                     planes=do['n_planes'].view(torch.int32).float().mean().item()))
+            fe2.close()
+            del dg, dd, do
+        bfm = hvo.BFMatcherHamming(local_rank)
+        c4 = {}
+        for name, nq, nt, seed in (('orb_2000x50000', 2000, 50000, 4), ('lbd_200x5000', 200, 5000, 5)):
+            q, t = synth.descriptors_S4(nq=nq, nt=nt, seed=seed)
+            dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+            di = torch.empty((nq, 2), dtype=torch.int32, device=dev); dd_ = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+            for _ in range(3):
+                bfm.knn2_device(dq.data_ptr(), nq, dt_.data_ptr(), nt, di.data_ptr(), dd_.data_ptr())
+            bfm.sync()
+            bfm.timer_start()
+            for _ in range(50):
+                bfm.knn2_device(dq.data_ptr(), nq, dt_.data_ptr(), nt, di.data_ptr(), dd_.data_ptr())
+            mm = bfm.timer_stop() / 50
+            peak_popc = 148 * 16 * (clk.get('sm_mhz') or 1965.0) * 1e6           # 16 POPC lanes per SM per clock (XU pipe)
+            r = dict(ms=mm, pairs_per_s=nq * nt / mm * 1e3, popc32_per_s=nq * nt * 8 / mm * 1e3, xu_pipe_frac=nq * nt * 8 / (mm * 1e-3) / peak_popc)
+            t0c = time.perf_counter()
+            idx, _ = bfm.knnMatch2(q, t)
+            r['host_call_ms'] = 1e3 * (time.perf_counter() - t0c)
+            try:
+                import cv2
+                t0c = time.perf_counter()
+                cvm = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(q, t, k=2)
+                r['cv2_bfmatcher_ms'] = 1e3 * (time.perf_counter() - t0c)
+                r['cv2_threads'] = cv2.getNumThreads()
+                r['same_as_cv2'] = bool(np.array_equal(idx, np.array([[a.trainIdx, b.trainIdx] for a, b in cvm], np.int32)))
+            except ImportError:
+                pass
+            c4[name] = r
+        bfm.close()
+        configs['C4'] = dict(workload='matching stress: brute-force Hamming knn-2 + ratio test inputs, device-resident', **c4)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(gray, depth)
+        cpu['latency_ms'] = cpu_latency(gray, depth)
 
     if rank == 0:
         emit({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic',
-            'config': {'workload': f'C1: synthetic TUM-fr3-shaped 640x480 RGB-D frames (TUM3.yaml: ORB 1000 features 8 levels x1.2, LINE 200), '
-                                   f'whole front-end of Frame::Frame, {B} frames per GPU per step ({n_distinct} distinct per GPU), frame-sharded over {world} GPU(s)',
-                       'stages': STAGES, 'batch_per_gpu': B, 'lanes': fe.lanes, 'chunk_frames': fe.chunk, 'mean_per_frame': means,
-                       'outputs': 'keypoints + descriptors + depth/uRight, keylines + LBD + line functions, planes + one-byte membership image, '
-                                  'surface normals',
-                       'l2': f'inputs larger than L2: per-step inputs {B} x 0.92 MB and working set ~{B} x 17 MB >> 126 MB'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
+            'config': {'workload': f'C5/C1: {args.frames} synthetic TUM-fr3-shaped 640x480 RGB-D frames per step (TUM3.yaml: ORB 1000 features 8 levels x1.2, '
+                                   f'LINE 200), whole front-end of Frame::Frame, frame-sharded over {world} GPU(s) in contiguous ranges: {count} frames per GPU '
+                                   f'per step ({n_distinct} distinct per GPU), {calls_per_step} call(s) of <= {call} frames',
+                       'stages': STAGES, 'frames_per_step': args.frames, 'frames_per_gpu': count, 'frames_per_call': call, 'lanes': fe.lanes,
+                       'chunk_frames': fe.chunk, 'mean_per_frame': means,
+                       'outputs': 'keypoints + descriptors + depth/uRight, keylines + LBD + line functions, planes + plane labels, surface normals',
+                       'l2': f'inputs larger than L2: per-step inputs {count} x 0.92 MB and working set ~{min(count, call)} x 17 MB >> 126 MB'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'weak': weak, 'configs': configs, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step, 'clocks': clk, 'p50_latency_ms_single_frame': p50,
         })
     teardown()
