@@ -79,6 +79,7 @@ ABI = {
     'hvo_match_knn2': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     'hvo_match_knn2_device': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     'hvo_match_distinctive': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
+    'hvo_match_lines_epipolar': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_float, C.c_float, _vp]),
     'hvo_matcher_sync': (C.c_int, [_vp]),
     'hvo_matcher_timer_start': (C.c_int, [_vp]),
     'hvo_matcher_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
@@ -104,6 +105,11 @@ ABI = {
     'hvo_proj_search_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
     'hvo_proj_search_triangulation': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp,
                                                C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_predict_scale_thresholds': (C.c_int, [C.c_float, C.c_int, C.c_int, _vp]),
+    'hvo_proj_frustum_points': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_float, _vp]),
+    'hvo_proj_search_local_map': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp,
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'hvo_proj_search_initialization': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
     'hvo_proj_timer_start': (C.c_int, [_vp]),
     'hvo_proj_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
     'hvo_line_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -154,6 +160,9 @@ ABI = {
     'hvo_lproj_get_grid': (C.c_int, [_vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     'hvo_lproj_features_in_area': (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, C.POINTER(C.c_int)]),
     'hvo_lproj_search': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
+    'hvo_lproj_frustum_lines': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_float, _vp]),
+    'hvo_lproj_search_local_map': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, C.c_float, _vp, _vp, _vp,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'hvo_lproj_last_rounds': (C.c_int, [_vp]),
     'hvo_lproj_last_launches': (C.c_int, [_vp]),
     'hvo_lpvo_create': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -220,6 +229,43 @@ def device_count():
     n = C.c_int(0)
     _check(lib().hvo_device_count(C.byref(n)))
     return n.value
+
+
+# hvo_frustum_cam / hvo_map_point / hvo_track_point / hvo_map_line / hvo_track_line (include/hvo_capi.h)
+FRUSTUM_CAM_DTYPE = np.dtype([('Rcw', '<f4', (9,)), ('tcw', '<f4', (3,)), ('Ow', '<f4', (3,)), ('fx', '<f4'), ('fy', '<f4'), ('cx', '<f4'),
+                              ('cy', '<f4'), ('bf', '<f4'), ('min_x', '<f4'), ('min_y', '<f4'), ('max_x', '<f4'), ('max_y', '<f4'),
+                              ('log_scale_factor', '<f4'), ('n_levels', '<i4')])
+MAP_POINT_DTYPE = np.dtype([('pos', '<f4', (3,)), ('normal', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4')])
+TRACK_POINT_DTYPE = np.dtype([('u', '<f4'), ('v', '<f4'), ('ur', '<f4'), ('level', '<i4'), ('view_cos', '<f4'), ('in_view', '<i4')])
+MAP_LINE_DTYPE = np.dtype([('pos', '<f8', (6,)), ('normal', '<f8', (3,)), ('dir', '<f8', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4')])
+TRACK_LINE_DTYPE = np.dtype([('x1', '<f4'), ('y1', '<f4'), ('x2', '<f4'), ('y2', '<f4'), ('level', '<i4'), ('view_cos', '<f4'), ('in_view', '<i4')])
+assert FRUSTUM_CAM_DTYPE.itemsize == 104 and MAP_POINT_DTYPE.itemsize == 32 and TRACK_POINT_DTYPE.itemsize == 24
+assert MAP_LINE_DTYPE.itemsize == 104 and TRACK_LINE_DTYPE.itemsize == 28
+
+
+def frustum_cam(Rcw, tcw, fx, fy, cx, cy, bf, bounds, scale_factor=1.2, n_levels=8):
+    """hvo_frustum_cam of a frame pose: mOw = -Rcw^T * tcw as Frame::UpdatePoseMatrices computes it (cv::gemm on CV_32F: float products
+    summed in k order), mfLogScaleFactor = log(scaleFactor) narrowed to float (src/Frame.cc:105)."""
+    c = np.zeros((), FRUSTUM_CAM_DTYPE)
+    R = np.asarray(Rcw, np.float32).reshape(3, 3); t = np.asarray(tcw, np.float32).reshape(3)
+    Ow = np.zeros(3, np.float32)
+    for i in range(3):
+        acc = np.float32(0)
+        for k in range(3):
+            acc = np.float32(acc + np.float32(np.float32(-R[k, i]) * t[k]))   # -mRcw.t() * mtcw
+        Ow[i] = acc
+    c['Rcw'] = R.reshape(9); c['tcw'] = t; c['Ow'] = Ow
+    c['fx'], c['fy'], c['cx'], c['cy'], c['bf'] = fx, fy, cx, cy, bf
+    c['min_x'], c['min_y'], c['max_x'], c['max_y'] = bounds
+    c['log_scale_factor'] = np.float32(np.log(np.float64(np.float32(scale_factor))))
+    c['n_levels'] = n_levels
+    return c
+
+
+def predict_scale_thresholds(log_scale_factor, lo, n):
+    thr = np.empty(max(n, 1), np.float32)
+    _check(lib().hvo_predict_scale_thresholds(float(log_scale_factor), int(lo), int(n), _np_ptr(thr)))
+    return thr[:n]
 
 
 class ORBextractor:
@@ -852,6 +898,16 @@ class BFMatcherHamming:
         _check(lib().hvo_match_knn2(self._h, _np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(idx), _np_ptr(dist)))
         return idx, dist
 
+    def lines_epipolar(self, ldesc1, kls1, ldesc2, kls2, kls2func, F, TH, nnratio):
+        """LSDmatcher::FrameBFMatchNew (src/LSDmatcher.cpp:968-1031): knn-2 + the epipolar overlap test of the nearest neighbour."""
+        d1 = np.ascontiguousarray(ldesc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(ldesc2, np.uint8).reshape(-1, 32)
+        k1 = np.ascontiguousarray(kls1, KL_DTYPE); k2 = np.ascontiguousarray(kls2, KL_DTYPE)
+        f2 = np.ascontiguousarray(kls2func, np.float64).reshape(-1, 3); Fm = np.ascontiguousarray(F, np.float32).reshape(9)
+        out = np.full(max(len(d1), 1), -1, np.int32)
+        _check(lib().hvo_match_lines_epipolar(self._h, _np_ptr(d1), _np_ptr(k1), len(d1), _np_ptr(d2), _np_ptr(k2), _np_ptr(f2), len(d2), _np_ptr(Fm),
+                                              float(TH), float(nnratio), _np_ptr(out)))
+        return out[:len(d1)]
+
     def distinctive(self, desc, offsets):
         """MapPoint / MapLine::ComputeDistinctiveDescriptors for a batch of map elements: group g = desc[offsets[g]:offsets[g+1]]
         (the descriptors of its observations).  Returns (best index inside each group or -1, its median distance)."""
@@ -939,6 +995,27 @@ class LineProjectionMatcher:
         _check(lib().hvo_lproj_search(self._h, _np_ptr(q), _np_ptr(qd), len(q), _np_ptr(cl) if cl is not None else None, int(mode),
                                       float(np.float32(nnratio)), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
         return idx[:len(q)], dist[:len(q)], nm.value
+
+    def frustum_lines(self, cam, lines, viewing_cos_limit=0.5):
+        """Frame::isInFrustum(MapLine*, viewingCosLimit) (src/Frame.cc:1438-1499) for a batch: lines MAP_LINE_DTYPE."""
+        cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); ml = np.ascontiguousarray(lines, MAP_LINE_DTYPE)
+        out = np.zeros(max(len(ml), 1), TRACK_LINE_DTYPE)
+        _check(lib().hvo_lproj_frustum_lines(self._h, _np_ptr(cam), _np_ptr(ml), len(ml), float(viewing_cos_limit), _np_ptr(out)))
+        return out[:len(ml)]
+
+    def search_local_map(self, cam, lines, ldesc, skip=None, claims=None, claimed=None, viewing_cos_limit=0.5, th=1.0, nnratio=0.95):
+        """isInFrustum over the local map lines + LSDmatcher::SearchByProjection(F, vpMapLines, eval_orient, th) in one call."""
+        cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); ml = np.ascontiguousarray(lines, MAP_LINE_DTYPE)
+        n = len(ml)
+        ld = np.ascontiguousarray(ldesc, np.uint8).reshape(-1, 32)
+        opt = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        sk, cl, cd = opt(skip), opt(claims), opt(claimed)
+        track = np.zeros(max(n, 1), TRACK_LINE_DTYPE); idx = np.full(max(n, 1), -1, np.int32); dist = np.full(max(n, 1), 256, np.int32)
+        niv, nm = C.c_int(0), C.c_int(0)
+        p = lambda a: _np_ptr(a) if a is not None else None
+        _check(lib().hvo_lproj_search_local_map(self._h, _np_ptr(cam), _np_ptr(ml), _np_ptr(ld), p(sk), p(cl), n, float(viewing_cos_limit), float(th),
+                                                p(cd), float(nnratio), _np_ptr(track), _np_ptr(idx), _np_ptr(dist), C.byref(niv), C.byref(nm)))
+        return track[:n], idx[:n], dist[:n], niv.value, nm.value
 
     def rounds(self):
         return lib().hvo_lproj_last_rounds(self._h)
@@ -1067,6 +1144,19 @@ class LSDmatcher:
         out[ok] = idx[ok, 0]
         return out
 
+    def FrameBFMatchNew(self, ldesc1, ldesc2, kls1, kls2, kls2func, F, TH):
+        """LSDmatcher::FrameBFMatchNew(ldesc1, ldesc2, LineMatches, kls1, kls2, kls2func, F, TH) (src/LSDmatcher.cpp:968-1031).  Returns LineMatches."""
+        return self._bf.lines_epipolar(ldesc1, kls1, ldesc2, kls2, kls2func, F, TH, self.mfNNratio)
+
+    def SearchLocalLines(self, F, cam, lines, ldesc, skip, has_obs, th=1.0, viewing_cos_limit=0.5):
+        """The device work of Tracking::SearchLocalLines (src/Tracking.cc:3315-3348): Frame::isInFrustum over the local map lines and
+        LSDmatcher::SearchByProjection(F, vpMapLines, eval_orient, th) in one call.  Updates F['mapline'] / F['claimed']; returns
+        (track, nmatches, match [M])."""
+        lpm = self._line_matcher(F, True)
+        track, idx, dist, niv, nm = lpm.search_local_map(cam, lines, ldesc, skip, has_obs, F.get('claimed'), viewing_cos_limit, th, self.mfNNratio)
+        self._apply(F, np.arange(len(idx)), idx, has_obs)
+        return track, nm, idx
+
     def SearchDouble(self, ldesc1, ldesc2):
         """LSDmatcher::SearchDouble(InitialFrame, CurrentFrame, LineMatches) (src/LSDmatcher.cpp:903-940): FrameBFMatch in both
         directions (the reference runs them on two threads), kept where they agree.  Returns (nmatches, LineMatches)."""
@@ -1164,6 +1254,42 @@ class ProjectionMatcher:
         _check(lib().hvo_proj_search(self._h, _np_ptr(q), _np_ptr(qd), len(q), _np_ptr(cl) if cl is not None else None, int(mode),
                                      int(th_dist), float(nnratio), _np_ptr(idx), _np_ptr(dist), C.byref(nm)))
         return idx[:len(q)], dist[:len(q)], nm.value
+
+    def frustum_points(self, cam, pts, viewing_cos_limit=0.5):
+        """Frame::isInFrustum(MapPoint*, viewingCosLimit) (src/Frame.cc:1371-1436) for a batch: cam FRUSTUM_CAM_DTYPE, pts MAP_POINT_DTYPE."""
+        cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+        out = np.zeros(max(len(pts), 1), TRACK_POINT_DTYPE)
+        _check(lib().hvo_proj_frustum_points(self._h, _np_ptr(cam), _np_ptr(pts), len(pts), float(viewing_cos_limit), _np_ptr(out)))
+        return out[:len(pts)]
+
+    def search_local_map(self, cam, pts, pdesc, scale_factors, skip=None, claims=None, claimed=None, viewing_cos_limit=0.5, th=1.0, th_dist=100,
+                         nnratio=0.8):
+        """isInFrustum over the local map + ORBmatcher::SearchByProjection(F, vpMapPoints, th) in one call (Tracking.cc:3251-3268)."""
+        cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+        n = len(pts)
+        pd = np.ascontiguousarray(pdesc, np.uint8).reshape(-1, 32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        opt = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        sk, cl, cd = opt(skip), opt(claims), opt(claimed)
+        track = np.zeros(max(n, 1), TRACK_POINT_DTYPE); idx = np.full(max(n, 1), -1, np.int32); dist = np.full(max(n, 1), 256, np.int32)
+        niv, nm = C.c_int(0), C.c_int(0)
+        p = lambda a: _np_ptr(a) if a is not None else None
+        _check(lib().hvo_proj_search_local_map(self._h, _np_ptr(cam), _np_ptr(pts), _np_ptr(pd), p(sk), p(cl), n, float(viewing_cos_limit), float(th),
+                                               _np_ptr(sf), p(cd), int(th_dist), float(nnratio), _np_ptr(track), _np_ptr(idx), _np_ptr(dist),
+                                               C.byref(niv), C.byref(nm)))
+        return track[:n], idx[:n], dist[:n], niv.value, nm.value
+
+    def search_initialization(self, prev_matched, octave1, desc1, window_size=100, th_dist=50, nnratio=0.9):
+        """The loop of ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:412-497) against the frame set by set_frame (= F2).
+        Returns (matches12, accepted12, nmatches) before the rotation-histogram culling."""
+        pm = np.ascontiguousarray(prev_matched, np.float32).reshape(-1, 2)
+        oc = np.ascontiguousarray(octave1, np.int32); d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        n1 = len(pm)
+        m12 = np.full(max(n1, 1), -1, np.int32); acc = np.full(max(n1, 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib().hvo_proj_search_initialization(self._h, _np_ptr(pm), _np_ptr(oc), _np_ptr(d1), n1, int(window_size), int(th_dist), float(nnratio),
+                                                    _np_ptr(m12), _np_ptr(acc), C.byref(nm)))
+        return m12[:n1], acc[:n1], nm.value
 
     def set_level_sigma(self, inv_level_sigma2):
         s = np.ascontiguousarray(inv_level_sigma2, np.float32)
@@ -1364,6 +1490,54 @@ class ORBmatcher:
                         match[i] = -1
                         nm -= 1
         return nm, match
+
+    def SearchLocalPoints(self, F, cam, pts, pdesc, skip, has_obs, th=1.0, viewing_cos_limit=0.5):
+        """The device work of Tracking::SearchLocalPoints (src/Tracking.cc:3251-3268): Frame::isInFrustum over the local map points and
+        ORBmatcher::SearchByProjection(F, vpMapPoints, th), the projected queries never leaving the device.  skip = already matched in
+        this frame (mnLastFrameSeen) or isBad().  Updates F['mappoint'] / F['claimed']; returns (track, nmatches, match [M])."""
+        self._set_frame(F)
+        track, idx, dist, niv, nm = self._pm.search_local_map(cam, pts, pdesc, F['scale_factors'], skip, has_obs, F.get('claimed'),
+                                                              viewing_cos_limit, th, self.TH_HIGH, self.mfNNratio)
+        for k, i in enumerate(idx):
+            if i >= 0:
+                F['mappoint'][i] = k
+                F['claimed'][i] = bool(has_obs[k])
+        return track, nm, idx
+
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:412-529): the sequential loop
+        on the device, the rotation histogram (:499-523) and the vbPrevMatched update (:525-528) here.  Fi = dict(keys_un, desc, bounds).
+        Returns (nmatches, vnMatches12, vbPrevMatched)."""
+        k1 = np.ascontiguousarray(F1['keys_un'], KP_DTYPE)
+        prev = np.array(vbPrevMatched, np.float32).reshape(-1, 2)
+        self._set_frame(F2)
+        m12, acc, nm = self._pm.search_initialization(prev, k1['octave'], F1['desc'], windowSize, self.TH_LOW, self.mfNNratio)
+        m12 = m12.copy()
+        if self.mbCheckOrientation:
+            k2 = np.ascontiguousarray(F2['keys_un'], KP_DTYPE)
+            hist = [[] for _ in range(self.HISTO_LENGTH)]
+            factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+            for i1, i2 in enumerate(acc):
+                if i2 < 0:
+                    continue
+                rot = np.float32(k1['angle'][i1] - k2['angle'][i2])
+                if rot < 0.0:
+                    rot = np.float32(rot + np.float32(360.0))
+                b = int(np.floor(float(np.float32(rot * factor)) + 0.5))
+                if b == self.HISTO_LENGTH:
+                    b = 0
+                hist[b].append(i1)
+            i1m, i2m, i3m = self.ComputeThreeMaxima([len(h) for h in hist])
+            for b in range(self.HISTO_LENGTH):
+                if b not in (i1m, i2m, i3m):
+                    for i1 in hist[b]:
+                        if m12[i1] >= 0:
+                            m12[i1] = -1
+                            nm -= 1
+        k2 = np.ascontiguousarray(F2['keys_un'], KP_DTYPE)
+        for i1 in np.nonzero(m12 >= 0)[0]:
+            prev[i1, 0] = k2['x'][m12[i1]]; prev[i1, 1] = k2['y'][m12[i1]]
+        return nm, m12, prev
 
     @staticmethod
     def ComputeThreeMaxima(sizes):  # ORBmatcher.cc:1630-1671

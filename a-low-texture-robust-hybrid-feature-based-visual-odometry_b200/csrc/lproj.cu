@@ -205,6 +205,76 @@ __global__ void k_lproj_fill(int* __restrict__ a, int n, int v) {
     if (i < n) a[i] = v;
 }
 
+
+// ---- Frame::isInFrustum(MapLine*, viewingCosLimit)  (src/Frame.cc:1438-1499) --------------------------------------------------
+// One thread per map line; cv::Mat arithmetic as in k_frustum_points (project.cu).  End points and normal are narrowed to float
+// first (Mat_<float> << P(0) ...); the mid point is cv::addWeighted(SP, 0.5, EP, 0.5) - mOw; PredictScale is not clamped.
+struct LFrustumCam { float R[9], t[3], O[3], fx, fy, cx, cy, min_x, min_y, max_x, max_y; int thr_lo, thr_n; };
+struct MapLn { double pos[6], normal[3], dir[3]; float min_dist, max_dist; };   // hvo_map_line
+struct TrackLn { float x1, y1, x2, y2; int level; float view_cos; int in_view; };  // hvo_track_line
+static_assert(sizeof(MapLn) == sizeof(hvo_map_line) && sizeof(TrackLn) == sizeof(hvo_track_line), "layout");
+
+__device__ __forceinline__ float lgemm_row3(const float* r, float x, float y, float z, float c) {
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(r[0], x), __fmul_rn(r[1], y)), __fmul_rn(r[2], z));
+    return (float)((double)t + (double)c);
+}
+__device__ __forceinline__ TrackLn frustum_line(const LFrustumCam& c, const MapLn& m, float cos_limit, const float* __restrict__ thr) {
+    TrackLn o;
+    o.x1 = o.y1 = o.x2 = o.y2 = 0.f; o.level = 0; o.view_cos = 0.f; o.in_view = 0;
+    const float sx = (float)m.pos[0], sy = (float)m.pos[1], sz = (float)m.pos[2], ex = (float)m.pos[3], ey = (float)m.pos[4], ez = (float)m.pos[5];
+    const float SX = lgemm_row3(c.R + 0, sx, sy, sz, c.t[0]), SY = lgemm_row3(c.R + 3, sx, sy, sz, c.t[1]), SZ = lgemm_row3(c.R + 6, sx, sy, sz, c.t[2]);
+    const float EX = lgemm_row3(c.R + 0, ex, ey, ez, c.t[0]), EY = lgemm_row3(c.R + 3, ex, ey, ez, c.t[1]), EZ = lgemm_row3(c.R + 6, ex, ey, ez, c.t[2]);
+    if (SZ < 0.0f || EZ < 0.0f) return o;
+    const float invz1 = __fdiv_rn(1.0f, SZ);
+    const float u1 = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, SX), invz1), c.cx), v1 = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, SY), invz1), c.cy);
+    if (u1 < c.min_x || u1 > c.max_x) return o;
+    if (v1 < c.min_y || v1 > c.max_y) return o;
+    const float invz2 = __fdiv_rn(1.0f, EZ);
+    const float u2 = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, EX), invz2), c.cx), v2 = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, EY), invz2), c.cy);
+    if (u2 < c.min_x || u2 > c.max_x) return o;
+    if (v2 < c.min_y || v2 > c.max_y) return o;
+    const float mx = __fsub_rn(__fadd_rn(__fmul_rn(sx, 0.5f), __fmul_rn(ex, 0.5f)), c.O[0]);
+    const float my = __fsub_rn(__fadd_rn(__fmul_rn(sy, 0.5f), __fmul_rn(ey, 0.5f)), c.O[1]);
+    const float mz = __fsub_rn(__fadd_rn(__fmul_rn(sz, 0.5f), __fmul_rn(ez, 0.5f)), c.O[2]);
+    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)mx, (double)mx), __dmul_rn((double)my, (double)my)), __dmul_rn((double)mz, (double)mz));
+    const float dist = (float)sqrt(n2);
+    if (dist < __fmul_rn(0.8f, m.min_dist) || dist > __fmul_rn(1.2f, m.max_dist)) return o;   // Get{Min,Max}DistanceInvariance
+    const float nx = (float)m.normal[0], ny = (float)m.normal[1], nz = (float)m.normal[2];
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)mx, (double)nx), __dmul_rn((double)my, (double)ny)), __dmul_rn((double)mz, (double)nz));
+    const float view_cos = (float)(dot / (double)dist);
+    if (view_cos < cos_limit) return o;
+    const float ratio = __fdiv_rn(m.max_dist, dist);
+    int level = c.thr_lo;
+    for (int k = 0; k < c.thr_n; ++k) level += ratio >= thr[k];
+    o.x1 = u1; o.y1 = v1; o.x2 = u2; o.y2 = v2; o.level = level; o.view_cos = view_cos; o.in_view = 1;
+    return o;
+}
+__global__ void __launch_bounds__(128) k_frustum_lines(LFrustumCam c, const MapLn* __restrict__ lines, const uint8_t* __restrict__ skip,
+                                                       const uint8_t* __restrict__ claims, int n, float cos_limit, const float* __restrict__ thr,
+                                                       float th, TrackLn* __restrict__ track, LQuery* __restrict__ qs, int* __restrict__ n_in_view) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    TrackLn o;
+    o.x1 = o.y1 = o.x2 = o.y2 = 0.f; o.level = 0; o.view_cos = 0.f; o.in_view = 0;
+    if (!(skip && skip[i])) o = frustum_line(c, lines[i], cos_limit, thr);
+    if (track) track[i] = o;
+    if (qs) {   // LSDmatcher::SearchByProjection(F, vpMapLines, eval_orient, th), LSDmatcher.cpp:727-736
+        LQuery q;
+        q.length = 0.f; q.pad[0] = q.pad[1] = 0;
+        if (o.in_view) {
+            float r = ((double)o.view_cos > 0.998) ? 5.0f : 8.0f;      // RadiusByViewingCos, LSDmatcher.cpp:1436-1442
+            if (th != 1.0f) r = __fmul_rn(r, th);
+            q.x1 = o.x1; q.y1 = o.y1; q.x2 = o.x2; q.y2 = o.y2; q.r = r; q.cos_th = 0.998f;
+            q.dir[0] = lines[i].dir[0]; q.dir[1] = lines[i].dir[1]; q.dir[2] = lines[i].dir[2];
+            q.claims = claims ? (claims[i] != 0) : 1;
+        } else {   // not searched: a window nothing falls into
+            q.x1 = q.y1 = q.x2 = q.y2 = -1e30f; q.r = -1.f; q.cos_th = 2.f; q.dir[0] = q.dir[1] = q.dir[2] = 0.0; q.claims = 0;
+        }
+        qs[i] = q;
+    }
+    if (n_in_view && o.in_view) atomicAdd(n_in_view, 1);
+}
+
 }  // namespace hvo
 
 using namespace hvo;
@@ -224,6 +294,10 @@ struct hvo_lproj {
     LQuery* d_q = nullptr;
     int* h_flag = nullptr;
     int last_rounds = 0, last_launches = 0;
+    // local-map projection (isInFrustum + search)
+    float* d_thr = nullptr; float thr_log = 0.f;
+    MapLn* d_lines = nullptr; TrackLn* d_track = nullptr; uint8_t *d_skip = nullptr, *d_claims = nullptr; int* d_count = nullptr;
+    int pcap = 0;
 };
 
 #define HVO_TRYB(call) do { if ((call) != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(cudaGetLastError())); return HVO_ERR_CUDA; } } while (0)
@@ -280,7 +354,8 @@ void hvo_lproj_destroy(hvo_lproj* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_kl, h->d_keys, h->d_func, h->d_l3d, h->d_desc, h->d_claimed, h->d_qdesc, h->d_cells, h->d_claim0, h->d_claim_a,
-                    h->d_claim_b, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_q};
+                    h->d_claim_b, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_q, h->d_thr, h->d_lines, h->d_track, h->d_skip, h->d_claims,
+                    h->d_count};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -356,34 +431,25 @@ int hvo_lproj_features_in_area(hvo_lproj* h, float x1, float y1, float x2, float
     return HVO_OK;
 }
 
-int hvo_lproj_search(hvo_lproj* h, const hvo_lproj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, float nnratio,
-                     int32_t* match_idx, int32_t* match_dist, int* n_matches) {
-    HVO_CHECK_ARG(h && match_idx, "null argument");
-    HVO_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (map lines) or 1 (last frame)");
-    if (n_matches) *n_matches = 0;
-    if (nq <= 0) return HVO_OK;
-    HVO_CHECK_ARG(queries && qdesc, "null queries");
-    if (h->n == 0) {
-        for (int i = 0; i < nq; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
-        return HVO_OK;
-    }
-    HVO_CHECK_ARG(mode == 1 || h->has3d, "mode 0 needs the frame's 3-D lines (lines3d of hvo_lproj_set_frame)");
-    HVO_CUDA(cudaSetDevice(h->device));
-    if (nq > h->qcap) {
-        const int cap = std::max(nq, 1024);
-        int st;
-        if ((st = lgrow(h->d_q, cap)) || (st = lgrow(h->d_qdesc, (size_t)cap * 32)) || (st = lgrow(h->d_choice, cap)) || (st = lgrow(h->d_cdist, cap))) return st;
-        h->qcap = cap;
-    }
+static int lproj_reserve_queries(hvo_lproj* h, int nq) {
+    if (nq <= h->qcap) return HVO_OK;
+    const int cap = std::max(nq, 1024);
+    int st;
+    if ((st = lgrow(h->d_q, cap)) || (st = lgrow(h->d_qdesc, (size_t)cap * 32)) || (st = lgrow(h->d_choice, cap)) || (st = lgrow(h->d_cdist, cap))) return st;
+    h->qcap = cap;
+    return HVO_OK;
+}
+// the fixed-point rounds over nq device-resident queries (h->d_q, h->d_qdesc)
+static int lproj_run_rounds(hvo_lproj* h, int nq, const uint8_t* claimed, int mode, float nnratio, int32_t* match_idx, int32_t* match_dist,
+                            int* n_matches, int launches) {
     cudaStream_t s = h->stream;
-    HVO_CUDA(cudaMemcpyAsync(h->d_q, queries, (size_t)nq * sizeof(LQuery), cudaMemcpyHostToDevice, s));
-    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
     if (claimed) HVO_CUDA(cudaMemcpyAsync(h->d_claimed, claimed, (size_t)h->n, cudaMemcpyHostToDevice, s));
     k_lproj_claim_init<<<div_up(h->n, 256), 256, 0, s>>>(claimed ? h->d_claimed : nullptr, h->n, h->d_claim0);
     HVO_CUDA(cudaMemcpyAsync(h->d_claim_a, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
     k_lproj_fill<<<div_up(nq, 256), 256, 0, s>>>(h->d_choice, nq, -2);
     const double th_normal = std::cos(15.0 / 180.0 * M_PI), cos_th_angle = std::cos(10.0 / 180.0 * M_PI);  // LSDmatcher.cpp:713-715, 563-565
-    int launches = 2, rounds = 0;
+    launches += 2;
+    int rounds = 0;
     int *prev = h->d_claim_a, *next = h->d_claim_b;
     while (true) {
         HVO_CUDA(cudaMemcpyAsync(next, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -405,6 +471,107 @@ int hvo_lproj_search(hvo_lproj* h, const hvo_lproj_query* queries, const uint8_t
     HVO_CUDA(cudaStreamSynchronize(s));
     if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
     return HVO_OK;
+}
+
+int hvo_lproj_search(hvo_lproj* h, const hvo_lproj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, float nnratio,
+                     int32_t* match_idx, int32_t* match_dist, int* n_matches) {
+    HVO_CHECK_ARG(h && match_idx, "null argument");
+    HVO_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (map lines) or 1 (last frame)");
+    if (n_matches) *n_matches = 0;
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(queries && qdesc, "null queries");
+    if (h->n == 0) {
+        for (int i = 0; i < nq; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
+        return HVO_OK;
+    }
+    HVO_CHECK_ARG(mode == 1 || h->has3d, "mode 0 needs the frame's 3-D lines (lines3d of hvo_lproj_set_frame)");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = lproj_reserve_queries(h, nq);
+    if (st != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_q, queries, (size_t)nq * sizeof(LQuery), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    return lproj_run_rounds(h, nq, claimed, mode, nnratio, match_idx, match_dist, n_matches, 0);
+}
+
+// ---- isInFrustum over a batch of map lines, alone or in front of the search ----
+static const int kLThrLo = -32, kLThrN = 96;   // MapLine::PredictScale levels representable: [-32, 64]
+static int lproj_prepare_frustum(hvo_lproj* h, const hvo_frustum_cam* cam, int n) {
+    if (!h->d_thr) { int st; if ((st = lgrow(h->d_thr, kLThrN)) || (st = lgrow(h->d_count, 1))) return st; }
+    if (h->thr_log != cam->log_scale_factor) {
+        float thr[kLThrN];
+        int st = hvo_predict_scale_thresholds(cam->log_scale_factor, kLThrLo, kLThrN, thr);
+        if (st != HVO_OK) return st;
+        HVO_CUDA(cudaMemcpyAsync(h->d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, h->stream));
+        HVO_CUDA(cudaStreamSynchronize(h->stream));
+        h->thr_log = cam->log_scale_factor;
+    }
+    if (n > h->pcap) {
+        const int cap = std::max(n, 2048);
+        int st;
+        if ((st = lgrow(h->d_lines, cap)) || (st = lgrow(h->d_track, cap)) || (st = lgrow(h->d_skip, cap)) || (st = lgrow(h->d_claims, cap))) return st;
+        h->pcap = cap;
+    }
+    return HVO_OK;
+}
+static LFrustumCam make_lcam(const hvo_frustum_cam* cam) {
+    LFrustumCam c;
+    for (int i = 0; i < 9; ++i) c.R[i] = cam->Rcw[i];
+    for (int i = 0; i < 3; ++i) { c.t[i] = cam->tcw[i]; c.O[i] = cam->Ow[i]; }
+    c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy;
+    c.min_x = cam->min_x; c.min_y = cam->min_y; c.max_x = cam->max_x; c.max_y = cam->max_y; c.thr_lo = kLThrLo; c.thr_n = kLThrN;
+    return c;
+}
+
+int hvo_lproj_frustum_lines(hvo_lproj* h, const hvo_frustum_cam* cam, const hvo_map_line* lines, int n, float viewing_cos_limit, hvo_track_line* out) {
+    HVO_CHECK_ARG(h && cam && out, "null argument");
+    if (n <= 0) return HVO_OK;
+    HVO_CHECK_ARG(lines, "null map lines");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = lproj_prepare_frustum(h, cam, n);
+    if (st != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_lines, lines, (size_t)n * sizeof(MapLn), cudaMemcpyHostToDevice, s));
+    k_frustum_lines<<<div_up(n, 128), 128, 0, s>>>(make_lcam(cam), h->d_lines, nullptr, nullptr, n, viewing_cos_limit, h->d_thr, 1.f, h->d_track, nullptr,
+                                                   nullptr);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(out, h->d_track, (size_t)n * sizeof(TrackLn), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_lproj_search_local_map(hvo_lproj* h, const hvo_frustum_cam* cam, const hvo_map_line* lines, const uint8_t* ldesc, const uint8_t* skip,
+                               const uint8_t* claims, int n, float viewing_cos_limit, float th, const uint8_t* claimed, float nnratio,
+                               hvo_track_line* track, int32_t* match_idx, int32_t* match_dist, int* n_in_view, int* n_matches) {
+    HVO_CHECK_ARG(h && cam && match_idx, "null argument");
+    if (n_matches) *n_matches = 0;
+    if (n_in_view) *n_in_view = 0;
+    if (n <= 0) return HVO_OK;
+    HVO_CHECK_ARG(lines && ldesc, "null map lines / descriptors");
+    HVO_CHECK_ARG(h->n == 0 || h->has3d, "the search needs the frame's 3-D lines (lines3d of hvo_lproj_set_frame)");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = lproj_prepare_frustum(h, cam, n);
+    if (st != HVO_OK || (st = lproj_reserve_queries(h, n)) != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_lines, lines, (size_t)n * sizeof(MapLn), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, ldesc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    if (skip) HVO_CUDA(cudaMemcpyAsync(h->d_skip, skip, (size_t)n, cudaMemcpyHostToDevice, s));
+    if (claims) HVO_CUDA(cudaMemcpyAsync(h->d_claims, claims, (size_t)n, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemsetAsync(h->d_count, 0, sizeof(int), s));
+    k_frustum_lines<<<div_up(n, 128), 128, 0, s>>>(make_lcam(cam), h->d_lines, skip ? h->d_skip : nullptr, claims ? h->d_claims : nullptr, n,
+                                                   viewing_cos_limit, h->d_thr, th, h->d_track, h->d_q, h->d_count);
+    HVO_CUDA(cudaGetLastError());
+    if (track) HVO_CUDA(cudaMemcpyAsync(track, h->d_track, (size_t)n * sizeof(TrackLn), cudaMemcpyDeviceToHost, s));
+    int count = 0;
+    HVO_CUDA(cudaMemcpyAsync(&count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    if (n_in_view) *n_in_view = count;
+    if (h->n == 0) {
+        for (int i = 0; i < n; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
+        return HVO_OK;
+    }
+    return lproj_run_rounds(h, n, claimed, 0, nnratio, match_idx, match_dist, n_matches, 1);
 }
 
 int hvo_lproj_last_rounds(const hvo_lproj* h) { return h ? h->last_rounds : 0; }

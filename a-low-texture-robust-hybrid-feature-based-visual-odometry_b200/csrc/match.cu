@@ -14,6 +14,8 @@
 #include <climits>
 #include <new>
 
+#include <vector>
+
 #include "hvo_common.cuh"
 
 namespace hvo {
@@ -122,6 +124,74 @@ __global__ void __launch_bounds__(kDistWarps * 32) k_distinctive(const uint4* __
     if (lane == 0) { best_idx[g] = bestIdx; best_median[g] = n > 0 ? bestMedian : -1; }
 }
 
+
+// ---- LSDmatcher::FrameBFMatchNew's epipolar test on the nearest neighbour (src/LSDmatcher.cpp:983-1029) + mutualOverlap (:1033-1108) ----
+// One thread per query line.  cv::Mat arithmetic as OpenCV evaluates it for CV_32F: F * p = float products summed in k order;
+// Mat::cross in float; `m /= s` = m * (float)(1. / s); cv::norm of a difference = sqrt of the double sum of squares, narrowed to float.
+struct F33 { float m[9]; };
+__device__ __forceinline__ void epi_mul(const F33& F, float x, float y, float* o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = __fadd_rn(__fadd_rn(__fmul_rn(F.m[3 * i], x), __fmul_rn(F.m[3 * i + 1], y)), __fmul_rn(F.m[3 * i + 2], 1.0f));
+}
+__device__ __forceinline__ void epi_cross(const float* a, const float* b, float* c) {   // a.cross(b)
+    c[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+    c[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+    c[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+}
+__device__ __forceinline__ float epi_dist(const float* a, const float* b) {
+    const float dx = __fsub_rn(a[0], b[0]), dy = __fsub_rn(a[1], b[1]), dz = __fsub_rn(a[2], b[2]);
+    return (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)), __dmul_rn((double)dz, (double)dz)));
+}
+__device__ float epi_mutual_overlap(const float (*pt)[3]) {
+    float max_dist = 0.0f;
+    int outer1 = 0, outer2 = 3, inner1, inner2;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 4; ++j) {
+            const float d = epi_dist(pt[i], pt[j]);
+            if (d > max_dist) { max_dist = d; outer1 = i; outer2 = j; }
+        }
+    if (max_dist < 1.0f) return 0.0f;
+    if (outer1 == 0) {
+        if (outer2 == 1) { inner1 = 2; inner2 = 3; }
+        else if (outer2 == 2) { inner1 = 1; inner2 = 3; }
+        else { inner1 = 1; inner2 = 2; }
+    } else if (outer1 == 1) {
+        inner1 = 0;
+        inner2 = outer2 == 2 ? 3 : 2;
+    } else { inner1 = 0; inner2 = 1; }
+    const float dx = __fsub_rn(pt[inner1][0], pt[inner2][0]), dy = __fsub_rn(pt[inner1][1], pt[inner2][1]), dz = __fsub_rn(pt[inner1][2], pt[inner2][2]);
+    const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)), __dmul_rn((double)dz, (double)dz)));
+    return (float)(nrm / (double)max_dist);
+}
+__global__ void k_lines_epipolar(const int32_t* __restrict__ idx2, const int32_t* __restrict__ dist2, const hvo_keyline* __restrict__ kls1, int n1,
+                                 const hvo_keyline* __restrict__ kls2, const double* __restrict__ func2, F33 F, float th, float nnratio,
+                                 int32_t* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n1) return;
+    int res = -1;
+    const int t = idx2[2 * q], t1 = idx2[2 * q + 1];
+    if (t >= 0 && t1 >= 0) {
+        const hvo_keyline a = kls1[q], b = kls2[t];
+        float e1[3], e2[3], pt[4][3];
+        epi_mul(F, a.startPointX, a.startPointY, e1);
+        epi_mul(F, a.endPointX, a.endPointY, e2);
+        const float l2[3] = {(float)func2[3 * t], (float)func2[3 * t + 1], (float)func2[3 * t + 2]};
+        epi_cross(l2, e1, pt[0]);
+        epi_cross(l2, e2, pt[1]);
+        if (fabs((double)pt[0][2]) > 1e-12 && fabs((double)pt[1][2]) > 1e-12) {
+            const float s0 = (float)(1.0 / (double)pt[0][2]), s1 = (float)(1.0 / (double)pt[1][2]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { pt[0][i] = __fmul_rn(pt[0][i], s0); pt[1][i] = __fmul_rn(pt[1][i], s1); }
+            pt[2][0] = b.startPointX; pt[2][1] = b.startPointY; pt[2][2] = 1.0f;
+            pt[3][0] = b.endPointX; pt[3][1] = b.endPointY; pt[3][2] = 1.0f;
+            const float score = epi_mutual_overlap(pt);
+            const float d0 = (float)dist2[2 * q], d1 = (float)dist2[2 * q + 1];
+            if (d0 < th && (double)score > 0.8 && d0 < __fmul_rn(nnratio, d1)) res = t;
+        }
+    }
+    out[q] = res;
+}
+
 }  // namespace hvo
 
 using namespace hvo;
@@ -172,10 +242,15 @@ int hvo_matcher_create(int device, hvo_matcher** out) {
     hvo_matcher* m = new (std::nothrow) hvo_matcher();
     if (!m) { set_error("out of host memory"); return HVO_ERR_ARG; }
     m->device = device;
-    HVO_CUDA(cudaSetDevice(device));
-    HVO_CUDA(create_stream(&m->stream));
-    for (auto& e : m->tev) HVO_CUDA(cudaEventCreate(&e));
-    HVO_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = create_stream(&m->stream);
+    for (auto& ev : m->tev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {   // one exit: nothing of the partial handle is leaked
+        set_error("hvo_matcher_create: %s", cudaGetErrorString(e));
+        hvo_matcher_destroy(m);
+        return HVO_ERR_CUDA;
+    }
     *out = m;
     return HVO_OK;
 }
@@ -259,6 +334,41 @@ int hvo_match_knn2(hvo_matcher* m, const uint8_t* q, int nq, const uint8_t* t, i
     HVO_CUDA(cudaMemcpyAsync(idx2, m->d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
     HVO_CUDA(cudaMemcpyAsync(dist2, m->d_dist, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
     HVO_CUDA(cudaStreamSynchronize(m->stream));
+    return HVO_OK;
+}
+
+int hvo_match_lines_epipolar(hvo_matcher* m, const uint8_t* ldesc1, const hvo_keyline* kls1, int n1, const uint8_t* ldesc2, const hvo_keyline* kls2,
+                             const double* kls2func, int n2, const float* F, float th, float nnratio, int32_t* line_matches) {
+    HVO_CHECK_ARG(m && line_matches && F, "null argument");
+    if (n1 <= 0) return HVO_OK;
+    for (int i = 0; i < n1; ++i) line_matches[i] = -1;
+    if (n2 < 2) return HVO_OK;          // knnMatch yields fewer than two neighbours: the reference's loop body never accepts
+    HVO_CHECK_ARG(ldesc1 && kls1 && ldesc2 && kls2 && kls2func, "null descriptors / keylines / line functions");
+    std::vector<int32_t> idx((size_t)n1 * 2), dist((size_t)n1 * 2);
+    int st = hvo_match_knn2(m, ldesc1, n1, ldesc2, n2, idx.data(), dist.data());   // leaves idx / dist of this call in m->d_idx / m->d_dist
+    if (st != HVO_OK) return st;
+    hvo_keyline *d_k1 = nullptr, *d_k2 = nullptr;
+    double* d_f = nullptr;
+    int32_t* d_out = nullptr;
+    cudaStream_t s = m->stream;
+    HVO_CUDA(cudaMallocAsync(&d_k1, (size_t)n1 * sizeof(hvo_keyline), s));
+    HVO_CUDA(cudaMallocAsync(&d_k2, (size_t)n2 * sizeof(hvo_keyline), s));
+    HVO_CUDA(cudaMallocAsync(&d_f, (size_t)n2 * 3 * sizeof(double), s));
+    HVO_CUDA(cudaMallocAsync(&d_out, (size_t)n1 * sizeof(int32_t), s));
+    HVO_CUDA(cudaMemcpyAsync(d_k1, kls1, (size_t)n1 * sizeof(hvo_keyline), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_k2, kls2, (size_t)n2 * sizeof(hvo_keyline), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(d_f, kls2func, (size_t)n2 * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    F33 f;
+    for (int i = 0; i < 9; ++i) f.m[i] = F[i];
+    k_lines_epipolar<<<div_up(n1, 128), 128, 0, s>>>(m->d_idx, m->d_dist, d_k1, n1, d_k2, d_f, f, th, nnratio, d_out);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(line_matches, d_out, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaFreeAsync(d_k1, s));
+    HVO_CUDA(cudaFreeAsync(d_k2, s));
+    HVO_CUDA(cudaFreeAsync(d_f, s));
+    HVO_CUDA(cudaFreeAsync(d_out, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    m->last_launches = 3;
     return HVO_OK;
 }
 

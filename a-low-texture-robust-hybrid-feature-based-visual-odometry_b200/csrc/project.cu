@@ -19,6 +19,8 @@
 // the sequential result.  Conflicts are rare, so this takes two or three rounds.
 #include <algorithm>
 #include <climits>
+#include <cmath>
+#include <cstring>
 #include <new>
 
 #include "hvo_common.cuh"
@@ -342,6 +344,138 @@ __global__ void __launch_bounds__(128) k_tri_search(const uint4* __restrict__ qd
 
 using namespace hvo;
 
+
+// ---- Frame::isInFrustum(MapPoint*, viewingCosLimit)  (src/Frame.cc:1371-1436) --------------------------------------------------
+// One thread per map point.  The arithmetic follows the reference's cv::Mat expressions as OpenCV evaluates them for CV_32F:
+//   mRcw * P + mtcw      cv::gemm 3x3 * 3x1: float products summed in k order, then (float)(double(t) + double(c))
+//   cv::norm(PO)         sqrt of the sum of squares accumulated in double, in order
+//   PO.dot(Pn) / dist    products accumulated in double, in order, divided in double
+// everything else in float, one rounding per operation.  PredictScale compares the ratio with host-made thresholds.
+struct FrustumCam { float R[9], t[3], O[3], fx, fy, cx, cy, bf, min_x, min_y, max_x, max_y; int n_levels; };
+struct MapPt { float pos[3], normal[3], min_dist, max_dist; };           // hvo_map_point
+struct TrackPt { float u, v, ur; int level; float view_cos; int in_view; };  // hvo_track_point
+
+__device__ __forceinline__ float gemm_row3(const float* r, float x, float y, float z, float c) {
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(r[0], x), __fmul_rn(r[1], y)), __fmul_rn(r[2], z));
+    return (float)((double)t + (double)c);
+}
+__device__ __forceinline__ TrackPt frustum_point(const FrustumCam& c, const MapPt& m, float cos_limit, const float* __restrict__ thr) {
+    TrackPt o;
+    o.u = o.v = o.ur = 0.f; o.level = 0; o.view_cos = 0.f; o.in_view = 0;
+    const float X = gemm_row3(c.R + 0, m.pos[0], m.pos[1], m.pos[2], c.t[0]);
+    const float Y = gemm_row3(c.R + 3, m.pos[0], m.pos[1], m.pos[2], c.t[1]);
+    const float Z = gemm_row3(c.R + 6, m.pos[0], m.pos[1], m.pos[2], c.t[2]);
+    if (Z < 0.0f) return o;
+    const float invz = __fdiv_rn(1.0f, Z);
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, X), invz), c.cx);
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, Y), invz), c.cy);
+    if (u < c.min_x || u > c.max_x) return o;
+    if (v < c.min_y || v > c.max_y) return o;
+    const float px = __fsub_rn(m.pos[0], c.O[0]), py = __fsub_rn(m.pos[1], c.O[1]), pz = __fsub_rn(m.pos[2], c.O[2]);
+    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)px, (double)px), __dmul_rn((double)py, (double)py)), __dmul_rn((double)pz, (double)pz));
+    const float dist = (float)sqrt(n2);
+    if (dist < __fmul_rn(0.8f, m.min_dist) || dist > __fmul_rn(1.2f, m.max_dist)) return o;   // Get{Min,Max}DistanceInvariance
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)px, (double)m.normal[0]), __dmul_rn((double)py, (double)m.normal[1])),
+                                 __dmul_rn((double)pz, (double)m.normal[2]));
+    const float view_cos = (float)(dot / (double)dist);
+    if (view_cos < cos_limit) return o;
+    const float ratio = __fdiv_rn(m.max_dist, dist);
+    int level = 0;
+    for (int k = 0; k < c.n_levels - 1; ++k) level += ratio >= thr[k];
+    o.u = u; o.v = v; o.ur = __fsub_rn(u, __fmul_rn(c.bf, invz)); o.level = level; o.view_cos = view_cos; o.in_view = 1;
+    return o;
+}
+
+// mode: bit 0 = write TrackPt, bit 1 = write the search query (ORBmatcher::SearchByProjection(F, vpMapPoints, th), :58-71)
+__global__ void __launch_bounds__(128) k_frustum_points(FrustumCam c, const MapPt* __restrict__ pts, const uint8_t* __restrict__ skip,
+                                                        const uint8_t* __restrict__ claims, int n, float cos_limit,
+                                                        const float* __restrict__ thr, float th, const float* __restrict__ scale_factors,
+                                                        TrackPt* __restrict__ track, ProjQuery* __restrict__ qs, int* __restrict__ n_in_view) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    TrackPt o;
+    o.u = o.v = o.ur = 0.f; o.level = 0; o.view_cos = 0.f; o.in_view = 0;
+    if (!(skip && skip[i])) o = frustum_point(c, pts[i], cos_limit, thr);
+    if (track) track[i] = o;
+    if (qs) {
+        ProjQuery q;
+        if (o.in_view) {
+            float r = ((double)o.view_cos > 0.998) ? 2.5f : 4.0f;      // RadiusByViewingCos, ORBmatcher.cc:134-140
+            if (th != 1.0f) r = __fmul_rn(r, th);
+            q.u = o.u; q.v = o.v; q.r = __fmul_rn(r, scale_factors[o.level]);
+            q.min_level = o.level - 1; q.max_level = o.level; q.ur = o.ur; q.claims = claims ? (claims[i] != 0) : 1; q.pad = 0;
+        } else {   // not searched: an empty window
+            q.u = -1e30f; q.v = -1e30f; q.r = -1.f; q.min_level = 0; q.max_level = 0; q.ur = 0.f; q.claims = 0; q.pad = 0;
+        }
+        qs[i] = q;
+    }
+    if (n_in_view && o.in_view) atomicAdd(n_in_view, 1);
+}
+
+// ---- ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:412-497) ------------------------------------------------------------
+// The loop is sequential through vMatchedDistance / vnMatches21 (a later query may take a keypoint over and un-match an earlier one),
+// and it only runs for the monocular initialisation: one warp walks the queries in order, 32 candidates of the window at a time.
+__global__ void __launch_bounds__(32) k_init_search(const ProjKey* __restrict__ pk, const uint4* __restrict__ desc, const int* __restrict__ cell_start,
+                                                    const int* __restrict__ cell_items, GridGeom g, int n2, const float2* __restrict__ prev,
+                                                    const int* __restrict__ octave1, const uint4* __restrict__ desc1, int n1, float window,
+                                                    int th_dist, float nnratio, int* __restrict__ matched_dist, int* __restrict__ matches21,
+                                                    int* __restrict__ matches12, int* __restrict__ accepted12, int* __restrict__ n_matches) {
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n2; i += 32) { matched_dist[i] = INT_MAX; matches21[i] = -1; }
+    for (int i = lane; i < n1; i += 32) { matches12[i] = -1; accepted12[i] = -1; }
+    __syncwarp();
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (octave1[i1] > 0) continue;
+        const float2 c = prev[i1];
+        const ProjWindow w = proj_window(g, c.x, c.y, window);
+        if (w.empty) continue;
+        const uint4 qa = desc1[2 * i1], qb = desc1[2 * i1 + 1];
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int ix = w.x0; ix <= w.x1; ++ix) {
+            const int b = cell_start[ix * kGridRows + w.y0], e = cell_start[ix * kGridRows + w.y1 + 1];
+            for (int base = b; base < e; base += 32) {
+                const int i = base + lane;
+                int id = -1, dist = 256;
+                bool ok = false;
+                if (i < e) {
+                    id = cell_items[i];
+                    ok = proj_in_area(pk[id], c.x, c.y, window, 0, 0);
+                    if (ok) {
+                        const uint4 da = desc[2 * id], db = desc[2 * id + 1];
+                        dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                               __popc(qb.x ^ db.x) + __popc(qb.y ^ db.y) + __popc(qb.z ^ db.z) + __popc(qb.w ^ db.w);
+                        ok = !(matched_dist[id] <= dist);
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ok);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int d = __shfl_sync(0xffffffffu, dist, j), cidx = __shfl_sync(0xffffffffu, id, j);
+                    if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = cidx; }
+                    else if (d < bestDist2) bestDist2 = d;
+                }
+            }
+        }
+        if (bestDist <= th_dist && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {
+            if (lane == 0) {
+                const int old = matches21[bestIdx2];
+                if (old >= 0) matches12[old] = -1;       // a taken-over keypoint un-matches its previous owner
+                matches12[i1] = bestIdx2;
+                accepted12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matched_dist[bestIdx2] = bestDist;
+            }
+        }
+        __syncwarp();
+    }
+    // nmatches = accepted - taken over = entries of matches12 that survive
+    int cnt = 0;
+    for (int i = lane; i < n1; i += 32) cnt += matches12[i] >= 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) *n_matches = cnt;
+}
+
 struct hvo_proj {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -363,6 +497,12 @@ struct hvo_proj {
     int4* d_best4 = nullptr;
     float* d_inv_sigma2 = nullptr;  // [64] mvInvLevelSigma2 (mode 2)
     bool has_sigma = false;
+    // local-map projection (isInFrustum + search) and SearchForInitialization
+    float* d_thr = nullptr;         // [64] PredictScale thresholds, [64..128) scale factors
+    float thr_log = 0.f; int thr_levels = 0;
+    MapPt* d_pts = nullptr; TrackPt* d_track = nullptr; uint8_t *d_skip = nullptr, *d_claims = nullptr;
+    int pcap = 0;
+    int *d_m21 = nullptr, *d_mdist = nullptr; int icap = 0;
     int last_rounds = 0, last_launches = 0;
 };
 
@@ -420,6 +560,7 @@ int hvo_proj_create(int device, hvo_proj** out) {
         HVO_TRY(cudaMalloc(&h->d_cell_start, (kGridCells + 1) * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_flag, 2 * sizeof(int)));
         HVO_TRY(cudaMalloc(&h->d_inv_sigma2, 64 * sizeof(float)));
+        HVO_TRY(cudaMalloc(&h->d_thr, 128 * sizeof(float)));
         HVO_TRY(cudaMallocHost(&h->h_flag, 2 * sizeof(int)));
 #undef HVO_TRY
     } while (0);
@@ -434,7 +575,7 @@ void hvo_proj_destroy(hvo_proj* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_keys, h->d_uright, h->d_desc, h->d_pk, h->d_cell_start, h->d_cell_items, h->d_cell_of, h->d_claimed, h->d_claim0,
                     h->d_claim_a, h->d_claim_b, h->d_q, h->d_qdesc, h->d_choice, h->d_cdist, h->d_flag, h->d_area, h->d_off, h->d_cand, h->d_best4,
-                    h->d_inv_sigma2};
+                    h->d_inv_sigma2, h->d_thr, h->d_pts, h->d_track, h->d_skip, h->d_claims, h->d_m21, h->d_mdist};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->h_flag) cudaFreeHost(h->h_flag);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
@@ -495,30 +636,17 @@ int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_le
     return HVO_OK;
 }
 
-int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
-                    float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
-    HVO_CHECK_ARG(h && match_idx, "null argument");
-    HVO_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (best + second, level ratio), 1 (best only) or 2 (Fuse: reprojection gate)");
-    HVO_CHECK_ARG(mode != 2 || (h->has_sigma && !claimed), "mode 2 needs hvo_proj_set_level_sigma and takes no claimed array");
-    if (n_matches) *n_matches = 0;
-    if (nq <= 0) return HVO_OK;
-    HVO_CHECK_ARG(queries && qdesc, "null queries");
-    if (h->n == 0) {
-        for (int i = 0; i < nq; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
-        return HVO_OK;
-    }
-    HVO_CUDA(cudaSetDevice(h->device));
-    int st = proj_reserve_queries(h, nq);
-    if (st != HVO_OK) return st;
+// the fixed-point rounds over nq device-resident queries (h->d_q, h->d_qdesc); results copied to the host arrays
+static int proj_run_rounds(hvo_proj* h, int nq, const uint8_t* claimed, int mode, int th_dist, float nnratio, int32_t* match_idx, int32_t* match_dist,
+                           int* n_matches, int launches) {
     cudaStream_t s = h->stream;
-    HVO_CUDA(cudaMemcpyAsync(h->d_q, queries, (size_t)nq * sizeof(ProjQuery), cudaMemcpyHostToDevice, s));
-    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
     if (claimed) HVO_CUDA(cudaMemcpyAsync(h->d_claimed, claimed, (size_t)h->n, cudaMemcpyHostToDevice, s));
     const int nb = div_up(h->n, 256);
     k_proj_claim_init<<<nb, 256, 0, s>>>(claimed ? h->d_claimed : nullptr, h->n, h->d_claim0);
     HVO_CUDA(cudaMemcpyAsync(h->d_claim_a, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
     k_proj_fill<<<div_up(nq, 256), 256, 0, s>>>(h->d_choice, nq, -2);
-    int launches = 2, rounds = 0;
+    launches += 2;
+    int rounds = 0;
     int *prev = h->d_claim_a, *next = h->d_claim_b;
     while (true) {
         HVO_CUDA(cudaMemcpyAsync(next, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -539,6 +667,163 @@ int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* q
     if (match_dist) HVO_CUDA(cudaMemcpyAsync(match_dist, h->d_cdist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
     HVO_CUDA(cudaStreamSynchronize(s));
     if (n_matches) { int c = 0; for (int i = 0; i < nq; ++i) c += match_idx[i] >= 0; *n_matches = c; }
+    return HVO_OK;
+}
+
+int hvo_proj_search(hvo_proj* h, const hvo_proj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, int th_dist,
+                    float nnratio, int32_t* match_idx, int32_t* match_dist, int* n_matches) {
+    HVO_CHECK_ARG(h && match_idx, "null argument");
+    HVO_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (best + second, level ratio), 1 (best only) or 2 (Fuse: reprojection gate)");
+    HVO_CHECK_ARG(mode != 2 || (h->has_sigma && !claimed), "mode 2 needs hvo_proj_set_level_sigma and takes no claimed array");
+    if (n_matches) *n_matches = 0;
+    if (nq <= 0) return HVO_OK;
+    HVO_CHECK_ARG(queries && qdesc, "null queries");
+    if (h->n == 0) {
+        for (int i = 0; i < nq; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
+        return HVO_OK;
+    }
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_queries(h, nq);
+    if (st != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_q, queries, (size_t)nq * sizeof(ProjQuery), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, qdesc, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    return proj_run_rounds(h, nq, claimed, mode, th_dist, nnratio, match_idx, match_dist, n_matches, 0);
+}
+
+// ---- isInFrustum over a batch of map points, alone or in front of the search ----
+static float predict_scale_host(float ratio, float log_scale_factor) { return std::ceil(std::log(ratio) / log_scale_factor); }  // float logf, float division
+
+int hvo_predict_scale_thresholds(float log_scale_factor, int lo, int n, float* thresholds) {
+    HVO_CHECK_ARG(thresholds && n >= 0 && log_scale_factor > 0.f, "null thresholds / non-positive log scale factor");
+    for (int k = 0; k < n; ++k) {
+        // smallest positive float r with ceil(logf(r) / L) > lo + k; bit patterns of positive floats are ordered like their values
+        const float want = (float)(lo + k);
+        uint32_t a = 0x00800000u, b = 0x7f800000u;   // predicate false at a (log of the smallest normal is hugely negative), true at +inf
+        while (b - a > 1) {
+            const uint32_t mid = a + (b - a) / 2;
+            float r; std::memcpy(&r, &mid, 4);
+            if (predict_scale_host(r, log_scale_factor) > want) b = mid; else a = mid;
+        }
+        std::memcpy(&thresholds[k], &b, 4);
+    }
+    return HVO_OK;
+}
+
+static int proj_reserve_points(hvo_proj* h, int n) {
+    if (n <= h->pcap) return HVO_OK;
+    const int cap = std::max(n, 4096);
+    int st;
+    if ((st = grow(h->d_pts, cap)) || (st = grow(h->d_track, cap)) || (st = grow(h->d_skip, cap)) || (st = grow(h->d_claims, cap))) return st;
+    h->pcap = cap;
+    return HVO_OK;
+}
+static int proj_set_thresholds(hvo_proj* h, const hvo_frustum_cam* cam) {
+    HVO_CHECK_ARG(cam->n_levels >= 1 && cam->n_levels <= 64, "n_levels must be in [1, 64]");
+    if (h->thr_log == cam->log_scale_factor && h->thr_levels == cam->n_levels) return HVO_OK;
+    float thr[64];
+    int st = hvo_predict_scale_thresholds(cam->log_scale_factor, 0, cam->n_levels - 1, thr);
+    if (st != HVO_OK) return st;
+    HVO_CUDA(cudaMemcpyAsync(h->d_thr, thr, sizeof(float) * (size_t)(cam->n_levels - 1), cudaMemcpyHostToDevice, h->stream));
+    HVO_CUDA(cudaStreamSynchronize(h->stream));   // thr lives on this stack frame
+    h->thr_log = cam->log_scale_factor; h->thr_levels = cam->n_levels;
+    return HVO_OK;
+}
+static FrustumCam make_cam(const hvo_frustum_cam* cam) {
+    FrustumCam c;
+    for (int i = 0; i < 9; ++i) c.R[i] = cam->Rcw[i];
+    for (int i = 0; i < 3; ++i) { c.t[i] = cam->tcw[i]; c.O[i] = cam->Ow[i]; }
+    c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy; c.bf = cam->bf;
+    c.min_x = cam->min_x; c.min_y = cam->min_y; c.max_x = cam->max_x; c.max_y = cam->max_y; c.n_levels = cam->n_levels;
+    return c;
+}
+
+int hvo_proj_frustum_points(hvo_proj* h, const hvo_frustum_cam* cam, const hvo_map_point* pts, int n, float viewing_cos_limit, hvo_track_point* out) {
+    HVO_CHECK_ARG(h && cam && out, "null argument");
+    if (n <= 0) return HVO_OK;
+    HVO_CHECK_ARG(pts, "null map points");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_points(h, n);
+    if (st != HVO_OK || (st = proj_set_thresholds(h, cam)) != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)n * sizeof(MapPt), cudaMemcpyHostToDevice, s));
+    k_frustum_points<<<div_up(n, 128), 128, 0, s>>>(make_cam(cam), h->d_pts, nullptr, nullptr, n, viewing_cos_limit, h->d_thr, 1.f, nullptr, h->d_track,
+                                                    nullptr, nullptr);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(out, h->d_track, (size_t)n * sizeof(TrackPt), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_proj_search_local_map(hvo_proj* h, const hvo_frustum_cam* cam, const hvo_map_point* pts, const uint8_t* pdesc, const uint8_t* skip,
+                              const uint8_t* claims, int n, float viewing_cos_limit, float th, const float* scale_factors, const uint8_t* claimed,
+                              int th_dist, float nnratio, hvo_track_point* track, int32_t* match_idx, int32_t* match_dist, int* n_in_view,
+                              int* n_matches) {
+    HVO_CHECK_ARG(h && cam && match_idx && scale_factors, "null argument");
+    if (n_matches) *n_matches = 0;
+    if (n_in_view) *n_in_view = 0;
+    if (n <= 0) return HVO_OK;
+    HVO_CHECK_ARG(pts && pdesc, "null map points / descriptors");
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_points(h, n);
+    if (st != HVO_OK || (st = proj_reserve_queries(h, n)) != HVO_OK || (st = proj_set_thresholds(h, cam)) != HVO_OK) return st;
+    cudaStream_t s = h->stream;
+    HVO_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)n * sizeof(MapPt), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, pdesc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    if (skip) HVO_CUDA(cudaMemcpyAsync(h->d_skip, skip, (size_t)n, cudaMemcpyHostToDevice, s));
+    if (claims) HVO_CUDA(cudaMemcpyAsync(h->d_claims, claims, (size_t)n, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_thr + 64, scale_factors, sizeof(float) * (size_t)cam->n_levels, cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemsetAsync(h->d_flag + 1, 0, sizeof(int), s));
+    k_frustum_points<<<div_up(n, 128), 128, 0, s>>>(make_cam(cam), h->d_pts, skip ? h->d_skip : nullptr, claims ? h->d_claims : nullptr, n,
+                                                    viewing_cos_limit, h->d_thr, th, h->d_thr + 64, h->d_track, h->d_q, h->d_flag + 1);
+    HVO_CUDA(cudaGetLastError());
+    if (track) HVO_CUDA(cudaMemcpyAsync(track, h->d_track, (size_t)n * sizeof(TrackPt), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaMemcpyAsync(h->h_flag + 1, h->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (h->n == 0) {
+        HVO_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < n; ++i) { match_idx[i] = -1; if (match_dist) match_dist[i] = 256; }
+        if (n_in_view) *n_in_view = h->h_flag[1];
+        return HVO_OK;
+    }
+    st = proj_run_rounds(h, n, claimed, 0, th_dist, nnratio, match_idx, match_dist, n_matches, 1);
+    if (st == HVO_OK && n_in_view) *n_in_view = h->h_flag[1];
+    return st;
+}
+
+int hvo_proj_search_initialization(hvo_proj* h, const float* prev_matched_xy, const int32_t* octave1, const uint8_t* desc1, int n1, int window_size,
+                                   int th_dist, float nnratio, int32_t* matches12, int32_t* accepted12, int* n_matches) {
+    HVO_CHECK_ARG(h && matches12, "null argument");
+    if (n_matches) *n_matches = 0;
+    if (n1 <= 0) return HVO_OK;
+    HVO_CHECK_ARG(prev_matched_xy && octave1 && desc1, "null queries");
+    if (h->n == 0) {
+        for (int i = 0; i < n1; ++i) { matches12[i] = -1; if (accepted12) accepted12[i] = -1; }
+        return HVO_OK;
+    }
+    HVO_CUDA(cudaSetDevice(h->device));
+    int st = proj_reserve_queries(h, n1);
+    if (st != HVO_OK) return st;
+    if (h->n > h->icap) {
+        const int cap = std::max(h->n, 2048);
+        if ((st = grow(h->d_m21, cap)) || (st = grow(h->d_mdist, cap))) return st;
+        h->icap = cap;
+    }
+    cudaStream_t s = h->stream;
+    // query staging reuses the search buffers: d_q holds the window centres (8 B each), d_off the octaves, d_choice / d_cdist the results
+    HVO_CUDA(cudaMemcpyAsync(h->d_q, prev_matched_xy, (size_t)n1 * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_off, octave1, (size_t)n1 * sizeof(int), cudaMemcpyHostToDevice, s));
+    HVO_CUDA(cudaMemcpyAsync(h->d_qdesc, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    k_init_search<<<1, 32, 0, s>>>(h->d_pk, reinterpret_cast<const uint4*>(h->d_desc), h->d_cell_start, h->d_cell_items, h->g, h->n,
+                                   reinterpret_cast<const float2*>(h->d_q), h->d_off, reinterpret_cast<const uint4*>(h->d_qdesc), n1, (float)window_size,
+                                   th_dist, nnratio, h->d_mdist, h->d_m21, h->d_choice, h->d_cdist, h->d_flag);
+    HVO_CUDA(cudaGetLastError());
+    HVO_CUDA(cudaMemcpyAsync(matches12, h->d_choice, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (accepted12) HVO_CUDA(cudaMemcpyAsync(accepted12, h->d_cdist, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    HVO_CUDA(cudaStreamSynchronize(s));
+    if (n_matches) *n_matches = h->h_flag[0];
+    h->last_launches = 1; h->last_rounds = 1;
     return HVO_OK;
 }
 

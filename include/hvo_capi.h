@@ -219,6 +219,56 @@ int hvo_proj_search_triangulation(hvo_proj* h, const uint8_t* qdesc, const hvo_k
                                   const hvo_keypoint* tkeys, const uint8_t* tflags, int nt, const int32_t* offsets, const int32_t* cand,
                                   const float* F12, float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
                                   int only_stereo, int th_low, int32_t* match_idx, int32_t* match_dist, int* n_matches);
+/* ---- tracking-time projection: Frame::isInFrustum(MapPoint*, float) (src/Frame.cc:1371-1436) for a batch of map points, and the
+ * whole of Tracking::SearchLocalPoints' device work (src/Tracking.cc:3251-3268): isInFrustum over the local map followed by
+ * ORBmatcher::SearchByProjection(F, vpMapPoints, th) in one call, the queries never leaving the device.
+ * Arithmetic is the reference's: mRcw * P + mtcw as cv::gemm evaluates it for CV_32F (float products and sums in k order, then
+ * (float)(double(t) + double(c))), cv::norm / Mat::dot with double accumulation, every other operation in float.  MapPoint::PredictScale
+ * (src/MapPoint.cc:400-415) = ceil(logf(maxDistance / dist) / mfLogScaleFactor) clamped to [0, nlevels): the level is found by comparing the
+ * ratio with thresholds the HOST derives from its own logf by bisection over float bit patterns (hvo_predict_scale_thresholds), so the
+ * level is the one the reference's libm yields, bit for bit, without a device logarithm. */
+typedef struct hvo_frustum_cam {
+    float Rcw[9];                      /* mRcw, row-major */
+    float tcw[3];                      /* mtcw */
+    float Ow[3];                       /* mOw */
+    float fx, fy, cx, cy, bf;          /* Frame::fx, fy, cx, cy, mbf */
+    float min_x, min_y, max_x, max_y;  /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float log_scale_factor;            /* mfLogScaleFactor */
+    int32_t n_levels;                  /* mnScaleLevels */
+} hvo_frustum_cam;
+typedef struct hvo_map_point {
+    float pos[3];     /* MapPoint::GetWorldPos() */
+    float normal[3];  /* GetNormal() */
+    float min_distance, max_distance; /* mfMinDistance, mfMaxDistance: the range test uses 0.8f * min and 1.2f * max
+                                         (Get{Min,Max}DistanceInvariance, src/MapPoint.cc:371-381), PredictScale mfMaxDistance itself */
+} hvo_map_point;
+typedef struct hvo_track_point { /* what isInFrustum leaves in the MapPoint (mTrackProjX, mTrackProjY, mTrackProjXR, mnTrackScaleLevel, mTrackViewCos, mbTrackInView) */
+    float u, v, ur;
+    int32_t level;
+    float view_cos;
+    int32_t in_view;
+} hvo_track_point;
+/* thresholds[k], k in [0, n): the smallest float ratio with ceil(logf(ratio) / log_scale_factor) > k + lo, i.e.
+ * level(ratio) = lo + #{k : ratio >= thresholds[k]} for levels in [lo, lo + n].  Host function (uses the C library's logf). */
+int hvo_predict_scale_thresholds(float log_scale_factor, int lo, int n, float* thresholds);
+/* out[i] for every map point; fields other than in_view are only meaningful where in_view != 0 */
+int hvo_proj_frustum_points(hvo_proj* h, const hvo_frustum_cam* cam, const hvo_map_point* pts, int n, float viewing_cos_limit, hvo_track_point* out);
+/* skip[i] != 0: the map point is not projected (mnLastFrameSeen == frame id, or isBad()); claims[i] != 0: it has observations.
+ * pdesc [n][32] = MapPoint::GetDescriptor().  scale_factors = F.mvScaleFactors.  track (may be NULL) receives the isInFrustum
+ * result; match_idx[i] = keypoint of the frame set by hvo_proj_set_frame that map point i is assigned to, or -1.  claimed as for
+ * hvo_proj_search. */
+int hvo_proj_search_local_map(hvo_proj* h, const hvo_frustum_cam* cam, const hvo_map_point* pts, const uint8_t* pdesc, const uint8_t* skip,
+                              const uint8_t* claims, int n, float viewing_cos_limit, float th, const float* scale_factors, const uint8_t* claimed,
+                              int th_dist, float nnratio, hvo_track_point* track, int32_t* match_idx, int32_t* match_dist, int* n_in_view,
+                              int* n_matches);
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:412-497): the sequential
+ * loop with its vMatchedDistance / vnMatches21 state, for the frame set by hvo_proj_set_frame as F2.  Queries = the level-0
+ * keypoints of F1 in index order: window centre prev_matched[i] (x, y), F1's descriptors.  octave1[i] != 0 skips the keypoint.
+ * matches12[i] = F2 keypoint or -1 BEFORE the rotation-histogram culling (:499-523, host); *n_matches likewise.  accepted12[i] = the
+ * F2 keypoint query i took when it was visited (-1 if none), whether or not a later query took it over: the entries the reference
+ * pushes into rotHist. */
+int hvo_proj_search_initialization(hvo_proj* h, const float* prev_matched_xy, const int32_t* octave1, const uint8_t* desc1, int n1, int window_size,
+                                   int th_dist, float nnratio, int32_t* matches12, int32_t* accepted12, int* n_matches);
 int hvo_proj_timer_start(hvo_proj* h);
 int hvo_proj_timer_stop(hvo_proj* h, float* ms_out);
 
@@ -378,6 +428,15 @@ int hvo_normals_sync(hvo_normals* h);
 int hvo_normals_timer_start(hvo_normals* h);
 int hvo_normals_timer_stop(hvo_normals* h, float* ms_out);
 
+/* LSDmatcher::FrameBFMatchNew(ldesc1, ldesc2, LineMatches, kls1, kls2, kls2func, F, TH) (src/LSDmatcher.cpp:968-1031) with
+ * mutualOverlap (:1033-1108): knn-2 of ldesc1 against ldesc2, then for the nearest neighbour only (the reference's inner loop runs
+ * for j < size() - 1 = 1) the epipolar test: the query's end points are mapped through F (cv::gemm, CV_32F), intersected with the
+ * train line (Mat::cross), and the overlap of the two collinear segments must exceed 0.8, with distance < TH and
+ * distance < nnratio * second distance.  kls1 / kls2 = keylines of the two frames, kls2func [n2][3] doubles, F row-major 3x3 float.
+ * line_matches[i] = train line or -1. */
+int hvo_match_lines_epipolar(hvo_matcher* m, const uint8_t* ldesc1, const hvo_keyline* kls1, int n1, const uint8_t* ldesc2, const hvo_keyline* kls2,
+                             const double* kls2func, int n2, const float* F, float th, float nnratio, int32_t* line_matches);
+
 /* ---- windowed line matchers -------------------------------------------------------------------------------------
  * Replaces, for one frame at a time, Frame::AssignFeaturesToGridForLine (src/Frame.cc:849-872, src/lineIterator.cpp),
  * Frame::GetFeaturesInAreaForLine (src/Frame.cc:1557-1631) and the two greedy searches
@@ -412,6 +471,26 @@ int hvo_lproj_features_in_area(hvo_lproj* h, float x1, float y1, float x2, float
  * the same-octave ratio test with nnratio (mfNNratio).  match_dist may be NULL. */
 int hvo_lproj_search(hvo_lproj* h, const hvo_lproj_query* queries, const uint8_t* qdesc, int nq, const uint8_t* claimed, int mode, float nnratio,
                      int32_t* match_idx, int32_t* match_dist, int* n_matches);
+/* Frame::isInFrustum(MapLine*, float) (src/Frame.cc:1438-1499) for a batch of map lines, and Tracking::SearchLocalLines' device work
+ * (src/Tracking.cc:3315-3348): isInFrustum followed by LSDmatcher::SearchByProjection(F, vpMapLines, eval_orient, th) in one call.
+ * The end points are narrowed to float as the reference does (Mat_<float> << P(0) ...); the mid point is
+ * cv::addWeighted(SP, 0.5, EP, 0.5) - mOw; MapLine::PredictScale (src/MapLine.cpp:549-558) is NOT clamped. */
+typedef struct hvo_map_line {
+    double pos[6];     /* MapLine::GetWorldPos(): start xyz, end xyz */
+    double normal[3];  /* GetNormal() */
+    double dir[3];     /* GetWorldVector() (used by the search only) */
+    float min_distance, max_distance; /* mfMinDistance, mfMaxDistance (src/MapLine.cpp:537-558), as for hvo_map_point */
+} hvo_map_line;
+typedef struct hvo_track_line {
+    float x1, y1, x2, y2; /* mTrackProjX1, Y1, X2, Y2 */
+    int32_t level;        /* mnTrackScaleLevel */
+    float view_cos;
+    int32_t in_view;
+} hvo_track_line;
+int hvo_lproj_frustum_lines(hvo_lproj* h, const hvo_frustum_cam* cam, const hvo_map_line* lines, int n, float viewing_cos_limit, hvo_track_line* out);
+int hvo_lproj_search_local_map(hvo_lproj* h, const hvo_frustum_cam* cam, const hvo_map_line* lines, const uint8_t* ldesc, const uint8_t* skip,
+                               const uint8_t* claims, int n, float viewing_cos_limit, float th, const uint8_t* claimed, float nnratio,
+                               hvo_track_line* track, int32_t* match_idx, int32_t* match_dist, int* n_in_view, int* n_matches);
 int hvo_lproj_last_rounds(const hvo_lproj* h);
 int hvo_lproj_last_launches(const hvo_lproj* h);
 

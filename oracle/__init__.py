@@ -695,6 +695,159 @@ def ref_line_search_by_projection_last(Cur, Last, th):
 
 
 # ---- surface normals (PCL integral-image style, Frame.cc:2155-2212) -------------------------------------------
+
+# ---- tracking-time projection and two matcher loops (oracle/track_oracle.cpp) ------------------------------------------------
+FRUSTUM_CAM_DTYPE = np.dtype([('Rcw', '<f4', (9,)), ('tcw', '<f4', (3,)), ('Ow', '<f4', (3,)), ('fx', '<f4'), ('fy', '<f4'), ('cx', '<f4'),
+                              ('cy', '<f4'), ('bf', '<f4'), ('min_x', '<f4'), ('min_y', '<f4'), ('max_x', '<f4'), ('max_y', '<f4'),
+                              ('log_scale_factor', '<f4'), ('n_levels', '<i4')])
+MAP_POINT_DTYPE = np.dtype([('pos', '<f4', (3,)), ('normal', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4')])
+TRACK_POINT_DTYPE = np.dtype([('u', '<f4'), ('v', '<f4'), ('ur', '<f4'), ('level', '<i4'), ('view_cos', '<f4'), ('in_view', '<i4')])
+MAP_LINE_DTYPE = np.dtype([('pos', '<f8', (6,)), ('normal', '<f8', (3,)), ('dir', '<f8', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4')])
+TRACK_LINE_DTYPE = np.dtype([('x1', '<f4'), ('y1', '<f4'), ('x2', '<f4'), ('y2', '<f4'), ('level', '<i4'), ('view_cos', '<f4'), ('in_view', '<i4')])
+
+
+def frustum_points(cam, pts, limit=0.5):
+    """Frame::isInFrustum(MapPoint*, limit) (src/Frame.cc:1371-1436)."""
+    cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+    out = np.zeros(max(len(pts), 1), TRACK_POINT_DTYPE)
+    f = lib().orc_frustum_points
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]; f.restype = None
+    f(_p(cam), _p(pts), len(pts), float(limit), _p(out))
+    return out[:len(pts)]
+
+
+def frustum_lines(cam, lines, limit=0.5):
+    """Frame::isInFrustum(MapLine*, limit) (src/Frame.cc:1438-1499)."""
+    cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE); ml = np.ascontiguousarray(lines, MAP_LINE_DTYPE)
+    out = np.zeros(max(len(ml), 1), TRACK_LINE_DTYPE)
+    f = lib().orc_frustum_lines
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]; f.restype = None
+    f(_p(cam), _p(ml), len(ml), float(limit), _p(out))
+    return out[:len(ml)]
+
+
+def three_maxima(sizes):
+    """ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1630-1671)."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, s in enumerate(sizes):
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if max2 < np.float32(0.1) * np.float32(max1):
+        ind2 = ind3 = -1
+    elif max3 < np.float32(0.1) * np.float32(max1):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def search_initialization(F1, F2, prev_matched, window=100, nnratio=0.9, check_ori=True, th_low=50):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:412-529), whole: Fi = dict(keys_un, desc, bounds).
+    Returns (nmatches, vnMatches12, vbPrevMatched, accepted12)."""
+    k1 = np.ascontiguousarray(F1['keys_un'], KP_DTYPE); k2 = np.ascontiguousarray(F2['keys_un'], KP_DTYPE)
+    d1 = np.ascontiguousarray(F1['desc'], np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(F2['desc'], np.uint8).reshape(-1, 32)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2)
+    oc = np.ascontiguousarray(k1['octave'], np.int32)
+    b = np.ascontiguousarray(F2['bounds'], np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32); acc = np.full(max(len(k1), 1), -1, np.int32)
+    f = lib().orc_search_initialization
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                  C.c_void_p]
+    nm = f(_p(k2), _p(d2), len(k2), _p(b), _p(prev), _p(oc), _p(d1), len(k1), int(window), int(th_low), float(nnratio), _p(m12), _p(acc))
+    m12 = m12[:len(k1)]; acc = acc[:len(k1)]
+    if check_ori:
+        hist = [[] for _ in range(30)]
+        factor = np.float32(1.0) / np.float32(30)
+        for i1, i2 in enumerate(acc):
+            if i2 < 0:
+                continue
+            rot = np.float32(k1['angle'][i1] - k2['angle'][i2])
+            if rot < 0.0:
+                rot = np.float32(rot + np.float32(360.0))
+            bin_ = int(np.floor(float(np.float32(rot * factor)) + 0.5))
+            if bin_ == 30:
+                bin_ = 0
+            hist[bin_].append(i1)
+        a, b2, c = three_maxima([len(h) for h in hist])
+        for i in range(30):
+            if i not in (a, b2, c):
+                for i1 in hist[i]:
+                    if m12[i1] >= 0:
+                        m12[i1] = -1
+                        nm -= 1
+    for i1 in np.nonzero(m12 >= 0)[0]:
+        prev[i1, 0] = k2['x'][m12[i1]]; prev[i1, 1] = k2['y'][m12[i1]]
+    return int(nm), m12, prev, acc
+
+
+def lines_epipolar(ldesc1, kls1, ldesc2, kls2, kls2func, F, TH, nnratio):
+    """LSDmatcher::FrameBFMatchNew (src/LSDmatcher.cpp:968-1031)."""
+    d1 = np.ascontiguousarray(ldesc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(ldesc2, np.uint8).reshape(-1, 32)
+    k1 = np.ascontiguousarray(kls1, KL_DTYPE); k2 = np.ascontiguousarray(kls2, KL_DTYPE)
+    f2 = np.ascontiguousarray(kls2func, np.float64).reshape(-1, 3); Fm = np.ascontiguousarray(F, np.float32).reshape(9)
+    out = np.full(max(len(d1), 1), -1, np.int32)
+    f = lib().orc_lines_epipolar
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    f.restype = None
+    f(_p(d1), _p(k1), len(d1), _p(d2), _p(k2), _p(f2), len(d2), _p(Fm), float(TH), float(nnratio), _p(out))
+    return out[:len(d1)]
+
+
+# the reference's own functions executed (oracle/_ref/ref_match ops 4-7)
+def _frustum_payload(op, cam, limit, body, n):
+    cam = np.ascontiguousarray(cam, FRUSTUM_CAM_DTYPE).reshape(())
+    b = struct.pack('<2i', 0x4d544348, op) + _f32([cam['min_x'], cam['min_y'], cam['max_x'], cam['max_y']])
+    b += _f32([cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf']]) + _f32(cam['Rcw']) + _f32(cam['tcw']) + _f32(cam['Ow'])
+    b += struct.pack('<fifi', float(cam['log_scale_factor']), int(cam['n_levels']), float(limit), n)
+    return b + body
+
+
+def ref_frustum_points(cam, pts, limit=0.5):
+    """The reference's Frame::isInFrustum(MapPoint*, float) executed over a batch.  None when oracle/_ref/ref_match is absent."""
+    pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+    raw = _run_ref_match(_frustum_payload(4, cam, limit, pts.tobytes(), len(pts)))
+    return None if raw is None else np.frombuffer(raw, TRACK_POINT_DTYPE, len(pts)).copy()
+
+
+def ref_frustum_lines(cam, lines, limit=0.5):
+    """The reference's Frame::isInFrustum(MapLine*, float) executed over a batch."""
+    ml = np.ascontiguousarray(lines, MAP_LINE_DTYPE)
+    raw = _run_ref_match(_frustum_payload(5, cam, limit, ml.tobytes(), len(ml)))
+    return None if raw is None else np.frombuffer(raw, TRACK_LINE_DTYPE, len(ml)).copy()
+
+
+def ref_search_initialization(F1, F2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """The reference's ORBmatcher::SearchForInitialization executed.  Returns (nmatches, vnMatches12, vbPrevMatched) or None."""
+    k1 = np.ascontiguousarray(F1['keys_un'], KP_DTYPE)
+    prev = np.ascontiguousarray(prev_matched, np.float32).reshape(-1, 2)
+    F2f = dict(F2); F2f.setdefault('scale_factors', np.ones(8, np.float32))
+    b = struct.pack('<2i', 0x4d544348, 6) + _f32(F2['bounds']) + _point_frame_bytes(F2f)
+    b += struct.pack('<i', len(k1)) + k1.tobytes() + np.ascontiguousarray(F1['desc'], np.uint8).tobytes() + prev.tobytes()
+    b += struct.pack('<ifi', int(window), float(nnratio), int(check_ori))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    n = len(k1)
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, n, 4).copy(), np.frombuffer(raw, np.float32, 2 * n, 4 + 4 * n).reshape(n, 2).copy()
+
+
+def ref_lines_epipolar(ldesc1, kls1, ldesc2, kls2, kls2func, F, TH, nnratio):
+    """The reference's LSDmatcher::FrameBFMatchNew executed.  Returns LineMatches or None."""
+    k1 = np.ascontiguousarray(kls1, KL_DTYPE); k2 = np.ascontiguousarray(kls2, KL_DTYPE)
+    b = struct.pack('<2i', 0x4d544348, 7) + _f32([0, 0, 640, 480])
+    b += struct.pack('<i', len(k1)) + k1.tobytes() + np.ascontiguousarray(ldesc1, np.uint8).tobytes()
+    b += struct.pack('<i', len(k2)) + k2.tobytes() + np.ascontiguousarray(ldesc2, np.uint8).tobytes()
+    b += np.ascontiguousarray(kls2func, np.float64).tobytes() + _f32(F) + struct.pack('<2f', float(TH), float(nnratio))
+    raw = _run_ref_match(b)
+    return None if raw is None else np.frombuffer(raw, np.int32, len(k1)).copy()
+
+
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)
     h, w = d.shape

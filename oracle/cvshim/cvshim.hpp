@@ -61,6 +61,7 @@ static inline int cvCeil(float v) { return cvp::cv_ceil(v); }
 // restatements living in oracle/_build/liboracle.so (pinned to cv2 4.13.0)
 extern "C" int orc_lsd_detect(const uint8_t* gray, int w, int h, float* segments4, int cap, uint8_t* scaled_out, int* sw, int* sh);
 extern "C" int orc_clip_line(int w, int h, long long* pts4);
+extern "C" void orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2);
 
 namespace cv {
 
@@ -235,7 +236,14 @@ public:
     void copyTo(Mat& dst) const { dst = clone(); }
     void copyTo(const class _OutputArray& dst) const;
     bool isContinuous() const { return step.v == (size_t)cols * cvshim_elem_size(type_); }
-    double dot(const Mat& o) const {  // CV_64F vectors only (Frame::TwoLineAngle); cv::Mat::dot accumulates in order
+    Mat cross(const Mat& o) const;   // CV_32F 3-vectors (LSDmatcher::FrameBFMatchNew)
+    double dot(const Mat& o) const {  // vectors (Frame::TwoLineAngle 64F, Frame::isInFrustum 32F); cv::Mat::dot accumulates in double, in order
+        if (type_ == CV_32FC1) {
+            assert(o.type_ == CV_32FC1 && rows * cols == o.rows * o.cols);
+            double r32 = 0;
+            for (int i = 0; i < rows * cols; ++i) r32 += (double)at<float>(i) * (double)o.at<float>(i);
+            return r32;
+        }
         assert(type_ == CV_64FC1 && o.type_ == CV_64FC1 && rows * cols == o.rows * o.cols);
         double r = 0;
         for (int i = 0; i < rows * cols; ++i) r += at<double>(i) * o.at<double>(i);
@@ -462,6 +470,71 @@ private:
         }
         const long long dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
         count = (int)std::max(dx, dy) + 1;
+    }
+};
+
+
+// ---- small CV_32F matrix algebra the tracking-time functions use (Frame::isInFrustum, LSDmatcher::FrameBFMatchNew) ----
+// Semantics checked against cv2 4.13.0 where Python exposes the operation (gemm, norm, addWeighted: tests/test_track.py); the
+// rest follows OpenCV's sources: Mat::dot / cv::norm accumulate in double in element order, Mat::cross works in float,
+// `m /= s` is convertTo(m, -1, 1. / s) i.e. a float multiplication by (float)(1. / s), `s * (A + B)` is addWeighted(A, s, B, s).
+// (A * B + C is one cv::gemm call in OpenCV, (float)(double(t) + double(c)): for two floats that equals the float sum.)
+static inline Mat operator-(const Mat& a, const Mat& b) {
+    assert(a.type() == CV_32FC1 && b.type() == CV_32FC1 && a.rows == b.rows && a.cols == b.cols);
+    Mat r(a.rows, a.cols, CV_32FC1);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) r.at<float>(i, j) = a.at<float>(i, j) - b.at<float>(i, j);
+    return r;
+}
+static inline Mat operator*(double s, const Mat& a) {
+    assert(a.type() == CV_32FC1);
+    Mat r(a.rows, a.cols, CV_32FC1);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) r.at<float>(i, j) = a.at<float>(i, j) * (float)s;
+    return r;
+}
+static inline Mat& operator/=(Mat& a, double s) {
+    assert(a.type() == CV_32FC1);
+    const float f = (float)(1. / s);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) a.at<float>(i, j) = a.at<float>(i, j) * f;
+    return a;
+}
+static inline double norm(const Mat& a) {
+    assert(a.type() == CV_32FC1);
+    double s = 0;
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += (double)a.at<float>(i, j) * (double)a.at<float>(i, j);
+    return std::sqrt(s);
+}
+static inline double cvshim_dot32f(const Mat& a, const Mat& b) {
+    assert(a.rows * a.cols == b.rows * b.cols);
+    double r = 0;
+    for (int i = 0; i < a.rows * a.cols; ++i) r += (double)a.at<float>(i) * (double)b.at<float>(i);
+    return r;
+}
+static inline Mat cvshim_cross32f(const Mat& a, const Mat& b) {
+    assert(a.type() == CV_32FC1 && b.type() == CV_32FC1 && a.rows * a.cols == 3 && b.rows * b.cols == 3);
+    Mat c(a.rows, a.cols, CV_32FC1);
+    const float a0 = a.at<float>(0), a1 = a.at<float>(1), a2 = a.at<float>(2), b0 = b.at<float>(0), b1 = b.at<float>(1), b2 = b.at<float>(2);
+    c.at<float>(0) = a1 * b2 - a2 * b1;
+    c.at<float>(1) = a2 * b0 - a0 * b2;
+    c.at<float>(2) = a0 * b1 - a1 * b0;
+    return c;
+}
+
+inline Mat Mat::cross(const Mat& o) const { return cvshim_cross32f(*this, o); }
+
+// cv::BFMatcher(NORM_HAMMING, false).knnMatch(q, t, matches, k = 2): forwards to the oracle's brute force, which is pinned to
+// cv2.BFMatcher (ties: lower train index first; tests/test_match.py)
+class BFMatcher {
+public:
+    BFMatcher(int normType, bool crossCheck = false) { assert(normType == NORM_HAMMING && !crossCheck); (void)normType; (void)crossCheck; }
+    void knnMatch(const Mat& q, const Mat& t, std::vector<std::vector<DMatch>>& matches, int k) const {
+        assert(k == 2 && q.type() == CV_8UC1 && t.type() == CV_8UC1 && q.cols == 32 && t.cols == 32 && q.isContinuous() && t.isContinuous());
+        (void)k;
+        std::vector<int32_t> idx((size_t)q.rows * 2), dist((size_t)q.rows * 2);
+        orc_knn2(q.data, q.rows, t.data, t.rows, idx.data(), dist.data());
+        matches.assign(q.rows, std::vector<DMatch>());
+        for (int i = 0; i < q.rows; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (idx[2 * i + j] >= 0) matches[i].push_back(DMatch(i, idx[2 * i + j], (float)dist[2 * i + j]));
     }
 };
 

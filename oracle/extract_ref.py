@@ -46,6 +46,18 @@ RANGES = {
                    ('src/LSDmatcher.cpp', 709, 801, 'int LSDmatcher::SearchByProjection(Frame &F, const std::vector<MapLine *> &vpMapLines'),
                    ('src/LSDmatcher.cpp', 1137, 1153, 'int LSDmatcher::DescriptorDistance('),
                    ('src/LSDmatcher.cpp', 1436, 1442, 'float LSDmatcher::RadiusByViewingCos(')],
+    # Frame::isInFrustum(MapPoint*, float) and (MapLine*, float); compiled under the name isInFrustumRef (a #define around the include)
+    # because the windowed line search above keeps its documented stand-in of the same name
+    'frame_frustum': [('src/Frame.cc', 1371, 1499, 'bool Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit)')],
+    # MapPoint::Get{Min,Max}DistanceInvariance + PredictScale(dist, Frame*); MapLine::Get{Min,Max}DistanceInvariance + PredictScale
+    'map_scale': [('src/MapPoint.cc', 371, 381, 'float MapPoint::GetMinDistanceInvariance()'),
+                  ('src/MapPoint.cc', 400, 415, 'int MapPoint::PredictScale(const float &currentDist, Frame *pF)'),
+                  ('src/MapLine.cpp', 537, 558, 'float MapLine::GetMinDistanceInvariance()')],
+    # ORBmatcher::SearchForInitialization (whole, with its rotation histogram)
+    'orb_init': [('src/ORBmatcher.cc', 412, 529, 'int ORBmatcher::SearchForInitialization(')],
+    # sort_descriptor_by_queryIdx; LSDmatcher::FrameBFMatchNew + mutualOverlap
+    'lsd_bfnew': [('include/auxiliar.h', 40, 45, 'struct sort_descriptor_by_queryIdx'),
+                  ('src/LSDmatcher.cpp', 968, 1108, 'void LSDmatcher::FrameBFMatchNew(')],
 }
 
 

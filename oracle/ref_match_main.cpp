@@ -4,6 +4,10 @@
 //   src/ORBmatcher.cc:37-43, 45-140, 1353-1497, 1630-1692   SearchByProjection(F, MapPoints, th), RadiusByViewingCos,
 //                                                            SearchByProjection(Cur, Last, th, mono), ComputeThreeMaxima, DescriptorDistance
 //   src/LSDmatcher.cpp:12-34, 561-664, 709-801, 1137-1153, 1436-1442   the two line SearchByProjection + helpers
+//   src/Frame.cc:1371-1499                                   isInFrustum(MapPoint*, float), isInFrustum(MapLine*, float)  (as isInFrustumRef)
+//   src/MapPoint.cc:371-381, 400-415; src/MapLine.cpp:537-558  Get{Min,Max}DistanceInvariance, PredictScale
+//   src/ORBmatcher.cc:412-529                                SearchForInitialization, whole
+//   include/auxiliar.h:40-45, src/LSDmatcher.cpp:968-1108    sort_descriptor_by_queryIdx, FrameBFMatchNew, mutualOverlap
 //   src/lineIterator.cpp                                     whole file, unmodified
 // and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
 // (declared below with the reference header line each one mirrors) plus the OpenCV / Eigen stand-ins.
@@ -11,11 +15,13 @@
 // precomputed mbTrackInView; the projection fields it would fill are given as input.
 //
 //   ref_match <in.bin> <out.bin>      (formats: see oracle/__init__.py ref_match_*)
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <list>
+#include <mutex>
 #include <set>
 #include <unordered_set>
 #include <vector>
@@ -35,9 +41,25 @@ typedef Matrix<double, 6, 1> Vector6d;   // include/auxiliar.h:23
 
 namespace ORB_SLAM2 {
 class KeyFrame;
-class MapPoint {                          // include/MapPoint.h:49-102
+class Frame;
+class MapPoint {                          // include/MapPoint.h:49-102, 150-154
 public:
     cv::Mat GetWorldPos() { return pos.clone(); }
+    cv::Mat GetNormal() { return normal.clone(); }
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, Frame* pF);
+    MapPoint() {}
+    MapPoint(const MapPoint& o) { *this = o; }
+    MapPoint& operator=(const MapPoint& o) {   // (std::mutex is not copyable; the harness keeps map points in vectors)
+        mTrackProjX = o.mTrackProjX; mTrackProjY = o.mTrackProjY; mTrackProjXR = o.mTrackProjXR; mbTrackInView = o.mbTrackInView;
+        mnTrackScaleLevel = o.mnTrackScaleLevel; mTrackViewCos = o.mTrackViewCos; pos = o.pos; desc = o.desc; normal = o.normal;
+        nobs = o.nobs; bad = o.bad; id = o.id; mfMinDistance = o.mfMinDistance; mfMaxDistance = o.mfMaxDistance;
+        return *this;
+    }
+    cv::Mat normal;
+    float mfMinDistance = 0.f, mfMaxDistance = 0.f;
+    std::mutex mMutexPos;
     int Observations() { return nobs; }
     bool isBad() { return bad; }
     cv::Mat GetDescriptor() { return desc.clone(); }
@@ -50,10 +72,25 @@ public:
     bool bad = false;
     int id = -1;
 };
-class MapLine {                           // include/MapLine.h:40-110
+class MapLine {                           // include/MapLine.h:40-110, 157-161
 public:
     Vector6d GetWorldPos() { return wpos; }
     Vector3d GetWorldVector() { return wvec; }
+    Vector3d GetNormal() { return wnormal; }
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, const float& logScaleFactor);
+    MapLine() {}
+    MapLine(const MapLine& o) { *this = o; }
+    MapLine& operator=(const MapLine& o) {
+        mTrackProjX1 = o.mTrackProjX1; mTrackProjY1 = o.mTrackProjY1; mTrackProjX2 = o.mTrackProjX2; mTrackProjY2 = o.mTrackProjY2;
+        mnTrackScaleLevel = o.mnTrackScaleLevel; mTrackViewCos = o.mTrackViewCos; mbTrackInView = o.mbTrackInView; wpos = o.wpos; wvec = o.wvec;
+        wnormal = o.wnormal; desc = o.desc; nobs = o.nobs; bad = o.bad; id = o.id; mfMinDistance = o.mfMinDistance; mfMaxDistance = o.mfMaxDistance;
+        return *this;
+    }
+    Vector3d wnormal;
+    float mfMinDistance = 0.f, mfMaxDistance = 0.f;
+    std::mutex mMutexPos;
     int Observations() { return nobs; }
     bool isBad() { return bad; }
     Mat GetDescriptor() { return desc.clone(); }
@@ -77,6 +114,11 @@ public:
     void AssignFeaturesToGridForLine();
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     bool isInFrustum(MapLine* pML, float) { return pML->mbTrackInView; }
+    bool isInFrustumRef(MapPoint* pMP, float viewingCosLimit);   // = the reference's isInFrustum, see the include below
+    bool isInFrustumRef(MapLine* pML, float viewingCosLimit);
+    cv::Mat mRcw, mtcw, mOw;                 // include/Frame.h:408-411
+    int mnScaleLevels = 8;                   // :330-332
+    float mfLogScaleFactor = 0.f;
     static float fx, fy, cx, cy;
     float mb = 0.f, mbf = 0.f;
     int N = 0, NL = 0;
@@ -106,6 +148,7 @@ public:
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     float RadiusByViewingCos(const float& viewCos);
@@ -119,6 +162,9 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th);
     int SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, const bool eval_orient, const float th = 3);
     static int DescriptorDistance(const Mat& a, const Mat& b);
+    void FrameBFMatchNew(cv::Mat ldesc1, cv::Mat ldesc2, vector<int>& LineMatches, vector<KeyLine> kls1, vector<KeyLine> kls2,
+                         vector<Eigen::Vector3d> kls2func, cv::Mat F, float TH);
+    float mutualOverlap(const std::vector<cv::Mat>& collinear_points);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     double computeAngle2D(const cv::Mat& vector1, const cv::Mat& vector2);
@@ -128,9 +174,15 @@ protected:
 };
 #include "gen/frame_grid.inc"
 #include "gen/orbmatcher.inc"
+#include "gen/orb_init.inc"
+#define isInFrustum isInFrustumRef
+#include "gen/frame_frustum.inc"
+#undef isInFrustum
+#include "gen/map_scale.inc"
 }  // namespace ORB_SLAM2
 namespace ORB_SLAM2 {
 #include "gen/lsdmatcher.inc"
+#include "gen/lsd_bfnew.inc"
 }  // namespace ORB_SLAM2
 
 using namespace ORB_SLAM2;
@@ -296,6 +348,72 @@ int main(int argc, char** argv) {
         const int nm = matcher.SearchByProjection(C, L, th);
         put<int32_t>(nm);
         for (int i = 0; i < C.NL; ++i) put<int32_t>(C.mvpMapLines[i] ? C.mvpMapLines[i]->id : -1);
+    } else if (op == 4 || op == 5) {   // Frame::isInFrustum(MapPoint*, limit) / (MapLine*, limit) over a batch
+        Frame F;
+        float cam[5]; get_n(cam, 5);
+        Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3]; F.mbf = cam[4];
+        F.mRcw = cv::Mat(3, 3, CV_32FC1); get_n((float*)F.mRcw.data, 9);
+        F.mtcw = cv::Mat(3, 1, CV_32FC1); get_n((float*)F.mtcw.data, 3);
+        F.mOw = cv::Mat(3, 1, CV_32FC1); get_n((float*)F.mOw.data, 3);
+        F.mfLogScaleFactor = get<float>(); F.mnScaleLevels = get<int32_t>();
+        const float limit = get<float>();
+        const int M = get<int32_t>();
+        if (op == 4) {
+            for (int i = 0; i < M; ++i) {
+                MapPoint m;
+                m.pos = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.pos.data, 3);
+                m.normal = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.normal.data, 3);
+                m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
+                m.mTrackProjX = m.mTrackProjY = m.mTrackProjXR = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = 0;
+                const bool in = F.isInFrustumRef(&m, limit);
+                put<float>(m.mTrackProjX); put<float>(m.mTrackProjY); put<float>(m.mTrackProjXR); put<int32_t>(m.mnTrackScaleLevel);
+                put<float>(m.mTrackViewCos); put<int32_t>(in && m.mbTrackInView ? 1 : 0);
+            }
+        } else {
+            for (int i = 0; i < M; ++i) {
+                MapLine m;
+                get_n(m.wpos.data(), 6); get_n(m.wnormal.data(), 3); get_n(m.wvec.data(), 3);
+                m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
+                m.mTrackProjX1 = m.mTrackProjY1 = m.mTrackProjX2 = m.mTrackProjY2 = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = 0;
+                const bool in = F.isInFrustumRef(&m, limit);
+                put<float>(m.mTrackProjX1); put<float>(m.mTrackProjY1); put<float>(m.mTrackProjX2); put<float>(m.mTrackProjY2);
+                put<int32_t>(m.mnTrackScaleLevel); put<float>(m.mTrackViewCos); put<int32_t>(in && m.mbTrackInView ? 1 : 0);
+            }
+        }
+    } else if (op == 6) {   // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+        Frame F1, F2; std::vector<MapPoint> pool;
+        read_point_frame(F2, pool);
+        F1.N = get<int32_t>();
+        F1.mvKeysUn.resize(F1.N); get_n(F1.mvKeysUn.data(), F1.N);
+        F1.mDescriptors = get_desc_rows(F1.N);
+        std::vector<cv::Point2f> prev(F1.N);
+        for (int i = 0; i < F1.N; ++i) { prev[i].x = get<float>(); prev[i].y = get<float>(); }
+        const int window = get<int32_t>();
+        const float nnratio = get<float>();
+        const int check_ori = get<int32_t>();
+        std::vector<int> m12;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int nm = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+        put<int32_t>(nm);
+        for (int i = 0; i < F1.N; ++i) put<int32_t>(m12[i]);
+        for (int i = 0; i < F1.N; ++i) { put<float>(prev[i].x); put<float>(prev[i].y); }
+    } else if (op == 7) {   // LSDmatcher::FrameBFMatchNew(ldesc1, ldesc2, LineMatches, kls1, kls2, kls2func, F, TH)
+        const int n1 = get<int32_t>();
+        vector<KeyLine> k1(n1); get_n(k1.data(), n1);
+        cv::Mat d1 = get_desc_rows(n1);
+        const int n2 = get<int32_t>();
+        vector<KeyLine> k2(n2); get_n(k2.data(), n2);
+        cv::Mat d2 = get_desc_rows(n2);
+        vector<Eigen::Vector3d> f2(n2);
+        for (int i = 0; i < n2; ++i) get_n(f2[i].data(), 3);
+        cv::Mat Fm(3, 3, CV_32FC1); get_n((float*)Fm.data, 9);
+        const float TH = get<float>(), nnratio = get<float>();
+        if (d1.rows != n1) d1 = d1.rowRange(0, n1);
+        if (d2.rows != n2) d2 = d2.rowRange(0, n2);
+        vector<int> lm;
+        LSDmatcher matcher(nnratio, true);
+        matcher.FrameBFMatchNew(d1, d2, lm, k1, k2, f2, Fm, TH);
+        for (int i = 0; i < n1; ++i) put<int32_t>(lm[i]);
     } else {
         return 5;
     }

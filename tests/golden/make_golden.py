@@ -15,6 +15,8 @@ peac_ref.npz   outputs of the reference's own plane extractor (src/PlaneExtracto
 lines_ref.npz  outputs of the reference's own line front-end (oracle/_ref/ref_lines: vendored LSDDetector_custom.cpp whole, the
                LBD functions of binary_descriptor_custom.cpp, LINEextractor::operator() and Frame::cullingLine extracted at build
                time) on synthetic frames: KeyLines + LBD + line functions before and after cullingLine.
+track_ref.npz  outputs of the reference's own Frame::isInFrustum x2, ORBmatcher::SearchForInitialization and LSDmatcher::FrameBFMatchNew
+               (oracle/_ref/ref_match ops 4-7) on the scenes of tests/test_track.py
 match_ref.npz  outputs of the reference's own windowed matchers (oracle/_ref/ref_match: Frame grids + GetFeaturesInArea*, the two
                ORBmatcher::SearchByProjection and the two LSDmatcher::SearchByProjection, extracted at build time) on the scenes of
                tests/test_ref_match.py: grids, candidate lists, final assignments, match counts.
@@ -199,8 +201,24 @@ def match():
     print('match_ref.npz written:', len(t.RECORD), 'arrays')
 
 
+def track():
+    if oracle.ref_bin('ref_match') is None:
+        print('oracle/_ref/ref_match missing: run make -C oracle first')
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_track as t
+    t._golden = None
+    t.test_oracle_frustum_equals_reference()
+    t.test_oracle_search_initialization_equals_reference(synth)
+    t.test_oracle_lines_epipolar_equals_reference(synth)
+    np.savez_compressed(os.path.join(OUT, 'track_ref.npz'), **t.RECORD)
+    print('track_ref.npz written:', len(t.RECORD), 'arrays')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track']
+    if 'track' in which:
+        track()
     if 'match' in which:
         match()
     if 'lines' in which:
