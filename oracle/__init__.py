@@ -567,8 +567,13 @@ def ref_lines(frames, n_features=200, cull=True):
 
 
 # ---- the reference's own windowed matchers, executed (oracle/_ref/ref_match; oracle/ref_match_main.cpp) ----------------
+# tests/test_shim_cpp.py runs the SAME payloads through tests/cpp/shim_match (the drop-in matcher classes behind the reference
+# harness' driver): MATCH_EXE[0] names that binary; its output has no grid / candidate-list sections.
+MATCH_EXE = [None]
+
+
 def _run_ref_match(payload):
-    exe = ref_bin('ref_match')
+    exe = MATCH_EXE[0] or ref_bin('ref_match')
     if exe is None:
         return None
     with tempfile.TemporaryDirectory() as td:
@@ -632,6 +637,9 @@ def ref_search_by_projection(F, MPs, th, nnratio, windows=()):
     raw = _run_ref_match(b)
     if raw is None:
         return None
+    if MATCH_EXE[0]:
+        (nm,) = struct.unpack_from('<i', raw, 0)
+        return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, len(F['keys_un']), 4).copy())
     cnt, items, off = _read_grid(raw, 0)
     areas, off = _read_lists(raw, off, len(w))
     (nm,) = struct.unpack_from('<i', raw, off); off += 4
@@ -670,6 +678,9 @@ def ref_line_search_by_projection(F, MLs, th, nnratio, windows=()):
     raw = _run_ref_match(b)
     if raw is None:
         return None
+    if MATCH_EXE[0]:
+        (nm,) = struct.unpack_from('<i', raw, 0)
+        return dict(nmatches=nm, assign=np.frombuffer(raw, np.int32, len(F['keylines_un']), 4).copy())
     cnt, items, off = _read_grid(raw, 0)
     areas, off = _read_lists(raw, off, len(w))
     (nm,) = struct.unpack_from('<i', raw, off); off += 4

@@ -26,9 +26,17 @@
 #include <unordered_set>
 #include <vector>
 
+// REF_MATCH_USE_SHIM (tests/cpp/shim_match_main.cpp): the same driver and stand-in types, but ORBmatcher / LSDmatcher are the drop-in
+// class templates of shim/ORBmatcher.h / shim/LSDmatcher.h (C ABI -> CUDA) instead of the reference's functions; nothing of the
+// reference is compiled, the grid / candidate-list dumps are skipped (the drop-in builds its grids on the device).
+#ifdef REF_MATCH_USE_SHIM
+#include "keyline_standin.hpp"
+#include <Eigen/Core>
+#else
 #include "precomp_custom.hpp"   // vendored line_descriptor umbrella (KeyLine)
 #include <Eigen/Core>
 #include "lineIterator.h"
+#endif
 
 using namespace std;
 using namespace cv;
@@ -142,6 +150,7 @@ public:
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
+#ifndef REF_MATCH_USE_SHIM
 class ORBmatcher {                        // include/ORBmatcher.h:38-104
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
@@ -184,6 +193,16 @@ namespace ORB_SLAM2 {
 #include "gen/lsdmatcher.inc"
 #include "gen/lsd_bfnew.inc"
 }  // namespace ORB_SLAM2
+#else
+}  // namespace ORB_SLAM2
+#include "ORBmatcher.h"
+#include "LSDmatcher.h"
+#include "FrustumGPU.h"
+namespace ORB_SLAM2 {
+typedef hvo_shim::ORBmatcherT<Frame, MapPoint> ORBmatcher;
+typedef hvo_shim::LSDmatcherT<Frame, MapLine> LSDmatcher;
+}  // namespace ORB_SLAM2
+#endif
 
 using namespace ORB_SLAM2;
 
@@ -217,7 +236,9 @@ static void read_point_frame(Frame& F, std::vector<MapPoint>& claimed_pool) {
     F.mvpMapPoints.assign(F.N, nullptr);
     for (int i = 0; i < F.N; ++i) if (cl[i]) { claimed_pool[i].nobs = 1; claimed_pool[i].id = -2; F.mvpMapPoints[i] = &claimed_pool[i]; }
     F.mvScaleFactors.resize(8); get_n(F.mvScaleFactors.data(), 8);
+#ifndef REF_MATCH_USE_SHIM
     F.AssignFeaturesToGrid();
+#endif
 }
 // line frame: NL, keylinesUn[NL], line functions [NL][3], desc, lines3D [NL][6], claimed[NL]
 static void read_line_frame(Frame& F, std::vector<MapLine>& claimed_pool) {
@@ -232,7 +253,9 @@ static void read_line_frame(Frame& F, std::vector<MapLine>& claimed_pool) {
     claimed_pool.resize(F.NL);
     F.mvpMapLines.assign(F.NL, nullptr);
     for (int i = 0; i < F.NL; ++i) if (cl[i]) { claimed_pool[i].nobs = 1; claimed_pool[i].id = -2; F.mvpMapLines[i] = &claimed_pool[i]; }
+#ifndef REF_MATCH_USE_SHIM
     F.AssignFeaturesToGridForLine();
+#endif
 }
 static void put_grid(const std::vector<std::size_t> (*grid)[FRAME_GRID_ROWS]) {
     for (int ix = 0; ix < FRAME_GRID_COLS; ++ix)
@@ -267,12 +290,14 @@ int main(int argc, char** argv) {
         // window queries answered by the reference's GetFeaturesInArea, for the grid / candidate-order pin
         const int nq = get<int32_t>();
         std::vector<float> wq((size_t)nq * 5); get_n(wq.data(), wq.size());
+#ifndef REF_MATCH_USE_SHIM
         put_grid(F.mGrid);
         for (int i = 0; i < nq; ++i) {
             const vector<size_t> v = F.GetFeaturesInArea(wq[5 * i], wq[5 * i + 1], wq[5 * i + 2], (int)wq[5 * i + 3], (int)wq[5 * i + 4]);
             put<int32_t>((int32_t)v.size());
             for (size_t x : v) put<int32_t>((int32_t)x);
         }
+#endif
         ORBmatcher matcher(nnratio, true);
         const int nm = matcher.SearchByProjection(F, vp, th);
         put<int32_t>(nm);
@@ -317,12 +342,14 @@ int main(int argc, char** argv) {
         }
         const int nq = get<int32_t>();
         std::vector<float> wq((size_t)nq * 6); get_n(wq.data(), wq.size());
+#ifndef REF_MATCH_USE_SHIM
         put_grid(F.mGridForLine);
         for (int i = 0; i < nq; ++i) {
             const vector<size_t> v = F.GetFeaturesInAreaForLine(wq[6 * i], wq[6 * i + 1], wq[6 * i + 2], wq[6 * i + 3], wq[6 * i + 4], -1, -1, wq[6 * i + 5]);
             put<int32_t>((int32_t)v.size());
             for (size_t x : v) put<int32_t>((int32_t)x);
         }
+#endif
         LSDmatcher matcher(nnratio, true);
         const int nm = matcher.SearchByProjection(F, vp, true, th);
         put<int32_t>(nm);
@@ -359,25 +386,49 @@ int main(int argc, char** argv) {
         const float limit = get<float>();
         const int M = get<int32_t>();
         if (op == 4) {
+            std::vector<MapPoint> ms(M);
             for (int i = 0; i < M; ++i) {
-                MapPoint m;
+                MapPoint& m = ms[i];
                 m.pos = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.pos.data, 3);
                 m.normal = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.normal.data, 3);
                 m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
                 m.mTrackProjX = m.mTrackProjY = m.mTrackProjXR = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = 0;
-                const bool in = F.isInFrustumRef(&m, limit);
+            }
+            std::vector<char> in(M, 0);
+#ifdef REF_MATCH_USE_SHIM
+            std::vector<MapPoint*> vp(M);
+            for (int i = 0; i < M; ++i) vp[i] = &ms[i];
+            hvo_shim::FrustumCullerT<Frame, MapPoint, MapLine> culler;
+            culler.isInFrustum(F, vp, limit, in);
+#else
+            for (int i = 0; i < M; ++i) in[i] = F.isInFrustumRef(&ms[i], limit);
+#endif
+            for (int i = 0; i < M; ++i) {
+                const MapPoint& m = ms[i];
                 put<float>(m.mTrackProjX); put<float>(m.mTrackProjY); put<float>(m.mTrackProjXR); put<int32_t>(m.mnTrackScaleLevel);
-                put<float>(m.mTrackViewCos); put<int32_t>(in && m.mbTrackInView ? 1 : 0);
+                put<float>(m.mTrackViewCos); put<int32_t>(in[i] && m.mbTrackInView ? 1 : 0);
             }
         } else {
+            std::vector<MapLine> ms(M);
             for (int i = 0; i < M; ++i) {
-                MapLine m;
+                MapLine& m = ms[i];
                 get_n(m.wpos.data(), 6); get_n(m.wnormal.data(), 3); get_n(m.wvec.data(), 3);
                 m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
                 m.mTrackProjX1 = m.mTrackProjY1 = m.mTrackProjX2 = m.mTrackProjY2 = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = 0;
-                const bool in = F.isInFrustumRef(&m, limit);
+            }
+            std::vector<char> in(M, 0);
+#ifdef REF_MATCH_USE_SHIM
+            std::vector<MapLine*> vp(M);
+            for (int i = 0; i < M; ++i) vp[i] = &ms[i];
+            hvo_shim::FrustumCullerT<Frame, MapPoint, MapLine> culler;
+            culler.isInFrustum(F, vp, limit, in);
+#else
+            for (int i = 0; i < M; ++i) in[i] = F.isInFrustumRef(&ms[i], limit);
+#endif
+            for (int i = 0; i < M; ++i) {
+                const MapLine& m = ms[i];
                 put<float>(m.mTrackProjX1); put<float>(m.mTrackProjY1); put<float>(m.mTrackProjX2); put<float>(m.mTrackProjY2);
-                put<int32_t>(m.mnTrackScaleLevel); put<float>(m.mTrackViewCos); put<int32_t>(in && m.mbTrackInView ? 1 : 0);
+                put<int32_t>(m.mnTrackScaleLevel); put<float>(m.mTrackViewCos); put<int32_t>(in[i] && m.mbTrackInView ? 1 : 0);
             }
         }
     } else if (op == 6) {   // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)

@@ -3,6 +3,7 @@ GPU, produces the same bytes as the oracle / the reference's own ORBextractor.cc
 import os
 import struct
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -142,3 +143,51 @@ def test_front_shims_equal_python_mirror(hvo, synth):
     assert np.array_equal(np.frombuffer(raw, np.int32, 2 * nn, off).reshape(nn, 2), rpix)
     off += 8 * nn
     assert off == len(raw)
+
+
+# ---- drop-in matcher classes (shim/ORBmatcher.h, shim/LSDmatcher.h, shim/FrustumGPU.h) ----------------------------------------
+EXE3 = os.path.join(ROOT, 'tests', 'cpp', 'shim_match')
+
+
+def _build_match():
+    """tests/cpp/shim_match = oracle/ref_match_main.cpp (the executed reference's driver and stand-in Frame / MapPoint / MapLine types)
+    compiled with REF_MATCH_USE_SHIM: ORBmatcher / LSDmatcher are the drop-in class templates, nothing of the reference is compiled."""
+    src = os.path.join(ROOT, 'tests', 'cpp', 'shim_match_main.cpp')
+    if not os.path.exists(os.path.join(PKG, 'libhvofront.so')):
+        import __graft_entry__
+        __graft_entry__.build()
+    subprocess.check_call(['g++', '-O2', '-std=c++14', '-I' + os.path.join(ROOT, 'oracle', 'cvshim'), '-I' + os.path.join(ROOT, 'oracle', 'eigenshim'),
+                           '-I' + os.path.join(ROOT, 'tests', 'cpp', 'standins'), '-I' + os.path.join(PKG, 'shim'), '-I' + os.path.join(ROOT, 'include'),
+                           src, '-o', EXE3, '-L' + PKG, '-lhvofront', '-Wl,-rpath,' + PKG])
+    return EXE3
+
+
+def test_dropin_matcher_classes_compile_against_reference_types():
+    assert os.path.exists(_build_match())
+
+
+@pytest.mark.gpu
+def test_dropin_matcher_classes_equal_executed_reference(hvo, synth):
+    """The same in.bin the reference's own binary was fed (scenes of tests/test_ref_match.py / tests/test_track.py) through the drop-in
+    classes: ORBmatcher::SearchByProjection x2 and SearchForInitialization, LSDmatcher::SearchByProjection x2 and FrameBFMatchNew,
+    Frame::isInFrustum x2 (batched) must write what the reference wrote (committed fixtures match_ref.npz / track_ref.npz)."""
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_ref_match as trm
+    import test_track as tt
+    assert trm._golden is not None and tt._golden is not None
+    oracle.MATCH_EXE[0] = _build_match()
+    try:
+        for check in (trm._check_search_by_projection, trm._check_search_last, trm._check_line_search, trm._check_line_search_last):
+            check(hvo, synth, gpu=True)
+        for seed, cam, pts, ml, limit in tt._frustum_cases():
+            (rp,) = tt._ref(f'fpt{seed}', lambda: oracle.ref_frustum_points(cam, pts, limit))
+            (rl,) = tt._ref(f'fln{seed}', lambda: oracle.ref_frustum_lines(cam, ml, limit))
+        for seed, window, ratio, ori in ((0, 100, 0.9, True), (1, 30, 0.9, True), (2, 100, 0.7, False)):
+            F1, F2, prev = tt._init_scene(synth, seed)
+            tt._ref(f'init{seed}', lambda: oracle.ref_search_initialization(F1, F2, prev, window, ratio, ori))
+        for seed, TH, ratio in ((0, 50.0, 0.95), (1, 80.0, 0.8)):
+            kl1, ld1, kl2, ld2, lv2, F = tt._line_scene(synth, seed)
+            tt._ref(f'epi{seed}', lambda: oracle.ref_lines_epipolar(ld1, kl1, ld2, kl2, lv2, F, TH, ratio))
+    finally:
+        oracle.MATCH_EXE[0] = None
