@@ -92,6 +92,11 @@ ABI = {
     'hvo_lbd_sync': (C.c_int, [_vp]),
     'hvo_lbd_timer_start': (C.c_int, [_vp]),
     'hvo_lbd_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    'hvo_bow_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    'hvo_bow_destroy': (None, [_vp]),
+    'hvo_bow_set_vocabulary': (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    'hvo_bow_transform': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'hvo_bow_last_launches': (C.c_int, [_vp]),
     'hvo_proj_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
     'hvo_proj_destroy': (None, [_vp]),
     'hvo_proj_set_frame': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -1198,6 +1203,58 @@ PROJ_QUERY_DTYPE = np.dtype([('u', '<f4'), ('v', '<f4'), ('r', '<f4'), ('min_lev
                              ('claims', '<i4'), ('reserved', '<i4')])
 assert PROJ_QUERY_DTYPE.itemsize == 32
 GRID_COLS, GRID_ROWS = 64, 48
+
+
+class ORBVocabulary:
+    """Mirror of ORB_SLAM2::ORBVocabulary (= DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>, reference include/ORBVocabulary.h) for the
+    one call on the path, transform(features, BowVector, FeatureVector, levelsup) as used by Frame::ComputeBoW (src/Frame.cc:1692-1699).
+    voc = dict(child_start [n+1], child_ids, node_desc [n,32], node_weight [n], node_word [n], L)."""
+
+    def __init__(self, voc, device=0):
+        out = _vp()
+        _check(lib().hvo_bow_create(int(device), C.byref(out)))
+        self._h = out
+        cs = np.ascontiguousarray(voc['child_start'], np.int32); ci = np.ascontiguousarray(voc['child_ids'], np.int32)
+        nd = np.ascontiguousarray(voc['node_desc'], np.uint8); nw = np.ascontiguousarray(voc['node_weight'], np.float64)
+        wd = np.ascontiguousarray(voc['node_word'], np.int32)
+        _check(lib().hvo_bow_set_vocabulary(self._h, len(nw), _np_ptr(cs), _np_ptr(ci) if len(ci) else None, _np_ptr(nd), _np_ptr(nw), _np_ptr(wd),
+                                            int(voc['L'])))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().hvo_bow_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform_batch(self, desc_list, levelsup=4):
+        """[(BowVector as (words, values), FeatureVector as dict node -> feature indices, word_of, node_of)] for every frame."""
+        counts = [len(d) for d in desc_list]
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        total = int(off[-1])
+        desc = np.concatenate([np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in desc_list] + [np.zeros((0, 32), np.uint8)])
+        nf = len(desc_list)
+        word = np.full(max(total, 1), -1, np.int32); node = np.zeros(max(total, 1), np.int32)
+        bc = np.zeros(max(nf, 1), np.int32); bw = np.zeros(max(total, 1), np.int32); bv = np.zeros(max(total, 1), np.float64)
+        fo = np.full(max(total, 1), -1, np.int32); fc = np.zeros(max(nf, 1), np.int32)
+        _check(lib().hvo_bow_transform(self._h, _np_ptr(desc) if total else None, _np_ptr(off), nf, int(levelsup), _np_ptr(word), _np_ptr(node),
+                                       _np_ptr(bc), _np_ptr(bw), _np_ptr(bv), _np_ptr(fo), _np_ptr(fc)))
+        out = []
+        for f in range(nf):
+            a, n = int(off[f]), counts[f]
+            order = fo[a:a + fc[f]]
+            fv = {}
+            for i in order:
+                fv.setdefault(int(node[a + i]), []).append(int(i))
+            out.append(((bw[a:a + bc[f]].copy(), bv[a:a + bc[f]].copy()), fv, word[a:a + n].copy(), node[a:a + n].copy()))
+        return out
+
+    def transform(self, desc, levelsup=4):
+        return self.transform_batch([desc], levelsup)[0]
 
 
 class ProjectionMatcher:

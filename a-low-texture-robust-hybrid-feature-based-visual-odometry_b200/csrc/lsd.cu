@@ -396,7 +396,10 @@ __device__ __forceinline__ double lsd_density(int n, const LsdRect& r) {
     return (double)n / (sqrt(dx * dx + dy * dy) * r.width);
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(const LsdPix* __restrict__ pix, int w, int h, const uint32_t* __restrict__ order,
+#ifndef HVO_GROW_MINBLOCKS
+#define HVO_GROW_MINBLOCKS 32  /* 64 registers, no spills: 32 resident warps per SM instead of 24 */
+#endif
+__global__ void __launch_bounds__(32, HVO_GROW_MINBLOCKS) k_lsd_grow(const LsdPix* __restrict__ pix, int w, int h, const uint32_t* __restrict__ order,
                                                  const int* __restrict__ norder, uint32_t* __restrict__ regbuf, int min_reg_size,
                                                  double prec, double density_th, double inv_scale_div, float* __restrict__ seg,
                                                  int seg_cap, int* __restrict__ nseg, uint32_t* __restrict__ usedbuf) {

@@ -157,6 +157,27 @@ int hvo_matcher_sync(hvo_matcher* m);
 int hvo_matcher_timer_start(hvo_matcher* m);
 int hvo_matcher_timer_stop(hvo_matcher* m, float* ms_out);
 
+/* ------------------------------------------------------------------------------------------------ BOW
+ * Replaces Frame::ComputeBoW (src/Frame.cc:1692-1699) = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&,
+ * FeatureVector&, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1137-1206, :1228-1270) for ORB-SLAM2's vocabulary type (TF-IDF
+ * weights, L1 scoring), for a batch of frames.  The vocabulary tree is handed over as arrays (what ORBVocabulary::loadFromTextFile /
+ * the YAML loader fill into m_nodes): node 0 is the root; node i has the children child_ids[child_start[i] .. child_start[i+1]) in the
+ * reference's order (empty = leaf = word), a 32-byte descriptor, a weight and a word id (-1 for inner nodes).                          */
+typedef struct hvo_bow hvo_bow;
+int hvo_bow_create(int device, hvo_bow** out);
+void hvo_bow_destroy(hvo_bow* h);
+int hvo_bow_set_vocabulary(hvo_bow* h, int n_nodes, const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc,
+                           const double* node_weight, const int32_t* node_word, int depth_levels /* m_L */);
+/* desc: the frames' descriptors concatenated (frame f = rows offsets[f] .. offsets[f+1], at most 4096 per frame).  Per feature (may be
+ * NULL): word_of = word id, or -1 when the word is stopped (weight <= 0); node_of = the node passed at level m_L - levelsup (0 = root
+ * when that level is <= 0 or the leaf is reached earlier, where the reference leaves the value undefined).  Per frame: the BowVector as
+ * bow_counts[f] (word, value) pairs at bow_words / bow_values [offsets[f] ..], ascending word id, L1-normalised, bit-identical to the
+ * reference's std::map; the FeatureVector as fv_order [offsets[f] .. + fv_counts[f]) = feature indices (inside the frame) sorted by
+ * (node_of, feature): consecutive runs of equal node_of are the map's vectors. */
+int hvo_bow_transform(hvo_bow* h, const uint8_t* desc, const int32_t* offsets, int nframes, int levelsup, int32_t* word_of, int32_t* node_of,
+                      int32_t* bow_counts, int32_t* bow_words, double* bow_values, int32_t* fv_order, int32_t* fv_counts);
+int hvo_bow_last_launches(const hvo_bow* h);
+
 /* ------------------------------------------------------------------------------------------- PROJECTION
  * Windowed matching against one frame: the frame grid (Frame::AssignFeaturesToGrid / PosInGrid, src/Frame.cc:832-847,
  * 1680-1690), Frame::GetFeaturesInArea (src/Frame.cc:1502-1555) and the greedy best / second-best search of

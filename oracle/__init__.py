@@ -859,6 +859,73 @@ def ref_lines_epipolar(ldesc1, kls1, ldesc2, kls2, kls2func, F, TH, nnratio):
     return None if raw is None else np.frombuffer(raw, np.int32, len(k1)).copy()
 
 
+
+# ---- bag of words (oracle/bow_oracle.cpp; the reference's own DBoW2 executed: oracle/_ref/ref_bow) --------------------------------
+def bow_transform(voc, desc, levelsup=4):
+    """DBoW2 transform(features, BowVector, FeatureVector, levelsup) for one frame.  Returns ((words, values), fv dict, word_of, node_of)."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(d)
+    cs = np.ascontiguousarray(voc['child_start'], np.int32); ci = np.ascontiguousarray(voc['child_ids'], np.int32)
+    nd = np.ascontiguousarray(voc['node_desc'], np.uint8); nw = np.ascontiguousarray(voc['node_weight'], np.float64)
+    wd = np.ascontiguousarray(voc['node_word'], np.int32)
+    word = np.full(max(n, 1), -1, np.int32); node = np.zeros(max(n, 1), np.int32)
+    bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); fo = np.zeros(max(n, 1), np.int32)
+    k1, k2 = C.c_int(0), C.c_int(0)
+    f = lib().orc_bow_transform
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+    f.restype = None
+    f(_p(cs), _p(ci), _p(nd), _p(nw), _p(wd), int(voc['L']), _p(d), n, int(levelsup), _p(word), _p(node), _p(bw), _p(bv), C.byref(k1), _p(fo), C.byref(k2))
+    fv = {}
+    for i in fo[:k2.value]:
+        fv.setdefault(int(node[i]), []).append(int(i))
+    return (bw[:k1.value].copy(), bv[:k1.value].copy()), fv, word[:n].copy(), node[:n].copy()
+
+
+def ref_bow(training, frames, k=10, L=4, seed=1, levelsup=2):
+    """The reference's own DBoW2 executed (oracle/_ref/ref_bow): builds a vocabulary with TemplatedVocabulary::create from `training`
+    (list of [n,32] descriptor arrays) and transforms `frames`.  Returns (voc dict, [((words, values), fv dict)]) or None."""
+    exe = ref_bin('ref_bow')
+    if exe is None:
+        return None
+    b = struct.pack('<6i', 0x424f5756, k, L, seed, levelsup, len(training))
+    for t in training:
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        b += struct.pack('<i', len(t)) + t.tobytes()
+    b += struct.pack('<i', len(frames))
+    for t in frames:
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        b += struct.pack('<i', len(t)) + t.tobytes()
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(b)
+        subprocess.check_call([exe, fi, fo], stdout=subprocess.DEVNULL)
+        raw = open(fo, 'rb').read()
+    off = 0
+    (nn,) = struct.unpack_from('<i', raw, off); off += 4
+    cs, ci, nd, nw, wd = [0], [], np.zeros((nn, 32), np.uint8), np.zeros(nn), np.zeros(nn, np.int32)
+    for i in range(nn):
+        parent, word, nc = struct.unpack_from('<3i', raw, off); off += 12
+        ci.extend(struct.unpack_from(f'<{nc}i', raw, off)); off += 4 * nc
+        cs.append(len(ci))
+        nd[i] = np.frombuffer(raw, np.uint8, 32, off); off += 32
+        (nw[i],) = struct.unpack_from('<d', raw, off); off += 8
+        wd[i] = word
+    voc = dict(child_start=np.asarray(cs, np.int32), child_ids=np.asarray(ci, np.int32), node_desc=nd, node_weight=nw, node_word=wd, L=L)
+    out = []
+    for _ in frames:
+        (m,) = struct.unpack_from('<i', raw, off); off += 4
+        rec = np.frombuffer(raw, np.dtype([('w', '<i4'), ('v', '<f8')]), m, off); off += 12 * m
+        (nn2,) = struct.unpack_from('<i', raw, off); off += 4
+        fv = {}
+        for _ in range(nn2):
+            nid, cnt = struct.unpack_from('<2i', raw, off); off += 8
+            fv[nid] = list(struct.unpack_from(f'<{cnt}i', raw, off)); off += 4 * cnt
+        out.append(((rec['w'].copy(), rec['v'].copy()), fv))
+    assert off == len(raw)
+    return voc, out
+
+
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)
     h, w = d.shape

@@ -145,8 +145,29 @@ struct DMatch {
     DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
     bool operator<(const DMatch& m) const { return distance < m.distance; }
 };
-struct FileNode {};
-struct FileStorage {};
+// cv::FileStorage / cv::FileNode: never opened on the path (the harnesses build their data in memory); the members exist so that the
+// YAML save / load members of DBoW2::TemplatedVocabulary (virtual, hence instantiated) compile.  isOpened() is false: they throw.
+struct FileNode {
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator float() const { return 0.f; }
+    operator double() const { return 0.; }
+    operator std::string() const { return std::string(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+};
+template <typename T> static inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 class Algorithm {
 public:
     virtual ~Algorithm() {}

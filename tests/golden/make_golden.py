@@ -15,6 +15,8 @@ peac_ref.npz   outputs of the reference's own plane extractor (src/PlaneExtracto
 lines_ref.npz  outputs of the reference's own line front-end (oracle/_ref/ref_lines: vendored LSDDetector_custom.cpp whole, the
                LBD functions of binary_descriptor_custom.cpp, LINEextractor::operator() and Frame::cullingLine extracted at build
                time) on synthetic frames: KeyLines + LBD + line functions before and after cullingLine.
+bow_ref.npz    a vocabulary built by the reference's own DBoW2 (TemplatedVocabulary::create, k = 10, L = 4, seeded) from synthetic ORB
+               descriptors, and its transform(features, BowVector, FeatureVector, levelsup) of six frames (oracle/_ref/ref_bow)
 track_ref.npz  outputs of the reference's own Frame::isInFrustum x2, ORBmatcher::SearchForInitialization and LSDmatcher::FrameBFMatchNew
                (oracle/_ref/ref_match ops 4-7) on the scenes of tests/test_track.py
 match_ref.npz  outputs of the reference's own windowed matchers (oracle/_ref/ref_match: Frame grids + GetFeaturesInArea*, the two
@@ -215,8 +217,20 @@ def track():
     print('track_ref.npz written:', len(t.RECORD), 'arrays')
 
 
+def bow():
+    if oracle.ref_bin('ref_bow') is None:
+        print('oracle/_ref/ref_bow missing: run make -C oracle first')
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_bow as t
+    out = t.make_golden(synth)
+    print('bow_ref.npz written:', len(out), 'arrays')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track', 'bow']
+    if 'bow' in which:
+        bow()
     if 'track' in which:
         track()
     if 'match' in which:
