@@ -96,9 +96,8 @@ struct KeyLineDev {  // cv::line_descriptor::KeyLine POD, 68 bytes
 __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__ dxI, const int16_t* __restrict__ dyI, int w, int h,
                                                      long long frame_px, const KeyLineDev* __restrict__ kls,
                                                      const int32_t* __restrict__ counts, int max_lines, LbdWeights W,
-                                                     uint8_t* __restrict__ desc, float* __restrict__ fdesc) {
+                                                     float* __restrict__ raw) {
     __shared__ float rows[kLbdH][8];  // per row: pL, nL, pO, nO and their squares (after the global weight)
-    __shared__ float des[72];
     const int line = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     if (line >= counts[f]) return;
     const KeyLineDev kl = kls[(long long)f * max_lines + line];
@@ -146,48 +145,69 @@ __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__
             const float c = W.L[r % kLbdBandW + (rb == b ? kLbdBandW : (rb == b + 1 ? 2 * kLbdBandW : 0))];
             acc += (q < 4) ? c * rows[r][q] : c * c * rows[r][q];
         }
-        des[tid] = acc;
+        // the 72 band sums of this line; the serial normalisation runs lane-parallel over lines in k_lbd_finish
+        raw[((long long)f * max_lines + line) * 72 + tid] = acc;
     }
-    __syncthreads();
-    if (tid == 0) {
-        const float invN2 = (float)(1.0 / (kLbdBandW * 2.0)), invN3 = (float)(1.0 / (kLbdBandW * 3.0));
-        float d[72];
-        for (int b = 0; b < kLbdBands; ++b) {
-            const float invN = (b == 0 || b == kLbdBands - 1) ? invN2 : invN3;
-            for (int q = 0; q < 4; ++q) {
-                const float temp = des[8 * b + q] * invN;
-                d[8 * b + q] = temp;
-                d[8 * b + 4 + q] = sqrtf(des[8 * b + 4 + q] * invN - temp * temp);
-            }
+}
+
+// Second half of computeLBD (binary_descriptor_custom.cpp:1300-1372): mean / standard deviation per band, the two normalisations, the 0.4
+// clamp, the final normalisation and the 32 comparison bytes.  Every sum is sequential in the reference, so it is one thread per line (the
+// lanes of a warp work on 32 different lines) instead of one thread of a 96-thread CTA with the other 95 waiting at a barrier.
+__global__ void __launch_bounds__(128) k_lbd_finish(const float* __restrict__ raw, const int32_t* __restrict__ counts, int max_lines, int nframes,
+                                                    uint8_t* __restrict__ desc, float* __restrict__ fdesc) {
+    __shared__ float sd[72][128];   // d[k] of thread t at sd[k][t]: conflict-free, dynamically indexable
+    const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (i >= (long long)nframes * max_lines) return;
+    const int f = (int)(i / max_lines), line = (int)(i - (long long)f * max_lines);
+    if (line >= counts[f]) return;
+    const float* des = raw + i * 72;
+    float(*d)[128] = reinterpret_cast<float(*)[128]>(&sd[0][threadIdx.x]);   // d[k][0] == sd[k][tid]
+    const float invN2 = (float)(1.0 / (kLbdBandW * 2.0)), invN3 = (float)(1.0 / (kLbdBandW * 3.0));
+    for (int b = 0; b < kLbdBands; ++b) {
+        const float invN = (b == 0 || b == kLbdBands - 1) ? invN2 : invN3;
+        const float4 m4 = *reinterpret_cast<const float4*>(des + 8 * b), s4 = *reinterpret_cast<const float4*>(des + 8 * b + 4);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float temp = mm[q] * invN;
+            d[8 * b + q][0] = temp;
+            d[8 * b + 4 + q][0] = sqrtf(ss[q] * invN - temp * temp);
         }
-        float tempM = 0, tempS = 0;
-        for (int b = 0; b < kLbdBands; ++b) {
-            for (int q = 0; q < 4; ++q) tempM += d[8 * b + q] * d[8 * b + q];
-            for (int q = 4; q < 8; ++q) tempS += d[8 * b + q] * d[8 * b + q];
-        }
-        tempM = 1.f / sqrtf(tempM);
-        tempS = 1.f / sqrtf(tempS);
-        for (int b = 0; b < kLbdBands; ++b) {
-            for (int q = 0; q < 4; ++q) d[8 * b + q] = d[8 * b + q] * tempM;
-            for (int q = 4; q < 8; ++q) d[8 * b + q] = d[8 * b + q] * tempS;
-        }
-        for (int i = 0; i < 72; ++i) if (d[i] > 0.4f) d[i] = 0.4f;  // (double)x > 0.4  <=>  x >= 0.4f, and the clamp value is 0.4f
-        float temp = 0;
-        for (int i = 0; i < 72; ++i) temp += d[i] * d[i];
-        temp = 1.f / sqrtf(temp);
-        for (int i = 0; i < 72; ++i) des[i] = d[i] * temp;
     }
-    __syncthreads();
-    const long long o = (long long)f * max_lines + line;
-    if (tid < 32) {
-        const float* f1 = &des[8 * c_comb[2 * tid]];
-        const float* f2 = &des[8 * c_comb[2 * tid + 1]];
+    float tempM = 0, tempS = 0;
+    for (int b = 0; b < kLbdBands; ++b) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tempM += d[8 * b + q][0] * d[8 * b + q][0];
+#pragma unroll
+        for (int q = 4; q < 8; ++q) tempS += d[8 * b + q][0] * d[8 * b + q][0];
+    }
+    tempM = 1.f / sqrtf(tempM);
+    tempS = 1.f / sqrtf(tempS);
+    float temp = 0;
+    for (int b = 0; b < kLbdBands; ++b)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v = d[8 * b + q][0] * (q < 4 ? tempM : tempS);
+            if (v > 0.4f) v = 0.4f;  // (double)x > 0.4  <=>  x >= 0.4f, and the clamp value is 0.4f
+            d[8 * b + q][0] = v;
+        }
+    for (int k = 0; k < 72; ++k) temp += d[k][0] * d[k][0];
+    temp = 1.f / sqrtf(temp);
+    for (int k = 0; k < 72; ++k) d[k][0] = d[k][0] * temp;
+    uint32_t words[8];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        const int i1 = 8 * c_comb[2 * t], i2 = 8 * c_comb[2 * t + 1];
         unsigned v = 0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) v |= (f1[b] > f2[b] ? 1u : 0u) << b;
-        desc[o * 32 + tid] = (uint8_t)v;
+        for (int b = 0; b < 8; ++b) v |= (d[i1 + b][0] > d[i2 + b][0] ? 1u : 0u) << b;
+        if ((t & 3) == 0) words[t >> 2] = v; else words[t >> 2] |= v << (8 * (t & 3));
     }
-    if (fdesc != nullptr && tid < 72) fdesc[o * 72 + tid] = des[tid];
+    uint4* o = reinterpret_cast<uint4*>(desc + i * 32);
+    o[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    o[1] = make_uint4(words[4], words[5], words[6], words[7]);
+    if (fdesc != nullptr)
+        for (int k = 0; k < 72; ++k) fdesc[i * 72 + k] = d[k][0];
 }
 
 }  // namespace hvo
@@ -205,6 +225,7 @@ struct hvo_lbd {
     int32_t* d_counts = nullptr;
     uint8_t* d_desc = nullptr;
     float* d_fdesc = nullptr;
+    float* d_raw = nullptr;   // [B][max_lines][72] band sums between k_lbd_describe and k_lbd_finish
     int last_launches = 0;
 };
 
@@ -216,8 +237,10 @@ static int lbd_run_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray
                                                                                               h->d_dx, h->d_dy);
     timeline_mark(stream, "k_lbd_describe");
     k_lbd_describe<<<dim3(h->max_lines, nframes), 96, 0, stream>>>(h->d_dx, h->d_dy, h->width, h->height, fpx, d_kl, d_counts,
-                                                                   h->max_lines, h->W, d_desc, d_fdesc);
-    h->last_launches = 2;
+                                                                   h->max_lines, h->W, h->d_raw);
+    timeline_mark(stream, "k_lbd_finish");
+    k_lbd_finish<<<div_up(nframes * h->max_lines, 128), 128, 0, stream>>>(h->d_raw, d_counts, h->max_lines, nframes, d_desc, d_fdesc);
+    h->last_launches = 3;
     HVO_CUDA(cudaGetLastError());
     return HVO_OK;
 }
@@ -271,6 +294,7 @@ int hvo_lbd_create(int width, int height, int max_batch, int max_lines, int devi
         HVO_TRY(cudaMalloc(&h->d_counts, B * sizeof(int32_t)));
         HVO_TRY(cudaMalloc(&h->d_desc, B * max_lines * 32));
         HVO_TRY(cudaMalloc(&h->d_fdesc, B * max_lines * 72 * sizeof(float)));
+        HVO_TRY(cudaMalloc(&h->d_raw, B * max_lines * 72 * sizeof(float)));
 #undef HVO_TRY
     } while (0);
     if (st != HVO_OK) { hvo_lbd_destroy(h); return st; }
@@ -282,7 +306,7 @@ void hvo_lbd_destroy(hvo_lbd* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_gray, h->d_dx, h->d_dy, h->d_kl, h->d_counts, h->d_desc, h->d_fdesc};
+    void* bufs[] = {h->d_gray, h->d_dx, h->d_dy, h->d_kl, h->d_counts, h->d_desc, h->d_fdesc, h->d_raw};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -965,10 +965,10 @@ static int line_extract_device(hvo_line* h, const uint8_t* d_gray, int nframes, 
         // the reference computes LBD twice (LineExtractor.cpp:361-363, Frame.cc:1094-1096) and discards the first result;
         // only the descriptors of the culled KeyLines survive, so only those are computed
         st = line_cull_device(h, d_gray, nframes, d_kl, d_desc, d_linevec, d_counts);
-        h->last_launches = 7;
+        h->last_launches = 8;
     } else {
         st = lbd_compute_on_stream(h->lbd, h->stream, d_gray, nframes, reinterpret_cast<const hvo_keyline*>(d_kl), d_counts, d_desc);
-        h->last_launches = 6;
+        h->last_launches = 7;
     }
     if (h->profiling) cudaEventRecord(h->sev[4], h->stream);
     return st;

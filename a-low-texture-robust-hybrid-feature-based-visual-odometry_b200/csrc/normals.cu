@@ -45,26 +45,50 @@ __global__ void k_sn_cloud(const uint16_t* __restrict__ depth, SnGeom g, float* 
 }
 
 // SAT layout: [f][ch+1][cw+1][6] doubles (dx.xyz, dy.xyz)
-__global__ void k_sn_rowscan(const float* __restrict__ pts, SnGeom g, double* __restrict__ sat) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+// One warp per SAT row: 32 cloud columns at a time, lane <-> column.  Every lane forms its six central differences, the
+// warp adds them up with a shuffle scan (the terms are float differences widened to double, whose partial sums are exact in
+// double, so the association does not matter) and each lane stores its six doubles next to its neighbours' (48 B per lane,
+// 1.5 KB contiguous per warp).  Round 1 had one thread per row writing 48-byte records 10 KB apart (2.4 ms per 1184 frames).
+__global__ void __launch_bounds__(128) k_sn_rowscan(const float* __restrict__ pts, SnGeom g, double* __restrict__ sat) {
+    const int r = blockIdx.x * 4 + (threadIdx.x >> 5), f = blockIdx.y, lane = threadIdx.x & 31;
     if (r > g.ch) return;
     const int iw = g.cw + 1;
     double* row = sat + ((long long)f * (g.ch + 1) + r) * iw * 6;
-    for (int k = 0; k < 6; ++k) row[k] = 0.0;
-    if (r == 0) { for (int c = 1; c <= g.cw; ++c) for (int k = 0; k < 6; ++k) row[c * 6 + k] = 0.0; return; }
+    if (r == 0) {
+        for (int i = lane; i < iw * 6; i += 32) row[i] = 0.0;
+        return;
+    }
+    if (lane < 6) row[lane] = 0.0;
     const int rr = r - 1;  // cloud row
+    const bool inner_row = rr >= 1 && rr < g.ch - 1;
     const float* P = pts + (long long)f * g.ch * g.cw * 3;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < g.cw; ++c) {
-        if (rr >= 1 && rr < g.ch - 1 && c >= 1 && c < g.cw - 1) {
+    double carry[6] = {0, 0, 0, 0, 0, 0};
+    for (int c0 = 0; c0 < g.cw; c0 += 32) {
+        const int c = c0 + lane;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (inner_row && c >= 1 && c < g.cw - 1) {
             const float* L = P + ((long long)rr * g.cw + c - 1) * 3;
             const float* R = P + ((long long)rr * g.cw + c + 1) * 3;
             const float* U = P + ((long long)(rr - 1) * g.cw + c) * 3;
             const float* Dn = P + ((long long)(rr + 1) * g.cw + c) * 3;
-            acc[0] += (double)(R[0] - L[0]); acc[1] += (double)(R[1] - L[1]); acc[2] += (double)(R[2] - L[2]);
-            acc[3] += (double)(Dn[0] - U[0]); acc[4] += (double)(Dn[1] - U[1]); acc[5] += (double)(Dn[2] - U[2]);
+            v[0] = (double)(R[0] - L[0]); v[1] = (double)(R[1] - L[1]); v[2] = (double)(R[2] - L[2]);
+            v[3] = (double)(Dn[0] - U[0]); v[4] = (double)(Dn[1] - U[1]); v[5] = (double)(Dn[2] - U[2]);
         }
-        for (int k = 0; k < 6; ++k) row[(c + 1) * 6 + k] = acc[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double t = __shfl_up_sync(0xffffffffu, v[k], o);
+                if (lane >= o) v[k] += t;
+            }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] += carry[k];
+        if (c < g.cw) {
+            double2* o2 = reinterpret_cast<double2*>(row + (long long)(c + 1) * 6);   // (c + 1) * 48 B: 16-byte aligned
+            o2[0] = make_double2(v[0], v[1]); o2[1] = make_double2(v[2], v[3]); o2[2] = make_double2(v[4], v[5]);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) carry[k] = __shfl_sync(0xffffffffu, v[k], 31);
     }
 }
 
@@ -186,7 +210,7 @@ static int sn_run(hvo_normals* h, const uint16_t* d_depth, int nf, float* d_out)
     timeline_mark(h->stream, "k_sn_cloud");
     k_sn_cloud<<<dim3(div_up(g.cw, 128), g.ch, nf), 128, 0, h->stream>>>(d_depth, g, h->d_pts, h->d_dist);
     timeline_mark(h->stream, "k_sn_rowscan");
-    k_sn_rowscan<<<dim3(div_up(g.ch + 1, 64), nf), 64, 0, h->stream>>>(h->d_pts, g, h->d_sat);
+    k_sn_rowscan<<<dim3(div_up(g.ch + 1, 4), nf), 128, 0, h->stream>>>(h->d_pts, g, h->d_sat);
     timeline_mark(h->stream, "k_sn_colscan");
     k_sn_colscan<<<dim3(div_up((g.cw + 1) * 6, 128), nf), 128, 0, h->stream>>>(g, h->d_sat);
     timeline_mark(h->stream, "k_sn_chamfer");
