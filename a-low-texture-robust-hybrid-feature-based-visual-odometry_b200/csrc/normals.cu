@@ -104,50 +104,102 @@ __global__ void k_sn_colscan(SnGeom g, double* __restrict__ sat) {
     }
 }
 
-__global__ void __launch_bounds__(32) k_sn_chamfer(SnGeom g, float* __restrict__ dist_all) {
-    extern __shared__ float sm[];  // 3 rows of cw floats: prev (or next), cur, m
-    const int f = blockIdx.x, lane = threadIdx.x, cw = g.cw, ch = g.ch;
-    float* dist = dist_all + (long long)f * ch * cw;
-    float *a = sm, *b = sm + cw, *m = sm + 2 * cw;
+// kChamferFrames frames per CTA, one warp each.  The three upper (lower) taps of a row are lane-parallel per frame; the left (right)
+// dependency is a float chain that has to be replayed in order, so it is done for all the CTA's frames at once by the first lanes of
+// warp 0 (lane j <-> frame j): the serial part costs kChamferFrames times fewer instructions than with one active lane per warp.
+static const int kChamferFrames = 8;
+__global__ void __launch_bounds__(32 * kChamferFrames) k_sn_chamfer(SnGeom g, float* __restrict__ dist_all, int nf) {
+    extern __shared__ float sm[];  // per frame 3 rows of cw floats: prev (or next), cur, m
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, cw = g.cw, ch = g.ch;
+    const int f = blockIdx.x * kChamferFrames + wid;
+    const bool live = f < nf;
+    float* dist = dist_all + (long long)(live ? f : 0) * ch * cw;
+    float* base = sm + (size_t)wid * 3 * cw;
+    int ia = 0, ib = 1;                       // row roles rotate identically in every warp
+    float* m = base + 2 * cw;
+    auto serial_fwd = [&]() {
+        if (wid == 0 && lane < kChamferFrames && blockIdx.x * kChamferFrames + lane < nf) {
+            float* bb = sm + (size_t)lane * 3 * cw + ib * cw;
+            const float* mm = sm + (size_t)lane * 3 * cw + 2 * cw;
+            float left = bb[0];
+            int c = 1;
+            for (; c + 3 < cw; c += 4) {   // loads first: only add / min / select are on the dependent chain
+                const float m0 = mm[c], m1 = mm[c + 1], m2 = mm[c + 2], m3 = mm[c + 3];
+                const float b0 = bb[c], b1 = bb[c + 1], b2 = bb[c + 2], b3 = bb[c + 3];
+                float v = fminf(m0, left + 1.0f); const float r0 = v < b0 ? v : b0;
+                v = fminf(m1, r0 + 1.0f); const float r1 = v < b1 ? v : b1;
+                v = fminf(m2, r1 + 1.0f); const float r2 = v < b2 ? v : b2;
+                v = fminf(m3, r2 + 1.0f); const float r3 = v < b3 ? v : b3;
+                bb[c] = r0; bb[c + 1] = r1; bb[c + 2] = r2; bb[c + 3] = r3;
+                left = r3;
+            }
+            for (; c < cw; ++c) {
+                const float v = fminf(mm[c], left + 1.0f);
+                float cur = bb[c];
+                if (v < cur) { cur = v; bb[c] = v; }
+                left = cur;
+            }
+        }
+    };
+    auto serial_bwd = [&]() {
+        if (wid == 0 && lane < kChamferFrames && blockIdx.x * kChamferFrames + lane < nf) {
+            float* bb = sm + (size_t)lane * 3 * cw + ib * cw;
+            const float* mm = sm + (size_t)lane * 3 * cw + 2 * cw;
+            float right = bb[cw - 1];
+            int c = cw - 2;
+            for (; c - 3 >= 0; c -= 4) {
+                const float m0 = mm[c], m1 = mm[c - 1], m2 = mm[c - 2], m3 = mm[c - 3];
+                const float b0 = bb[c], b1 = bb[c - 1], b2 = bb[c - 2], b3 = bb[c - 3];
+                float v = fminf(m0, right + 1.0f); const float r0 = v < b0 ? v : b0;
+                v = fminf(m1, r0 + 1.0f); const float r1 = v < b1 ? v : b1;
+                v = fminf(m2, r1 + 1.0f); const float r2 = v < b2 ? v : b2;
+                v = fminf(m3, r2 + 1.0f); const float r3 = v < b3 ? v : b3;
+                bb[c] = r0; bb[c - 1] = r1; bb[c - 2] = r2; bb[c - 3] = r3;
+                right = r3;
+            }
+            for (; c >= 0; --c) {
+                const float v = fminf(mm[c], right + 1.0f);
+                float cur = bb[c];
+                if (v < cur) { cur = v; bb[c] = v; }
+                right = cur;
+            }
+        }
+    };
     // forward pass
-    for (int c = lane; c < cw; c += 32) a[c] = dist[c];
-    __syncwarp();
+    if (live) for (int c = lane; c < cw; c += 32) base[ia * cw + c] = dist[c];
+    __syncthreads();
     for (int r = 1; r < ch; ++r) {
-        for (int c = lane; c < cw; c += 32) b[c] = dist[(long long)r * cw + c];
-        __syncwarp();
-        for (int c = 1 + lane; c < cw; c += 32) {
-            const float ur = (c + 1 < cw) ? a[c + 1] : b[0];  // PCL reads one element past the previous row
-            m[c] = fminf(fminf(a[c - 1] + 1.4f, a[c] + 1.0f), ur + 1.4f);
-        }
-        __syncwarp();
-        if (lane == 0)
-            for (int c = 1; c < cw; ++c) {
-                const float v = fminf(m[c], b[c - 1] + 1.0f);
-                if (v < b[c]) b[c] = v;
+        float *a = base + ia * cw, *b = base + ib * cw;
+        if (live) {
+            for (int c = lane; c < cw; c += 32) b[c] = dist[(long long)r * cw + c];
+            __syncwarp();
+            for (int c = 1 + lane; c < cw; c += 32) {
+                const float ur = (c + 1 < cw) ? a[c + 1] : b[0];  // PCL reads one element past the previous row
+                m[c] = fminf(fminf(a[c - 1] + 1.4f, a[c] + 1.0f), ur + 1.4f);
             }
-        __syncwarp();
-        for (int c = lane; c < cw; c += 32) dist[(long long)r * cw + c] = b[c];
-        float* t = a; a = b; b = t;
-        __syncwarp();
+        }
+        __syncthreads();
+        serial_fwd();
+        __syncthreads();
+        if (live) for (int c = lane; c < cw; c += 32) dist[(long long)r * cw + c] = b[c];
+        const int t = ia; ia = ib; ib = t;
     }
-    // backward pass: `a` holds the last row
+    // backward pass: row `ia` holds the last row
     for (int r = ch - 2; r >= 0; --r) {
-        for (int c = lane; c < cw; c += 32) b[c] = dist[(long long)r * cw + c];
-        __syncwarp();
-        for (int c = lane; c <= cw - 2; c += 32) {
-            const float ll = (c >= 1) ? a[c - 1] : b[cw - 1];  // PCL reads one element before the next row
-            m[c] = fminf(fminf(ll + 1.4f, a[c] + 1.0f), a[c + 1] + 1.4f);
-        }
-        __syncwarp();
-        if (lane == 0)
-            for (int c = cw - 2; c >= 0; --c) {
-                const float v = fminf(m[c], b[c + 1] + 1.0f);
-                if (v < b[c]) b[c] = v;
+        float *a = base + ia * cw, *b = base + ib * cw;
+        if (live) {
+            for (int c = lane; c < cw; c += 32) b[c] = dist[(long long)r * cw + c];
+            __syncwarp();
+            for (int c = lane; c <= cw - 2; c += 32) {
+                const float ll = (c >= 1) ? a[c - 1] : b[cw - 1];  // PCL reads one element before the next row
+                m[c] = fminf(fminf(ll + 1.4f, a[c] + 1.0f), a[c + 1] + 1.4f);
             }
-        __syncwarp();
-        for (int c = lane; c < cw; c += 32) dist[(long long)r * cw + c] = b[c];
-        float* t = a; a = b; b = t;
-        __syncwarp();
+        }
+        __syncthreads();
+        serial_bwd();
+        __syncthreads();
+        if (live) for (int c = lane; c < cw; c += 32) dist[(long long)r * cw + c] = b[c];
+        const int t = ia; ia = ib; ib = t;
     }
 }
 
@@ -214,7 +266,7 @@ static int sn_run(hvo_normals* h, const uint16_t* d_depth, int nf, float* d_out)
     timeline_mark(h->stream, "k_sn_colscan");
     k_sn_colscan<<<dim3(div_up((g.cw + 1) * 6, 128), nf), 128, 0, h->stream>>>(g, h->d_sat);
     timeline_mark(h->stream, "k_sn_chamfer");
-    k_sn_chamfer<<<nf, 32, 3 * g.cw * sizeof(float), h->stream>>>(g, h->d_dist);
+    k_sn_chamfer<<<div_up(nf, kChamferFrames), 32 * kChamferFrames, (size_t)kChamferFrames * 3 * g.cw * sizeof(float), h->stream>>>(g, h->d_dist, nf);
     timeline_mark(h->stream, "k_sn_normals");
     k_sn_normals<<<dim3(div_up(h->n_out, 128), nf), 128, 0, h->stream>>>(g, h->d_pts, h->d_dist, h->d_sat, d_out);
     HVO_CUDA(cudaGetLastError());
