@@ -584,6 +584,65 @@ def main():
         bfm.close()
         configs['C4'] = dict(workload='matching stress: brute-force Hamming knn-2 + ratio test inputs, device-resident', **c4)
 
+        # ---- tracking-time path (host call, host buffers in / out): Tracking::SearchLocalPoints as one call (isInFrustum over the local map +
+        #      SearchByProjection) for a 2000-keypoint frame against 10^4 / 5 x 10^4 map points, and Frame::ComputeBoW on a synthetic k = 10, L = 6
+        #      vocabulary (10^6 words, random descriptors: the reference's ORBvoc.bin is not in the tree) ----
+        try:
+            rng = np.random.RandomState(7)
+            nk = 2000
+            keys = np.zeros(nk, hvo.KP_DTYPE)
+            keys['x'] = rng.uniform(20, W - 20, nk); keys['y'] = rng.uniform(20, H - 20, nk); keys['octave'] = rng.randint(0, 8, nk)
+            kdesc = rng.randint(0, 256, (nk, 32)).astype(np.uint8)
+            sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+            cam = hvo.frustum_cam(np.eye(3, dtype=np.float32), np.zeros(3, np.float32), CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], 40.0, (0.0, 0.0, float(W), float(H)))
+            pmh = hvo.ProjectionMatcher(local_rank)
+            pmh.set_frame(keys, None, kdesc, 0.0, 0.0, float(W), float(H))
+            track = {}
+            for M in (10000, 50000):
+                z = rng.uniform(0.5, 6.0, M)
+                src = rng.randint(0, nk, M)
+                pts = np.zeros(M, hvo.MAP_POINT_DTYPE)
+                u = keys['x'][src] + rng.normal(0, 1.5, M); v = keys['y'][src] + rng.normal(0, 1.5, M)
+                pts['pos'] = np.stack([(u - CAM['cx']) * z / CAM['fx'], (v - CAM['cy']) * z / CAM['fy'], z], 1).astype(np.float32)
+                nrm = -pts['pos'] / np.linalg.norm(pts['pos'], axis=1)[:, None]
+                pts['normal'] = -nrm
+                d = np.linalg.norm(pts['pos'], axis=1)
+                pts['max_distance'] = (d * sf[keys['octave'][src]]).astype(np.float32); pts['min_distance'] = pts['max_distance'] / sf[7]
+                pdesc = kdesc[src].copy()
+                flip = rng.randint(0, 256, M)
+                pdesc[np.arange(M), flip // 8] ^= (1 << (flip % 8)).astype(np.uint8)
+                for _ in range(2):
+                    res = pmh.search_local_map(cam, pts, pdesc, sf, th=3.0, th_dist=100, nnratio=0.8)
+                t0c = time.perf_counter()
+                for _ in range(5):
+                    res = pmh.search_local_map(cam, pts, pdesc, sf, th=3.0, th_dist=100, nnratio=0.8)
+                ms_c = 1e3 * (time.perf_counter() - t0c) / 5
+                track[f'search_local_points_{M}'] = dict(host_call_ms=ms_c, map_points_per_s=M / ms_c * 1e3, in_view=int(res[3]), matches=int(res[4]),
+                                                         rounds=int(pmh.rounds()))
+            pmh.close()
+            kk, LL = 10, 6
+            nn = (kk ** (LL + 1) - 1) // (kk - 1)
+            first_leaf = (kk ** LL - 1) // (kk - 1)
+            child_start = np.minimum(np.arange(nn + 1, dtype=np.int64) * kk, (first_leaf) * kk).astype(np.int32)
+            child_ids = np.arange(1, first_leaf * kk + 1, dtype=np.int32)
+            voc = dict(child_start=child_start, child_ids=child_ids, node_desc=rng.randint(0, 256, (nn, 32)).astype(np.uint8),
+                       node_weight=np.where(np.arange(nn) >= first_leaf, rng.uniform(0.5, 8.0, nn), 0.0),
+                       node_word=np.where(np.arange(nn) >= first_leaf, np.arange(nn) - first_leaf, -1).astype(np.int32), L=LL)
+            vv = hvo.ORBVocabulary(voc, local_rank)
+            frames_d = [rng.randint(0, 256, (1000, 32)).astype(np.uint8) for _ in range(64)]
+            for _ in range(2):
+                vv.transform_batch(frames_d, 4)
+            t0c = time.perf_counter()
+            for _ in range(3):
+                vv.transform_batch(frames_d, 4)
+            ms_c = 1e3 * (time.perf_counter() - t0c) / 3
+            vv.close()
+            track['compute_bow_64x1000'] = dict(host_call_ms=ms_c, frames_per_s=64 / ms_c * 1e3, vocabulary=f'synthetic k={kk} L={LL}, {nn - first_leaf} words')
+            configs['track'] = dict(workload='tracking-time path through the C ABI with host buffers, wall clock around the mirror call (uploads, downloads and the '
+                                             'Python-side unpacking included): isInFrustum + SearchByProjection over a local map; ComputeBoW', **track)
+        except Exception as e:   # a profiling extra must never take the bench line down
+            configs['track'] = dict(error=repr(e))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(gray, depth)
