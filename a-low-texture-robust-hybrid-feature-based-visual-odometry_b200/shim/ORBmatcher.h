@@ -16,9 +16,10 @@
 //   SearchByProjection(F, vpMapPoints, th)                         src/ORBmatcher.cc:45-132
 //   SearchByProjection(CurrentFrame, LastFrame, th, bMono)         src/ORBmatcher.cc:1353-1497
 //   SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, w) src/ORBmatcher.cc:412-529
+//   SearchByBoW(pKF, F, vpMapPointMatches)                         src/ORBmatcher.cc:162-293    (KeyFrame type deduced)
 //   DescriptorDistance                                             src/ORBmatcher.cc:1676-1692
-// (SearchByBoW / Fuse / SearchForTriangulation / SearchBySim3 need KeyFrame + DBoW2 types: their device loops are reached through
-//  shim/WindowedMatcherGPU.h's PointWindowMatcher, see INTEGRATION.md.)
+// (Fuse / SearchForTriangulation / SearchBySim3 need the KeyFrame pose / observation bookkeeping: their device loops are reached
+//  through shim/WindowedMatcherGPU.h's PointWindowMatcher, see INTEGRATION.md.)
 #ifndef HVO_SHIM_ORBMATCHER_H
 #define HVO_SHIM_ORBMATCHER_H
 
@@ -172,6 +173,58 @@ public:
         }
         for (size_t i1 = 0; i1 < vnMatches12.size(); i1++)
             if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;
+        return nmatches;
+    }
+
+    // src/ORBmatcher.cc:162-293.  KeyFrame is the reference's own type (deduced): GetMapPointMatches(), mFeatVec, mvKeysUn, mDescriptors;
+    // F.mFeatVec, F.mvKeys, F.mDescriptors.  The walk over the two DBoW2::FeatureVectors (std::map, equal node ids) stays here and builds
+    // the queries in the reference's visiting order; the greedy candidate loop runs on the device (hvo_proj_search_candidates).
+    template <class KeyFrame>
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+        const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+        const auto& vFeatVecKF = pKF->mFeatVec;
+        std::vector<uint8_t> qdesc, tdesc;
+        std::vector<int32_t> offsets(1, 0), cand, who;
+        auto KFit = vFeatVecKF.begin(), KFend = vFeatVecKF.end();
+        auto Fit = F.mFeatVec.begin(), Fend = F.mFeatVec.end();
+        while (KFit != KFend && Fit != Fend) {
+            if (KFit->first == Fit->first) {
+                for (size_t iKF = 0; iKF < KFit->second.size(); iKF++) {
+                    const unsigned int realIdxKF = KFit->second[iKF];
+                    MapPoint* pMP = vpMapPointsKF[realIdxKF];
+                    if (!pMP || pMP->isBad()) continue;
+                    appendDescriptor(qdesc, pKF->mDescriptors.row(realIdxKF));
+                    for (size_t iF = 0; iF < Fit->second.size(); iF++) cand.push_back((int32_t)Fit->second[iF]);
+                    offsets.push_back((int32_t)cand.size());
+                    who.push_back((int32_t)realIdxKF);
+                }
+                KFit++; Fit++;
+            } else if (KFit->first < Fit->first) KFit = vFeatVecKF.lower_bound(Fit->first);
+            else Fit = F.mFeatVec.lower_bound(KFit->first);
+        }
+        const int nq = (int)who.size();
+        if (nq == 0 || F.N == 0 || !h_) return 0;
+        for (int i = 0; i < F.N; ++i) appendDescriptor(tdesc, F.mDescriptors.row(i));
+        std::vector<int32_t> idx(nq, -1);
+        int nmatches = 0;
+        if (!ok(hvo_proj_search_candidates(h_, qdesc.data(), nq, tdesc.data(), F.N, offsets.data(), cand.data(), TH_LOW, mfNNratio, idx.data(), nullptr,
+                                           &nmatches)))
+            return 0;
+        const float factor = 1.0f / HISTO_LENGTH;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (int k = 0; k < nq; ++k) {
+            if (idx[k] < 0) continue;
+            vpMapPointMatches[idx[k]] = vpMapPointsKF[who[k]];
+            if (mbCheckOrientation) rotHist[rotationBin(pKF->mvKeysUn[who[k]].angle - F.mvKeys[idx[k]].angle, factor)].push_back(idx[k]);
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++)
+                if (i != ind1 && i != ind2 && i != ind3)
+                    for (size_t j = 0; j < rotHist[i].size(); j++) { vpMapPointMatches[rotHist[i][j]] = static_cast<MapPoint*>(NULL); nmatches--; }
+        }
         return nmatches;
     }
 

@@ -926,6 +926,46 @@ def ref_bow(training, frames, k=10, L=4, seed=1, levelsup=2):
     return voc, out
 
 
+
+def ref_distinctive(desc, offsets, lines=False):
+    """The reference's MapPoint / MapLine::ComputeDistinctiveDescriptors executed for a batch of map elements (oracle/_ref/ref_match op 8).
+    Returns (best_idx [ngroups] (-1 for an element without observations), best descriptors [ngroups, 32]) or None."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(offsets, np.int32)
+    ng = len(off) - 1
+    b = struct.pack('<2i', 0x4d544348, 8) + _f32([0, 0, 640, 480]) + struct.pack('<2i', int(lines), ng) + off.tobytes() + d.tobytes()
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    rec = np.frombuffer(raw, np.dtype([('idx', '<i4'), ('desc', 'u1', (32,))]), ng)
+    return rec['idx'].copy(), rec['desc'].copy()
+
+
+def _featvec_bytes(fv):
+    b = struct.pack('<i', len(fv))
+    for node in sorted(fv):
+        idx = np.asarray(fv[node], np.int32)
+        b += struct.pack('<2i', int(node), len(idx)) + idx.tobytes()
+    return b
+
+
+def ref_search_by_bow(KF, F, nnratio=0.7, check_ori=True, kf_bad=None):
+    """The reference's ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) executed (op 9) on the mirror's dict layout
+    (hvo.ORBmatcher.SearchByBoW).  Returns (nmatches, match [M]) or None."""
+    k0 = np.ascontiguousarray(KF['keys_un'], KP_DTYPE); k1 = np.ascontiguousarray(F['keys'], KP_DTYPE)
+    n0 = len(k0)
+    bad = np.zeros(n0, np.uint8) if kf_bad is None else np.asarray(kf_bad, np.uint8)
+    b = struct.pack('<2i', 0x4d544348, 9) + _f32([0, 0, 640, 480])
+    b += struct.pack('<i', n0) + k0.tobytes() + np.ascontiguousarray(KF['desc'], np.uint8).tobytes() + np.asarray(KF['has_mappoint'], np.uint8).tobytes() + bad.tobytes()
+    b += _featvec_bytes(KF['featvec'])
+    b += struct.pack('<i', len(k1)) + k1.tobytes() + np.ascontiguousarray(F['desc'], np.uint8).tobytes() + _featvec_bytes(F['featvec'])
+    b += struct.pack('<fi', float(nnratio), int(check_ori))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, len(k1), 4).copy()
+
+
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)
     h, w = d.shape

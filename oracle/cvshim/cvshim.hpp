@@ -524,6 +524,13 @@ static inline double norm(const Mat& a) {
     for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += (double)a.at<float>(i, j) * (double)a.at<float>(i, j);
     return std::sqrt(s);
 }
+static inline double norm(const Mat& a, const Mat& b, int normType) {   // NORM_HAMMING on CV_8U rows (MapLine::ComputeDistinctiveDescriptors)
+    assert(normType == NORM_HAMMING && a.type() == CV_8UC1 && b.type() == CV_8UC1 && a.rows * a.cols == b.rows * b.cols);
+    (void)normType;
+    int d = 0;
+    for (int i = 0; i < a.rows * a.cols; ++i) d += __builtin_popcount((unsigned)(a.at<uchar>(i) ^ b.at<uchar>(i)));
+    return (double)d;
+}
 static inline double cvshim_dot32f(const Mat& a, const Mat& b) {
     assert(a.rows * a.cols == b.rows * b.cols);
     double r = 0;

@@ -55,6 +55,11 @@ RANGES = {
                   ('src/MapLine.cpp', 537, 558, 'float MapLine::GetMinDistanceInvariance()')],
     # ORBmatcher::SearchForInitialization (whole, with its rotation histogram)
     'orb_init': [('src/ORBmatcher.cc', 412, 529, 'int ORBmatcher::SearchForInitialization(')],
+    # ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
+    'orb_bow': [('src/ORBmatcher.cc', 162, 293, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F')],
+    # MapPoint::ComputeDistinctiveDescriptors, MapLine::ComputeDistinctiveDescriptors
+    'distinctive': [('src/MapPoint.cc', 240, 305, 'void MapPoint::ComputeDistinctiveDescriptors()'),
+                    ('src/MapLine.cpp', 331, 396, 'void MapLine::ComputeDistinctiveDescriptors()')],
     # sort_descriptor_by_queryIdx; LSDmatcher::FrameBFMatchNew + mutualOverlap
     'lsd_bfnew': [('include/auxiliar.h', 40, 45, 'struct sort_descriptor_by_queryIdx'),
                   ('src/LSDmatcher.cpp', 968, 1108, 'void LSDmatcher::FrameBFMatchNew(')],

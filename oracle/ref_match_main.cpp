@@ -8,6 +8,9 @@
 //   src/MapPoint.cc:371-381, 400-415; src/MapLine.cpp:537-558  Get{Min,Max}DistanceInvariance, PredictScale
 //   src/ORBmatcher.cc:412-529                                SearchForInitialization, whole
 //   include/auxiliar.h:40-45, src/LSDmatcher.cpp:968-1108    sort_descriptor_by_queryIdx, FrameBFMatchNew, mutualOverlap
+//   src/ORBmatcher.cc:162-293                                SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), whole (with Thirdparty/DBoW2's
+//                                                            own FeatureVector, FeatureVector.cpp compiled unmodified)
+//   src/MapPoint.cc:240-305, src/MapLine.cpp:331-396         ComputeDistinctiveDescriptors x2
 //   src/lineIterator.cpp                                     whole file, unmodified
 // and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
 // (declared below with the reference header line each one mirrors) plus the OpenCV / Eigen stand-ins.
@@ -19,8 +22,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <list>
+#include <map>
 #include <mutex>
 #include <set>
 #include <unordered_set>
@@ -29,6 +34,7 @@
 // REF_MATCH_USE_SHIM (tests/cpp/shim_match_main.cpp): the same driver and stand-in types, but ORBmatcher / LSDmatcher are the drop-in
 // class templates of shim/ORBmatcher.h / shim/LSDmatcher.h (C ABI -> CUDA) instead of the reference's functions; nothing of the
 // reference is compiled, the grid / candidate-list dumps are skipped (the drop-in builds its grids on the device).
+#include "DBoW2/FeatureVector.h"   // Thirdparty/DBoW2 (header + FeatureVector.cpp, unmodified): std::map<NodeId, std::vector<unsigned int>>
 #ifdef REF_MATCH_USE_SHIM
 #include "keyline_standin.hpp"
 #include <Eigen/Core>
@@ -65,6 +71,11 @@ public:
         nobs = o.nobs; bad = o.bad; id = o.id; mfMinDistance = o.mfMinDistance; mfMaxDistance = o.mfMaxDistance;
         return *this;
     }
+    void ComputeDistinctiveDescriptors();
+    std::map<KeyFrame*, size_t> mObservations;      // include/MapPoint.h:129-155
+    cv::Mat mDescriptor;
+    bool mbBad = false;
+    std::mutex mMutexFeatures;
     cv::Mat normal;
     float mfMinDistance = 0.f, mfMaxDistance = 0.f;
     std::mutex mMutexPos;
@@ -94,8 +105,14 @@ public:
         mTrackProjX1 = o.mTrackProjX1; mTrackProjY1 = o.mTrackProjY1; mTrackProjX2 = o.mTrackProjX2; mTrackProjY2 = o.mTrackProjY2;
         mnTrackScaleLevel = o.mnTrackScaleLevel; mTrackViewCos = o.mTrackViewCos; mbTrackInView = o.mbTrackInView; wpos = o.wpos; wvec = o.wvec;
         wnormal = o.wnormal; desc = o.desc; nobs = o.nobs; bad = o.bad; id = o.id; mfMinDistance = o.mfMinDistance; mfMaxDistance = o.mfMaxDistance;
+        mObservations = o.mObservations; mLDescriptor = o.mLDescriptor; mbBad = o.mbBad;
         return *this;
     }
+    void ComputeDistinctiveDescriptors();
+    std::map<KeyFrame*, size_t> mObservations;      // include/MapLine.h:138-162
+    Mat mLDescriptor;
+    bool mbBad = false;
+    std::mutex mMutexFeatures;
     Vector3d wnormal;
     float mfMinDistance = 0.f, mfMaxDistance = 0.f;
     std::mutex mMutexPos;
@@ -113,6 +130,16 @@ public:
     bool bad = false;
     int id = -1;
 };
+class KeyFrame {                          // include/KeyFrame.h: the members SearchByBoW / ComputeDistinctiveDescriptors touch
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    bool isBad() { return bad; }
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors, mLineDescriptors;
+    std::vector<MapPoint*> mvpMapPoints;
+    bool bad = false;
+};
 class Frame {                             // include/Frame.h:129-131, 224-353
 public:
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
@@ -124,6 +151,7 @@ public:
     bool isInFrustum(MapLine* pML, float) { return pML->mbTrackInView; }
     bool isInFrustumRef(MapPoint* pMP, float viewingCosLimit);   // = the reference's isInFrustum, see the include below
     bool isInFrustumRef(MapLine* pML, float viewingCosLimit);
+    DBoW2::FeatureVector mFeatVec;           // include/Frame.h:268
     cv::Mat mRcw, mtcw, mOw;                 // include/Frame.h:408-411
     int mnScaleLevels = 8;                   // :330-332
     float mfLogScaleFactor = 0.f;
@@ -158,6 +186,7 @@ public:
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     float RadiusByViewingCos(const float& viewCos);
@@ -184,6 +213,7 @@ protected:
 #include "gen/frame_grid.inc"
 #include "gen/orbmatcher.inc"
 #include "gen/orb_init.inc"
+#include "gen/orb_bow.inc"
 #define isInFrustum isInFrustumRef
 #include "gen/frame_frustum.inc"
 #undef isInFrustum
@@ -192,6 +222,7 @@ protected:
 namespace ORB_SLAM2 {
 #include "gen/lsdmatcher.inc"
 #include "gen/lsd_bfnew.inc"
+#include "gen/distinctive.inc"
 }  // namespace ORB_SLAM2
 #else
 }  // namespace ORB_SLAM2
@@ -465,6 +496,68 @@ int main(int argc, char** argv) {
         LSDmatcher matcher(nnratio, true);
         matcher.FrameBFMatchNew(d1, d2, lm, k1, k2, f2, Fm, TH);
         for (int i = 0; i < n1; ++i) put<int32_t>(lm[i]);
+    } else if (op == 8) {   // MapPoint / MapLine::ComputeDistinctiveDescriptors over a batch of map elements
+        const int lines = get<int32_t>(), ngroups = get<int32_t>();
+        std::vector<int32_t> off(ngroups + 1); get_n(off.data(), ngroups + 1);
+        const int total = off[ngroups];
+        std::vector<KeyFrame> kfs(total > 0 ? total : 1);   // one key frame per observation, ascending addresses = std::map order
+        for (int i = 0; i < total; ++i) {
+            cv::Mat d = get_desc_rows(1);
+            kfs[i].mDescriptors = d; kfs[i].mLineDescriptors = d;
+        }
+#ifndef REF_MATCH_USE_SHIM
+        for (int g = 0; g < ngroups; ++g) {
+            cv::Mat best;
+            if (lines) {
+                MapLine m;
+                for (int i = off[g]; i < off[g + 1]; ++i) m.mObservations[&kfs[i]] = 0;
+                m.ComputeDistinctiveDescriptors();
+                best = m.mLDescriptor;
+            } else {
+                MapPoint m;
+                for (int i = off[g]; i < off[g + 1]; ++i) m.mObservations[&kfs[i]] = 0;
+                m.ComputeDistinctiveDescriptors();
+                best = m.mDescriptor;
+            }
+            int idx = -1;    // which observation's descriptor was kept (first identical row)
+            if (!best.empty())
+                for (int i = off[g]; i < off[g + 1] && idx < 0; ++i) if (std::memcmp(best.data, kfs[i].mDescriptors.data, 32) == 0) idx = i - off[g];
+            put<int32_t>(idx);
+            uint8_t zero[32] = {0};
+            std::fwrite(best.empty() ? zero : best.data, 1, 32, g_out);
+        }
+#else
+        return 6;   // the drop-in for this call is hvo_match_distinctive (C ABI), exercised from Python
+#endif
+    } else if (op == 9) {   // ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches)
+        KeyFrame KF; Frame F;
+        const int n1 = get<int32_t>();
+        KF.mvKeysUn.resize(n1); get_n(KF.mvKeysUn.data(), n1);
+        KF.mDescriptors = get_desc_rows(n1);
+        std::vector<uint8_t> has(n1), bad(n1); get_n(has.data(), n1); get_n(bad.data(), n1);
+        std::vector<MapPoint> mps(n1);
+        KF.mvpMapPoints.assign(n1, nullptr);
+        for (int i = 0; i < n1; ++i) { mps[i].id = i; mps[i].bad = bad[i] != 0; if (has[i]) KF.mvpMapPoints[i] = &mps[i]; }
+        auto read_fv = [&](DBoW2::FeatureVector& fv) {
+            const int nn = get<int32_t>();
+            for (int k = 0; k < nn; ++k) {
+                const int node = get<int32_t>(), cnt = get<int32_t>();
+                for (int j = 0; j < cnt; ++j) fv.addFeature((DBoW2::NodeId)node, (unsigned int)get<int32_t>());
+            }
+        };
+        read_fv(KF.mFeatVec);
+        F.N = get<int32_t>();
+        F.mvKeys.resize(F.N); get_n(F.mvKeys.data(), F.N);
+        F.mvKeysUn = F.mvKeys;
+        F.mDescriptors = get_desc_rows(F.N);
+        read_fv(F.mFeatVec);
+        const float nnratio = get<float>();
+        const int check_ori = get<int32_t>();
+        std::vector<MapPoint*> matches;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int nm = matcher.SearchByBoW(&KF, F, matches);
+        put<int32_t>(nm);
+        for (int i = 0; i < F.N; ++i) put<int32_t>(matches[i] ? matches[i]->id : -1);
     } else {
         return 5;
     }

@@ -189,5 +189,9 @@ def test_dropin_matcher_classes_equal_executed_reference(hvo, synth):
         for seed, TH, ratio in ((0, 50.0, 0.95), (1, 80.0, 0.8)):
             kl1, ld1, kl2, ld2, lv2, F = tt._line_scene(synth, seed)
             tt._ref(f'epi{seed}', lambda: oracle.ref_lines_epipolar(ld1, kl1, ld2, kl2, lv2, F, TH, ratio))
+        from test_projection import _bow_scenario
+        for seed, ratio, ori in ((0, 0.7, True), (1, 0.9, True), (2, 0.75, False)):
+            KF, F = _bow_scenario(synth, seed)
+            tt._ref(f'bow{seed}', lambda: oracle.ref_search_by_bow(KF, F, ratio, ori))
     finally:
         oracle.MATCH_EXE[0] = None

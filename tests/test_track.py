@@ -195,6 +195,40 @@ def test_oracle_lines_epipolar_equals_reference(synth):
     assert total > 5
 
 
+def test_oracle_distinctive_equals_reference(synth):
+    """MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:240-305, src/MapLine.cpp:331-396) executed: the kept descriptor and,
+    where it is unique inside the element, its index."""
+    from test_match import _distinctive_groups
+    desc, off = _distinctive_groups(synth, ngroups=200)
+    for lines in (False, True):
+        ri, rd = _ref(f'dist{int(lines)}', lambda: oracle.ref_distinctive(desc, off, lines))
+        bi, bm = oracle.distinctive(desc, off)
+        for g in range(len(off) - 1):
+            if off[g + 1] == off[g]:
+                assert bi[g] == -1 and ri[g] == -1
+            else:
+                assert np.array_equal(desc[off[g] + bi[g]], rd[g]), g
+                assert ri[g] == bi[g] or np.array_equal(desc[off[g] + ri[g]], desc[off[g] + bi[g]])   # duplicates: the first identical row
+
+
+def test_oracle_search_by_bow_equals_reference(hvo, synth):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:162-293) executed with Thirdparty/DBoW2's own FeatureVector: the
+    mirror (query order, rotation histogram) on top of the oracle's candidate search must give the reference's matches."""
+    from test_projection import _bow_scenario
+    import test_ref_match as trm
+
+    class OraclePMc(trm.OraclePM):
+        def search_candidates(self, q, t, off, cand, th, ratio):
+            return oracle.search_candidates(q, t, off, cand, th, ratio)
+    for seed, ratio, ori in ((0, 0.7, True), (1, 0.9, True), (2, 0.75, False)):
+        KF, F = _bow_scenario(synth, seed)
+        nm_r, match_r = _ref(f'bow{seed}', lambda: oracle.ref_search_by_bow(KF, F, ratio, ori))
+        m = hvo.ORBmatcher.__new__(hvo.ORBmatcher)
+        m.mfNNratio, m.mbCheckOrientation, m._pm = float(ratio), bool(ori), OraclePMc()
+        nm, match = m.SearchByBoW(KF, F)
+        assert nm == int(nm_r) and np.array_equal(match, match_r) and nm > 50
+
+
 def test_predict_scale_thresholds_reproduce_logf(hvo):
     """level(ratio) from the thresholds == ceil(logf(ratio) / L) of the host libm for random ratios and for both float neighbours of
     every threshold (the boundaries), clamped (points) and unclamped (lines)."""
@@ -375,3 +409,24 @@ def test_gpu_search_local_lines_equals_two_step_reference_path(hvo, synth):
                     bad=np.zeros(M, bool), has_obs=has_obs, desc=ldesc, world_vector=ml['dir'])
         nm_o, match_o = trm._lsd_matcher(hvo, False, 0.95).SearchByProjection(F2, MLs2, True, th)
         assert nm == nm_o and np.array_equal(match, match_o) and np.array_equal(F['mapline'], F2['mapline'])
+
+
+@pytest.mark.gpu
+def test_gpu_distinctive_and_search_by_bow_equal_reference(hvo, synth):
+    from test_match import _distinctive_groups
+    from test_projection import _bow_scenario
+    desc, off = _distinctive_groups(synth, ngroups=200)
+    bf = hvo.BFMatcherHamming()
+    bi, bm = bf.distinctive(desc, off)
+    for lines in (False, True):
+        ri, rd = _ref(f'dist{int(lines)}', lambda: oracle.ref_distinctive(desc, off, lines))
+        for g in range(len(off) - 1):
+            if off[g + 1] == off[g]:
+                assert bi[g] == -1
+            else:
+                assert np.array_equal(desc[off[g] + bi[g]], rd[g]), g
+    for seed, ratio, ori in ((0, 0.7, True), (1, 0.9, True), (2, 0.75, False)):
+        KF, F = _bow_scenario(synth, seed)
+        nm_r, match_r = _ref(f'bow{seed}', lambda: oracle.ref_search_by_bow(KF, F, ratio, ori))
+        nm, match = hvo.ORBmatcher(ratio, ori).SearchByBoW(KF, F)
+        assert nm == int(nm_r) and np.array_equal(match, match_r)
