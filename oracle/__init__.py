@@ -966,6 +966,44 @@ def ref_search_by_bow(KF, F, nnratio=0.7, check_ori=True, kf_bad=None):
     return nm, np.frombuffer(raw, np.int32, len(k1), 4).copy()
 
 
+
+def ref_search_for_triangulation(KF1, KF2, F12, Cw1, R2w, t2w, cam2, only_stereo=False, check_ori=True, nnratio=0.6):
+    """The reference's ORBmatcher::SearchForTriangulation executed (op 10) on the mirror's dict layout.  Cw1 = pKF1->GetCameraCenter(),
+    R2w / t2w = pKF2's pose, cam2 = (fx, fy, cx, cy) of pKF2.  Returns (nmatches, pairs [n, 2]) or None."""
+    def kf(K):
+        k = np.ascontiguousarray(K['keys_un'], KP_DTYPE)
+        return (struct.pack('<i', len(k)) + k.tobytes() + _f32(K['uright']) + np.ascontiguousarray(K['desc'], np.uint8).tobytes()
+                + np.asarray(K['has_mappoint'], np.uint8).tobytes() + _featvec_bytes(K['featvec']))
+    sf = np.zeros(8, np.float32); sf[:len(KF2['scale_factors'])] = KF2['scale_factors']
+    sg = np.zeros(8, np.float32); sg[:len(KF2['level_sigma2'])] = KF2['level_sigma2']
+    b = struct.pack('<2i', 0x4d544348, 10) + _f32([0, 0, 640, 480]) + kf(KF1) + _f32(Cw1) + kf(KF2) + _f32(R2w) + _f32(t2w) + _f32(cam2)
+    b += sf.tobytes() + sg.tobytes() + _f32(F12) + struct.pack('<2if', int(only_stereo), int(check_ori), float(nnratio))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    nm, npairs = struct.unpack_from('<2i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, 2 * npairs, 8).reshape(npairs, 2).copy()
+
+
+
+def ref_fuse(KF, kf_obs, cam5, Rcw, tcw, Ow, inv_sigma2, log_scale_factor, n_levels, th, pts, pdesc, present, bad, nobs, in_kf):
+    """The reference's ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) executed (op 11).  KF = point-frame dict (keys_un, uright, desc, bounds,
+    scale_factors, claimed = the keypoint holds a map point); kf_obs = Observations() of those map points; pts MAP_POINT_DTYPE.
+    Returns (nFused, events [n, 3] = (map point, key-frame keypoint, action)) or None."""
+    pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+    M = len(pts)
+    b = struct.pack('<2i', 0x4d544348, 11) + _f32(KF['bounds']) + _point_frame_bytes(KF) + np.asarray(kf_obs, np.uint8).tobytes()
+    b += _f32(cam5) + _f32(Rcw) + _f32(tcw) + _f32(Ow) + _f32(inv_sigma2) + struct.pack('<fifi', float(log_scale_factor), int(n_levels), float(th), M)
+    pd = np.ascontiguousarray(pdesc, np.uint8).reshape(-1, 32)
+    for i in range(M):
+        b += pts[i].tobytes() + pd[i].tobytes() + struct.pack('<4B', int(present[i]), int(bad[i]), int(nobs[i]), int(in_kf[i]))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    nf, ne = struct.unpack_from('<2i', raw, 0)
+    return nf, np.frombuffer(raw, np.int32, 3 * ne, 8).reshape(ne, 3).copy()
+
+
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)
     h, w = d.shape

@@ -57,6 +57,14 @@ RANGES = {
     'orb_init': [('src/ORBmatcher.cc', 412, 529, 'int ORBmatcher::SearchForInitialization(')],
     # ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
     'orb_bow': [('src/ORBmatcher.cc', 162, 293, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F')],
+    # ORBmatcher::CheckDistEpipolarLine, SearchForTriangulation
+    'orb_tri': [('src/ORBmatcher.cc', 143, 160, 'bool ORBmatcher::CheckDistEpipolarLine('),
+                ('src/ORBmatcher.cc', 668, 836, 'int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2')],
+    # ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th); KeyFrame::GetFeaturesInArea, IsInImage; MapPoint::PredictScale(dist, KeyFrame*)
+    'orb_fuse': [('src/ORBmatcher.cc', 838, 994, 'int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)')],
+    'keyframe_area': [('src/KeyFrame.cc', 627, 666, 'vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const'),
+                      ('src/KeyFrame.cc', 780, 783, 'bool KeyFrame::IsInImage(')],
+    'mappoint_scale_kf': [('src/MapPoint.cc', 383, 398, 'int MapPoint::PredictScale(const float &currentDist, KeyFrame *pKF)')],
     # MapPoint::ComputeDistinctiveDescriptors, MapLine::ComputeDistinctiveDescriptors
     'distinctive': [('src/MapPoint.cc', 240, 305, 'void MapPoint::ComputeDistinctiveDescriptors()'),
                     ('src/MapLine.cpp', 331, 396, 'void MapLine::ComputeDistinctiveDescriptors()')],

@@ -10,6 +10,9 @@
 //   include/auxiliar.h:40-45, src/LSDmatcher.cpp:968-1108    sort_descriptor_by_queryIdx, FrameBFMatchNew, mutualOverlap
 //   src/ORBmatcher.cc:162-293                                SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), whole (with Thirdparty/DBoW2's
 //                                                            own FeatureVector, FeatureVector.cpp compiled unmodified)
+//   src/ORBmatcher.cc:143-160, 668-836                       CheckDistEpipolarLine, SearchForTriangulation, whole
+//   src/ORBmatcher.cc:838-994                                Fuse(KeyFrame*, vpMapPoints, th), whole; src/KeyFrame.cc:627-666, 780-783
+//                                                            GetFeaturesInArea, IsInImage; src/MapPoint.cc:383-398 PredictScale(dist, KeyFrame*)
 //   src/MapPoint.cc:240-305, src/MapLine.cpp:331-396         ComputeDistinctiveDescriptors x2
 //   src/lineIterator.cpp                                     whole file, unmodified
 // and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
@@ -72,6 +75,11 @@ public:
         return *this;
     }
     void ComputeDistinctiveDescriptors();
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+    // bookkeeping stand-ins: what Fuse decides is logged as (map point id, key-frame keypoint or -1, action)
+    void Replace(MapPoint* pMP);
+    void AddObservation(KeyFrame* pKF, size_t idx);
     std::map<KeyFrame*, size_t> mObservations;      // include/MapPoint.h:129-155
     cv::Mat mDescriptor;
     bool mbBad = false;
@@ -133,7 +141,23 @@ public:
 class KeyFrame {                          // include/KeyFrame.h: the members SearchByBoW / ComputeDistinctiveDescriptors touch
 public:
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
     bool isBad() { return bad; }
+    bool IsInImage(const float& x, const float& y) const;
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+    int N = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+    std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+    int mnScaleLevels = 8;
+    float mfLogScaleFactor = 0.f;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;   // include/KeyFrame.h:172-175, 249-252 (ints)
+    float mfGridElementWidthInv = 0.f, mfGridElementHeightInv = 0.f;
+    std::vector<std::vector<std::vector<size_t>>> mGrid;
+    cv::Mat Ow, Rcw, tcw;
     DBoW2::FeatureVector mFeatVec;
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mDescriptors, mLineDescriptors;
@@ -187,8 +211,11 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo);
+    int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
+    bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF);
     float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     float mfNNratio;
@@ -214,6 +241,29 @@ protected:
 #include "gen/orbmatcher.inc"
 #include "gen/orb_init.inc"
 #include "gen/orb_bow.inc"
+#include "gen/orb_tri.inc"
+#include "gen/orb_fuse.inc"
+#include "gen/keyframe_area.inc"
+#include "gen/mappoint_scale_kf.inc"
+struct FuseEvent { int32_t mp, idx, action; };   // action 0: AddObservation + AddMapPoint, 1: pMP->Replace(pMPinKF), 2: pMPinKF->Replace(pMP)
+static std::vector<FuseEvent> g_fuse_log;
+static KeyFrame* g_fuse_kf = nullptr;
+void MapPoint::AddObservation(KeyFrame*, size_t idx) { g_fuse_log.push_back(FuseEvent{id, (int32_t)idx, 0}); nobs++; }
+void MapPoint::Replace(MapPoint* pMP) {
+    // `this` is replaced by pMP.  One of the two sits in a slot of the key frame (pMPinKF), the other is the incoming map point.
+    int32_t idx = -1;
+    bool this_in_kf = false;
+    for (size_t i = 0; i < g_fuse_kf->mvpMapPoints.size() && idx < 0; ++i) {
+        if (g_fuse_kf->mvpMapPoints[i] == this) { idx = (int32_t)i; this_in_kf = true; }
+        else if (g_fuse_kf->mvpMapPoints[i] == pMP) idx = (int32_t)i;
+    }
+    if (this_in_kf) {   // pMPinKF->Replace(pMP): the incoming point takes the slot (MapPoint::Replace re-points the key frame, src/MapPoint.cc:185-238)
+        g_fuse_log.push_back(FuseEvent{pMP->id, idx, 2});
+        g_fuse_kf->mvpMapPoints[idx] = pMP;
+    } else {            // pMP->Replace(pMPinKF): the incoming point dissolves into the one the key frame holds
+        g_fuse_log.push_back(FuseEvent{id, idx, 1});
+    }
+}
 #define isInFrustum isInFrustumRef
 #include "gen/frame_frustum.inc"
 #undef isInFrustum
@@ -558,6 +608,92 @@ int main(int argc, char** argv) {
         const int nm = matcher.SearchByBoW(&KF, F, matches);
         put<int32_t>(nm);
         for (int i = 0; i < F.N; ++i) put<int32_t>(matches[i] ? matches[i]->id : -1);
+    } else if (op == 10) {   // ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
+#ifndef REF_MATCH_USE_SHIM
+        KeyFrame K1, K2;
+        std::vector<MapPoint> pool1, pool2;
+        auto read_kf = [&](KeyFrame& K, std::vector<MapPoint>& pool) {
+            K.N = get<int32_t>();
+            K.mvKeysUn.resize(K.N); get_n(K.mvKeysUn.data(), K.N);
+            K.mvuRight.resize(K.N); get_n(K.mvuRight.data(), K.N);
+            K.mDescriptors = get_desc_rows(K.N);
+            std::vector<uint8_t> has(K.N); get_n(has.data(), K.N);
+            pool.resize(K.N);
+            K.mvpMapPoints.assign(K.N, nullptr);
+            for (int i = 0; i < K.N; ++i) if (has[i]) K.mvpMapPoints[i] = &pool[i];
+            const int nn = get<int32_t>();
+            for (int k = 0; k < nn; ++k) {
+                const int node = get<int32_t>(), cnt = get<int32_t>();
+                for (int j = 0; j < cnt; ++j) K.mFeatVec.addFeature((DBoW2::NodeId)node, (unsigned int)get<int32_t>());
+            }
+        };
+        read_kf(K1, pool1);
+        K1.Ow = cv::Mat(3, 1, CV_32FC1); get_n((float*)K1.Ow.data, 3);
+        read_kf(K2, pool2);
+        K2.Rcw = cv::Mat(3, 3, CV_32FC1); get_n((float*)K2.Rcw.data, 9);
+        K2.tcw = cv::Mat(3, 1, CV_32FC1); get_n((float*)K2.tcw.data, 3);
+        float cam[4]; get_n(cam, 4);
+        K2.fx = cam[0]; K2.fy = cam[1]; K2.cx = cam[2]; K2.cy = cam[3];
+        K2.mvScaleFactors.resize(8); get_n(K2.mvScaleFactors.data(), 8);
+        K2.mvLevelSigma2.resize(8); get_n(K2.mvLevelSigma2.data(), 8);
+        cv::Mat F12(3, 3, CV_32FC1); get_n((float*)F12.data, 9);
+        const int only_stereo = get<int32_t>(), check_ori = get<int32_t>();
+        const float nnratio = get<float>();
+        std::vector<pair<size_t, size_t>> pairs;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int nm = matcher.SearchForTriangulation(&K1, &K2, F12, pairs, only_stereo != 0);
+        put<int32_t>(nm);
+        put<int32_t>((int32_t)pairs.size());
+        for (const auto& pr : pairs) { put<int32_t>((int32_t)pr.first); put<int32_t>((int32_t)pr.second); }
+#else
+        return 6;   // reached through hvo_proj_search_triangulation (PointWindowMatcher), exercised from Python
+#endif
+    } else if (op == 11) {   // ORBmatcher::Fuse(pKF, vpMapPoints, th)
+#ifndef REF_MATCH_USE_SHIM
+        Frame F; std::vector<MapPoint> pool;
+        read_point_frame(F, pool);               // key frame's features through the Frame reader (grid included); claimed = holds a map point
+        KeyFrame K;
+        K.N = F.N; K.mvKeysUn = F.mvKeysUn; K.mvuRight = F.mvuRight; K.mDescriptors = F.mDescriptors; K.mvScaleFactors = F.mvScaleFactors;
+        std::vector<uint8_t> kfobs(K.N); get_n(kfobs.data(), K.N);      // Observations() of the map point a keypoint holds
+        std::vector<MapPoint> held(K.N);
+        K.mvpMapPoints.assign(K.N, nullptr);
+        for (int i = 0; i < K.N; ++i) if (F.mvpMapPoints[i]) { held[i].id = -100 - i; held[i].nobs = kfobs[i]; K.mvpMapPoints[i] = &held[i]; }
+        K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+        for (int ix = 0; ix < FRAME_GRID_COLS; ++ix) for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) K.mGrid[ix][iy] = F.mGrid[ix][iy];   // KeyFrame ctor: mGrid = F.mGrid
+        K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+        K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+        float cam[5]; get_n(cam, 5);
+        K.fx = cam[0]; K.fy = cam[1]; K.cx = cam[2]; K.cy = cam[3]; K.mbf = cam[4];
+        K.Rcw = cv::Mat(3, 3, CV_32FC1); get_n((float*)K.Rcw.data, 9);
+        K.tcw = cv::Mat(3, 1, CV_32FC1); get_n((float*)K.tcw.data, 3);
+        K.Ow = cv::Mat(3, 1, CV_32FC1); get_n((float*)K.Ow.data, 3);
+        K.mvInvLevelSigma2.resize(8); get_n(K.mvInvLevelSigma2.data(), 8);
+        K.mfLogScaleFactor = get<float>(); K.mnScaleLevels = get<int32_t>();
+        const float th = get<float>();
+        const int M = get<int32_t>();
+        std::vector<MapPoint> mps(M);
+        std::vector<MapPoint*> vp(M, nullptr);
+        for (int i = 0; i < M; ++i) {
+            MapPoint& m = mps[i];
+            m.pos = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.pos.data, 3);
+            m.normal = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.normal.data, 3);
+            m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
+            m.desc = get_desc_rows(1);
+            const int present = get<uint8_t>(); m.bad = get<uint8_t>() != 0; m.nobs = get<uint8_t>(); const int inkf = get<uint8_t>();
+            m.id = i;
+            if (inkf) m.mObservations[&K] = 0;
+            if (present) vp[i] = &m;
+        }
+        g_fuse_kf = &K;
+        g_fuse_log.clear();
+        ORBmatcher matcher(0.6f, true);
+        const int nf = matcher.Fuse(&K, vp, th);
+        put<int32_t>(nf);
+        put<int32_t>((int32_t)g_fuse_log.size());
+        for (const FuseEvent& e : g_fuse_log) { put<int32_t>(e.mp); put<int32_t>(e.idx); put<int32_t>(e.action); }
+#else
+        return 6;   // reached through hvo_proj_search mode 2 (PointWindowMatcher), exercised from Python
+#endif
     } else {
         return 5;
     }

@@ -215,6 +215,8 @@ def track():
     t.test_oracle_lines_epipolar_equals_reference(synth)
     t.test_oracle_distinctive_equals_reference(synth)
     t.test_oracle_search_by_bow_equals_reference(hvo_b200, synth)
+    t.test_oracle_search_for_triangulation_equals_reference(hvo_b200, synth)
+    t.test_oracle_fuse_equals_reference(hvo_b200, synth)
     np.savez_compressed(os.path.join(OUT, 'track_ref.npz'), **t.RECORD)
     print('track_ref.npz written:', len(t.RECORD), 'arrays')
 

@@ -229,6 +229,148 @@ def test_oracle_search_by_bow_equals_reference(hvo, synth):
         assert nm == int(nm_r) and np.array_equal(match, match_r) and nm > 50
 
 
+def _tri_scene(synth, seed):
+    from test_projection import _bow_scenario, _fundamental
+    KFa, Fb = _bow_scenario(synth, seed=2)
+    rng = np.random.RandomState(12 + seed)
+    k1, k2 = KFa['keys_un'], Fb['keys']
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32); sg = (sf * sf).astype(np.float32)
+    ur1 = np.where(rng.rand(len(k1)) < 0.6, k1['x'] - 20, -1).astype(np.float32)
+    ur2 = np.where(rng.rand(len(k2)) < 0.6, k2['x'] - 20, -1).astype(np.float32)
+    KF1 = dict(desc=KFa['desc'], keys_un=k1, uright=ur1, featvec=KFa['featvec'], has_mappoint=rng.rand(len(k1)) < 0.4, scale_factors=sf, level_sigma2=sg)
+    KF2 = dict(desc=Fb['desc'], keys_un=k2, uright=ur2, featvec=Fb['featvec'], has_mappoint=rng.rand(len(k2)) < 0.3, scale_factors=sf, level_sigma2=sg)
+    F12 = np.asarray(_fundamental(0.004, 0.0005), np.float32)
+    cam2 = np.float32([535.4, 539.2, 320.1, 247.6])
+    # pKF1's camera centre seen from pKF2 (R2w = I): far to the side (epipole outside the image) or in front (epipole inside)
+    Cw1 = np.float32([[-3.0, 0.01, 0.02], [0.02, -0.01, 1.0]][seed % 2])
+    t2w = np.zeros(3, np.float32)
+    C2 = (Cw1 + t2w).astype(np.float32)                       # R2w * Cw + t2w with R2w = I (cv::gemm: exact products, float sums)
+    invz = np.float32(1.0) / C2[2]
+    ex = np.float32(np.float32(np.float32(cam2[0] * C2[0]) * invz) + cam2[2]); ey = np.float32(np.float32(np.float32(cam2[1] * C2[1]) * invz) + cam2[3])
+    return KF1, KF2, F12, Cw1, np.eye(3, dtype=np.float32), t2w, cam2, (ex, ey)
+
+
+def _check_triangulation(hvo, synth, gpu):
+    import test_ref_match as trm
+
+    class OraclePMt(trm.OraclePM):
+        def search_triangulation(self, *a):
+            return oracle.search_triangulation(*a)
+    total = 0
+    for seed, only_stereo, ori in ((0, False, True), (1, False, True), (2, True, False)):
+        KF1, KF2, F12, Cw1, R2w, t2w, cam2, epi = _tri_scene(synth, seed)
+        nm_r, pairs_r = _ref(f'tri{seed}', lambda: oracle.ref_search_for_triangulation(KF1, KF2, F12, Cw1, R2w, t2w, cam2, only_stereo, ori, 0.6))
+        if gpu:
+            m = hvo.ORBmatcher(0.6, ori)
+        else:
+            m = hvo.ORBmatcher.__new__(hvo.ORBmatcher)
+            m.mfNNratio, m.mbCheckOrientation, m._pm = 0.6, bool(ori), OraclePMt()
+        nm, pairs = m.SearchForTriangulation(KF1, KF2, F12, epi, only_stereo)
+        assert nm == int(nm_r) and np.array_equal(pairs, np.asarray(pairs_r).reshape(-1, 2))
+        total += nm
+    assert total > 20
+
+
+def test_oracle_search_for_triangulation_equals_reference(hvo, synth):
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:668-836) + CheckDistEpipolarLine (:143-160) executed."""
+    _check_triangulation(hvo, synth, gpu=False)
+
+
+def _fuse_project(cam, pts, n_levels=8):
+    """The projection tests of ORBmatcher::Fuse (src/ORBmatcher.cc:866-900) with the reference's float rules (cv::gemm float sums, cv::norm /
+    Mat::dot in double); PredictScale(dist, pKF) through the library's logf thresholds.  Returns (ok, u, v, ur, level)."""
+    import hvo_b200
+    f32 = np.float32
+    R = cam['Rcw'].reshape(3, 3); t = cam['tcw']; O = cam['Ow']
+    P = pts['pos']
+    Pc = np.zeros((len(P), 3), f32)
+    for i in range(3):
+        acc = np.zeros(len(P), f32)
+        for k in range(3):
+            acc = (acc + (R[i, k] * P[:, k]).astype(f32)).astype(f32)
+        Pc[:, i] = (acc + t[i]).astype(f32)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        invz = (f32(1) / Pc[:, 2]).astype(f32)
+        x = (Pc[:, 0] * invz).astype(f32); y = (Pc[:, 1] * invz).astype(f32)
+        u = ((cam['fx'] * x).astype(f32) + cam['cx']).astype(f32); v = ((cam['fy'] * y).astype(f32) + cam['cy']).astype(f32)
+        ur = (u - (cam['bf'] * invz).astype(f32)).astype(f32)
+        ok = ~(Pc[:, 2] < 0) & (u >= cam['min_x']) & (u < cam['max_x']) & (v >= cam['min_y']) & (v < cam['max_y'])
+        PO = (P - O[None, :]).astype(f32)
+        d64 = np.sqrt(PO[:, 0].astype(np.float64) ** 2 + PO[:, 1].astype(np.float64) ** 2 + PO[:, 2].astype(np.float64) ** 2)
+        dist = d64.astype(f32)
+        ok &= ~(dist < (f32(0.8) * pts['min_distance']).astype(f32)) & ~(dist > (f32(1.2) * pts['max_distance']).astype(f32))
+        Pn = pts['normal']
+        dot = (PO[:, 0].astype(np.float64) * Pn[:, 0] + PO[:, 1].astype(np.float64) * Pn[:, 1]) + PO[:, 2].astype(np.float64) * Pn[:, 2]
+        ok &= ~(dot < 0.5 * dist.astype(np.float64))
+        ratio = (pts['max_distance'] / dist).astype(f32)
+    thr = hvo_b200.predict_scale_thresholds(cam['log_scale_factor'], 0, n_levels - 1)
+    level = (ratio[:, None] >= thr[None, :]).sum(1).astype(np.int32)
+    return ok, u, v, ur, level
+
+
+def _check_fuse(hvo, synth, gpu):
+    import test_ref_match as trm
+    from test_ref_match import _point_scene
+
+    class OraclePMf(trm.OraclePM):
+        def set_level_sigma(self, s):
+            self.sig = np.ascontiguousarray(s, np.float32)
+
+        def search(self, q, qd, claimed, mode, th, ratio):
+            assert mode == 2
+            return oracle.search_fuse(self.k, self.ur, self.d, self.b, q, qd, self.sig, th)
+    total = 0
+    for seed, th in ((0, 3.0), (1, 5.0)):
+        rng = np.random.RandomState(80 + seed)
+        F, _, _, _ = _point_scene(synth, seed)            # key frame = the point frame of the projection tests
+        k0, n0 = F['keys_un'], len(F['keys_un'])
+        cam, R, t = _cam(hvo, rng)
+        z = rng.uniform(0.8, 5.0, n0)
+        Pc = np.stack([(k0['x'] + rng.normal(0, 1, n0) - 320.1) * z / 535.4, (k0['y'] + rng.normal(0, 1, n0) - 247.6) * z / 539.2, z], 1)
+        pts = np.concatenate([_point_batch(rng, R, t, n0), _point_batch(rng, R, t, 400)])
+        pts['pos'][:n0] = ((Pc - t.astype(np.float64)) @ R.astype(np.float64)).astype(np.float32)
+        Ow = -(R.astype(np.float64).T @ t.astype(np.float64))
+        view = pts['pos'][:n0].astype(np.float64) - Ow
+        dist = np.linalg.norm(view, axis=1)
+        pts['normal'][:n0] = (view / dist[:, None]).astype(np.float32)
+        pts['max_distance'][:n0] = (dist * SF[np.clip(k0['octave'], 0, 7)]).astype(np.float32)
+        pts['min_distance'][:n0] = pts['max_distance'][:n0] / SF[7]
+        M = len(pts)
+        pdesc = np.concatenate([F['desc'], rng.randint(0, 256, (400, 32)).astype(np.uint8)])
+        flips = rng.randint(0, 256, M)
+        pdesc[np.arange(M), flips // 8] ^= (1 << (flips % 8)).astype(np.uint8)
+        present = rng.rand(M) > 0.05; bad = rng.rand(M) < 0.05; nobs = rng.randint(0, 6, M); in_kf = rng.rand(M) < 0.1
+        kf_obs = rng.randint(0, 6, n0)
+        inv = (np.float32(1.0) / (SF * SF)).astype(np.float32)
+        cam = cam.reshape(())
+        ref = _ref(f'fuse{seed}', lambda: oracle.ref_fuse(F, kf_obs, [cam['fx'], cam['fy'], cam['cx'], cam['cy'], cam['bf']], cam['Rcw'], cam['tcw'], cam['Ow'],
+                                                         inv, cam['log_scale_factor'], 8, th, pts, pdesc, present, bad, nobs, in_kf))
+        nf_r, ev = int(ref[0]), np.asarray(ref[1]).reshape(-1, 3)
+        ok, u, v, ur, level = _fuse_project(cam, pts)
+        use = ok & present & ~bad & ~in_kf
+        sel = np.nonzero(use)[0]
+        KF = dict(keys_un=k0, uright=F['uright'], desc=F['desc'], bounds=BOUNDS, scale_factors=SF, inv_level_sigma2=inv)
+        MPs = dict(u=u[sel], v=v[sel], ur=ur[sel], level=level[sel], desc=pdesc[sel])
+        if gpu:
+            m = hvo.ORBmatcher(0.6, True)
+        else:
+            m = hvo.ORBmatcher.__new__(hvo.ORBmatcher)
+            m.mfNNratio, m.mbCheckOrientation, m._pm = 0.6, True, OraclePMf()
+        nf, best = m.Fuse(KF, MPs, th)
+        full = np.full(M, -1, np.int32); full[sel] = best
+        want = np.full(M, -1, np.int32); want[ev[:, 0]] = ev[:, 1]
+        assert nf == nf_r == len(ev) and np.array_equal(full, want)
+        assert len(set(ev[:, 2])) == 3            # AddObservation and both Replace directions occurred
+        total += nf
+    assert total > 300
+
+
+def test_oracle_fuse_equals_reference(hvo, synth):
+    """ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:838-994) executed with KeyFrame::GetFeaturesInArea / IsInImage
+    (src/KeyFrame.cc:627-666, 780-783) and MapPoint::PredictScale(dist, KeyFrame*): the key-frame keypoint every map point is fused into."""
+    _check_fuse(hvo, synth, gpu=False)
+
+
 def test_predict_scale_thresholds_reproduce_logf(hvo):
     """level(ratio) from the thresholds == ceil(logf(ratio) / L) of the host libm for random ratios and for both float neighbours of
     every threshold (the boundaries), clamped (points) and unclamped (lines)."""
@@ -430,3 +572,13 @@ def test_gpu_distinctive_and_search_by_bow_equal_reference(hvo, synth):
         nm_r, match_r = _ref(f'bow{seed}', lambda: oracle.ref_search_by_bow(KF, F, ratio, ori))
         nm, match = hvo.ORBmatcher(ratio, ori).SearchByBoW(KF, F)
         assert nm == int(nm_r) and np.array_equal(match, match_r)
+
+
+@pytest.mark.gpu
+def test_gpu_search_for_triangulation_equals_reference(hvo, synth):
+    _check_triangulation(hvo, synth, gpu=True)
+
+
+@pytest.mark.gpu
+def test_gpu_fuse_equals_reference(hvo, synth):
+    _check_fuse(hvo, synth, gpu=True)
