@@ -284,8 +284,12 @@ def main():
     dev = torch.device('cuda', local_rank)
     d_gray = torch.from_numpy(gray).to(dev).repeat(reps, 1, 1)[:count].contiguous()
     d_depth = torch.from_numpy(depth.view(np.int16)).to(dev).repeat(reps, 1, 1)[:count].contiguous()
+    # A call that is smaller than two chunks (strong scaling at 8 GPUs: 1024 frames per rank and step) still gets two lanes of `call` frames:
+    # consecutive calls then alternate lanes, so the upload of call k + 1 and the download of call k - 1 run beside the kernels of call k.
+    two_small_lanes = args.lanes == 0 and call < 2048
     fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
-                           lanes=args.lanes, membership='u4', normals='n3', max_planes=MAX_PLANES, max_batch=call, device=local_rank,
+                           lanes=2 if two_small_lanes else args.lanes, membership='u4', normals='n3', max_planes=MAX_PLANES,
+                           max_batch=2 * call if two_small_lanes else call, device=local_rank,
                            nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'], nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
     # one set of device outputs for a call, reused by every call of a step (the bench keeps no results)
     shapes = fe.output_shapes(call)
