@@ -25,7 +25,7 @@ namespace hvo {
 // ------------------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------------------
-__constant__ int8_t c_pattern[1024] = {
+__device__ __align__(16) const int8_t g_pattern[1024] = {   // read once per CTA, coalesced (lane-varying constant reads serialise)
 #include "../../include/hvo_orb_pattern.inc"
 };
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -95,6 +95,78 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
                         v = min(255, max(0, v));
                         packed |= (uint32_t)v << (8 * i);
                     }
+                    uint8_t* D = dst + (long long)f * dframe + (long long)y * dpitch + x0;
+                    if (x0 + 3 < dw) *reinterpret_cast<uint32_t*>(D) = packed;  // dpitch and x0 are multiples of 4
+                    else for (int i = 0; x0 + i < dw; ++i) D[i] = (uint8_t)(packed >> (8 * i));
+                }
+            }
+        }
+    }
+}
+
+// K1 for the usual pyramid factors (<= ~1.3: the source rows of a tile fit kRtSrcRows x kRtSrcWords words): the source band of the
+// tile goes to shared memory first as aligned words (coalesced, every byte read once), pass H reads its two taps per output from
+// there (byte offsets in registers, no global latency inside the pass), pass V blends with the row coefficients staged per tile and
+// the >> 16 of both products folded into multiply-high.  Same arithmetic as k_resize, bit for bit.
+static const int kRtSrcRows = 44, kRtSrcWords = 44;
+
+__global__ void __launch_bounds__(256) k_resize_tile(const uint8_t* __restrict__ src, int spitch, long long sframe, int sw,
+                                                     uint8_t* __restrict__ dst, int dpitch, long long dframe, int dw, int dh,
+                                                     const int2* __restrict__ xtab, const int4* __restrict__ ytab) {
+    __shared__ uint32_t sraw[kRtSrcRows * kRtSrcWords];
+    __shared__ __align__(8) uint16_t hrow[kRtSrcRows * kRsW];
+    __shared__ int4 syt[kRsH];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int tx = blockIdx.x * kRsW, ty = blockIdx.y * kRsH;
+    const int xlast = min(tx + kRsW, dw) - 1, ylast = min(ty + kRsH, dh) - 1;
+    const int s_base = __ldg(&ytab[ty]).x;
+    const int ns = min(__ldg(&ytab[ylast]).y - s_base + 1, kRtSrcRows);
+    const int xs = __ldg(&xtab[tx]).x & ~3;
+    const int nwords = min(((min(__ldg(&xtab[xlast]).x + 1, sw - 1) - xs) >> 2) + 1, kRtSrcWords);
+    const uint8_t* S = src + (long long)f * sframe + (long long)s_base * spitch + xs;
+    if (tid < kRsH) syt[tid] = __ldg(&ytab[min(ty + tid, dh - 1)]);
+    {   // source band: 64 threads across the words of a row, 4 rows per sweep
+        const int k = tid & 63, r0 = tid >> 6;
+        if (k < nwords)
+            for (int r = r0; r < ns; r += 4) sraw[r * kRtSrcWords + k] = __ldg(reinterpret_cast<const uint32_t*>(S + (long long)r * spitch) + k);
+    }
+    __syncthreads();
+    {   // pass H
+        const int col = tid & (kRsW - 1), half = tid >> 7;
+        const int x = tx + col;
+        if (x < dw) {
+            const int2 xt = __ldg(&xtab[x]);
+            const int o0 = xt.x - xs, o1 = min(xt.x + 1, sw - 1) - xs;
+            const int w0 = (int)(short)(xt.y & 0xffff), w1 = xt.y >> 16;
+            const uint8_t* b = reinterpret_cast<const uint8_t*>(sraw) + half * (kRtSrcWords * 4);
+            uint16_t* hr = hrow + half * kRsW + col;
+#pragma unroll 4
+            for (int r = half; r < ns; r += 2) {
+                *hr = (uint16_t)((b[o0] * w0 + b[o1] * w1) >> 4);
+                b += 2 * kRtSrcWords * 4;
+                hr += 2 * kRsW;
+            }
+        }
+    }
+    __syncthreads();
+    {   // pass V: 4 columns x 4 rows per thread; ((b0 * h0) >> 16) + ((b1 * h1) >> 16) as multiply-high by the coefficients << 16
+        const int cg = tid & 31, rs = tid >> 5;
+        const int x0 = tx + 4 * cg;
+        if (x0 < dw) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int y = ty + rs * 4 + j;
+                if (y < dh) {
+                    const int4 yt = syt[rs * 4 + j];
+                    const uint2 a = *reinterpret_cast<const uint2*>(&hrow[(yt.x - s_base) * kRsW + 4 * cg]);
+                    const uint2 b = *reinterpret_cast<const uint2*>(&hrow[(yt.y - s_base) * kRsW + 4 * cg]);
+                    const uint32_t b0 = (uint32_t)yt.z << 16, b1 = (uint32_t)yt.w << 16;
+                    const uint32_t v0 = (__umulhi(b0, a.x & 0xffffu) + __umulhi(b1, b.x & 0xffffu) + 2u) >> 2;
+                    const uint32_t v1 = (__umulhi(b0, a.x >> 16) + __umulhi(b1, b.x >> 16) + 2u) >> 2;
+                    const uint32_t v2 = (__umulhi(b0, a.y & 0xffffu) + __umulhi(b1, b.y & 0xffffu) + 2u) >> 2;
+                    const uint32_t v3 = (__umulhi(b0, a.y >> 16) + __umulhi(b1, b.y >> 16) + 2u) >> 2;
+                    // b0 + b1 = 2048 and h <= 32640: the sum is at most 255, no saturation needed
+                    const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
                     uint8_t* D = dst + (long long)f * dframe + (long long)y * dpitch + x0;
                     if (x0 + 3 < dw) *reinterpret_cast<uint32_t*>(D) = packed;  // dpitch and x0 are multiples of 4
                     else for (int i = 0; x0 + i < dw; ++i) D[i] = (uint8_t)(packed >> (8 * i));
@@ -628,134 +700,110 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K4: orientation + on-the-fly blur + rBRIEF + output assembly, one warp per keypoint
+// K4: orientation + 7x7 sigma-2 Gaussian of the keypoint's patch + steered rBRIEF + output assembly, one warp per keypoint.
+//
+// The reference blurs every level (ORBextractor.cc:1083-1084) and computeOrbDescriptor (.cc:106-144) then reads 512 samples
+// of the blurred level around each keypoint: rotated pattern coordinates reach +-18 (|(-13,-13)| = 18.4), so only the 37x37
+// blurred patch matters, i.e. the 43x43 patch of the level itself (BORDER_REFLECT_101 where it leaves the image).  For
+// ~1000 keypoints on 950 K pyramid pixels blurring the patches costs less than half the instructions of blurring the levels
+// and a third of the DRAM traffic (no blurred pyramid is written or read back), so the blur lives here:
+//   load   44 x 12 aligned words of the level (rows cy-21 .. cy+22, the last one only pads the row pairs) -> shared memory
+//   angle  IC_Angle (.cc:75-102) on the raw patch: lane <-> column
+//   H      cv::GaussianBlur fixed point (Q8 kernel 18,34,48,56,48,34,18): horizontal pass exact in 16 bits, four outputs of two
+//          rows per work item with __dp4a on funnel-shifted words; results are stored as vertical PAIRS (row 2r | row 2r+1 << 16)
+//   V      vertical pass as four __dp2a per pixel on the row pairs (an output row starting on an odd row uses the pairs one
+//          row earlier with the coefficients shifted by one: the extra row gets coefficient 0), rounded (v + 2^15) >> 16;
+//          the blurred 37x37 patch overlays the raw one
+//   rBRIEF lane i -> descriptor byte i, samples read from shared memory
 // ------------------------------------------------------------------------------------------------------
-
-// ------------------------------------------------------------------------------------------------------
-// K4: 7x7 sigma-2 Gaussian of every level (cv::GaussianBlur fixed point: Q8 kernel 18,34,48,56,48,34,18,
-// horizontal pass exact in 16 bits, vertical pass rounded (v + 2^15) >> 16, BORDER_REFLECT_101).
-// One CTA = 128 x 32 output pixels; horizontal pass with __dp4a on aligned words, vertical pass 4x4 px / thread.
-// ------------------------------------------------------------------------------------------------------
-static const int kBlW = 128, kBlH = 32, kBlRawStride = 35, kBlHbStride = 66;
-
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, ImgSrc src,
-                                              const TileDesc* __restrict__ tiles, uint8_t* __restrict__ blur) {
-    __shared__ uint32_t raw[(kBlH + 6) * kBlRawStride];
-    __shared__ __align__(8) uint32_t hb[(kBlH + 6) * kBlHbStride];
-    const TileDesc t = tiles[blockIdx.x];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const LevelGeom& L = g.lv[t.level];
-    int pitch;
-    const uint8_t* img = level_ptr(g, src, t.level, f, pitch);
-    const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
-    const int tx = t.tx, ty = t.ty;
-    for (int idx = tid; idx < (kBlH + 6) * 34; idx += 256) {
-        const int r = idx / 34, wi = idx - r * 34;
-        const int y = reflect101(ty - 3 + r, L.h);
-        const int x = tx - 4 + 4 * wi;
-        const uint8_t* row = img + (long long)y * pitch;
-        uint32_t w = 0;
-        if (aligned && x >= 0 && x + 3 < L.w) {
-            w = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int xx = min(max(reflect101(x + j, L.w), 0), L.w - 1);
-                w |= (uint32_t)__ldg(row + xx) << (8 * j);
-            }
-        }
-        raw[r * kBlRawStride + wi] = w;
-    }
-    __syncthreads();
-    const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
-    for (int idx = tid; idx < (kBlH + 6) * 32; idx += 256) {
-        const int r = idx >> 5, gq = idx & 31;
-        const uint32_t a = raw[r * kBlRawStride + gq], b = raw[r * kBlRawStride + gq + 1], c = raw[r * kBlRawStride + gq + 2];
-        // output x = 4gq + j reads tile bytes 4gq + j + 1 .. + 7
-        const uint32_t o0 = __dp4a(__byte_perm(a, b, 0x4321), K0123, __dp4a(__byte_perm(b, c, 0x4321), K456, 0u));
-        const uint32_t o1 = __dp4a(__byte_perm(a, b, 0x5432), K0123, __dp4a(__byte_perm(b, c, 0x5432), K456, 0u));
-        const uint32_t o2 = __dp4a(__byte_perm(a, b, 0x6543), K0123, __dp4a(__byte_perm(b, c, 0x6543), K456, 0u));
-        const uint32_t o3 = __dp4a(b, K0123, __dp4a(c, K456, 0u));
-        *reinterpret_cast<uint2*>(&hb[r * kBlHbStride + 2 * gq]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
-    }
-    __syncthreads();
-    {
-        const int q = tid & 31, sgm = tid >> 5;  // 4 columns x 4 rows per thread
-        const int x0 = tx + 4 * q;
-        if (x0 < L.w) {
-            uint32_t col[10][2];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                const uint2 v = *reinterpret_cast<const uint2*>(&hb[(4 * sgm + r) * kBlHbStride + 2 * q]);
-                col[r][0] = v.x; col[r][1] = v.y;
-            }
-            uint8_t* out = blur + (long long)f * g.blur_frame_bytes + L.blur_off;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int y = ty + 4 * sgm + j;
-                uint32_t packed = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t h[7];
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) h[k] = (i & 1) ? (col[j + k][i >> 1] >> 16) : (col[j + k][i >> 1] & 0xffffu);
-                    const uint32_t acc = 18u * (h[0] + h[6]) + 34u * (h[1] + h[5]) + 48u * (h[2] + h[4]) + 56u * h[3];
-                    packed |= ((acc + 32768u) >> 16) << (8 * i);
-                }
-                if (y < L.h) {
-                    uint8_t* D = out + (long long)y * L.bpitch + x0;
-                    if (x0 + 3 < L.w) *reinterpret_cast<uint32_t*>(D) = packed;
-                    else for (int i = 0; x0 + i < L.w; ++i) D[i] = (uint8_t)(packed >> (8 * i));
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// K5: orientation + steered rBRIEF + output assembly, one warp per keypoint
-// ------------------------------------------------------------------------------------------------------
-static const int kDescWarps = 8;
+static const int kDescWarps = 4;
+static const int kPatRows = 44, kPatWords = 12;   // raw patch: rows cy-21 .. cy+22, 48 bytes from the aligned column at or below cx-21
+static const int kPatPairs = kPatRows / 2;
+static const int kBlurPitch = 40;                 // columns of the H / blurred patch rows (37 used)
 
 __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_constant__ OrbGeom g, ImgSrc src,
-                                                              const uint8_t* __restrict__ blur,
                                                               const uint32_t* __restrict__ okp_all,
                                                               const int* __restrict__ on, hvo_keypoint* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int32_t* __restrict__ counts,
                                                               const uint16_t* __restrict__ depth16, float depth_factor,
                                                               float bf, int distorted, float* __restrict__ kp_depth,
                                                               float* __restrict__ kp_uright) {
-    __shared__ int8_t s_pat[1024];
+    __shared__ uint32_t s_pat[256];   // test t of descriptor byte b at word t * 32 + b: (ax, ay, bx, by), conflict-free for lane <-> b
+    __shared__ __align__(16) uint32_t s_raw[kDescWarps][kPatRows * kPatWords + 8];
+    __shared__ __align__(16) uint32_t s_hp[kDescWarps][kPatPairs * kBlurPitch];
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pat[(i & 7) * 32 + (i >> 3)] = __ldg(reinterpret_cast<const uint32_t*>(g_pattern) + i);
     __syncthreads();
 
-    // locate keypoint gi (level-major) of frame f
+    // locate keypoint gi (level-major) of frame f: lane l holds the count of level l, inclusive scan over the levels
     const int gi = blockIdx.x * kDescWarps + warp;
-    int total = 0, lvl = -1, idx = 0;
-    for (int l = 0; l < g.nlevels; ++l) {
-        const int nl = on[f * g.nlevels + l];
-        if (lvl < 0 && gi < total + nl) { lvl = l; idx = gi - total; }
-        total += nl;
-    }
+    const int nl = lane < g.nlevels ? __ldg(&on[f * g.nlevels + lane]) : 0;
+    int incl = nl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned below = __ballot_sync(0xffffffffu, incl <= gi);   // levels that end at or before gi: a prefix of the lanes
+    const int lvl = __popc(below);
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[f] = min(total, g.out_cap);
-    if (lvl < 0 || gi >= g.out_cap) return;
+    if (gi >= total || gi >= g.out_cap) return;
+    const int idx = gi - __shfl_sync(0xffffffffu, incl - nl, lvl);
 
     const LevelGeom& L = g.lv[lvl];
     const uint32_t c = okp_all[(long long)f * g.kp_total + L.kp_off + idx];
     const int cx = c & 0xfff, cy = (c >> 12) & 0xfff, resp = c >> 24;
     int pitch;
     const uint8_t* img = level_ptr(g, src, lvl, f, pitch);
+    uint32_t* raw = s_raw[warp];
+    uint32_t* hp = s_hp[warp];
 
-    // IC_Angle on the unblurred level: lane <-> column u = lane - 15, rows are coalesced 31-byte reads
+    // ---- load: word k of row r holds level bytes xa + 4k .. + 3 of row reflect101(cy - 21 + r) ----
+    const int x0 = cx - 21, xa = x0 & ~3, sh = x0 - xa;   // patch column 0 sits at byte `sh` of a raw row
+    const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    const int lw = L.w, lh = L.h;
+    // interior keypoints (the 43 x 43 patch inside the level, every word of it inside the allocation): straight word loads, all in flight
+    const bool interior = aligned && xa >= 0 && cx + 21 < lw && cy >= 21 && cy + 21 < lh && (xa + 4 * kPatWords <= pitch || cy + 21 < lh - 1);
+    if (interior) {
+        const uint8_t* base = img + (long long)(cy - 21) * pitch + xa;
+#pragma unroll
+        for (int it = 0; it < (kPatRows * kPatWords + 31) / 32; ++it) {
+            const int i = lane + 32 * it;
+            if (i < kPatRows * kPatWords) {
+                const int r = (i * 43691) >> 19, k = i - kPatWords * r;   // i / 12
+                raw[i] = __ldg(reinterpret_cast<const uint32_t*>(base + min(r, kPatRows - 2) * pitch + 4 * k));   // row 43 only pads the last pair
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < kPatRows * kPatWords; i += 32) {
+            const int r = (i * 43691) >> 19, k = i - kPatWords * r;
+            const int y = min(max(reflect101(cy - 21 + r, lh), 0), lh - 1);
+            const int x = xa + 4 * k;
+            const uint8_t* row = img + (long long)y * pitch;
+            uint32_t w = 0;
+            if (aligned && x >= 0 && x + 3 < lw) {
+                w = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = min(max(reflect101(x + j, lw), 0), lw - 1);
+                    w |= (uint32_t)__ldg(row + xx) << (8 * j);
+                }
+            }
+            raw[i] = w;
+        }
+    }
+    if (lane < 8) raw[kPatRows * kPatWords + lane] = 0u;   // the word behind the last row is read (and multiplied by nothing that is kept)
+    __syncwarp();
+
+    // ---- IC_Angle on the unblurred patch: lane <-> column u = lane - 15 ----
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = abs(u);
-        const uint8_t* p = img + (long long)cy * pitch + cx + u;
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(raw) + 21 * (kPatWords * 4) + sh + 21 + u;
 #pragma unroll
         for (int v = -15; v <= 15; ++v) {
             if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = __ldg(p + (long long)v * pitch);
+                const int val = p[v * (kPatWords * 4)];
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -768,27 +816,85 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const __grid_const
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // steered rBRIEF on the blurred level: lane i -> descriptor byte i
+    // ---- H pass: item = (row pair, group of 4 columns) ----
+    {
+        const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
+        const int fs = 8 * sh;
+#pragma unroll 1
+        for (int it = 0; it < (kPatPairs * (kBlurPitch / 4) + 31) / 32; ++it) {
+            const int item = lane + 32 * it;
+            if (item < kPatPairs * (kBlurPitch / 4)) {
+                const int rp = (item * 6554) >> 16, cg = item - (kBlurPitch / 4) * rp;   // item / 10
+                uint32_t o[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t* rr = raw + (2 * rp + h) * kPatWords + cg;
+                    const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2], w3 = rr[3];
+                    const uint32_t A = __funnelshift_r(w0, w1, fs), B = __funnelshift_r(w1, w2, fs), C = __funnelshift_r(w2, w3, fs);
+                    o[h][0] = __dp4a(A, K0123, __dp4a(B, K456, 0u));
+                    o[h][1] = __dp4a(__byte_perm(A, B, 0x4321), K0123, __dp4a(__byte_perm(B, C, 0x4321), K456, 0u));
+                    o[h][2] = __dp4a(__byte_perm(A, B, 0x5432), K0123, __dp4a(__byte_perm(B, C, 0x5432), K456, 0u));
+                    o[h][3] = __dp4a(__byte_perm(A, B, 0x6543), K0123, __dp4a(__byte_perm(B, C, 0x6543), K456, 0u));
+                }
+                *reinterpret_cast<uint4*>(&hp[rp * kBlurPitch + 4 * cg]) =
+                    make_uint4(__byte_perm(o[0][0], o[1][0], 0x5410), __byte_perm(o[0][1], o[1][1], 0x5410), __byte_perm(o[0][2], o[1][2], 0x5410),
+                               __byte_perm(o[0][3], o[1][3], 0x5410));
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- V pass: lane = (band of 14 output rows, group of 4 columns); the blurred patch overlays the raw one ----
+    if (lane < 30) {
+        const int band = lane / 10, cg = lane - 10 * band;
+        const int y0 = 14 * band;   // even: every iteration makes the even row y and the odd row y + 1 from the same four row pairs
+        // row pairs {2p, 2p+1}: the even output row y uses pairs y/2 .. y/2+3 with (k0,k1)(k2,k3)(k4,k5)(k6,0), the odd row y+1 the same
+        // pairs with (0,k0)(k1,k2)(k3,k4)(k5,k6)
+        const uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+        const uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+        const uint4* hp4 = reinterpret_cast<const uint4*>(hp) + cg;
+        const int p0 = y0 >> 1;
+        uint4 P0 = hp4[p0 * (kBlurPitch / 4)], P1 = hp4[(p0 + 1) * (kBlurPitch / 4)], P2 = hp4[(p0 + 2) * (kBlurPitch / 4)];
+        uint32_t* bl = raw + y0 * (kBlurPitch / 4) + cg;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const uint4 P3 = hp4[min(p0 + j + 3, kPatPairs - 1) * (kBlurPitch / 4)];   // rows past 36 (last band) are computed and dropped
+            {
+                const uint32_t a0 = __dp2a_lo(P0.x, E0, __dp2a_lo(P1.x, E1, __dp2a_lo(P2.x, E2, __dp2a_lo(P3.x, E3, 32768u))));
+                const uint32_t a1 = __dp2a_lo(P0.y, E0, __dp2a_lo(P1.y, E1, __dp2a_lo(P2.y, E2, __dp2a_lo(P3.y, E3, 32768u))));
+                const uint32_t a2 = __dp2a_lo(P0.z, E0, __dp2a_lo(P1.z, E1, __dp2a_lo(P2.z, E2, __dp2a_lo(P3.z, E3, 32768u))));
+                const uint32_t a3 = __dp2a_lo(P0.w, E0, __dp2a_lo(P1.w, E1, __dp2a_lo(P2.w, E2, __dp2a_lo(P3.w, E3, 32768u))));
+                if (y0 + 2 * j < 37) bl[(2 * j) * (kBlurPitch / 4)] = __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+            }
+            {
+                const uint32_t a0 = __dp2a_lo(P0.x, O0, __dp2a_lo(P1.x, O1, __dp2a_lo(P2.x, O2, __dp2a_lo(P3.x, O3, 32768u))));
+                const uint32_t a1 = __dp2a_lo(P0.y, O0, __dp2a_lo(P1.y, O1, __dp2a_lo(P2.y, O2, __dp2a_lo(P3.y, O3, 32768u))));
+                const uint32_t a2 = __dp2a_lo(P0.z, O0, __dp2a_lo(P1.z, O1, __dp2a_lo(P2.z, O2, __dp2a_lo(P3.z, O3, 32768u))));
+                const uint32_t a3 = __dp2a_lo(P0.w, O0, __dp2a_lo(P1.w, O1, __dp2a_lo(P2.w, O2, __dp2a_lo(P3.w, O3, 32768u))));
+                if (y0 + 2 * j + 1 < 37) bl[(2 * j + 1) * (kBlurPitch / 4)] = __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+            }
+            P0 = P1; P1 = P2; P2 = P3;
+        }
+    }
+    __syncwarp();
+
+    // ---- steered rBRIEF on the blurred patch: lane i -> descriptor byte i ----
     const float factorPI = 0.017453292519943295769236907684886f;  // (float)(CV_PI / 180.f)
     const float ang = __fmul_rn(angle, factorPI);
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t* ctr = blur + (long long)f * g.blur_frame_bytes + L.blur_off + (long long)cy * L.bpitch + cx;
-    const int bp = L.bpitch;
-    const int8_t* pt = s_pat + lane * 32;
-    int t0v[8], t1v[8];
+    const uint8_t* ctr = reinterpret_cast<const uint8_t*>(raw) + 18 * kBlurPitch + 18;
+    int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const float ax = pt[4 * t], ay = pt[4 * t + 1], bx = pt[4 * t + 2], by = pt[4 * t + 3];
+        const uint32_t pw = s_pat[t * 32 + lane];
+        const float ax = (float)(int8_t)(pw & 0xff), ay = (float)(int8_t)((pw >> 8) & 0xff), bx = (float)(int8_t)((pw >> 16) & 0xff), by = (float)(int8_t)(pw >> 24);
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(ax, b), __fmul_rn(ay, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(ax, a), __fmul_rn(ay, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(bx, b), __fmul_rn(by, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(bx, a), __fmul_rn(by, b)));
-        t0v[t] = __ldg(ctr + r0 * bp + c0);
-        t1v[t] = __ldg(ctr + r1 * bp + c1);
+        const int t0 = ctr[r0 * kBlurPitch + c0], t1 = ctr[r1 * kBlurPitch + c1];
+        val |= (t0 < t1 ? 1 : 0) << t;
     }
-    int val = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) val |= (t0v[t] < t1v[t] ? 1 : 0) << t;
     const long long o = (long long)f * g.out_cap + gi;
     desc[o * 32 + lane] = (uint8_t)val;
 
@@ -850,9 +956,8 @@ int hvo_orb::init() {
     // ---- level geometry ----
     std::memset(&g, 0, sizeof(g));
     g.nlevels = n; g.width = width; g.height = height;
-    long long off = 0, boff = 0;
+    long long off = 0;
     int cand_off = 0, kp_off = 0;
-    std::vector<TileDesc> btiles;
     std::vector<StripDesc> strips;
     fast_smem = 0;
     max_quota = 0;
@@ -869,9 +974,6 @@ int hvo_orb::init() {
         L.kp_size = (float)(int)(31 * sf[l]);
         const float fw = (float)(L.maxBX - L.minBX), fh = (float)(L.maxBY - L.minBY);
         L.nCols = (int)(fw / 30.f); L.nRows = (int)(fh / 30.f);
-        L.bpitch = (int)align_up((size_t)L.w, 128); L.blur_off = boff; boff += (long long)L.bpitch * L.h;
-        for (int yy = 0; yy < L.h; yy += kBlH)
-            for (int xx = 0; xx < L.w; xx += kBlW) { TileDesc t; t.level = (short)l; t.tx = (short)xx; t.ty = (short)yy; t.pad = 0; btiles.push_back(t); }
         L.cand_off = cand_off; L.cand_cap = 0;
         L.kp_off = kp_off; L.kp_cap = L.quota + 4;
         kp_off += L.kp_cap;
@@ -928,8 +1030,6 @@ int hvo_orb::init() {
     }
     if (max_quota + 8 > 16383) { set_error("nfeatures too large"); return HVO_ERR_ARG; }
     g.pyr_frame_bytes = (long long)align_up((size_t)off, 256);
-    g.blur_frame_bytes = (long long)align_up((size_t)boff, 256);
-    nbtiles = (int)btiles.size();
     g.cand_total = std::max(cand_off, 1);
     g.kp_total = kp_off;
     g.out_cap = kp_off;
@@ -937,15 +1037,12 @@ int hvo_orb::init() {
 
     // ---- CUDA resources ----
     HVO_CUDA(cudaSetDevice(device));
-    pin_carveout(k_resize); pin_carveout(k_fast_strips); pin_carveout(k_octree); pin_carveout(k_blur); pin_carveout(k_describe);
+    pin_carveout(k_resize); pin_carveout(k_resize_tile); pin_carveout(k_fast_strips); pin_carveout(k_octree); pin_carveout(k_describe);
     HVO_CUDA(create_stream(&stream));
     for (auto& e : ev) HVO_CUDA(cudaEventCreate(&e));
     for (auto& e : tev) HVO_CUDA(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch;
     HVO_CUDA(cudaMalloc(&d_pyr, std::max<size_t>(B * (size_t)g.pyr_frame_bytes, 256)));
-    HVO_CUDA(cudaMalloc(&d_blur, B * (size_t)g.blur_frame_bytes));
-    HVO_CUDA(cudaMalloc(&d_btiles, btiles.size() * sizeof(TileDesc)));
-    HVO_CUDA(cudaMemcpy(d_btiles, btiles.data(), btiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
     HVO_CUDA(cudaMalloc(&d_cand, B * g.cand_total * sizeof(uint32_t)));
     HVO_CUDA(cudaMalloc(&d_knode, B * g.cand_total * sizeof(uint16_t)));
     HVO_CUDA(cudaMalloc(&d_ncand, B * n * sizeof(int)));
@@ -991,6 +1088,22 @@ int hvo_orb::init() {
             yt.push_back(make_int4(sy0, sy1, b0, b1));
         }
     }
+    resize_tile_ok.assign(n, 0);
+    for (int l = 1; l < n; ++l) {   // does every 128 x 32 destination tile read at most kRtSrcRows x kRtSrcWords source words?
+        const LevelGeom& S = g.lv[l - 1];
+        const LevelGeom& D = g.lv[l];
+        bool ok = true;
+        for (int ty = 0; ty < D.h && ok; ty += kRsH) {
+            const int yl = std::min(ty + kRsH, D.h) - 1;
+            ok = yt[ytab_off[l] + yl].y - yt[ytab_off[l] + ty].x + 1 <= kRtSrcRows;
+        }
+        for (int tx = 0; tx < D.w && ok; tx += kRsW) {
+            const int xl = std::min(tx + kRsW, D.w) - 1;
+            const int xs = xt[xtab_off[l] + tx].x & ~3;
+            ok = ((std::min(xt[xtab_off[l] + xl].x + 1, S.w - 1) - xs) >> 2) + 1 <= kRtSrcWords;
+        }
+        resize_tile_ok[l] = ok ? 1 : 0;
+    }
     HVO_CUDA(cudaMalloc(&d_xtab, std::max<size_t>(xt.size(), 1) * sizeof(int2)));
     HVO_CUDA(cudaMalloc(&d_ytab, std::max<size_t>(yt.size(), 1) * sizeof(int4)));
     if (!xt.empty()) HVO_CUDA(cudaMemcpy(d_xtab, xt.data(), xt.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1013,7 +1126,7 @@ int hvo_orb::init() {
 void hvo_orb::release() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    void* bufs[] = {d_blur, d_btiles, d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_strips, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
+    void* bufs[] = {d_l0, d_depth, d_pyr, d_xtab, d_ytab, d_strips, d_cand, d_ncand, d_knode, d_okp, d_on, d_err,
                     d_kps, d_desc, d_counts, d_kpdepth, d_kpuright};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -1039,8 +1152,14 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
         const long long sframe = l == 1 ? src.l0_frame : g.pyr_frame_bytes;
         dim3 grd(div_up(D.w, kRsW), div_up(D.h, kRsH), B);
         timeline_mark(stream, "k_resize");
-        k_resize<<<grd, 256, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
-                                          d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
+        // the shared-memory band kernel needs aligned source words (level 0 is the caller's buffer) and a tile's source rows to fit
+        const bool tile_ok = resize_tile_ok[l] && (S.pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(sp) & 3) == 0 && (sframe & 3) == 0;
+        if (tile_ok)
+            k_resize_tile<<<grd, 256, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
+                                                   d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
+        else
+            k_resize<<<grd, 256, 0, stream>>>(sp, S.pitch, sframe, S.w, d_pyr + D.img_off, D.pitch, g.pyr_frame_bytes, D.w, D.h,
+                                              d_xtab + xtab_off[l], d_ytab + ytab_off[l]);
         ++launches;
     }
     if (profiling) HVO_CUDA(cudaEventRecord(ev[1], stream));
@@ -1056,15 +1175,13 @@ int hvo_orb::run(const uint8_t* d_gray, int nframes, hvo_keypoint* d_kps_out, ui
     k_octree<<<dim3(n, B), 256, oct_smem, stream>>>(g, d_cand, d_ncand, d_knode, d_okp, d_on, max_quota + 8, d_err);
     ++launches;
     if (profiling) HVO_CUDA(cudaEventRecord(ev[3], stream));
-    // K4: blur of every level, K5: describe
-    timeline_mark(stream, "k_blur");
-    k_blur<<<dim3(nbtiles, B), 256, 0, stream>>>(g, src, d_btiles, d_blur);
-    ++launches;
+    // K4: describe (the 7x7 blur of the reference's pyramid is computed per keypoint patch inside; stage 'blur' stays in the
+    // stage-time record as an empty interval)
     if (profiling) HVO_CUDA(cudaEventRecord(ev[4], stream));
     const bool rgbd_on = d_depth16 != nullptr && rgbd != nullptr && d_kp_depth != nullptr && d_kp_uright != nullptr;
     timeline_mark(stream, "k_describe");
     k_describe<<<dim3(div_up(g.out_cap, kDescWarps), B), kDescWarps * 32, 0, stream>>>(
-        g, src, d_blur, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
+        g, src, d_okp, d_on, d_kps_out, d_desc_out, d_counts_out, rgbd_on ? d_depth16 : nullptr,
         rgbd_on ? rgbd->depth_factor : 0.f, rgbd_on ? rgbd->bf : 0.f, rgbd_on ? rgbd->distorted : 0, d_kp_depth, d_kp_uright);
     ++launches;
     if (profiling) { HVO_CUDA(cudaEventRecord(ev[5], stream)); have_stage_times = true; }

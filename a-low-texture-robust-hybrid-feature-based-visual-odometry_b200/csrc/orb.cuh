@@ -10,8 +10,6 @@ namespace hvo {
 struct LevelGeom {
     int w, h, pitch;          // level image size; pitch in bytes (levels >= 1: 128-byte aligned)
     long long img_off;        // byte offset of the level inside one frame's pyramid block (levels >= 1)
-    long long blur_off;       // byte offset of the blurred level inside one frame's blur block
-    int bpitch;               // pitch of the blurred level (128-byte aligned)
     int minBX, minBY, maxBX, maxBY;  // FAST search window (ORBextractor.cc:771-774)
     int nCols, nRows, wCell, hCell;  // cell grid (ORBextractor.cc:779-785)
     int quota;                // mnFeaturesPerLevel[l]
@@ -28,7 +26,6 @@ struct OrbGeom {
     int cand_total, kp_total;  // per-frame arena sizes (entries)
     int out_cap;               // rows per frame in the caller's kps/desc buffers
     long long pyr_frame_bytes; // bytes per frame of levels >= 1
-    long long blur_frame_bytes; // bytes per frame of the blurred pyramid (all levels)
     LevelGeom lv[HVO_MAX_LEVELS];
 };
 
@@ -37,10 +34,6 @@ struct ImgSrc {  // where the pyramid of frame f lives
     long long l0_frame; // bytes per frame
     int l0_pitch;
     uint8_t* pyr;       // levels >= 1
-};
-
-struct TileDesc {  // one 128x32 tile of a level (blur kernel)
-    short level, tx, ty, pad;
 };
 
 struct StripDesc {  // one FAST strip = the detection zones of a run of cells of one reference cell row (zone = ROI minus the 3-px ring)
@@ -69,12 +62,10 @@ struct hvo_orb {
     uint8_t* d_l0 = nullptr;        // staging for host frames [B][h][w]
     uint16_t* d_depth = nullptr;    // staging for host depth [B][h][w]
     uint8_t* d_pyr = nullptr;       // [B][pyr_frame_bytes]
-    uint8_t* d_blur = nullptr;      // [B][blur_frame_bytes] 7x7 sigma-2 blurred pyramid
-    hvo::TileDesc* d_btiles = nullptr;
-    int nbtiles = 0;
     int2* d_xtab = nullptr;         // per level: {sx, w0 | w1 << 16}
     int4* d_ytab = nullptr;         // per level: {sy0, sy1, b0, b1}
     std::vector<int> xtab_off, ytab_off;
+    std::vector<char> resize_tile_ok;  // per level: the shared-memory band kernel applies (pyramid factor small enough)
     hvo::StripDesc* d_strips = nullptr;
     uint32_t* d_cand = nullptr;     // [B][cand_total] packed x | y << 12 | score << 24
     int* d_ncand = nullptr;         // [B][nlevels]
