@@ -66,9 +66,15 @@ __global__ void k_pack_normals3(const float* __restrict__ n8, float* __restrict_
     }
 }
 
-// One lane = an independent copy of the three pipelines (own handles, streams, scratch) for chunks of `cap` frames.
+// One lane = the staging of one chunk of `cap` frames in flight: input buffers, output buffers, an upload stream and one download
+// stream per pipeline.  The pipeline handles (kernels' scratch and streams) belong to lane 0 and are shared by every lane: the
+// kernels of consecutive chunks run one after the other anyway (see lane_launch), so a second copy of the 15 MB / frame of scratch
+// would buy nothing, while sharing it lets a chunk be as large as the ordered kernels want (4096+ frames) inside 180 GB.
 struct FrameLane {
     int cap = 0;
+    bool owns = false;          // lane 0 owns the pipeline handles
+    cudaStream_t down[4] = {nullptr, nullptr, nullptr, nullptr};  // host API: downloads of pipeline i (ORB, lines, planes, normals)
+    cudaEvent_t fork_depth = nullptr;  // host API: the chunk's depth has arrived (the plane pipeline starts on it; gray follows)
     hvo_orb* orb = nullptr;
     hvo_line* line = nullptr;
     hvo_plane* plane = nullptr;
@@ -123,15 +129,31 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
 // stream, record the lane's join events.  Launch order = placement order: the ordered (latency-bound) pipelines first.
 // `after`: lane whose kernels must have finished first (host API: chunks compute one after the other, so the ordered kernels
 // of two chunks never slow each other down, while the copies of the neighbouring chunks run beside the kernels).
-static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint8_t* d_gray, const uint16_t* d_depth, int n, int base,
-                       const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
+//
+// Two schedules (measured on B200, whole front-end, device-resident): SIDE BY SIDE (every pipeline starts at once on its own stream)
+// is what a small batch wants - a single frame takes max(planes, lines) instead of their sum - but each of the ordered kernels fills
+// the register file with one warp / CTA per frame by itself, and from about 2000 frames on running them beside each other only makes
+// them slower (4736 frames: 16.2 K frames/s side by side, 18.2 K one after the other; ORB / normals beside the ordered kernels:
+// 16.5-17.3 K).  So a chunk of >= kSerialFrames frames runs its pipelines ONE AFTER THE OTHER (planes, lines, ORB, normals), each at
+// its saturating batch, and the download of a pipeline's results runs beside the kernels of the next one.
+// HVO_FRAME_SERIAL=0 / 1 forces one schedule (tuning aid).
+static const int kSerialFrames = 2048;
+static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, cudaEvent_t start_depth, const uint8_t* d_gray, const uint16_t* d_depth, int n,
+                       int base, const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
-    if (after == &L) after = nullptr;  // one lane: every pipeline stream is already in order behind its own previous chunk
-    auto wait_start = [&](cudaStream_t s) -> int {
-        HVO_CUDA(cudaStreamWaitEvent(s, start, 0));
-        if (after)
+    static const int serial_env = [] { const char* e = getenv("HVO_FRAME_SERIAL"); return e ? atoi(e) : -1; }();
+    const bool serial = serial_env >= 0 ? serial_env != 0 : n >= kSerialFrames;
+    // side by side on one lane: every pipeline stream is already in order behind its own previous chunk
+    if (after == &L && !serial) after = nullptr;
+    cudaEvent_t prev_done = nullptr;   // serial schedule: the pipeline launched before this one
+    auto wait_start = [&](cudaStream_t s, bool depth_only) -> int {
+        HVO_CUDA(cudaStreamWaitEvent(s, (depth_only && start_depth) ? start_depth : start, 0));
+        if (serial && prev_done) {
+            HVO_CUDA(cudaStreamWaitEvent(s, prev_done, 0));
+        } else if (after) {   // (serial: only the first pipeline waits for the previous chunk, the others follow it)
             for (int i = 0; i < 4; ++i)
                 if (h->p.stages & (i == 0 ? ST_ORB : i == 1 ? ST_LINE : i == 2 ? ST_PLANE : ST_NORMALS)) HVO_CUDA(cudaStreamWaitEvent(s, after->cdone[i], 0));
+        }
         return HVO_OK;
     };
     // ---- phase 1: the kernels of every pipeline are queued before any copy.  (A device-to-host copy into pageable memory
@@ -139,7 +161,7 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
     // pipelines from even starting.) ----
     if (h->p.stages & ST_PLANE) {
         cudaStream_t s = plane_stream(L.plane);
-        if (int ws = wait_start(s)) return ws;
+        if (int ws = wait_start(s, true)) return ws;
         int st = o.membership8 ? hvo_plane_detect_batch_device_u8(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership, o.membership8)
                                : hvo_plane_detect_batch_device(L.plane, d_depth, n, o.n_planes, o.planes7, h->p.max_planes, o.membership);
         if (st != HVO_OK) return st;
@@ -151,19 +173,21 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         }
         k_frame_fold_status<<<(n + 255) / 256, 256, 0, s>>>(plane_status(L.plane), n, 0, 0, base, FAULT_PLANE, h->d_fault);
         HVO_CUDA(cudaEventRecord(L.cdone[2], s));
+        prev_done = L.cdone[2];
     }
     if (h->p.stages & ST_LINE) {
         cudaStream_t s = line_stream(L.line);
-        if (int ws = wait_start(s)) return ws;
+        if (int ws = wait_start(s, false)) return ws;
         int st = hvo_line_extract_batch_device(L.line, d_gray, n, o.keylines, o.line_desc, o.linevec3, o.line_counts);
         if (st != HVO_OK) return st;
         *launches += hvo_line_last_launches(L.line) + 1;
         k_frame_fold_status<<<(n + 255) / 256, 256, 0, s>>>(line_segment_counts(L.line), n, 0, line_segment_cap(L.line), base, FAULT_LINE, h->d_fault);
         HVO_CUDA(cudaEventRecord(L.cdone[1], s));
+        prev_done = L.cdone[1];
     }
     if (h->p.stages & ST_ORB) {
         cudaStream_t s = orb_stream(L.orb);
-        if (int ws = wait_start(s)) return ws;
+        if (int ws = wait_start(s, false)) return ws;
         hvo_rgbd_params rg{h->p.depth_factor, h->p.bf, h->p.distorted};
         int st = hvo_orb_extract_batch_device(L.orb, d_gray, n, o.kps, o.desc, o.kp_counts, d_depth, &rg, o.kp_depth, o.kp_uright);
         if (st != HVO_OK) return st;
@@ -171,10 +195,11 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         k_frame_fold_status<<<1, 32, 0, s>>>(orb_error_flag(L.orb), 1, 1, 0, base, FAULT_ORB, h->d_fault);   // one flag per chunk
         HVO_CUDA(cudaMemsetAsync(orb_error_flag(L.orb), 0, sizeof(int), s));
         HVO_CUDA(cudaEventRecord(L.cdone[0], s));
+        prev_done = L.cdone[0];
     }
     if (h->p.stages & ST_NORMALS) {
         cudaStream_t s = normals_stream(L.normals);
-        if (int ws = wait_start(s)) return ws;
+        if (int ws = wait_start(s, false)) return ws;
         int st = hvo_normals_compute_batch_device(L.normals, d_depth, n, o.normals8);
         if (st != HVO_OK) return st;
         *launches += 5;
@@ -184,17 +209,44 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
             ++*launches;
         }
         HVO_CUDA(cudaEventRecord(L.cdone[3], s));
+        prev_done = L.cdone[3];
     }
-    // ---- phase 2: results back to the host on each pipeline's own stream (shortest pipelines first), then the join events ----
-    if (h->p.stages & ST_NORMALS) {
-        cudaStream_t s = normals_stream(L.normals);
-        if (host && host->normals8) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
-        if (host && host->normals3) HVO_CUDA(cudaMemcpyAsync(host->normals3, o.normals3, N * (size_t)h->normals_count * 12, cudaMemcpyDeviceToHost, s));
-        timeline_mark(s, "end_normals");
-        HVO_CUDA(cudaEventRecord(L.join[3], s));
+    // ---- phase 2: results back to the host on the lane's download streams (one per pipeline, each behind its pipeline's kernels:
+    // the shared pipeline streams stay free for the next chunk), then the join events ----
+    auto down_stream = [&](int i, cudaStream_t pipe, cudaStream_t* out) -> int {
+        *out = pipe;
+        if (host) { HVO_CUDA(cudaStreamWaitEvent(L.down[i], L.cdone[i], 0)); *out = L.down[i]; }
+        return HVO_OK;
+    };
+    if (h->p.stages & ST_PLANE) {
+        cudaStream_t s;
+        if (int ds = down_stream(2, plane_stream(L.plane), &s)) return ds;
+        if (host) {
+            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
+            if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
+            if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
+            if (host->membership4) HVO_CUDA(cudaMemcpyAsync(host->membership4, o.membership4, N * (px / 2), cudaMemcpyDeviceToHost, s));
+        }
+        timeline_mark(s, "end_planes");
+        HVO_CUDA(cudaEventRecord(L.join[2], s));
+    }
+    if (h->p.stages & ST_LINE) {
+        cudaStream_t s;
+        if (int ds = down_stream(1, line_stream(L.line), &s)) return ds;
+        if (host) {
+            const size_t c = (size_t)h->max_lines;
+            HVO_CUDA(cudaMemcpyAsync(host->line_counts, o.line_counts, N * 4, cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->keylines, o.keylines, N * c * sizeof(hvo_keyline), cudaMemcpyDeviceToHost, s));
+            HVO_CUDA(cudaMemcpyAsync(host->line_desc, o.line_desc, N * c * 32, cudaMemcpyDeviceToHost, s));
+            if (host->linevec3) HVO_CUDA(cudaMemcpyAsync(host->linevec3, o.linevec3, N * c * 24, cudaMemcpyDeviceToHost, s));
+        }
+        timeline_mark(s, "end_lines");
+        HVO_CUDA(cudaEventRecord(L.join[1], s));
     }
     if (h->p.stages & ST_ORB) {
-        cudaStream_t s = orb_stream(L.orb);
+        cudaStream_t s;
+        if (int ds = down_stream(0, orb_stream(L.orb), &s)) return ds;
         if (host) {
             const size_t c = (size_t)h->orb_cap;
             HVO_CUDA(cudaMemcpyAsync(host->kp_counts, o.kp_counts, N * 4, cudaMemcpyDeviceToHost, s));
@@ -206,29 +258,13 @@ static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, const uint
         timeline_mark(s, "end_orb");
         HVO_CUDA(cudaEventRecord(L.join[0], s));
     }
-    if (h->p.stages & ST_LINE) {
-        cudaStream_t s = line_stream(L.line);
-        if (host) {
-            const size_t c = (size_t)h->max_lines;
-            HVO_CUDA(cudaMemcpyAsync(host->line_counts, o.line_counts, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->keylines, o.keylines, N * c * sizeof(hvo_keyline), cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->line_desc, o.line_desc, N * c * 32, cudaMemcpyDeviceToHost, s));
-            if (host->linevec3) HVO_CUDA(cudaMemcpyAsync(host->linevec3, o.linevec3, N * c * 24, cudaMemcpyDeviceToHost, s));
-        }
-        timeline_mark(s, "end_lines");
-        HVO_CUDA(cudaEventRecord(L.join[1], s));
-    }
-    if (h->p.stages & ST_PLANE) {
-        cudaStream_t s = plane_stream(L.plane);
-        if (host) {
-            HVO_CUDA(cudaMemcpyAsync(host->n_planes, o.n_planes, N * 4, cudaMemcpyDeviceToHost, s));
-            HVO_CUDA(cudaMemcpyAsync(host->planes7, o.planes7, N * (size_t)h->p.max_planes * 56, cudaMemcpyDeviceToHost, s));
-            if (host->membership) HVO_CUDA(cudaMemcpyAsync(host->membership, o.membership, N * px * 4, cudaMemcpyDeviceToHost, s));
-            if (host->membership8) HVO_CUDA(cudaMemcpyAsync(host->membership8, o.membership8, N * px, cudaMemcpyDeviceToHost, s));
-            if (host->membership4) HVO_CUDA(cudaMemcpyAsync(host->membership4, o.membership4, N * (px / 2), cudaMemcpyDeviceToHost, s));
-        }
-        timeline_mark(s, "end_planes");
-        HVO_CUDA(cudaEventRecord(L.join[2], s));
+    if (h->p.stages & ST_NORMALS) {
+        cudaStream_t s;
+        if (int ds = down_stream(3, normals_stream(L.normals), &s)) return ds;
+        if (host && host->normals8) HVO_CUDA(cudaMemcpyAsync(host->normals8, o.normals8, N * (size_t)h->normals_count * 32, cudaMemcpyDeviceToHost, s));
+        if (host && host->normals3) HVO_CUDA(cudaMemcpyAsync(host->normals3, o.normals3, N * (size_t)h->normals_count * 12, cudaMemcpyDeviceToHost, s));
+        timeline_mark(s, "end_normals");
+        HVO_CUDA(cudaEventRecord(L.join[3], s));
     }
     return HVO_OK;
 }
@@ -317,6 +353,11 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
         FrameLane& L = h->lane[li];
         L.cap = cap;
         L.d_out = hvo_frame_outputs{};
+        if (li > 0) {   // the pipelines (scratch + streams) are lane 0's
+            L.orb = h->lane[0].orb; L.line = h->lane[0].line; L.plane = h->lane[0].plane; L.normals = h->lane[0].normals;
+            continue;
+        }
+        L.owns = true;
         set_next_stream_priority(prio_lo);
         if (st == HVO_OK && (p->stages & ST_ORB)) st = hvo_orb_create(&p->orb, width, height, cap, device, &L.orb);
         set_next_stream_priority(prio_hi);
@@ -353,6 +394,9 @@ int hvo_frame_create(const hvo_frame_params* p, int width, int height, int max_b
             FrameLane& L = h->lane[li];
             HVO_TRY(cudaStreamCreateWithFlags(&L.up, cudaStreamNonBlocking));
             HVO_TRY(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+            HVO_TRY(cudaEventCreateWithFlags(&L.fork_depth, cudaEventDisableTiming));
+            for (auto& d : L.down) HVO_TRY(cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking));
+            if (st != HVO_OK) break;
             for (auto& e : L.join) HVO_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             if (st != HVO_OK) break;
             for (auto& e : L.cdone) HVO_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -400,10 +444,14 @@ void hvo_frame_destroy(hvo_frame* h) {
     cudaDeviceSynchronize();
     for (int li = 0; li < kMaxLanes; ++li) {
         FrameLane& L = h->lane[li];
-        if (L.orb) hvo_orb_destroy(L.orb);
-        if (L.line) hvo_line_destroy(L.line);
-        if (L.plane) hvo_plane_destroy(L.plane);
-        if (L.normals) hvo_normals_destroy(L.normals);
+        if (L.owns) {
+            if (L.orb) hvo_orb_destroy(L.orb);
+            if (L.line) hvo_line_destroy(L.line);
+            if (L.plane) hvo_plane_destroy(L.plane);
+            if (L.normals) hvo_normals_destroy(L.normals);
+        }
+        for (auto& d : L.down) if (d) cudaStreamDestroy(d);
+        if (L.fork_depth) cudaEventDestroy(L.fork_depth);
         hvo_frame_outputs& o = L.d_out;
         void* bufs[] = {L.d_gray, L.d_depth, o.kps, o.desc, o.kp_counts, o.kp_depth, o.kp_uright, o.keylines, o.line_desc, o.linevec3,
                         o.line_counts, o.n_planes, o.planes7, o.membership, o.membership8, o.normals8, o.membership4, o.normals3};
@@ -470,7 +518,7 @@ int hvo_frame_extract_batch_device(hvo_frame* h, const uint8_t* d_gray, const ui
     for (int off = 0; off < nframes; off += per, ++used) {
         FrameLane& L = h->lane[used];
         const int n = std::min(per, nframes - off);
-        st = lane_launch(h, L, h->fork, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, off, outputs_at(h, *d_out, (size_t)off), nullptr, &launches,
+        st = lane_launch(h, L, h->fork, nullptr, d_gray + (size_t)off * px, d_depth16 + (size_t)off * px, n, off, outputs_at(h, *d_out, (size_t)off), nullptr, &launches,
                          h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
         h->last_lane = used;
@@ -505,15 +553,17 @@ int hvo_frame_extract_batch_async(hvo_frame* h, const uint8_t* gray, const uint1
         const int n = std::min(per, nframes - off);
         st = wait_joins(h, L.up, L);  // the lane's previous chunk (of this or an earlier call) must be done with the staging buffers
         if (st != HVO_OK) return st;
-        HVO_CUDA(cudaMemcpyAsync(L.d_gray, gray + (size_t)off * px, (size_t)n * px, cudaMemcpyHostToDevice, L.up));
+        // depth first: the plane pipeline (first in the serial schedule) needs nothing else, the gray upload runs beside its kernels
         HVO_CUDA(cudaMemcpyAsync(L.d_depth, depth16 + (size_t)off * px, (size_t)n * px * 2, cudaMemcpyHostToDevice, L.up));
+        HVO_CUDA(cudaEventRecord(L.fork_depth, L.up));
+        HVO_CUDA(cudaMemcpyAsync(L.d_gray, gray + (size_t)off * px, (size_t)n * px, cudaMemcpyHostToDevice, L.up));
         HVO_CUDA(cudaEventRecord(L.fork, L.up));
         hvo_frame_outputs d = L.d_out;
         if (!out->membership8 && !out->membership4) d.membership8 = nullptr;
         if (!out->membership4) d.membership4 = nullptr;
         if (!out->normals3) d.normals3 = nullptr;
         const hvo_frame_outputs hostk = outputs_at(h, *out, (size_t)off);
-        st = lane_launch(h, L, L.fork, L.d_gray, L.d_depth, n, off, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
+        st = lane_launch(h, L, L.fork, L.fork_depth, L.d_gray, L.d_depth, n, off, d, &hostk, &launches, h->last_lane >= 0 ? &h->lane[h->last_lane] : nullptr);
         if (st != HVO_OK) return st;
         h->last_lane = li;
     }

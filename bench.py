@@ -7,12 +7,13 @@
 A "step" is one pass of the hot path over the C5 sequence of BASELINE.json: 8192 synthetic TUM-fr3-shaped 640x480 RGB-D frames,
 frame-sharded across the N GPUs in contiguous ranges (8192 / N frames per GPU per step: "scaling": "strong").  Frames are
 independent, so there is no data-path collective; torch.distributed carries only the barrier and the max-over-ranks of the time.
-A GPU processes its share as calls of at most 2368 frames (2 chunks of 1184 = 8 frames per SM).
+A GPU processes its share as calls of at most 4096 frames; a call of >= 2048 frames is one chunk whose pipelines run one after the
+other, each at its saturating batch (scheduling); two lanes of staging overlap the copies of neighbouring calls.
 
   value     whole-job frames/s with the inputs already resident in HBM (CUDA events on the library's master stream, max over ranks)
   e2e       the same through the reference-facing C-ABI call with HOST (pinned) buffers: host->device copy of gray + depth and
             device->host read of every output inside the timed region (compact outputs: 4-bit plane labels, normal-only normals)
-  weak      the round-1 line for comparison: every GPU processes 2368 frames per step, whatever N is
+  weak      the round-1 line for comparison: every GPU processes one call (<= 4096 frames) per step, whatever N is
   configs   sub-records for the other BASELINE.json configs: C2 (ICL-shaped low texture), C3 (1280x720, 2000 ORB), C4 (matching
             stress 2000 x 50 000 ORB + 200 x 5 000 LBD with cv2.BFMatcher beside it)
   roofline / cpu_baseline (throughput AND per-frame latency in the reference's 3-thread shape) / clocks / gpu_launches /
@@ -48,28 +49,29 @@ def emit(obj):
 
 METRIC = 'front-end frames/s @640x480'
 C5_FRAMES = 8192                                                               # BASELINE.json configs[4]
-CALL_FRAMES = 2368                                                             # frames per library call: 2 chunks of 1184 = 8 frames per SM
-CHUNK = 1184
+CALL_FRAMES = 4096                                                             # frames per library call = one chunk (serial pipeline schedule)
 ORB = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)  # TUM3.yaml:41-54
 CAM = dict(fx=535.4, fy=539.2, cx=320.1, cy=247.6)                             # TUM3.yaml:8-11
 DEPTH_FACTOR, BF, NLINES = 1.0 / 5000.0, 40.0, 200                             # TUM3.yaml:34, Camera.bf, LINE.nFeatures
 MAX_PLANES = 15                                                                # rows of planes7 (4-bit labels on the wire)
 ORACLE_CAM = (DEPTH_FACTOR, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'])
 ORACLE_STAGES = 15 | 16  # ORB | lines | planes | normals | cullingLine after the line extractor (what Frame::Frame runs)
-STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + blur + rBRIEF + RGB-D depth lookup',
+STAGES = ['orb: 8-level pyramid + per-cell FAST + quadtree + IC_Angle + 7x7 blur (per keypoint patch) + rBRIEF + RGB-D depth lookup',
           'lines: LSD (blur, 0.8 resize, gradient, ordered region growing, rectangles) + KeyLines + top-200 + LBD + line functions + '
           'Frame::cullingLine (merge, rebuild, LBD again)',
           'planes: depth back-projection + 10x10 block fits + AHC merging + block erosion + ordered pixel flood fill + last merge',
           'normals: 3x subsampled cloud + integral-image normals (PCL AVERAGE_3D_GRADIENT restatement)']
 # algorithmic bytes per 640x480 frame of the HBM-bound kernels
-ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_strips': 950532, 'k_blur': 1901064, 'k_describe': 1922000 + 60000,
+# (k_describe: the 43 x 43 level patch of ~1000 keypoints + the outputs; the reference's blurred pyramid, 1 901 064 B written and read
+# back, is no longer materialised: the 7 x 7 blur is computed per patch inside k_describe)
+ALG_BYTES = {'k_resize x7': 1569878, 'k_fast_strips': 950532, 'k_describe': 1000 * 43 * 43 + 60000,
              'k_lsd_prep': 307200 + 16 * 512 * 384, 'k_plane_blocks': 614400 + 3072 * 96}
 # whole front-end: ORB 6 403 474 + LBD pre 2 150 400 + LBD gather 2 x 3 024 000 + LSD 3 452 928 + seed order / regions 2 359 296 +
 # planes 909 312 + membership 1 536 000 + normals 2 054 400
 ALG_BYTES_FRAME = 6403474 + 2150400 + 2 * 3024000 + 3452928 + 2359296 + 909312 + 1536000 + 2054400
 # dram__bytes_read.sum + dram__bytes_write.sum per frame of the same kernels, from this round's committed ncu capture
-# (profiles/r2_ncu_full_orb_kernels_b296.csv for the ORB kernels; profiles/r1d_* for the others, unchanged kernels)
-NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_strips': 968000, 'k_blur': 1997000, 'k_describe': 1965000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
+# (profiles/r2b_ncu_full_orb_kernels_b296.csv for the ORB kernels; profiles/r1d_* for the others, unchanged kernels)
+NCU_DRAM_BYTES = {'k_resize x7': 1555000, 'k_fast_strips': 968000, 'k_describe': 1102000, 'k_lsd_prep': 3592000, 'k_plane_blocks': 857000}
 
 
 def _gen(args):
@@ -245,7 +247,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--frames', type=int, default=C5_FRAMES, help='frames per step over all GPUs (default: the C5 sequence, 8192)')
-    ap.add_argument('--batch', type=int, default=CALL_FRAMES, help='frames per library call (default 2368 = 2 chunks of 1184)')
+    ap.add_argument('--batch', type=int, default=CALL_FRAMES, help='frames per library call (default 4096 = one chunk)')
     ap.add_argument('--stages', type=int, default=15, help='bit 0 ORB, 1 lines, 2 planes, 3 normals (profiling aid; the metric is 15)')
     ap.add_argument('--lanes', type=int, default=0, help='pipeline lanes of the frame handle (0 = library default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -284,12 +286,11 @@ def main():
     dev = torch.device('cuda', local_rank)
     d_gray = torch.from_numpy(gray).to(dev).repeat(reps, 1, 1)[:count].contiguous()
     d_depth = torch.from_numpy(depth.view(np.int16)).to(dev).repeat(reps, 1, 1)[:count].contiguous()
-    # A call that is smaller than two chunks (strong scaling at 8 GPUs: 1024 frames per rank and step) still gets two lanes of `call` frames:
-    # consecutive calls then alternate lanes, so the upload of call k + 1 and the download of call k - 1 run beside the kernels of call k.
-    two_small_lanes = args.lanes == 0 and call < 2048
+    # Two lanes of `call` frames each (the lanes share the pipelines' scratch; a lane is the input / output staging of one call in flight):
+    # consecutive calls alternate lanes, so the upload of call k + 1 and the download of call k - 1 run beside the kernels of call k.
+    nl = args.lanes if args.lanes > 0 else 2
     fe = hvo.FrameFrontEnd(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, bf=BF, n_lines=NLINES, stages=args.stages, line_cull=True,
-                           lanes=2 if two_small_lanes else args.lanes, membership='u4', normals='n3', max_planes=MAX_PLANES,
-                           max_batch=2 * call if two_small_lanes else call, device=local_rank,
+                           lanes=nl, membership='u4', normals='n3', max_planes=MAX_PLANES, max_batch=nl * call, device=local_rank,
                            nfeatures=ORB['nfeatures'], scale_factor=ORB['scale_factor'], nlevels=ORB['nlevels'], ini_th=ORB['ini_th'], min_th=ORB['min_th'])
     # one set of device outputs for a call, reused by every call of a step (the bench keeps no results)
     shapes = fe.output_shapes(call)
@@ -297,10 +298,18 @@ def main():
     d_ptrs = {k: v.data_ptr() for k, v in d_out.items()}
     torch.cuda.synchronize()
 
+    fe_open = [True]
+
+    def close_fe():
+        if fe_open[0]:
+            torch.cuda.synchronize()
+            fe.close()
+            fe_open[0] = False
+
     def teardown():
         # leave the device idle and release everything in a fixed order (handles before the process group)
         torch.cuda.synchronize()
-        fe.close()
+        close_fe()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -370,7 +379,7 @@ def main():
     roofline = None
     if not args.e2e_only:
         # ---- per-stage device times: every pipeline alone at the chunk size the frame handle runs (standalone handles) ----
-        Bs = min(count, CHUNK)
+        Bs = min(count, call)
         stage_ms, kern_ms = {}, {}
         ex = hvo.ORBextractor(ORB['nfeatures'], ORB['scale_factor'], ORB['nlevels'], ORB['ini_th'], ORB['min_th'], width=W, height=H,
                               max_batch=Bs, device=local_rank)
@@ -394,7 +403,7 @@ def main():
             for k, v in ex.stage_times().items():
                 acc[k] = acc.get(k, 0.0) + v / 5
         ex.close()
-        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_strips': acc['fast'], 'k_octree': acc['octree'], 'k_blur': acc['blur'], 'k_describe': acc['describe']})
+        kern_ms.update({'k_resize x7': acc['pyramid'], 'k_fast_strips': acc['fast'], 'k_octree': acc['octree'], 'k_describe': acc['describe']})
 
         le = hvo.LINEextractor(1, 1.2, NLINES, 0.125, width=W, height=H, max_batch=Bs, device=local_rank)
         le.set_culling(True)
@@ -457,7 +466,7 @@ def main():
         step_gbs = ALG_BYTES_FRAME * count / ((ms / args.steps) * 1e-3) / 1e9
         roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                         traffic=NCU_DRAM_BYTES[dom] * Bs, traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/'
-                        'r2_ncu_full_orb_kernels_b296.csv) x frames per launch',
+                        'r2b_ncu_full_orb_kernels_b296.csv) x frames per launch',
                         peak_source=peak_src, algorithmic_bytes_per_launch=ALG_BYTES[dom] * Bs, batch=Bs,
                         kernel_ms={k: round(v, 4) for k, v in kern_ms.items()},
                         frac_of_hbm={k: round(ALG_BYTES[k] * Bs / (kern_ms[k] * 1e-3) / 1e9 / peak, 4) for k in ALG_BYTES},
@@ -506,7 +515,7 @@ def main():
     e2e = dict(value=args.frames * e2e_steps / (e2e_ms * 1e-3), unit='frames/s',
                h2d_bytes_per_step=int(count * px * 3), d2h_bytes_per_step=int(count * out_bytes_frame), d2h_bytes_per_frame=int(out_bytes_frame),
                bytes_are='per GPU', ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
-               call='hvo_frame_extract_batch_async per 2368 frames + hvo_frame_timer_stop (pinned host buffers, two output sets alternating; outputs: '
+               call=f'hvo_frame_extract_batch_async per {call} frames + hvo_frame_timer_stop (pinned host buffers, two output sets alternating; outputs: '
                     'keypoints, descriptors, depth / uRight, keylines, LBD, line functions, planes, 4-bit plane labels, surface normals)',
                blocking_calls_value=args.frames * 2 / (e2e_blocking_ms * 1e-3))
 
@@ -529,10 +538,14 @@ def main():
     fe1.close()
 
     # ---- the other BASELINE.json configs (rank 0): device-resident throughput of C2 / C3, matching stress C4 ----
+    fe_lanes, fe_chunk = fe.lanes, fe.chunk
+    close_fe()                       # the C5 handle and its buffers make room for the C2 / C3 handles
+    del d_gray, d_depth, d_out
+    torch.cuda.empty_cache()
     configs = None
     if rank == 0 and not args.no_configs:
         configs = {}
-        for name, cfg, w2, h2, nfeat, nb in (('C2', 'S2', 640, 480, 1000, 1184), ('C3', 'S3', 1280, 720, 2000, 592)):
+        for name, cfg, w2, h2, nfeat, nb in (('C2', 'S2', 640, 480, 1000, 4096), ('C3', 'S3', 1280, 720, 2000, 2048)):
             c = synth.CONFIGS[cfg]
             g2, dp2 = make_frames(64, cfg=cfg)
             fe2 = hvo.FrameFrontEnd(w2, h2, c['fx'], c['fy'], c['cx'], c['cy'], 1.0 / c['factor'], bf=BF, n_lines=NLINES, line_cull=True, lanes=1,
@@ -660,8 +673,9 @@ def main():
             'config': {'workload': f'C5/C1: {args.frames} synthetic TUM-fr3-shaped 640x480 RGB-D frames per step (TUM3.yaml: ORB 1000 features 8 levels x1.2, '
                                    f'LINE 200), whole front-end of Frame::Frame, frame-sharded over {world} GPU(s) in contiguous ranges: {count} frames per GPU '
                                    f'per step ({n_distinct} distinct per GPU), {calls_per_step} call(s) of <= {call} frames',
-                       'stages': STAGES, 'frames_per_step': args.frames, 'frames_per_gpu': count, 'frames_per_call': call, 'lanes': fe.lanes,
-                       'chunk_frames': fe.chunk, 'mean_per_frame': means,
+                       'stages': STAGES, 'frames_per_step': args.frames, 'frames_per_gpu': count, 'frames_per_call': call, 'lanes': fe_lanes,
+                       'chunk_frames': fe_chunk, 'schedule': 'pipelines one after the other (planes, lines, ORB, normals)' if min(call, count) >= 2048 else 'pipelines side by side',
+                       'mean_per_frame': means,
                        'outputs': 'keypoints + descriptors + depth/uRight, keylines + LBD + line functions, planes + plane labels, surface normals',
                        'l2': f'inputs larger than L2: per-step inputs {count} x 0.92 MB and working set ~{min(count, call)} x 17 MB >> 126 MB'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'weak': weak, 'configs': configs, 'gpu_launches': launches_per_step * args.steps,
