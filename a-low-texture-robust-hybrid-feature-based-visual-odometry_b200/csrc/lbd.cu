@@ -25,7 +25,7 @@ __constant__ int8_t c_comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 2, 1, 3
                                   2, 8, 3, 4, 3, 5, 3, 6, 3, 7, 3, 8, 4, 5, 4, 6, 4, 7, 4, 8, 5, 6, 5, 7, 5, 8, 6, 7, 6, 8, 7, 8};
 
 __global__ void __launch_bounds__(256) k_lbd_grad(const uint8_t* __restrict__ gray, int w, int h, long long frame_px,
-                                                  int16_t* __restrict__ dx, int16_t* __restrict__ dy) {
+                                                  uint32_t* __restrict__ dxy) {
     __shared__ __align__(4) uint8_t raw[(kGH + 6) * (kGW + 8)];
     __shared__ uint16_t hb[(kGH + 6) * (kGW + 2)];
     __shared__ uint8_t bl[(kGH + 2) * (kGW + 4)];
@@ -78,8 +78,7 @@ __global__ void __launch_bounds__(256) k_lbd_grad(const uint8_t* __restrict__ gr
         const int gx = (p[-S + 1] - p[-S - 1]) + 2 * (p[1] - p[-1]) + (p[S + 1] - p[S - 1]);
         const int gy = (p[S - 1] - p[-S - 1]) + 2 * (p[S] - p[-S]) + (p[S + 1] - p[-S + 1]);
         const long long o = (long long)f * frame_px + (long long)y * w + x;
-        dx[o] = (int16_t)gx;
-        dy[o] = (int16_t)gy;
+        dxy[o] = ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16);   // dx | dy << 16: one load per visited pixel in k_lbd_describe
     }
 }
 
@@ -93,7 +92,7 @@ struct KeyLineDev {  // cv::line_descriptor::KeyLine POD, 68 bytes
     int numOfPixels;
 };
 
-__global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__ dxI, const int16_t* __restrict__ dyI, int w, int h,
+__global__ void __launch_bounds__(64) k_lbd_describe(const uint32_t* __restrict__ dxyI, int w, int h,
                                                      long long frame_px, const KeyLineDev* __restrict__ kls,
                                                      const int32_t* __restrict__ counts, int max_lines, LbdWeights W,
                                                      float* __restrict__ raw) {
@@ -101,8 +100,7 @@ __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__
     const int line = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     if (line >= counts[f]) return;
     const KeyLineDev kl = kls[(long long)f * max_lines + line];
-    const int16_t* dxp = dxI + (long long)f * frame_px;
-    const int16_t* dyp = dyI + (long long)f * frame_px;
+    const uint32_t* gp = dxyI + (long long)f * frame_px;
     const int len = (short)kl.numOfPixels;
     const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
     if (tid < kLbdH) {
@@ -115,12 +113,14 @@ __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__
         float sCorY = -dL1 * halfWidth - dL0 * halfHeight + midY;
         for (int k = 0; k < tid; ++k) { sCorX -= dL1; sCorY += dL0; }  // the reference advances the row origin by repeated addition
         float pL = 0, nL = 0, pO = 0, nO = 0;
+#pragma unroll 4
         for (int wID = 0; wID < len; ++wID) {
             int t = (int)(short)roundf(sCorX);
             const int xCor = t < 0 ? 0 : (t > imageWidth ? imageWidth : t);
             t = (int)(short)roundf(sCorY);
             const int yCor = t < 0 ? 0 : (t > imageHeight ? imageHeight : t);
-            const int gx = __ldg(dxp + yCor * w + xCor), gy = __ldg(dyp + yCor * w + xCor);
+            const uint32_t g2 = __ldg(gp + yCor * w + xCor);
+            const int gx = (int)(short)(g2 & 0xffffu), gy = (int)g2 >> 16;
             const float gDL = (float)gx * dL0 + (float)gy * dL1;
             const float gDO = (float)gx * dO0 + (float)gy * dO1;
             if (gDL > 0) pL += gDL; else nL -= gDL;
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__
         rows[tid][4] = pL * pL; rows[tid][5] = nL * nL; rows[tid][6] = pO * pO; rows[tid][7] = nO * nO;
     }
     __syncthreads();
-    if (tid < 72) {
+    for (int e = tid; e < 72; e += 64) {
         // band b, quantity q: rows contribute in increasing row order: rows of band b-1 (as "band below" of that row,
         // weight L[r % 7]), band b (L[r % 7 + 7]), band b+1 (as "band above", L[r % 7 + 14])
-        const int b = tid >> 3, q = tid & 7;
+        const int b = e >> 3, q = e & 7;
         float acc = 0;
         const int r0 = max(0, (b - 1) * kLbdBandW), r1 = min(kLbdH, (b + 2) * kLbdBandW);
         for (int r = r0; r < r1; ++r) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(96) k_lbd_describe(const int16_t* __restrict__
             acc += (q < 4) ? c * rows[r][q] : c * c * rows[r][q];
         }
         // the 72 band sums of this line; the serial normalisation runs lane-parallel over lines in k_lbd_finish
-        raw[((long long)f * max_lines + line) * 72 + tid] = acc;
+        raw[((long long)f * max_lines + line) * 72 + e] = acc;
     }
 }
 
@@ -220,7 +220,7 @@ struct hvo_lbd {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     LbdWeights W;
     uint8_t* d_gray = nullptr;
-    int16_t *d_dx = nullptr, *d_dy = nullptr;
+    uint32_t* d_dxy = nullptr;   // Sobel dx | dy << 16 of the blurred frame
     KeyLineDev* d_kl = nullptr;
     int32_t* d_counts = nullptr;
     uint8_t* d_desc = nullptr;
@@ -234,9 +234,9 @@ static int lbd_run_stream(hvo_lbd* h, cudaStream_t stream, const uint8_t* d_gray
     const long long fpx = (long long)h->width * h->height;
     timeline_mark(stream, "k_lbd_grad");
     k_lbd_grad<<<dim3(div_up(h->width, kGW), div_up(h->height, kGH), nframes), 256, 0, stream>>>(d_gray, h->width, h->height, fpx,
-                                                                                              h->d_dx, h->d_dy);
+                                                                                              h->d_dxy);
     timeline_mark(stream, "k_lbd_describe");
-    k_lbd_describe<<<dim3(h->max_lines, nframes), 96, 0, stream>>>(h->d_dx, h->d_dy, h->width, h->height, fpx, d_kl, d_counts,
+    k_lbd_describe<<<dim3(h->max_lines, nframes), 64, 0, stream>>>(h->d_dxy, h->width, h->height, fpx, d_kl, d_counts,
                                                                    h->max_lines, h->W, h->d_raw);
     timeline_mark(stream, "k_lbd_finish");
     k_lbd_finish<<<div_up(nframes * h->max_lines, 128), 128, 0, stream>>>(h->d_raw, d_counts, h->max_lines, nframes, d_desc, d_fdesc);
@@ -288,8 +288,7 @@ int hvo_lbd_create(int width, int height, int max_batch, int max_lines, int devi
         HVO_TRY(cudaEventCreate(&h->tev[1]));
         const size_t B = (size_t)max_batch, px = (size_t)width * height;
         HVO_TRY(cudaMalloc(&h->d_gray, B * px));
-        HVO_TRY(cudaMalloc(&h->d_dx, B * px * 2));
-        HVO_TRY(cudaMalloc(&h->d_dy, B * px * 2));
+        HVO_TRY(cudaMalloc(&h->d_dxy, B * px * 4));
         HVO_TRY(cudaMalloc(&h->d_kl, B * max_lines * sizeof(KeyLineDev)));
         HVO_TRY(cudaMalloc(&h->d_counts, B * sizeof(int32_t)));
         HVO_TRY(cudaMalloc(&h->d_desc, B * max_lines * 32));
@@ -306,7 +305,7 @@ void hvo_lbd_destroy(hvo_lbd* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_gray, h->d_dx, h->d_dy, h->d_kl, h->d_counts, h->d_desc, h->d_fdesc, h->d_raw};
+    void* bufs[] = {h->d_gray, h->d_dxy, h->d_kl, h->d_counts, h->d_desc, h->d_fdesc, h->d_raw};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -362,8 +361,9 @@ int hvo_lbd_get_gradients(hvo_lbd* h, int frame, int16_t* dx, int16_t* dy) {
     HVO_CHECK_ARG(frame >= 0 && frame < h->max_batch, "frame out of range");
     HVO_CUDA(cudaSetDevice(h->device));
     const size_t px = (size_t)h->width * h->height;
-    HVO_CUDA(cudaMemcpyAsync(dx, h->d_dx + frame * px, px * 2, cudaMemcpyDeviceToHost, h->stream));
-    HVO_CUDA(cudaMemcpyAsync(dy, h->d_dy + frame * px, px * 2, cudaMemcpyDeviceToHost, h->stream));
+    // the device keeps dx | dy << 16 per pixel: strided 2-byte copies split it
+    HVO_CUDA(cudaMemcpy2DAsync(dx, 2, reinterpret_cast<const char*>(h->d_dxy + frame * px), 4, 2, px, cudaMemcpyDeviceToHost, h->stream));
+    HVO_CUDA(cudaMemcpy2DAsync(dy, 2, reinterpret_cast<const char*>(h->d_dxy + frame * px) + 2, 4, 2, px, cudaMemcpyDeviceToHost, h->stream));
     HVO_CUDA(cudaStreamSynchronize(h->stream));
     return HVO_OK;
 }
