@@ -61,7 +61,7 @@ __device__ __forceinline__ void fastdiv(const FastDiv& f, int i, int& q, int& r)
 __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gray, int W, int H, long long frame_px, int sw, int sh,
                                                   const LinCoef* __restrict__ cx, const LinCoef* __restrict__ cy,
                                                   const float2* __restrict__ cstab, int sq_low_max, LsdPix* __restrict__ pix,
-                                                  uint8_t* __restrict__ scaled_out, int* __restrict__ maxsq) {
+                                                  uint8_t* __restrict__ scaled_out, int* __restrict__ maxsq, uint32_t* __restrict__ sqkey) {
     __shared__ __align__(4) uint8_t raw[kSrcH][kSrcW];
     __shared__ uint16_t hb[kSrcH][kSrcW];
     __shared__ uint8_t bl[kSrcH][kSrcW];
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
         if (x >= sw || y >= sh) continue;
         LsdPix p;
         p.ang = LSD_NOTDEF; p.c = 0.f; p.s = 0.f; p.gxgy = 0;
+        uint32_t key = 0u;   // gx^2 + gy^2 of a defined pixel, 0 otherwise: all k_lsd_order needs (4 instead of 16 bytes per pixel)
         if (x < sw - 1 && y < sh - 1) {
             const int DA = sc[r + 1][c + 1] - sc[r][c], BC = sc[r][c + 1] - sc[r + 1][c];
             const int gx = DA + BC, gy = DA - BC;
@@ -155,10 +156,12 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
                 const float2 cs = __ldg(&cstab[(gx + 510) * 1021 + (gy + 510)]);
                 p.c = cs.x; p.s = cs.y;
                 lmax = max(lmax, sq);
+                key = (uint32_t)sq;
             }
         }
         const long long o = (long long)f * sw * sh + (long long)y * sw + x;
         pix[o] = p;
+        sqkey[o] = key;
         if (scaled_out) scaled_out[o] = sc[r][c];
     }
 #pragma unroll
@@ -173,17 +176,19 @@ __global__ void __launch_bounds__(256) k_lsd_prep(const uint8_t* __restrict__ gr
 // max_grad), descending; scan order inside a bin.  (Undefined pixels are skipped by the seed loop, so they are not listed.)
 static const int kOrdWarps = 32, kBins = 1024;
 
-__device__ __forceinline__ int lsd_bin(const LsdPix& p, double bin_coef) {
-    const int gx = (int)(short)(p.gxgy & 0xffff), gy = p.gxgy >> 16;
-    return (int)(sqrt((double)(gx * gx + gy * gy) / 4.0) * bin_coef);
+// `key` (written by k_lsd_prep; the region buffer of k_lsd_grow, unused until then): gx^2 + gy^2 per defined pixel, 0 otherwise.  The
+// counting pass replaces it in place by bin + 1, which the scatter pass reads back: the 16-byte pixel records are not touched and the
+// double-precision square root runs once per pixel.
+__device__ __forceinline__ int lsd_bin(uint32_t sq, double bin_coef) {
+    return (int)(sqrt((double)(int)sq / 4.0) * bin_coef);
 }
 
-__global__ void __launch_bounds__(1024) k_lsd_order(const LsdPix* __restrict__ pix, int npix, const int* __restrict__ maxsq,
+__global__ void __launch_bounds__(1024) k_lsd_order(uint32_t* __restrict__ key, int npix, const int* __restrict__ maxsq,
                                                      uint32_t* __restrict__ order, int* __restrict__ norder) {
     extern __shared__ uint32_t hist[];  // [kOrdWarps][kBins]
     __shared__ uint32_t s_warp[32];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const LsdPix* P = pix + (long long)f * npix;
+    uint32_t* K = key + (long long)f * npix;
     uint32_t* out = order + (long long)f * npix;
     const int mq = maxsq[f];
     if (mq <= 0) { if (tid == 0) norder[f] = 0; return; }
@@ -192,9 +197,14 @@ __global__ void __launch_bounds__(1024) k_lsd_order(const LsdPix* __restrict__ p
     __syncthreads();
     const int seg = (npix + kOrdWarps - 1) / kOrdWarps, s0 = wid * seg, s1 = min(npix, s0 + seg);
     uint32_t* myh = hist + wid * kBins;
-    for (int i = s0 + lane; i < s1; i += 32) {
-        const LsdPix p = P[i];
-        if (p.ang != LSD_NOTDEF) atomicAdd(&myh[lsd_bin(p, bin_coef)], 1u);
+    // four loads in flight per lane: with one CTA per SM the passes are bound by memory-level parallelism, not by bandwidth
+    for (int i = s0 + lane; i < s1; i += 128) {
+        uint32_t q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = (i + 32 * u < s1) ? K[i + 32 * u] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q[u]) { const int bin = lsd_bin(q[u], bin_coef); atomicAdd(&myh[bin], 1u); K[i + 32 * u] = (uint32_t)bin + 1u; }
     }
     __syncthreads();
     {   // thread t owns bin (kBins-1-t): descending bins <-> ascending t
@@ -219,19 +229,24 @@ __global__ void __launch_bounds__(1024) k_lsd_order(const LsdPix* __restrict__ p
         for (int w = 0; w < kOrdWarps; ++w) hist[w * kBins + b] += base;
     }
     __syncthreads();
-    for (int i0 = s0; i0 < s1; i0 += 32) {
-        const int i = i0 + lane;
-        int bin = -1;
-        if (i < s1) { const LsdPix p = P[i]; if (p.ang != LSD_NOTDEF) bin = lsd_bin(p, bin_coef); }
-        const unsigned peers = __match_any_sync(kFull, bin);
-        uint32_t pos = 0;
-        if (bin >= 0) pos = myh[bin] + __popc(peers & ((1u << lane) - 1u));
-        __syncwarp();
-        if (bin >= 0) {
-            out[pos] = (uint32_t)i;
-            if ((int)(__ffs(peers) - 1) == lane) myh[bin] += __popc(peers);
+    for (int i0 = s0; i0 < s1; i0 += 128) {
+        int bins[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u + lane; bins[u] = (i < s1) ? (int)K[i] - 1 : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // scan order inside a bin: the four groups of 32 pixels go in order
+            const int bin = bins[u];
+            if (!__any_sync(kFull, bin >= 0)) continue;
+            const unsigned peers = __match_any_sync(kFull, bin);
+            uint32_t pos = 0;
+            if (bin >= 0) pos = myh[bin] + __popc(peers & ((1u << lane) - 1u));
+            __syncwarp();
+            if (bin >= 0) {
+                out[pos] = (uint32_t)(i0 + 32 * u + lane);
+                if ((int)(__ffs(peers) - 1) == lane) myh[bin] += __popc(peers);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -928,10 +943,10 @@ static int line_detect_device(hvo_line* h, const uint8_t* d_gray, int nframes) {
     timeline_mark(s, "k_lsd_prep");
     k_lsd_prep<<<dim3(div_up(h->sw, kPW), div_up(h->sh, kPH), nframes), 256, 0, s>>>(
         d_gray, h->width, h->height, (long long)h->width * h->height, h->sw, h->sh, h->d_cx, h->d_cy, h->d_cstab, h->sq_low_max, h->d_pix,
-        h->d_scaled, h->d_maxsq);
+        h->d_scaled, h->d_maxsq, h->d_reg);
     if (h->profiling) cudaEventRecord(h->sev[1], s);
     timeline_mark(s, "k_lsd_order");
-    k_lsd_order<<<nframes, 1024, kOrdWarps * kBins * sizeof(uint32_t), s>>>(h->d_pix, npix, h->d_maxsq, h->d_order, h->d_norder);
+    k_lsd_order<<<nframes, 1024, kOrdWarps * kBins * sizeof(uint32_t), s>>>(h->d_reg, npix, h->d_maxsq, h->d_order, h->d_norder);
     if (h->profiling) cudaEventRecord(h->sev[2], s);
     timeline_mark(s, "k_lsd_grow");
     k_lsd_grow<<<nframes, 32, 0, s>>>(h->d_pix, h->sw, h->sh, h->d_order, h->d_norder, h->d_reg, h->min_reg_size, h->prec, 0.7, 0.8,
