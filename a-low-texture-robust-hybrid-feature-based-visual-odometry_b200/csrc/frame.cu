@@ -136,13 +136,14 @@ static hvo_frame_outputs outputs_at(const hvo_frame* h, const hvo_frame_outputs&
 // them slower (4736 frames: 16.2 K frames/s side by side, 18.2 K one after the other; ORB / normals beside the ordered kernels:
 // 16.5-17.3 K).  So a chunk of >= kSerialFrames frames runs its pipelines ONE AFTER THE OTHER (planes, lines, ORB, normals), each at
 // its saturating batch, and the download of a pipeline's results runs beside the kernels of the next one.
-// HVO_FRAME_SERIAL=0 / 1 forces one schedule (tuning aid).
+// HVO_FRAME_SERIAL=0 / 1 forces one schedule (tuning aid).  Also measured for 1024-frame chunks and rejected: planes || lines first and
+// ORB || normals afterwards (87 instead of 65-79 ms), a third priority level that puts planes above lines (no change).
 static const int kSerialFrames = 2048;
 static int lane_launch(hvo_frame* h, FrameLane& L, cudaEvent_t start, cudaEvent_t start_depth, const uint8_t* d_gray, const uint16_t* d_depth, int n,
                        int base, const hvo_frame_outputs& o, const hvo_frame_outputs* host, int* launches, FrameLane* after = nullptr) {
     const size_t N = (size_t)n, px = (size_t)h->width * h->height;
     static const int serial_env = [] { const char* e = getenv("HVO_FRAME_SERIAL"); return e ? atoi(e) : -1; }();
-    const bool serial = serial_env >= 0 ? serial_env != 0 : n >= kSerialFrames;
+    const bool serial = serial_env >= 0 ? serial_env == 1 : n >= kSerialFrames;
     // side by side on one lane: every pipeline stream is already in order behind its own previous chunk
     if (after == &L && !serial) after = nullptr;
     cudaEvent_t prev_done = nullptr;   // serial schedule: the pipeline launched before this one

@@ -751,12 +751,12 @@ __global__ void __launch_bounds__(32, HVO_AHC_MINBLOCKS) k_plane_cluster(AhcArgs
 #endif
 // visits per step = 4 * threads; a visit's rank inside the step takes kFloodPosBits bits of the tournament word, 4 buckets per visit
 static const int kFloodThreads = HVO_FLOOD_THREADS;
-static const int kFloodPosBits = kFloodThreads == 256 ? 10 : (kFloodThreads == 512 ? 11 : 12);
+static const int kFloodPosBits = kFloodThreads == 128 ? 9 : (kFloodThreads == 256 ? 10 : (kFloodThreads == 512 ? 11 : 12));
 // Two hash tables of 2 buckets per visit each: a visit goes when it holds the bucket of its pixel in EITHER table.  Visits of one pixel
 // share their bucket in both tables, so only the earliest pending one can hold either; a visit of another pixel blocks it falsely only if it
 // collides in both (a few percent instead of ~ 20 % with one table of the same total size): 4.2 -> fewer tournament rounds per step.
 static const int kFloodBuckets = 4 << kFloodPosBits, kFloodHashShift = 32 - (kFloodPosBits + 1);
-static_assert(kFloodThreads == 256 || kFloodThreads == 512 || kFloodThreads == 1024, "flood CTA size");
+static_assert(kFloodThreads == 128 || kFloodThreads == 256 || kFloodThreads == 512 || kFloodThreads == 1024, "flood CTA size");
 
 struct FloodPix { double px, py, z; };
 // (double)v for a 16-bit value without the conversion pipe: 2^52 + v is exact, subtracting 2^52 gives v

@@ -253,6 +253,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip the C2 / C3 / C4 sub-records')
     ap.add_argument('--device-only', action='store_true', help='profiling aid: only the device-resident loop')
+    ap.add_argument('--as-shard', default='', help='profiling aid: R/W = process the range rank R of W would get (single process)')
     ap.add_argument('--e2e-only', action='store_true', help='profiling aid: skip the per-stage passes, the latency probe and the CPU baseline')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -273,15 +274,18 @@ def main():
     W, H = 640, 480
     px = W * H
     first, count = shard(args.frames, world, rank)            # this rank's contiguous range of the sequence
+    if args.as_shard and world == 1:
+        first, count = shard(args.frames, int(args.as_shard.split('/')[1]), int(args.as_shard.split('/')[0]))
     call = min(args.batch, count)
     # distinct synthetic frames of this rank's range (seeds 1000 + first ...): up to 1024, repeated to fill the range.  Generated
     # (forked worker pool) before this process touches CUDA or NCCL.
     n_distinct = min(count, 1024)
     gray, depth = make_frames(n_distinct, start=first)
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 or os.environ.get('HVO_BENCH_FORCE_DIST'):   # (the switch: profiling aid, a process group of one)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        os.environ.setdefault('MASTER_PORT', '29540')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), rank=rank, world_size=world)
     reps = (count + n_distinct - 1) // n_distinct
     dev = torch.device('cuda', local_rank)
     d_gray = torch.from_numpy(gray).to(dev).repeat(reps, 1, 1)[:count].contiguous()
@@ -340,18 +344,32 @@ def main():
         step_device()
     fe.sync()
     clocks = ClockSampler(local_rank)
-    if rank == 0:  # one sampler per job (rank 0's GPU): N concurrent nvidia-smi loops would only load the driver
+    if rank == 0 and not os.environ.get('HVO_BENCH_NO_CLOCKS'):  # one sampler per job (rank 0's GPU): N concurrent nvidia-smi loops would only load the driver
         clocks.start()
     time.sleep(0.25)
     barrier()
     t0 = time.time()
+    if os.environ.get('HVO_BENCH_TIMELINE'):   # profiling aid: per-stream kernel start times of the timed steps (hvo_timeline_*)
+        hvo.timeline(True)
     fe.timer_start()
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - th0) / args.steps   # host time to queue one step (the device runs behind)
     ms = fe.timer_stop()
+    if os.environ.get('HVO_BENCH_TIMELINE'):
+        by = {}
+        for t, s_, n_ in hvo.timeline_dump():
+            by.setdefault(s_, []).append((t, n_))
+        hvo.timeline(False)
+        with open(os.path.join(ROOT, 'gpurun_out', f'timeline_rank{rank}.txt'), 'w') as fh:
+            fh.write(f'rank {rank}/{world}: {ms / args.steps:.2f} ms/step\n')
+            for s_ in sorted(by):
+                fh.write(f'stream {s_}: ' + '  '.join(f'{n_}@{t:.1f}' for t, n_ in by[s_]) + '\n')
     t1 = time.time()
     barrier()
     clk = clocks.stop(t0, t1)
+    ms_rank = ms
     ms = max_over_ranks(ms)
     calls_per_step = (count + call - 1) // call
     launches_per_step = fe.last_launches() * calls_per_step
@@ -359,7 +377,7 @@ def main():
     means = dict(keypoints=d_counts('kp_counts'), lines=d_counts('line_counts'), planes=d_counts('n_planes'))
 
     if args.device_only:
-        emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'device_only': True, 'frames_per_step': args.frames,
+        emit({'metric': METRIC, 'value': value, 'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'rank': rank, 'ms_per_step_this_rank': ms_rank / args.steps, 'host_enqueue_ms_per_step': host_enqueue_ms, 'device_only': True, 'frames_per_step': args.frames,
               'stages': args.stages, 'lanes': fe.lanes, 'chunk': fe.chunk, 'means': means})
         teardown()
         return
@@ -440,10 +458,16 @@ def main():
         kern_ms['k_plane_blocks'] = pd.timer_stop() / 5
         cyc = pd.phase_cycles(0)
         rest = stage_ms['planes'] - kern_ms['k_plane_blocks']
-        tot_c = float(sum(cyc.values())) or 1.0
-        kern_ms['k_plane_cluster'] = rest * cyc.get('cluster', 0) / tot_c       # split of the ordered chain by its own cycle counters (frame 0)
-        kern_ms['k_plane_flood'] = rest * (cyc.get('seeds', 0) + cyc.get('flood', 0)) / tot_c
-        kern_ms['k_plane_merge + k_plane_relabel'] = rest * cyc.get('merge_relabel', 0) / tot_c
+        # split of the ordered chain by its own cycle counters (frame 0) x the waves each kernel needs for Bs frames: k_plane_cluster keeps
+        # 16 frames resident per SM (one warp each, 128 registers), k_plane_flood 4 (one CTA of 256 each), the last merge 16; the ncu launch
+        # list of the same chunk (profiles/r2b_launch_summary.txt) gives the same split
+        waves = lambda per_sm: -(-Bs // (per_sm * 148))
+        wc = dict(cluster=cyc.get('cluster', 0) * waves(16), flood=(cyc.get('seeds', 0) + cyc.get('flood', 0)) * waves(4),
+                  merge=cyc.get('merge_relabel', 0) * waves(16))
+        tot_c = float(sum(wc.values())) or 1.0
+        kern_ms['k_plane_cluster'] = rest * wc['cluster'] / tot_c
+        kern_ms['k_plane_flood'] = rest * wc['flood'] / tot_c
+        kern_ms['k_plane_merge + k_plane_relabel'] = rest * wc['merge'] / tot_c
         pd.close()
 
         sn = hvo.SurfaceNormals(W, H, CAM['fx'], CAM['fy'], CAM['cx'], CAM['cy'], DEPTH_FACTOR, max_batch=Bs, device=local_rank)

@@ -557,8 +557,12 @@ typedef struct hvo_frame_params {
     int stages;           /* HVO_STAGE_* bits */
     int max_planes;       /* rows of planes7 per frame */
     int line_cull;        /* != 0: Frame::cullingLine after the line extractor, as Frame::ExtractLSD does (src/Frame.cc:939) */
-    int lanes;            /* 0 = default.  The handle splits a batch into chunks that go round-robin through `lanes` independent
-                             copies of the three pipelines, so uploads, kernels and downloads of different chunks overlap. */
+    int lanes;            /* 0 = default (2 from max_batch 2048 on, else 1).  The handle splits a batch into chunks of max_batch / lanes
+                             frames that go round-robin through `lanes` sets of input / output staging (upload stream, one download
+                             stream per pipeline), so uploads, kernels and downloads of different chunks overlap.  The pipelines'
+                             own scratch exists once (chunk-sized): the kernels of consecutive chunks run one after the other.
+                             A chunk of >= 2048 frames runs its pipelines one after the other (planes, lines, ORB, normals), each
+                             alone at its saturating batch; smaller chunks run them side by side (lowest latency). */
 } hvo_frame_params;
 
 /* Output arrays of a batch of n frames.  Host pointers for hvo_frame_extract_batch, device pointers for

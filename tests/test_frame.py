@@ -144,6 +144,46 @@ def test_gpu_frame_async_calls_overlap_and_equal_blocking(hvo, synth):
     fe.close()
 
 
+_SERIAL_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import hvo_b200 as hvo
+from hvo_b200 import synth
+c = synth.CONFIGS['S1']
+gray, depth = synth.sequence('S1', 5, start=23)
+fe = hvo.FrameFrontEnd(640, 480, c['fx'], c['fy'], c['cx'], c['cy'], 1.0 / c['factor'], bf=40.0, max_batch=4, lanes=2, line_cull=True, membership='u8')
+a = fe.extract_batch(gray, depth)          # 5 frames through 2 lanes of 2: three chunks, lanes alternate
+b = fe.extract_batch(gray[:3], depth[:3])  # the next call starts on the other lane
+fe.close()
+np.savez(sys.argv[2], **{'a_' + k: v for k, v in a.items()}, **{'b_' + k: v for k, v in b.items()})
+"""
+
+
+@pytest.mark.gpu
+def test_gpu_frame_serial_schedule_equals_side_by_side(hvo, synth, tmp_path):
+    """Chunks of >= 2048 frames run their pipelines one after the other (planes, lines, ORB, normals) with the downloads on the lane's
+    own streams and the depth uploaded ahead of the gray image; HVO_FRAME_SERIAL=1 forces that schedule on a small batch (the switch
+    is read once per process, hence the child process).  Every output must equal the side-by-side schedule's."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ('0', '1'):
+        out = str(tmp_path / f'serial{mode}.npz')
+        env = dict(os.environ, HVO_FRAME_SERIAL=mode)
+        subprocess.run([sys.executable, '-c', _SERIAL_SCRIPT, root, out], check=True, env=env, timeout=600)
+        res[mode] = np.load(out)
+    for pre, n in (('a_', 5), ('b_', 3)):
+        a = {k[2:]: res['0'][k] for k in res['0'].files if k.startswith(pre)}
+        b = {k[2:]: res['1'][k] for k in res['1'].files if k.startswith(pre)}
+        _same_outputs(hvo, a, b, n)
+        assert np.array_equal(a['membership8'], b['membership8'])
+    fx, fy, cx, cy, df = _cam(synth, 'S1')
+    gray, depth = synth.sequence('S1', 5, start=23)
+    ok, od = oracle.OrbOracle().extract(gray[4])   # and the child's outputs are the real thing, not two equal failures
+    n = int(res['1']['a_kp_counts'][4])
+    assert n == len(ok) and np.array_equal(res['1']['a_desc'][4, :n], od)
+
+
 @pytest.mark.gpu
 def test_gpu_frame_reports_device_side_overflow(hvo, synth, monkeypatch):
     """The pipelines' fixed-capacity buffers cannot overflow by construction; HVO_DEBUG_* shrinks two of them so that the
