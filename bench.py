@@ -99,6 +99,30 @@ def make_frames(n, start=0, cfg='S1'):
     return gray, depth
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """N > 1: run this rank on the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers are allocated, so that the
+    pages the copy engines read and write (first touch) and the thread that queues the copies sit on the GPU's own NUMA node; eight
+    ranks then do not funnel 8 x 1.3 MB per frame through one socket's memory.  Returns the CPU list, or None where NVML / the
+    affinity call is unavailable or the box has one node (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index), (ncpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(set(cpus) & allowed)
+        if not cpus or len(cpus) >= len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:   # a placement hint must never take the bench down
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -281,6 +305,7 @@ def main():
     # (forked worker pool) before this process touches CUDA or NCCL.
     n_distinct = min(count, 1024)
     gray, depth = make_frames(n_distinct, start=first)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1 or os.environ.get('HVO_BENCH_FORCE_DIST'):   # (the switch: profiling aid, a process group of one)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
@@ -538,7 +563,7 @@ def main():
     out_bytes_frame = sum(v.nbytes for v in outs[0].values()) // call
     e2e = dict(value=args.frames * e2e_steps / (e2e_ms * 1e-3), unit='frames/s',
                h2d_bytes_per_step=int(count * px * 3), d2h_bytes_per_step=int(count * out_bytes_frame), d2h_bytes_per_frame=int(out_bytes_frame),
-               bytes_are='per GPU', ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
+               bytes_are='per GPU', host_cpus=(f'{len(numa)} CPUs local to the GPU (NVML affinity)' if numa else 'unbound'), ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
                call=f'hvo_frame_extract_batch_async per {call} frames + hvo_frame_timer_stop (pinned host buffers, two output sets alternating; outputs: '
                     'keypoints, descriptors, depth / uRight, keylines, LBD, line functions, planes, 4-bit plane labels, surface normals)',
                blocking_calls_value=args.frames * 2 / (e2e_blocking_ms * 1e-3))
