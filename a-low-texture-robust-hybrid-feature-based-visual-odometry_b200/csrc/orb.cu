@@ -1,13 +1,14 @@
 // ORB extractor kernels for sm_100a (B200).  From-scratch design, batched over frames:
 //
-//   k_resize      x(nlevels-1)  fixed-point bilinear pyramid, bit-exact with cv::resize INTER_LINEAR 8U
-//                               (reference ORBextractor.cc:1105-1130)
+//   k_resize_tile x(nlevels-1)  fixed-point bilinear pyramid, bit-exact with cv::resize INTER_LINEAR 8U
+//                               (reference ORBextractor.cc:1105-1130); k_resize = the general fallback
+//                               (pyramid factors > ~1.3, unaligned level 0)
 //   k_fast_strips x1            one CTA per row of reference FAST cells: FAST-9/16 strength, cell-local NMS,
 //                               per-cell threshold fallback (ORBextractor.cc:763-826) - no score map in HBM
 //   k_octree      x1            one CTA per (frame, level): DistributeOctTree (ORBextractor.cc:537-761)
 //                               with parallel key partitioning and the std::list order emulated exactly
-//   k_describe    x1            one warp per keypoint: IC_Angle (.cc:75-102), on-the-fly 7x7 Q8 Gaussian
-//                               of the 37x37 patch (.cc:1083-1084), steered rBRIEF-256 (.cc:106-144),
+//   k_describe    x1            one warp per keypoint: IC_Angle (.cc:75-102), 7x7 Q8 Gaussian of the 37x37
+//                               patch in shared memory (.cc:1083-1084), steered rBRIEF-256 (.cc:106-144),
 //                               KeyPoint assembly (.cc:835-846,1093-1099), RGB-D depth lookup
 //                               (Frame.cc:1940-1961) - no blurred pyramid in HBM
 //
