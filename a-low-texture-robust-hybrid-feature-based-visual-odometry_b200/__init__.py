@@ -104,6 +104,7 @@ ABI = {
     'hvo_proj_features_in_area': (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
     'hvo_proj_search': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, C.POINTER(C.c_int)]),
     'hvo_proj_set_level_sigma': (C.c_int, [_vp, _vp, C.c_int]),
+    'hvo_proj_set_window_origin': (C.c_int, [_vp, C.c_float, C.c_float]),
     'hvo_proj_last_rounds': (C.c_int, [_vp]),
     'hvo_proj_last_launches': (C.c_int, [_vp]),
     'hvo_proj_match_candidates': (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
@@ -1174,6 +1175,21 @@ class LSDmatcher:
         out = np.where(ok, m12, -1).astype(np.int32)
         return int(ok.sum()), out
 
+    def SearchDoubleKF(self, ldesc_kf, has_mapline, ldesc_cur):
+        """LSDmatcher::SearchDouble(KeyFrame *KF, Frame &CurrentFrame) (src/LSDmatcher.cpp:865-901): FrameBFMatch in both directions; a
+        current-frame line i whose match j agrees (tempMatches1[j] == i) receives the key frame's MapLine j when it holds one.
+        Returns (nmatches, match [len(ldesc_cur)] = key-frame line or -1)."""
+        out = np.full(len(ldesc_cur), -1, np.int32)
+        if len(ldesc_kf) == 0 or len(ldesc_cur) == 0:
+            return 0, out
+        m12 = self.FrameBFMatch(ldesc_kf, ldesc_cur, self.TH_LOW)
+        m21 = self.FrameBFMatch(ldesc_cur, ldesc_kf, self.TH_LOW)
+        has = np.asarray(has_mapline, bool)
+        for i, j in enumerate(m21):
+            if j >= 0 and m12[j] == i and has[j]:
+                out[i] = j
+        return int((out >= 0).sum()), out
+
     def SearchByDescriptor(self, ldesc_kf, ldesc_cur, has_mapline=None):
         """Matching part of LSDmatcher::SearchByDescriptor(pKF, currentF, vpMapLineMatches) (src/LSDmatcher.cpp:522-559): knn-2 of
         the key frame's descriptors in the current frame, accepted when d0 / d1 < 1 / 1.5 AND the key-frame line holds a MapLine
@@ -1279,13 +1295,17 @@ class ProjectionMatcher:
         except Exception:
             pass
 
-    def set_frame(self, keys_un, uright, desc, min_x, min_y, max_x, max_y):
+    def set_frame(self, keys_un, uright, desc, min_x, min_y, max_x, max_y, window_origin=None):
+        """window_origin = (mnMinX, mnMinY) of a KeyFrame (integers, include/KeyFrame.h:249-252): KeyFrame::GetFeaturesInArea locates its
+        windows from them in the cells the Frame assigned with the float bounds (hvo_proj_set_window_origin)."""
         keys = np.ascontiguousarray(keys_un, KP_DTYPE)
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
         ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
         self.n = len(keys)
         _check(lib().hvo_proj_set_frame(self._h, _np_ptr(keys), _np_ptr(ur) if ur is not None else None, _np_ptr(desc), self.n,
                                         float(min_x), float(min_y), float(max_x), float(max_y)))
+        if window_origin is not None:
+            _check(lib().hvo_proj_set_window_origin(self._h, float(window_origin[0]), float(window_origin[1])))
 
     def grid(self):
         """(cell_start [64*48+1], cell_items): cell ix*48+iy lists mGrid[ix][iy]."""
@@ -1433,6 +1453,13 @@ class ORBmatcher:
         b = F['bounds']
         self._pm.set_frame(F['keys_un'], F.get('uright'), F['desc'], b[0], b[1], b[2], b[3])
 
+    def _set_keyframe(self, KF, with_uright):
+        """A key frame searched in: the grid of its Frame (float bounds), windows located from the key frame's integer origin
+        (src/KeyFrame.cc:627-666); KF['bounds'] are the Frame's float bounds."""
+        b = KF['bounds']
+        self._pm.set_frame(KF['keys_un'], KF.get('uright') if with_uright else None, KF['desc'], b[0], b[1], b[2], b[3],
+                           window_origin=(int(b[0]), int(b[1])))
+
     def SearchByProjection(self, F, MPs, th=1.0):
         """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:45-132).  Updates F['mappoint']
         and F['claimed'] in place, returns (nmatches, match [M] keypoint index or -1)."""
@@ -1513,6 +1540,45 @@ class ORBmatcher:
                         nm -= 1
         i1 = np.nonzero(m12 >= 0)[0]
         return nm, np.stack([i1, m12[i1]], axis=1).astype(np.int32)
+
+    def SearchByBoWKF(self, KF1, KF2):
+        """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:531-666).  KFi = dict(desc, keys_un, featvec, has_mappoint [N] bool
+        (map point present and not bad)).  Candidates of a node = pKF2's features of that node that hold a good map point; accepted when
+        bestDist1 < TH_LOW (strict) and best < ratio * second; a matched pKF2 feature is skipped by later queries.
+        Returns (nmatches, match12 [N1] = pKF2 feature whose map point pKF1's feature is matched to, or -1)."""
+        qi, off, cand = self.bow_queries(KF1['featvec'], KF2['featvec'], np.asarray(KF1['has_mappoint'], bool))
+        m12 = np.full(len(KF1['desc']), -1, np.int32)
+        if len(qi) == 0:
+            return 0, m12
+        good2 = np.asarray(KF2['has_mappoint'], bool)
+        off2, cand2 = [0], []
+        for a, b in zip(off[:-1], off[1:]):
+            seg = cand[a:b]
+            cand2.extend(seg[good2[seg]]); off2.append(len(cand2))
+        idx, _, nm = self._pm.search_candidates(np.asarray(KF1['desc'], np.uint8)[qi], KF2['desc'], np.asarray(off2, np.int32),
+                                                np.asarray(cand2, np.int32), self.TH_LOW - 1, self.mfNNratio)
+        hist = [[] for _ in range(self.HISTO_LENGTH)]
+        factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+        for k, i in zip(qi, idx):
+            if i < 0:
+                continue
+            m12[k] = i
+            if self.mbCheckOrientation:
+                rot = np.float32(KF1['keys_un']['angle'][k]) - np.float32(KF2['keys_un']['angle'][i])
+                if rot < 0.0:
+                    rot = np.float32(rot + np.float32(360.0))
+                b = int(np.floor(float(np.float32(rot * factor)) + 0.5))  # round(): rot >= 0 here
+                if b == self.HISTO_LENGTH:
+                    b = 0
+                hist[b].append(k)
+        if self.mbCheckOrientation:
+            keepb = set(self.ComputeThreeMaxima([len(h) for h in hist]))
+            for b in range(self.HISTO_LENGTH):
+                if b not in keepb:
+                    for k in hist[b]:
+                        m12[k] = -1
+                        nm -= 1
+        return nm, m12
 
     def SearchByBoW(self, KF, F):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:162-293).
@@ -1646,7 +1712,7 @@ class ORBmatcher:
         q['u'] = MPs['u']; q['v'] = MPs['v']; q['ur'] = MPs['ur']
         q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
         q['min_level'] = lvl - 1; q['max_level'] = lvl
-        self._set_frame(KF)
+        self._set_keyframe(KF, True)
         self._pm.set_level_sigma(KF['inv_level_sigma2'])
         idx, _, nm = self._pm.search(q, MPs['desc'], None, 2, self.TH_LOW, self.mfNNratio)
         return nm, idx.copy()
@@ -1661,8 +1727,7 @@ class ORBmatcher:
         q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1
         q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
         q['min_level'] = lvl - 1; q['max_level'] = lvl
-        b = KF['bounds']
-        self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+        self._set_keyframe(KF, False)
         idx, _, nm = self._pm.search(q, pts['desc'], None, 1, self.TH_LOW, self.mfNNratio)
         return nm, idx.copy()
 
@@ -1678,8 +1743,7 @@ class ORBmatcher:
             q['u'] = pts['u']; q['v'] = pts['v']; q['ur'] = -1
             q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
             q['min_level'] = lvl - 1; q['max_level'] = lvl
-            b = KF['bounds']
-            self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+            self._set_keyframe(KF, False)
             return self._pm.search(q, pts['desc'], None, 1, self.TH_HIGH, self.mfNNratio)[0]
         m1 = np.full(len(KF1['desc']), -1, np.int32); m2 = np.full(len(KF2['desc']), -1, np.int32)
         if len(pts1in2['u']):
@@ -1701,8 +1765,7 @@ class ORBmatcher:
         q['r'] = (np.float32(th) * np.asarray(KF['scale_factors'], np.float32)[lvl]).astype(np.float32)
         q['min_level'] = lvl - 1; q['max_level'] = lvl
         q['claims'] = 1
-        b = KF['bounds']
-        self._pm.set_frame(KF['keys_un'], None, KF['desc'], b[0], b[1], b[2], b[3])
+        self._set_keyframe(KF, False)
         idx, _, nm = self._pm.search(q, pts['desc'], np.asarray(matched, np.uint8), 1, self.TH_LOW, self.mfNNratio)
         matched[idx[idx >= 0]] = True
         return nm, idx.copy()

@@ -481,7 +481,8 @@ struct hvo_proj {
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[2] = {nullptr, nullptr};
     int n = 0, kcap = 0, qcap = 0, ccap = 0;
-    GridGeom g{0, 0, 0, 0};
+    GridGeom g{0, 0, 0, 0};    // geometry the cells were built with (Frame::AssignFeaturesToGrid)
+    GridGeom gw{0, 0, 0, 0};   // geometry of the window lookups: = g, or with KeyFrame's integer origin (hvo_proj_set_window_origin)
     hvo_keypoint* d_keys = nullptr;
     float* d_uright = nullptr;
     uint8_t* d_desc = nullptr;
@@ -595,6 +596,7 @@ int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* ur
     h->g.min_x = min_x; h->g.min_y = min_y;
     h->g.inv_w = (float)kGridCols / (max_x - min_x);   // Frame.cc:419-420
     h->g.inv_h = (float)kGridRows / (max_y - min_y);
+    h->gw = h->g;
     if (n > 0) {
         HVO_CUDA(cudaMemcpyAsync(h->d_keys, keys_un, (size_t)n * sizeof(hvo_keypoint), cudaMemcpyHostToDevice, h->stream));
         if (uright) HVO_CUDA(cudaMemcpyAsync(h->d_uright, uright, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -603,6 +605,12 @@ int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* ur
     k_proj_grid<<<1, 1024, 0, h->stream>>>(h->d_keys, uright ? h->d_uright : nullptr, n, h->g, h->d_pk, h->d_cell_start, h->d_cell_items, h->d_cell_of);
     HVO_CUDA(cudaGetLastError());
     h->last_launches = 1;
+    return HVO_OK;
+}
+
+int hvo_proj_set_window_origin(hvo_proj* h, float min_x, float min_y) {
+    HVO_CHECK_ARG(h, "null handle");
+    h->gw.min_x = min_x; h->gw.min_y = min_y;   // cells stay as built (h->g); inv_w / inv_h are the frame's (KeyFrame copies them, KeyFrame.cc:47-48)
     return HVO_OK;
 }
 
@@ -623,7 +631,7 @@ int hvo_proj_features_in_area(hvo_proj* h, float x, float y, float r, int min_le
     HVO_CUDA(cudaSetDevice(h->device));
     *n_out = 0;
     if (h->n == 0) return HVO_OK;
-    k_proj_area<<<1, 32, 0, h->stream>>>(h->d_pk, h->d_cell_start, h->d_cell_items, h->g, x, y, r, min_level, max_level, h->d_area, h->kcap,
+    k_proj_area<<<1, 32, 0, h->stream>>>(h->d_pk, h->d_cell_start, h->d_cell_items, h->gw, x, y, r, min_level, max_level, h->d_area, h->kcap,
                                           h->d_flag);
     HVO_CUDA(cudaGetLastError());
     HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -652,7 +660,7 @@ static int proj_run_rounds(hvo_proj* h, int nq, const uint8_t* claimed, int mode
         HVO_CUDA(cudaMemcpyAsync(next, h->d_claim0, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
         HVO_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
         k_proj_round<<<div_up(nq * 32, 128), 128, 0, s>>>(h->d_pk, reinterpret_cast<const uint4*>(h->d_desc), h->d_cell_start, h->d_cell_items,
-                                                          h->g, h->d_q, reinterpret_cast<const uint4*>(h->d_qdesc), nq, prev, next, mode, th_dist,
+                                                          h->gw, h->d_q, reinterpret_cast<const uint4*>(h->d_qdesc), nq, prev, next, mode, th_dist,
                                                           nnratio, h->d_inv_sigma2, h->d_choice, h->d_cdist, h->d_flag);
         HVO_CUDA(cudaGetLastError());
         HVO_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -14,6 +14,9 @@
 //   matchNNR / match                                       src/LSDmatcher.cpp:803-863
 //   FrameBFMatch (knn-2 + MAD gates)                       src/LSDmatcher.cpp:942-966, lineDescriptorMAD :1110-1135
 //   FrameBFMatchNew (knn-2 + epipolar overlap)             src/LSDmatcher.cpp:968-1031
+//   SearchByDescriptor(pKF, currentF, vpMapLineMatches)    src/LSDmatcher.cpp:522-559   (KeyFrame type deduced: mLineDescriptors, GetMapLineMatches())
+//   SearchDouble(InitialFrame, CurrentFrame, LineMatches)  src/LSDmatcher.cpp:903-940   (FrameBFMatch both ways + cross-check)
+//   SearchDouble(KF, CurrentFrame)                         src/LSDmatcher.cpp:865-901   (KF->NL, mLineDescriptors, GetMapLine())
 //   DescriptorDistance                                     src/LSDmatcher.cpp:1137-1153
 #ifndef HVO_SHIM_LSDMATCHER_H
 #define HVO_SHIM_LSDMATCHER_H
@@ -122,6 +125,70 @@ public:
             const float d0 = (float)dist[2 * i], d1 = (float)dist[2 * i + 1];
             if ((double)gap[i] > nn12_dist_th && d0 < TH && d0 < mfNNratio * d1) LineMatches[i] = idx[2 * i];
         }
+    }
+
+    // src/LSDmatcher.cpp:522-559: knn-2 of the key frame's line descriptors in the frame's, ratio d0 / d1 < 1 / 1.5; a frame line receives the
+    // MapLine of the key-frame line (later key-frame lines overwrite earlier ones, key-frame lines without a MapLine are skipped).
+    // (The reference also calls currentF.lineDescriptorMAD here; its results are not used.)
+    template <class KeyFrame>
+    int SearchByDescriptor(KeyFrame* pKF, Frame& currentF, std::vector<MapLine*>& vpMapLineMatches) {
+        const std::vector<MapLine*> vpMapLinesKF = pKF->GetMapLineMatches();
+        vpMapLineMatches = std::vector<MapLine*>(currentF.NL, static_cast<MapLine*>(NULL));
+        int nmatches = 0;
+        std::vector<int32_t> idx, dist;
+        const int n = pKF->mLineDescriptors.rows;
+        if (n == 0 || currentF.mLdesc.rows < 2 || !knn2(pKF->mLineDescriptors, currentF.mLdesc, idx, dist)) return 0;
+        const float minRatio = 1.0f / 1.5f;
+        for (int qdx = 0; qdx < n; ++qdx) {
+            const int tdx = idx[2 * qdx];
+            const double dist_12 = (float)dist[2 * qdx] / (float)dist[2 * qdx + 1];
+            if (dist_12 < minRatio) {
+                MapLine* mapLine = vpMapLinesKF[qdx];
+                if (mapLine) { vpMapLineMatches[tdx] = mapLine; nmatches++; }
+            }
+        }
+        return nmatches;
+    }
+
+    // src/LSDmatcher.cpp:903-940 (the reference runs the two FrameBFMatch calls in two threads; here they are two device calls)
+    int SearchDouble(Frame& InitialFrame, Frame& CurrentFrame, std::vector<int>& LineMatches) {
+        LineMatches = std::vector<int>(InitialFrame.NL, -1);
+        std::vector<int> tempMatches1, tempMatches2;
+        cv::Mat ldesc1 = InitialFrame.mLdesc, ldesc2 = CurrentFrame.mLdesc;
+        if (ldesc1.rows == 0 || ldesc2.rows == 0) return 0;
+        int nmatches = 0;
+        FrameBFMatch(ldesc1, ldesc2, tempMatches1, TH_LOW);
+        FrameBFMatch(ldesc2, ldesc1, tempMatches2, TH_LOW);
+        for (size_t i = 0; i < tempMatches1.size(); i++) {
+            int j = tempMatches1[i];
+            if (j >= 0) {
+                if (tempMatches2[j] != (int)i) tempMatches1[i] = -1;
+                else nmatches++;
+            }
+        }
+        LineMatches = tempMatches1;
+        return nmatches;
+    }
+
+    // src/LSDmatcher.cpp:865-901
+    template <class KeyFrame>
+    int SearchDouble(KeyFrame* KF, Frame& CurrentFrame) {
+        std::vector<int> tempMatches1(KF->NL, -1), tempMatches2(CurrentFrame.NL, -1);
+        cv::Mat ldesc1 = KF->mLineDescriptors, ldesc2 = CurrentFrame.mLdesc;
+        if (ldesc1.rows == 0 || ldesc2.rows == 0) return 0;
+        int nmatches = 0;
+        FrameBFMatch(ldesc1, ldesc2, tempMatches1, TH_LOW);
+        FrameBFMatch(ldesc2, ldesc1, tempMatches2, TH_LOW);
+        for (size_t i = 0; i < tempMatches2.size(); i++) {
+            int j = tempMatches2[i];
+            if (j >= 0 && tempMatches1[j] == (int)i) {
+                MapLine* pML = KF->GetMapLine(j);
+                if (!pML) continue;
+                CurrentFrame.mvpMapLines[i] = pML;
+                nmatches++;
+            }
+        }
+        return nmatches;
     }
 
     template <class KeyLine, class Vec3>

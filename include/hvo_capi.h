@@ -203,6 +203,12 @@ void hvo_proj_destroy(hvo_proj* h);
  * Uploads them and builds the 64 x 48 grid on the device. */
 int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* uright, const uint8_t* desc, int n, float min_x, float min_y,
                        float max_x, float max_y);
+/* KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:627-666) searches the grid it copied from its Frame (cells assigned with the
+ * frame's float bounds, same mfGridElement*Inv) but computes the cell range of a window from its own INTEGER mnMinX / mnMinY
+ * (include/KeyFrame.h:249-252: the float bounds truncated), which differs from the Frame's for distorted cameras.  After
+ * hvo_proj_set_frame, this call makes every window lookup of the handle (hvo_proj_search, hvo_proj_features_in_area) use
+ * (min_x, min_y) as origin, the cells unchanged; the next hvo_proj_set_frame resets it. */
+int hvo_proj_set_window_origin(hvo_proj* h, float min_x, float min_y);
 /* inspection: cell_start [64*48 + 1] (cell = ix * 48 + iy), cell_items [n] = mGrid[ix][iy] concatenated */
 int hvo_proj_get_grid(hvo_proj* h, int32_t* cell_start, int32_t* cell_items);
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel): indices in the reference's order; *n_out may exceed capacity */

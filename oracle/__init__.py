@@ -245,6 +245,18 @@ def grid_build(keys, bounds):
     return cnt, items[:cnt.sum()].copy()
 
 
+def window_origin(origin=None):
+    """KeyFrame::GetFeaturesInArea's integer origin (src/KeyFrame.cc:627-666, include/KeyFrame.h:249-252) for the window lookups of the
+    calls that follow on this thread; None restores the Frame rule (origin = the float bounds)."""
+    f = lib().orc_window_origin
+    f.argtypes = [C.c_int, C.c_float, C.c_float]
+    f.restype = None
+    if origin is None:
+        f(0, 0.0, 0.0)
+    else:
+        f(1, float(origin[0]), float(origin[1]))
+
+
 def features_in_area(keys, bounds, x, y, r, min_level=-1, max_level=-1):
     keys = np.ascontiguousarray(keys, KP_DTYPE)
     out = np.zeros(max(len(keys), 1), np.int32)
@@ -1002,6 +1014,148 @@ def ref_fuse(KF, kf_obs, cam5, Rcw, tcw, Ow, inv_sigma2, log_scale_factor, n_lev
         return None
     nf, ne = struct.unpack_from('<2i', raw, 0)
     return nf, np.frombuffer(raw, np.int32, 3 * ne, 8).reshape(ne, 3).copy()
+
+
+def _kf_camera_bytes(cam):
+    """fx fy cx cy bf, Rcw, tcw, Ow, mfLogScaleFactor, mnScaleLevels from a FRUSTUM_CAM record (read_kf_camera of the harness)"""
+    c = np.asarray(cam).reshape(())
+    return (_f32([c['fx'], c['fy'], c['cx'], c['cy'], c['bf']]) + _f32(c['Rcw']) + _f32(c['tcw']) + _f32(c['Ow'])
+            + struct.pack('<fi', float(c['log_scale_factor']), int(c['n_levels'])))
+
+
+def _map_point_records(pts, pdesc, flags, slots=None):
+    """hvo_map_point + descriptor + 4 flag bytes + int32 slot per map point (read_map_point of the harness)"""
+    pts = np.ascontiguousarray(pts, MAP_POINT_DTYPE)
+    pd = np.ascontiguousarray(pdesc, np.uint8).reshape(-1, 32)
+    fl = np.ascontiguousarray(flags, np.uint8).reshape(-1, 4)
+    sl = np.full(len(pts), -1, np.int32) if slots is None else np.asarray(slots, np.int32)
+    rec = np.zeros(len(pts), np.dtype([('p', MAP_POINT_DTYPE), ('d', 'u1', (32,)), ('f', 'u1', (4,)), ('s', '<i4')]))
+    rec['p'] = pts; rec['d'] = pd; rec['f'] = fl; rec['s'] = sl
+    return rec.tobytes()
+
+
+def ref_search_by_projection_scw(KF, cam, Scw, th, pts, pdesc, bad, found_slot):
+    """The reference's ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) executed (op 12).  KF = point-frame dict whose
+    `claimed` marks the entries of vpMatched that are set at call time; found_slot[i] >= 0: point i itself sits in vpMatched[found_slot[i]].
+    Returns (nmatches, vpMatched ids [N]: candidate index, -100 - i for the pre-set entry of slot i, -1 empty) or None."""
+    M = len(pts)
+    fl = np.zeros((M, 4), np.uint8); fl[:, 1] = bad; fl[:, 3] = np.asarray(found_slot) >= 0
+    b = struct.pack('<2i', 0x4d544348, 12) + _f32(KF['bounds']) + _point_frame_bytes(KF) + _kf_camera_bytes(cam) + _f32(Scw)
+    b += struct.pack('<2i', int(th), M) + _map_point_records(pts, pdesc, fl, found_slot)
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, len(KF['keys_un']), 4).copy()
+
+
+def ref_fuse_scw(KF, kf_bad, cam, Scw, th, pts, pdesc, bad, held_slot):
+    """The reference's ORBmatcher::Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) executed (op 13).  KF['claimed'] = the keypoint holds a map
+    point (kf_bad: that point isBad()); held_slot[i] >= 0: candidate i is the map point of that slot.  Returns (nFused, replace ids [M],
+    AddObservation events [n, 2] = (map point, keypoint), key-frame slots after the call [N]) or None."""
+    M, N = len(pts), len(KF['keys_un'])
+    fl = np.zeros((M, 4), np.uint8); fl[:, 1] = bad; fl[:, 3] = np.asarray(held_slot) >= 0
+    b = struct.pack('<2i', 0x4d544348, 13) + _f32(KF['bounds']) + _point_frame_bytes(KF) + np.asarray(kf_bad, np.uint8).tobytes()
+    b += _kf_camera_bytes(cam) + _f32(Scw) + struct.pack('<fi', float(th), M) + _map_point_records(pts, pdesc, fl, held_slot)
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nf,) = struct.unpack_from('<i', raw, 0)
+    rep = np.frombuffer(raw, np.int32, M, 4).copy()
+    (ne,) = struct.unpack_from('<i', raw, 4 + 4 * M)
+    ev = np.frombuffer(raw, np.int32, 2 * ne, 8 + 4 * M).reshape(ne, 2).copy()
+    slots = np.frombuffer(raw, np.int32, N, 8 + 4 * M + 8 * ne).copy()
+    return nf, rep, ev, slots
+
+
+def _kf_with_points_bytes(KF, cam, mp):
+    """point frame + camera + the map point of every keypoint (mp = dict(pts, desc, has, bad[, found]))"""
+    n = len(KF['keys_un'])
+    fl = np.zeros((n, 4), np.uint8); fl[:, 0] = mp['has']; fl[:, 1] = mp['bad']
+    if 'found' in mp:
+        fl[:, 2] = mp['found']
+    return _map_point_records(mp['pts'], mp['desc'], fl)
+
+
+def ref_search_by_sim3(KF1, cam1, mp1, KF2, cam2, mp2, matches12, s12, R12, t12, th):
+    """The reference's ORBmatcher::SearchBySim3 executed (op 14).  matches12 [N1] = index of the KF2 map point already matched, or -1.
+    Returns (nFound, vpMatches12 ids [N1]) or None."""
+    b = struct.pack('<2i', 0x4d544348, 14) + _f32(KF1['bounds'])
+    b += _point_frame_bytes(KF1) + _kf_camera_bytes(cam1) + _kf_with_points_bytes(KF1, cam1, mp1)
+    b += _point_frame_bytes(KF2) + _kf_camera_bytes(cam2) + _kf_with_points_bytes(KF2, cam2, mp2)
+    b += np.asarray(matches12, np.int32).tobytes() + struct.pack('<f', float(s12)) + _f32(R12) + _f32(t12) + struct.pack('<f', float(th))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nf,) = struct.unpack_from('<i', raw, 0)
+    return nf, np.frombuffer(raw, np.int32, len(KF1['keys_un']), 4).copy()
+
+
+def ref_search_by_projection_reloc(Cur, cam4, Tcw, log_scale_factor, n_levels, th, orb_dist, check_ori, kf_keys, mp):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist) executed (op 15).  Cur['claimed'] =
+    the frame's keypoint holds a map point; mp = the key frame's map points per keypoint (pts, desc, has, bad, found).
+    Returns (nmatches, ids [N]: key-frame keypoint whose map point the frame keypoint received, -2 kept its own, -1 none) or None."""
+    k = np.ascontiguousarray(kf_keys, KP_DTYPE)
+    b = struct.pack('<2i', 0x4d544348, 15) + _f32(Cur['bounds']) + _point_frame_bytes(Cur) + _f32(cam4) + _f32(Tcw)
+    b += struct.pack('<fifii', float(log_scale_factor), int(n_levels), float(th), int(orb_dist), int(check_ori))
+    b += struct.pack('<i', len(k)) + k.tobytes() + _kf_with_points_bytes(dict(keys_un=k), None, mp)
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, len(Cur['keys_un']), 4).copy()
+
+
+def ref_search_by_bow_kf(KF1, KF2, nnratio=0.75, check_ori=True):
+    """The reference's ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) executed (op 16).  KFi = dict(keys_un, desc, has_mappoint, bad, featvec).
+    Returns (nmatches, vpMatches12 [N1] = keypoint of pKF2 whose map point was matched, or -1) or None."""
+    def kf(K):
+        k = np.ascontiguousarray(K['keys_un'], KP_DTYPE)
+        bad = np.zeros(len(k), np.uint8) if K.get('bad') is None else np.asarray(K['bad'], np.uint8)
+        return (struct.pack('<i', len(k)) + k.tobytes() + np.ascontiguousarray(K['desc'], np.uint8).tobytes()
+                + np.asarray(K['has_mappoint'], np.uint8).tobytes() + bad.tobytes() + _featvec_bytes(K['featvec']))
+    b = struct.pack('<2i', 0x4d544348, 16) + _f32([0, 0, 640, 480]) + kf(KF1) + kf(KF2) + struct.pack('<fi', float(nnratio), int(check_ori))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (nm,) = struct.unpack_from('<i', raw, 0)
+    return nm, np.frombuffer(raw, np.int32, len(KF1['keys_un']), 4).copy()
+
+
+def ref_line_bf(ldesc1, ldesc2, TH, nnratio, nnr):
+    """The reference's LSDmatcher::FrameBFMatch(ldesc1, ldesc2, LineMatches, TH), match(desc1, desc2, nnr, matches_12) and
+    SearchDouble(InitialFrame, CurrentFrame, LineMatches) executed (op 17).  Returns (LineMatches [n1], n_nnr, matches_12 [n1], n_double,
+    LineMatches of SearchDouble [n1]) or None."""
+    d1 = np.ascontiguousarray(ldesc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(ldesc2, np.uint8).reshape(-1, 32)
+    n1 = len(d1)
+    b = struct.pack('<2i', 0x4d544348, 17) + _f32([0, 0, 640, 480]) + struct.pack('<i', n1) + d1.tobytes() + struct.pack('<i', len(d2)) + d2.tobytes()
+    b += struct.pack('<3f', float(TH), float(nnratio), float(nnr))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    lm = np.frombuffer(raw, np.int32, n1, 0).copy()
+    (n_nnr,) = struct.unpack_from('<i', raw, 4 * n1)
+    m12 = np.frombuffer(raw, np.int32, n1, 4 * n1 + 4).copy()
+    (n_dbl,) = struct.unpack_from('<i', raw, 8 * n1 + 4)
+    dbl = np.frombuffer(raw, np.int32, n1, 8 * n1 + 8).copy()
+    return lm, n_nnr, m12, n_dbl, dbl
+
+
+def ref_line_by_descriptor(kf_ldesc, kf_has_mapline, ldesc, nnratio):
+    """The reference's LSDmatcher::SearchByDescriptor(pKF, currentF, vpMapLineMatches) and SearchDouble(KF, CurrentFrame) executed (op 18).
+    Returns (nmatches, ids [NL] = key-frame line whose MapLine the frame line received, n_double, ids of SearchDouble [NL]) or None."""
+    d1 = np.ascontiguousarray(kf_ldesc, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(ldesc, np.uint8).reshape(-1, 32)
+    n2 = len(d2)
+    b = struct.pack('<2i', 0x4d544348, 18) + _f32([0, 0, 640, 480]) + struct.pack('<i', len(d1)) + d1.tobytes() + np.asarray(kf_has_mapline, np.uint8).tobytes()
+    b += struct.pack('<i', n2) + d2.tobytes() + struct.pack('<f', float(nnratio))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    (n1,) = struct.unpack_from('<i', raw, 0)
+    by = np.frombuffer(raw, np.int32, n2, 4).copy()
+    (nd,) = struct.unpack_from('<i', raw, 4 + 4 * n2)
+    dbl = np.frombuffer(raw, np.int32, n2, 8 + 4 * n2).copy()
+    return n1, by, nd, dbl
 
 
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):

@@ -209,6 +209,7 @@ struct MatStep {
 struct MatZerosExpr { int rows, cols, type; };
 struct MatOnesExpr { int rows, cols, type; };
 
+struct MatTExpr;
 class Mat {
 public:
     int rows, cols;
@@ -247,12 +248,7 @@ public:
     Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
     Size size() const { return Size(cols, rows); }
     Mat col(int x) const { return (*this)(Rect(x, 0, 1, rows)); }
-    Mat t() const {  // CV_32F only (pose blocks)
-        assert(type_ == CV_32FC1);
-        Mat r(cols, rows, CV_32FC1);
-        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) r.at<float>(x, y) = at<float>(y, x);
-        return r;
-    }
+    MatTExpr t() const;  // CV_32F only (pose blocks); an expression, as in OpenCV: see MatTExpr below
     Mat row(int y) const { return (*this)(Rect(0, y, cols, 1)); }
     void copyTo(Mat& dst) const { dst = clone(); }
     void copyTo(const class _OutputArray& dst) const;
@@ -497,6 +493,46 @@ private:
 
 // ---- small CV_32F matrix algebra the tracking-time functions use (Frame::isInFrustum, LSDmatcher::FrameBFMatchNew) ----
 // Semantics checked against cv2 4.13.0 where Python exposes the operation (gemm, norm, addWeighted: tests/test_track.py); the
+// A.t() is an expression in OpenCV (MatOp_T) and the reference's `-Rcw.t()*tcw` (ORBmatcher.cc:308, 1009, 1366, 1505; LSDmatcher.cpp:577)
+// becomes ONE cv::gemm(Rcw, tcw, -1, noArray(), 0, GEMM_1_T).  With a transpose flag cv::gemm leaves its small-matrix path and runs
+// GEMMSingleMul<float, double>: products and sums in double, (float)(sum * alpha) at the end (checked against cv2.gemm 4.13.0 with
+// GEMM_1_T: 0 mismatches in 5000 random 3x3^T * 3x1, whereas float accumulation differs in 80 % of them;
+// tests/test_track.py::test_opencv_float_matrix_rules).  `s * A.t()` assigned to a Mat is transpose + convertTo(alpha): a float product.
+struct MatTExpr {
+    Mat a;
+    double alpha;
+    operator Mat() const {
+        assert(a.type() == CV_32FC1);
+        Mat r(a.cols, a.rows, CV_32FC1);
+        const float f = (float)alpha;
+        for (int y = 0; y < a.rows; ++y)
+            for (int x = 0; x < a.cols; ++x) r.at<float>(x, y) = alpha == 1. ? a.at<float>(y, x) : a.at<float>(y, x) * f;
+        return r;
+    }
+};
+inline MatTExpr Mat::t() const { return MatTExpr{*this, 1.}; }
+static inline MatTExpr operator-(MatTExpr e) { e.alpha = -e.alpha; return e; }
+static inline MatTExpr operator*(double s, MatTExpr e) { e.alpha *= s; return e; }
+static inline Mat operator*(const MatTExpr& e, const Mat& b) {
+    assert(e.a.type() == CV_32FC1 && b.type() == CV_32FC1 && e.a.rows == b.rows);
+    Mat r(e.a.cols, b.cols, CV_32FC1);
+    for (int i = 0; i < e.a.cols; ++i)
+        for (int j = 0; j < b.cols; ++j) {
+            double s = 0.;
+            for (int k = 0; k < e.a.rows; ++k) s += (double)e.a.at<float>(k, i) * (double)b.at<float>(k, j);
+            r.at<float>(i, j) = (float)(s * e.alpha);
+        }
+    return r;
+}
+// A / s is convertTo(A, -1, 1. / s): a float multiplication by (float)(1. / s) (ORBmatcher.cc:306-307, 1007-1008: sRcw / scw)
+static inline Mat operator/(const Mat& a, double s) {
+    assert(a.type() == CV_32FC1);
+    Mat r(a.rows, a.cols, CV_32FC1);
+    const float f = (float)(1. / s);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) r.at<float>(i, j) = a.at<float>(i, j) * f;
+    return r;
+}
+
 // rest follows OpenCV's sources: Mat::dot / cv::norm accumulate in double in element order, Mat::cross works in float,
 // `m /= s` is convertTo(m, -1, 1. / s) i.e. a float multiplication by (float)(1. / s), `s * (A + B)` is addWeighted(A, s, B, s).
 // (A * B + C is one cv::gemm call in OpenCV, (float)(double(t) + double(c)): for two floats that equals the float sum.)
@@ -554,6 +590,7 @@ inline Mat Mat::cross(const Mat& o) const { return cvshim_cross32f(*this, o); }
 class BFMatcher {
 public:
     BFMatcher(int normType, bool crossCheck = false) { assert(normType == NORM_HAMMING && !crossCheck); (void)normType; (void)crossCheck; }
+    static Ptr<BFMatcher> create(int normType, bool crossCheck = false) { return Ptr<BFMatcher>(new BFMatcher(normType, crossCheck)); }
     void knnMatch(const Mat& q, const Mat& t, std::vector<std::vector<DMatch>>& matches, int k) const {
         assert(k == 2 && q.type() == CV_8UC1 && t.type() == CV_8UC1 && q.cols == 32 && t.cols == 32 && q.isContinuous() && t.isContinuous());
         (void)k;

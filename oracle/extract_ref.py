@@ -65,6 +65,23 @@ RANGES = {
     'keyframe_area': [('src/KeyFrame.cc', 627, 666, 'vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const'),
                       ('src/KeyFrame.cc', 780, 783, 'bool KeyFrame::IsInImage(')],
     'mappoint_scale_kf': [('src/MapPoint.cc', 383, 398, 'int MapPoint::PredictScale(const float &currentDist, KeyFrame *pKF)')],
+    # ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (loop detection); SearchByBoW(pKF1, pKF2, vpMatches12);
+    # Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint); SearchBySim3; SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist)
+    'orb_kf_scw': [('src/ORBmatcher.cc', 295, 410, 'int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw')],
+    'orb_bow_kf': [('src/ORBmatcher.cc', 531, 666, 'int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2')],
+    'orb_fuse_scw': [('src/ORBmatcher.cc', 996, 1121, 'int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw')],
+    'orb_sim3': [('src/ORBmatcher.cc', 1123, 1351, 'int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2')],
+    'orb_reloc': [('src/ORBmatcher.cc', 1499, 1628, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound')],
+    # KeyFrame::GetMapPoints; MapPoint::GetIndexInKeyFrame
+    'keyframe_mps': [('src/KeyFrame.cc', 254, 267, 'set<MapPoint*> KeyFrame::GetMapPoints()')],
+    'mappoint_index': [('src/MapPoint.cc', 313, 320, 'int MapPoint::GetIndexInKeyFrame(KeyFrame *pKF)')],
+    # the two MAD comparators; LSDmatcher::SearchByDescriptor; matchNNR, match, SearchDouble x2, FrameBFMatch; LSDmatcher::lineDescriptorMAD;
+    # Frame::lineDescriptorMAD (what SearchByDescriptor calls)
+    'lsd_bf': [('include/auxiliar.h', 26, 38, 'struct compare_descriptor_by_NN_dist'),
+               ('src/LSDmatcher.cpp', 522, 559, 'int LSDmatcher::SearchByDescriptor('),
+               ('src/LSDmatcher.cpp', 803, 966, 'int LSDmatcher::matchNNR('),
+               ('src/LSDmatcher.cpp', 1110, 1135, 'void LSDmatcher::lineDescriptorMAD('),
+               ('src/Frame.cc', 1331, 1355, 'void Frame::lineDescriptorMAD(')],
     # MapPoint::ComputeDistinctiveDescriptors, MapLine::ComputeDistinctiveDescriptors
     'distinctive': [('src/MapPoint.cc', 240, 305, 'void MapPoint::ComputeDistinctiveDescriptors()'),
                     ('src/MapLine.cpp', 331, 396, 'void MapLine::ComputeDistinctiveDescriptors()')],

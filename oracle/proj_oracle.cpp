@@ -24,18 +24,23 @@ struct Query { float u, v, r; int min_level, max_level; float ur; int claims; in
 
 static const int kCols = 64, kRows = 48;
 
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:627-666) looks windows up with the key frame's integer mnMinX / mnMinY in cells its Frame
+// assigned with the float bounds; orc_window_origin(1, x, y) selects that origin for the grids built afterwards on this thread.
+static thread_local bool g_win_on = false;
+static thread_local float g_win_x = 0.f, g_win_y = 0.f;
+
 struct Grid {
     float min_x, min_y, inv_w, inv_h;
     std::vector<int> cell[kCols][kRows];
     void build(const KeyPoint* k, int n, float mnx, float mny, float mxx, float mxy) {
-        min_x = mnx; min_y = mny;
         inv_w = (float)kCols / (mxx - mnx);
         inv_h = (float)kRows / (mxy - mny);
         for (int i = 0; i < n; ++i) {
-            const int px = (int)std::round((k[i].x - min_x) * inv_w), py = (int)std::round((k[i].y - min_y) * inv_h);
+            const int px = (int)std::round((k[i].x - mnx) * inv_w), py = (int)std::round((k[i].y - mny) * inv_h);
             if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
             cell[px][py].push_back(i);
         }
+        min_x = g_win_on ? g_win_x : mnx; min_y = g_win_on ? g_win_y : mny;   // origin of the window lookups below
     }
     void area(const KeyPoint* k, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
         out.clear();
@@ -78,6 +83,7 @@ static int hamming(const uint8_t* a, const uint8_t* b) {
 extern "C" {
 
 // grid inspection: cell_count [64*48] (index ix * 48 + iy), cell_items in the same order (n entries at most)
+void orc_window_origin(int on, float x, float y) { projo::g_win_on = on != 0; projo::g_win_x = x; projo::g_win_y = y; }
 void orc_grid_build(const void* keys, int n, float min_x, float min_y, float max_x, float max_y, int32_t* cell_count, int32_t* cell_items) {
     projo::Grid g;
     g.build((const projo::KeyPoint*)keys, n, min_x, min_y, max_x, max_y);

@@ -14,6 +14,11 @@
 //   src/ORBmatcher.cc:838-994                                Fuse(KeyFrame*, vpMapPoints, th), whole; src/KeyFrame.cc:627-666, 780-783
 //                                                            GetFeaturesInArea, IsInImage; src/MapPoint.cc:383-398 PredictScale(dist, KeyFrame*)
 //   src/MapPoint.cc:240-305, src/MapLine.cpp:331-396         ComputeDistinctiveDescriptors x2
+//   src/ORBmatcher.cc:295-410, 531-666, 996-1121, 1123-1351, 1499-1628   SearchByProjection(KeyFrame*, Scw, ...), SearchByBoW(pKF1, pKF2, ...),
+//                                                            Fuse(KeyFrame*, Scw, ...), SearchBySim3, SearchByProjection(Cur, KeyFrame*, found, th, ORBdist),
+//                                                            whole; src/KeyFrame.cc:254-267 GetMapPoints, src/MapPoint.cc:313-320 GetIndexInKeyFrame
+//   include/auxiliar.h:26-38, src/LSDmatcher.cpp:522-559, 803-966, 1110-1135, src/Frame.cc:1331-1355   SearchByDescriptor, matchNNR, match,
+//                                                            SearchDouble x2, FrameBFMatch, lineDescriptorMAD x2 (their std::threads included)
 //   src/lineIterator.cpp                                     whole file, unmodified
 // and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
 // (declared below with the reference header line each one mirrors) plus the OpenCV / Eigen stand-ins.
@@ -31,6 +36,7 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -72,11 +78,13 @@ public:
         mTrackProjX = o.mTrackProjX; mTrackProjY = o.mTrackProjY; mTrackProjXR = o.mTrackProjXR; mbTrackInView = o.mbTrackInView;
         mnTrackScaleLevel = o.mnTrackScaleLevel; mTrackViewCos = o.mTrackViewCos; pos = o.pos; desc = o.desc; normal = o.normal;
         nobs = o.nobs; bad = o.bad; id = o.id; mfMinDistance = o.mfMinDistance; mfMaxDistance = o.mfMaxDistance;
+        mObservations = o.mObservations;
         return *this;
     }
     void ComputeDistinctiveDescriptors();
     int PredictScale(const float& currentDist, KeyFrame* pKF);
     bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+    int GetIndexInKeyFrame(KeyFrame* pKF);
     // bookkeeping stand-ins: what Fuse decides is logged as (map point id, key-frame keypoint or -1, action)
     void Replace(MapPoint* pMP);
     void AddObservation(KeyFrame* pKF, size_t idx);
@@ -142,6 +150,12 @@ class KeyFrame {                          // include/KeyFrame.h: the members Sea
 public:
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    std::set<MapPoint*> GetMapPoints();
+    std::vector<MapLine*> GetMapLineMatches() { return mvpMapLines; }
+    MapLine* GetMapLine(const size_t& idx) { return mvpMapLines[idx]; }
+    int NL = 0;
+    std::vector<MapLine*> mvpMapLines;
+    std::mutex mMutexFeatures;
     cv::Mat GetCameraCenter() { return Ow.clone(); }
     cv::Mat GetRotation() { return Rcw.clone(); }
     cv::Mat GetTranslation() { return tcw.clone(); }
@@ -175,6 +189,7 @@ public:
     bool isInFrustum(MapLine* pML, float) { return pML->mbTrackInView; }
     bool isInFrustumRef(MapPoint* pMP, float viewingCosLimit);   // = the reference's isInFrustum, see the include below
     bool isInFrustumRef(MapLine* pML, float viewingCosLimit);
+    void lineDescriptorMAD(vector<vector<DMatch>> matches, double& nn_mad, double& nn12_mad) const;   // include/Frame.h:98
     DBoW2::FeatureVector mFeatVec;           // include/Frame.h:268
     cv::Mat mRcw, mtcw, mOw;                 // include/Frame.h:408-411
     int mnScaleLevels = 8;                   // :330-332
@@ -213,6 +228,11 @@ public:
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo);
     int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, const float th);
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF);
@@ -230,6 +250,13 @@ public:
     void FrameBFMatchNew(cv::Mat ldesc1, cv::Mat ldesc2, vector<int>& LineMatches, vector<KeyLine> kls1, vector<KeyLine> kls2,
                          vector<Eigen::Vector3d> kls2func, cv::Mat F, float TH);
     float mutualOverlap(const std::vector<cv::Mat>& collinear_points);
+    int SearchByDescriptor(KeyFrame* pKF, Frame& currentF, vector<MapLine*>& vpMapLineMatches);
+    int matchNNR(const cv::Mat& desc1, const cv::Mat& desc2, float nnr, std::vector<int>& matches_12);
+    int match(const cv::Mat& desc1, const cv::Mat& desc2, float nnr, std::vector<int>& matches_12);
+    int SearchDouble(Frame& InitialFrame, Frame& CurrentFrame, vector<int>& LineMatches);
+    int SearchDouble(KeyFrame* KF, Frame& CurrentFrame);
+    void FrameBFMatch(cv::Mat ldesc1, cv::Mat ldesc2, vector<int>& LineMatches, float TH);
+    void lineDescriptorMAD(vector<vector<DMatch>> line_matches, double& nn_mad, double& nn12_mad) const;
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     double computeAngle2D(const cv::Mat& vector1, const cv::Mat& vector2);
@@ -245,11 +272,43 @@ protected:
 #include "gen/orb_fuse.inc"
 #include "gen/keyframe_area.inc"
 #include "gen/mappoint_scale_kf.inc"
+#include "gen/orb_kf_scw.inc"
+#include "gen/orb_bow_kf.inc"
+#include "gen/orb_fuse_scw.inc"
+#include "gen/orb_sim3.inc"
+#include "gen/orb_reloc.inc"
+#include "gen/keyframe_mps.inc"
+#include "gen/mappoint_index.inc"
+#define isInFrustum isInFrustumRef
+#include "gen/frame_frustum.inc"
+#undef isInFrustum
+#include "gen/map_scale.inc"
+}  // namespace ORB_SLAM2
+namespace ORB_SLAM2 {
+#include "gen/lsdmatcher.inc"
+#include "gen/lsd_bfnew.inc"
+#include "gen/lsd_bf.inc"
+#include "gen/distinctive.inc"
+}  // namespace ORB_SLAM2
+#else
+}  // namespace ORB_SLAM2
+#include "standin_host.hpp"   // tests/cpp/standins: KeyFrame::GetMapPoints / IsInImage, MapPoint::PredictScale ... for the stand-in types
+#include "ORBmatcher.h"
+#include "LSDmatcher.h"
+#include "FrustumGPU.h"
+namespace ORB_SLAM2 {
+typedef hvo_shim::ORBmatcherT<Frame, MapPoint> ORBmatcher;
+typedef hvo_shim::LSDmatcherT<Frame, MapLine> LSDmatcher;
+}  // namespace ORB_SLAM2
+#endif
+
+using namespace ORB_SLAM2;
+
 struct FuseEvent { int32_t mp, idx, action; };   // action 0: AddObservation + AddMapPoint, 1: pMP->Replace(pMPinKF), 2: pMPinKF->Replace(pMP)
 static std::vector<FuseEvent> g_fuse_log;
 static KeyFrame* g_fuse_kf = nullptr;
-void MapPoint::AddObservation(KeyFrame*, size_t idx) { g_fuse_log.push_back(FuseEvent{id, (int32_t)idx, 0}); nobs++; }
-void MapPoint::Replace(MapPoint* pMP) {
+void ORB_SLAM2::MapPoint::AddObservation(KeyFrame*, size_t idx) { g_fuse_log.push_back(FuseEvent{id, (int32_t)idx, 0}); nobs++; }
+void ORB_SLAM2::MapPoint::Replace(MapPoint* pMP) {
     // `this` is replaced by pMP.  One of the two sits in a slot of the key frame (pMPinKF), the other is the incoming map point.
     int32_t idx = -1;
     bool this_in_kf = false;
@@ -264,28 +323,7 @@ void MapPoint::Replace(MapPoint* pMP) {
         g_fuse_log.push_back(FuseEvent{id, idx, 1});
     }
 }
-#define isInFrustum isInFrustumRef
-#include "gen/frame_frustum.inc"
-#undef isInFrustum
-#include "gen/map_scale.inc"
-}  // namespace ORB_SLAM2
-namespace ORB_SLAM2 {
-#include "gen/lsdmatcher.inc"
-#include "gen/lsd_bfnew.inc"
-#include "gen/distinctive.inc"
-}  // namespace ORB_SLAM2
-#else
-}  // namespace ORB_SLAM2
-#include "ORBmatcher.h"
-#include "LSDmatcher.h"
-#include "FrustumGPU.h"
-namespace ORB_SLAM2 {
-typedef hvo_shim::ORBmatcherT<Frame, MapPoint> ORBmatcher;
-typedef hvo_shim::LSDmatcherT<Frame, MapLine> LSDmatcher;
-}  // namespace ORB_SLAM2
-#endif
 
-using namespace ORB_SLAM2;
 
 // ---- binary I/O ----
 static FILE *g_in, *g_out;
@@ -344,6 +382,56 @@ static void put_grid(const std::vector<std::size_t> (*grid)[FRAME_GRID_ROWS]) {
             put<int32_t>((int32_t)grid[ix][iy].size());
             for (size_t v : grid[ix][iy]) put<int32_t>((int32_t)v);
         }
+}
+
+// key frame = a point frame read through the Frame reader (grid included) + what KeyFrame's constructor copies from it
+// (src/KeyFrame.cc:33-60: the grid, the integer image bounds, the inverse cell sizes)
+static void keyframe_from_frame(const Frame& F, KeyFrame& K) {
+    K.N = F.N; K.mvKeysUn = F.mvKeysUn; K.mvuRight = F.mvuRight; K.mDescriptors = F.mDescriptors; K.mvScaleFactors = F.mvScaleFactors;
+    K.mvpMapPoints.assign(K.N, nullptr);
+#ifndef REF_MATCH_USE_SHIM
+    K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int ix = 0; ix < FRAME_GRID_COLS; ++ix) for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) K.mGrid[ix][iy] = F.mGrid[ix][iy];
+#endif
+    K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+}
+// fx fy cx cy bf, Rcw, tcw, Ow, mfLogScaleFactor, mnScaleLevels
+static void read_kf_camera(KeyFrame& K) {
+    float cam[5]; get_n(cam, 5);
+    K.fx = cam[0]; K.fy = cam[1]; K.cx = cam[2]; K.cy = cam[3]; K.mbf = cam[4];
+    K.Rcw = cv::Mat(3, 3, CV_32FC1); get_n((float*)K.Rcw.data, 9);
+    K.tcw = cv::Mat(3, 1, CV_32FC1); get_n((float*)K.tcw.data, 3);
+    K.Ow = cv::Mat(3, 1, CV_32FC1); get_n((float*)K.Ow.data, 3);
+    K.mfLogScaleFactor = get<float>(); K.mnScaleLevels = get<int32_t>();
+}
+// map point record: pos[3], normal[3], min, max distance (hvo_map_point), descriptor[32], 4 flag bytes, int32 slot
+static void read_map_point(MapPoint& m, uint8_t fl[4], int32_t& slot) {
+    m.pos = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.pos.data, 3);
+    m.normal = cv::Mat(3, 1, CV_32FC1); get_n((float*)m.normal.data, 3);
+    m.mfMinDistance = get<float>(); m.mfMaxDistance = get<float>();
+    m.desc = get_desc_rows(1);
+    get_n(fl, 4);
+    slot = get<int32_t>();
+}
+static void read_featvec(DBoW2::FeatureVector& fv) {
+    const int nn = get<int32_t>();
+    for (int k = 0; k < nn; ++k) {
+        const int node = get<int32_t>(), cnt = get<int32_t>();
+        for (int j = 0; j < cnt; ++j) fv.addFeature((DBoW2::NodeId)node, (unsigned int)get<int32_t>());
+    }
+}
+// the map points a key frame holds (ops 14, 15): per keypoint has / bad / found / - flags (slot unused), ids = keypoint index
+static void read_kf_map_points(KeyFrame& K, std::vector<MapPoint>& mps, std::vector<uint8_t>* found) {
+    mps.resize(K.N);
+    if (found) found->assign(K.N, 0);
+    for (int i = 0; i < K.N; ++i) {
+        uint8_t fl[4]; int32_t slot;
+        read_map_point(mps[i], fl, slot);
+        mps[i].id = i; mps[i].bad = fl[1] != 0; mps[i].nobs = 1;
+        if (found) (*found)[i] = fl[2];
+        if (fl[0]) { K.mvpMapPoints[i] = &mps[i]; mps[i].mObservations[&K] = (size_t)i; }
+    }
 }
 
 int main(int argc, char** argv) {
@@ -609,7 +697,6 @@ int main(int argc, char** argv) {
         put<int32_t>(nm);
         for (int i = 0; i < F.N; ++i) put<int32_t>(matches[i] ? matches[i]->id : -1);
     } else if (op == 10) {   // ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
-#ifndef REF_MATCH_USE_SHIM
         KeyFrame K1, K2;
         std::vector<MapPoint> pool1, pool2;
         auto read_kf = [&](KeyFrame& K, std::vector<MapPoint>& pool) {
@@ -645,11 +732,7 @@ int main(int argc, char** argv) {
         put<int32_t>(nm);
         put<int32_t>((int32_t)pairs.size());
         for (const auto& pr : pairs) { put<int32_t>((int32_t)pr.first); put<int32_t>((int32_t)pr.second); }
-#else
-        return 6;   // reached through hvo_proj_search_triangulation (PointWindowMatcher), exercised from Python
-#endif
     } else if (op == 11) {   // ORBmatcher::Fuse(pKF, vpMapPoints, th)
-#ifndef REF_MATCH_USE_SHIM
         Frame F; std::vector<MapPoint> pool;
         read_point_frame(F, pool);               // key frame's features through the Frame reader (grid included); claimed = holds a map point
         KeyFrame K;
@@ -658,8 +741,10 @@ int main(int argc, char** argv) {
         std::vector<MapPoint> held(K.N);
         K.mvpMapPoints.assign(K.N, nullptr);
         for (int i = 0; i < K.N; ++i) if (F.mvpMapPoints[i]) { held[i].id = -100 - i; held[i].nobs = kfobs[i]; K.mvpMapPoints[i] = &held[i]; }
+#ifndef REF_MATCH_USE_SHIM
         K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
         for (int ix = 0; ix < FRAME_GRID_COLS; ++ix) for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) K.mGrid[ix][iy] = F.mGrid[ix][iy];   // KeyFrame ctor: mGrid = F.mGrid
+#endif
         K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
         K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
         float cam[5]; get_n(cam, 5);
@@ -691,9 +776,150 @@ int main(int argc, char** argv) {
         put<int32_t>(nf);
         put<int32_t>((int32_t)g_fuse_log.size());
         for (const FuseEvent& e : g_fuse_log) { put<int32_t>(e.mp); put<int32_t>(e.idx); put<int32_t>(e.action); }
-#else
-        return 6;   // reached through hvo_proj_search mode 2 (PointWindowMatcher), exercised from Python
-#endif
+    } else if (op == 12) {   // ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th)   (loop detection)
+        Frame F; std::vector<MapPoint> pool;
+        read_point_frame(F, pool);               // claimed[i] = vpMatched[i] is set at call time
+        KeyFrame K; keyframe_from_frame(F, K);
+        read_kf_camera(K);
+        cv::Mat Scw = get_pose();
+        const int th = get<int32_t>();
+        const int M = get<int32_t>();
+        std::vector<MapPoint*> vpMatched(K.N, nullptr);
+        for (int i = 0; i < K.N; ++i) if (F.mvpMapPoints[i]) { pool[i].id = -100 - i; vpMatched[i] = &pool[i]; }
+        std::vector<MapPoint> mps(M);
+        std::vector<MapPoint*> vp(M);
+        for (int i = 0; i < M; ++i) {
+            uint8_t fl[4]; int32_t slot;
+            read_map_point(mps[i], fl, slot);    // flags: -, bad, -, already in vpMatched (at `slot`)
+            mps[i].id = i; mps[i].bad = fl[1] != 0; vp[i] = &mps[i];
+            if (fl[3] && slot >= 0 && slot < K.N) vpMatched[slot] = &mps[i];
+        }
+        ORBmatcher matcher(0.75f, true);
+        const int nm = matcher.SearchByProjection(&K, Scw, vp, vpMatched, th);
+        put<int32_t>(nm);
+        for (int i = 0; i < K.N; ++i) put<int32_t>(vpMatched[i] ? vpMatched[i]->id : -1);
+    } else if (op == 13) {   // ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)   (loop closing)
+        Frame F; std::vector<MapPoint> pool;
+        read_point_frame(F, pool);               // claimed[i] = the key frame's keypoint holds a map point
+        KeyFrame K; keyframe_from_frame(F, K);
+        std::vector<uint8_t> kfbad(K.N); get_n(kfbad.data(), K.N);
+        for (int i = 0; i < K.N; ++i) if (F.mvpMapPoints[i]) { pool[i].id = -100 - i; pool[i].bad = kfbad[i] != 0; K.mvpMapPoints[i] = &pool[i]; }
+        read_kf_camera(K);
+        cv::Mat Scw = get_pose();
+        const float th = get<float>();
+        const int M = get<int32_t>();
+        std::vector<MapPoint> mps(M);
+        std::vector<MapPoint*> vp(M);
+        for (int i = 0; i < M; ++i) {
+            uint8_t fl[4]; int32_t slot;
+            read_map_point(mps[i], fl, slot);    // flags: -, bad, -, held by the key frame (at `slot`)
+            mps[i].id = i; mps[i].bad = fl[1] != 0; vp[i] = &mps[i];
+            if (fl[3] && slot >= 0 && slot < K.N) K.mvpMapPoints[slot] = &mps[i];
+        }
+        std::vector<MapPoint*> vpReplace(M, nullptr);
+        g_fuse_kf = &K;
+        g_fuse_log.clear();
+        ORBmatcher matcher(0.8f, true);
+        const int nf = matcher.Fuse(&K, Scw, vp, th, vpReplace);
+        put<int32_t>(nf);
+        for (int i = 0; i < M; ++i) put<int32_t>(vpReplace[i] ? vpReplace[i]->id : -1);
+        put<int32_t>((int32_t)g_fuse_log.size());
+        for (const FuseEvent& e : g_fuse_log) { put<int32_t>(e.mp); put<int32_t>(e.idx); }
+        for (int i = 0; i < K.N; ++i) put<int32_t>(K.mvpMapPoints[i] ? K.mvpMapPoints[i]->id : -1);
+    } else if (op == 14) {   // ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)
+        Frame F1, F2; std::vector<MapPoint> pool1, pool2, mps1, mps2;
+        KeyFrame K1, K2;
+        read_point_frame(F1, pool1); keyframe_from_frame(F1, K1); read_kf_camera(K1); read_kf_map_points(K1, mps1, nullptr);
+        read_point_frame(F2, pool2); keyframe_from_frame(F2, K2); read_kf_camera(K2); read_kf_map_points(K2, mps2, nullptr);
+        std::vector<int32_t> m12(K1.N); get_n(m12.data(), K1.N);
+        std::vector<MapPoint*> vpMatches12(K1.N, nullptr);
+        for (int i = 0; i < K1.N; ++i) if (m12[i] >= 0) vpMatches12[i] = &mps2[m12[i]];
+        const float s12 = get<float>();
+        cv::Mat R12(3, 3, CV_32FC1); get_n((float*)R12.data, 9);
+        cv::Mat t12(3, 1, CV_32FC1); get_n((float*)t12.data, 3);
+        const float th = get<float>();
+        ORBmatcher matcher(0.75f, true);
+        const int nf = matcher.SearchBySim3(&K1, &K2, vpMatches12, s12, R12, t12, th);
+        put<int32_t>(nf);
+        for (int i = 0; i < K1.N; ++i) put<int32_t>(vpMatches12[i] ? vpMatches12[i]->id : -1);
+    } else if (op == 15) {   // ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   (relocalisation)
+        Frame C; std::vector<MapPoint> pool, mps;
+        read_point_frame(C, pool);               // claimed[i] = the frame's keypoint holds a map point
+        float cam[4]; get_n(cam, 4);
+        Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3];
+        C.mTcw = get_pose();
+        C.mfLogScaleFactor = get<float>(); C.mnScaleLevels = get<int32_t>();
+        const float th = get<float>();
+        const int ORBdist = get<int32_t>(), check_ori = get<int32_t>();
+        KeyFrame K;
+        K.N = get<int32_t>();
+        K.mvKeysUn.resize(K.N); get_n(K.mvKeysUn.data(), K.N);
+        K.mvpMapPoints.assign(K.N, nullptr);
+        std::vector<uint8_t> found;
+        read_kf_map_points(K, mps, &found);
+        std::set<MapPoint*> sFound;
+        for (int i = 0; i < K.N; ++i) if (found[i]) sFound.insert(&mps[i]);
+        ORBmatcher matcher(0.9f, check_ori != 0);
+        const int nm = matcher.SearchByProjection(C, &K, sFound, th, ORBdist);
+        put<int32_t>(nm);
+        for (int i = 0; i < C.N; ++i) put<int32_t>(C.mvpMapPoints[i] ? C.mvpMapPoints[i]->id : -1);
+    } else if (op == 16) {   // ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12)
+        KeyFrame K1, K2; std::vector<MapPoint> mps1, mps2;
+        auto read_kf = [&](KeyFrame& K, std::vector<MapPoint>& mps) {
+            K.N = get<int32_t>();
+            K.mvKeysUn.resize(K.N); get_n(K.mvKeysUn.data(), K.N);
+            K.mDescriptors = get_desc_rows(K.N);
+            std::vector<uint8_t> has(K.N), bad(K.N); get_n(has.data(), K.N); get_n(bad.data(), K.N);
+            mps.resize(K.N);
+            K.mvpMapPoints.assign(K.N, nullptr);
+            for (int i = 0; i < K.N; ++i) { mps[i].id = i; mps[i].bad = bad[i] != 0; if (has[i]) K.mvpMapPoints[i] = &mps[i]; }
+            read_featvec(K.mFeatVec);
+        };
+        read_kf(K1, mps1); read_kf(K2, mps2);
+        const float nnratio = get<float>();
+        const int check_ori = get<int32_t>();
+        std::vector<MapPoint*> m12;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int nm = matcher.SearchByBoW(&K1, &K2, m12);
+        put<int32_t>(nm);
+        for (int i = 0; i < K1.N; ++i) put<int32_t>(m12[i] ? m12[i]->id : -1);
+    } else if (op == 17) {   // LSDmatcher::FrameBFMatch, match / matchNNR, SearchDouble(InitialFrame, CurrentFrame, LineMatches)
+        Frame F1, F2;
+        F1.NL = get<int32_t>(); F1.mLdesc = get_desc_rows(F1.NL);
+        F2.NL = get<int32_t>(); F2.mLdesc = get_desc_rows(F2.NL);
+        if (F1.mLdesc.rows != F1.NL) F1.mLdesc = F1.mLdesc.rowRange(0, F1.NL);
+        if (F2.mLdesc.rows != F2.NL) F2.mLdesc = F2.mLdesc.rowRange(0, F2.NL);
+        const float TH = get<float>(), nnratio = get<float>(), nnr = get<float>();
+        LSDmatcher matcher(nnratio, true);
+        std::vector<int> lm, m12, dbl;
+        matcher.FrameBFMatch(F1.mLdesc, F2.mLdesc, lm, TH);
+        const int n_nnr = matcher.match(F1.mLdesc, F2.mLdesc, nnr, m12);
+        const int n_dbl = matcher.SearchDouble(F1, F2, dbl);
+        for (int i = 0; i < F1.NL; ++i) put<int32_t>(lm[i]);
+        put<int32_t>(n_nnr);
+        for (int i = 0; i < F1.NL; ++i) put<int32_t>(m12[i]);
+        put<int32_t>(n_dbl);
+        for (int i = 0; i < F1.NL; ++i) put<int32_t>(dbl[i]);
+    } else if (op == 18) {   // LSDmatcher::SearchByDescriptor(pKF, currentF, vpMapLineMatches), SearchDouble(KF, CurrentFrame)
+        KeyFrame K; Frame F;
+        K.NL = get<int32_t>(); K.mLineDescriptors = get_desc_rows(K.NL);
+        if (K.mLineDescriptors.rows != K.NL) K.mLineDescriptors = K.mLineDescriptors.rowRange(0, K.NL);
+        std::vector<uint8_t> has(K.NL); get_n(has.data(), K.NL);
+        std::vector<MapLine> mls(K.NL);
+        K.mvpMapLines.assign(K.NL, nullptr);
+        for (int i = 0; i < K.NL; ++i) { mls[i].id = i; if (has[i]) K.mvpMapLines[i] = &mls[i]; }
+        F.NL = get<int32_t>(); F.mLdesc = get_desc_rows(F.NL);
+        if (F.mLdesc.rows != F.NL) F.mLdesc = F.mLdesc.rowRange(0, F.NL);
+        F.mvpMapLines.assign(F.NL, nullptr);
+        const float nnratio = get<float>();
+        LSDmatcher matcher(nnratio, true);
+        std::vector<MapLine*> byDesc;
+        const int n1 = matcher.SearchByDescriptor(&K, F, byDesc);
+        const int n2 = matcher.SearchDouble(&K, F);
+        put<int32_t>(n1);
+        for (int i = 0; i < F.NL; ++i) put<int32_t>(byDesc[i] ? byDesc[i]->id : -1);
+        put<int32_t>(n2);
+        for (int i = 0; i < F.NL; ++i) put<int32_t>(F.mvpMapLines[i] ? F.mvpMapLines[i]->id : -1);
     } else {
         return 5;
     }

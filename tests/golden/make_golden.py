@@ -19,6 +19,9 @@ bow_ref.npz    a vocabulary built by the reference's own DBoW2 (TemplatedVocabul
                descriptors, and its transform(features, BowVector, FeatureVector, levelsup) of six frames (oracle/_ref/ref_bow)
 track_ref.npz  outputs of the reference's own Frame::isInFrustum x2, ORBmatcher::SearchForInitialization and LSDmatcher::FrameBFMatchNew
                (oracle/_ref/ref_match ops 4-7) on the scenes of tests/test_track.py
+kf_ref.npz     outputs of the reference's own key-frame matchers (ref_match ops 12-18: ORBmatcher::SearchByProjection(KF, Scw, ...) / (Cur, KF, ...),
+               Fuse(KF, Scw, ...), SearchBySim3, SearchByBoW(KF1, KF2), LSDmatcher::FrameBFMatch / match / SearchDouble x2 / SearchByDescriptor)
+               on the scenes of tests/test_ref_kf.py
 match_ref.npz  outputs of the reference's own windowed matchers (oracle/_ref/ref_match: Frame grids + GetFeaturesInArea*, the two
                ORBmatcher::SearchByProjection and the two LSDmatcher::SearchByProjection, extracted at build time) on the scenes of
                tests/test_ref_match.py: grids, candidate lists, final assignments, match counts.
@@ -221,6 +224,19 @@ def track():
     print('track_ref.npz written:', len(t.RECORD), 'arrays')
 
 
+def kf():
+    if oracle.ref_bin('ref_match') is None:
+        print('oracle/_ref/ref_match missing: run make -C oracle first')
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_ref_kf as t
+    t._golden = None
+    for check in t.CHECKS:
+        check(hvo_b200, synth, gpu=False)          # CPU leg: the mirrors on the oracle must already equal the live reference
+    np.savez_compressed(os.path.join(OUT, 'kf_ref.npz'), **t.RECORD)
+    print('kf_ref.npz written:', len(t.RECORD), 'arrays')
+
+
 def bow():
     if oracle.ref_bin('ref_bow') is None:
         print('oracle/_ref/ref_bow missing: run make -C oracle first')
@@ -232,9 +248,11 @@ def bow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track', 'bow']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track', 'bow', 'kf']
     if 'bow' in which:
         bow()
+    if 'kf' in which:
+        kf()
     if 'track' in which:
         track()
     if 'match' in which:

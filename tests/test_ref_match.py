@@ -58,11 +58,19 @@ def _ref(key, run):
 class OraclePM:
     """hvo.ProjectionMatcher's interface served by the CPU oracle (for the CPU leg of these tests)."""
 
-    def set_frame(self, keys, uright, desc, a, b, c, d):
-        self.k, self.ur, self.d, self.b = keys, uright, desc, (a, b, c, d)
+    def set_frame(self, keys, uright, desc, a, b, c, d, window_origin=None):
+        self.k, self.ur, self.d, self.b, self.wo = keys, uright, desc, (a, b, c, d), window_origin
+
+    def with_origin(self, call):
+        """a key frame locates its windows from its integer image origin (src/KeyFrame.cc:627-666)"""
+        oracle.window_origin(self.wo)
+        try:
+            return call()
+        finally:
+            oracle.window_origin(None)
 
     def search(self, q, qd, claimed, mode, th, ratio):
-        return oracle.search_projection(self.k, self.ur, self.d, self.b, q, qd, claimed, mode, th, ratio)
+        return self.with_origin(lambda: oracle.search_projection(self.k, self.ur, self.d, self.b, q, qd, claimed, mode, th, ratio))
 
 
 class OracleLPM:

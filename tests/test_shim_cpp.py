@@ -169,8 +169,9 @@ def test_dropin_matcher_classes_compile_against_reference_types():
 @pytest.mark.gpu
 def test_dropin_matcher_classes_equal_executed_reference(hvo, synth):
     """The same in.bin the reference's own binary was fed (scenes of tests/test_ref_match.py / tests/test_track.py) through the drop-in
-    classes: ORBmatcher::SearchByProjection x2 and SearchForInitialization, LSDmatcher::SearchByProjection x2 and FrameBFMatchNew,
-    Frame::isInFrustum x2 (batched) must write what the reference wrote (committed fixtures match_ref.npz / track_ref.npz)."""
+    classes: all twelve public methods of ORBmatcher (SearchByProjection x4, SearchByBoW x2, SearchForInitialization, SearchForTriangulation,
+    SearchBySim3, Fuse x2), LSDmatcher::SearchByProjection x2, FrameBFMatch, FrameBFMatchNew, match, SearchDouble x2, SearchByDescriptor and
+    Frame::isInFrustum x2 (batched) must write what the reference wrote (committed fixtures match_ref.npz / track_ref.npz / kf_ref.npz)."""
     import oracle
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import test_ref_match as trm
@@ -193,5 +194,14 @@ def test_dropin_matcher_classes_equal_executed_reference(hvo, synth):
         for seed, ratio, ori in ((0, 0.7, True), (1, 0.9, True), (2, 0.75, False)):
             KF, F = _bow_scenario(synth, seed)
             tt._ref(f'bow{seed}', lambda: oracle.ref_search_by_bow(KF, F, ratio, ori))
+        # the key-frame side (tests/test_ref_kf.py, fixture kf_ref.npz): SearchByProjection(pKF, Scw, ...) / (Cur, pKF, found, th, ORBdist),
+        # Fuse(pKF, Scw, ...), SearchBySim3, SearchByBoW(pKF1, pKF2), LSDmatcher::FrameBFMatch / match / SearchDouble x2 / SearchByDescriptor,
+        # and SearchForTriangulation / Fuse(pKF, vpMapPoints, th) (fixture track_ref.npz): every public method of the two matcher classes
+        import test_ref_kf as tk
+        assert tk._golden is not None
+        for check in tk.CHECKS:
+            check(hvo, synth, gpu=True)
+        tt._check_triangulation(hvo, synth, gpu=True)
+        tt._check_fuse(hvo, synth, gpu=True)
     finally:
         oracle.MATCH_EXE[0] = None

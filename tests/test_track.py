@@ -318,7 +318,7 @@ def _check_fuse(hvo, synth, gpu):
 
         def search(self, q, qd, claimed, mode, th, ratio):
             assert mode == 2
-            return oracle.search_fuse(self.k, self.ur, self.d, self.b, q, qd, self.sig, th)
+            return self.with_origin(lambda: oracle.search_fuse(self.k, self.ur, self.d, self.b, q, qd, self.sig, th))
     total = 0
     for seed, th in ((0, 3.0), (1, 5.0)):
         rng = np.random.RandomState(80 + seed)
