@@ -413,6 +413,15 @@ def test_opencv_float_matrix_rules():
         assert cv2.norm(v) == np.sqrt(np.float64(v[0, 0]) ** 2 + np.float64(v[1, 0]) ** 2 + np.float64(v[2, 0]) ** 2)
         a = (rng.randn(3, 1) * 10 ** rng.uniform(-3, 3)).astype(f32); b = (rng.randn(3, 1) * 10 ** rng.uniform(-3, 3)).astype(f32)
         assert np.array_equal(cv2.addWeighted(a, 0.5, b, 0.5, 0), (a * f32(0.5) + b * f32(0.5)).astype(f32))
+        # -R.t() * t (ORBmatcher.cc:308, 1009, 1366, 1505) = one gemm(R, t, -1, GEMM_1_T): off the small-matrix path, double accumulation
+        g = cv2.gemm(R, t, -1.0, None, 0.0, flags=cv2.GEMM_1_T)
+        for i in range(3):
+            acc = 0.0
+            for k in range(3):
+                acc += float(R[k, i]) * float(t[k, 0])
+            assert g[i, 0] == f32(acc * -1.0)
+        # (A / s and s * A, ORBmatcher.cc:306-307, 1140-1141, are Mat::convertTo(alpha): a float product with (float)alpha in OpenCV's sources;
+        #  convertTo has no Python binding to check against)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
