@@ -1245,6 +1245,25 @@ def lpvo_normals(depth16, factor, fx, fy, cx, cy):
     return nrm[:n], dep[:n], pix[:n]
 
 
+def ref_lpvo(depth16, factor, fx, fy, cx, cy, as_built=False):
+    """The reference's own Manhattan::computeNormalsLPVO executed (oracle/_ref/ref_lpvo: src/Manhattan.cpp:237-393 + removeMatRow / removeMatCol
+    compiled with their cv::Rect body; as_built=True: the memcpy body Manhattan.cpp is built with, which mis-sizes the CV_64F rows).
+    Returns (normals [n,3] float64, depth [n] float32) in push_back order, or None when the binary is absent."""
+    exe = ref_bin('ref_lpvo_asbuilt' if as_built else 'ref_lpvo')
+    if exe is None:
+        return None
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('<2i5f', w, h, float(factor), float(fx), float(fy), float(cx), float(cy)) + d.tobytes())
+        subprocess.check_call([exe, fi, fo], stdout=subprocess.DEVNULL)
+        raw = open(fo, 'rb').read()
+    (n,) = struct.unpack_from('<i', raw, 0)
+    return np.frombuffer(raw, np.float64, 3 * n, 4).reshape(n, 3).copy(), np.frombuffer(raw, np.float32, n, 4 + 24 * n).copy()
+
+
 # ---- whole front-end (bench.py CPU arm) ----------------------------------------------------------------------
 def frontend_batch(gray, depth, cam, stages=15, nthreads=1, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                    nlines=200):

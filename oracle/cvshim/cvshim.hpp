@@ -232,6 +232,7 @@ public:
         step.v = (size_t)c * cvshim_elem_size(type);
     }
     void release() { buf_.reset(); rows = cols = 0; data = nullptr; step.v = 0; }
+    Mat(const MatZerosExpr& z) : rows(0), cols(0), data(nullptr) { create(z.rows, z.cols, z.type); }   // cv::Mat m = cv::Mat::zeros(...): fresh, zero-filled
     Mat& operator=(const MatZerosExpr& z) {
         create(z.rows, z.cols, z.type);  // no-op for a view of matching size: zeros are written in place
         for (int y = 0; y < rows; ++y) std::memset(data + (size_t)y * step.v, 0, (size_t)cols);
@@ -251,6 +252,10 @@ public:
     MatTExpr t() const;  // CV_32F only (pose blocks); an expression, as in OpenCV: see MatTExpr below
     Mat row(int y) const { return (*this)(Rect(0, y, cols, 1)); }
     void copyTo(Mat& dst) const { dst = clone(); }
+    void copyTo(Mat&& view) const {   // src(rect).copyTo(dst(rect)): the destination is a view of the same size and type, written in place
+        assert(view.rows == rows && view.cols == cols && view.type_ == type_);
+        for (int y = 0; y < rows; ++y) std::memmove(view.data + (size_t)y * view.step.v, data + (size_t)y * step.v, (size_t)cols * cvshim_elem_size(type_));
+    }
     void copyTo(const class _OutputArray& dst) const;
     bool isContinuous() const { return step.v == (size_t)cols * cvshim_elem_size(type_); }
     Mat cross(const Mat& o) const;   // CV_32F 3-vectors (LSDmatcher::FrameBFMatchNew)

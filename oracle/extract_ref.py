@@ -82,6 +82,9 @@ RANGES = {
                ('src/LSDmatcher.cpp', 803, 966, 'int LSDmatcher::matchNNR('),
                ('src/LSDmatcher.cpp', 1110, 1135, 'void LSDmatcher::lineDescriptorMAD('),
                ('src/Frame.cc', 1331, 1355, 'void Frame::lineDescriptorMAD(')],
+    # Manhattan::computeNormalsLPVO, removeMatRow, removeMatCol
+    'manhattan_lpvo': [('src/Manhattan.cpp', 237, 393, 'void Manhattan::computeNormalsLPVO('),
+                       ('src/Manhattan.cpp', 395, 493, 'void Manhattan::removeMatRow(')],
     # MapPoint::ComputeDistinctiveDescriptors, MapLine::ComputeDistinctiveDescriptors
     'distinctive': [('src/MapPoint.cc', 240, 305, 'void MapPoint::ComputeDistinctiveDescriptors()'),
                     ('src/MapLine.cpp', 331, 396, 'void MapLine::ComputeDistinctiveDescriptors()')],

@@ -7,8 +7,11 @@
 //
 // cv::integral is un-vendored OpenCV: its accumulation order (per row a running double sum s, sum[y][x] = sum[y-1][x] + s)
 // is restated in orc_integral_f32 and PINNED to cv2 4.13.0 (tests/golden/prims_cv2.npz + live when cv2 is importable).
-// cv::normalize of the 3x1 double vector is pinned the same way (orc_normalize3).  The rest follows the source text only:
-// PARITY UNPINNED by execution (Manhattan.cpp needs OpenCV).
+// cv::normalize of the 3x1 double vector is pinned the same way (orc_normalize3).  The function itself is PINNED BY EXECUTION:
+// oracle/_ref/ref_lpvo compiles Manhattan.cpp:237-393 + removeMatRow / removeMatCol (cv::Rect body) against the OpenCV stand-in and
+// this file reproduces its output bit for bit (tests/test_lpvo.py, fixture tests/golden/lpvo_ref.npz).  The memcpy body of removeMatRow /
+// removeMatCol that Manhattan.cpp is actually built with (USE_CV_RECT is defined in Frame.cc only) sizes CV_64F rows with sizeof(float) and
+// turns most normals into NaN; it is executed too (ref_lpvo_asbuilt) but not followed.
 //
 // Reference bug: the live caller hands the raw CV_16U Mat to this function, which reads it with
 // .at<float>.  Oracle and GPU implement the intended behaviour: the float depth image imDepth.convertTo(CV_32F, factor).

@@ -19,6 +19,7 @@ bow_ref.npz    a vocabulary built by the reference's own DBoW2 (TemplatedVocabul
                descriptors, and its transform(features, BowVector, FeatureVector, levelsup) of six frames (oracle/_ref/ref_bow)
 track_ref.npz  outputs of the reference's own Frame::isInFrustum x2, ORBmatcher::SearchForInitialization and LSDmatcher::FrameBFMatchNew
                (oracle/_ref/ref_match ops 4-7) on the scenes of tests/test_track.py
+lpvo_ref.npz   outputs of the reference's own Manhattan::computeNormalsLPVO (oracle/_ref/ref_lpvo, cv::Rect body of removeMatRow / removeMatCol)
 kf_ref.npz     outputs of the reference's own key-frame matchers (ref_match ops 12-18: ORBmatcher::SearchByProjection(KF, Scw, ...) / (Cur, KF, ...),
                Fuse(KF, Scw, ...), SearchBySim3, SearchByBoW(KF1, KF2), LSDmatcher::FrameBFMatch / match / SearchDouble x2 / SearchByDescriptor)
                on the scenes of tests/test_ref_kf.py
@@ -224,6 +225,22 @@ def track():
     print('track_ref.npz written:', len(t.RECORD), 'arrays')
 
 
+def lpvo_ref():
+    if oracle.ref_bin('ref_lpvo') is None:
+        print('oracle/_ref/ref_lpvo missing: run make -C oracle first')
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_lpvo as t
+    out = {}
+    for cfg, idx in t.REF_CASES:
+        for k in (0, 1):
+            cam = t._cam(synth, cfg)
+            n, z = oracle.ref_lpvo(t._holes(synth.frame(cfg, idx)[1], k), **cam)
+            out[f'{cfg}_{idx}_{k}_n'] = n; out[f'{cfg}_{idx}_{k}_z'] = z
+    np.savez_compressed(os.path.join(OUT, 'lpvo_ref.npz'), **out)
+    print('lpvo_ref.npz written:', len(out), 'arrays')
+
+
 def kf():
     if oracle.ref_bin('ref_match') is None:
         print('oracle/_ref/ref_match missing: run make -C oracle first')
@@ -248,11 +265,13 @@ def bow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track', 'bow', 'kf']
+    which = sys.argv[1:] or ['prims', 'orb', 'lsd', 'lpvo', 'peac', 'lines', 'match', 'track', 'bow', 'kf', 'lpvo_ref']
     if 'bow' in which:
         bow()
     if 'kf' in which:
         kf()
+    if 'lpvo_ref' in which:
+        lpvo_ref()
     if 'track' in which:
         track()
     if 'match' in which:

@@ -1,6 +1,7 @@
 """Manhattan::computeNormalsLPVO (reference src/Manhattan.cpp:237-393): oracle pins and CUDA parity.
-Bar: the two OpenCV primitives inside it (cv::integral 32F->64F, cv::normalize) bit-exact vs cv2 4.13.0; the CUDA path
-returns the same samples in the same order with bit-identical doubles (it adds in cv::integral's order)."""
+Bar: the two OpenCV primitives inside it (cv::integral 32F->64F, cv::normalize) bit-exact vs cv2 4.13.0; the function itself EXECUTED
+(oracle/_ref/ref_lpvo, fixture tests/golden/lpvo_ref.npz); oracle and CUDA return the reference's samples in its order with bit-identical
+doubles (they add in cv::integral's order)."""
 import os
 
 import numpy as np
@@ -48,6 +49,73 @@ def test_oracle_lpvo_on_the_synthetic_room(synth):
     # an empty depth image has no valid tangent anywhere
     n0, _, _ = oracle.lpvo_normals(np.zeros_like(d), **cam)
     assert len(n0) == 0
+
+
+GOLDEN_REF = os.path.join(ROOT, 'tests', 'golden', 'lpvo_ref.npz')
+REF_CASES = [('S1', 0), ('S2', 3), ('S1', 5)]
+
+
+def _holes(d, k):
+    """case k > 0 of a frame: a hole, a strip at the range limits (z = 0.2 exactly; z = 8 > 7)"""
+    d = d.copy()
+    if k:
+        d[100:300, 200:400] = 0
+        d[:, :40] = 1000
+        d[:, 600:] = 40000
+    return d
+
+
+def _ref_lpvo(synth, cfg, idx, k):
+    """the executed reference's (normals, depth) for a case: live when oracle/_ref/ref_lpvo exists (and equal to the fixture), else the fixture"""
+    cam = _cam(synth, cfg)
+    d = _holes(synth.frame(cfg, idx)[1], k)
+    key = f'{cfg}_{idx}_{k}'
+    g = np.load(GOLDEN_REF) if os.path.exists(GOLDEN_REF) else None
+    live = oracle.ref_lpvo(d, **cam)
+    if live is not None:
+        if g is not None and key + '_n' in g:
+            assert live[0].tobytes() == g[key + '_n'].tobytes() and live[1].tobytes() == g[key + '_z'].tobytes(), 'fixture differs from the live reference'
+        return d, cam, live[0], live[1]
+    if g is None:
+        pytest.skip('neither oracle/_ref/ref_lpvo nor tests/golden/lpvo_ref.npz is available')
+    return d, cam, g[key + '_n'], g[key + '_z']
+
+
+@pytest.mark.parametrize('cfg,idx', REF_CASES)
+def test_oracle_lpvo_equals_executed_reference(synth, cfg, idx):
+    """Manhattan::computeNormalsLPVO executed (src/Manhattan.cpp:237-393 + removeMatRow / removeMatCol, cv::Rect body; oracle/ref_lpvo_main.cpp):
+    same samples in the same order, doubles bit for bit."""
+    for k in (0, 1):
+        d, cam, rn, rz = _ref_lpvo(synth, cfg, idx, k)
+        n, z, _ = oracle.lpvo_normals(d, **cam)
+        assert len(rn) > 300 and n.tobytes() == rn.tobytes() and z.tobytes() == rz.tobytes()
+
+
+def test_reference_lpvo_as_built_corrupts_its_integral_images(synth):
+    """Manhattan.cpp is built WITHOUT USE_CV_RECT (only src/Frame.cc:32 defines it): removeMatRow / removeMatCol then move
+    width * sizeof(float) bytes per row of a CV_64F integral image.  Executed, that body turns most normals into NaN: the pin above
+    uses the cv::Rect body, which does what the function's comment says."""
+    cam = _cam(synth, 'S1')
+    d = synth.frame('S1', 0)[1]
+    good, bad = oracle.ref_lpvo(d, **cam), oracle.ref_lpvo(d, as_built=True, **cam)
+    if good is None or bad is None:
+        pytest.skip('oracle/_ref/ref_lpvo is not built (reference tree absent)')
+    assert len(good[0]) == len(bad[0]) and not np.isnan(good[0]).any()
+    assert np.isnan(bad[0]).mean() > 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cfg,idx', REF_CASES)
+def test_gpu_lpvo_equals_executed_reference(hvo, synth, cfg, idx):
+    K = None
+    for k in (0, 1):
+        d, cam, rn, rz = _ref_lpvo(synth, cfg, idx, k)
+        if K is None:
+            K = np.array([[cam['fx'], 0, cam['cx']], [0, cam['fy'], cam['cy']], [0, 0, 1]], np.float32)
+            m = hvo.Manhattan(K, 640, 480, cam['factor'])
+        n, z, _ = m.computeNormalsLPVO(d)
+        assert n.tobytes() == rn.tobytes() and z.tobytes() == rz.tobytes()
+    m.close()
 
 
 @pytest.mark.gpu
