@@ -893,10 +893,11 @@ def bow_transform(voc, desc, levelsup=4):
     return (bw[:k1.value].copy(), bv[:k1.value].copy()), fv, word[:n].copy(), node[:n].copy()
 
 
-def ref_bow(training, frames, k=10, L=4, seed=1, levelsup=2):
+def ref_bow(training, frames, k=10, L=4, seed=1, levelsup=2, exe_name='ref_bow'):
     """The reference's own DBoW2 executed (oracle/_ref/ref_bow): builds a vocabulary with TemplatedVocabulary::create from `training`
-    (list of [n,32] descriptor arrays) and transforms `frames`.  Returns (voc dict, [((words, values), fv dict)]) or None."""
-    exe = ref_bin('ref_bow')
+    (list of [n,32] descriptor arrays) and transforms `frames`.  Returns (voc dict, [((words, values), fv dict)]) or None.
+    exe_name='shim_bow': the same driver and DBoW2 vocabulary object with the transform routed through shim/ORBVocabularyGPU.h (needs a GPU)."""
+    exe = ref_bin(exe_name)
     if exe is None:
         return None
     b = struct.pack('<6i', 0x424f5756, k, L, seed, levelsup, len(training))

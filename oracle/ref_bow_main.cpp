@@ -19,6 +19,9 @@
 #include "DBoW2/FORB.h"
 #include "DBoW2/TemplatedVocabulary.h"
 #include "DUtils/Random.h"
+#ifdef REF_BOW_USE_SHIM   // oracle/_ref/shim_bow: the same driver, the transform through the drop-in (shim/ORBVocabularyGPU.h -> C ABI -> CUDA)
+#include "ORBVocabularyGPU.h"
+#endif
 
 using namespace DBoW2;
 
@@ -66,11 +69,19 @@ int main(int argc, char** argv) {
         put<double>(nd.weight);
     }
     const int nframes = get<int32_t>();
+#ifdef REF_BOW_USE_SHIM
+    hvo_shim::BowTransformerT<TemplatedVocabulary<FORB::TDescriptor, FORB>> gpu(voc);   // handed the reference's own vocabulary object
+    if (!gpu.valid()) return 7;
+#endif
     for (int f = 0; f < nframes; ++f) {
         std::vector<cv::Mat> feats = get_descriptors();
         BowVector bv;
         FeatureVector fv;
+#ifdef REF_BOW_USE_SHIM
+        gpu.transform(feats, bv, fv, levelsup);
+#else
         voc.transform(feats, bv, fv, levelsup);
+#endif
         put<int32_t>((int32_t)bv.size());
         for (const auto& e : bv) { put<int32_t>((int32_t)e.first); put<double>(e.second); }
         put<int32_t>((int32_t)fv.size());

@@ -98,3 +98,21 @@ def test_gpu_bow_equals_oracle_and_reference(hvo, ref):
         _check(g, (o[0], o[1]))
         assert np.array_equal(g[3], o[3])
     v.close()
+
+
+@pytest.mark.gpu
+def test_dropin_bow_transformer_equals_executed_reference(synth, ref):
+    """oracle/_ref/shim_bow = the executed reference's own driver (oracle/ref_bow_main.cpp) and DBoW2's own vocabulary object, built by its
+    create(), with transform(features, BowVector, FeatureVector, levelsup) routed through the drop-in hvo_shim::BowTransformerT
+    (shim/ORBVocabularyGPU.h -> C ABI -> CUDA): it must write what the reference's transform wrote.  The binary compiles DBoW2's sources, so it
+    is built where the reference tree is mounted (oracle/Makefile) and travels with oracle/_ref."""
+    if oracle.ref_bin('shim_bow') is None:
+        pytest.skip('oracle/_ref/shim_bow is not built (reference tree absent at build time)')
+    voc, res, frames = ref
+    train, frames2 = _descriptors(synth)
+    svoc, sres = oracle.ref_bow(train, frames2, K, L, 1, LEVELSUP, exe_name='shim_bow')
+    for k in ('child_start', 'child_ids', 'node_desc', 'node_weight', 'node_word'):
+        assert np.asarray(svoc[k]).tobytes() == np.asarray(voc[k]).tobytes()
+    assert len(sres) == len(res)
+    for got, want in zip(sres, res):
+        _check(got, want)
