@@ -1190,6 +1190,22 @@ class LSDmatcher:
                 out[i] = j
         return int((out >= 0).sum()), out
 
+    def SearchForTriangulation(self, ldesc1, has_mapline1, ldesc2, has_mapline2, th=None, is_double=True):
+        """LSDmatcher::SearchForTriangulation (src/LSDmatcher.cpp:1155-1231): FrameBFMatch both ways; th = TH_LOW with the cross-check always on
+        is the vector<pair> overload (:1155-1193), th = TH_HIGH with is_double the vector<int> overload (:1195-1231); pairs where either line
+        already holds a MapLine are dropped.  Returns (nmatches, match [len(ldesc1)] = line of pKF2 or -1)."""
+        th = self.TH_LOW if th is None else th
+        out = np.full(len(ldesc1), -1, np.int32)
+        if len(ldesc1) == 0 or len(ldesc2) == 0:
+            return 0, out
+        m12 = self.FrameBFMatch(ldesc1, ldesc2, th)
+        m21 = self.FrameBFMatch(ldesc2, ldesc1, th)
+        h1, h2 = np.asarray(has_mapline1, bool), np.asarray(has_mapline2, bool)
+        for i, j in enumerate(m12):
+            if j >= 0 and (not is_double or m21[j] == i) and not (h1[i] or h2[j]):
+                out[i] = j
+        return int((out >= 0).sum()), out
+
     def SearchByDescriptor(self, ldesc_kf, ldesc_cur, has_mapline=None):
         """Matching part of LSDmatcher::SearchByDescriptor(pKF, currentF, vpMapLineMatches) (src/LSDmatcher.cpp:522-559): knn-2 of
         the key frame's descriptors in the current frame, accepted when d0 / d1 < 1 / 1.5 AND the key-frame line holds a MapLine

@@ -17,6 +17,8 @@
 //   SearchByDescriptor(pKF, currentF, vpMapLineMatches)    src/LSDmatcher.cpp:522-559   (KeyFrame type deduced: mLineDescriptors, GetMapLineMatches())
 //   SearchDouble(InitialFrame, CurrentFrame, LineMatches)  src/LSDmatcher.cpp:903-940   (FrameBFMatch both ways + cross-check)
 //   SearchDouble(KF, CurrentFrame)                         src/LSDmatcher.cpp:865-901   (KF->NL, mLineDescriptors, GetMapLine())
+//   SearchForTriangulation(pKF1, pKF2, vector<pair>&)      src/LSDmatcher.cpp:1155-1193 (FrameBFMatch both ways at TH_LOW, cross-check, no MapLine)
+//   SearchForTriangulation(pKF1, pKF2, vector<int>&, dbl)  src/LSDmatcher.cpp:1195-1231 (TH_HIGH, optional cross-check)
 //   DescriptorDistance                                     src/LSDmatcher.cpp:1137-1153
 #ifndef HVO_SHIM_LSDMATCHER_H
 #define HVO_SHIM_LSDMATCHER_H
@@ -24,6 +26,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "hvo_capi.h"
@@ -185,6 +188,50 @@ public:
                 MapLine* pML = KF->GetMapLine(j);
                 if (!pML) continue;
                 CurrentFrame.mvpMapLines[i] = pML;
+                nmatches++;
+            }
+        }
+        return nmatches;
+    }
+
+    // src/LSDmatcher.cpp:1155-1193
+    template <class KeyFrame>
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs) {
+        vMatchedPairs.clear();
+        std::vector<int> tempMatches1, tempMatches2;
+        cv::Mat ldesc1 = pKF1->mLineDescriptors, ldesc2 = pKF2->mLineDescriptors;
+        if (ldesc1.rows == 0 || ldesc2.rows == 0) return 0;
+        int nmatches = 0;
+        FrameBFMatch(ldesc1, ldesc2, tempMatches1, TH_LOW);
+        FrameBFMatch(ldesc2, ldesc1, tempMatches2, TH_LOW);
+        for (size_t i = 0; i < tempMatches1.size(); i++) {
+            int j = tempMatches1[i];
+            if (j >= 0 && tempMatches2[j] == (int)i) {
+                if (pKF1->GetMapLine(i) || pKF2->GetMapLine(j)) continue;
+                vMatchedPairs.push_back(std::make_pair(i, (size_t)j));
+                nmatches++;
+            }
+        }
+        return nmatches;
+    }
+
+    // src/LSDmatcher.cpp:1195-1231
+    template <class KeyFrame>
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<int>& vMatchedPairs, bool isDouble = false) {
+        vMatchedPairs.clear();
+        vMatchedPairs.resize(pKF1->NL, -1);
+        std::vector<int> tempMatches1, tempMatches2;
+        cv::Mat ldesc1 = pKF1->mLineDescriptors, ldesc2 = pKF2->mLineDescriptors;
+        if (ldesc1.rows == 0 || ldesc2.rows == 0) return 0;
+        int nmatches = 0;
+        FrameBFMatch(ldesc1, ldesc2, tempMatches1, TH_HIGH);
+        FrameBFMatch(ldesc2, ldesc1, tempMatches2, TH_HIGH);
+        for (size_t i = 0; i < tempMatches1.size(); i++) {
+            int j = tempMatches1[i];
+            if (j >= 0) {
+                if (isDouble && tempMatches2[j] != (int)i) continue;
+                if (pKF1->GetMapLine(i) || pKF2->GetMapLine(j)) continue;
+                vMatchedPairs[i] = j;
                 nmatches++;
             }
         }

@@ -1159,6 +1159,28 @@ def ref_line_by_descriptor(kf_ldesc, kf_has_mapline, ldesc, nnratio):
     return n1, by, nd, dbl
 
 
+def ref_line_triangulation(ldesc1, has1, ldesc2, has2, nnratio):
+    """The reference's LSDmatcher::SearchForTriangulation(pKF1, pKF2, vector<pair>&) and (pKF1, pKF2, vector<int>&, isDouble) for isDouble =
+    false / true executed (op 19).  Returns (n, pairs [n,2], n_single, match_single [NL1], n_double, match_double [NL1]) or None."""
+    d1 = np.ascontiguousarray(ldesc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(ldesc2, np.uint8).reshape(-1, 32)
+    n1 = len(d1)
+    b = struct.pack('<2i', 0x4d544348, 19) + _f32([0, 0, 640, 480])
+    b += struct.pack('<i', n1) + d1.tobytes() + np.asarray(has1, np.uint8).tobytes()
+    b += struct.pack('<i', len(d2)) + d2.tobytes() + np.asarray(has2, np.uint8).tobytes() + struct.pack('<f', float(nnratio))
+    raw = _run_ref_match(b)
+    if raw is None:
+        return None
+    n0, npairs = struct.unpack_from('<2i', raw, 0)
+    pairs = np.frombuffer(raw, np.int32, 2 * npairs, 8).reshape(npairs, 2).copy()
+    off = 8 + 8 * npairs
+    out = [n0, pairs]
+    for _ in range(2):
+        (n,) = struct.unpack_from('<i', raw, off)
+        out += [n, np.frombuffer(raw, np.int32, n1, off + 4).copy()]
+        off += 4 + 4 * n1
+    return tuple(out)
+
+
 def surface_normals(depth16, factor, fx, fy, cx, cy, max_depth_change=0.05, smoothing=10.0, want_dist=False):
     d = np.ascontiguousarray(depth16, np.uint16)
     h, w = d.shape

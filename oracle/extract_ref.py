@@ -82,6 +82,8 @@ RANGES = {
                ('src/LSDmatcher.cpp', 803, 966, 'int LSDmatcher::matchNNR('),
                ('src/LSDmatcher.cpp', 1110, 1135, 'void LSDmatcher::lineDescriptorMAD('),
                ('src/Frame.cc', 1331, 1355, 'void Frame::lineDescriptorMAD(')],
+    # LSDmatcher::SearchForTriangulation(pKF1, pKF2, vector<pair>&) and (pKF1, pKF2, vector<int>&, isDouble)
+    'lsd_tri': [('src/LSDmatcher.cpp', 1155, 1231, 'int LSDmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2,')],
     # Manhattan::computeNormalsLPVO, removeMatRow, removeMatCol
     'manhattan_lpvo': [('src/Manhattan.cpp', 237, 393, 'void Manhattan::computeNormalsLPVO('),
                        ('src/Manhattan.cpp', 395, 493, 'void Manhattan::removeMatRow(')],

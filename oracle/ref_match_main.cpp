@@ -19,6 +19,7 @@
 //                                                            whole; src/KeyFrame.cc:254-267 GetMapPoints, src/MapPoint.cc:313-320 GetIndexInKeyFrame
 //   include/auxiliar.h:26-38, src/LSDmatcher.cpp:522-559, 803-966, 1110-1135, src/Frame.cc:1331-1355   SearchByDescriptor, matchNNR, match,
 //                                                            SearchDouble x2, FrameBFMatch, lineDescriptorMAD x2 (their std::threads included)
+//   src/LSDmatcher.cpp:1155-1231                             SearchForTriangulation(pKF1, pKF2, vector<pair>&) and (pKF1, pKF2, vector<int>&, isDouble)
 //   src/lineIterator.cpp                                     whole file, unmodified
 // and compiled against stand-in Frame / MapPoint / MapLine classes that carry exactly the members those functions touch
 // (declared below with the reference header line each one mirrors) plus the OpenCV / Eigen stand-ins.
@@ -257,6 +258,8 @@ public:
     int SearchDouble(KeyFrame* KF, Frame& CurrentFrame);
     void FrameBFMatch(cv::Mat ldesc1, cv::Mat ldesc2, vector<int>& LineMatches, float TH);
     void lineDescriptorMAD(vector<vector<DMatch>> line_matches, double& nn_mad, double& nn12_mad) const;
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t, size_t>>& vMatchedPairs);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<int>& vMatchedPairs, bool isDouble = false);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     double computeAngle2D(const cv::Mat& vector1, const cv::Mat& vector2);
@@ -288,6 +291,7 @@ namespace ORB_SLAM2 {
 #include "gen/lsdmatcher.inc"
 #include "gen/lsd_bfnew.inc"
 #include "gen/lsd_bf.inc"
+#include "gen/lsd_tri.inc"
 #include "gen/distinctive.inc"
 }  // namespace ORB_SLAM2
 #else
@@ -920,6 +924,31 @@ int main(int argc, char** argv) {
         for (int i = 0; i < F.NL; ++i) put<int32_t>(byDesc[i] ? byDesc[i]->id : -1);
         put<int32_t>(n2);
         for (int i = 0; i < F.NL; ++i) put<int32_t>(F.mvpMapLines[i] ? F.mvpMapLines[i]->id : -1);
+    } else if (op == 19) {   // LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs) and (pKF1, pKF2, vMatchedPairs, isDouble) x2
+        KeyFrame K1, K2;
+        std::vector<MapLine> ml1, ml2;
+        auto read_kf = [&](KeyFrame& K, std::vector<MapLine>& mls) {
+            K.NL = get<int32_t>(); K.mLineDescriptors = get_desc_rows(K.NL);
+            if (K.mLineDescriptors.rows != K.NL) K.mLineDescriptors = K.mLineDescriptors.rowRange(0, K.NL);
+            std::vector<uint8_t> has(K.NL); get_n(has.data(), K.NL);
+            mls.resize(K.NL);
+            K.mvpMapLines.assign(K.NL, nullptr);
+            for (int i = 0; i < K.NL; ++i) { mls[i].id = i; if (has[i]) K.mvpMapLines[i] = &mls[i]; }
+        };
+        read_kf(K1, ml1); read_kf(K2, ml2);
+        const float nnratio = get<float>();
+        LSDmatcher matcher(nnratio, true);
+        std::vector<pair<size_t, size_t>> pairs;
+        const int n0 = matcher.SearchForTriangulation(&K1, &K2, pairs);
+        put<int32_t>(n0);
+        put<int32_t>((int32_t)pairs.size());
+        for (const auto& pr : pairs) { put<int32_t>((int32_t)pr.first); put<int32_t>((int32_t)pr.second); }
+        for (int dbl = 0; dbl < 2; ++dbl) {
+            std::vector<int> m;
+            const int n = matcher.SearchForTriangulation(&K1, &K2, m, dbl != 0);
+            put<int32_t>(n);
+            for (int i = 0; i < K1.NL; ++i) put<int32_t>(m[i]);
+        }
     } else {
         return 5;
     }

@@ -443,6 +443,14 @@ def _check_line_bf(hvo, synth, gpu):
         assert n1 == int(n1_r) and np.array_equal(by, by_r)
         nd, dk = m.SearchDoubleKF(ld1, has, ld2)
         assert nd == int(nd_r) and np.array_equal(dk, dk_r)
+        has2 = rng.rand(len(ld2)) < 0.3
+        n0_r, pairs_r, ns_r, ms_r, ndb_r, mdb_r = _ref(f'ltri{seed}', lambda: oracle.ref_line_triangulation(ld1, has, ld2, has2, ratio))
+        n0, m0 = m.SearchForTriangulation(ld1, has, ld2, has2)
+        i0 = np.nonzero(m0 >= 0)[0]
+        assert n0 == int(n0_r) and np.array_equal(np.stack([i0, m0[i0]], 1).reshape(-1, 2), np.asarray(pairs_r).reshape(-1, 2))
+        for dbl, nr, mr in ((False, ns_r, ms_r), (True, ndb_r, mdb_r)):
+            n, mm = m.SearchForTriangulation(ld1, has, ld2, has2, th=m.TH_HIGH, is_double=dbl)
+            assert n == int(nr) and np.array_equal(mm, mr)
         total += n_dbl + n1 + nd
     assert oracle.MATCH_EXE[0] or total > 60
 
