@@ -115,7 +115,7 @@ def bind_to_gpu_numa_node(gpu_index):
         cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
         allowed = os.sched_getaffinity(0)
         cpus = sorted(set(cpus) & allowed)
-        if not cpus or len(cpus) >= len(allowed):
+        if len(cpus) < 4 or len(cpus) >= len(allowed):   # one node, or a cpuset that leaves this GPU next to no local CPUs: stay unbound
             return None
         os.sched_setaffinity(0, cpus)
         return cpus
