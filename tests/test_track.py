@@ -320,11 +320,20 @@ def _check_fuse(hvo, synth, gpu):
             assert mode == 2
             return self.with_origin(lambda: oracle.search_fuse(self.k, self.ur, self.d, self.b, q, qd, self.sig, th))
     total = 0
-    for seed, th in ((0, 3.0), (1, 5.0)):
+    for seed, th in ((0, 3.0), (1, 5.0), (2, 4.0)):
         rng = np.random.RandomState(80 + seed)
         F, _, _, _ = _point_scene(synth, seed)            # key frame = the point frame of the projection tests
         k0, n0 = F['keys_un'], len(F['keys_un'])
         cam, R, t = _cam(hvo, rng)
+        bounds = BOUNDS
+        if seed == 2:
+            # a distorted camera's image bounds are not integers: the key frame truncates them (include/KeyFrame.h:249-252) for IsInImage and
+            # for the origin of its window lookups (src/KeyFrame.cc:627-666), in a grid its Frame assigned with the float bounds
+            bounds = (-13.6, -9.3, 655.2, 492.7)
+            F = dict(F); F['bounds'] = bounds
+            cam = np.array(cam, copy=True)
+            for k, b in zip(('min_x', 'min_y', 'max_x', 'max_y'), bounds):
+                cam[k] = np.float32(int(b))
         z = rng.uniform(0.8, 5.0, n0)
         Pc = np.stack([(k0['x'] + rng.normal(0, 1, n0) - 320.1) * z / 535.4, (k0['y'] + rng.normal(0, 1, n0) - 247.6) * z / 539.2, z], 1)
         pts = np.concatenate([_point_batch(rng, R, t, n0), _point_batch(rng, R, t, 400)])
@@ -349,7 +358,7 @@ def _check_fuse(hvo, synth, gpu):
         ok, u, v, ur, level = _fuse_project(cam, pts)
         use = ok & present & ~bad & ~in_kf
         sel = np.nonzero(use)[0]
-        KF = dict(keys_un=k0, uright=F['uright'], desc=F['desc'], bounds=BOUNDS, scale_factors=SF, inv_level_sigma2=inv)
+        KF = dict(keys_un=k0, uright=F['uright'], desc=F['desc'], bounds=bounds, scale_factors=SF, inv_level_sigma2=inv)
         MPs = dict(u=u[sel], v=v[sel], ur=ur[sel], level=level[sel], desc=pdesc[sel])
         if gpu:
             m = hvo.ORBmatcher(0.6, True)
