@@ -207,7 +207,10 @@ int hvo_proj_set_frame(hvo_proj* h, const hvo_keypoint* keys_un, const float* ur
  * frame's float bounds, same mfGridElement*Inv) but computes the cell range of a window from its own INTEGER mnMinX / mnMinY
  * (include/KeyFrame.h:249-252: the float bounds truncated), which differs from the Frame's for distorted cameras.  After
  * hvo_proj_set_frame, this call makes every window lookup of the handle (hvo_proj_search, hvo_proj_features_in_area) use
- * (min_x, min_y) as origin, the cells unchanged; the next hvo_proj_set_frame resets it. */
+ * (min_x, min_y) as origin, the cells unchanged; the next hvo_proj_set_frame resets it.
+ * (The candidate LISTS cannot differ: cells are assigned by round(), cell ranges by floor() / ceil(), so a shift of the origin by less
+ * than half a cell only adds or drops cells that hold no keypoint within r.  The call exists so that the lookup is literally the
+ * reference's; KeyFrame::IsInImage with the truncated bounds, which does change results, stays on the host.) */
 int hvo_proj_set_window_origin(hvo_proj* h, float min_x, float min_y);
 /* inspection: cell_start [64*48 + 1] (cell = ix * 48 + iy), cell_items [n] = mGrid[ix][iy] concatenated */
 int hvo_proj_get_grid(hvo_proj* h, int32_t* cell_start, int32_t* cell_items);
