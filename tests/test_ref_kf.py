@@ -467,3 +467,33 @@ def test_oracle_equals_reference(check, hvo, synth):
 @pytest.mark.parametrize('check', CHECKS, ids=lambda c: c.__name__[7:])
 def test_gpu_equals_reference(check, hvo, synth):
     check(hvo, synth, gpu=True)
+
+
+def test_integer_window_origin_cannot_change_a_candidate_list():
+    """The claim of include/hvo_capi.h (hvo_proj_set_window_origin): cells are assigned by round(), window cell ranges by floor() / ceil(), so
+    locating the window from the key frame's truncated origin (a shift below one pixel, a tenth of a cell) only adds or drops cells without a
+    keypoint within r: KeyFrame::GetFeaturesInArea and Frame::GetFeaturesInArea return the same list in the same order."""
+    rng = np.random.RandomState(9)
+    total = 0
+    for trial in range(40):
+        n = 1500
+        bounds = (float(rng.uniform(-30, 30)), float(rng.uniform(-30, 30)), float(640 + rng.uniform(-30, 30)), float(480 + rng.uniform(-30, 30)))
+        keys = np.zeros(n, oracle.KP_DTYPE)
+        keys['x'] = rng.uniform(bounds[0], bounds[2], n).astype(f32); keys['y'] = rng.uniform(bounds[1], bounds[3], n).astype(f32)
+        keys['octave'] = rng.randint(0, 8, n)
+        # every fifth keypoint exactly on a cell border of the float grid, where round() flips
+        cw = (bounds[2] - bounds[0]) / 64.0
+        keys['x'][::5] = (bounds[0] + (rng.randint(0, 64, len(keys[::5])) + 0.5) * cw).astype(f32)
+        for _ in range(60):
+            x, y = f32(rng.uniform(bounds[0] - 20, bounds[2] + 20)), f32(rng.uniform(bounds[1] - 20, bounds[3] + 20))
+            r = f32(rng.choice([1.5, 4.0, 7.5, 10.0, 25.0, 60.0]))
+            lv = (-1, -1) if rng.rand() < 0.5 else (int(rng.randint(0, 4)), int(rng.randint(3, 8)))
+            a = oracle.features_in_area(keys, bounds, x, y, r, *lv)
+            oracle.window_origin((int(bounds[0]), int(bounds[1])))
+            try:
+                b = oracle.features_in_area(keys, bounds, x, y, r, *lv)
+            finally:
+                oracle.window_origin(None)
+            assert np.array_equal(a, b)
+            total += len(a)
+    assert total > 5000
