@@ -260,8 +260,11 @@ def cpu_latency(gray, depth, nframes=60, warm=5):
 
 
 def shard(n, world, rank):
-    base, rem = divmod(n, world)
-    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+    """(first frame, frame count) of rank's contiguous range of the sequence: the package's partition (sharding.shard_range, the one
+    hvo_seq_* uses below the C ABI and tests/test_sharding_cpu.py checks under gloo)"""
+    from hvo_b200.sharding import shard_range
+    lo, hi = shard_range(n, rank, world)
+    return lo, hi - lo
 
 
 def main():
